@@ -1,0 +1,238 @@
+"""ctypes binding of the CPU oracle (oracle/liborb_oracle.so).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs, never by the
+product package."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+_lib = None
+u8p = C.POINTER(C.c_uint8)
+f32p = C.POINTER(C.c_float)
+i32p = C.POINTER(C.c_int)
+
+
+def build(force=False):
+    so = os.path.join(ORACLE_DIR, "liborb_oracle.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("orb_oracle.cpp", "orb_oracle_batch.cpp", "orb_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        vp = C.c_void_p
+        L.orc_resize_linear.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int]
+        L.orc_border_reflect101.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_gaussian7x7.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_fast9.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_descriptor_distance.argtypes = [vp, vp]
+        L.orc_extractor_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orc_extractor_create.restype = vp
+        L.orc_extractor_destroy.argtypes = [vp]
+        L.orc_extract.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int]
+        L.orc_levels.argtypes = [vp]
+        L.orc_scale_factors.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_features_per_level.argtypes = [vp, vp]
+        L.orc_umax.argtypes = [vp, vp]
+        for fn in (L.orc_pyramid_level, L.orc_pyramid_padded, L.orc_stage_blurred):
+            fn.argtypes = [vp, C.c_int, i32p, i32p, i32p]
+            fn.restype = vp
+        L.orc_stage_candidates.argtypes = [vp, C.c_int, vp, C.c_int]
+        L.orc_stage_level_keypoints.argtypes = [vp, C.c_int, vp, C.c_int]
+        L.orc_distribute_octree.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_stereo_match.argtypes = [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, C.c_float, C.c_float, vp, vp]
+        L.orc_frame_create.argtypes = [C.c_int, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, vp]
+        L.orc_frame_create.restype = vp
+        L.orc_frame_destroy.argtypes = [vp]
+        L.orc_features_in_area.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_search_for_initialization.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_int]
+        L.orc_search_by_projection_mappoints.argtypes = [vp, C.c_int] + [vp] * 9 + [C.c_int, C.c_float, vp]
+        L.orc_search_by_projection_lastframe.argtypes = [vp, C.c_int] + [vp] * 8 + [C.c_float, C.c_int, C.c_int, vp,
+                                                                                 C.c_float, C.c_int, vp]
+        L.orc_bench_stereo_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                             C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
+        L.orc_bench_stereo_batch.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def border_reflect101(img, b):
+    h, w = img.shape
+    buf = np.zeros((h + 2 * b, w + 2 * b), np.uint8)
+    buf[b:b + h, b:b + w] = img
+    lib().orc_border_reflect101(_p(buf), w, h, buf.strides[0], b)
+    return buf
+
+
+def gaussian7x7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().orc_gaussian7x7(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def fast9(img, threshold, nms=True):
+    img = np.ascontiguousarray(img, np.uint8)
+    cap = img.size
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().orc_fast9(_p(img), img.shape[1], img.shape[0], img.strides[0], threshold, int(nms), _p(out), cap)
+    return out[:n]
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def distribute_octree(cand, minX, maxX, minY, maxY, N):
+    cand = np.ascontiguousarray(cand, KP_DTYPE)
+    out = np.zeros(max(len(cand), 1), KP_DTYPE)
+    n = lib().orc_distribute_octree(_p(cand), len(cand), minX, maxX, minY, maxY, N, _p(out), len(out))
+    return out[:n]
+
+
+class Extractor:
+    def __init__(self, nfeatures=2000, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.h = lib().orc_extractor_create(nfeatures, scale, nlevels, ini_th, min_th)
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_extractor_destroy(self.h)
+            self.h = None
+
+    def extract(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = self.nfeatures + 64 * self.nlevels + 64
+        while True:
+            kps = np.zeros(cap, KP_DTYPE)
+            desc = np.zeros((cap, 32), np.uint8)
+            n = lib().orc_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0], _p(kps), _p(desc), cap)
+            if n >= 0:
+                return kps[:n].copy(), desc[:n].copy()
+            cap = -n + 16
+
+    def tables(self):
+        n = self.nlevels
+        s, i, s2, i2 = (np.zeros(n, np.float32) for _ in range(4))
+        lib().orc_scale_factors(self.h, _p(s), _p(i), _p(s2), _p(i2))
+        fpl = np.zeros(n, np.int32)
+        lib().orc_features_per_level(self.h, _p(fpl))
+        um = np.zeros(16, np.int32)
+        lib().orc_umax(self.h, _p(um))
+        return dict(scale=s, inv_scale=i, sigma2=s2, inv_sigma2=i2, features_per_level=fpl, umax=um)
+
+    def _plane(self, fn, level):
+        w, h, st = C.c_int(), C.c_int(), C.c_int()
+        ptr = fn(self.h, level, C.byref(w), C.byref(h), C.byref(st))
+        if not ptr or w.value == 0:
+            return np.zeros((0, 0), np.uint8)
+        buf = (C.c_uint8 * (st.value * (h.value - 1) + w.value)).from_address(ptr)
+        a = np.frombuffer(buf, np.uint8)
+        return np.lib.stride_tricks.as_strided(a, (h.value, w.value), (st.value, 1)).copy()
+
+    def pyramid_level(self, level):
+        return self._plane(lib().orc_pyramid_level, level)
+
+    def pyramid_padded(self, level):
+        return self._plane(lib().orc_pyramid_padded, level)
+
+    def blurred(self, level):
+        return self._plane(lib().orc_stage_blurred, level)
+
+    def candidates(self, level):
+        out = np.zeros(1 << 20, KP_DTYPE)
+        n = lib().orc_stage_candidates(self.h, level, _p(out), len(out))
+        return out[:n].copy()
+
+    def level_keypoints(self, level):
+        out = np.zeros(1 << 16, KP_DTYPE)
+        n = lib().orc_stage_level_keypoints(self.h, level, _p(out), len(out))
+        return out[:n].copy()
+
+
+def stereo_match(exL, exR, kl, dl, kr, dr, bf, baseline):
+    kl = np.ascontiguousarray(kl, KP_DTYPE); kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = np.ascontiguousarray(dl, np.uint8); dr = np.ascontiguousarray(dr, np.uint8)
+    ur = np.zeros(len(kl), np.float32); dp = np.zeros(len(kl), np.float32)
+    n = lib().orc_stereo_match(exL.h, exR.h, len(kl), _p(kl), _p(dl), len(kr), _p(kr), _p(dr), bf, baseline,
+                               _p(ur), _p(dp))
+    return n, ur, dp
+
+
+class Frame:
+    def __init__(self, kps, desc, scale_factors, bounds, u_right=None):
+        self.kps = np.ascontiguousarray(kps, KP_DTYPE)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.scale = np.ascontiguousarray(scale_factors, np.float32)
+        self.ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        self.bounds = bounds
+        self.h = lib().orc_frame_create(len(self.kps), _p(self.kps), _p(self.desc), _p(self.ur), bounds[0], bounds[1],
+                                        bounds[2], bounds[3], len(self.scale), _p(self.scale))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_frame_destroy(self.h)
+            self.h = None
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        out = np.zeros(len(self.kps) + 1, np.int32)
+        n = lib().orc_features_in_area(self.h, x, y, r, min_level, max_level, _p(out), len(out))
+        return out[:n].copy()
+
+
+def search_for_initialization(f1, f2, prev_matched, window=100, nnratio=0.9, check_ori=True):
+    pm = np.ascontiguousarray(prev_matched, np.float32).copy()
+    m12 = np.zeros(len(f1.kps), np.int32)
+    n = lib().orc_search_for_initialization(f1.h, f2.h, _p(pm), _p(m12), window, nnratio, int(check_ori))
+    return n, m12, pm
+
+
+def search_by_projection_mappoints(f, valid, px, py, pxr, level, viewcos, mp_desc, has_obs, occupied, th=1,
+                                   nnratio=0.8):
+    a = lambda v, t: np.ascontiguousarray(v, t)
+    assigned = np.zeros(len(f.kps), np.int32)
+    n = lib().orc_search_by_projection_mappoints(
+        f.h, len(valid), _p(a(valid, np.uint8)), _p(a(px, np.float32)), _p(a(py, np.float32)),
+        _p(a(pxr, np.float32)), _p(a(level, np.int32)), _p(a(viewcos, np.float32)), _p(a(mp_desc, np.uint8)),
+        _p(a(has_obs, np.uint8)), _p(a(occupied, np.uint8)), th, nnratio, _p(assigned))
+    return n, assigned
+
+
+def search_by_projection_lastframe(cur, valid, u, v, invzc, octave, angle, mp_desc, has_obs, bf, forward, backward,
+                                   occupied, th, check_ori=True):
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    assigned = np.zeros(len(cur.kps), np.int32)
+    n = lib().orc_search_by_projection_lastframe(
+        cur.h, len(valid), _p(a(valid, np.uint8)), _p(a(u, np.float32)), _p(a(v, np.float32)),
+        _p(a(invzc, np.float32)), _p(a(octave, np.int32)), _p(a(angle, np.float32)), _p(a(mp_desc, np.uint8)),
+        _p(a(has_obs, np.uint8)), bf, int(forward), int(backward), _p(a(occupied, np.uint8)), th, int(check_ori),
+        _p(assigned))
+    return n, assigned
