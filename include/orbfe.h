@@ -1,0 +1,186 @@
+/*
+ * orbfe.h -- C ABI of the B200-native ORB front-end (liborbfe.so).
+ *
+ * Drop-in boundary for the frame front-end hot path of ThorsteinnJonsson/SLAM_framework.
+ * Each entry point names the reference interface it replaces (file:line relative to the
+ * reference tree).  The C++ shim classes with the reference's own signatures
+ * (ORBextractor::Compute, Frame::ComputeStereoMatches, OrbMatcher::*) live in
+ * include/orbfe_shim.hpp and are thin wrappers over these functions; INTEGRATION.md shows the
+ * reference-side edit.
+ *
+ * Conventions: plain pointers and sizes, no C++/OpenCV/torch types; every function returns an
+ * orbfe_status (0 = ok, <0 = error) and never throws; orbfe_last_error() gives a thread-local
+ * message.  A handle is bound to (device, private stream); calls on ONE handle must be
+ * serialised by the caller (an ORBextractor instance is not re-entrant either,
+ * orb_extractor.h:25-93), calls on DIFFERENT handles may run concurrently from different
+ * threads (frame.cpp:86-89 runs the left and right extractor on two std::threads).
+ * There is no CPU fallback: without a CUDA device every compute call returns ORBFE_ERR_CUDA.
+ */
+#ifndef ORBFE_H_
+#define ORBFE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ORBFE_OK = 0,
+  ORBFE_ERR_INVALID = -1,   /* bad argument / unsupported geometry */
+  ORBFE_ERR_CUDA = -2,      /* CUDA runtime error (message in orbfe_last_error) */
+  ORBFE_ERR_CAPACITY = -3,  /* caller buffer too small; *n_out holds the needed count */
+  ORBFE_ERR_NOMEM = -4
+} orbfe_status;
+
+/* cv::KeyPoint memory layout (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id */
+typedef struct {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} orbfe_keypoint;
+
+/* ORBextractor ctor arguments (orb_extractor.cpp:351-355) + capacity of the device arena. */
+typedef struct {
+  int32_t nfeatures;
+  float scale_factor;
+  int32_t nlevels;
+  int32_t ini_th_fast;
+  int32_t min_th_fast;
+  int32_t max_width;   /* largest image this handle will see */
+  int32_t max_height;
+  int32_t max_images;  /* image slots resident on the device (1 for the drop-in shim) */
+} orbfe_params;
+
+typedef struct orbfe_extractor orbfe_extractor;
+typedef struct orbfe_frame orbfe_frame;
+
+const char* orbfe_last_error(void);
+const char* orbfe_version(void);
+/* number of CUDA devices visible (0 => every compute call will fail with ORBFE_ERR_CUDA) */
+int orbfe_device_count(void);
+
+/* ---- ORBextractor (src/orb_features/orb_extractor.h:25-93) ------------------------------ */
+/* replaces ORBextractor::ORBextractor (orb_extractor.cpp:351-411) */
+int orbfe_extractor_create(const orbfe_params* p, int device, orbfe_extractor** out);
+int orbfe_extractor_destroy(orbfe_extractor* ex);
+/* replaces GetLevels/GetScaleFactors/GetInverseScaleFactors/GetScaleSigmaSquares/
+ * GetInverseScaleSigmaSquares (orb_extractor.h:46-56); any output pointer may be NULL */
+int orbfe_extractor_tables(const orbfe_extractor* ex, int* nlevels, float* scale, float* inv_scale,
+                           float* sigma2, float* inv_sigma2, int32_t* features_per_level);
+/* upper bound of keypoints one image can produce (sum over levels of max(N_l+3, 4*nIni)) */
+int orbfe_extractor_max_keypoints(const orbfe_extractor* ex);
+
+/* replaces ORBextractor::Compute(image, mask, keypoints, descriptors)
+ * (orb_extractor.cpp:985-1049; mask is ignored there too, orb_extractor.h:40).
+ * img: CV_8UC1, `stride` bytes per row, host memory.  kps/desc: caller-allocated, `capacity`
+ * entries (desc is capacity x 32 bytes).  Synchronous.  Empty image (w<=0||h<=0||!img) => ok,
+ * *n_out = 0 (orb_extractor.cpp:990-991). */
+int orbfe_extract(orbfe_extractor* ex, const uint8_t* img, int w, int h, size_t stride,
+                  orbfe_keypoint* kps, uint8_t* desc, int capacity, int* n_out);
+
+/* Batched form of the same call over n_imgs same-sized images (image i -> slot i);
+ * kps/desc hold n_imgs*capacity entries, n_out has n_imgs entries.  This is the offline
+ * loop of examples/main_stereo.cpp:102-143 with the frames of one batch in flight at once. */
+int orbfe_extract_batch(orbfe_extractor* ex, const uint8_t* const* imgs, int n_imgs, int w, int h,
+                        size_t stride, orbfe_keypoint* kps, uint8_t* desc, int capacity, int* n_out);
+
+/* replaces GetImagePyramid()[level] (orb_extractor.h:58): copies the ROI view (un-padded
+ * level) of image slot `slot` to host memory.  dst may be NULL to query the size only. */
+int orbfe_pyramid_level(orbfe_extractor* ex, int slot, int level, uint8_t* dst, size_t dst_stride,
+                        int* w, int* h);
+
+/* ---- device-resident batch path (bench / streaming; same kernels) ----------------------- */
+/* async H2D of n_imgs images into slots [first_slot, first_slot+n_imgs) (pinned host memory
+ * recommended). */
+int orbfe_upload(orbfe_extractor* ex, int first_slot, const uint8_t* const* imgs, int n_imgs, int w,
+                 int h, size_t stride);
+/* enqueue the full extractor on slots [0, n_imgs); results stay on the device */
+int orbfe_run(orbfe_extractor* ex, int n_imgs);
+/* enqueue Frame::ComputeStereoMatches for pairs p = (slot 2p, slot 2p+1), p < n_pairs */
+int orbfe_run_stereo(orbfe_extractor* ex, int n_pairs, float bf, float baseline);
+/* async D2H of the results of slots [0, n_imgs); kps/desc/n_out as in orbfe_extract_batch;
+ * u_right/depth (n_imgs*capacity floats, may be NULL) are filled for even (left) slots. */
+int orbfe_download(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t* desc, int capacity,
+                   int* n_out, float* u_right, float* depth);
+int orbfe_sync(orbfe_extractor* ex);
+/* CUDA-event timing on the handle's own stream: record event `slot` (0..63) now; elapsed ms
+ * between two recorded slots (after orbfe_sync). */
+int orbfe_event_record(orbfe_extractor* ex, int slot);
+int orbfe_event_elapsed_ms(orbfe_extractor* ex, int slot_a, int slot_b, float* ms);
+/* when enabled, orbfe_run/orbfe_run_stereo record one event per stage (slots 32..47):
+ * 32 start, 33 pyramid, 34 fast, 35 octree, 36 blur, 37 describe, 38 stereo search, 39 median */
+int orbfe_set_stage_timing(orbfe_extractor* ex, int enabled);
+/* number of kernel launches issued by this handle since creation */
+long long orbfe_launch_count(const orbfe_extractor* ex);
+/* stage outputs of slot `slot` for per-stage parity tests: FAST candidates of a level
+ * (x, y relative to the (16,16) detection origin, response) and the level's distributed
+ * keypoints before orientation; returns count via *n_out */
+int orbfe_debug_candidates(orbfe_extractor* ex, int slot, int level, orbfe_keypoint* out, int capacity, int* n_out);
+int orbfe_debug_level_keypoints(orbfe_extractor* ex, int slot, int level, orbfe_keypoint* out, int capacity, int* n_out);
+int orbfe_debug_blurred(orbfe_extractor* ex, int slot, int level, uint8_t* dst, size_t dst_stride, int* w, int* h);
+
+/* ---- Frame::ComputeStereoMatches (src/data/frame.cpp:406-577; frame.h:95) ---------------- */
+/* left/right: the two extractor handles whose last orbfe_extract produced the keypoints (their
+ * device-resident pyramids are read, as the reference reads GetImagePyramid() at
+ * frame.cpp:412,501,514,520).  kps/desc are the host arrays the Frame holds (keypoints_,
+ * right_keypoints_, descriptors_, right_descriptors_).  baseline replaces the uninitialised
+ * baseline_ read at frame.cpp:436 (pass bf/fx).  u_right/depth: n_left floats (stereo_coords_,
+ * depths_; -1 = no match).  Both handles must be on the same device with identical params
+ * and image size. */
+int orbfe_stereo_match(orbfe_extractor* left, orbfe_extractor* right, int n_left,
+                       const orbfe_keypoint* kps_left, const uint8_t* desc_left, int n_right,
+                       const orbfe_keypoint* kps_right, const uint8_t* desc_right, float bf,
+                       float baseline, float* u_right, float* depth, int* n_matched);
+
+/* ---- OrbMatcher (src/orb_features/orb_matcher.h:14-119) ---------------------------------- */
+/* static OrbMatcher::DescriptorDistance (orb_matcher.cpp:1630-1646), batched: d[i] =
+ * hamming(a[i], b[i]) over n pairs of 32-byte rows (host memory). */
+int orbfe_descriptor_distance(int device, const uint8_t* a, const uint8_t* b, int n, int32_t* d);
+
+/* A Frame as the matchers see it: undistorted keypoints, descriptors, stereo right
+ * coordinates (NULL = monocular), image bounds and scale table; builds the 64x48 feature
+ * grid of Frame::AssignFeaturesToGrid / PosInGrid (frame.cpp:234-248, 339-346) on the GPU. */
+int orbfe_frame_create(int device, int n, const orbfe_keypoint* kps_un, const uint8_t* desc,
+                       const float* u_right, float min_x, float max_x, float min_y, float max_y,
+                       int nlevels, const float* scale_factors, orbfe_frame** out);
+int orbfe_frame_destroy(orbfe_frame* f);
+/* Frame::GetFeaturesInArea (frame.cpp:348-403): indices in the reference's order */
+int orbfe_features_in_area(orbfe_frame* f, float x, float y, float r, int min_level, int max_level,
+                           int32_t* out, int capacity, int* n_out);
+
+/* OrbMatcher::SearchForInitialization (orb_matcher.cpp:264-382).  prev_matched: n1 (x,y)
+ * pairs, in/out (vbPrevMatched); matches12: n1 ints (vnMatches12). */
+int orbfe_search_for_initialization(orbfe_frame* f1, orbfe_frame* f2, float* prev_matched_xy,
+                                    int32_t* matches12, int window_size, float nnratio,
+                                    int check_orientation, int* n_matches);
+
+/* OrbMatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (orb_matcher.cpp:13-111).
+ * Per map point i: valid = track_is_in_view && !isBad(); proj_x/proj_y/proj_xr/pred_level/
+ * view_cos = the track_* fields written by Frame::IsInFrustum (frame.cpp:328-334);
+ * mp_desc = GetDescriptor() (32 bytes); has_obs = NumObservations()>0.
+ * occupied[k] = keypoint k already holds a map point with observations (orb_matcher.cpp:59-63).
+ * assigned[k] (out) = index of the map point F.SetMapPoint(k, .) received, else -1. */
+int orbfe_search_by_projection_mappoints(orbfe_frame* f, int n_mp, const uint8_t* valid,
+                                         const float* proj_x, const float* proj_y,
+                                         const float* proj_xr, const int32_t* pred_level,
+                                         const float* view_cos, const uint8_t* mp_desc,
+                                         const uint8_t* has_obs, const uint8_t* occupied, int th,
+                                         float nnratio, int32_t* assigned, int* n_matches);
+
+/* OrbMatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, bMono)
+ * (orb_matcher.cpp:1312-1453).  Per last-frame keypoint i: valid = has map point && !outlier;
+ * (u, v, invzc) = the projection of :1346-1356 (cv::Mat arithmetic, done by the shim);
+ * forward/backward = the booleans of :1334-1335. */
+int orbfe_search_by_projection_lastframe(orbfe_frame* cur, int n_last, const uint8_t* valid,
+                                         const float* u, const float* v, const float* invzc,
+                                         const int32_t* last_octave, const float* last_angle,
+                                         const uint8_t* mp_desc, const uint8_t* has_obs, float bf,
+                                         int forward, int backward, const uint8_t* occupied,
+                                         float th, int check_orientation, int32_t* assigned,
+                                         int* n_matches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBFE_H_ */

@@ -117,19 +117,25 @@ void border_reflect101(uint8_t* buf, int w, int h, int stride, int b) {
 void gaussian7x7(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride) {
   static const int k[7] = {18, 34, 48, 56, 48, 34, 18};
   std::vector<uint16_t> H((size_t)w * h);
-  for (int y = 0; y < h; ++y) {
+  std::vector<uint8_t> prow((size_t)w + 6);
+  for (int y = 0; y < h; ++y) {  // horizontal pass on a REFLECT_101-extended row
     const uint8_t* S = src + (size_t)y * sstride;
-    for (int x = 0; x < w; ++x) {
-      int acc = 0;
-      for (int i = 0; i < 7; ++i) acc += k[i] * S[reflect101(x + i - 3, w)];
-      H[(size_t)y * w + x] = (uint16_t)acc;  // <= 65280
-    }
+    for (int i = 0; i < 3; ++i) { prow[i] = S[reflect101(i - 3, w)]; prow[w + 3 + i] = S[reflect101(w + i, w)]; }
+    std::memcpy(prow.data() + 3, S, (size_t)w);
+    uint16_t* Hr = &H[(size_t)y * w];
+    const uint8_t* P = prow.data();
+    for (int x = 0; x < w; ++x)
+      Hr[x] = (uint16_t)(k[0] * P[x] + k[1] * P[x + 1] + k[2] * P[x + 2] + k[3] * P[x + 3] + k[4] * P[x + 4] +
+                         k[5] * P[x + 5] + k[6] * P[x + 6]);  // <= 65280
   }
-  for (int y = 0; y < h; ++y) {
+  for (int y = 0; y < h; ++y) {  // vertical pass, single rounding
+    const uint16_t* r[7];
+    for (int j = 0; j < 7; ++j) r[j] = &H[(size_t)reflect101(y + j - 3, h) * w];
     uint8_t* D = dst + (size_t)y * dstride;
     for (int x = 0; x < w; ++x) {
-      uint32_t acc = 0;
-      for (int j = 0; j < 7; ++j) acc += (uint32_t)k[j] * H[(size_t)reflect101(y + j - 3, h) * w + x];
+      const uint32_t acc = (uint32_t)k[0] * r[0][x] + (uint32_t)k[1] * r[1][x] + (uint32_t)k[2] * r[2][x] +
+                           (uint32_t)k[3] * r[3][x] + (uint32_t)k[4] * r[4][x] + (uint32_t)k[5] * r[5][x] +
+                           (uint32_t)k[6] * r[6][x];
       D[x] = (uint8_t)((acc + 32768u) >> 16);
     }
   }
@@ -257,14 +263,21 @@ float ic_angle(const uint8_t* img, int stride, float px, float py, const std::ve
 
 // ---- computeOrbDescriptor (orb_extractor.cpp:48-88) ---------------------------------------
 const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);  // :48
-void orb_descriptor(const KP& kpt, const uint8_t* img, int step, uint8_t* desc) {
+// `img` is the blurred CLONE of the level: a continuous w x h buffer (step == w), so a sample
+// whose column falls outside [0,w) reads the neighbouring row exactly as the reference's
+// center[iy*step + ix] does.  The pattern reaches 18 px but keypoints may sit 16 px from the edge;
+// a sample before/after the whole buffer is an out-of-allocation read in the reference (UB):
+// the oracle defines it as 0 (header item 6).
+void orb_descriptor(const KP& kpt, const uint8_t* img, int step, int rows, uint8_t* desc) {
   const float angle = (float)kpt.angle * factorPI;
   const float a = cosf(angle), b = sinf(angle);  // cos/sin on a float => cosf/sinf (:54)
-  const uint8_t* center = img + (ptrdiff_t)cvRoundF(kpt.y) * step + cvRoundF(kpt.x);
+  const ptrdiff_t center = (ptrdiff_t)cvRoundF(kpt.y) * step + cvRoundF(kpt.x);
+  const ptrdiff_t total = (ptrdiff_t)step * rows;
   const signed char* pat = kPattern;
   auto get = [&](int idx) -> int {
     const float x = (float)pat[2 * idx], y = (float)pat[2 * idx + 1];
-    return center[cvRoundF(x * b + y * a) * step + cvRoundF(x * a - y * b)];
+    const ptrdiff_t lin = center + (ptrdiff_t)cvRoundF(x * b + y * a) * step + cvRoundF(x * a - y * b);
+    return (lin < 0 || lin >= total) ? 0 : img[lin];
   };
   for (int i = 0; i < 32; ++i, pat += 32) {
     int val = 0;
@@ -609,7 +622,7 @@ int orc_extract(orc_extractor* e, const uint8_t* img, int w, int h, int stride, 
     work.alloc(e->lw[level], e->lh[level]);
     gaussian7x7(e->roi(level), e->lw[level], e->lh[level], e->padded[level].stride, work.data.data(), work.stride);
     for (size_t i = 0; i < keypoints.size(); ++i) {
-      if (fits) orb_descriptor(keypoints[i], work.data.data(), work.stride, desc + (size_t)(offset + i) * 32);
+      if (fits) orb_descriptor(keypoints[i], work.data.data(), work.stride, work.h, desc + (size_t)(offset + i) * 32);
     }
     if (level != 0) {
       const float scale = e->scale[level];

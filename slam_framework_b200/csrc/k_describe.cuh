@@ -1,0 +1,173 @@
+// k_describe.cuh -- E5 + E7 + E8: orientation, rotated-BRIEF descriptor and keypoint packing.
+// One warp per keypoint slot of an image (slots are level-major, the order of
+// ORBextractor::Compute's output, orb_extractor.cpp:1016-1048).
+//   E5  IC_Angle (orb_extractor.cpp:18-45): lanes own the 31 columns of the radius-15 disc and
+//       walk its 31 rows on the UNBLURRED level; m10/m01 are exact int32 sums reduced by
+//       warp shuffles; angle = cv::fastAtan2 restated op for op in non-contracted fp32
+//       (SURVEY Appendix A.4).
+//   E7  computeOrbDescriptor (orb_extractor.cpp:48-88): a = cosf, b = sinf of angle*pi/180 with
+//       glibc's sincosf algorithm (double polynomial, verified bit-identical to glibc 2.39 over
+//       1.6e8 arguments); lane i produces descriptor byte i from 16 rotated samples
+//       of the BLURRED level, sample coordinates cvRound(x*b+y*a), cvRound(x*a-y*b) with
+//       separate fmul/fadd (no FMA) and round-half-even.
+//   E8  pt += (16,16) is already folded in, pt *= scale[level] for level != 0 (:1039-1045),
+//       size = (float)(int)(31*scale), octave = level, class_id = -1.
+#pragma once
+#include "orbfe_common.cuh"
+
+#define ORBFE_DESC_THREADS 256
+
+__constant__ signed char c_orb_pattern[1024] = {
+#include "orb_pattern_31.inc"
+};
+// circular patch half-widths (orb_extractor.cpp:393-410)
+__constant__ signed char c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+struct orbfe_kp_dev {
+  float x, y, size, angle, response;
+  int octave, class_id;
+};
+
+__device__ __forceinline__ float orbfe_fast_atan2(float y, float x) {
+  const float sc = (float)(180 / 3.141592653589793238462643383279502884);
+  const float p1 = 0.9997878412794807f * sc, p3 = -0.3258083974640975f * sc;
+  const float p5 = 0.1555786518463281f * sc, p7 = -0.04432655554792128f * sc;
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float eps = (float)2.2204460492503131e-16;
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+// glibc >= 2.28 sinf/cosf (ARM optimized-routines sincosf), argument range |y| < 120 only
+// (angles here are in [0, 2*pi]).  All double ops are explicit round-to-nearest, no FMA.
+__device__ __forceinline__ float orbfe_sincos_poly(double x, double x2, bool neg_tab, int n) {
+  const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+  double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+         C4 = 0x1.99343027bf8c3p-16;
+  if (neg_tab) { C0 = -C0; C1 = -C1; C2 = -C2; C3 = -C3; C4 = -C4; }
+  if ((n & 1) == 0) {
+    const double x3 = __dmul_rn(x, x2);
+    const double s1 = __dadd_rn(S2, __dmul_rn(x2, S3));
+    const double x7 = __dmul_rn(x3, x2);
+    const double s = __dadd_rn(x, __dmul_rn(x3, S1));
+    return __double2float_rn(__dadd_rn(s, __dmul_rn(x7, s1)));
+  } else {
+    const double x4 = __dmul_rn(x2, x2);
+    const double c2 = __dadd_rn(C3, __dmul_rn(x2, C4));
+    const double c1 = __dadd_rn(C1, __dmul_rn(x2, C2));
+    const double x6 = __dmul_rn(x4, x2);
+    const double c = __dadd_rn(C0, __dmul_rn(x2, c1));
+    return __double2float_rn(__dadd_rn(c, __dmul_rn(x6, c2)));
+  }
+}
+__device__ __forceinline__ unsigned orbfe_abstop12(float x) { return (__float_as_uint(x) >> 20) & 0x7ffu; }
+// is_cos = 0: sinf(y), 1: cosf(y)
+__device__ __forceinline__ float orbfe_sincosf(float y, int is_cos) {
+  double x = (double)y;
+  if (orbfe_abstop12(y) < orbfe_abstop12(0x1.921FB6p-1f)) {
+    const double s = __dmul_rn(x, x);
+    if (orbfe_abstop12(y) < orbfe_abstop12(0x1p-12f)) return is_cos ? 1.0f : y;
+    return orbfe_sincos_poly(x, s, false, is_cos);
+  }
+  const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
+  const int n = ((int)r + 0x800000) >> 24;
+  x = __dsub_rn(x, __dmul_rn((double)n, 0x1.921FB54442D18p0));
+  const double sgn = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
+  return orbfe_sincos_poly(__dmul_rn(x, sgn), __dmul_rn(x, x), (n & 2) != 0, n ^ is_cos);
+}
+
+__global__ void __launch_bounds__(ORBFE_DESC_THREADS)
+k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
+                  const unsigned* __restrict__ lvlKp, const int* __restrict__ lvlCnt, orbfe_kp_dev* __restrict__ kps,
+                  uint8_t* __restrict__ desc, int* __restrict__ nKp) {
+  const int slot = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int wglobal = blockIdx.x * (ORBFE_DESC_THREADS / 32) + (threadIdx.x >> 5);
+  const int* cnt = lvlCnt + (size_t)slot * g.nlevels;
+  int level = -1, idx = wglobal, total = 0;
+  for (int l = 0; l < g.nlevels; ++l) {
+    const int c = cnt[l];
+    if (level < 0 && idx < c) level = l;
+    if (level < 0) idx -= c;
+    total += c;
+  }
+  if (wglobal == 0 && lane == 0) nKp[slot] = total;
+  if (level < 0) return;  // whole warp exits together
+  const LevelGeom& L = g.lv[level];
+  const unsigned pk = lvlKp[(size_t)slot * g.totalOut + L.outOff + idx];
+  const int kx = ORBFE_PX(pk) + ORBFE_MINB, ky = ORBFE_PY(pk) + ORBFE_MINB;  // level coordinates
+  // ---- E5: intensity centroid on the unblurred level
+  const uint8_t* center = pyr + (size_t)slot * g.pyrStride + L.planeOff + (size_t)(ky + ORBFE_EDGE) * L.pitch + kx + ORBFE_EDGE;
+  int m10 = 0, m01 = 0;
+  if (lane < 31) {
+    const int u = lane - ORBFE_HALF_PATCH;
+    const int au = u < 0 ? -u : u;
+    for (int v = -ORBFE_HALF_PATCH; v <= ORBFE_HALF_PATCH; ++v) {
+      const int av = v < 0 ? -v : v;
+      if (au <= c_umax[av]) {
+        const int val = __ldg(center + v * L.pitch + u);
+        m10 += u * val;
+        m01 += v * val;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+  }
+  const float angle = orbfe_fast_atan2((float)m01, (float)m10);
+  // ---- E7: rotated BRIEF on the blurred level
+  const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);  // :48
+  const float ang = __fmul_rn(angle, factorPI);
+  const float a = orbfe_sincosf(ang, 1), b = orbfe_sincosf(ang, 0);
+  const uint8_t* bplane = blur + (size_t)slot * g.blurStride + L.blurOff;
+  const signed char* pat = c_orb_pattern + 32 * lane;
+  unsigned val = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int t[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float px = (float)pat[4 * k + 2 * h], py = (float)pat[4 * k + 2 * h + 1];
+      const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+      const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+      // the reference samples a CONTINUOUS w x h clone (step == w): a column overshoot lands in
+      // the adjacent row; a sample outside the buffer is UB there and defined as 0
+      int col = kx + ix, row = ky + iy;
+      if (col < 0) { col += L.w; --row; } else if (col >= L.w) { col -= L.w; ++row; }
+      t[h] = (row < 0 || row >= L.h) ? 0 : (int)__ldg(bplane + (size_t)row * L.bpitch + col);
+    }
+    val |= (unsigned)(t[0] < t[1]) << k;
+  }
+  const size_t o = (size_t)slot * g.totalOut + L.outOff;  // level-major slots: outOff is NOT the
+  (void)o;                                                 // packed position; compute it below
+  // packed position inside the image = sum of counts of lower levels + idx
+  int pos = idx;
+  for (int l = 0; l < level; ++l) pos += cnt[l];
+  uint8_t* d = desc + ((size_t)slot * g.totalOut + pos) * 32;
+  d[lane] = (uint8_t)val;
+  if (lane == 0) {
+    orbfe_kp_dev kp;
+    const float fx = (float)kx, fy = (float)ky;
+    kp.x = level != 0 ? __fmul_rn(fx, L.scale) : fx;
+    kp.y = level != 0 ? __fmul_rn(fy, L.scale) : fy;
+    kp.size = L.kpSize;
+    kp.angle = angle;
+    kp.response = (float)ORBFE_PS(pk);
+    kp.octave = level;
+    kp.class_id = -1;
+    kps[(size_t)slot * g.totalOut + pos] = kp;
+  }
+}

@@ -1,0 +1,221 @@
+// k_stereo.cuh -- S1-S4: Frame::ComputeStereoMatches (src/data/frame.cpp:406-577).
+//   k_stereo_search (warp per left keypoint):
+//     S1/S2  the reference's row table (:415-433) is a membership test: right keypoint iR is a
+//            candidate of left row (int)vL iff floor(yR - r) <= row <= ceil(yR + r),
+//            r = 2*scale[octR].  Lanes stride over the right keypoints in ascending iR, apply
+//            the octave (+-1) and uR in [uL-maxD, uL] filters, compute the 256-bit Hamming
+//            distance with __popc, and a warp-shuffle argmin on (dist, iR) reproduces the strict
+//            '<' scan from bestDist = TH_HIGH (ties -> lowest iR) (:444-488).
+//     S3     if bestDist < 75: 11 SADs of 11x11 centre-subtracted patches on the UNBLURRED
+//            pyramid level of the left keypoint's octave, lanes own 4 of the 121 pixels, sums
+//            reduced by shuffles; parabola fit in non-contracted fp32 (:491-562).
+//   k_stereo_median (CTA per pair):
+//     S4     median of the accepted SADs = element size/2 of the sorted (SAD, iL) list, found by
+//            a two-pass radix select; matches with SAD >= 1.5f*1.4f*median are undone (:565-576).
+#pragma once
+#include "orbfe_common.cuh"
+#include "k_describe.cuh"
+
+#define ORBFE_ST_THREADS 256
+
+struct StereoPair {
+  const uint8_t* pyrL;          // slot base of the left / right pyramid block
+  const uint8_t* pyrR;
+  const orbfe_kp_dev* kpL;
+  const orbfe_kp_dev* kpR;
+  const uint8_t* descL;
+  const uint8_t* descR;
+  const int* nL;
+  const int* nR;
+  float* uR;                    // outputs, indexed by left keypoint
+  float* depth;
+  int* sad;
+};
+
+__device__ __forceinline__ int orbfe_hamming256(const uint4 a0, const uint4 a1, const uint8_t* __restrict__ b) {
+  const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(b));
+  const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(b) + 1);
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(ORBFE_ST_THREADS)
+k_stereo_search(const __grid_constant__ Geom g, const StereoPair* __restrict__ pairs, const float bf, const float baseline,
+                const int maxKp) {
+  const StereoPair P = pairs[blockIdx.y];
+  const int lane = threadIdx.x & 31;
+  const int iL = blockIdx.x * (ORBFE_ST_THREADS / 32) + (threadIdx.x >> 5);
+  const int nL = min(*P.nL, maxKp), nR = min(*P.nR, maxKp);
+  if (iL >= nL) return;
+  const orbfe_kp_dev kpL = P.kpL[iL];
+  float uRout = -1.0f, depthOut = -1.0f;
+  int sadOut = -1;
+  const int levelL = kpL.octave;
+  const float vL = kpL.y, uL = kpL.x;
+  const int nRows = g.lv[0].h;
+  const int row = (int)vL;
+  const float minD = 0.f;
+  const float maxD = __fdiv_rn(bf, baseline);
+  const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
+  int bestDist = 100;  // OrbMatcher::TH_HIGH
+  int bestIdxR = 0x7fffffff;
+  if (row >= 0 && row < nRows && !(maxU < 0)) {
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(P.descL + (size_t)iL * 32));
+    const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(P.descL + (size_t)iL * 32) + 1);
+    for (int iR = lane; iR < nR; iR += 32) {
+      const orbfe_kp_dev kr = P.kpR[iR];
+      const float r = __fmul_rn(2.0f, g.lv[kr.octave].scale);
+      const int maxr = (int)ceilf(__fadd_rn(kr.y, r));
+      const int minr = (int)floorf(__fsub_rn(kr.y, r));
+      if (row < minr || row > maxr) continue;
+      if (kr.octave < levelL - 1 || kr.octave > levelL + 1) continue;
+      if (kr.x >= minU && kr.x <= maxU) {
+        const int dist = orbfe_hamming256(a0, a1, P.descR + (size_t)iR * 32);
+        if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int od = __shfl_xor_sync(0xffffffffu, bestDist, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bestIdxR, o);
+    if (od < bestDist || (od == bestDist && oi < bestIdxR)) { bestDist = od; bestIdxR = oi; }
+  }
+  const int thOrbDist = (100 + 50) / 2;
+  if (bestDist < thOrbDist) {  // warp-uniform
+    const float uR0 = P.kpR[bestIdxR].x;
+    const LevelGeom& L = g.lv[levelL];
+    const float scaleFactor = __fdiv_rn(1.0f, L.scale);  // mvInvScaleFactor (orb_extractor.cpp:371)
+    const float scaleduL = roundf(__fmul_rn(kpL.x, scaleFactor));
+    const float scaledvL = roundf(__fmul_rn(kpL.y, scaleFactor));
+    const float scaleduR0 = roundf(__fmul_rn(uR0, scaleFactor));
+    const int w = 5;
+    const float iniu = scaleduR0;             // scaleduR0 + L - w with L == w == 5 (:509)
+    const float endu = scaleduR0 + 11.0f;     // scaleduR0 + L + w + 1
+    const int yl0 = (int)scaledvL - w, xl0 = (int)scaleduL - w, xr0 = (int)scaleduR0 - w;
+    // guards: the reference indexes the level unchecked; outside the padded plane we drop the match
+    const bool inside = yl0 >= -ORBFE_EDGE && yl0 + 11 <= L.h + ORBFE_EDGE && xl0 >= -ORBFE_EDGE &&
+                        xl0 + 11 <= L.w + ORBFE_EDGE && xr0 - 5 >= -ORBFE_EDGE;
+    if (!(iniu < 0 || endu >= (float)L.w) && inside) {
+      const uint8_t* pl = P.pyrL + L.planeOff + (size_t)ORBFE_EDGE * L.pitch + ORBFE_EDGE;
+      const uint8_t* pr = P.pyrR + L.planeOff + (size_t)ORBFE_EDGE * L.pitch + ORBFE_EDGE;
+      const int cL = __ldg(pl + (yl0 + w) * L.pitch + xl0 + w);
+      int sums[11];
+#pragma unroll
+      for (int s = 0; s < 11; ++s) sums[s] = 0;
+      int cR[11];
+#pragma unroll
+      for (int s = 0; s < 11; ++s) cR[s] = __ldg(pr + (yl0 + w) * L.pitch + xr0 + (s - 5) + w);
+      for (int p = lane; p < 121; p += 32) {
+        const int py = p / 11, px = p - py * 11;
+        const int il = (int)__ldg(pl + (yl0 + py) * L.pitch + xl0 + px) - cL;
+        const uint8_t* rrow = pr + (yl0 + py) * L.pitch + xr0 + px - 5;
+#pragma unroll
+        for (int s = 0; s < 11; ++s) {
+          const int ir = (int)__ldg(rrow + s) - cR[s];
+          const int df = il - ir;
+          sums[s] += df < 0 ? -df : df;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < 11; ++s) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sums[s] += __shfl_xor_sync(0xffffffffu, sums[s], o);
+      }
+      int bestS = 0x7fffffff, bestinc = 0;
+#pragma unroll
+      for (int s = 0; s < 11; ++s)
+        if (sums[s] < bestS) { bestS = sums[s]; bestinc = s - 5; }
+      if (bestinc != -5 && bestinc != 5) {
+        float d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+        for (int s = 1; s < 10; ++s)
+          if (s - 5 == bestinc) { d1 = (float)sums[s - 1]; d2 = (float)sums[s]; d3 = (float)sums[s + 1]; }
+        const float num = __fsub_rn(d1, d3);
+        const float den = __fmul_rn(2.0f, __fsub_rn(__fadd_rn(d1, d3), __fmul_rn(2.0f, d2)));
+        const float deltaR = __fdiv_rn(num, den);
+        if (!(deltaR < -1.f || deltaR > 1.f)) {
+          float bestuR = __fmul_rn(L.scale, __fadd_rn(__fadd_rn(scaleduR0, (float)bestinc), deltaR));
+          float disparity = __fsub_rn(uL, bestuR);
+          if (disparity >= minD && disparity < maxD) {
+            if (disparity <= 0.f) { disparity = 0.01f; bestuR = __fsub_rn(uL, 0.01f); }
+            depthOut = __fdiv_rn(bf, disparity);
+            uRout = bestuR;
+            sadOut = bestS;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) { P.uR[iL] = uRout; P.depth[iL] = depthOut; P.sad[iL] = sadOut; }
+}
+
+__global__ void __launch_bounds__(ORBFE_ST_THREADS)
+k_stereo_median(const StereoPair* __restrict__ pairs, const int maxKp, int* __restrict__ nMatched) {
+  __shared__ int s_hist[256];
+  __shared__ int s_sel[4];
+  const StereoPair P = pairs[blockIdx.x];
+  const int nL = min(*P.nL, maxKp);
+  const int tid = threadIdx.x;
+  // count accepted matches
+  int c = 0;
+  for (int i = tid; i < nL; i += ORBFE_ST_THREADS) c += P.sad[i] >= 0;
+  const int total = __syncthreads_count(0) * 0 + 0;  // placeholder to keep barrier structure uniform
+  (void)total;
+  // block sum of c via histogram slot 0
+  if (tid < 256) s_hist[tid] = 0;
+  __syncthreads();
+  if (c) atomicAdd(&s_hist[0], c);
+  __syncthreads();
+  const int size = s_hist[0];
+  __syncthreads();
+  if (size == 0) {  // empty list: the reference's vDistIdx[0] read is UB; the cut is skipped
+    if (tid == 0) nMatched[blockIdx.x] = 0;
+    return;
+  }
+  const int rank = size / 2;  // element size/2 of the ascending sort
+  // pass 1: high byte of the 16-bit SAD (SAD <= 121*510 = 61710 < 65536)
+  if (tid < 256) s_hist[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < nL; i += ORBFE_ST_THREADS) {
+    const int s = P.sad[i];
+    if (s >= 0) atomicAdd(&s_hist[(s >> 8) & 0xff], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0, b = 0;
+    for (; b < 256; ++b) { if (acc + s_hist[b] > rank) break; acc += s_hist[b]; }
+    s_sel[0] = b; s_sel[1] = rank - acc;
+  }
+  __syncthreads();
+  const int hiBin = s_sel[0], rank2 = s_sel[1];
+  __syncthreads();
+  if (tid < 256) s_hist[tid] = 0;
+  __syncthreads();
+  for (int i = tid; i < nL; i += ORBFE_ST_THREADS) {
+    const int s = P.sad[i];
+    if (s >= 0 && ((s >> 8) & 0xff) == hiBin) atomicAdd(&s_hist[s & 0xff], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0, b = 0;
+    for (; b < 256; ++b) { if (acc + s_hist[b] > rank2) break; acc += s_hist[b]; }
+    s_sel[2] = (hiBin << 8) | b;
+  }
+  __syncthreads();
+  const float median = (float)s_sel[2];
+  const float thDist = __fmul_rn(1.5f * 1.4f, median);
+  int kept = 0;
+  for (int i = tid; i < nL; i += ORBFE_ST_THREADS) {
+    const int s = P.sad[i];
+    if (s < 0) continue;
+    if (!((float)s < thDist)) { P.uR[i] = -1.0f; P.depth[i] = -1.0f; }
+    else ++kept;
+  }
+  __syncthreads();
+  if (tid < 256) s_hist[tid] = 0;
+  __syncthreads();
+  if (kept) atomicAdd(&s_hist[0], kept);
+  __syncthreads();
+  if (tid == 0) nMatched[blockIdx.x] = s_hist[0];
+}

@@ -1,0 +1,711 @@
+// orbfe_api.cu -- host side of liborbfe.so: the C ABI of include/orbfe.h over the sm_100a kernels
+// (k_pyramid / k_fast / k_octree / k_blur / k_describe / k_stereo).  No CPU fallback: every compute entry
+// point needs a CUDA device and fails with ORBFE_ERR_CUDA otherwise.
+//
+// One handle = one device arena sized for `max_images` image slots + one private stream.  A batch
+// of n images is processed by 8 pyramid launches (the level chain of orb_extractor.cpp:1051-1076 is
+// sequential by definition) + 4 launches (FAST, quad-tree, blur, orientation+descriptor), each
+// launch covering every (slot, level, tile) of the batch; stereo adds 2 launches per batch of pairs.
+#include "../../include/orbfe.h"
+
+#include "k_pyramid.cuh"
+#include "k_fast.cuh"
+#include "k_octree.cuh"
+#include "k_blur.cuh"
+#include "k_describe.cuh"
+#include "k_stereo.cuh"
+#include "orbfe_host.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+static_assert(sizeof(orbfe_keypoint) == 28, "cv::KeyPoint layout");
+static_assert(sizeof(orbfe_kp_dev) == 28, "cv::KeyPoint layout");
+
+// ---- error plumbing ---------------------------------------------------------------------------
+static thread_local std::string t_last_error;
+int orbfe_fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_last_error = buf;
+  return code;
+}
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+static inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// cvRound: round-half-to-even in the default rounding mode
+static inline int cv_round_f(float v) { return (int)lrintf(v); }
+static inline int cv_floor_f(float v) { int i = (int)v; return i - (i > v); }
+
+struct orbfe_extractor {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  orbfe_params p{};
+  int S = 1;
+  float scale[ORBFE_MAX_LEVELS], invScale[ORBFE_MAX_LEVELS], sigma2[ORBFE_MAX_LEVELS], invSigma2[ORBFE_MAX_LEVELS];
+  int fpl[ORBFE_MAX_LEVELS];
+  Geom g{};
+  bool configured = false;
+  int fastTilePitch = 0, fastMaxInnerH = 0;
+  size_t fastSmem = 0, octSmem = 0;
+  // device arena
+  uint8_t* d_img = nullptr;
+  uint8_t* d_pyr = nullptr;
+  uint8_t* d_blur = nullptr;
+  int* d_cellCnt = nullptr;
+  unsigned* d_cellList = nullptr;
+  OctScratch oct{};
+  size_t bestStride = 0;
+  unsigned* d_lvlKp = nullptr;
+  int* d_lvlCnt = nullptr;
+  orbfe_kp_dev* d_kps = nullptr;
+  uint8_t* d_desc = nullptr;
+  int* d_nKp = nullptr;
+  ResizeLut* d_lut = nullptr;
+  int* d_err = nullptr;
+  // stereo
+  StereoPair* d_pairs = nullptr;
+  float* d_uR = nullptr;
+  float* d_depth = nullptr;
+  int* d_sad = nullptr;
+  int* d_nMatched = nullptr;
+  // pinned staging
+  int* h_n = nullptr;          // S counts + S matched + 1 err
+  orbfe_kp_dev* h_kps = nullptr;
+  uint8_t* h_desc = nullptr;
+  float* h_uR = nullptr;
+  float* h_depth = nullptr;
+  StereoPair* h_pairs = nullptr;
+  cudaEvent_t ev[64] = {};
+  bool stageTiming = false;
+  long long launches = 0;
+};
+
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return orbfe_fail(ORBFE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#ifdef ORBFE_EMU
+#define ORBFE_LAUNCH(ex, kernel, grid, block, smem, ...)                                           \
+  do { emu::launch(grid, block, smem, [&]() { kernel(__VA_ARGS__); }); (ex)->launches++; } while (0)
+#else
+#define ORBFE_LAUNCH(ex, kernel, grid, block, smem, ...)                                           \
+  do { kernel<<<grid, block, smem, (ex)->stream>>>(__VA_ARGS__); (ex)->launches++; } while (0)
+#endif
+
+// ---- geometry ---------------------------------------------------------------------------------
+// cv::resize(INTER_LINEAR) coefficient tables for one axis
+static void build_resize_lut(int dn, int sn, ResizeLut* out) {
+  const double inv_scale = (double)dn / sn;
+  const double scale = 1.0 / inv_scale;
+  for (int d = 0; d < dn; ++d) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = cv_floor_f(f);
+    f -= (float)s;
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+    out[d].ofs = s;
+    out[d].c0 = (short)cv_round_f((1.f - f) * 2048.f);
+    out[d].c1 = (short)cv_round_f(f * 2048.f);
+  }
+}
+
+static void free_arena(orbfe_extractor* ex) {
+  cudaFree(ex->d_img); cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_cellCnt); cudaFree(ex->d_cellList);
+  cudaFree(ex->oct.cand); cudaFree(ex->oct.knode); cudaFree(ex->oct.cellStart); cudaFree(ex->oct.nodes);
+  cudaFree(ex->oct.childCnt); cudaFree(ex->oct.childSlot); cudaFree(ex->oct.best); cudaFree(ex->oct.finSeq);
+  cudaFree(ex->oct.finKey); cudaFree(ex->d_lvlKp); cudaFree(ex->d_lvlCnt); cudaFree(ex->d_kps); cudaFree(ex->d_desc);
+  cudaFree(ex->d_nKp); cudaFree(ex->d_lut); cudaFree(ex->d_err); cudaFree(ex->d_pairs); cudaFree(ex->d_uR);
+  cudaFree(ex->d_depth); cudaFree(ex->d_sad); cudaFree(ex->d_nMatched);
+  cudaFreeHost(ex->h_n); cudaFreeHost(ex->h_kps); cudaFreeHost(ex->h_desc); cudaFreeHost(ex->h_uR);
+  cudaFreeHost(ex->h_depth); cudaFreeHost(ex->h_pairs);
+  ex->d_img = ex->d_pyr = ex->d_blur = nullptr; ex->d_cellCnt = nullptr; ex->d_cellList = nullptr;
+  ex->oct = OctScratch{}; ex->d_lvlKp = nullptr; ex->d_lvlCnt = nullptr; ex->d_kps = nullptr; ex->d_desc = nullptr;
+  ex->d_nKp = nullptr; ex->d_lut = nullptr; ex->d_err = nullptr; ex->d_pairs = nullptr; ex->d_uR = nullptr;
+  ex->d_depth = nullptr; ex->d_sad = nullptr; ex->d_nMatched = nullptr;
+  ex->h_n = nullptr; ex->h_kps = nullptr; ex->h_desc = nullptr; ex->h_uR = nullptr; ex->h_depth = nullptr;
+  ex->h_pairs = nullptr;
+  ex->configured = false;
+}
+
+// Computes the level geometry for a w0 x h0 input and (re)allocates the device arena.
+static int configure(orbfe_extractor* ex, int w0, int h0) {
+  if (ex->configured && ex->g.w0 == w0 && ex->g.h0 == h0) return ORBFE_OK;
+  if (w0 > 4095 + 32 || h0 > 4095 + 32)
+    return orbfe_fail(ORBFE_ERR_INVALID, "image %dx%d exceeds the 12-bit packed coordinate range", w0, h0);
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  free_arena(ex);
+  Geom& g = ex->g;
+  memset(&g, 0, sizeof(g));
+  const int nl = ex->p.nlevels;
+  g.nlevels = nl; g.w0 = w0; g.h0 = h0; g.iniTh = ex->p.ini_th_fast; g.minTh = ex->p.min_th_fast;
+  g.imgPitch = align_up(w0, 16);
+  g.imgStride = (unsigned)align_up_sz((size_t)g.imgPitch * h0, 256);
+  size_t pyrOff = 0, blurOff = 0, cellListOff = 0, candOff = 0, nodeOff = 0;
+  int cellBase = 0, outOff = 0, tileBase = 0, lutOff = 0, maxSort = 1;
+  int maxCw = 8, maxInnerH = 1;
+  std::vector<ResizeLut> lut;
+  for (int l = 0; l < nl; ++l) {
+    LevelGeom& L = g.lv[l];
+    // level size (orb_extractor.cpp:1055-1056)
+    L.w = cv_round_f((float)w0 * ex->invScale[l]);
+    L.h = cv_round_f((float)h0 * ex->invScale[l]);
+    if (L.w < 1 || L.h < 1) return orbfe_fail(ORBFE_ERR_INVALID, "pyramid level %d of a %dx%d image is empty", l, w0, h0);
+    L.scale = ex->scale[l];
+    L.kpSize = (float)(int)(ORBFE_PATCH * ex->scale[l]);  // :776 scaledPatchSize
+    L.pitch = align_up(L.w + 2 * ORBFE_EDGE, 16);
+    L.bpitch = align_up(L.w, 16);
+    L.planeOff = (unsigned)pyrOff;
+    pyrOff += align_up_sz((size_t)L.pitch * (L.h + 2 * ORBFE_EDGE), 256);
+    L.blurOff = (unsigned)blurOff;
+    blurOff += align_up_sz((size_t)L.bpitch * L.h, 256);
+    // resize LUT (level l from level l-1)
+    L.area2 = 0;
+    if (l > 0) {
+      const LevelGeom& P = g.lv[l - 1];
+      L.area2 = (P.w == 2 * L.w && P.h == 2 * L.h) ? 1 : 0;  // exact 2x: OpenCV executes INTER_AREA
+      L.lutXOff = lutOff; lutOff += L.w;
+      L.lutYOff = lutOff; lutOff += L.h;
+      lut.resize(lutOff);
+      build_resize_lut(L.w, P.w, lut.data() + L.lutXOff);
+      build_resize_lut(L.h, P.h, lut.data() + L.lutYOff);
+    }
+    L.pyrWords = (L.w + 2 * ORBFE_EDGE + 3) / 4;
+    L.pyrBlocks = (L.pyrWords * (L.h + 2 * ORBFE_EDGE) + ORBFE_PYR_THREADS - 1) / ORBFE_PYR_THREADS;
+    // FAST grid (orb_extractor.cpp:714-728)
+    L.maxBX = L.w - ORBFE_EDGE + 3;
+    L.maxBY = L.h - ORBFE_EDGE + 3;
+    const float width = (float)(L.maxBX - ORBFE_MINB), height = (float)(L.maxBY - ORBFE_MINB);
+    const float W = 30;
+    L.nCols = (int)(width / W);
+    L.nRows = (int)(height / W);
+    if (L.nCols < 1 || L.nRows < 1) {  // level too small for one cell (the reference divides by zero)
+      L.nCols = L.nRows = 0; L.wCell = L.hCell = 1;
+    } else {
+      L.wCell = (int)std::ceil(width / L.nCols);
+      L.hCell = (int)std::ceil(height / L.nRows);
+    }
+    L.cellBase = cellBase;
+    cellBase += L.nCols * L.nRows;
+    // strict 8-neighbour NMS => survivors are an independent set of the king graph
+    L.cellCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
+    L.cellListOff = (unsigned)cellListOff;
+    cellListOff += (size_t)L.nCols * L.nRows * L.cellCap;
+    if (L.nCols > 0) {
+      maxCw = std::max(maxCw, L.wCell + 6);
+      maxInnerH = std::max(maxInnerH, L.hCell);
+    }
+    // quad-tree (orb_extractor.cpp:480-531)
+    L.N = ex->fpl[l];
+    L.boxW = L.maxBX - ORBFE_MINB;
+    L.boxH = L.maxBY - ORBFE_MINB;
+    int nIni = L.boxH > 0 ? (int)std::round((float)L.boxW / (float)L.boxH) : 1;
+    if (nIni < 1) nIni = 1;
+    L.nIni = nIni;
+    L.hX = (float)L.boxW / (float)nIni;
+    L.candCap = std::max(L.nCols * L.nRows * L.cellCap, 1);
+    L.candOff = (unsigned)candOff;
+    candOff += (size_t)L.candCap;
+    L.nodeCap = 4 * std::max(L.N, nIni) + 16;
+    L.nodeOff = (unsigned)nodeOff;
+    nodeOff += (size_t)L.nodeCap;
+    L.outCap = std::max(L.N + 3, 4 * nIni);
+    L.outOff = outOff;
+    outOff += L.outCap;
+    maxSort = std::max(maxSort, std::max(L.outCap, std::max(L.N, nIni)));
+    L.tilesX = (L.w + ORBFE_BLUR_TW - 1) / ORBFE_BLUR_TW;
+    L.tilesY = (L.h + ORBFE_BLUR_TH - 1) / ORBFE_BLUR_TH;
+    L.tileBase = tileBase;
+    tileBase += L.tilesX * L.tilesY;
+  }
+  g.totalCells = cellBase;
+  g.totalTiles = tileBase;
+  g.totalOut = outOff;
+  g.pyrStride = (unsigned)pyrOff;
+  g.blurStride = (unsigned)blurOff;
+  g.cellListStride = (unsigned)std::max<size_t>(cellListOff, 1);
+  g.candStride = (unsigned)candOff;
+  g.nodeStride = (unsigned)nodeOff;
+  int sc = 1;
+  while (sc < maxSort) sc <<= 1;
+  g.sortCap = sc;
+  ex->octSmem = (size_t)sc * sizeof(unsigned long long);
+  if (ex->octSmem > 200 * 1024)
+    return orbfe_fail(ORBFE_ERR_INVALID, "nfeatures per level too large for the shared-memory sort (%d)", maxSort);
+  ex->fastTilePitch = align_up(maxCw, 4);
+  ex->fastMaxInnerH = maxInnerH;
+  ex->fastSmem = (size_t)(2 * maxInnerH + 8) * ex->fastTilePitch;
+  if (ex->fastSmem > 200 * 1024) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too large");
+  ex->bestStride = (size_t)g.nodeStride * 5 / 4 + 16 * ORBFE_MAX_LEVELS;
+
+  const size_t S = (size_t)ex->S;
+  CUDA_TRY(cudaMalloc(&ex->d_img, S * g.imgStride));
+  CUDA_TRY(cudaMalloc(&ex->d_pyr, S * g.pyrStride));
+  CUDA_TRY(cudaMalloc(&ex->d_blur, S * g.blurStride));
+  CUDA_TRY(cudaMalloc(&ex->d_cellCnt, S * std::max(g.totalCells, 1) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->d_cellList, S * g.cellListStride * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&ex->oct.cand, S * g.candStride * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&ex->oct.knode, S * g.candStride * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->oct.cellStart, S * std::max(g.totalCells, 1) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->oct.nodes, S * 2 * g.nodeStride * sizeof(OctNode)));
+  CUDA_TRY(cudaMalloc(&ex->oct.childCnt, S * g.nodeStride * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->oct.childSlot, S * g.nodeStride * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->oct.best, S * ex->bestStride * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&ex->oct.finSeq, S * g.totalOut * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->oct.finKey, S * g.totalOut * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->d_lvlKp, S * g.totalOut * sizeof(unsigned)));
+  CUDA_TRY(cudaMalloc(&ex->d_lvlCnt, S * nl * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->d_kps, S * g.totalOut * sizeof(orbfe_kp_dev)));
+  CUDA_TRY(cudaMalloc(&ex->d_desc, S * g.totalOut * 32));
+  CUDA_TRY(cudaMalloc(&ex->d_nKp, S * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->d_lut, std::max<size_t>(lut.size(), 1) * sizeof(ResizeLut)));
+  CUDA_TRY(cudaMalloc(&ex->d_err, sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->d_pairs, S * sizeof(StereoPair)));
+  CUDA_TRY(cudaMalloc(&ex->d_uR, S * g.totalOut * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&ex->d_depth, S * g.totalOut * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&ex->d_sad, S * g.totalOut * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->d_nMatched, S * sizeof(int)));
+  CUDA_TRY(cudaMallocHost(&ex->h_n, (2 * S + 1) * sizeof(int)));
+  CUDA_TRY(cudaMallocHost(&ex->h_kps, S * g.totalOut * sizeof(orbfe_kp_dev)));
+  CUDA_TRY(cudaMallocHost(&ex->h_desc, S * g.totalOut * 32));
+  CUDA_TRY(cudaMallocHost(&ex->h_uR, S * g.totalOut * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&ex->h_depth, S * g.totalOut * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&ex->h_pairs, S * sizeof(StereoPair)));
+  if (!lut.empty())
+    CUDA_TRY(cudaMemcpyAsync(ex->d_lut, lut.data(), lut.size() * sizeof(ResizeLut), cudaMemcpyHostToDevice, ex->stream));
+  CUDA_TRY(cudaMemsetAsync(ex->d_err, 0, sizeof(int), ex->stream));
+  CUDA_TRY(cudaMemsetAsync(ex->d_nKp, 0, S * sizeof(int), ex->stream));
+  CUDA_TRY(cudaMemsetAsync(ex->d_nMatched, 0, S * sizeof(int), ex->stream));
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));  // `lut` goes out of scope
+#ifndef ORBFE_EMU
+  CUDA_TRY(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
+  CUDA_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octSmem));
+#endif
+  ex->configured = true;
+  return ORBFE_OK;
+}
+
+static int stage_event(orbfe_extractor* ex, int slot) {
+  if (ex->stageTiming) CUDA_TRY(cudaEventRecord(ex->ev[slot], ex->stream));
+  return ORBFE_OK;
+}
+
+static int enqueue_extract(orbfe_extractor* ex, int n) {
+  const Geom& g = ex->g;
+  int rc;
+  if ((rc = stage_event(ex, 32))) return rc;
+  for (int l = 0; l < g.nlevels; ++l)
+    ORBFE_LAUNCH(ex, k_pyramid_level, dim3(g.lv[l].pyrBlocks, n), dim3(ORBFE_PYR_THREADS), 0, g, l, ex->d_img, ex->d_pyr,
+                 ex->d_lut);
+  if ((rc = stage_event(ex, 33))) return rc;
+  if (g.totalCells > 0)
+    ORBFE_LAUNCH(ex, k_fast_cells, dim3(g.totalCells, n), dim3(ORBFE_FAST_THREADS), ex->fastSmem, g, ex->d_pyr,
+                 ex->d_cellCnt, ex->d_cellList, ex->fastTilePitch, ex->fastMaxInnerH);
+  if ((rc = stage_event(ex, 34))) return rc;
+  ORBFE_LAUNCH(ex, k_octree, dim3(g.nlevels, n), dim3(ORBFE_OCT_THREADS), ex->octSmem, g, ex->d_cellCnt, ex->d_cellList,
+               ex->oct, ex->d_lvlKp, ex->d_lvlCnt, ex->d_err);
+  if ((rc = stage_event(ex, 35))) return rc;
+  ORBFE_LAUNCH(ex, k_blur, dim3(g.totalTiles, n), dim3(ORBFE_BLUR_THREADS), 0, g, ex->d_pyr, ex->d_blur);
+  if ((rc = stage_event(ex, 36))) return rc;
+  ORBFE_LAUNCH(ex, k_orient_describe, dim3((g.totalOut + ORBFE_DESC_THREADS / 32 - 1) / (ORBFE_DESC_THREADS / 32), n),
+               dim3(ORBFE_DESC_THREADS), 0, g, ex->d_pyr, ex->d_blur, ex->d_lvlKp, ex->d_lvlCnt, ex->d_kps, ex->d_desc,
+               ex->d_nKp);
+  if ((rc = stage_event(ex, 37))) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return ORBFE_OK;
+}
+
+static int check_images(orbfe_extractor* ex, int first, int n) {
+  if (!ex) return orbfe_fail(ORBFE_ERR_INVALID, "null extractor handle");
+  if (n < 0 || first < 0 || first + n > ex->S)
+    return orbfe_fail(ORBFE_ERR_INVALID, "slots [%d,%d) exceed max_images=%d", first, first + n, ex->S);
+  return ORBFE_OK;
+}
+
+extern "C" {
+
+const char* orbfe_last_error(void) { return t_last_error.c_str(); }
+const char* orbfe_version(void) {
+#ifdef ORBFE_EMU
+  return "orbfe 0.1 (EMULATED TEST BUILD - not a product library)";
+#else
+  return "orbfe 0.1 (sm_100a)";
+#endif
+}
+int orbfe_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int orbfe_extractor_create(const orbfe_params* p, int device, orbfe_extractor** out) {
+  if (!p || !out) return orbfe_fail(ORBFE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (p->nlevels < 1 || p->nlevels > ORBFE_MAX_LEVELS)
+    return orbfe_fail(ORBFE_ERR_INVALID, "nlevels must be in [1,%d]", ORBFE_MAX_LEVELS);
+  if (p->nfeatures < 1 || !(p->scale_factor > 1.0f) || p->ini_th_fast < 1 || p->min_th_fast < 1 ||
+      p->ini_th_fast > 255 || p->min_th_fast > p->ini_th_fast)
+    return orbfe_fail(ORBFE_ERR_INVALID, "bad ORB parameters");
+  const int ndev = orbfe_device_count();
+  if (device < 0 || device >= ndev)
+    return orbfe_fail(ORBFE_ERR_CUDA, "CUDA device %d not available (%d visible); this library has no CPU path", device, ndev);
+  orbfe_extractor* ex = new (std::nothrow) orbfe_extractor();
+  if (!ex) return orbfe_fail(ORBFE_ERR_NOMEM, "out of host memory");
+  ex->device = device;
+  ex->p = *p;
+  ex->S = p->max_images > 0 ? p->max_images : 1;
+  // scale tables and per-level feature quota (orb_extractor.cpp:356-387); scaleFactor is a double
+  // member holding the float argument (orb_extractor.h:79)
+  const double sf = (double)p->scale_factor;
+  const int nl = p->nlevels;
+  ex->scale[0] = 1.0f; ex->sigma2[0] = 1.0f;
+  for (int i = 1; i < nl; ++i) {
+    ex->scale[i] = (float)((double)ex->scale[i - 1] * sf);
+    ex->sigma2[i] = ex->scale[i] * ex->scale[i];
+  }
+  for (int i = 0; i < nl; ++i) { ex->invScale[i] = 1.0f / ex->scale[i]; ex->invSigma2[i] = 1.0f / ex->sigma2[i]; }
+  const float factor = (float)(1.0 / sf);
+  float nDesired = p->nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nl));
+  int sum = 0;
+  for (int l = 0; l < nl - 1; ++l) {
+    ex->fpl[l] = cv_round_f(nDesired);
+    sum += ex->fpl[l];
+    nDesired *= factor;
+  }
+  ex->fpl[nl - 1] = std::max(p->nfeatures - sum, 0);
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 64 && e == cudaSuccess; ++i) e = cudaEventCreate(&ex->ev[i]);
+  if (e != cudaSuccess) {
+    delete ex;
+    return orbfe_fail(ORBFE_ERR_CUDA, "device %d setup failed: %s", device, cudaGetErrorString(e));
+  }
+  if (p->max_width > 0 && p->max_height > 0) {
+    const int rc = configure(ex, p->max_width, p->max_height);
+    if (rc != ORBFE_OK) { orbfe_extractor_destroy(ex); return rc; }
+  }
+  *out = ex;
+  return ORBFE_OK;
+}
+
+int orbfe_extractor_destroy(orbfe_extractor* ex) {
+  if (!ex) return ORBFE_OK;
+  cudaSetDevice(ex->device);
+  if (ex->stream) cudaStreamSynchronize(ex->stream);
+  free_arena(ex);
+  for (int i = 0; i < 64; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
+  if (ex->stream) cudaStreamDestroy(ex->stream);
+  delete ex;
+  return ORBFE_OK;
+}
+
+int orbfe_extractor_tables(const orbfe_extractor* ex, int* nlevels, float* scale, float* inv_scale, float* sigma2,
+                           float* inv_sigma2, int32_t* features_per_level) {
+  if (!ex) return orbfe_fail(ORBFE_ERR_INVALID, "null extractor handle");
+  if (nlevels) *nlevels = ex->p.nlevels;
+  for (int i = 0; i < ex->p.nlevels; ++i) {
+    if (scale) scale[i] = ex->scale[i];
+    if (inv_scale) inv_scale[i] = ex->invScale[i];
+    if (sigma2) sigma2[i] = ex->sigma2[i];
+    if (inv_sigma2) inv_sigma2[i] = ex->invSigma2[i];
+    if (features_per_level) features_per_level[i] = ex->fpl[i];
+  }
+  return ORBFE_OK;
+}
+
+int orbfe_extractor_max_keypoints(const orbfe_extractor* ex) {
+  if (!ex) return orbfe_fail(ORBFE_ERR_INVALID, "null extractor handle");
+  if (ex->configured) return ex->g.totalOut;
+  // before the first image the aspect ratio (nIni) is unknown: N_l + 3 per level, and 4*nIni for
+  // levels whose quota is tiny; 64 per level covers aspect ratios up to 16:1
+  return ex->p.nfeatures + 64 * ex->p.nlevels;
+}
+
+int orbfe_upload(orbfe_extractor* ex, int first_slot, const uint8_t* const* imgs, int n_imgs, int w, int h,
+                 size_t stride) {
+  int rc = check_images(ex, first_slot, n_imgs);
+  if (rc) return rc;
+  if (!imgs || w <= 0 || h <= 0 || stride < (size_t)w) return orbfe_fail(ORBFE_ERR_INVALID, "bad image arguments");
+  CUDA_TRY(cudaSetDevice(ex->device));
+  if ((rc = configure(ex, w, h))) return rc;
+  for (int i = 0; i < n_imgs; ++i) {
+    if (!imgs[i]) return orbfe_fail(ORBFE_ERR_INVALID, "null image %d", i);
+    CUDA_TRY(cudaMemcpy2DAsync(ex->d_img + (size_t)(first_slot + i) * ex->g.imgStride, ex->g.imgPitch, imgs[i], stride,
+                               (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ex->stream));
+  }
+  return ORBFE_OK;
+}
+
+int orbfe_run(orbfe_extractor* ex, int n_imgs) {
+  int rc = check_images(ex, 0, n_imgs);
+  if (rc) return rc;
+  if (!ex->configured) return orbfe_fail(ORBFE_ERR_INVALID, "orbfe_run before any orbfe_upload");
+  if (n_imgs == 0) return ORBFE_OK;
+  CUDA_TRY(cudaSetDevice(ex->device));
+  return enqueue_extract(ex, n_imgs);
+}
+
+// fills the StereoPair table for pairs (slot 2p, slot 2p+1) of ONE handle
+static void fill_pairs_same_handle(orbfe_extractor* ex, int n_pairs) {
+  const Geom& g = ex->g;
+  for (int p = 0; p < n_pairs; ++p) {
+    const size_t a = 2 * (size_t)p, b = a + 1;
+    StereoPair& P = ex->h_pairs[p];
+    P.pyrL = ex->d_pyr + a * g.pyrStride; P.pyrR = ex->d_pyr + b * g.pyrStride;
+    P.kpL = ex->d_kps + a * g.totalOut; P.kpR = ex->d_kps + b * g.totalOut;
+    P.descL = ex->d_desc + a * g.totalOut * 32; P.descR = ex->d_desc + b * g.totalOut * 32;
+    P.nL = ex->d_nKp + a; P.nR = ex->d_nKp + b;
+    P.uR = ex->d_uR + a * g.totalOut; P.depth = ex->d_depth + a * g.totalOut; P.sad = ex->d_sad + a * g.totalOut;
+  }
+}
+
+static int enqueue_stereo(orbfe_extractor* ex, int n_pairs, float bf, float baseline) {
+  const Geom& g = ex->g;
+  CUDA_TRY(cudaMemcpyAsync(ex->d_pairs, ex->h_pairs, (size_t)n_pairs * sizeof(StereoPair), cudaMemcpyHostToDevice, ex->stream));
+  ORBFE_LAUNCH(ex, k_stereo_search, dim3((g.totalOut + ORBFE_ST_THREADS / 32 - 1) / (ORBFE_ST_THREADS / 32), n_pairs),
+               dim3(ORBFE_ST_THREADS), 0, g, ex->d_pairs, bf, baseline, g.totalOut);
+  int rc;
+  if ((rc = stage_event(ex, 38))) return rc;
+  ORBFE_LAUNCH(ex, k_stereo_median, dim3(n_pairs), dim3(ORBFE_ST_THREADS), 0, ex->d_pairs, g.totalOut, ex->d_nMatched);
+  if ((rc = stage_event(ex, 39))) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return ORBFE_OK;
+}
+
+int orbfe_run_stereo(orbfe_extractor* ex, int n_pairs, float bf, float baseline) {
+  int rc = check_images(ex, 0, 2 * n_pairs);
+  if (rc) return rc;
+  if (!ex->configured) return orbfe_fail(ORBFE_ERR_INVALID, "orbfe_run_stereo before any orbfe_upload");
+  if (!(baseline > 0.f) || !(bf > 0.f)) return orbfe_fail(ORBFE_ERR_INVALID, "bf and baseline must be positive");
+  if (n_pairs == 0) return ORBFE_OK;
+  CUDA_TRY(cudaSetDevice(ex->device));
+  // h_pairs is rewritten only when the previous table has been consumed
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  fill_pairs_same_handle(ex, n_pairs);
+  return enqueue_stereo(ex, n_pairs, bf, baseline);
+}
+
+int orbfe_download(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t* desc, int capacity, int* n_out,
+                   float* u_right, float* depth) {
+  int rc = check_images(ex, 0, n_imgs);
+  if (rc) return rc;
+  if (!ex->configured) return orbfe_fail(ORBFE_ERR_INVALID, "orbfe_download before any orbfe_upload");
+  if (!n_out || capacity < 0) return orbfe_fail(ORBFE_ERR_INVALID, "bad output arguments");
+  if (n_imgs == 0) return ORBFE_OK;
+  CUDA_TRY(cudaSetDevice(ex->device));
+  const Geom& g = ex->g;
+  const size_t S = (size_t)ex->S, T = (size_t)g.totalOut, n = (size_t)n_imgs;
+  CUDA_TRY(cudaMemcpyAsync(ex->h_n, ex->d_nKp, n * sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
+  CUDA_TRY(cudaMemcpyAsync(ex->h_n + 2 * S, ex->d_err, sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
+  if (kps) CUDA_TRY(cudaMemcpyAsync(ex->h_kps, ex->d_kps, n * T * sizeof(orbfe_kp_dev), cudaMemcpyDeviceToHost, ex->stream));
+  if (desc) CUDA_TRY(cudaMemcpyAsync(ex->h_desc, ex->d_desc, n * T * 32, cudaMemcpyDeviceToHost, ex->stream));
+  if (u_right) CUDA_TRY(cudaMemcpyAsync(ex->h_uR, ex->d_uR, n * T * sizeof(float), cudaMemcpyDeviceToHost, ex->stream));
+  if (depth) CUDA_TRY(cudaMemcpyAsync(ex->h_depth, ex->d_depth, n * T * sizeof(float), cudaMemcpyDeviceToHost, ex->stream));
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  if (ex->h_n[2 * S] != 0) {
+    cudaMemsetAsync(ex->d_err, 0, sizeof(int), ex->stream);
+    return orbfe_fail(ORBFE_ERR_CUDA, "quad-tree kernel reported an internal capacity error (flag %d)", ex->h_n[2 * S]);
+  }
+  int status = ORBFE_OK;
+  for (size_t i = 0; i < n; ++i) {
+    const int c = ex->h_n[i];
+    n_out[i] = c;
+    if (c > capacity) { status = ORBFE_ERR_CAPACITY; continue; }
+    if (kps) memcpy(kps + i * (size_t)capacity, ex->h_kps + i * T, (size_t)c * sizeof(orbfe_keypoint));
+    if (desc) memcpy(desc + i * (size_t)capacity * 32, ex->h_desc + i * T * 32, (size_t)c * 32);
+    if ((i & 1) == 0) {
+      if (u_right) memcpy(u_right + i * (size_t)capacity, ex->h_uR + i * T, (size_t)c * sizeof(float));
+      if (depth) memcpy(depth + i * (size_t)capacity, ex->h_depth + i * T, (size_t)c * sizeof(float));
+    }
+  }
+  if (status != ORBFE_OK) return orbfe_fail(status, "capacity %d too small for the keypoint count", capacity);
+  return ORBFE_OK;
+}
+
+int orbfe_sync(orbfe_extractor* ex) {
+  if (!ex) return orbfe_fail(ORBFE_ERR_INVALID, "null extractor handle");
+  CUDA_TRY(cudaSetDevice(ex->device));
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  return ORBFE_OK;
+}
+
+int orbfe_extract_batch(orbfe_extractor* ex, const uint8_t* const* imgs, int n_imgs, int w, int h, size_t stride,
+                        orbfe_keypoint* kps, uint8_t* desc, int capacity, int* n_out) {
+  int rc = orbfe_upload(ex, 0, imgs, n_imgs, w, h, stride);
+  if (rc) return rc;
+  if ((rc = orbfe_run(ex, n_imgs))) return rc;
+  return orbfe_download(ex, n_imgs, kps, desc, capacity, n_out, nullptr, nullptr);
+}
+
+int orbfe_extract(orbfe_extractor* ex, const uint8_t* img, int w, int h, size_t stride, orbfe_keypoint* kps,
+                  uint8_t* desc, int capacity, int* n_out) {
+  if (!ex || !n_out) return orbfe_fail(ORBFE_ERR_INVALID, "null argument");
+  *n_out = 0;
+  if (!img || w <= 0 || h <= 0) return ORBFE_OK;  // _image.empty() => return (orb_extractor.cpp:990-991)
+  const uint8_t* one[1] = {img};
+  return orbfe_extract_batch(ex, one, 1, w, h, stride, kps, desc, capacity, n_out);
+}
+
+int orbfe_pyramid_level(orbfe_extractor* ex, int slot, int level, uint8_t* dst, size_t dst_stride, int* w, int* h) {
+  int rc = check_images(ex, slot, 1);
+  if (rc) return rc;
+  if (!ex->configured) return orbfe_fail(ORBFE_ERR_INVALID, "no image has been processed yet");
+  if (level < 0 || level >= ex->g.nlevels) return orbfe_fail(ORBFE_ERR_INVALID, "bad level %d", level);
+  const LevelGeom& L = ex->g.lv[level];
+  if (w) *w = L.w;
+  if (h) *h = L.h;
+  if (!dst) return ORBFE_OK;
+  if (dst_stride < (size_t)L.w) return orbfe_fail(ORBFE_ERR_INVALID, "dst_stride too small");
+  CUDA_TRY(cudaSetDevice(ex->device));
+  const uint8_t* src = ex->d_pyr + (size_t)slot * ex->g.pyrStride + L.planeOff + (size_t)ORBFE_EDGE * L.pitch + ORBFE_EDGE;
+  CUDA_TRY(cudaMemcpy2DAsync(dst, dst_stride, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, ex->stream));
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  return ORBFE_OK;
+}
+
+int orbfe_event_record(orbfe_extractor* ex, int slot) {
+  if (!ex || slot < 0 || slot >= 64) return orbfe_fail(ORBFE_ERR_INVALID, "bad event slot");
+  CUDA_TRY(cudaSetDevice(ex->device));
+  CUDA_TRY(cudaEventRecord(ex->ev[slot], ex->stream));
+  return ORBFE_OK;
+}
+int orbfe_event_elapsed_ms(orbfe_extractor* ex, int a, int b, float* ms) {
+  if (!ex || !ms || a < 0 || a >= 64 || b < 0 || b >= 64) return orbfe_fail(ORBFE_ERR_INVALID, "bad event slot");
+  CUDA_TRY(cudaSetDevice(ex->device));
+  CUDA_TRY(cudaEventElapsedTime(ms, ex->ev[a], ex->ev[b]));
+  return ORBFE_OK;
+}
+int orbfe_set_stage_timing(orbfe_extractor* ex, int enabled) {
+  if (!ex) return orbfe_fail(ORBFE_ERR_INVALID, "null extractor handle");
+  ex->stageTiming = enabled != 0;
+  return ORBFE_OK;
+}
+long long orbfe_launch_count(const orbfe_extractor* ex) { return ex ? ex->launches : 0; }
+
+// ---- debug taps (per-stage parity tests) ------------------------------------------------------
+static void unpack_kp(unsigned pk, orbfe_keypoint* k) {
+  k->x = (float)ORBFE_PX(pk); k->y = (float)ORBFE_PY(pk); k->size = 7.f; k->angle = -1.f;
+  k->response = (float)ORBFE_PS(pk); k->octave = 0; k->class_id = -1;
+}
+
+int orbfe_debug_candidates(orbfe_extractor* ex, int slot, int level, orbfe_keypoint* out, int capacity, int* n_out) {
+  int rc = check_images(ex, slot, 1);
+  if (rc) return rc;
+  if (!ex->configured || level < 0 || level >= ex->g.nlevels || !n_out) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
+  CUDA_TRY(cudaSetDevice(ex->device));
+  const Geom& g = ex->g;
+  const LevelGeom& L = g.lv[level];
+  const int nCells = L.nCols * L.nRows;
+  std::vector<int> cnt(std::max(nCells, 1));
+  std::vector<unsigned> list((size_t)std::max(nCells, 1) * L.cellCap);
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  if (nCells > 0) {
+    CUDA_TRY(cudaMemcpy(cnt.data(), ex->d_cellCnt + (size_t)slot * g.totalCells + L.cellBase, nCells * sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(list.data(), ex->d_cellList + (size_t)slot * g.cellListStride + L.cellListOff,
+                        (size_t)nCells * L.cellCap * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  }
+  int n = 0;
+  for (int c = 0; c < nCells; ++c)
+    for (int k = 0; k < cnt[c]; ++k, ++n)
+      if (out && n < capacity) unpack_kp(list[(size_t)c * L.cellCap + k], &out[n]);
+  *n_out = n;
+  return ORBFE_OK;
+}
+
+int orbfe_debug_level_keypoints(orbfe_extractor* ex, int slot, int level, orbfe_keypoint* out, int capacity, int* n_out) {
+  int rc = check_images(ex, slot, 1);
+  if (rc) return rc;
+  if (!ex->configured || level < 0 || level >= ex->g.nlevels || !n_out) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
+  CUDA_TRY(cudaSetDevice(ex->device));
+  const Geom& g = ex->g;
+  const LevelGeom& L = g.lv[level];
+  int n = 0;
+  std::vector<unsigned> v(L.outCap);
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  CUDA_TRY(cudaMemcpy(&n, ex->d_lvlCnt + (size_t)slot * g.nlevels + level, sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(cudaMemcpy(v.data(), ex->d_lvlKp + (size_t)slot * g.totalOut + L.outOff, (size_t)L.outCap * sizeof(unsigned), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n && i < capacity && out; ++i) unpack_kp(v[i], &out[i]);
+  *n_out = n;
+  return ORBFE_OK;
+}
+
+int orbfe_debug_blurred(orbfe_extractor* ex, int slot, int level, uint8_t* dst, size_t dst_stride, int* w, int* h) {
+  int rc = check_images(ex, slot, 1);
+  if (rc) return rc;
+  if (!ex->configured || level < 0 || level >= ex->g.nlevels) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
+  const LevelGeom& L = ex->g.lv[level];
+  if (w) *w = L.w;
+  if (h) *h = L.h;
+  if (!dst) return ORBFE_OK;
+  CUDA_TRY(cudaSetDevice(ex->device));
+  CUDA_TRY(cudaMemcpy2DAsync(dst, dst_stride, ex->d_blur + (size_t)slot * ex->g.blurStride + L.blurOff, L.bpitch, L.w, L.h,
+                             cudaMemcpyDeviceToHost, ex->stream));
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  return ORBFE_OK;
+}
+
+// ---- Frame::ComputeStereoMatches drop-in (frame.cpp:406-577) ----------------------------------
+int orbfe_stereo_match(orbfe_extractor* left, orbfe_extractor* right, int n_left, const orbfe_keypoint* kps_left,
+                       const uint8_t* desc_left, int n_right, const orbfe_keypoint* kps_right, const uint8_t* desc_right,
+                       float bf, float baseline, float* u_right, float* depth, int* n_matched) {
+  if (!left || !right || !u_right || !depth) return orbfe_fail(ORBFE_ERR_INVALID, "null argument");
+  if (n_left < 0 || n_right < 0 || (n_left && (!kps_left || !desc_left)) || (n_right && (!kps_right || !desc_right)))
+    return orbfe_fail(ORBFE_ERR_INVALID, "bad keypoint arrays");
+  if (!(baseline > 0.f) || !(bf > 0.f)) return orbfe_fail(ORBFE_ERR_INVALID, "bf and baseline must be positive");
+  if (!left->configured || !right->configured) return orbfe_fail(ORBFE_ERR_INVALID, "extract both images first");
+  if (left->device != right->device || left->g.w0 != right->g.w0 || left->g.h0 != right->g.h0 ||
+      left->g.nlevels != right->g.nlevels || left->p.scale_factor != right->p.scale_factor)
+    return orbfe_fail(ORBFE_ERR_INVALID, "left/right extractors differ in device, image size or pyramid");
+  if (n_matched) *n_matched = 0;
+  for (int i = 0; i < n_left; ++i) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+  if (n_left == 0 || n_right == 0) return ORBFE_OK;
+  const Geom& g = left->g;
+  if (n_left > g.totalOut || n_right > right->g.totalOut)
+    return orbfe_fail(ORBFE_ERR_INVALID, "more keypoints than one image can produce (%d/%d > %d)", n_left, n_right, g.totalOut);
+  CUDA_TRY(cudaSetDevice(left->device));
+  CUDA_TRY(cudaStreamSynchronize(right->stream));  // right pyramid complete
+  CUDA_TRY(cudaStreamSynchronize(left->stream));
+  orbfe_extractor* ex = left;
+  const bool same = left == right;
+  // the Frame's own arrays are authoritative (the reference reads keypoints_/descriptors_):
+  // upload them into slot 0 of each handle's keypoint block (slot 1 of `left` if both are one handle)
+  const size_t rslot = same ? 1 : 0;
+  if (same && left->S < 2) return orbfe_fail(ORBFE_ERR_INVALID, "one shared handle needs max_images >= 2");
+  int* cnts = ex->h_n;
+  cnts[0] = n_left; cnts[1] = n_right;
+  CUDA_TRY(cudaMemcpyAsync(left->d_kps, kps_left, (size_t)n_left * sizeof(orbfe_kp_dev), cudaMemcpyHostToDevice, ex->stream));
+  CUDA_TRY(cudaMemcpyAsync(left->d_desc, desc_left, (size_t)n_left * 32, cudaMemcpyHostToDevice, ex->stream));
+  CUDA_TRY(cudaMemcpyAsync(right->d_kps + rslot * right->g.totalOut, kps_right, (size_t)n_right * sizeof(orbfe_kp_dev), cudaMemcpyHostToDevice, ex->stream));
+  CUDA_TRY(cudaMemcpyAsync(right->d_desc + rslot * right->g.totalOut * 32, desc_right, (size_t)n_right * 32, cudaMemcpyHostToDevice, ex->stream));
+  CUDA_TRY(cudaMemcpyAsync(left->d_nKp, &cnts[0], sizeof(int), cudaMemcpyHostToDevice, ex->stream));
+  CUDA_TRY(cudaMemcpyAsync(right->d_nKp + rslot, &cnts[1], sizeof(int), cudaMemcpyHostToDevice, ex->stream));
+  StereoPair& P = ex->h_pairs[0];
+  P.pyrL = left->d_pyr; P.pyrR = right->d_pyr + rslot * right->g.pyrStride;
+  P.kpL = left->d_kps; P.kpR = right->d_kps + rslot * right->g.totalOut;
+  P.descL = left->d_desc; P.descR = right->d_desc + rslot * right->g.totalOut * 32;
+  P.nL = left->d_nKp; P.nR = right->d_nKp + rslot;
+  P.uR = left->d_uR; P.depth = left->d_depth; P.sad = left->d_sad;
+  int rc = enqueue_stereo(ex, 1, bf, baseline);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ex->h_uR, ex->d_uR, (size_t)n_left * sizeof(float), cudaMemcpyDeviceToHost, ex->stream));
+  CUDA_TRY(cudaMemcpyAsync(ex->h_depth, ex->d_depth, (size_t)n_left * sizeof(float), cudaMemcpyDeviceToHost, ex->stream));
+  CUDA_TRY(cudaMemcpyAsync(ex->h_n + ex->S, ex->d_nMatched, sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  memcpy(u_right, ex->h_uR, (size_t)n_left * sizeof(float));
+  memcpy(depth, ex->h_depth, (size_t)n_left * sizeof(float));
+  if (n_matched) *n_matched = ex->h_n[ex->S];
+  return ORBFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+// orbfe_common.cuh -- shared definitions of the B200 ORB front-end kernels.
+// Device memory layout (per extractor handle, S = max_images slots; all per-slot blocks are
+// strided arrays so one launch covers (slot, level, tile)):
+//   img      S x imgStride      u8   input frames (pitch = align16(max_w))
+//   pyr      S x pyrStride      u8   8 padded planes (w+38)x(h+38), pitch align16, plane align256
+//   blur     S x blurStride     u8   8 blurred planes w x h
+//   cellCnt  S x totalCells     i32  FAST survivors per 30-px grid cell
+//   cellList S x cellListStride u32  per-cell candidate lists (x | y<<12 | score<<24, relative
+//                                    to the (16,16) detection origin)
+//   cand     S x candStride     u32  per-level candidate list in reference order
+//   knode    S x candStride     i32  quad-tree: owning node of each candidate
+//   nodes... quad-tree generations, finals list (see k_octree.cuh)
+//   lvlKp    S x totalOut       u32  distributed keypoints per level (packed like cand)
+//   lvlCnt   S x nlevels        i32
+//   kps/desc S x totalOut       cv::KeyPoint (28 B) / 32 B descriptors, level-major order
+#pragma once
+#include <stdint.h>
+
+#ifndef ORBFE_EMU
+#include <cuda_runtime.h>
+#endif
+
+#define ORBFE_MAX_LEVELS 12
+#define ORBFE_EDGE 19        // EDGE_THRESHOLD, orb_extractor.cpp:15
+#define ORBFE_MINB 16        // EDGE_THRESHOLD-3, orb_extractor.cpp:714
+#define ORBFE_HALF_PATCH 15  // orb_extractor.cpp:14
+#define ORBFE_PATCH 31       // orb_extractor.cpp:13
+
+struct LevelGeom {
+  int w, h;              // level size (orb_extractor.cpp:1056)
+  int pitch;             // padded plane pitch (bytes)
+  int bpitch;            // blurred plane pitch (bytes)
+  unsigned planeOff;     // byte offset of the padded plane inside a slot's pyramid block
+  unsigned blurOff;      // byte offset of the blurred plane inside a slot's blur block
+  int lutXOff, lutYOff;  // offsets into the resize LUT (entries)
+  int area2;             // exact 2x decimation (OpenCV executes INTER_AREA)
+  // FAST grid (orb_extractor.cpp:714-728)
+  int nCols, nRows, wCell, hCell, maxBX, maxBY;
+  int cellBase, cellCap;
+  unsigned cellListOff;  // u32 entries
+  // quad-tree (orb_extractor.cpp:480-704)
+  int N, nIni, boxW, boxH;
+  float hX;
+  int candCap;
+  unsigned candOff;      // u32 entries
+  int nodeCap;
+  unsigned nodeOff;      // nodes
+  int outCap, outOff;    // distributed keypoints of this level
+  // blur tiling
+  int tilesX, tilesY, tileBase;
+  // pyramid tiling (rows of 4-px words)
+  int pyrWords, pyrBlockBase, pyrBlocks;
+  float scale;           // mvScaleFactor[level]
+  float kpSize;          // (float)(int)(PATCH_SIZE*scale), orb_extractor.cpp:776
+};
+
+struct Geom {
+  int nlevels, w0, h0, iniTh, minTh;
+  int imgPitch;
+  int totalCells, totalTiles, totalOut, totalPyrBlocks;
+  int sortCap;           // power of two >= max(outCap, N) over levels
+  unsigned imgStride, pyrStride, blurStride, cellListStride, candStride, nodeStride;
+  LevelGeom lv[ORBFE_MAX_LEVELS];
+};
+
+// resize LUT entry (cv::resize INTER_LINEAR fixed-point coefficients)
+struct ResizeLut {
+  int ofs;
+  short c0, c1;
+};
+
+// packed candidate / keypoint: x (12 bits) | y (12 bits) << 12 | score (8 bits) << 24
+__host__ __device__ __forceinline__ unsigned orbfe_pack(int x, int y, int s) {
+  return (unsigned)x | ((unsigned)y << 12) | ((unsigned)s << 24);
+}
+#define ORBFE_PX(p) ((int)((p) & 0xfffu))
+#define ORBFE_PY(p) ((int)(((p) >> 12) & 0xfffu))
+#define ORBFE_PS(p) ((int)((p) >> 24))
+
+__device__ __forceinline__ int orbfe_reflect101(int p, int n) {
+  // cv::borderInterpolate(BORDER_REFLECT_101)
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * (n - 1) - p;
+  return p;
+}
+
+// ---- block-wide exclusive scan of one int per thread (all threads must call) ---------------
+// s_warp: shared int[33].  Returns the exclusive prefix; *total = block sum.
+__device__ __forceinline__ int orbfe_block_exscan(int v, int* s_warp, int* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();  // protect s_warp reuse across consecutive calls
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < nw ? s_warp[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < nw) s_warp[lane] = winc - w;
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[wid] + inc - v;
+}
+
+// ---- block-wide bitonic sort, descending, of n2 (power of two) u64 keys in shared memory ----
+__device__ __forceinline__ void orbfe_block_sort_desc(unsigned long long* s, int n2) {
+  for (int k = 2; k <= n2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s[i], b = s[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) { s[i] = b; s[ixj] = a; }
+        }
+      }
+    }
+  __syncthreads();
+}
+
+#ifdef ORBFE_EMU
+#define ORBFE_DYN_SMEM(name) unsigned char* name = emu::S().dyn_smem
+#else
+#define ORBFE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif

@@ -1,0 +1,373 @@
+"""ctypes binding of liborbfe.so (include/orbfe.h) + Python mirrors of the reference's C++ front-end
+interface, used by tests/ and bench.py.
+
+The reference is C++ (its drop-in shim is include/orbfe_shim.hpp); this module mirrors the same
+call surface for Python callers:
+
+    ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST).Compute(image, mask)
+                                          -> src/orb_features/orb_extractor.h:25-93
+    ComputeStereoMatches(left, right, ...) -> Frame::ComputeStereoMatches, src/data/frame.cpp:406-577
+    OrbMatcher(nnratio, checkOri).Search*  -> src/orb_features/orb_matcher.h:14-119
+
+Everything computes on the GPU through the C ABI.  There is NO CPU fallback: if the CUDA library
+cannot be loaded, or no CUDA device is visible, calls raise OrbfeError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28  # cv::KeyPoint
+
+TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30  # orb_matcher.cpp:5-7
+
+
+class OrbfeError(RuntimeError):
+    pass
+
+
+class _Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("max_width", C.c_int32),
+                ("max_height", C.c_int32), ("max_images", C.c_int32)]
+
+
+EXPORTS = [
+    "orbfe_last_error", "orbfe_version", "orbfe_device_count", "orbfe_extractor_create", "orbfe_extractor_destroy",
+    "orbfe_extractor_tables", "orbfe_extractor_max_keypoints", "orbfe_extract", "orbfe_extract_batch",
+    "orbfe_pyramid_level", "orbfe_upload", "orbfe_run", "orbfe_run_stereo", "orbfe_download", "orbfe_sync",
+    "orbfe_event_record", "orbfe_event_elapsed_ms", "orbfe_set_stage_timing", "orbfe_launch_count",
+    "orbfe_debug_candidates", "orbfe_debug_level_keypoints", "orbfe_debug_blurred", "orbfe_stereo_match",
+    "orbfe_descriptor_distance", "orbfe_frame_create", "orbfe_frame_destroy", "orbfe_features_in_area",
+    "orbfe_search_for_initialization", "orbfe_search_by_projection_mappoints",
+    "orbfe_search_by_projection_lastframe",
+]
+
+_libs = {}
+vp = C.c_void_p
+
+
+def load(path=None, _test_emulation=False):
+    """Loads the C-ABI library.  `path=None` = the in-tree product build (compiled on demand with
+    nvcc).  The emulated test build under tests/emu is refused unless a test asks for it."""
+    if path is None:
+        path = _build.LIB
+        if not os.path.exists(path):
+            _build.build()
+    path = os.path.abspath(path)
+    if path in _libs:
+        return _libs[path]
+    try:
+        L = C.CDLL(path)
+    except OSError as e:  # fail loudly: no fallback
+        raise OrbfeError(f"cannot load the CUDA library {path}: {e}") from e
+    L.orbfe_last_error.restype = C.c_char_p
+    L.orbfe_version.restype = C.c_char_p
+    L.orbfe_launch_count.restype = C.c_longlong
+    L.orbfe_launch_count.argtypes = [vp]
+    if b"EMULATED" in L.orbfe_version() and not _test_emulation:
+        raise OrbfeError("refusing to load the emulated TEST build as the product library")
+    i, f, sz = C.c_int, C.c_float, C.c_size_t
+    L.orbfe_extractor_create.argtypes = [C.POINTER(_Params), i, C.POINTER(vp)]
+    L.orbfe_extractor_destroy.argtypes = [vp]
+    L.orbfe_extractor_tables.argtypes = [vp] * 7
+    L.orbfe_extractor_max_keypoints.argtypes = [vp]
+    L.orbfe_extract.argtypes = [vp, vp, i, i, sz, vp, vp, i, vp]
+    L.orbfe_extract_batch.argtypes = [vp, vp, i, i, i, sz, vp, vp, i, vp]
+    L.orbfe_pyramid_level.argtypes = [vp, i, i, vp, sz, vp, vp]
+    L.orbfe_upload.argtypes = [vp, i, vp, i, i, i, sz]
+    L.orbfe_run.argtypes = [vp, i]
+    L.orbfe_run_stereo.argtypes = [vp, i, f, f]
+    L.orbfe_download.argtypes = [vp, i, vp, vp, i, vp, vp, vp]
+    L.orbfe_sync.argtypes = [vp]
+    L.orbfe_event_record.argtypes = [vp, i]
+    L.orbfe_event_elapsed_ms.argtypes = [vp, i, i, vp]
+    L.orbfe_set_stage_timing.argtypes = [vp, i]
+    L.orbfe_debug_candidates.argtypes = [vp, i, i, vp, i, vp]
+    L.orbfe_debug_level_keypoints.argtypes = [vp, i, i, vp, i, vp]
+    L.orbfe_debug_blurred.argtypes = [vp, i, i, vp, sz, vp, vp]
+    L.orbfe_stereo_match.argtypes = [vp, vp, i, vp, vp, i, vp, vp, f, f, vp, vp, vp]
+    L.orbfe_descriptor_distance.argtypes = [i, vp, vp, i, vp]
+    L.orbfe_frame_create.argtypes = [i, i, vp, vp, vp, f, f, f, f, i, vp, C.POINTER(vp)]
+    L.orbfe_frame_destroy.argtypes = [vp]
+    L.orbfe_features_in_area.argtypes = [vp, f, f, f, i, i, vp, i, vp]
+    L.orbfe_search_for_initialization.argtypes = [vp, vp, vp, vp, i, f, i, vp]
+    L.orbfe_search_by_projection_mappoints.argtypes = [vp, i] + [vp] * 9 + [i, f, vp, vp]
+    L.orbfe_search_by_projection_lastframe.argtypes = [vp, i] + [vp] * 8 + [f, i, i, vp, f, i, vp, vp]
+    _libs[path] = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(vp) if a is not None else None
+
+
+def _check(L, rc, allow=()):
+    if rc != 0 and rc not in allow:
+        raise OrbfeError(f"orbfe error {rc}: {L.orbfe_last_error().decode(errors='replace')}")
+    return rc
+
+
+def device_count(lib=None):
+    return (lib or load()).orbfe_device_count()
+
+
+class ORBextractor:
+    """Mirror of ORBextractor (src/orb_features/orb_extractor.h:25-93)."""
+
+    def __init__(self, nfeatures=2000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, device=0,
+                 max_images=1, max_size=None, lib=None):
+        self.L = lib or load()
+        self.nfeatures, self.nlevels, self.max_images = nfeatures, nlevels, max_images
+        w, h = (max_size or (0, 0))
+        prm = _Params(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, w, h, max_images)
+        self.h = vp()
+        _check(self.L, self.L.orbfe_extractor_create(C.byref(prm), device, C.byref(self.h)))
+        n = nlevels
+        self._scale, self._inv, self._s2, self._is2 = (np.zeros(n, np.float32) for _ in range(4))
+        self._fpl = np.zeros(n, np.int32)
+        nl = C.c_int()
+        _check(self.L, self.L.orbfe_extractor_tables(self.h, C.byref(nl), _p(self._scale), _p(self._inv), _p(self._s2),
+                                                    _p(self._is2), _p(self._fpl)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.orbfe_extractor_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # -- orb_extractor.h:46-58
+    def GetLevels(self): return self.nlevels
+    def GetScaleFactor(self): return float(self._scale[1]) if self.nlevels > 1 else 1.0
+    def GetScaleFactors(self): return self._scale.copy()
+    def GetInverseScaleFactors(self): return self._inv.copy()
+    def GetScaleSigmaSquares(self): return self._s2.copy()
+    def GetInverseScaleSigmaSquares(self): return self._is2.copy()
+    def features_per_level(self): return self._fpl.copy()
+
+    def max_keypoints(self):
+        return self.L.orbfe_extractor_max_keypoints(self.h)
+
+    def Compute(self, image, mask=None):
+        """ORBextractor::Compute(image, mask, keypoints, descriptors) (orb_extractor.cpp:985-1049).
+        Returns (keypoints[KP_DTYPE], descriptors[N,32] u8); mask is ignored as in the reference."""
+        if image is None or image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        if image.dtype != np.uint8 or image.ndim != 2:
+            raise OrbfeError("image must be CV_8UC1 (2-D uint8)")  # assert at orb_extractor.cpp:994
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        cap = self.max_keypoints()
+        while True:
+            kps = np.zeros(cap, KP_DTYPE)
+            desc = np.zeros((cap, 32), np.uint8)
+            n = C.c_int()
+            rc = _check(self.L, self.L.orbfe_extract(self.h, _p(image), image.shape[1], image.shape[0], image.strides[0],
+                                                    _p(kps), _p(desc), cap, C.byref(n)), allow=(-3,))
+            if rc == 0:
+                return kps[:n.value].copy(), desc[:n.value].copy()
+            cap = max(n.value, self.max_keypoints())
+
+    __call__ = Compute  # upstream ORB-SLAM2 spells the entry point operator()
+
+    def GetImagePyramid(self, slot=0):
+        """mvImagePyramid ROI views (orb_extractor.h:58), copied from the device."""
+        out = []
+        for l in range(self.nlevels):
+            out.append(self.pyramid_level(l, slot))
+        return out
+
+    def pyramid_level(self, level, slot=0):
+        w, h = C.c_int(), C.c_int()
+        _check(self.L, self.L.orbfe_pyramid_level(self.h, slot, level, None, 0, C.byref(w), C.byref(h)))
+        a = np.empty((h.value, w.value), np.uint8)
+        _check(self.L, self.L.orbfe_pyramid_level(self.h, slot, level, _p(a), a.strides[0], C.byref(w), C.byref(h)))
+        return a
+
+    # -- stage taps for parity tests
+    def debug_candidates(self, level, slot=0):
+        out = np.zeros(1 << 18, KP_DTYPE)
+        n = C.c_int()
+        _check(self.L, self.L.orbfe_debug_candidates(self.h, slot, level, _p(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def debug_level_keypoints(self, level, slot=0):
+        out = np.zeros(1 << 16, KP_DTYPE)
+        n = C.c_int()
+        _check(self.L, self.L.orbfe_debug_level_keypoints(self.h, slot, level, _p(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def debug_blurred(self, level, slot=0):
+        w, h = C.c_int(), C.c_int()
+        _check(self.L, self.L.orbfe_debug_blurred(self.h, slot, level, None, 0, C.byref(w), C.byref(h)))
+        a = np.empty((h.value, w.value), np.uint8)
+        _check(self.L, self.L.orbfe_debug_blurred(self.h, slot, level, _p(a), a.strides[0], C.byref(w), C.byref(h)))
+        return a
+
+    # -- batched / device-resident path (bench, offline loop of examples/main_stereo.cpp:102-143)
+    def _ptr_array(self, imgs):
+        arr = (vp * len(imgs))()
+        for i, im in enumerate(imgs):
+            assert im.dtype == np.uint8 and im.ndim == 2 and im.strides[1] == 1
+            assert im.shape == imgs[0].shape and im.strides[0] == imgs[0].strides[0]
+            arr[i] = im.ctypes.data
+        return arr
+
+    def upload(self, imgs, first_slot=0):
+        arr = self._ptr_array(imgs)
+        im = imgs[0]
+        _check(self.L, self.L.orbfe_upload(self.h, first_slot, arr, len(imgs), im.shape[1], im.shape[0], im.strides[0]))
+
+    def upload_ptrs(self, ptr_array, n, w, h, stride, first_slot=0):
+        _check(self.L, self.L.orbfe_upload(self.h, first_slot, ptr_array, n, w, h, stride))
+
+    def run(self, n_imgs):
+        _check(self.L, self.L.orbfe_run(self.h, n_imgs))
+
+    def run_stereo(self, n_pairs, bf, baseline):
+        _check(self.L, self.L.orbfe_run_stereo(self.h, n_pairs, bf, baseline))
+
+    def sync(self):
+        _check(self.L, self.L.orbfe_sync(self.h))
+
+    def make_buffers(self, n_imgs, stereo=False):
+        cap = self.max_keypoints()
+        b = dict(kps=np.zeros((n_imgs, cap), KP_DTYPE), desc=np.zeros((n_imgs, cap, 32), np.uint8),
+                 n=np.zeros(n_imgs, np.int32), cap=cap, ur=None, depth=None)
+        if stereo:
+            b["ur"] = np.zeros((n_imgs, cap), np.float32)
+            b["depth"] = np.zeros((n_imgs, cap), np.float32)
+        return b
+
+    def download(self, n_imgs, buf):
+        _check(self.L, self.L.orbfe_download(self.h, n_imgs, _p(buf["kps"]), _p(buf["desc"]), buf["cap"], _p(buf["n"]),
+                                            _p(buf["ur"]), _p(buf["depth"])))
+        return buf
+
+    def extract_batch(self, imgs):
+        buf = self.make_buffers(len(imgs))
+        arr = self._ptr_array(imgs)
+        im = imgs[0]
+        _check(self.L, self.L.orbfe_extract_batch(self.h, arr, len(imgs), im.shape[1], im.shape[0], im.strides[0],
+                                                 _p(buf["kps"]), _p(buf["desc"]), buf["cap"], _p(buf["n"])))
+        return [(buf["kps"][i, :buf["n"][i]].copy(), buf["desc"][i, :buf["n"][i]].copy()) for i in range(len(imgs))]
+
+    def event_record(self, slot):
+        _check(self.L, self.L.orbfe_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        _check(self.L, self.L.orbfe_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
+    def set_stage_timing(self, on):
+        _check(self.L, self.L.orbfe_set_stage_timing(self.h, int(on)))
+
+    def launch_count(self):
+        return self.L.orbfe_launch_count(self.h)
+
+
+def ComputeStereoMatches(left, right, kps_left, desc_left, kps_right, desc_right, bf, baseline):
+    """Frame::ComputeStereoMatches (src/data/frame.cpp:406-577).  `left`/`right` are the two
+    ORBextractor objects that produced the keypoints (their device pyramids are read).
+    Returns (n_matched, stereo_coords_[N], depths_[N])."""
+    L = left.L
+    kl = np.ascontiguousarray(kps_left, KP_DTYPE); kr = np.ascontiguousarray(kps_right, KP_DTYPE)
+    dl = np.ascontiguousarray(desc_left, np.uint8); dr = np.ascontiguousarray(desc_right, np.uint8)
+    ur = np.zeros(len(kl), np.float32)
+    dp = np.zeros(len(kl), np.float32)
+    n = C.c_int()
+    _check(L, L.orbfe_stereo_match(left.h, right.h, len(kl), _p(kl), _p(dl), len(kr), _p(kr), _p(dr), bf, baseline,
+                                   _p(ur), _p(dp), C.byref(n)))
+    return n.value, ur, dp
+
+
+class Frame:
+    """The matcher's view of a Frame: undistorted keypoints, descriptors, stereo coordinates, image
+    bounds, scale table; owns the 64x48 feature grid (frame.cpp:234-248, 339-403) on the GPU."""
+
+    def __init__(self, kps_un, desc, scale_factors, bounds, u_right=None, device=0, lib=None):
+        self.L = lib or load()
+        self.kps = np.ascontiguousarray(kps_un, KP_DTYPE)
+        self.desc = np.ascontiguousarray(desc, np.uint8)
+        self.scale = np.ascontiguousarray(scale_factors, np.float32)
+        self.ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+        self.bounds = tuple(float(b) for b in bounds)
+        self.h = vp()
+        _check(self.L, self.L.orbfe_frame_create(device, len(self.kps), _p(self.kps), _p(self.desc), _p(self.ur),
+                                                self.bounds[0], self.bounds[1], self.bounds[2], self.bounds[3],
+                                                len(self.scale), _p(self.scale), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.orbfe_frame_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def GetFeaturesInArea(self, x, y, r, minLevel=-1, maxLevel=-1):
+        out = np.zeros(len(self.kps) + 1, np.int32)
+        n = C.c_int()
+        _check(self.L, self.L.orbfe_features_in_area(self.h, x, y, r, minLevel, maxLevel, _p(out), len(out), C.byref(n)))
+        return out[:n.value].copy()
+
+
+def DescriptorDistance(a, b, device=0, lib=None):
+    """static OrbMatcher::DescriptorDistance (orb_matcher.cpp:1630-1646), batched over rows."""
+    L = lib or load()
+    a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+    b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+    d = np.zeros(len(a), np.int32)
+    _check(L, L.orbfe_descriptor_distance(device, _p(a), _p(b), len(a), _p(d)))
+    return d
+
+
+class OrbMatcher:
+    """Mirror of OrbMatcher (src/orb_features/orb_matcher.h:14-119) for the hot-path routines."""
+    TH_LOW, TH_HIGH, HISTO_LENGTH = TH_LOW, TH_HIGH, HISTO_LENGTH
+
+    def __init__(self, nnratio=0.6, checkOri=True):
+        self.nnratio, self.checkOri = float(nnratio), bool(checkOri)
+
+    DescriptorDistance = staticmethod(DescriptorDistance)
+
+    def SearchForInitialization(self, F1, F2, vbPrevMatched, windowSize=10):
+        """orb_matcher.cpp:264-382 -> (nmatches, vnMatches12, updated vbPrevMatched)."""
+        pm = np.ascontiguousarray(vbPrevMatched, np.float32).copy()
+        m12 = np.zeros(len(F1.kps), np.int32)
+        n = C.c_int()
+        _check(F1.L, F1.L.orbfe_search_for_initialization(F1.h, F2.h, _p(pm), _p(m12), windowSize, self.nnratio,
+                                                         int(self.checkOri), C.byref(n)))
+        return n.value, m12, pm
+
+    def SearchByProjectionMapPoints(self, F, valid, proj_x, proj_y, proj_xr, pred_level, view_cos, mp_desc, has_obs,
+                                    occupied, th=1):
+        """SearchByProjection(Frame&, const vector<MapPoint*>&, th) (orb_matcher.cpp:13-111)."""
+        a = lambda v, t: np.ascontiguousarray(v, t)
+        assigned = np.zeros(len(F.kps), np.int32)
+        n = C.c_int()
+        args = [a(valid, np.uint8), a(proj_x, np.float32), a(proj_y, np.float32), a(proj_xr, np.float32),
+                a(pred_level, np.int32), a(view_cos, np.float32), a(mp_desc, np.uint8), a(has_obs, np.uint8),
+                a(occupied, np.uint8)]
+        _check(F.L, F.L.orbfe_search_by_projection_mappoints(F.h, len(args[0]), *[_p(x) for x in args], int(th),
+                                                            self.nnratio, _p(assigned), C.byref(n)))
+        return n.value, assigned
+
+    def SearchByProjectionLastFrame(self, Cur, valid, u, v, invzc, last_octave, last_angle, mp_desc, has_obs, bf,
+                                    forward, backward, occupied, th):
+        """SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (orb_matcher.cpp:1312-1453)."""
+        a = lambda x, t: np.ascontiguousarray(x, t)
+        assigned = np.zeros(len(Cur.kps), np.int32)
+        n = C.c_int()
+        args = [a(valid, np.uint8), a(u, np.float32), a(v, np.float32), a(invzc, np.float32),
+                a(last_octave, np.int32), a(last_angle, np.float32), a(mp_desc, np.uint8), a(has_obs, np.uint8)]
+        _check(Cur.L, Cur.L.orbfe_search_by_projection_lastframe(Cur.h, len(args[0]), *[_p(x) for x in args], bf,
+                                                                int(forward), int(backward),
+                                                                _p(a(occupied, np.uint8)), th, int(self.checkOri),
+                                                                _p(assigned), C.byref(n)))
+        return n.value, assigned
