@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- stereo frames/s of the ORB front-end hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one pass of the hot path over one batch of `--pairs` synthetic KITTI-shaped stereo
+pairs (1241x376 u8): ORB extraction of both images (8-level pyramid, grid FAST, quad-tree, blur,
+orientation + rBRIEF) + Frame::ComputeStereoMatches, on one GPU per rank.  Frames are independent,
+so ranks share nothing (no collective on the data path): weak scaling.
+
+  value : stereo pairs/s with the batch already resident in HBM (device-side CUDA events on the
+          library's own stream, max over ranks).
+  e2e   : the same metric through the C-ABI calls a user makes (orbfe_upload from pinned host
+          memory -> orbfe_run -> orbfe_run_stereo -> orbfe_download to host arrays), host<->device
+          copies inside the timed region, wall clock, max over ranks.
+  roofline      : per-stage CUDA-event times of the timed region against the measured HBM peak.
+  cpu_baseline  : the oracle (CPU restatement of the reference path; the reference itself cannot be
+                  built here) on the box's host cores, bounded sample; rank 0 at N=1 only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+W, H = 1241, 376
+NFEATURES, SCALE, NLEVELS, INI_TH, MIN_TH = 2000, 1.2, 8, 20, 7   # config/kitti_config_stereo.json
+BF, FX = 386.1448, 718.856
+METRIC = "stereo frames/s, ORB extract+stereo match 1241x376"
+UNIT = "stereo pairs/s"
+
+
+def level_pixels(w, h, nlevels=NLEVELS):
+    """sum of pyramid level pixels, sizes exactly as orb_extractor.cpp:1055-1056"""
+    s, tot = np.float32(1.0), 0
+    for l in range(nlevels):
+        inv = np.float32(1.0) / s
+        lw = int(np.rint(np.float32(w) * inv)); lh = int(np.rint(np.float32(h) * inv))
+        tot += lw * lh
+        s = np.float32(np.float64(s) * np.float64(np.float32(SCALE)))
+    return tot
+
+
+def algorithmic_bytes_per_image(w=W, h=H):
+    """compulsory traffic per image, u8 = 1 B/px."""
+    I, P = w * h, level_pixels(w, h)
+    return {"pyramid": I + P, "fast": P, "blur": 2 * P, "extract_total": I + 4 * P}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    FIELDS = ["clocks.sm", "clocks.max.sm", "clocks_event_reasons.hw_slowdown",
+              "clocks_event_reasons.hw_thermal_slowdown", "clocks_event_reasons.sw_thermal_slowdown",
+              "clocks_event_reasons.sw_power_cap"]
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + ",".join(self.FIELDS),
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_pairs(n, seed0):
+    from slam_framework_b200 import synth
+    return [synth.stereo_pair(H, W, seed=seed0 + i) for i in range(n)]
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_throughput(pairs, n_pairs, threads, pair_threads=1):
+    """oracle batch driver (oracle/orb_oracle_batch.cpp) over n_pairs pairs cycling through `pairs`."""
+    import oracle_lib as O
+    L = O.lib()
+    lp = (ctypes.c_void_p * n_pairs)()
+    rp = (ctypes.c_void_p * n_pairs)()
+    for i in range(n_pairs):
+        l, r = pairs[i % len(pairs)]
+        lp[i], rp[i] = l.ctypes.data, r.ctypes.data
+    kps, mt = ctypes.c_long(), ctypes.c_long()
+    sec = L.orc_bench_stereo_batch(lp, rp, n_pairs, W, H, NFEATURES, SCALE, NLEVELS, INI_TH, MIN_TH, BF, BF / FX,
+                                   threads, pair_threads, ctypes.byref(kps), ctypes.byref(mt))
+    return n_pairs / sec, sec, kps.value, mt.value
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The
+    reference cannot be compiled in this image (OpenCV C++/Eigen/catkin absent), so
+    this is the oracle port, with one worker per host core over independent pairs."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    pairs = make_pairs(min(8, max(2, cores)), 0)
+    per_step = max(cores, 4)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_throughput(pairs, per_step, cores)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(args.steps):
+        cpu_reference_throughput(pairs, per_step, cores)
+        done += per_step
+    sec = time.perf_counter() - t0
+    val = done / sec
+    sample = f"{per_step} stereo pairs per step x {args.steps} steps, one oracle worker per host core"
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+           "config": {"workload": "configs[1]: synthetic KITTI-size stereo pair, L+R ORB extraction + ComputeStereoMatches",
+                      "pairs_per_step": per_step, "nfeatures": NFEATURES, "levels": NLEVELS},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from slam_framework_b200 import orbfe
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    L = orbfe.load()
+    B = args.pairs
+    n_img = 2 * B
+    ex = orbfe.ORBextractor(NFEATURES, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_images=n_img, max_size=(W, H), lib=L)
+    # synthetic input: `distinct` different pairs per rank, tiled to the batch (frames are independent)
+    distinct = min(B, args.distinct)
+    pairs = make_pairs(distinct, 10_000 * rank)
+    host = torch.empty((n_img, H, W), dtype=torch.uint8, pin_memory=True)
+    hnp = host.numpy()
+    for p in range(B):
+        l, r = pairs[p % distinct]
+        hnp[2 * p], hnp[2 * p + 1] = l, r
+    ptrs = (ctypes.c_void_p * n_img)(*[hnp[i].ctypes.data for i in range(n_img)])
+    baseline = BF / FX
+    buf = ex.make_buffers(n_img, stereo=True)
+
+    def step_resident():
+        ex.run(n_img)
+        ex.run_stereo(B, BF, baseline)
+
+    def step_e2e():
+        ex.upload_ptrs(ptrs, n_img, W, H, W)
+        ex.run(n_img)
+        ex.run_stereo(B, BF, baseline)
+        ex.download(n_img, buf)
+
+    # ---- device-resident leg -----------------------------------------------------------------
+    ex.upload_ptrs(ptrs, n_img, W, H, W)
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    ex.sync()
+    ex.set_stage_timing(True)
+    ex.stage_summary()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    launches0 = ex.launch_count()
+    ex.event_record(0)
+    for _ in range(args.steps):
+        step_resident()
+    ex.event_record(1)
+    ex.sync()
+    barrier()
+    ms = max_over_ranks(ex.event_elapsed_ms(0, 1))
+    launches = ex.launch_count() - launches0
+    stages, runs = ex.stage_summary()
+    ex.set_stage_timing(False)
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end leg (host buffers, copies inside the timed region) ---------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    ex.sync()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop()
+    e2e_value = world * B * args.steps / t_e2e
+    cap = buf["cap"]
+    h2d = n_img * H * W
+    d2h = n_img * cap * (28 + 32 + 4 + 4) + n_img * 4 + 4
+    n_kp = int(buf["n"].sum())
+    n_matched = int((buf["ur"][0::2] >= 0).sum())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline (dominant stage of the timed region, CUDA events on the library's stream) ------
+    peak, peak_src = measured_peak()
+    alg = algorithmic_bytes_per_image()
+    kp_img = n_kp / n_img
+    stage_bytes = {  # algorithmic bytes per image for each stage (DESIGN.md "Kernels")
+        "pyramid": alg["pyramid"], "fast": alg["fast"], "blur": alg["blur"],
+        "quadtree": None, "describe": None, "stereo_search": None, "stereo_median": None}
+    stage_launches = {"pyramid": NLEVELS, "fast": 1, "quadtree": 1, "blur": 1, "describe": 1, "stereo_search": 1,
+                      "stereo_median": 1}
+    per_stage = {}
+    for k, tot in stages.items():
+        t_step = tot / max(runs, 1)
+        ent = {"ms_per_step": t_step, "share": tot / max(sum(stages.values()), 1e-9), "launches_per_step": stage_launches[k]}
+        if stage_bytes[k] is not None and t_step > 0:
+            ent["alg_bytes_per_step"] = stage_bytes[k] * n_img
+            ent["gbs"] = stage_bytes[k] * n_img / (t_step * 1e-3) / 1e9
+            ent["frac_of_hbm_peak"] = ent["gbs"] / peak
+        per_stage[k] = ent
+    dom = max(stages, key=lambda k: stages[k])
+    dom_ms = stages[dom] / max(runs, 1)
+    if stage_bytes[dom] is not None:
+        dom_bytes = stage_bytes[dom] * n_img
+    else:  # integer/latency-bound stages: their compulsory HBM traffic is the candidate / keypoint records
+        dom_bytes = int({"quadtree": 4 * 13000 + 4 * kp_img, "describe": (4 + 28 + 32) * kp_img,
+                         "stereo_search": 2 * (28 + 32) * kp_img, "stereo_median": 12 * kp_img}[dom] * n_img)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    whole = alg["extract_total"] * n_img / (ms / args.steps * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": dom_bytes // stage_launches[dom], "launch_ms": dom_ms / stage_launches[dom],
+                "whole_step": {"alg_bytes": alg["extract_total"] * n_img, "gbs": whole, "frac": whole / peak},
+                "stages": per_stage}
+
+    # ---- p50 latency of ONE pair through the drop-in calls (2 handles, 2 host threads, frame.cpp:86-89)
+    latency = None
+    if world == 1 and not args.no_latency:
+        eL = orbfe.ORBextractor(NFEATURES, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, lib=L)
+        eR = orbfe.ORBextractor(NFEATURES, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, lib=L)
+        l, r = pairs[0]
+        lat = []
+        for it in range(60):
+            t0 = time.perf_counter()
+            res = [None, None]
+            th = threading.Thread(target=lambda: res.__setitem__(1, eR.Compute(r)))
+            th.start()
+            res[0] = eL.Compute(l)
+            th.join()
+            orbfe.ComputeStereoMatches(eL, eR, res[0][0], res[0][1], res[1][0], res[1][1], BF, baseline)
+            if it >= 10:
+                lat.append((time.perf_counter() - t0) * 1e3)
+        latency = {"p50_ms_per_frame": statistics.median(lat), "min_ms": min(lat), "runs": len(lat),
+                   "path": "2x orbfe_extract (two host threads) + orbfe_stereo_match, host in/out"}
+        eL.close(); eR.close()
+
+    # ---- CPU baseline (oracle port on the host cores; bounded sample) ----------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = host_cores()
+        v1, s1, _, _ = cpu_reference_throughput(pairs, cores, cores)
+        reps = int(min(max(12.0 / max(s1, 1e-3), 1), 40))
+        n = cores * reps
+        v, sec, ckps, cmt = cpu_reference_throughput(pairs, n, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} stereo pairs ({sec:.1f} s), one oracle worker per host core; reference itself not buildable here"}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u8", "data": "synthetic",
+           "config": {"workload": "configs[1]: synthetic KITTI-size stereo pair (1241x376), L+R ORB extraction "
+                                  "(nFeatures 2000, 8 levels, 1.2, FAST 20/7) + ComputeStereoMatches, batched",
+                      "pairs_per_step_per_gpu": B, "distinct_pairs": distinct, "parallelism": f"frames sharded x{world}, no collective",
+                      "l2": "per-step working set (images+pyramids+blur) ~%d MB > 126 MB L2" % ((n_img * (H * W + 2 * 1738559)) >> 20)},
+           "gpu_launches": int(launches),
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": 1e3 * t_e2e / args.steps},
+           "clocks": clocks, "roofline": roofline,
+           "keypoints_per_image": kp_img, "stereo_matches_per_pair": n_matched / B}
+    if cpu:
+        out["cpu_baseline"] = cpu
+    if latency:
+        out["latency"] = latency
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=64, help="stereo pairs per step per GPU")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs tiled into the batch")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -108,9 +108,14 @@ int orbfe_sync(orbfe_extractor* ex);
  * between two recorded slots (after orbfe_sync). */
 int orbfe_event_record(orbfe_extractor* ex, int slot);
 int orbfe_event_elapsed_ms(orbfe_extractor* ex, int slot_a, int slot_b, float* ms);
-/* when enabled, orbfe_run/orbfe_run_stereo record one event per stage (slots 32..47):
- * 32 start, 33 pyramid, 34 fast, 35 octree, 36 blur, 37 describe, 38 stereo search, 39 median */
+/* when enabled, every orbfe_run (+ the orbfe_run_stereo that follows it) brackets its stages
+ * with CUDA events on the handle's stream, kept in a ring of the last 64 runs. */
 int orbfe_set_stage_timing(orbfe_extractor* ex, int enabled);
+/* sums the per-stage device time over the runs recorded since the last summary (at most 64) and
+ * clears the ring.  ms_sum[7] = pyramid, FAST, quad-tree, blur, orientation+descriptor,
+ * stereo search, stereo median.  Synchronises the handle's stream. */
+#define ORBFE_NUM_STAGES 7
+int orbfe_stage_summary(orbfe_extractor* ex, float* ms_sum, int* n_runs);
 /* number of kernel launches issued by this handle since creation */
 long long orbfe_launch_count(const orbfe_extractor* ex);
 /* stage outputs of slot `slot` for per-stage parity tests: FAST candidates of a level

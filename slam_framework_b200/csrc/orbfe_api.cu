@@ -85,6 +85,10 @@ struct orbfe_extractor {
   float* h_depth = nullptr;
   StereoPair* h_pairs = nullptr;
   cudaEvent_t ev[64] = {};
+  cudaEvent_t stageEv[64][8] = {};  // ring of per-run stage brackets
+  unsigned char stageHas[64] = {};  // 1 = extract recorded, 2 = stereo recorded too
+  int stageRuns = 0;                // runs recorded since the last summary
+  int pairsCached = 0;              // d_pairs holds the same-handle table for this many pairs
   bool stageTiming = false;
   long long launches = 0;
 };
@@ -136,6 +140,7 @@ static void free_arena(orbfe_extractor* ex) {
   ex->d_depth = nullptr; ex->d_sad = nullptr; ex->d_nMatched = nullptr;
   ex->h_n = nullptr; ex->h_kps = nullptr; ex->h_desc = nullptr; ex->h_uR = nullptr; ex->h_depth = nullptr;
   ex->h_pairs = nullptr;
+  ex->pairsCached = 0;
   ex->configured = false;
 }
 
@@ -296,32 +301,41 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   return ORBFE_OK;
 }
 
-static int stage_event(orbfe_extractor* ex, int slot) {
-  if (ex->stageTiming) CUDA_TRY(cudaEventRecord(ex->ev[slot], ex->stream));
+// stage brackets: event k of the current ring entry (0 start, 1 pyramid, 2 FAST, 3 quad-tree,
+// 4 blur, 5 describe, 6 stereo search, 7 stereo median)
+static int stage_event(orbfe_extractor* ex, int k) {
+  if (!ex->stageTiming) return ORBFE_OK;
+  if (k == 0) { ex->stageRuns++; ex->stageHas[(ex->stageRuns - 1) & 63] = 0; }
+  if (ex->stageRuns == 0) return ORBFE_OK;
+  const int set = (ex->stageRuns - 1) & 63;
+  if (!ex->stageEv[set][k]) CUDA_TRY(cudaEventCreate(&ex->stageEv[set][k]));
+  CUDA_TRY(cudaEventRecord(ex->stageEv[set][k], ex->stream));
+  if (k == 5) ex->stageHas[set] = 1;
+  if (k == 7 && ex->stageHas[set] == 1) ex->stageHas[set] = 2;
   return ORBFE_OK;
 }
 
 static int enqueue_extract(orbfe_extractor* ex, int n) {
   const Geom& g = ex->g;
   int rc;
-  if ((rc = stage_event(ex, 32))) return rc;
+  if ((rc = stage_event(ex, 0))) return rc;
   for (int l = 0; l < g.nlevels; ++l)
     ORBFE_LAUNCH(ex, k_pyramid_level, dim3(g.lv[l].pyrBlocks, n), dim3(ORBFE_PYR_THREADS), 0, g, l, ex->d_img, ex->d_pyr,
                  ex->d_lut);
-  if ((rc = stage_event(ex, 33))) return rc;
+  if ((rc = stage_event(ex, 1))) return rc;
   if (g.totalCells > 0)
     ORBFE_LAUNCH(ex, k_fast_cells, dim3(g.totalCells, n), dim3(ORBFE_FAST_THREADS), ex->fastSmem, g, ex->d_pyr,
                  ex->d_cellCnt, ex->d_cellList, ex->fastTilePitch, ex->fastMaxInnerH);
-  if ((rc = stage_event(ex, 34))) return rc;
+  if ((rc = stage_event(ex, 2))) return rc;
   ORBFE_LAUNCH(ex, k_octree, dim3(g.nlevels, n), dim3(ORBFE_OCT_THREADS), ex->octSmem, g, ex->d_cellCnt, ex->d_cellList,
                ex->oct, ex->d_lvlKp, ex->d_lvlCnt, ex->d_err);
-  if ((rc = stage_event(ex, 35))) return rc;
+  if ((rc = stage_event(ex, 3))) return rc;
   ORBFE_LAUNCH(ex, k_blur, dim3(g.totalTiles, n), dim3(ORBFE_BLUR_THREADS), 0, g, ex->d_pyr, ex->d_blur);
-  if ((rc = stage_event(ex, 36))) return rc;
+  if ((rc = stage_event(ex, 4))) return rc;
   ORBFE_LAUNCH(ex, k_orient_describe, dim3((g.totalOut + ORBFE_DESC_THREADS / 32 - 1) / (ORBFE_DESC_THREADS / 32), n),
                dim3(ORBFE_DESC_THREADS), 0, g, ex->d_pyr, ex->d_blur, ex->d_lvlKp, ex->d_lvlCnt, ex->d_kps, ex->d_desc,
                ex->d_nKp);
-  if ((rc = stage_event(ex, 37))) return rc;
+  if ((rc = stage_event(ex, 5))) return rc;
   CUDA_TRY(cudaGetLastError());
   return ORBFE_OK;
 }
@@ -405,6 +419,8 @@ int orbfe_extractor_destroy(orbfe_extractor* ex) {
   if (ex->stream) cudaStreamSynchronize(ex->stream);
   free_arena(ex);
   for (int i = 0; i < 64; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
+  for (int i = 0; i < 64; ++i)
+    for (int k = 0; k < 8; ++k) if (ex->stageEv[i][k]) cudaEventDestroy(ex->stageEv[i][k]);
   if (ex->stream) cudaStreamDestroy(ex->stream);
   delete ex;
   return ORBFE_OK;
@@ -472,13 +488,12 @@ static void fill_pairs_same_handle(orbfe_extractor* ex, int n_pairs) {
 
 static int enqueue_stereo(orbfe_extractor* ex, int n_pairs, float bf, float baseline) {
   const Geom& g = ex->g;
-  CUDA_TRY(cudaMemcpyAsync(ex->d_pairs, ex->h_pairs, (size_t)n_pairs * sizeof(StereoPair), cudaMemcpyHostToDevice, ex->stream));
   ORBFE_LAUNCH(ex, k_stereo_search, dim3((g.totalOut + ORBFE_ST_THREADS / 32 - 1) / (ORBFE_ST_THREADS / 32), n_pairs),
                dim3(ORBFE_ST_THREADS), 0, g, ex->d_pairs, bf, baseline, g.totalOut);
   int rc;
-  if ((rc = stage_event(ex, 38))) return rc;
+  if ((rc = stage_event(ex, 6))) return rc;
   ORBFE_LAUNCH(ex, k_stereo_median, dim3(n_pairs), dim3(ORBFE_ST_THREADS), 0, ex->d_pairs, g.totalOut, ex->d_nMatched);
-  if ((rc = stage_event(ex, 39))) return rc;
+  if ((rc = stage_event(ex, 7))) return rc;
   CUDA_TRY(cudaGetLastError());
   return ORBFE_OK;
 }
@@ -490,9 +505,13 @@ int orbfe_run_stereo(orbfe_extractor* ex, int n_pairs, float bf, float baseline)
   if (!(baseline > 0.f) || !(bf > 0.f)) return orbfe_fail(ORBFE_ERR_INVALID, "bf and baseline must be positive");
   if (n_pairs == 0) return ORBFE_OK;
   CUDA_TRY(cudaSetDevice(ex->device));
-  // h_pairs is rewritten only when the previous table has been consumed
-  CUDA_TRY(cudaStreamSynchronize(ex->stream));
-  fill_pairs_same_handle(ex, n_pairs);
+  if (ex->pairsCached < n_pairs) {
+    // h_pairs is rewritten only when the previous table has been consumed
+    CUDA_TRY(cudaStreamSynchronize(ex->stream));
+    fill_pairs_same_handle(ex, n_pairs);
+    CUDA_TRY(cudaMemcpyAsync(ex->d_pairs, ex->h_pairs, (size_t)n_pairs * sizeof(StereoPair), cudaMemcpyHostToDevice, ex->stream));
+    ex->pairsCached = n_pairs;
+  }
   return enqueue_stereo(ex, n_pairs, bf, baseline);
 }
 
@@ -589,6 +608,31 @@ int orbfe_event_elapsed_ms(orbfe_extractor* ex, int a, int b, float* ms) {
 int orbfe_set_stage_timing(orbfe_extractor* ex, int enabled) {
   if (!ex) return orbfe_fail(ORBFE_ERR_INVALID, "null extractor handle");
   ex->stageTiming = enabled != 0;
+  return ORBFE_OK;
+}
+int orbfe_stage_summary(orbfe_extractor* ex, float* ms_sum, int* n_runs) {
+  if (!ex || !ms_sum || !n_runs) return orbfe_fail(ORBFE_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(ex->device));
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  for (int k = 0; k < ORBFE_NUM_STAGES; ++k) ms_sum[k] = 0.f;
+  const int runs = ex->stageRuns < 64 ? ex->stageRuns : 64;
+  for (int r = 0; r < runs; ++r) {
+    const int set = (ex->stageRuns - 1 - r) & 63;
+    const int last = ex->stageHas[set] == 2 ? 7 : (ex->stageHas[set] == 1 ? 5 : 0);
+    for (int k = 1; k <= last; ++k) {
+      if (k == 6) {  // the stereo launch follows the describe bracket (+ the pair-table copy)
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ex->stageEv[set][5], ex->stageEv[set][6]));
+        ms_sum[5] += ms;
+        continue;
+      }
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, ex->stageEv[set][k - 1], ex->stageEv[set][k]));
+      ms_sum[k - 1] += ms;
+    }
+  }
+  *n_runs = runs;
+  ex->stageRuns = 0;
   return ORBFE_OK;
 }
 long long orbfe_launch_count(const orbfe_extractor* ex) { return ex ? ex->launches : 0; }
@@ -696,6 +740,8 @@ int orbfe_stereo_match(orbfe_extractor* left, orbfe_extractor* right, int n_left
   P.descL = left->d_desc; P.descR = right->d_desc + rslot * right->g.totalOut * 32;
   P.nL = left->d_nKp; P.nR = right->d_nKp + rslot;
   P.uR = left->d_uR; P.depth = left->d_depth; P.sad = left->d_sad;
+  ex->pairsCached = 0;
+  CUDA_TRY(cudaMemcpyAsync(ex->d_pairs, ex->h_pairs, sizeof(StereoPair), cudaMemcpyHostToDevice, ex->stream));
   int rc = enqueue_stereo(ex, 1, bf, baseline);
   if (rc) return rc;
   CUDA_TRY(cudaMemcpyAsync(ex->h_uR, ex->d_uR, (size_t)n_left * sizeof(float), cudaMemcpyDeviceToHost, ex->stream));

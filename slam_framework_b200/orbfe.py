@@ -40,7 +40,8 @@ EXPORTS = [
     "orbfe_last_error", "orbfe_version", "orbfe_device_count", "orbfe_extractor_create", "orbfe_extractor_destroy",
     "orbfe_extractor_tables", "orbfe_extractor_max_keypoints", "orbfe_extract", "orbfe_extract_batch",
     "orbfe_pyramid_level", "orbfe_upload", "orbfe_run", "orbfe_run_stereo", "orbfe_download", "orbfe_sync",
-    "orbfe_event_record", "orbfe_event_elapsed_ms", "orbfe_set_stage_timing", "orbfe_launch_count",
+    "orbfe_event_record", "orbfe_event_elapsed_ms", "orbfe_set_stage_timing", "orbfe_stage_summary",
+    "orbfe_launch_count",
     "orbfe_debug_candidates", "orbfe_debug_level_keypoints", "orbfe_debug_blurred", "orbfe_stereo_match",
     "orbfe_descriptor_distance", "orbfe_frame_create", "orbfe_frame_destroy", "orbfe_features_in_area",
     "orbfe_search_for_initialization", "orbfe_search_by_projection_mappoints",
@@ -87,6 +88,7 @@ def load(path=None, _test_emulation=False):
     L.orbfe_event_record.argtypes = [vp, i]
     L.orbfe_event_elapsed_ms.argtypes = [vp, i, i, vp]
     L.orbfe_set_stage_timing.argtypes = [vp, i]
+    L.orbfe_stage_summary.argtypes = [vp, vp, vp]
     L.orbfe_debug_candidates.argtypes = [vp, i, i, vp, i, vp]
     L.orbfe_debug_level_keypoints.argtypes = [vp, i, i, vp, i, vp]
     L.orbfe_debug_blurred.argtypes = [vp, i, i, vp, sz, vp, vp]
@@ -267,6 +269,15 @@ class ORBextractor:
 
     def set_stage_timing(self, on):
         _check(self.L, self.L.orbfe_set_stage_timing(self.h, int(on)))
+
+    STAGES = ("pyramid", "fast", "quadtree", "blur", "describe", "stereo_search", "stereo_median")
+
+    def stage_summary(self):
+        """(dict stage -> summed ms, runs) since the last call (needs set_stage_timing(True))."""
+        ms = (C.c_float * 7)()
+        n = C.c_int()
+        _check(self.L, self.L.orbfe_stage_summary(self.h, ms, C.byref(n)))
+        return dict(zip(self.STAGES, [float(x) for x in ms])), n.value
 
     def launch_count(self):
         return self.L.orbfe_launch_count(self.h)

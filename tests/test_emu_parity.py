@@ -1,0 +1,49 @@
+"""Kernel LOGIC parity on CPU: the same CUDA sources compiled against tests/emu/cuda_emu.h (a
+TEST-ONLY emulation of the CUDA subset the kernels use) are diffed against the oracle.  This is
+what lets the GPU-less container catch logic errors; the parity tests proper are test_gpu_parity.py
+(-m gpu), which run the real sm_100a build."""
+import numpy as np
+import pytest
+
+import parity_common as P
+from emu import build_emu
+from slam_framework_b200 import orbfe, synth
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return orbfe.load(build_emu.build(), _test_emulation=True)
+
+
+@pytest.mark.parametrize("h,w,seed", [(120, 400, 0), (97, 131, 1), (200, 640, 2)])
+def test_extract_small(emu, h, w, seed):
+    P.check_extract(emu, synth.frame(h, w, seed=seed), nfeatures=500)
+
+
+def test_extract_kitti_frame(emu):
+    kps, _ = P.check_extract(emu, synth.frame(seed=0))
+    assert 1900 < len(kps) < 2100
+
+
+def test_extract_strided_and_noise(emu):
+    rng = np.random.default_rng(4)
+    big = rng.integers(0, 256, (150, 420), dtype=np.uint8)
+    P.check_extract(emu, big[5:140, 7:400], nfeatures=1000)  # non-contiguous rows, dense texture
+
+
+def test_extract_flat_image_yields_nothing(emu):
+    ex = orbfe.ORBextractor(lib=emu)
+    kps, desc = ex.Compute(np.full((100, 300), 128, np.uint8))
+    assert len(kps) == 0 and desc.shape == (0, 32)
+    kps, desc = ex.Compute(np.zeros((0, 0), np.uint8))  # empty image => silent return (:990-991)
+    assert len(kps) == 0
+
+
+def test_stereo_kitti_pair(emu):
+    left, right = synth.stereo_pair(seed=0)
+    assert P.check_stereo(emu, left, right) > 300
+
+
+def test_batch_stereo_two_pairs(emu):
+    pairs = [synth.stereo_pair(160, 500, seed=s) for s in (3, 4)]
+    assert P.check_batch_stereo(emu, pairs, nfeatures=600) > 50

@@ -1,0 +1,112 @@
+"""Parity tests proper: the sm_100a build of liborbfe.so, called through the C ABI, against the CPU
+oracle on the same seeded inputs (BASELINE.json configs 1-3), plus size-independent properties at
+full batch size.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+import parity_common as P
+from slam_framework_b200 import orbfe, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    L = orbfe.load()
+    if L.orbfe_device_count() < 1:
+        pytest.fail("no CUDA device: the product library has no CPU path")
+    assert b"EMULATED" not in L.orbfe_version()
+    return L
+
+
+def test_config1_single_kitti_frame(lib):
+    kps, desc = P.check_extract(lib, synth.frame(seed=0))
+    assert 1900 < len(kps) <= 2000 + 24
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_extract_more_frames(lib, seed):
+    P.check_extract(lib, synth.frame(seed=seed))
+
+
+@pytest.mark.parametrize("h,w,nf", [(120, 400, 500), (97, 131, 300), (480, 640, 1000), (1080, 1920, 8000)])
+def test_extract_other_sizes(lib, h, w, nf):
+    P.check_extract(lib, synth.frame(h, w, seed=h), nfeatures=nf)
+
+
+def test_extract_dense_noise_and_strided(lib):
+    rng = np.random.default_rng(4)
+    big = rng.integers(0, 256, (400, 1300), dtype=np.uint8)
+    P.check_extract(lib, big[10:386, 20:1261])  # white noise: ~65k candidates, non-contiguous rows
+
+
+def test_flat_and_empty_images(lib):
+    ex = orbfe.ORBextractor(lib=lib)
+    kps, desc = ex.Compute(np.full((376, 1241), 90, np.uint8))
+    assert len(kps) == 0 and desc.shape == (0, 32)
+    kps, desc = ex.Compute(np.zeros((0, 0), np.uint8))
+    assert len(kps) == 0
+
+
+def test_handle_reuse_across_sizes(lib):
+    ex = orbfe.ORBextractor(lib=lib)
+    import oracle_lib as O
+    for shape in ((376, 1241), (200, 640), (376, 1241)):
+        img = synth.frame(*shape, seed=11)
+        kps, desc = ex.Compute(img)
+        ok, od = O.Extractor().extract(img)
+        P.assert_kps_equal(kps, ok)
+        assert np.array_equal(desc, od)
+
+
+@pytest.mark.parametrize("seed", [0, 5])
+def test_config2_stereo_pair(lib, seed):
+    left, right = synth.stereo_pair(seed=seed)
+    assert P.check_stereo(lib, left, right) > 300
+
+
+def test_config3_batch_sharded_stereo(lib):
+    pairs = [synth.stereo_pair(seed=100 + s) for s in range(6)]
+    assert P.check_batch_stereo(lib, pairs) > 6 * 300
+
+
+def test_batch_is_deterministic_and_slot_independent(lib):
+    """size-independent property at a larger batch: the same pair in every slot position gives
+    byte-identical outputs, run after run."""
+    l, r = synth.stereo_pair(seed=42)
+    n = 32
+    ex = orbfe.ORBextractor(lib=lib, max_images=2 * n)
+    ex.upload([l, r] * n)
+    outs = []
+    for _ in range(2):
+        ex.run(2 * n)
+        ex.run_stereo(n, P.KITTI["bf"], P.KITTI["bf"] / P.KITTI["fx"])
+        b = ex.download(2 * n, ex.make_buffers(2 * n, stereo=True))
+        outs.append(b)
+    for b in outs:
+        n0 = b["n"][0]
+        for p in range(n):
+            assert b["n"][2 * p] == n0
+            assert np.array_equal(b["kps"][2 * p, :n0], outs[0]["kps"][0, :n0])
+            assert np.array_equal(b["desc"][2 * p, :n0], outs[0]["desc"][0, :n0])
+            assert np.array_equal(b["ur"][2 * p, :n0], outs[0]["ur"][0, :n0])
+
+
+def test_two_handles_concurrent_threads(lib):
+    """frame.cpp:86-89 runs the left and right extractor on two std::threads."""
+    import threading
+    import oracle_lib as O
+    l, r = synth.stereo_pair(seed=9)
+    exs = [orbfe.ORBextractor(lib=lib), orbfe.ORBextractor(lib=lib)]
+    res = [None, None]
+
+    def work(i, img):
+        for _ in range(5):
+            res[i] = exs[i].Compute(img)
+    ts = [threading.Thread(target=work, args=(i, im)) for i, im in enumerate((l, r))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for (k, d), img in zip(res, (l, r)):
+        ok, od = O.Extractor().extract(img)
+        P.assert_kps_equal(k, ok)
+        assert np.array_equal(d, od)
