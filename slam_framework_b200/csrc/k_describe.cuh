@@ -1,5 +1,5 @@
 // k_describe.cuh -- E5 + E7 + E8: orientation, rotated-BRIEF descriptor and keypoint packing.
-// One warp per keypoint slot of an image (slots are level-major, the order of
+// One warp per 32 keypoint slots of an image (slots are level-major, the order of
 // ORBextractor::Compute's output, orb_extractor.cpp:1016-1048).
 //   E5  IC_Angle (orb_extractor.cpp:18-45): lanes own the 31 columns of the radius-15 disc and
 //       walk its 31 rows on the UNBLURRED level; m10/m01 are exact int32 sums reduced by
@@ -15,7 +15,7 @@
 #pragma once
 #include "orbfe_common.cuh"
 
-#define ORBFE_DESC_THREADS 256
+#define ORBFE_DESC_THREADS 64
 
 __constant__ signed char c_orb_pattern[1024] = {
 #include "orb_pattern_31.inc"
@@ -87,6 +87,14 @@ __device__ __forceinline__ float orbfe_sincosf(float y, int is_cos) {
   return orbfe_sincos_poly(__dmul_rn(x, sgn), __dmul_rn(x, x), (n & 2) != 0, n ^ is_cos);
 }
 
+// One warp owns 32 consecutive keypoint slots of an image:
+//   phase 1  warp-cooperative moments per keypoint (lane = patch column), lane k keeps (m01,m10)
+//            of keypoint k;
+//   phase 2  lane-parallel: fastAtan2 + glibc sincosf (the fp64 polynomial runs once per
+//            keypoint instead of 32x redundantly) + the cv::KeyPoint record;
+//   phase 3  per keypoint, lane i builds descriptor byte i; the lane's 16 pattern points live in
+//            registers for all 32 keypoints (per-lane constant-bank reads are serialised by the
+//            address-divergence unit, so they are paid once per warp, not once per keypoint).
 __global__ void __launch_bounds__(ORBFE_DESC_THREADS)
 k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                   const unsigned* __restrict__ lvlKp, const int* __restrict__ lvlCnt, orbfe_kp_dev* __restrict__ kps,
@@ -95,7 +103,9 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * (ORBFE_DESC_THREADS / 32) + (threadIdx.x >> 5);
   const int* cnt = lvlCnt + (size_t)slot * g.nlevels;
-  int level = -1, idx = wglobal, total = 0;
+  const int base = wglobal * 32;
+  // this lane's keypoint: packed position base+lane -> (level, index inside the level)
+  int level = -1, idx = base + lane, total = 0;
   for (int l = 0; l < g.nlevels; ++l) {
     const int c = cnt[l];
     if (level < 0 && idx < c) level = l;
@@ -103,71 +113,97 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     total += c;
   }
   if (wglobal == 0 && lane == 0) nKp[slot] = total;
-  if (level < 0) return;  // whole warp exits together
-  const LevelGeom& L = g.lv[level];
-  const unsigned pk = lvlKp[(size_t)slot * g.totalOut + L.outOff + idx];
-  const int kx = ORBFE_PX(pk) + ORBFE_MINB, ky = ORBFE_PY(pk) + ORBFE_MINB;  // level coordinates
+  if (base >= total) return;  // whole warp exits together
+  const int nk = min(32, total - base);
+  int kx = 0, ky = 0, resp = 0;
+  if (level >= 0) {
+    const unsigned pk = lvlKp[(size_t)slot * g.totalOut + g.lv[level].outOff + idx];
+    kx = ORBFE_PX(pk) + ORBFE_MINB; ky = ORBFE_PY(pk) + ORBFE_MINB;  // level coordinates
+    resp = ORBFE_PS(pk);
+  }
+  const uint8_t* pyrSlot = pyr + (size_t)slot * g.pyrStride;
   // ---- E5: intensity centroid on the unblurred level
-  const uint8_t* center = pyr + (size_t)slot * g.pyrStride + L.planeOff + (size_t)(ky + ORBFE_EDGE) * L.pitch + kx + ORBFE_EDGE;
-  int m10 = 0, m01 = 0;
-  if (lane < 31) {
-    const int u = lane - ORBFE_HALF_PATCH;
-    const int au = u < 0 ? -u : u;
-    for (int v = -ORBFE_HALF_PATCH; v <= ORBFE_HALF_PATCH; ++v) {
-      const int av = v < 0 ? -v : v;
-      if (au <= c_umax[av]) {
-        const int val = __ldg(center + v * L.pitch + u);
-        m10 += u * val;
-        m01 += v * val;
+  int my10 = 0, my01 = 0;
+  const int u = lane - ORBFE_HALF_PATCH;
+  const int au = u < 0 ? -u : u;
+  for (int k = 0; k < nk; ++k) {
+    const int lv = __shfl_sync(0xffffffffu, level, k);
+    const int cx = __shfl_sync(0xffffffffu, kx, k), cy = __shfl_sync(0xffffffffu, ky, k);
+    const LevelGeom& L = g.lv[lv];
+    const uint8_t* center = pyrSlot + L.planeOff + (size_t)(cy + ORBFE_EDGE) * L.pitch + cx + ORBFE_EDGE;
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+#pragma unroll
+      for (int v = -ORBFE_HALF_PATCH; v <= ORBFE_HALF_PATCH; ++v) {
+        const int av = v < 0 ? -v : v;
+        if (au <= c_umax[av]) {  // av is a compile-time constant after unrolling: uniform bank read
+          const int val = __ldg(center + v * L.pitch + u);
+          m10 += u * val;
+          m01 += v * val;
+        }
       }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-  }
-  const float angle = orbfe_fast_atan2((float)m01, (float)m10);
-  // ---- E7: rotated BRIEF on the blurred level
-  const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);  // :48
-  const float ang = __fmul_rn(angle, factorPI);
-  const float a = orbfe_sincosf(ang, 1), b = orbfe_sincosf(ang, 0);
-  const uint8_t* bplane = blur + (size_t)slot * g.blurStride + L.blurOff;
-  const signed char* pat = c_orb_pattern + 32 * lane;
-  unsigned val = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    int t[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float px = (float)pat[4 * k + 2 * h], py = (float)pat[4 * k + 2 * h + 1];
-      const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-      const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-      // the reference samples a CONTINUOUS w x h clone (step == w): a column overshoot lands in
-      // the adjacent row; a sample outside the buffer is UB there and defined as 0
-      int col = kx + ix, row = ky + iy;
-      if (col < 0) { col += L.w; --row; } else if (col >= L.w) { col -= L.w; ++row; }
-      t[h] = (row < 0 || row >= L.h) ? 0 : (int)__ldg(bplane + (size_t)row * L.bpitch + col);
+    for (int o = 16; o > 0; o >>= 1) {
+      m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+      m01 += __shfl_xor_sync(0xffffffffu, m01, o);
     }
-    val |= (unsigned)(t[0] < t[1]) << k;
+    if (lane == k) { my10 = m10; my01 = m01; }
   }
-  const size_t o = (size_t)slot * g.totalOut + L.outOff;  // level-major slots: outOff is NOT the
-  (void)o;                                                 // packed position; compute it below
-  // packed position inside the image = sum of counts of lower levels + idx
-  int pos = idx;
-  for (int l = 0; l < level; ++l) pos += cnt[l];
-  uint8_t* d = desc + ((size_t)slot * g.totalOut + pos) * 32;
-  d[lane] = (uint8_t)val;
-  if (lane == 0) {
+  // ---- lane-parallel angle, sin/cos and keypoint record
+  float angle = 0.f, a = 1.f, b = 0.f;
+  int pos = base + lane;
+  if (level >= 0) {
+    angle = orbfe_fast_atan2((float)my01, (float)my10);
+    const float factorPI = (float)(3.141592653589793238462643383279502884 / 180.f);  // :48
+    const float ang = __fmul_rn(angle, factorPI);
+    a = orbfe_sincosf(ang, 1);
+    b = orbfe_sincosf(ang, 0);
+    const LevelGeom& L = g.lv[level];
     orbfe_kp_dev kp;
     const float fx = (float)kx, fy = (float)ky;
     kp.x = level != 0 ? __fmul_rn(fx, L.scale) : fx;
     kp.y = level != 0 ? __fmul_rn(fy, L.scale) : fy;
     kp.size = L.kpSize;
     kp.angle = angle;
-    kp.response = (float)ORBFE_PS(pk);
+    kp.response = (float)resp;
     kp.octave = level;
     kp.class_id = -1;
     kps[(size_t)slot * g.totalOut + pos] = kp;
+  }
+  // ---- E7: rotated BRIEF on the blurred level; lane i -> descriptor byte i
+  float px[16], py[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    px[t] = (float)c_orb_pattern[32 * lane + 2 * t];
+    py[t] = (float)c_orb_pattern[32 * lane + 2 * t + 1];
+  }
+  const uint8_t* blurSlot = blur + (size_t)slot * g.blurStride;
+  uint8_t* dOut = desc + ((size_t)slot * g.totalOut + base) * 32;
+  for (int k = 0; k < nk; ++k) {
+    const int lv = __shfl_sync(0xffffffffu, level, k);
+    const int cx = __shfl_sync(0xffffffffu, kx, k), cy = __shfl_sync(0xffffffffu, ky, k);
+    const float ca = __shfl_sync(0xffffffffu, a, k), sb = __shfl_sync(0xffffffffu, b, k);
+    const LevelGeom& L = g.lv[lv];
+    const uint8_t* bplane = blurSlot + L.blurOff;
+    const int W = L.w, Hh = L.h, bp = L.bpitch;
+    unsigned val = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      int tv[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float x = px[2 * t + h], y = py[2 * t + h];
+        const int iy = __float2int_rn(__fadd_rn(__fmul_rn(x, sb), __fmul_rn(y, ca)));
+        const int ix = __float2int_rn(__fsub_rn(__fmul_rn(x, ca), __fmul_rn(y, sb)));
+        // the reference samples a CONTINUOUS w x h clone (step == w): a column overshoot lands in
+        // the adjacent row; a sample outside the buffer is UB there and defined as 0
+        int col = cx + ix, row = cy + iy;
+        if (col < 0) { col += W; --row; } else if (col >= W) { col -= W; ++row; }
+        tv[h] = (row < 0 || row >= Hh) ? 0 : (int)__ldg(bplane + (size_t)row * bp + col);
+      }
+      val |= (unsigned)(tv[0] < tv[1]) << t;
+    }
+    dOut[k * 32 + lane] = (uint8_t)val;
   }
 }

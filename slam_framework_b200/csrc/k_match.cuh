@@ -1,0 +1,379 @@
+// k_match.cuh -- M0-M4: the Frame feature grid and the windowed Hamming searches of OrbMatcher.
+//
+//   k_grid_build      Frame::AssignFeaturesToGrid / PosInGrid (frame.cpp:234-248, 339-346): 64x48 cells,
+//                     cell lists stored ix-major so that the cells (ix, iyMin..iyMax) of a query window
+//                     are ONE contiguous item range already in the reference's visiting order
+//                     (ix outer, iy inner, ascending keypoint index inside a cell).
+//   k_match_candidates (phase A, one warp per query, fully parallel): Frame::GetFeaturesInArea
+//                     (frame.cpp:348-403) + the static filters of the search routine (octave range,
+//                     stereo-right consistency) + DescriptorDistance (orb_matcher.cpp:1630-1646, 8 x
+//                     __popc on 32-byte rows).  Writes each query's candidates IN REFERENCE ORDER.
+//   k_match_resolve   (phase B, one warp): walks the queries in the reference's serial order and
+//                     applies the state that couples them (vMatchedDistance in
+//                     SearchForInitialization :306-307, F.SetMapPoint feedback in SearchByProjection
+//                     :59-63/:97); lanes scan a query's candidates, best / second-best are reduced with
+//                     warp shuffles on the composite key (distance, position), which reproduces the
+//                     strict '<' scans of the reference exactly; then the rotation-histogram
+//                     consistency check (ComputeThreeMaxima :1584-1625).
+#pragma once
+#include "orbfe_common.cuh"
+
+#define ORBFE_GRID_COLS 64   // frame.h:104
+#define ORBFE_GRID_ROWS 48   // frame.h:105
+#define ORBFE_GRID_CELLS (ORBFE_GRID_COLS * ORBFE_GRID_ROWS)
+#define ORBFE_HISTO_LENGTH 30  // orb_matcher.cpp:7
+
+struct MatchKp {  // what the matchers read of an undistorted cv::KeyPoint
+  float x, y, angle;
+  int octave;
+};
+
+struct FrameGrid {
+  const MatchKp* kp;
+  const uint8_t* desc;      // n x 32
+  const float* uR;          // n (stereo right coordinate, <= 0: none)
+  const int* cellStart;     // ORBFE_GRID_CELLS + 1, ix-major
+  const int* cellItems;     // keypoint indices
+  int n;
+  float minX, minY, gw, gh;
+};
+
+struct MatchQueries {
+  const float* x;           // window centre
+  const float* y;
+  const float* r;           // window half-size
+  const float* xr;          // predicted right coordinate (stereo consistency), may be null
+  const int* minLevel;
+  const int* maxLevel;
+  const uint8_t* valid;
+  const uint8_t* desc;      // n x 32
+  int n;
+  int checkUR;
+};
+
+struct MatchScratch {
+  uint2* cand;              // x = keypoint index, y = distance | octave << 16
+  int* qOff;
+  int* qCnt;
+  int* cursor;              // [0] allocation cursor, [1] overflow flag
+  int capacity;
+};
+
+// ---- M0: grid build (one CTA) -------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_grid_build(const MatchKp* __restrict__ kp, const int n, const float minX, const float minY, const float gw,
+             const float gh, int* __restrict__ cellStart, int* __restrict__ cellItems) {
+  __shared__ int s_cnt[ORBFE_GRID_CELLS];
+  __shared__ int s_scan[33];
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int c = tid; c < ORBFE_GRID_CELLS; c += T) s_cnt[c] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += T) {
+    const int px = (int)roundf(__fdiv_rn(__fsub_rn(kp[i].x, minX), gw));
+    const int py = (int)roundf(__fdiv_rn(__fsub_rn(kp[i].y, minY), gh));
+    if (px >= 0 && px < ORBFE_GRID_COLS && py >= 0 && py < ORBFE_GRID_ROWS) atomicAdd(&s_cnt[px * ORBFE_GRID_ROWS + py], 1);
+  }
+  __syncthreads();
+  // exclusive scan over the cells: each thread owns 3 consecutive cells (3072 = 1024*3)
+  const int per = (ORBFE_GRID_CELLS + T - 1) / T;
+  const int c0 = min(tid * per, ORBFE_GRID_CELLS), c1 = min(c0 + per, ORBFE_GRID_CELLS);
+  int sum = 0;
+  for (int c = c0; c < c1; ++c) sum += s_cnt[c];
+  int total;
+  int run = orbfe_block_exscan(sum, s_scan, &total);
+  for (int c = c0; c < c1; ++c) { const int v = s_cnt[c]; cellStart[c] = run; s_cnt[c] = run; run += v; }
+  if (tid == 0) cellStart[ORBFE_GRID_CELLS] = total;
+  __syncthreads();
+  for (int i = tid; i < n; i += T) {
+    const int px = (int)roundf(__fdiv_rn(__fsub_rn(kp[i].x, minX), gw));
+    const int py = (int)roundf(__fdiv_rn(__fsub_rn(kp[i].y, minY), gh));
+    if (px >= 0 && px < ORBFE_GRID_COLS && py >= 0 && py < ORBFE_GRID_ROWS)
+      cellItems[atomicAdd(&s_cnt[px * ORBFE_GRID_ROWS + py], 1)] = i;
+  }
+  __syncthreads();
+  // push_back order = ascending keypoint index: insertion-sort each (short) cell list
+  for (int c = tid; c < ORBFE_GRID_CELLS; c += T) {
+    const int b = cellStart[c], e = s_cnt[c];
+    for (int i = b + 1; i < e; ++i) {
+      const int v = cellItems[i];
+      int j = i - 1;
+      while (j >= b && cellItems[j] > v) { cellItems[j + 1] = cellItems[j]; --j; }
+      cellItems[j + 1] = v;
+    }
+  }
+}
+
+// cell range of a query window (frame.cpp:356-369); returns false if the window misses the grid
+__device__ __forceinline__ bool orbfe_window_cells(const FrameGrid& F, float x, float y, float r, int& x0, int& x1, int& y0,
+                                                   int& y1) {
+  x0 = max(0, (int)floorf(__fdiv_rn(__fsub_rn(__fsub_rn(x, F.minX), r), F.gw)));
+  x1 = min(ORBFE_GRID_COLS - 1, (int)ceilf(__fdiv_rn(__fadd_rn(__fsub_rn(x, F.minX), r), F.gw)));
+  if (x1 < 0 || x0 >= ORBFE_GRID_COLS) return false;
+  y0 = max(0, (int)floorf(__fdiv_rn(__fsub_rn(__fsub_rn(y, F.minY), r), F.gh)));
+  y1 = min(ORBFE_GRID_ROWS - 1, (int)ceilf(__fdiv_rn(__fadd_rn(__fsub_rn(y, F.minY), r), F.gh)));
+  if (y1 < 0 || y0 >= ORBFE_GRID_ROWS) return false;
+  return true;
+}
+
+// ---- phase A: ordered candidates + distances, one warp per query ----------------------------------
+#define ORBFE_MATCH_THREADS 128
+
+__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
+k_match_candidates(const FrameGrid F, const MatchQueries Q, const MatchScratch S) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
+  if (q >= Q.n) return;
+  int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+  const float x = Q.x[q], y = Q.y[q], r = Q.r[q];
+  const bool live = Q.valid[q] && orbfe_window_cells(F, x, y, r, x0, x1, y0, y1);
+  if (!live) {
+    if (lane == 0) { S.qOff[q] = 0; S.qCnt[q] = 0; }
+    return;
+  }
+  // upper bound of the list = items of the window's cells; one allocation per query
+  int bound = 0;
+  for (int ix = x0 + lane; ix <= x1; ix += 32)
+    bound += F.cellStart[ix * ORBFE_GRID_ROWS + y1 + 1] - F.cellStart[ix * ORBFE_GRID_ROWS + y0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bound += __shfl_xor_sync(0xffffffffu, bound, o);
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&S.cursor[0], bound);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (base + bound > S.capacity) {  // host grows the buffer and re-runs
+    if (lane == 0) { S.cursor[1] = 1; S.qOff[q] = 0; S.qCnt[q] = 0; }
+    return;
+  }
+  const int minL = Q.minLevel[q], maxL = Q.maxLevel[q];
+  const bool checkLevels = (minL > 0) || (maxL >= 0);  // frame.cpp:372 (quirk kept)
+  const float xr = Q.checkUR ? Q.xr[q] : 0.f;
+  const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(Q.desc + (size_t)q * 32));
+  const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(Q.desc + (size_t)q * 32) + 1);
+  int count = 0;
+  for (int ix = x0; ix <= x1; ++ix) {
+    const int b = F.cellStart[ix * ORBFE_GRID_ROWS + y0], e = F.cellStart[ix * ORBFE_GRID_ROWS + y1 + 1];
+    for (int j0 = b; j0 < e; j0 += 32) {
+      const int j = j0 + lane;
+      bool ok = j < e;
+      int idx = 0, oct = 0;
+      if (ok) {
+        idx = F.cellItems[j];
+        const MatchKp k = F.kp[idx];
+        oct = k.octave;
+        if (checkLevels && (oct < minL || (maxL >= 0 && oct > maxL))) ok = false;
+        const float dx = __fsub_rn(k.x, x), dy = __fsub_rn(k.y, y);
+        if (!(fabsf(dx) < r && fabsf(dy) < r)) ok = false;
+        if (ok && Q.checkUR) {  // orb_matcher.cpp:65-70 / :1404-1411
+          const float u = F.uR[idx];
+          if (u > 0 && fabsf(__fsub_rn(xr, u)) > r) ok = false;
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(F.desc + (size_t)idx * 32));
+        const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(F.desc + (size_t)idx * 32) + 1);
+        const int dist = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+        S.cand[base + count + __popc(bal & ((1u << lane) - 1u))] = make_uint2((unsigned)idx, (unsigned)dist | ((unsigned)oct << 16));
+      }
+      count += __popc(bal);
+    }
+  }
+  if (lane == 0) { S.qOff[q] = base; S.qCnt[q] = count; }
+}
+
+// ---- phase B: serial-order resolve, one warp ------------------------------------------------------
+enum { ORBFE_MODE_INIT = 0, ORBFE_MODE_MAPPOINTS = 1, ORBFE_MODE_LASTFRAME = 2 };
+
+struct ResolveArgs {
+  int mode;
+  int nQ, nKp;               // queries; keypoints of the searched frame
+  float nnratio;
+  int checkOri;
+  const uint8_t* hasObs;      // per query (modes 1, 2)
+  const uint8_t* occupiedIn;  // per keypoint (modes 1, 2)
+  const float* qAngle;        // per query: angle of the query keypoint (modes 0, 2)
+  const MatchKp* kp;          // searched frame keypoints (angles)
+  int* out;                   // mode 0: matches12[nQ]; modes 1, 2: assigned[nKp]
+  int* evBin;                 // per query: histogram bin of its acceptance, or -1
+  int* evIdx;                 // per query: mode 0 -> query index, mode 2 -> keypoint index
+  int* result;                // [0] nmatches
+};
+
+// 2 smallest of the union of two sorted pairs
+__device__ __forceinline__ void orbfe_merge2(unsigned& b, unsigned& s, unsigned ob, unsigned os) {
+  const unsigned nb = min(b, ob);
+  const unsigned ns = min(max(b, ob), min(s, os));
+  b = nb; s = ns;
+}
+
+__global__ void __launch_bounds__(32)
+k_match_resolve(const ResolveArgs A, const MatchScratch S) {
+  ORBFE_DYN_SMEM(smem);
+  int* s_state = reinterpret_cast<int*>(smem);  // mode 0: vMatchedDistance[nKp] then vnMatches21[nKp]; else occupied[nKp]
+  __shared__ int s_hist[ORBFE_HISTO_LENGTH];
+  const int lane = threadIdx.x;
+  if (S.cursor[1]) return;  // candidate buffer overflowed: the host re-runs with a larger one
+  const int nKp = A.nKp;
+  if (A.mode == ORBFE_MODE_INIT) {
+    for (int i = lane; i < nKp; i += 32) { s_state[i] = 0x7fffffff; s_state[nKp + i] = -1; }
+    for (int i = lane; i < A.nQ; i += 32) A.out[i] = -1;
+  } else {
+    for (int i = lane; i < nKp; i += 32) { s_state[i] = A.occupiedIn[i]; A.out[i] = -1; }
+  }
+  for (int i = lane; i < ORBFE_HISTO_LENGTH; i += 32) s_hist[i] = 0;
+  for (int i = lane; i < A.nQ; i += 32) A.evBin[i] = -1;
+  __syncwarp();
+  int nmatches = 0;
+  const float factor = 1.0f / ORBFE_HISTO_LENGTH;  // orb_matcher.cpp:275 (the reference's bin-width bug, kept)
+  for (int q = 0; q < A.nQ; ++q) {
+    const int cnt = S.qCnt[q];
+    if (cnt == 0) continue;
+    const int off = S.qOff[q];
+    // key = dist << 20 | position (position < 2^20); sentinel = "none"
+    unsigned best = 0xffffffffu, second = 0xffffffffu;
+    for (int c = lane; c < cnt; c += 32) {
+      const uint2 cd = S.cand[off + c];
+      const int dist = (int)(cd.y & 0xffffu);
+      bool ok;
+      if (A.mode == ORBFE_MODE_INIT) ok = !(s_state[cd.x] <= dist);  // vMatchedDistance[i2] <= dist => skip (:306)
+      else ok = !s_state[cd.x] && dist < 256;                        // occupied; bestDist starts at 256
+      if (ok) {
+        const unsigned key = ((unsigned)dist << 20) | (unsigned)c;
+        if (key < best) { second = best; best = key; } else if (key < second) second = key;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const unsigned os = __shfl_xor_sync(0xffffffffu, second, o);
+      orbfe_merge2(best, second, ob, os);
+    }
+    if (best == 0xffffffffu) continue;  // warp-uniform
+    if (lane == 0) {
+      const int bestDist = (int)(best >> 20);
+      const uint2 bc = S.cand[off + (int)(best & 0xfffffu)];
+      const int bestIdx = (int)bc.x;
+      bool accept = false;
+      if (A.mode == ORBFE_MODE_INIT) {
+        // bestDist <= TH_LOW && bestDist < (float)bestDist2 * mfNNratio (:320-322); no second => INT_MAX
+        const float d2 = second == 0xffffffffu ? (float)0x7fffffff : (float)(int)(second >> 20);
+        accept = bestDist <= 50 && (float)bestDist < __fmul_rn(d2, A.nnratio);
+        if (accept) {
+          const int prev = s_state[nKp + bestIdx];  // vnMatches21
+          if (prev >= 0) { A.out[prev] = -1; --nmatches; }
+          A.out[q] = bestIdx;
+          s_state[nKp + bestIdx] = q;
+          s_state[bestIdx] = bestDist;
+          ++nmatches;
+        }
+      } else if (A.mode == ORBFE_MODE_MAPPOINTS) {
+        if (bestDist <= 100) {  // TH_HIGH
+          accept = true;
+          if (second != 0xffffffffu) {
+            const uint2 sc = S.cand[off + (int)(second & 0xfffffu)];
+            const int bestDist2 = (int)(second >> 20);
+            const int bestLevel = (int)(bc.y >> 16), bestLevel2 = (int)(sc.y >> 16);
+            if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(A.nnratio, (float)bestDist2)) accept = false;
+          }
+          // no second: bestLevel2 == -1 != bestLevel => accepted (:92-95)
+          if (accept) { A.out[bestIdx] = q; s_state[bestIdx] = A.hasObs[q]; ++nmatches; }
+        }
+      } else {
+        if (bestDist <= 100) {
+          accept = true;
+          A.out[bestIdx] = q; s_state[bestIdx] = A.hasObs[q]; ++nmatches;
+        }
+      }
+      if (accept && A.checkOri && A.mode != ORBFE_MODE_MAPPOINTS) {
+        float rot = __fsub_rn(A.qAngle[q], A.kp[bestIdx].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        int bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == ORBFE_HISTO_LENGTH) bin = 0;
+        s_hist[bin]++;
+        A.evBin[q] = bin;
+        A.evIdx[q] = A.mode == ORBFE_MODE_INIT ? q : bestIdx;
+      }
+    }
+    __syncwarp();
+  }
+  nmatches = __shfl_sync(0xffffffffu, nmatches, 0);
+  if (A.checkOri && A.mode != ORBFE_MODE_MAPPOINTS) {
+    // ComputeThreeMaxima (orb_matcher.cpp:1584-1625), lane 0
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    if (lane == 0) {
+      int max1 = 0, max2 = 0, max3 = 0;
+      for (int i = 0; i < ORBFE_HISTO_LENGTH; i++) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+    }
+    ind1 = __shfl_sync(0xffffffffu, ind1, 0);
+    ind2 = __shfl_sync(0xffffffffu, ind2, 0);
+    ind3 = __shfl_sync(0xffffffffu, ind3, 0);
+    __syncwarp();
+    int removed = 0;
+    for (int q0 = 0; q0 < A.nQ; q0 += 32) {
+      const int q = q0 + lane;
+      if (q < A.nQ) {
+        const int bin = A.evBin[q];
+        if (bin >= 0 && bin != ind1 && bin != ind2 && bin != ind3) {
+          const int idx = A.evIdx[q];
+          if (A.mode == ORBFE_MODE_INIT) {
+            if (A.out[idx] >= 0) { A.out[idx] = -1; ++removed; }  // :364-370
+          } else {
+            A.out[idx] = -1; ++removed;  // CurrentFrame.SetMapPoint(idx, NULL); nmatches-- (:1441-1446)
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+    nmatches -= removed;
+  }
+  if (lane == 0) A.result[0] = nmatches;
+}
+
+// ---- OrbMatcher::DescriptorDistance, batched (orb_matcher.cpp:1630-1646) --------------------------
+__global__ void __launch_bounds__(256)
+k_descriptor_distance(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, const int n, int* __restrict__ d) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(a + (size_t)i * 32)), a1 = __ldg(reinterpret_cast<const uint4*>(a + (size_t)i * 32) + 1);
+  const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(b + (size_t)i * 32)), b1 = __ldg(reinterpret_cast<const uint4*>(b + (size_t)i * 32) + 1);
+  d[i] = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ---- Frame::GetFeaturesInArea as a call of its own (one warp) --------------------------------------
+__global__ void __launch_bounds__(32)
+k_features_in_area(const FrameGrid F, const float x, const float y, const float r, const int minL, const int maxL,
+                   int* __restrict__ out, const int capacity, int* __restrict__ nOut) {
+  const int lane = threadIdx.x;
+  int x0, x1, y0, y1, count = 0;
+  if (orbfe_window_cells(F, x, y, r, x0, x1, y0, y1)) {
+    const bool checkLevels = (minL > 0) || (maxL >= 0);
+    for (int ix = x0; ix <= x1; ++ix) {
+      const int b = F.cellStart[ix * ORBFE_GRID_ROWS + y0], e = F.cellStart[ix * ORBFE_GRID_ROWS + y1 + 1];
+      for (int j0 = b; j0 < e; j0 += 32) {
+        const int j = j0 + lane;
+        bool ok = j < e;
+        int idx = 0;
+        if (ok) {
+          idx = F.cellItems[j];
+          const MatchKp k = F.kp[idx];
+          if (checkLevels && (k.octave < minL || (maxL >= 0 && k.octave > maxL))) ok = false;
+          if (!(fabsf(__fsub_rn(k.x, x)) < r && fabsf(__fsub_rn(k.y, y)) < r)) ok = false;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        const int pos = count + __popc(bal & ((1u << lane) - 1u));
+        if (ok && pos < capacity) out[pos] = idx;
+        count += __popc(bal);
+      }
+    }
+  }
+  if (lane == 0) *nOut = count;
+}

@@ -332,7 +332,7 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
   if ((rc = stage_event(ex, 3))) return rc;
   ORBFE_LAUNCH(ex, k_blur, dim3(g.totalTiles, n), dim3(ORBFE_BLUR_THREADS), 0, g, ex->d_pyr, ex->d_blur);
   if ((rc = stage_event(ex, 4))) return rc;
-  ORBFE_LAUNCH(ex, k_orient_describe, dim3((g.totalOut + ORBFE_DESC_THREADS / 32 - 1) / (ORBFE_DESC_THREADS / 32), n),
+  ORBFE_LAUNCH(ex, k_orient_describe, dim3((g.totalOut + ORBFE_DESC_THREADS - 1) / ORBFE_DESC_THREADS, n),  // 32 keypoints per warp
                dim3(ORBFE_DESC_THREADS), 0, g, ex->d_pyr, ex->d_blur, ex->d_lvlKp, ex->d_lvlCnt, ex->d_kps, ex->d_desc,
                ex->d_nKp);
   if ((rc = stage_event(ex, 5))) return rc;

@@ -87,3 +87,112 @@ def check_batch_stereo(lib, pairs, nfeatures=2000, bf=KITTI["bf"], fx=KITTI["fx"
         total += on
     ex.close()
     return total
+
+
+# ---- matchers (BASELINE configs 4 and 5, per-frame tracking) --------------------------------------
+def make_frames(kps, desc, scale, w, h, lib, u_right=None):
+    """(product Frame, oracle Frame) over the same undistorted keypoints; image bounds as
+    Frame::ComputeImageBounds for an undistorted camera (0..cols, 0..rows)."""
+    bounds = (0.0, float(w), 0.0, float(h))
+    return (orbfe.Frame(kps, desc, scale, bounds, u_right, lib=lib), O.Frame(kps, desc, scale, bounds, u_right))
+
+
+def check_features_in_area(F, OF, rng, w, h, n=60):
+    for _ in range(n):
+        x, y = rng.uniform(-20, w + 20), rng.uniform(-20, h + 20)
+        r = rng.choice([3.0, 10.0, 40.0, 100.0])
+        lo, hi = [(-1, -1), (0, 0), (1, 3), (2, -1), (0, 7)][rng.integers(0, 5)]
+        a = F.GetFeaturesInArea(x, y, r, lo, hi)
+        b = OF.features_in_area(x, y, r, lo, hi)
+        assert np.array_equal(a, b), f"GetFeaturesInArea({x},{y},{r},{lo},{hi})"
+
+
+def check_search_for_initialization(lib, img1, img2, extract, nfeatures=4000, window=100):
+    """config 4: mono frames with nFeatures=4000, SearchForInitialization(F1,F2,prev=F1 pts,100), 0.9."""
+    k1, d1 = extract(img1, nfeatures)
+    k2, d2 = extract(img2, nfeatures)
+    scale = O.Extractor(nfeatures).tables()["scale"]
+    h, w = img1.shape
+    F1, OF1 = make_frames(k1, d1, scale, w, h, lib)
+    F2, OF2 = make_frames(k2, d2, scale, w, h, lib)
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    n, m12, pm = orbfe.OrbMatcher(0.9, True).SearchForInitialization(F1, F2, prev, window)
+    on, om12, opm = O.search_for_initialization(OF1, OF2, prev, window, 0.9, True)
+    assert n == on, f"SearchForInitialization: {n} vs oracle {on}"
+    assert np.array_equal(m12, om12), "vnMatches12 differs"
+    assert np.array_equal(pm, opm), "vbPrevMatched differs"
+    # second call with the updated vbPrevMatched and no orientation check
+    n2, m12b, _ = orbfe.OrbMatcher(0.9, False).SearchForInitialization(F1, F2, pm, window // 2)
+    on2, om12b, _ = O.search_for_initialization(OF1, OF2, opm, window // 2, 0.9, False)
+    assert n2 == on2 and np.array_equal(m12b, om12b)
+    return n
+
+
+def synth_map_points(kps, desc, rng, n_mp, u_right=None):
+    """config 5 recipe: descriptors = random frame descriptors with 0-40 flipped bits,
+    projections = that keypoint + jitter, predicted level = octave (+1 w.p. 1/2)."""
+    n = len(kps)
+    src = rng.integers(0, n, n_mp)
+    d = desc[src].copy()
+    for i in range(n_mp):
+        nb = rng.integers(0, 41)
+        bits = rng.choice(256, nb, replace=False)
+        for b in bits:
+            d[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    lvl = np.minimum(kps["octave"][src] + rng.integers(0, 2, n_mp), 7).astype(np.int32)
+    view = rng.choice(np.array([0.999, 0.9], np.float32), n_mp)
+    px = (kps["x"][src] + rng.uniform(-3, 3, n_mp)).astype(np.float32)
+    py = (kps["y"][src] + rng.uniform(-3, 3, n_mp)).astype(np.float32)
+    pxr = (px - rng.uniform(0, 40, n_mp)).astype(np.float32)
+    if u_right is not None:
+        has = u_right[src] > 0
+        pxr[has] = (u_right[src][has] + rng.uniform(-6, 6, has.sum())).astype(np.float32)
+    valid = (rng.uniform(0, 1, n_mp) < 0.9).astype(np.uint8)
+    has_obs = (rng.uniform(0, 1, n_mp) < 0.8).astype(np.uint8)
+    occupied = (rng.uniform(0, 1, n) < 0.1).astype(np.uint8)
+    return dict(valid=valid, px=px, py=py, pxr=pxr, lvl=lvl, view=view, desc=d, has_obs=has_obs, occupied=occupied)
+
+
+def check_search_by_projection_mappoints(lib, kps, desc, scale, w, h, n_mp, seed=0, u_right=None, th=1, nnratio=0.8):
+    rng = np.random.default_rng(seed)
+    F, OF = make_frames(kps, desc, scale, w, h, lib, u_right)
+    check_features_in_area(F, OF, rng, w, h)
+    mp = synth_map_points(kps, desc, rng, n_mp, u_right)
+    n, asg = orbfe.OrbMatcher(nnratio).SearchByProjectionMapPoints(F, mp["valid"], mp["px"], mp["py"], mp["pxr"], mp["lvl"],
+                                                                  mp["view"], mp["desc"], mp["has_obs"], mp["occupied"], th)
+    on, oasg = O.search_by_projection_mappoints(OF, mp["valid"], mp["px"], mp["py"], mp["pxr"], mp["lvl"], mp["view"],
+                                                mp["desc"], mp["has_obs"], mp["occupied"], th, nnratio)
+    assert n == on, f"SearchByProjection(map points): {n} vs oracle {on}"
+    assert np.array_equal(asg, oasg), "assigned map points differ"
+    return n
+
+
+def check_search_by_projection_lastframe(lib, kps, desc, scale, w, h, seed=0, u_right=None, th=7.0):
+    """per-frame tracking match: the 'last frame' points are this frame's keypoints displaced."""
+    rng = np.random.default_rng(seed)
+    F, OF = make_frames(kps, desc, scale, w, h, lib, u_right)
+    n = len(kps)
+    sel = rng.permutation(n)[: max(n // 2, 1)]
+    u = (kps["x"][sel] + rng.uniform(-5, 5, len(sel))).astype(np.float32)
+    v = (kps["y"][sel] + rng.uniform(-5, 5, len(sel))).astype(np.float32)
+    u[:5] -= 2000.0  # out of bounds
+    invzc = rng.uniform(0.01, 0.2, len(sel)).astype(np.float32)
+    invzc[5:9] = -0.1
+    octv = kps["octave"][sel].astype(np.int32)
+    ang = ((kps["angle"][sel] + rng.choice([0.0, 0.0, 0.0, 45.0, 170.0], len(sel))) % 360).astype(np.float32)
+    d = desc[sel].copy()
+    d[:, 0] ^= rng.integers(0, 256, len(sel)).astype(np.uint8)
+    valid = (rng.uniform(0, 1, len(sel)) < 0.9).astype(np.uint8)
+    has_obs = (rng.uniform(0, 1, len(sel)) < 0.7).astype(np.uint8)
+    occupied = (rng.uniform(0, 1, n) < 0.05).astype(np.uint8)
+    tot = 0
+    for fwd, bwd in ((0, 0), (1, 0), (0, 1)):
+        for ori in (True, False):
+            m, asg = orbfe.OrbMatcher(0.9, ori).SearchByProjectionLastFrame(F, valid, u, v, invzc, octv, ang, d, has_obs,
+                                                                           KITTI["bf"], fwd, bwd, occupied, th)
+            om, oasg = O.search_by_projection_lastframe(OF, valid, u, v, invzc, octv, ang, d, has_obs, KITTI["bf"], fwd,
+                                                        bwd, occupied, th, ori)
+            assert m == om, f"SearchByProjection(last frame) fwd={fwd} bwd={bwd} ori={ori}: {m} vs {om}"
+            assert np.array_equal(asg, oasg)
+            tot += m
+    return tot

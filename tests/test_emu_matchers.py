@@ -1,0 +1,60 @@
+"""Matcher kernel LOGIC on CPU (emulated TEST build, see test_emu_parity.py) against the oracle."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import parity_common as P
+from emu import build_emu
+from slam_framework_b200 import orbfe, synth
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return orbfe.load(build_emu.build(), _test_emulation=True)
+
+
+def oracle_extract(img, nfeatures):
+    return O.Extractor(nfeatures).extract(img)
+
+
+def test_descriptor_distance(emu):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (500, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (500, 32), dtype=np.uint8)
+    b[:10] = a[:10]
+    b[10:20] = ~a[10:20]
+    d = orbfe.DescriptorDistance(a, b, lib=emu)
+    assert np.array_equal(d, np.unpackbits(a ^ b, axis=1).sum(1))
+    assert d[:10].max() == 0 and d[10:20].min() == 256
+
+
+def test_search_for_initialization_small(emu):
+    a, b = synth.shifted_frame(3, 200, 640, dx=8, dy=4)
+    assert P.check_search_for_initialization(emu, a, b, oracle_extract, nfeatures=1500) > 20
+
+
+def test_search_by_projection_mappoints(emu):
+    img = synth.frame(240, 800, seed=2)
+    kps, desc = oracle_extract(img, 1500)
+    scale = O.Extractor(1500).tables()["scale"]
+    rng = np.random.default_rng(1)
+    ur = np.where(rng.uniform(0, 1, len(kps)) < 0.6, kps["x"] - rng.uniform(1, 60, len(kps)), -1).astype(np.float32)
+    assert P.check_search_by_projection_mappoints(emu, kps, desc, scale, 800, 240, 3000, seed=5, u_right=ur) > 200
+    assert P.check_search_by_projection_mappoints(emu, kps, desc, scale, 800, 240, 2000, seed=6, th=3) > 100
+
+
+def test_search_by_projection_lastframe(emu):
+    img = synth.frame(240, 800, seed=4)
+    kps, desc = oracle_extract(img, 1200)
+    scale = O.Extractor(1200).tables()["scale"]
+    rng = np.random.default_rng(2)
+    ur = np.where(rng.uniform(0, 1, len(kps)) < 0.5, kps["x"] - rng.uniform(1, 60, len(kps)), -1).astype(np.float32)
+    assert P.check_search_by_projection_lastframe(emu, kps, desc, scale, 800, 240, seed=7, u_right=ur) > 100
+
+
+def test_empty_frames(emu):
+    scale = O.Extractor().tables()["scale"]
+    F = orbfe.Frame(np.zeros(0, orbfe.KP_DTYPE), np.zeros((0, 32), np.uint8), scale, (0, 100, 0, 100), lib=emu)
+    assert len(F.GetFeaturesInArea(10, 10, 5)) == 0
+    n, m, _ = orbfe.OrbMatcher(0.9).SearchForInitialization(F, F, np.zeros((0, 2), np.float32), 100)
+    assert n == 0 and len(m) == 0

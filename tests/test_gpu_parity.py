@@ -110,3 +110,51 @@ def test_two_handles_concurrent_threads(lib):
         ok, od = O.Extractor().extract(img)
         P.assert_kps_equal(k, ok)
         assert np.array_equal(d, od)
+
+
+# ---- matchers: configs 4 and 5 + per-frame tracking match -------------------------------------------
+def gpu_extract(lib):
+    def f(img, nfeatures):
+        ex = orbfe.ORBextractor(nfeatures, lib=lib)
+        out = ex.Compute(img)
+        ex.close()
+        return out
+    return f
+
+
+def test_descriptor_distance(lib):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (20000, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (20000, 32), dtype=np.uint8)
+    b[:10] = a[:10]
+    b[10:20] = ~a[10:20]
+    d = orbfe.DescriptorDistance(a, b, lib=lib)
+    assert np.array_equal(d, np.unpackbits(a ^ b, axis=1).sum(1))
+
+
+def test_config4_search_for_initialization(lib):
+    a, b = synth.shifted_frame(21, dx=8, dy=4)
+    assert P.check_search_for_initialization(lib, a, b, gpu_extract(lib), nfeatures=4000) > 100
+    a, b = synth.shifted_frame(22, dx=-8, dy=-4)
+    assert P.check_search_for_initialization(lib, a, b, gpu_extract(lib), nfeatures=4000) > 100
+
+
+@pytest.mark.parametrize("h,w", [(1080, 1920), (2160, 3840)])
+def test_config5_search_by_projection_20k_mappoints(lib, h, w):
+    import oracle_lib as O
+    img = synth.frame(h, w, seed=w)
+    kps, desc = P.check_extract(lib, img, nfeatures=8000, stages=False)
+    scale = O.Extractor(8000).tables()["scale"]
+    assert P.check_search_by_projection_mappoints(lib, kps, desc, scale, w, h, 20000, seed=3) > 3000
+
+
+def test_tracking_search_by_projection_lastframe(lib):
+    import oracle_lib as O
+    l, r = synth.stereo_pair(seed=31)
+    eL, eR = orbfe.ORBextractor(lib=lib), orbfe.ORBextractor(lib=lib)
+    kl, dl = eL.Compute(l)
+    kr, dr = eR.Compute(r)
+    _, ur, _ = orbfe.ComputeStereoMatches(eL, eR, kl, dl, kr, dr, P.KITTI["bf"], P.KITTI["bf"] / P.KITTI["fx"])
+    scale = eL.GetScaleFactors()
+    assert P.check_search_by_projection_lastframe(lib, kl, dl, scale, 1241, 376, seed=8, u_right=ur, th=7.0) > 1000
+    assert P.check_search_by_projection_mappoints(lib, kl, dl, scale, 1241, 376, 5000, seed=9, u_right=ur) > 500
