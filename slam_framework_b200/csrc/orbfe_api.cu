@@ -54,7 +54,7 @@ struct orbfe_extractor {
   int fpl[ORBFE_MAX_LEVELS];
   Geom g{};
   bool configured = false;
-  int fastTilePitch = 0, fastMaxInnerH = 0;
+  int fastTilePitch = 0, fastMaxInnerH = 0, fastQueueCap = 0;
   size_t fastSmem = 0, octSmem = 0;
   // device arena
   uint8_t* d_img = nullptr;
@@ -159,7 +159,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   g.imgStride = (unsigned)align_up_sz((size_t)g.imgPitch * h0, 256);
   size_t pyrOff = 0, blurOff = 0, cellListOff = 0, candOff = 0, nodeOff = 0;
   int cellBase = 0, outOff = 0, tileBase = 0, lutOff = 0, maxSort = 1;
-  int maxCw = 8, maxInnerH = 1;
+  int maxCw = 8, maxInnerH = 1, fastBase = 0, maxQueue = 1;
   std::vector<ResizeLut> lut;
   for (int l = 0; l < nl; ++l) {
     LevelGeom& L = g.lv[l];
@@ -207,9 +207,15 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
     L.cellCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
     L.cellListOff = (unsigned)cellListOff;
     cellListOff += (size_t)L.nCols * L.nRows * L.cellCap;
+    // FAST CTAs: a band segment of fG cells (tile <= ~256 px wide)
+    L.fG = std::max(1, std::min(ORBFE_FAST_MAXG / 2, 256 / L.wCell));
+    L.fSegs = L.nCols > 0 ? (L.nCols + L.fG - 1) / L.fG : 0;
+    L.fastBase = fastBase;
+    fastBase += L.fSegs * L.nRows;
     if (L.nCols > 0) {
-      maxCw = std::max(maxCw, L.wCell + 6);
+      maxCw = std::max(maxCw, L.fG * L.wCell + 6 + 3);  // + alignment slack
       maxInnerH = std::max(maxInnerH, L.hCell);
+      maxQueue = std::max(maxQueue, L.fG * L.wCell * L.hCell);
     }
     // quad-tree (orb_extractor.cpp:480-531)
     L.N = ex->fpl[l];
@@ -248,9 +254,12 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   ex->octSmem = (size_t)sc * sizeof(unsigned long long);
   if (ex->octSmem > 200 * 1024)
     return orbfe_fail(ORBFE_ERR_INVALID, "nfeatures per level too large for the shared-memory sort (%d)", maxSort);
-  ex->fastTilePitch = align_up(maxCw, 4);
-  ex->fastMaxInnerH = maxInnerH;
-  ex->fastSmem = (size_t)(2 * maxInnerH + 8) * ex->fastTilePitch;
+  g.totalFast = fastBase;
+  if (maxCw > 511 || maxInnerH + 6 > 127) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too large for the 16-bit queue code");
+  ex->fastTilePitch = align_up(maxCw, 4) / 4 + 1;  // words
+  ex->fastMaxInnerH = maxInnerH + 6;              // tile rows
+  ex->fastQueueCap = maxQueue;
+  ex->fastSmem = (size_t)2 * ex->fastMaxInnerH * ex->fastTilePitch * 4 + (size_t)maxQueue * 2 + 16;
   if (ex->fastSmem > 200 * 1024) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too large");
   ex->bestStride = (size_t)g.nodeStride * 5 / 4 + 16 * ORBFE_MAX_LEVELS;
 
@@ -323,9 +332,9 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
     ORBFE_LAUNCH(ex, k_pyramid_level, dim3(g.lv[l].pyrBlocks, n), dim3(ORBFE_PYR_THREADS), 0, g, l, ex->d_img, ex->d_pyr,
                  ex->d_lut);
   if ((rc = stage_event(ex, 1))) return rc;
-  if (g.totalCells > 0)
-    ORBFE_LAUNCH(ex, k_fast_cells, dim3(g.totalCells, n), dim3(ORBFE_FAST_THREADS), ex->fastSmem, g, ex->d_pyr,
-                 ex->d_cellCnt, ex->d_cellList, ex->fastTilePitch, ex->fastMaxInnerH);
+  if (g.totalFast > 0)
+    ORBFE_LAUNCH(ex, k_fast_cells, dim3(g.totalFast, n), dim3(ORBFE_FAST_THREADS), ex->fastSmem, g, ex->d_pyr,
+                 ex->d_cellCnt, ex->d_cellList, ex->fastTilePitch, ex->fastMaxInnerH, ex->fastQueueCap);
   if ((rc = stage_event(ex, 2))) return rc;
   ORBFE_LAUNCH(ex, k_octree, dim3(g.nlevels, n), dim3(ORBFE_OCT_THREADS), ex->octSmem, g, ex->d_cellCnt, ex->d_cellList,
                ex->oct, ex->d_lvlKp, ex->d_lvlCnt, ex->d_err);

@@ -37,6 +37,7 @@ struct LevelGeom {
   // FAST grid (orb_extractor.cpp:714-728)
   int nCols, nRows, wCell, hCell, maxBX, maxBY;
   int cellBase, cellCap;
+  int fG, fSegs, fastBase;  // FAST CTAs: fG cells per CTA, fSegs CTAs per cell row
   unsigned cellListOff;  // u32 entries
   // quad-tree (orb_extractor.cpp:480-704)
   int N, nIni, boxW, boxH;
@@ -57,7 +58,7 @@ struct LevelGeom {
 struct Geom {
   int nlevels, w0, h0, iniTh, minTh;
   int imgPitch;
-  int totalCells, totalTiles, totalOut, totalPyrBlocks;
+  int totalCells, totalTiles, totalOut, totalPyrBlocks, totalFast;
   int sortCap;           // power of two >= max(outCap, N) over levels
   unsigned imgStride, pyrStride, blurStride, cellListStride, candStride, nodeStride;
   LevelGeom lv[ORBFE_MAX_LEVELS];
