@@ -75,48 +75,55 @@ __device__ __forceinline__ int orbfe_fast_score(const uint8_t* p, int tp, int th
 // One CTA = up to L.fG consecutive grid cells of one cell row of one level of one image.  The cells'
 // detection windows tile the level's inner region exactly (origin (19,19), stride wCell x hCell, SURVEY
 // A.2), so the CTA stages ONE pixel tile (hCell+6 rows x fG*wCell+6 columns, word-aligned, coalesced
-// 4-byte loads) and runs:
-//   1. compass pre-test, 4 pixels per instruction (SIMD-in-register u8): a 9-arc of the 16-ring always
-//      contains two ADJACENT compass points (ring 0/4/8/12), so pixels without two adjacent compass
-//      points both > v+t or both < v-t are rejected; survivors (~10 %) are compacted into a queue;
-//   2. exact FAST-9 test + corner score on the queue only, all lanes busy;
-//   3. strict 3x3 NMS restricted to the cell (neighbours outside the cell's window count 0) + the
-//      per-cell "any survivor >= iniThFAST" flag that drives the minThFAST fallback (:753-757);
-//   4. one warp per cell: row-major ordered emission with warp ballots (the order cv::FAST returns).
-#ifndef ORBFE_EMU
-#define ORBFE_VADDUS4(a, b) __vaddus4(a, b)
-#define ORBFE_VSUBUS4(a, b) __vsubus4(a, b)
-#define ORBFE_VCMPGTU4(a, b) __vcmpgtu4(a, b)
-#define ORBFE_VCMPLTU4(a, b) __vcmpltu4(a, b)
-#else
-static inline unsigned orbfe_emu_b4(unsigned a, unsigned b, int op) {
-  unsigned r = 0;
-  for (int i = 0; i < 4; ++i) {
-    const int x = (a >> (8 * i)) & 0xff, y = (b >> (8 * i)) & 0xff;
-    int v = 0;
-    if (op == 0) v = x + y > 255 ? 255 : x + y;
-    if (op == 1) v = x - y < 0 ? 0 : x - y;
-    if (op == 2) v = x > y ? 0xff : 0;
-    if (op == 3) v = x < y ? 0xff : 0;
-    r |= (unsigned)v << (8 * i);
+// 4-byte loads) and runs up to two rounds, first at iniThFAST over the whole tile, then at minThFAST
+// over the cells that produced no keypoint (the post-NMS emptiness fallback of :753-757; cv::FAST at
+// threshold t == "score >= t" on the threshold-independent score map):
+//   1. compass pre-test, 4 pixels per instruction (VABSDIFF4 + carry trick): a 9-arc of the 16-ring
+//      always contains two ADJACENT compass points (ring 0/4/8/12), so a pixel without two adjacent
+//      compass points differing from it by more than t cannot be a corner; survivors are compacted
+//      into a shared-memory queue;
+//   2. exact corner score (max_arc min_9 of +-(ring - v), 3-input min/max networks) on the queue only,
+//      all lanes busy; corner at t <=> score >= t;
+//   3. strict 3x3 NMS restricted to the cell (neighbours outside the cell's window count 0);
+//   4. one warp per cell: row-major ordered emission with warp ballots (the order cv::FAST returns),
+//      visiting only rows that hold a survivor.
+#define ORBFE_FAST_ROWWORDS 3  // survivor row masks: up to 96 tile rows
+
+// exact FAST-9/16 corner score of the pixel at p (shared-memory tile, byte pitch tp)
+__device__ __forceinline__ int orbfe_fast_score3(const uint8_t* p, int tp) {
+  const int v = p[0];
+  int d[16];
+  d[0] = p[3 * tp] - v;       d[1] = p[3 * tp + 1] - v;   d[2] = p[2 * tp + 2] - v;   d[3] = p[tp + 3] - v;
+  d[4] = p[3] - v;            d[5] = p[-tp + 3] - v;      d[6] = p[-2 * tp + 2] - v;  d[7] = p[-3 * tp + 1] - v;
+  d[8] = p[-3 * tp] - v;      d[9] = p[-3 * tp - 1] - v;  d[10] = p[-2 * tp - 2] - v; d[11] = p[-tp - 3] - v;
+  d[12] = p[-3] - v;          d[13] = p[tp - 3] - v;      d[14] = p[2 * tp - 2] - v;  d[15] = p[3 * tp - 1] - v;
+  int lo3[16], hi3[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    lo3[i] = __vimin3_s32(d[i], d[(i + 1) & 15], d[(i + 2) & 15]);
+    hi3[i] = __vimax3_s32(d[i], d[(i + 1) & 15], d[(i + 2) & 15]);
   }
-  return r;
+  int bright = -512, dark = 512;  // max_arc min_9 (d)   /   min_arc max_9 (d)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    bright = max(bright, __vimin3_s32(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]));
+    dark = min(dark, __vimax3_s32(hi3[i], hi3[(i + 3) & 15], hi3[(i + 6) & 15]));
+  }
+  return max(bright, -dark) - 1;
 }
-#define ORBFE_VADDUS4(a, b) orbfe_emu_b4(a, b, 0)
-#define ORBFE_VSUBUS4(a, b) orbfe_emu_b4(a, b, 1)
-#define ORBFE_VCMPGTU4(a, b) orbfe_emu_b4(a, b, 2)
-#define ORBFE_VCMPLTU4(a, b) orbfe_emu_b4(a, b, 3)
-#endif
 
 __global__ void __launch_bounds__(ORBFE_FAST_THREADS)
 k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, int* __restrict__ cellCnt,
              unsigned* __restrict__ cellList, const int pitchW, const int maxRows, const int queueCap) {
   ORBFE_DYN_SMEM(smem);
-  unsigned* tileW = reinterpret_cast<unsigned*>(smem);               // [maxRows][pitchW] pixels, later NMS survivors
+  unsigned* tileW = reinterpret_cast<unsigned*>(smem);               // [maxRows][pitchW] pixels
   unsigned* scoreW = tileW + (size_t)maxRows * pitchW;               // [maxRows][pitchW] corner scores
-  unsigned short* queue = reinterpret_cast<unsigned short*>(scoreW + (size_t)maxRows * pitchW);
+  unsigned* bitsW = scoreW + (size_t)maxRows * pitchW;               // [maxRows][pitchW/8+1] NMS survivor bits
+  unsigned short* queue = reinterpret_cast<unsigned short*>(bitsW + (size_t)maxRows * (pitchW / 8 + 1));
   __shared__ int s_qn;
   __shared__ int s_any[ORBFE_FAST_MAXG];
+  __shared__ unsigned s_rowmask[ORBFE_FAST_MAXG][ORBFE_FAST_ROWWORDS];
+  __shared__ uint8_t s_colCell[512];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int slot = blockIdx.y;
   int level = 0;
@@ -137,9 +144,10 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
     if (tid < nj) cnt[tid] = 0;
     return;
   }
-  const int pitchB = pitchW * 4;
+  const int pitchB = pitchW * 4, bitsP = pitchW / 8 + 1;
   const int gx0 = (iniX + ORBFE_EDGE) & ~3;                          // padded-plane column of tile column 0
   const int tw = (maxX + ORBFE_EDGE - gx0 + 3) >> 2;                  // tile width in words
+  const int ix0 = iniX + 3 + ORBFE_EDGE - gx0, ix1 = maxX - 3 + ORBFE_EDGE - gx0;  // inner columns (tile coords)
   const uint8_t* src = pyr + (size_t)slot * g.pyrStride + L.planeOff + (size_t)(iniY + ORBFE_EDGE) * L.pitch + gx0;
   for (int r = wid; r < rows; r += ORBFE_FAST_THREADS / 32) {
     const unsigned* srow = reinterpret_cast<const unsigned*>(src + (size_t)r * L.pitch);
@@ -147,89 +155,118 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
       tileW[r * pitchW + c] = c < tw ? __ldg(srow + c) : 0u;
       scoreW[r * pitchW + c] = 0u;
     }
+    for (int c = lane; c < bitsP; c += 32) bitsW[r * bitsP + c] = 0u;
   }
-  if (tid == 0) s_qn = 0;
-  if (tid < ORBFE_FAST_MAXG) s_any[tid] = 0;
-  __syncthreads();
-  // ---- 1. compass pre-test on words
-  const int ix0 = iniX + 3 + ORBFE_EDGE - gx0, ix1 = maxX - 3 + ORBFE_EDGE - gx0;  // inner columns (tile coords)
-  const int w0 = ix0 >> 2, nWi = ((ix1 - 1) >> 2) - w0 + 1, nRi = rows - 6;
-  const unsigned th4 = (unsigned)g.minTh * 0x01010101u;
-  for (int t = tid; t < nRi * nWi; t += ORBFE_FAST_THREADS) {
-    const int ry = t / nWi, wx = w0 + t - ry * nWi, y = 3 + ry;
-    const unsigned* row = tileW + y * pitchW + wx;
-    const unsigned c = row[0], up = row[-3 * pitchW], dn = row[3 * pitchW];
-    const unsigned prev = wx > 0 ? row[-1] : 0u, next = wx + 1 < pitchW ? row[1] : 0u;
-    const unsigned lf = __funnelshift_r(prev, c, 8), rt = __funnelshift_r(c, next, 24);
-    const unsigned hi = ORBFE_VADDUS4(c, th4), lo = ORBFE_VSUBUS4(c, th4);
-    const unsigned B0 = ORBFE_VCMPGTU4(dn, hi), B4 = ORBFE_VCMPGTU4(rt, hi), B8 = ORBFE_VCMPGTU4(up, hi), B12 = ORBFE_VCMPGTU4(lf, hi);
-    const unsigned D0 = ORBFE_VCMPLTU4(dn, lo), D4 = ORBFE_VCMPLTU4(rt, lo), D8 = ORBFE_VCMPLTU4(up, lo), D12 = ORBFE_VCMPLTU4(lf, lo);
-    unsigned m = ((B0 | B8) & (B4 | B12)) | ((D0 | D8) & (D4 | D12));
-    // (B0&B4)|(B4&B8)|(B8&B12)|(B12&B0) == (B0|B8)&(B4|B12)
-    if (m == 0u) continue;
-    const int xb = 4 * wx;
+  if (tid < ORBFE_FAST_MAXG) {
+    s_any[tid] = 0;
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if (xb + b < ix0 || xb + b >= ix1) m &= ~(0xffu << (8 * b));
-    const int n = __popc(m & 0x01010101u);
-    if (n == 0) continue;
-    int pos = atomicAdd(&s_qn, n);
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if ((m >> (8 * b)) & 1u) { if (pos < queueCap) queue[pos] = (unsigned short)((y << 9) | (xb + b)); ++pos; }
+    for (int k = 0; k < ORBFE_FAST_ROWWORDS; ++k) s_rowmask[tid][k] = 0u;
   }
-  __syncthreads();
-  // ---- 2. exact test + score on the queue
-  const int qn = min(s_qn, queueCap);
+  for (int x = tid; x < pitchB && x < 512; x += ORBFE_FAST_THREADS)
+    s_colCell[x] = (uint8_t)((x >= ix0 && x < ix1) ? (x - ix0) / L.wCell : 0xff);
   const uint8_t* tileB = reinterpret_cast<const uint8_t*>(tileW);
   uint8_t* scoreB = reinterpret_cast<uint8_t*>(scoreW);
-  for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
-    const int code = queue[e], x = code & 511, y = code >> 9;
-    const int s = orbfe_fast_score(tileB + y * pitchB + x, pitchB, g.minTh);
-    if (s > 0) scoreB[y * pitchB + x] = (uint8_t)s;
-  }
-  __syncthreads();
-  // the pixel tile is no longer needed: it becomes the plane of NMS survivors
-  for (int t = tid; t < rows * pitchW; t += ORBFE_FAST_THREADS) tileW[t] = 0u;
-  __syncthreads();
-  // ---- 3. NMS inside the cell + fallback flag
-  uint8_t* nmsB = reinterpret_cast<uint8_t*>(tileW);
-  for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
-    const int code = queue[e], x = code & 511, y = code >> 9;
-    const uint8_t* c = scoreB + y * pitchB + x;
-    const int s = c[0];
-    if (s == 0) continue;
-    const int jl = (x - ix0) / L.wCell;
-    const int cx0 = ix0 + jl * L.wCell, cx1 = min(cx0 + L.wCell, ix1);
-    const bool hasL = x > cx0, hasR = x + 1 < cx1;  // rows outside the inner band hold score 0 already
-    bool keep = s > c[-pitchB] && s > c[pitchB];
-    if (hasL) keep = keep && s > c[-1] && s > c[-pitchB - 1] && s > c[pitchB - 1];
-    if (hasR) keep = keep && s > c[1] && s > c[-pitchB + 1] && s > c[pitchB + 1];
-    if (keep) {
-      nmsB[y * pitchB + x] = (uint8_t)s;
-      if (s >= g.iniTh) s_any[jl] = 1;
+  const int w0 = ix0 >> 2, nWi = ((ix1 - 1) >> 2) - w0 + 1;
+
+  for (int round = 0; round < 2; ++round) {
+    const int th = round == 0 ? g.iniTh : g.minTh;
+    if (tid == 0) s_qn = 0;
+    __syncthreads();
+    if (round == 1) {  // block-uniform: does any cell of this CTA need the minThFAST fallback?
+      bool need = false;
+      for (int jl = 0; jl < nj; ++jl) need = need || !s_any[jl];
+      if (!need || g.minTh >= g.iniTh) break;
     }
+    // ---- 1. compass pre-test on words: flag bit 7 of byte b <=> |ring - centre| > th
+    const unsigned K4 = (unsigned)(th < 128 ? 127 - th : 255 - th) * 0x01010101u;
+    for (int y = 3 + wid; y < rows - 3; y += ORBFE_FAST_THREADS / 32)
+      for (int wi = lane; wi < nWi; wi += 32) {
+        const int wx = w0 + wi, xb = 4 * wx;
+        if (round == 1) {  // only the fallback cells are re-examined
+          const unsigned ca = s_colCell[min(max(xb, ix0), ix1 - 1)], cb = s_colCell[max(min(xb + 3, ix1 - 1), ix0)];
+          if (s_any[ca] && s_any[cb]) continue;
+        }
+        const unsigned* row = tileW + y * pitchW + wx;
+        const unsigned c = row[0], up = row[-3 * pitchW], dn = row[3 * pitchW];
+        const unsigned prev = wx > 0 ? row[-1] : 0u, next = wx + 1 < pitchW ? row[1] : 0u;
+        const unsigned lf = __funnelshift_r(prev, c, 8), rt = __funnelshift_r(c, next, 24);
+        const unsigned a0 = __vabsdiffu4(dn, c), a4 = __vabsdiffu4(rt, c), a8 = __vabsdiffu4(up, c), a12 = __vabsdiffu4(lf, c);
+        unsigned f0, f4, f8, f12;
+        if (th < 128) {
+          f0 = ((a0 & 0x7f7f7f7fu) + K4) | a0;   f4 = ((a4 & 0x7f7f7f7fu) + K4) | a4;
+          f8 = ((a8 & 0x7f7f7f7fu) + K4) | a8;   f12 = ((a12 & 0x7f7f7f7fu) + K4) | a12;
+        } else {
+          f0 = ((a0 & 0x7f7f7f7fu) + K4) & a0;   f4 = ((a4 & 0x7f7f7f7fu) + K4) & a4;
+          f8 = ((a8 & 0x7f7f7f7fu) + K4) & a8;   f12 = ((a12 & 0x7f7f7f7fu) + K4) & a12;
+        }
+        unsigned m = (f0 | f8) & (f4 | f12) & 0x80808080u;  // two adjacent compass points differ by > th
+        if (m == 0u) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int x = xb + b;
+          if (x < ix0 || x >= ix1 || (round == 1 && s_any[s_colCell[x]])) m &= ~(0x80u << (8 * b));
+        }
+        const int n = __popc(m);
+        if (n == 0) continue;
+        int pos = atomicAdd(&s_qn, n);
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if ((m >> (8 * b + 7)) & 1u) { if (pos < queueCap) queue[pos] = (unsigned short)((y << 9) | (xb + b)); ++pos; }
+      }
+    __syncthreads();
+    // ---- 2. exact score on the queue; corner at th <=> score >= th
+    const int qn = min(s_qn, queueCap);
+    for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
+      const int code = queue[e], x = code & 511, y = code >> 9;
+      const int s = orbfe_fast_score3(tileB + y * pitchB + x, pitchB);
+      if (s >= th) scoreB[y * pitchB + x] = (uint8_t)s;
+    }
+    __syncthreads();
+    // ---- 3. NMS inside the cell; survivors -> bit plane + row masks; keypoint found => no fallback
+    for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
+      const int code = queue[e], x = code & 511, y = code >> 9;
+      const uint8_t* c = scoreB + y * pitchB + x;
+      const int s = c[0];
+      if (s == 0) continue;
+      const int jl = s_colCell[x];
+      const int cx0 = ix0 + jl * L.wCell, cx1 = min(cx0 + L.wCell, ix1);
+      const bool hasL = x > cx0, hasR = x + 1 < cx1;  // rows outside the inner band hold score 0 already
+      bool keep = s > c[-pitchB] && s > c[pitchB];
+      if (hasL) keep = keep && s > c[-1] && s > c[-pitchB - 1] && s > c[pitchB - 1];
+      if (hasR) keep = keep && s > c[1] && s > c[-pitchB + 1] && s > c[pitchB + 1];
+      if (keep) {
+        atomicOr(&bitsW[y * bitsP + (x >> 5)], 1u << (x & 31));
+        atomicOr(&s_rowmask[jl][y >> 5], 1u << (y & 31));
+        s_any[jl] = 1;
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // ---- 4. ordered emission, one warp per cell
+  // ---- 4. ordered emission, one warp per cell, only rows that hold a survivor
   for (int jl = wid; jl < nj; jl += ORBFE_FAST_THREADS / 32) {
     const int cx0 = ix0 + jl * L.wCell, cx1 = min(cx0 + L.wCell, ix1);
-    const int th = s_any[jl] ? g.iniTh : g.minTh;
     unsigned* out = list + (size_t)jl * L.cellCap;
     int base = 0;
     if (cx1 > cx0) {
-      for (int y = 3; y < rows - 3; ++y)
-        for (int c0 = cx0; c0 < cx1; c0 += 32) {
-          const int x = c0 + lane;
-          const int s = x < cx1 ? nmsB[y * pitchB + x] : 0;
-          const bool emit = s >= th;
-          const unsigned bal = __ballot_sync(0xffffffffu, emit);
-          if (emit) {
-            const int pos = base + __popc(bal & ((1u << lane) - 1u));
-            if (pos < L.cellCap) out[pos] = orbfe_pack(x + gx0 - ORBFE_EDGE - ORBFE_MINB, y + iniY - ORBFE_MINB, s);
+#pragma unroll
+      for (int k = 0; k < ORBFE_FAST_ROWWORDS; ++k) {
+        unsigned rm = s_rowmask[jl][k];
+        while (rm) {
+          const int y = 32 * k + __ffs((int)rm) - 1;
+          rm &= rm - 1;
+          for (int c0 = cx0; c0 < cx1; c0 += 32) {
+            const int x = c0 + lane;
+            const bool emit = x < cx1 && ((bitsW[y * bitsP + (x >> 5)] >> (x & 31)) & 1u);
+            const unsigned bal = __ballot_sync(0xffffffffu, emit);
+            if (emit) {
+              const int pos = base + __popc(bal & ((1u << lane) - 1u));
+              if (pos < L.cellCap)
+                out[pos] = orbfe_pack(x + gx0 - ORBFE_EDGE - ORBFE_MINB, y + iniY - ORBFE_MINB, scoreB[y * pitchB + x]);
+            }
+            base += __popc(bal);
           }
-          base += __popc(bal);
         }
+      }
     }
     if (lane == 0) cnt[jl] = min(base, L.cellCap);
   }

@@ -259,7 +259,8 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   ex->fastTilePitch = align_up(maxCw, 4) / 4 + 1;  // words
   ex->fastMaxInnerH = maxInnerH + 6;              // tile rows
   ex->fastQueueCap = maxQueue;
-  ex->fastSmem = (size_t)2 * ex->fastMaxInnerH * ex->fastTilePitch * 4 + (size_t)maxQueue * 2 + 16;
+  if (ex->fastMaxInnerH > 32 * ORBFE_FAST_ROWWORDS) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too tall");
+  ex->fastSmem = (size_t)ex->fastMaxInnerH * (2 * ex->fastTilePitch + ex->fastTilePitch / 8 + 1) * 4 + (size_t)maxQueue * 2 + 16;
   if (ex->fastSmem > 200 * 1024) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too large");
   ex->bestStride = (size_t)g.nodeStride * 5 / 4 + 16 * ORBFE_MAX_LEVELS;
 
