@@ -2,57 +2,85 @@
 // (cv::GaussianBlur on a clone of the level, orb_extractor.cpp:1029-1030).
 // OpenCV >= 3.4.1 fixed-point path: taps [18,34,48,56,48,34,18]/256 per
 // axis, u16 horizontal sums (<= 65280), one final rounding (V + 32768) >> 16.
-// One CTA = one 64x32 output tile of one level of one image slot; the (64+6)x(32+6) source
-// window is staged in shared memory with the reflection applied at the level edges, the
-// horizontal pass writes u16 rows to shared memory, the vertical pass writes 4-pixel words.
+//
+// The source is the PADDED pyramid plane: its 19-px border already holds the level's
+// BORDER_REFLECT_101 extension (orb_extractor.cpp:1066-1071), which is exactly the extension
+// cv::GaussianBlur applies to the clone, so no reflection logic is needed; and because the ROI
+// starts at column 19, output word k (pixels 4k..4k+3) reads input bytes 16+4k..25+4k = the three
+// ALIGNED words k+4..k+6 of the padded row.
+//
+// One warp = a strip of 30 output words (120 px) x ORBFE_BLUR_ROWS rows.  Lanes load one aligned
+// word per input row (coalesced 128 B), fetch the two following words with shuffles, form the 7-tap
+// horizontal sums with byte funnel-shifts + IDP.4A (2 dp4a per pixel), keep the last 7 rows of sums
+// in registers and emit one 4-pixel word per row: no shared memory, every byte read once per strip.
 #pragma once
 #include "orbfe_common.cuh"
 
-#define ORBFE_BLUR_THREADS 256
-#define ORBFE_BLUR_TW 64
-#define ORBFE_BLUR_TH 32
+#define ORBFE_BLUR_THREADS 128
+#define ORBFE_BLUR_WORDS 30   // output words per warp strip (32 loaded - 2 for the right neighbours)
+#define ORBFE_BLUR_ROWS 32    // output rows per warp strip
+// legacy tile macros (geometry fields tilesX/tilesY/tileBase now count warp strips)
+#define ORBFE_BLUR_TW (4 * ORBFE_BLUR_WORDS)
+#define ORBFE_BLUR_TH ORBFE_BLUR_ROWS
+
+__device__ __forceinline__ unsigned orbfe_dp4a_u8(unsigned a, unsigned b, unsigned c) { return __dp4a(a, b, c); }
 
 __global__ void __launch_bounds__(ORBFE_BLUR_THREADS)
 k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
-  __shared__ uint8_t s_src[ORBFE_BLUR_TH + 6][ORBFE_BLUR_TW + 8];
-  __shared__ uint16_t s_h[ORBFE_BLUR_TH + 6][ORBFE_BLUR_TW];
   const int slot = blockIdx.y;
-  const int tile = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int task = blockIdx.x * (ORBFE_BLUR_THREADS / 32) + (threadIdx.x >> 5);
+  if (task >= g.totalTiles) return;
   int level = 0;
   for (int l = 1; l < g.nlevels; ++l)
-    if (tile >= g.lv[l].tileBase) level = l;
+    if (task >= g.lv[l].tileBase) level = l;
   const LevelGeom& L = g.lv[level];
-  const int ti = tile - L.tileBase;
+  const int ti = task - L.tileBase;
   const int ty = ti / L.tilesX, tx = ti - ty * L.tilesX;
-  const int x0 = tx * ORBFE_BLUR_TW, y0 = ty * ORBFE_BLUR_TH;
-  const uint8_t* src = pyr + (size_t)slot * g.pyrStride + L.planeOff + (size_t)ORBFE_EDGE * L.pitch + ORBFE_EDGE;
-  uint8_t* dst = blur + (size_t)slot * g.blurStride + L.blurOff;
-  for (int t = threadIdx.x; t < (ORBFE_BLUR_TH + 6) * (ORBFE_BLUR_TW + 6); t += ORBFE_BLUR_THREADS) {
-    const int r = t / (ORBFE_BLUR_TW + 6), c = t - r * (ORBFE_BLUR_TW + 6);
-    const int sy = orbfe_reflect101(min(y0 + r - 3, L.h + 2), L.h);
-    const int sx = orbfe_reflect101(min(x0 + c - 3, L.w + 2), L.w);
-    s_src[r][c] = __ldg(src + (size_t)sy * L.pitch + sx);
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < (ORBFE_BLUR_TH + 6) * ORBFE_BLUR_TW; t += ORBFE_BLUR_THREADS) {
-    const int r = t / ORBFE_BLUR_TW, c = t - r * ORBFE_BLUR_TW;
-    const uint8_t* p = &s_src[r][c];
-    s_h[r][c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < ORBFE_BLUR_TH * (ORBFE_BLUR_TW / 4); t += ORBFE_BLUR_THREADS) {
-    const int r = t / (ORBFE_BLUR_TW / 4), c4 = (t - r * (ORBFE_BLUR_TW / 4)) * 4;
-    const int y = y0 + r, x = x0 + c4;
-    if (y >= L.h || x >= L.w) continue;
-    unsigned w = 0;
+  const int k = tx * ORBFE_BLUR_WORDS + lane;  // output word of this lane (lanes 30,31 only feed neighbours)
+  const int y0 = ty * ORBFE_BLUR_ROWS;
+  const int nrows = min(ORBFE_BLUR_ROWS, L.h - y0);
+  const int pitchW = L.pitch >> 2;
+  // input word k+4 of padded row (19 + y - 3); clamp the column so that every lane reads inside the plane
+  const int inW = min(k + 4, pitchW - 1);
+  const unsigned* src = reinterpret_cast<const unsigned*>(pyr + (size_t)slot * g.pyrStride + L.planeOff) +
+                        (size_t)(ORBFE_EDGE - 3 + y0) * pitchW + inW;
+  uint8_t* dst = blur + (size_t)slot * g.blurStride + L.blurOff + (size_t)y0 * L.bpitch + 4 * k;
+  const bool writer = lane < ORBFE_BLUR_WORDS && 4 * k < L.w;
+  const unsigned KA = 0x38302212u;  // taps 18,34,48,56 (bytes 0..3)
+  const unsigned KB = 0x00122230u;  // taps 48,34,18,0
+  unsigned H[7][4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int c = c4 + b;
-      const unsigned acc = 18u * ((unsigned)s_h[r][c] + s_h[r + 6][c]) + 34u * ((unsigned)s_h[r + 1][c] + s_h[r + 5][c]) +
-                           48u * ((unsigned)s_h[r + 2][c] + s_h[r + 4][c]) + 56u * (unsigned)s_h[r + 3][c];
-      w |= ((acc + 32768u) >> 16) << (8 * b);
+  for (int s = 0; s < 7; ++s)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) H[s][j] = 0u;
+  const int total = nrows + 6;
+  for (int r0 = 0; r0 < total; r0 += 7) {
+#pragma unroll
+    for (int s = 0; s < 7; ++s) {
+      const int r = r0 + s;
+      if (r < total) {  // warp-uniform
+        const unsigned w0 = __ldg(src + (size_t)r * pitchW);
+        const unsigned w1 = __shfl_down_sync(0xffffffffu, w0, 1);
+        const unsigned w2 = __shfl_down_sync(0xffffffffu, w0, 2);
+        // horizontal sums of the 4 pixels of this word: bytes j..j+6 of (w0,w1,w2)
+        H[s][0] = orbfe_dp4a_u8(w1, KB, orbfe_dp4a_u8(w0, KA, 0u));
+        H[s][1] = orbfe_dp4a_u8(__funnelshift_r(w1, w2, 8), KB, orbfe_dp4a_u8(__funnelshift_r(w0, w1, 8), KA, 0u));
+        H[s][2] = orbfe_dp4a_u8(__funnelshift_r(w1, w2, 16), KB, orbfe_dp4a_u8(__funnelshift_r(w0, w1, 16), KA, 0u));
+        H[s][3] = orbfe_dp4a_u8(__funnelshift_r(w1, w2, 24), KB, orbfe_dp4a_u8(__funnelshift_r(w0, w1, 24), KA, 0u));
+        if (r >= 6 && writer) {
+          // window rows r-6..r live in H[(s+1)%7] (oldest) .. H[s] (newest)
+          unsigned out = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const unsigned acc = 18u * (H[(s + 1) % 7][j] + H[s][j]) + 34u * (H[(s + 2) % 7][j] + H[(s + 6) % 7][j]) +
+                                 48u * (H[(s + 3) % 7][j] + H[(s + 5) % 7][j]) + 56u * H[(s + 4) % 7][j];
+            out |= ((acc + 32768u) >> 16) << (8 * j);
+          }
+          // bpitch is a multiple of 16: the word store is aligned; bytes past w land in row padding
+          *reinterpret_cast<unsigned*>(dst + (size_t)(r - 6) * L.bpitch) = out;
+        }
+      }
     }
-    // bpitch is a multiple of 16, so the word store is aligned; bytes past w land in row padding
-    *reinterpret_cast<unsigned*>(dst + (size_t)y * L.bpitch + x) = w;
   }
 }

@@ -37,11 +37,18 @@ k_pyramid_level(const __grid_constant__ Geom g, const int level, const uint8_t* 
   unsigned out = 0;
   if (level == 0) {
     const uint8_t* src = img + (size_t)slot * g.imgStride + (size_t)y * g.imgPitch;
+    const int x0 = 4 * wx - ORBFE_EDGE;  // image column of byte 0 = 4*(wx-5)+1
+    if (x0 >= 0 && x0 + 3 < L.w) {
+      // interior: two aligned words of the image row, shifted by one byte (imgPitch is a multiple of 16)
+      const unsigned* s4 = reinterpret_cast<const unsigned*>(src) + (wx - 5);
+      out = __funnelshift_r(__ldg(s4), __ldg(s4 + 1), 8);
+    } else {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int px = 4 * wx + b;
-      const int x = orbfe_reflect101(min(px, pw - 1) - ORBFE_EDGE, L.w);
-      out |= (unsigned)__ldg(src + x) << (8 * b);
+      for (int b = 0; b < 4; ++b) {
+        const int px = 4 * wx + b;
+        const int x = orbfe_reflect101(min(px, pw - 1) - ORBFE_EDGE, L.w);
+        out |= (unsigned)__ldg(src + x) << (8 * b);
+      }
     }
   } else {
     const LevelGeom& P = g.lv[level - 1];
@@ -69,4 +76,89 @@ k_pyramid_level(const __grid_constant__ Geom g, const int level, const uint8_t* 
     }
   }
   *reinterpret_cast<unsigned*>(plane + (size_t)py * L.pitch + 4 * wx) = out;
+}
+
+// ---- fast resize path (levels >= 1, scale factor <= 2, not the exact-2x INTER_AREA case) ------------
+// One warp = 32 consecutive words of the PADDED destination plane x ORBFE_PYR_ROWS rows.  Everything that
+// depends only on the column lives in registers for the whole strip (host-built PyrWordLut: source word,
+// byte shift, the 4 byte offsets and the packed 11-bit coefficient pairs); per SOURCE row the lane loads 3
+// aligned words, aligns them with 2 funnel shifts and forms the 4 horizontal interpolations with one
+// funnel shift + one IDP.2A each; horizontally interpolated rows are cached across destination rows
+// (consecutive rows share a source row), and the vertical blend (b*(T>>4))>>16 is one IMAD.HI.
+#define ORBFE_PYR_ROWS 32
+
+struct PyrWordLut {
+  int srcW;          // first source word of the padded source row
+  int sh;            // 8 * (first source byte & 3)
+  unsigned offs;     // byte j = 8 * (offset of pixel j's left source byte inside the aligned window)
+  unsigned cpack[4]; // c0 | c1 << 16 (cv::resize 11-bit coefficients)
+};
+
+__device__ __forceinline__ void orbfe_hrow(const unsigned* __restrict__ srow, const PyrWordLut& W, const int (&sj)[4],
+                                           unsigned (&T)[4]) {
+  const unsigned w0 = __ldg(srow + W.srcW), w1 = __ldg(srow + W.srcW + 1), w2 = __ldg(srow + W.srcW + 2);
+  const unsigned lo = __funnelshift_r(w0, w1, W.sh), hi = __funnelshift_r(w1, w2, W.sh);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned B = sj[j] >= 32 ? hi >> (sj[j] - 32) : __funnelshift_r(lo, hi, sj[j]);
+    T[j] = __dp2a_lo(W.cpack[j], B, 0u) >> 4;  // (S0*c0 + S1*c1) >> 4
+  }
+}
+
+__global__ void __launch_bounds__(ORBFE_PYR_THREADS)
+k_pyramid_resize(const __grid_constant__ Geom g, const int level, uint8_t* __restrict__ pyr,
+                 const ResizeLut* __restrict__ lut, const PyrWordLut* __restrict__ wlut) {
+  const LevelGeom& L = g.lv[level];
+  const LevelGeom& P = g.lv[level - 1];
+  const int slot = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int task = blockIdx.x * (ORBFE_PYR_THREADS / 32) + (threadIdx.x >> 5);
+  const int strips = (L.pyrWords + 31) >> 5;
+  const int ph = L.h + 2 * ORBFE_EDGE;
+  const int ty = task / strips, tx = task - ty * strips;
+  const int py0 = ty * ORBFE_PYR_ROWS;
+  if (py0 >= ph) return;
+  const int wx = min(tx * 32 + lane, L.pyrWords - 1);  // duplicate lanes rewrite the last word with the same value
+  const PyrWordLut W = wlut[L.wlutOff + wx];
+  int sj[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sj[j] = (int)((W.offs >> (8 * j)) & 0xffu);
+  const int spitchW = P.pitch >> 2;
+  const unsigned* src = reinterpret_cast<const unsigned*>(pyr + (size_t)slot * g.pyrStride + P.planeOff);
+  unsigned* dst = reinterpret_cast<unsigned*>(pyr + (size_t)slot * g.pyrStride + L.planeOff) + wx;
+  const int dpitchW = L.pitch >> 2;
+  unsigned Ta[4] = {0, 0, 0, 0}, Tb[4] = {0, 0, 0, 0};
+  int ra = -1, rb = -1;
+  const int pyEnd = min(py0 + ORBFE_PYR_ROWS, ph);
+  for (int py = py0; py < pyEnd; ++py) {
+    const int y = orbfe_reflect101(py - ORBFE_EDGE, L.h);
+    const ResizeLut ly = lut[L.lutYOff + y];
+    const int s0 = ly.ofs, s1 = min(ly.ofs + 1, P.h - 1);
+    // warp-uniform row cache
+    if (s0 == rb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const unsigned t = Ta[j]; Ta[j] = Tb[j]; Tb[j] = t; }
+      const int t = ra; ra = rb; rb = t;
+    } else if (s0 != ra) {
+      orbfe_hrow(src + (size_t)(s0 + ORBFE_EDGE) * spitchW, W, sj, Ta);
+      ra = s0;
+    }
+    if (s1 != rb) {
+      if (s1 == ra) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Tb[j] = Ta[j];
+      } else {
+        orbfe_hrow(src + (size_t)(s1 + ORBFE_EDGE) * spitchW, W, sj, Tb);
+      }
+      rb = s1;
+    }
+    const unsigned b0 = (unsigned)ly.c0 << 16, b1 = (unsigned)ly.c1 << 16;
+    unsigned out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned v = (__umulhi(b0, Ta[j]) + __umulhi(b1, Tb[j]) + 2u) >> 2;  // ((b0*(T0>>4))>>16 + (b1*(T1>>4))>>16 + 2) >> 2
+      out |= v << (8 * j);
+    }
+    dst[(size_t)py * dpitchW] = out;
+  }
 }

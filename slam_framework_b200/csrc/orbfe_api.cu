@@ -70,6 +70,7 @@ struct orbfe_extractor {
   uint8_t* d_desc = nullptr;
   int* d_nKp = nullptr;
   ResizeLut* d_lut = nullptr;
+  PyrWordLut* d_wlut = nullptr;
   int* d_err = nullptr;
   // stereo
   StereoPair* d_pairs = nullptr;
@@ -130,7 +131,7 @@ static void free_arena(orbfe_extractor* ex) {
   cudaFree(ex->oct.cand); cudaFree(ex->oct.knode); cudaFree(ex->oct.cellStart); cudaFree(ex->oct.nodes);
   cudaFree(ex->oct.childCnt); cudaFree(ex->oct.childSlot); cudaFree(ex->oct.best); cudaFree(ex->oct.finSeq);
   cudaFree(ex->oct.finKey); cudaFree(ex->d_lvlKp); cudaFree(ex->d_lvlCnt); cudaFree(ex->d_kps); cudaFree(ex->d_desc);
-  cudaFree(ex->d_nKp); cudaFree(ex->d_lut); cudaFree(ex->d_err); cudaFree(ex->d_pairs); cudaFree(ex->d_uR);
+  cudaFree(ex->d_nKp); cudaFree(ex->d_lut); cudaFree(ex->d_wlut); ex->d_wlut = nullptr; cudaFree(ex->d_err); cudaFree(ex->d_pairs); cudaFree(ex->d_uR);
   cudaFree(ex->d_depth); cudaFree(ex->d_sad); cudaFree(ex->d_nMatched);
   cudaFreeHost(ex->h_n); cudaFreeHost(ex->h_kps); cudaFreeHost(ex->h_desc); cudaFreeHost(ex->h_uR);
   cudaFreeHost(ex->h_depth); cudaFreeHost(ex->h_pairs);
@@ -161,6 +162,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   int cellBase = 0, outOff = 0, tileBase = 0, lutOff = 0, maxSort = 1;
   int maxCw = 8, maxInnerH = 1, fastBase = 0, maxQueue = 1;
   std::vector<ResizeLut> lut;
+  std::vector<PyrWordLut> wlut;
   for (int l = 0; l < nl; ++l) {
     LevelGeom& L = g.lv[l];
     // level size (orb_extractor.cpp:1055-1056)
@@ -187,6 +189,40 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
       build_resize_lut(L.h, P.h, lut.data() + L.lutYOff);
     }
     L.pyrWords = (L.w + 2 * ORBFE_EDGE + 3) / 4;
+    // per-word LUT of the fast resize kernel (k_pyramid_resize)
+    L.wlutOff = (int)wlut.size();
+    L.fastResize = 0;
+    if (l > 0 && !L.area2) {
+      const LevelGeom& P = g.lv[l - 1];
+      const ResizeLut* lx = lut.data() + L.lutXOff;
+      const int pw = L.w + 2 * ORBFE_EDGE;
+      bool ok = true;
+      std::vector<PyrWordLut> words(L.pyrWords);
+      for (int k = 0; k < L.pyrWords && ok; ++k) {
+        int sb[4], mn = 1 << 30;
+        for (int j = 0; j < 4; ++j) {
+          int x = std::min(4 * k + j, pw - 1) - ORBFE_EDGE;
+          while (x < 0 || x >= L.w) x = x < 0 ? -x : 2 * (L.w - 1) - x;  // BORDER_REFLECT_101
+          if (L.w == 1) x = 0;
+          sb[j] = ORBFE_EDGE + lx[x].ofs;  // byte of the padded source row
+          mn = std::min(mn, sb[j]);
+          words[k].cpack[j] = (unsigned)(unsigned short)lx[x].c0 | ((unsigned)(unsigned short)lx[x].c1 << 16);
+        }
+        words[k].srcW = mn >> 2;
+        words[k].sh = 8 * (mn & 3);
+        words[k].offs = 0;
+        for (int j = 0; j < 4; ++j) {
+          const int pj = sb[j] - mn;
+          if (pj + 1 > 7) ok = false;
+          words[k].offs |= (unsigned)(8 * pj) << (8 * j);
+        }
+        if ((words[k].srcW + 2) * 4 + 3 >= P.pitch) ok = false;  // the 3-word window must stay inside the row
+      }
+      if (ok) {
+        wlut.insert(wlut.end(), words.begin(), words.end());
+        L.fastResize = 1;
+      }
+    }
     L.pyrBlocks = (L.pyrWords * (L.h + 2 * ORBFE_EDGE) + ORBFE_PYR_THREADS - 1) / ORBFE_PYR_THREADS;
     // FAST grid (orb_extractor.cpp:714-728)
     L.maxBX = L.w - ORBFE_EDGE + 3;
@@ -285,6 +321,9 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   CUDA_TRY(cudaMalloc(&ex->d_desc, S * g.totalOut * 32));
   CUDA_TRY(cudaMalloc(&ex->d_nKp, S * sizeof(int)));
   CUDA_TRY(cudaMalloc(&ex->d_lut, std::max<size_t>(lut.size(), 1) * sizeof(ResizeLut)));
+  CUDA_TRY(cudaMalloc(&ex->d_wlut, std::max<size_t>(wlut.size(), 1) * sizeof(PyrWordLut)));
+  if (!wlut.empty())
+    CUDA_TRY(cudaMemcpyAsync(ex->d_wlut, wlut.data(), wlut.size() * sizeof(PyrWordLut), cudaMemcpyHostToDevice, ex->stream));
   CUDA_TRY(cudaMalloc(&ex->d_err, sizeof(int)));
   CUDA_TRY(cudaMalloc(&ex->d_pairs, S * sizeof(StereoPair)));
   CUDA_TRY(cudaMalloc(&ex->d_uR, S * g.totalOut * sizeof(float)));
@@ -329,9 +368,17 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
   const Geom& g = ex->g;
   int rc;
   if ((rc = stage_event(ex, 0))) return rc;
-  for (int l = 0; l < g.nlevels; ++l)
-    ORBFE_LAUNCH(ex, k_pyramid_level, dim3(g.lv[l].pyrBlocks, n), dim3(ORBFE_PYR_THREADS), 0, g, l, ex->d_img, ex->d_pyr,
-                 ex->d_lut);
+  for (int l = 0; l < g.nlevels; ++l) {
+    const LevelGeom& L = g.lv[l];
+    if (L.fastResize) {
+      const int tasks = ((L.pyrWords + 31) / 32) * ((L.h + 2 * ORBFE_EDGE + ORBFE_PYR_ROWS - 1) / ORBFE_PYR_ROWS);
+      ORBFE_LAUNCH(ex, k_pyramid_resize, dim3((tasks + ORBFE_PYR_THREADS / 32 - 1) / (ORBFE_PYR_THREADS / 32), n),
+                   dim3(ORBFE_PYR_THREADS), 0, g, l, ex->d_pyr, ex->d_lut, ex->d_wlut);
+    } else {
+      ORBFE_LAUNCH(ex, k_pyramid_level, dim3(L.pyrBlocks, n), dim3(ORBFE_PYR_THREADS), 0, g, l, ex->d_img, ex->d_pyr,
+                   ex->d_lut);
+    }
+  }
   if ((rc = stage_event(ex, 1))) return rc;
   if (g.totalFast > 0)
     ORBFE_LAUNCH(ex, k_fast_cells, dim3(g.totalFast, n), dim3(ORBFE_FAST_THREADS), ex->fastSmem, g, ex->d_pyr,
@@ -340,7 +387,8 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
   ORBFE_LAUNCH(ex, k_octree, dim3(g.nlevels, n), dim3(ORBFE_OCT_THREADS), ex->octSmem, g, ex->d_cellCnt, ex->d_cellList,
                ex->oct, ex->d_lvlKp, ex->d_lvlCnt, ex->d_err);
   if ((rc = stage_event(ex, 3))) return rc;
-  ORBFE_LAUNCH(ex, k_blur, dim3(g.totalTiles, n), dim3(ORBFE_BLUR_THREADS), 0, g, ex->d_pyr, ex->d_blur);
+  ORBFE_LAUNCH(ex, k_blur, dim3((g.totalTiles + ORBFE_BLUR_THREADS / 32 - 1) / (ORBFE_BLUR_THREADS / 32), n),
+               dim3(ORBFE_BLUR_THREADS), 0, g, ex->d_pyr, ex->d_blur);  // one warp per strip
   if ((rc = stage_event(ex, 4))) return rc;
   ORBFE_LAUNCH(ex, k_orient_describe, dim3((g.totalOut + ORBFE_DESC_THREADS - 1) / ORBFE_DESC_THREADS, n),  // 32 keypoints per warp
                dim3(ORBFE_DESC_THREADS), 0, g, ex->d_pyr, ex->d_blur, ex->d_lvlKp, ex->d_lvlCnt, ex->d_kps, ex->d_desc,

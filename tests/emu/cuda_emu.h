@@ -302,6 +302,14 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
   const unsigned long long v = ((unsigned long long)hi << 32) | lo;
   return (unsigned)(v >> (sh & 31));
 }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+  for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+  return c;
+}
+static inline unsigned __dp2a_lo(unsigned a, unsigned b, unsigned c) {
+  return c + (a & 0xffffu) * (b & 0xffu) + (a >> 16) * ((b >> 8) & 0xffu);
+}
 static inline unsigned __vabsdiffu4(unsigned a, unsigned b) {
   unsigned r = 0;
   for (int i = 0; i < 4; ++i) { const int x = (a >> (8 * i)) & 0xff, y = (b >> (8 * i)) & 0xff; r |= (unsigned)std::abs(x - y) << (8 * i); }
