@@ -214,6 +214,14 @@ def run_ours(args):
     baseline = BF / FX
     buf = ex.make_buffers(n_img, stereo=True)
 
+    def pinned_buffers(e):
+        """make_buffers layout in pinned host memory (D2H lands here without a staging copy)"""
+        cap = e.max_keypoints()
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+        return dict(kps=mk((n_img, cap, 28), torch.uint8).view(orbfe.KP_DTYPE).reshape(n_img, cap),
+                    desc=mk((n_img, cap, 32), torch.uint8), n=mk((n_img,), torch.int32), cap=cap,
+                    ur=mk((n_img, cap), torch.float32), depth=mk((n_img, cap), torch.float32))
+
     def step_resident():
         ex.run(n_img)
         ex.run_stereo(B, BF, baseline)
@@ -248,15 +256,33 @@ def run_ours(args):
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end-to-end leg (host buffers, copies inside the timed region) ---------------------------
-    for _ in range(max(args.warmup, 3)):
-        step_e2e()
+    # two handles (= two streams) alternate steps so that the H2D copy of step k+1 overlaps the kernels
+    # of step k; every step still uploads its own inputs and downloads its own results.
+    ex2 = orbfe.ORBextractor(NFEATURES, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_images=n_img, max_size=(W, H), lib=L)
+    lanes = [(ex, pinned_buffers(ex)), (ex2, pinned_buffers(ex2))]
+
+    def step_e2e_pipelined(k):
+        e, b = lanes[k & 1]
+        e.sync()  # the previous step on this handle (2 steps ago) has delivered its results
+        e.upload_ptrs(ptrs, n_img, W, H, W)
+        e.run(n_img)
+        e.run_stereo(B, BF, baseline)
+        e.download_async(n_img, b)
+
+    for k in range(2 * max(args.warmup, 3)):
+        step_e2e_pipelined(k)
+    ex.sync(); ex2.sync()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    ex.sync()
+    for k in range(args.steps):
+        step_e2e_pipelined(k)
+    ex.sync(); ex2.sync()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     barrier()
+    buf = lanes[0][1]
+    for kk in ("kps", "desc", "ur", "depth", "n"):  # both lanes delivered identical results for identical inputs
+        assert np.array_equal(lanes[0][1][kk], lanes[1][1][kk]) or args.steps < 2, kk
+    ex2.close()
     clocks = sampler.stop()
     e2e_value = world * B * args.steps / t_e2e
     cap = buf["cap"]
@@ -329,7 +355,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         cores = host_cores()
         v1, s1, _, _ = cpu_reference_throughput(pairs, cores, cores)
-        reps = int(min(max(12.0 / max(s1, 1e-3), 1), 40))
+        reps = int(min(max(12.0 / max(s1, 1e-3), 1), 400))  # ~12 s of host work
         n = cores * reps
         v, sec, ckps, cmt = cpu_reference_throughput(pairs, n, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -103,6 +103,12 @@ int orbfe_run_stereo(orbfe_extractor* ex, int n_pairs, float bf, float baseline)
  * u_right/depth (n_imgs*capacity floats, may be NULL) are filled for even (left) slots. */
 int orbfe_download(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t* desc, int capacity,
                    int* n_out, float* u_right, float* depth);
+/* same, without the staging copy and without waiting: capacity must equal
+ * orbfe_extractor_max_keypoints() so that the host arrays mirror the device layout; the D2H copies
+ * are enqueued straight into the caller's (ideally pinned) arrays, which are valid after orbfe_sync.
+ * Lets a caller keep two handles in flight (upload of batch k+1 overlapping compute of batch k). */
+int orbfe_download_async(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t* desc, int capacity,
+                         int* n_out, float* u_right, float* depth);
 int orbfe_sync(orbfe_extractor* ex);
 /* CUDA-event timing on the handle's own stream: record event `slot` (0..63) now; elapsed ms
  * between two recorded slots (after orbfe_sync). */

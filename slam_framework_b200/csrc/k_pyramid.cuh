@@ -85,7 +85,7 @@ k_pyramid_level(const __grid_constant__ Geom g, const int level, const uint8_t* 
 // aligned words, aligns them with 2 funnel shifts and forms the 4 horizontal interpolations with one
 // funnel shift + one IDP.2A each; horizontally interpolated rows are cached across destination rows
 // (consecutive rows share a source row), and the vertical blend (b*(T>>4))>>16 is one IMAD.HI.
-#define ORBFE_PYR_ROWS 32
+#define ORBFE_PYR_ROWS 8
 
 struct PyrWordLut {
   int srcW;          // first source word of the padded source row

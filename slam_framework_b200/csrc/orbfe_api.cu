@@ -331,6 +331,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   CUDA_TRY(cudaMalloc(&ex->d_sad, S * g.totalOut * sizeof(int)));
   CUDA_TRY(cudaMalloc(&ex->d_nMatched, S * sizeof(int)));
   CUDA_TRY(cudaMallocHost(&ex->h_n, (2 * S + 1) * sizeof(int)));
+  memset(ex->h_n, 0, (2 * S + 1) * sizeof(int));
   CUDA_TRY(cudaMallocHost(&ex->h_kps, S * g.totalOut * sizeof(orbfe_kp_dev)));
   CUDA_TRY(cudaMallocHost(&ex->h_desc, S * g.totalOut * 32));
   CUDA_TRY(cudaMallocHost(&ex->h_uR, S * g.totalOut * sizeof(float)));
@@ -610,10 +611,36 @@ int orbfe_download(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t
   return ORBFE_OK;
 }
 
+int orbfe_download_async(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t* desc, int capacity, int* n_out,
+                         float* u_right, float* depth) {
+  int rc = check_images(ex, 0, n_imgs);
+  if (rc) return rc;
+  if (!ex->configured) return orbfe_fail(ORBFE_ERR_INVALID, "orbfe_download_async before any orbfe_upload");
+  if (!n_out) return orbfe_fail(ORBFE_ERR_INVALID, "bad output arguments");
+  if (capacity != ex->g.totalOut)
+    return orbfe_fail(ORBFE_ERR_INVALID, "orbfe_download_async needs capacity == orbfe_extractor_max_keypoints() (%d)", ex->g.totalOut);
+  if (n_imgs == 0) return ORBFE_OK;
+  CUDA_TRY(cudaSetDevice(ex->device));
+  const size_t T = (size_t)ex->g.totalOut, n = (size_t)n_imgs;
+  CUDA_TRY(cudaMemcpyAsync(n_out, ex->d_nKp, n * sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
+  CUDA_TRY(cudaMemcpyAsync(ex->h_n + 2 * (size_t)ex->S, ex->d_err, sizeof(int), cudaMemcpyDeviceToHost, ex->stream));  // checked by orbfe_sync
+  if (kps) CUDA_TRY(cudaMemcpyAsync(kps, ex->d_kps, n * T * sizeof(orbfe_kp_dev), cudaMemcpyDeviceToHost, ex->stream));
+  if (desc) CUDA_TRY(cudaMemcpyAsync(desc, ex->d_desc, n * T * 32, cudaMemcpyDeviceToHost, ex->stream));
+  if (u_right) CUDA_TRY(cudaMemcpyAsync(u_right, ex->d_uR, n * T * sizeof(float), cudaMemcpyDeviceToHost, ex->stream));
+  if (depth) CUDA_TRY(cudaMemcpyAsync(depth, ex->d_depth, n * T * sizeof(float), cudaMemcpyDeviceToHost, ex->stream));
+  return ORBFE_OK;
+}
+
 int orbfe_sync(orbfe_extractor* ex) {
   if (!ex) return orbfe_fail(ORBFE_ERR_INVALID, "null extractor handle");
   CUDA_TRY(cudaSetDevice(ex->device));
   CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  if (ex->configured && ex->h_n[2 * (size_t)ex->S] != 0) {
+    const int flag = ex->h_n[2 * (size_t)ex->S];
+    ex->h_n[2 * (size_t)ex->S] = 0;
+    cudaMemsetAsync(ex->d_err, 0, sizeof(int), ex->stream);
+    return orbfe_fail(ORBFE_ERR_CUDA, "quad-tree kernel reported an internal capacity error (flag %d)", flag);
+  }
   return ORBFE_OK;
 }
 

@@ -39,7 +39,8 @@ class _Params(C.Structure):
 EXPORTS = [
     "orbfe_last_error", "orbfe_version", "orbfe_device_count", "orbfe_extractor_create", "orbfe_extractor_destroy",
     "orbfe_extractor_tables", "orbfe_extractor_max_keypoints", "orbfe_extract", "orbfe_extract_batch",
-    "orbfe_pyramid_level", "orbfe_upload", "orbfe_run", "orbfe_run_stereo", "orbfe_download", "orbfe_sync",
+    "orbfe_pyramid_level", "orbfe_upload", "orbfe_run", "orbfe_run_stereo", "orbfe_download", "orbfe_download_async",
+    "orbfe_sync",
     "orbfe_event_record", "orbfe_event_elapsed_ms", "orbfe_set_stage_timing", "orbfe_stage_summary",
     "orbfe_launch_count",
     "orbfe_debug_candidates", "orbfe_debug_level_keypoints", "orbfe_debug_blurred", "orbfe_stereo_match",
@@ -84,6 +85,7 @@ def load(path=None, _test_emulation=False):
     L.orbfe_run.argtypes = [vp, i]
     L.orbfe_run_stereo.argtypes = [vp, i, f, f]
     L.orbfe_download.argtypes = [vp, i, vp, vp, i, vp, vp, vp]
+    L.orbfe_download_async.argtypes = [vp, i, vp, vp, i, vp, vp, vp]
     L.orbfe_sync.argtypes = [vp]
     L.orbfe_event_record.argtypes = [vp, i]
     L.orbfe_event_elapsed_ms.argtypes = [vp, i, i, vp]
@@ -249,6 +251,12 @@ class ORBextractor:
     def download(self, n_imgs, buf):
         _check(self.L, self.L.orbfe_download(self.h, n_imgs, _p(buf["kps"]), _p(buf["desc"]), buf["cap"], _p(buf["n"]),
                                             _p(buf["ur"]), _p(buf["depth"])))
+        return buf
+
+    def download_async(self, n_imgs, buf):
+        """enqueue the D2H copies straight into `buf` (make_buffers layout, ideally pinned); valid after sync()"""
+        _check(self.L, self.L.orbfe_download_async(self.h, n_imgs, _p(buf["kps"]), _p(buf["desc"]), buf["cap"],
+                                                  _p(buf["n"]), _p(buf["ur"]), _p(buf["depth"])))
         return buf
 
     def extract_batch(self, imgs):
