@@ -36,12 +36,15 @@ k_pyramid_level(const __grid_constant__ Geom g, const int level, const uint8_t* 
   const int y = orbfe_reflect101(py - ORBFE_EDGE, L.h);
   unsigned out = 0;
   if (level == 0) {
-    const uint8_t* src = img + (size_t)slot * g.imgStride + (size_t)y * g.imgPitch;
-    const int x0 = 4 * wx - ORBFE_EDGE;  // image column of byte 0 = 4*(wx-5)+1
+    const size_t rowByte = (size_t)slot * g.imgStride + (size_t)y * g.imgPitch;
+    const uint8_t* src = img + rowByte;
+    const int x0 = 4 * wx - ORBFE_EDGE;  // image column of byte 0
     if (x0 >= 0 && x0 + 3 < L.w) {
-      // interior: two aligned words of the image row, shifted by one byte (imgPitch is a multiple of 16)
-      const unsigned* s4 = reinterpret_cast<const unsigned*>(src) + (wx - 5);
-      out = __funnelshift_r(__ldg(s4), __ldg(s4 + 1), 8);
+      // interior: the image block is tightly packed (imgPitch == width, rows start at any byte), so
+      // the 4 pixels come from the two aligned words around them (the block has 16 B of slack)
+      const size_t a = rowByte + (size_t)x0;
+      const unsigned* s4 = reinterpret_cast<const unsigned*>(img) + (a >> 2);
+      out = __funnelshift_r(__ldg(s4), __ldg(s4 + 1), 8 * (int)(a & 3));
     } else {
 #pragma unroll
       for (int b = 0; b < 4; ++b) {

@@ -156,8 +156,10 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   memset(&g, 0, sizeof(g));
   const int nl = ex->p.nlevels;
   g.nlevels = nl; g.w0 = w0; g.h0 = h0; g.iniTh = ex->p.ini_th_fast; g.minTh = ex->p.min_th_fast;
-  g.imgPitch = align_up(w0, 16);
-  g.imgStride = (unsigned)align_up_sz((size_t)g.imgPitch * h0, 256);
+  // input frames are kept tightly packed (pitch == width) so that one contiguous H2D copy per image
+  // (or per batch, when the host frames are contiguous) feeds them; k_pyramid_level re-aligns on the fly
+  g.imgPitch = w0;
+  g.imgStride = (unsigned)align_up_sz((size_t)w0 * h0, 4);
   size_t pyrOff = 0, blurOff = 0, cellListOff = 0, candOff = 0, nodeOff = 0;
   int cellBase = 0, outOff = 0, tileBase = 0, lutOff = 0, maxSort = 1;
   int maxCw = 8, maxInnerH = 1, fastBase = 0, maxQueue = 1;
@@ -301,7 +303,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   ex->bestStride = (size_t)g.nodeStride * 5 / 4 + 16 * ORBFE_MAX_LEVELS;
 
   const size_t S = (size_t)ex->S;
-  CUDA_TRY(cudaMalloc(&ex->d_img, S * g.imgStride));
+  CUDA_TRY(cudaMalloc(&ex->d_img, S * g.imgStride + 16));
   CUDA_TRY(cudaMalloc(&ex->d_pyr, S * g.pyrStride));
   CUDA_TRY(cudaMalloc(&ex->d_blur, S * g.blurStride));
   CUDA_TRY(cudaMalloc(&ex->d_cellCnt, S * std::max(g.totalCells, 1) * sizeof(int)));
@@ -514,10 +516,24 @@ int orbfe_upload(orbfe_extractor* ex, int first_slot, const uint8_t* const* imgs
   if (!imgs || w <= 0 || h <= 0 || stride < (size_t)w) return orbfe_fail(ORBFE_ERR_INVALID, "bad image arguments");
   CUDA_TRY(cudaSetDevice(ex->device));
   if ((rc = configure(ex, w, h))) return rc;
-  for (int i = 0; i < n_imgs; ++i) {
+  for (int i = 0; i < n_imgs; ++i)
     if (!imgs[i]) return orbfe_fail(ORBFE_ERR_INVALID, "null image %d", i);
-    CUDA_TRY(cudaMemcpy2DAsync(ex->d_img + (size_t)(first_slot + i) * ex->g.imgStride, ex->g.imgPitch, imgs[i], stride,
-                               (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ex->stream));
+  const size_t bytes = (size_t)w * h;
+  if (stride == (size_t)w) {
+    // tightly packed frames: one 1-D copy per run of frames that are contiguous on the host too
+    int i = 0;
+    while (i < n_imgs) {
+      int j = i + 1;
+      if (ex->g.imgStride == bytes)
+        while (j < n_imgs && imgs[j] == imgs[j - 1] + bytes) ++j;
+      CUDA_TRY(cudaMemcpyAsync(ex->d_img + (size_t)(first_slot + i) * ex->g.imgStride, imgs[i], (size_t)(j - i) * bytes,
+                               cudaMemcpyHostToDevice, ex->stream));
+      i = j;
+    }
+  } else {
+    for (int i = 0; i < n_imgs; ++i)
+      CUDA_TRY(cudaMemcpy2DAsync(ex->d_img + (size_t)(first_slot + i) * ex->g.imgStride, ex->g.imgPitch, imgs[i], stride,
+                                 (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ex->stream));
   }
   return ORBFE_OK;
 }
