@@ -1,0 +1,51 @@
+"""The header-only C++ drop-in shim (include/orbfe_shim.hpp) compiles against the OpenCV stand-ins
+(include/cv_compat.h; real OpenCV C++ is absent here), links liborbfe.so, and - on the GPU box - produces
+the oracle's keypoints, descriptors and stereo matches when driven like the reference's Frame ctor."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from slam_framework_b200 import build as B
+from slam_framework_b200 import orbfe, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "shim", "shim_demo")
+
+
+def build_demo():
+    lib = B.build()
+    src = os.path.join(ROOT, "tests", "shim", "shim_demo.cpp")
+    deps = [src, os.path.join(ROOT, "include", "orbfe_shim.hpp"), os.path.join(ROOT, "include", "cv_compat.h"), lib]
+    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
+        subprocess.check_call(["g++", "-std=c++11", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
+                               lib, "-Wl,-rpath," + os.path.dirname(lib), "-pthread"])
+    return EXE
+
+
+def test_shim_compiles_as_cpp11_and_links():
+    out = subprocess.check_output([build_demo(), "--link-check"], text=True)
+    assert out.startswith("orbfe 0.1 (sm_100a)")
+
+
+@pytest.mark.gpu
+def test_shim_matches_oracle(tmp_path):
+    import oracle_lib as O
+    l, r = synth.stereo_pair(seed=77)
+    l.tofile(tmp_path / "l.raw"); r.tofile(tmp_path / "r.raw")
+    out = subprocess.check_output([build_demo(), "1241", "376", str(tmp_path / "l.raw"), str(tmp_path / "r.raw"),
+                                   str(tmp_path / "o")], text=True)
+    nl, nr, pw, ph = map(int, out.split())
+    oL, oR = O.Extractor(), O.Extractor()
+    okl, odl = oL.extract(l); okr, odr = oR.extract(r)
+    kl = np.fromfile(tmp_path / "o.kl", orbfe.KP_DTYPE); kr = np.fromfile(tmp_path / "o.kr", orbfe.KP_DTYPE)
+    assert nl == len(okl) and nr == len(okr)
+    assert np.array_equal(kl, okl) and np.array_equal(kr, okr)
+    assert np.array_equal(np.fromfile(tmp_path / "o.dl", np.uint8).reshape(-1, 32), odl)
+    assert np.array_equal(np.fromfile(tmp_path / "o.dr", np.uint8).reshape(-1, 32), odr)
+    baseline = float(np.float32(386.1448) / np.float32(718.856))  # the demo divides in float
+    on, our, odp = O.stereo_match(oL, oR, okl, odl, okr, odr, 386.1448, baseline)
+    assert np.array_equal(np.fromfile(tmp_path / "o.ur", np.float32), our)
+    assert np.array_equal(np.fromfile(tmp_path / "o.depth", np.float32), odp)
+    assert np.array_equal(np.fromfile(tmp_path / "o.pyr3", np.uint8).reshape(ph, pw), oL.pyramid_level(3))
