@@ -17,7 +17,9 @@
 
 #define ORBFE_DESC_THREADS 64
 
-__constant__ signed char c_orb_pattern[1024] = {
+// global (L1-cached) rather than __constant__: each lane reads ITS 32 bytes, and per-lane addresses in
+// the constant bank are serialised by the address-divergence unit (58 % ADU busy in the ncu profile)
+static __device__ __align__(16) const signed char d_orb_pattern[1024] = {
 #include "orb_pattern_31.inc"
 };
 // circular patch half-widths (orb_extractor.cpp:393-410)
@@ -173,10 +175,15 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
   }
   // ---- E7: rotated BRIEF on the blurred level; lane i -> descriptor byte i
   float px[16], py[16];
+  {
+    const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(d_orb_pattern) + 2 * lane);
+    const uint4 p1 = __ldg(reinterpret_cast<const uint4*>(d_orb_pattern) + 2 * lane + 1);
+    const unsigned w[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
 #pragma unroll
-  for (int t = 0; t < 16; ++t) {
-    px[t] = (float)c_orb_pattern[32 * lane + 2 * t];
-    py[t] = (float)c_orb_pattern[32 * lane + 2 * t + 1];
+    for (int t = 0; t < 16; ++t) {
+      px[t] = (float)(signed char)((w[t >> 1] >> (16 * (t & 1))) & 0xffu);
+      py[t] = (float)(signed char)((w[t >> 1] >> (16 * (t & 1) + 8)) & 0xffu);
+    }
   }
   const uint8_t* blurSlot = blur + (size_t)slot * g.blurStride;
   uint8_t* dOut = desc + ((size_t)slot * g.totalOut + base) * 32;

@@ -1,8 +1,7 @@
 // k_stereo.cuh -- S1-S4: Frame::ComputeStereoMatches (src/data/frame.cpp:406-577).
+//   k_stereo_rows (CTA per pair): S1, the reference's row table (:415-433).
 //   k_stereo_search (warp per left keypoint):
-//     S1/S2  the reference's row table (:415-433) is a membership test: right keypoint iR is a
-//            candidate of left row (int)vL iff floor(yR - r) <= row <= ceil(yR + r),
-//            r = 2*scale[octR].  Lanes stride over the right keypoints in ascending iR, apply
+//     S2     lanes stride over vRowIndices[(int)vL], apply
 //            the octave (+-1) and uR in [uL-maxD, uL] filters, compute the 256-bit Hamming
 //            distance with __popc, and a warp-shuffle argmin on (dist, iR) reproduces the strict
 //            '<' scan from bestDist = TH_HIGH (ties -> lowest iR) (:444-488).
@@ -30,7 +29,53 @@ struct StereoPair {
   float* uR;                    // outputs, indexed by left keypoint
   float* depth;
   int* sad;
+  int* rowStart;                // S1 row table of the right image: nRows+1 offsets ...
+  int* rowItems;                // ... into right-keypoint indices (k_stereo_rows)
+  int rowCap;
 };
+
+// S1 (frame.cpp:415-433): right keypoint iR is pushed into every row yi in [floor(y-r), ceil(y+r)],
+// r = 2*scale[octave].  One CTA per pair builds the table (count, scan, fill); the order inside a row
+// does not matter because the search reduces on (distance, iR).
+__global__ void __launch_bounds__(256)
+k_stereo_rows(const __grid_constant__ Geom g, const StereoPair* __restrict__ pairs, const int maxKp) {
+  ORBFE_DYN_SMEM(smem);
+  int* s_cnt = reinterpret_cast<int*>(smem);  // nRows + 1
+  __shared__ int s_scan[33];
+  const StereoPair P = pairs[blockIdx.x];
+  const int nRows = g.lv[0].h;
+  const int nR = min(*P.nR, maxKp);
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int r = tid; r <= nRows; r += T) s_cnt[r] = 0;
+  __syncthreads();
+  for (int iR = tid; iR < nR; iR += T) {
+    const orbfe_kp_dev kr = P.kpR[iR];
+    const float r = __fmul_rn(2.0f, g.lv[kr.octave].scale);
+    const int maxr = min((int)ceilf(__fadd_rn(kr.y, r)), nRows - 1);
+    const int minr = max((int)floorf(__fsub_rn(kr.y, r)), 0);
+    for (int yi = minr; yi <= maxr; ++yi) atomicAdd(&s_cnt[yi], 1);
+  }
+  __syncthreads();
+  const int per = (nRows + T - 1) / T;
+  const int r0 = min(tid * per, nRows), r1 = min(r0 + per, nRows);
+  int sum = 0;
+  for (int r = r0; r < r1; ++r) sum += s_cnt[r];
+  int total;
+  int run = orbfe_block_exscan(sum, s_scan, &total);
+  for (int r = r0; r < r1; ++r) { const int c = s_cnt[r]; P.rowStart[r] = run; s_cnt[r] = run; run += c; }
+  if (tid == 0) P.rowStart[nRows] = min(total, P.rowCap);
+  __syncthreads();
+  for (int iR = tid; iR < nR; iR += T) {
+    const orbfe_kp_dev kr = P.kpR[iR];
+    const float r = __fmul_rn(2.0f, g.lv[kr.octave].scale);
+    const int maxr = min((int)ceilf(__fadd_rn(kr.y, r)), nRows - 1);
+    const int minr = max((int)floorf(__fsub_rn(kr.y, r)), 0);
+    for (int yi = minr; yi <= maxr; ++yi) {
+      const int pos = atomicAdd(&s_cnt[yi], 1);
+      if (pos < P.rowCap) P.rowItems[pos] = iR;
+    }
+  }
+}
 
 __device__ __forceinline__ int orbfe_hamming256(const uint4 a0, const uint4 a1, const uint8_t* __restrict__ b) {
   const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(b));
@@ -62,12 +107,10 @@ k_stereo_search(const __grid_constant__ Geom g, const StereoPair* __restrict__ p
   if (row >= 0 && row < nRows && !(maxU < 0)) {
     const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(P.descL + (size_t)iL * 32));
     const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(P.descL + (size_t)iL * 32) + 1);
-    for (int iR = lane; iR < nR; iR += 32) {
+    const int cb = P.rowStart[row], ce = min(P.rowStart[row + 1], P.rowCap);
+    for (int c = cb + lane; c < ce; c += 32) {
+      const int iR = P.rowItems[c];  // vRowIndices[row] (frame.cpp:450)
       const orbfe_kp_dev kr = P.kpR[iR];
-      const float r = __fmul_rn(2.0f, g.lv[kr.octave].scale);
-      const int maxr = (int)ceilf(__fadd_rn(kr.y, r));
-      const int minr = (int)floorf(__fsub_rn(kr.y, r));
-      if (row < minr || row > maxr) continue;
       if (kr.octave < levelL - 1 || kr.octave > levelL + 1) continue;
       if (kr.x >= minU && kr.x <= maxU) {
         const int dist = orbfe_hamming256(a0, a1, P.descR + (size_t)iR * 32);

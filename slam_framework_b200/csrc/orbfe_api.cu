@@ -78,6 +78,10 @@ struct orbfe_extractor {
   float* d_depth = nullptr;
   int* d_sad = nullptr;
   int* d_nMatched = nullptr;
+  int* d_rowStart = nullptr;        // per pair: h0 + 1 offsets
+  int* d_rowItems = nullptr;        // per pair: rowCap indices
+  int rowCap = 0;
+  size_t rowSmem = 0;
   // pinned staging
   int* h_n = nullptr;          // S counts + S matched + 1 err
   orbfe_kp_dev* h_kps = nullptr;
@@ -132,7 +136,8 @@ static void free_arena(orbfe_extractor* ex) {
   cudaFree(ex->oct.childCnt); cudaFree(ex->oct.childSlot); cudaFree(ex->oct.best); cudaFree(ex->oct.finSeq);
   cudaFree(ex->oct.finKey); cudaFree(ex->d_lvlKp); cudaFree(ex->d_lvlCnt); cudaFree(ex->d_kps); cudaFree(ex->d_desc);
   cudaFree(ex->d_nKp); cudaFree(ex->d_lut); cudaFree(ex->d_wlut); ex->d_wlut = nullptr; cudaFree(ex->d_err); cudaFree(ex->d_pairs); cudaFree(ex->d_uR);
-  cudaFree(ex->d_depth); cudaFree(ex->d_sad); cudaFree(ex->d_nMatched);
+  cudaFree(ex->d_depth); cudaFree(ex->d_sad); cudaFree(ex->d_nMatched); cudaFree(ex->d_rowStart); cudaFree(ex->d_rowItems);
+  ex->d_rowStart = ex->d_rowItems = nullptr;
   cudaFreeHost(ex->h_n); cudaFreeHost(ex->h_kps); cudaFreeHost(ex->h_desc); cudaFreeHost(ex->h_uR);
   cudaFreeHost(ex->h_depth); cudaFreeHost(ex->h_pairs);
   ex->d_img = ex->d_pyr = ex->d_blur = nullptr; ex->d_cellCnt = nullptr; ex->d_cellList = nullptr;
@@ -332,6 +337,11 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   CUDA_TRY(cudaMalloc(&ex->d_depth, S * g.totalOut * sizeof(float)));
   CUDA_TRY(cudaMalloc(&ex->d_sad, S * g.totalOut * sizeof(int)));
   CUDA_TRY(cudaMalloc(&ex->d_nMatched, S * sizeof(int)));
+  // stereo row table: a right keypoint spans at most 2*r+3 rows, r = 2*scale[octave] (frame.cpp:427-433)
+  ex->rowCap = g.totalOut * (2 * (int)std::ceil(2.0f * ex->scale[nl - 1]) + 3);
+  ex->rowSmem = (size_t)(h0 + 1) * sizeof(int);
+  CUDA_TRY(cudaMalloc(&ex->d_rowStart, S * (size_t)(h0 + 1) * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->d_rowItems, S * (size_t)ex->rowCap * sizeof(int)));
   CUDA_TRY(cudaMallocHost(&ex->h_n, (2 * S + 1) * sizeof(int)));
   memset(ex->h_n, 0, (2 * S + 1) * sizeof(int));
   CUDA_TRY(cudaMallocHost(&ex->h_kps, S * g.totalOut * sizeof(orbfe_kp_dev)));
@@ -348,6 +358,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
 #ifndef ORBFE_EMU
   CUDA_TRY(cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
   CUDA_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octSmem));
+  CUDA_TRY(cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->rowSmem));
 #endif
   ex->configured = true;
   return ORBFE_OK;
@@ -558,11 +569,14 @@ static void fill_pairs_same_handle(orbfe_extractor* ex, int n_pairs) {
     P.descL = ex->d_desc + a * g.totalOut * 32; P.descR = ex->d_desc + b * g.totalOut * 32;
     P.nL = ex->d_nKp + a; P.nR = ex->d_nKp + b;
     P.uR = ex->d_uR + a * g.totalOut; P.depth = ex->d_depth + a * g.totalOut; P.sad = ex->d_sad + a * g.totalOut;
+    P.rowStart = ex->d_rowStart + (size_t)p * (g.h0 + 1); P.rowItems = ex->d_rowItems + (size_t)p * ex->rowCap;
+    P.rowCap = ex->rowCap;
   }
 }
 
 static int enqueue_stereo(orbfe_extractor* ex, int n_pairs, float bf, float baseline) {
   const Geom& g = ex->g;
+  ORBFE_LAUNCH(ex, k_stereo_rows, dim3(n_pairs), dim3(256), ex->rowSmem, g, ex->d_pairs, g.totalOut);
   ORBFE_LAUNCH(ex, k_stereo_search, dim3((g.totalOut + ORBFE_ST_THREADS / 32 - 1) / (ORBFE_ST_THREADS / 32), n_pairs),
                dim3(ORBFE_ST_THREADS), 0, g, ex->d_pairs, bf, baseline, g.totalOut);
   int rc;
@@ -841,6 +855,7 @@ int orbfe_stereo_match(orbfe_extractor* left, orbfe_extractor* right, int n_left
   P.descL = left->d_desc; P.descR = right->d_desc + rslot * right->g.totalOut * 32;
   P.nL = left->d_nKp; P.nR = right->d_nKp + rslot;
   P.uR = left->d_uR; P.depth = left->d_depth; P.sad = left->d_sad;
+  P.rowStart = left->d_rowStart; P.rowItems = left->d_rowItems; P.rowCap = left->rowCap;
   ex->pairsCached = 0;
   CUDA_TRY(cudaMemcpyAsync(ex->d_pairs, ex->h_pairs, sizeof(StereoPair), cudaMemcpyHostToDevice, ex->stream));
   int rc = enqueue_stereo(ex, 1, bf, baseline);
