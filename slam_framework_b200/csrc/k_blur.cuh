@@ -56,11 +56,14 @@ k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t*
     for (int j = 0; j < 4; ++j) H[s][j] = 0u;
   const int total = nrows + 6;
   for (int r0 = 0; r0 < total; r0 += 7) {
+    unsigned wl[7];  // the 7 row loads of this group are issued back to back (latency overlap)
+#pragma unroll
+    for (int s = 0; s < 7; ++s) wl[s] = r0 + s < total ? __ldg(src + (size_t)(r0 + s) * pitchW) : 0u;
 #pragma unroll
     for (int s = 0; s < 7; ++s) {
       const int r = r0 + s;
       if (r < total) {  // warp-uniform
-        const unsigned w0 = __ldg(src + (size_t)r * pitchW);
+        const unsigned w0 = wl[s];
         const unsigned w1 = __shfl_down_sync(0xffffffffu, w0, 1);
         const unsigned w2 = __shfl_down_sync(0xffffffffu, w0, 2);
         // horizontal sums of the 4 pixels of this word: bytes j..j+6 of (w0,w1,w2)

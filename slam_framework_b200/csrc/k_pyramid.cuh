@@ -84,33 +84,46 @@ k_pyramid_level(const __grid_constant__ Geom g, const int level, const uint8_t* 
 // ---- fast resize path (levels >= 1, scale factor <= 2, not the exact-2x INTER_AREA case) ------------
 // One warp = 32 consecutive words of the PADDED destination plane x ORBFE_PYR_ROWS rows.  Everything that
 // depends only on the column lives in registers for the whole strip (host-built PyrWordLut: source word,
-// byte shift, the 4 byte offsets and the packed 11-bit coefficient pairs); per SOURCE row the lane loads 3
-// aligned words, aligns them with 2 funnel shifts and forms the 4 horizontal interpolations with one
-// funnel shift + one IDP.2A each; horizontally interpolated rows are cached across destination rows
-// (consecutive rows share a source row), and the vertical blend (b*(T>>4))>>16 is one IMAD.HI.
+// byte shift, PRMT selectors and the packed 11-bit coefficient pairs); everything that depends only on
+// the row comes from one 16-byte PyrRowLut entry (source rows of the REFLECTED destination row, vertical
+// coefficients pre-shifted for IMAD.HI).  Per SOURCE row a lane loads 3 aligned words, aligns them with 2
+// funnel shifts and forms the 4 horizontal interpolations with one PRMT + one IDP.2A each.  The two
+// register sets of horizontally interpolated rows swap roles every destination row (loop unrolled by 2),
+// so the common "+1 source row" step re-uses the previous bottom row as the new top row without moves.
 #define ORBFE_PYR_ROWS 8
 
 struct PyrWordLut {
   int srcW;          // first source word of the padded source row
   int sh;            // 8 * (first source byte & 3)
-  unsigned offs;     // byte j = 8 * (offset of pixel j's left source byte inside the aligned window)
+  unsigned sel;      // byte j = PRMT selector picking pixel j's two source bytes from the aligned window
   unsigned cpack[4]; // c0 | c1 << 16 (cv::resize 11-bit coefficients)
 };
+struct PyrRowLut {
+  int s0, s1;        // source rows (level l-1 coordinates) of the vertical blend
+  unsigned b0, b1;   // vertical coefficients << 16
+};
 
-__device__ __forceinline__ void orbfe_hrow(const unsigned* __restrict__ srow, const PyrWordLut& W, const int (&sj)[4],
-                                           unsigned (&T)[4]) {
-  const unsigned w0 = __ldg(srow + W.srcW), w1 = __ldg(srow + W.srcW + 1), w2 = __ldg(srow + W.srcW + 2);
-  const unsigned lo = __funnelshift_r(w0, w1, W.sh), hi = __funnelshift_r(w1, w2, W.sh);
+__device__ __forceinline__ void orbfe_hrow(const unsigned* __restrict__ srow, const int srcW, const int sh,
+                                           const unsigned (&sel)[4], const unsigned (&cp)[4], unsigned (&T)[4]) {
+  const unsigned w0 = __ldg(srow + srcW), w1 = __ldg(srow + srcW + 1), w2 = __ldg(srow + srcW + 2);
+  const unsigned lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) T[j] = __dp2a_lo(cp[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;  // (S0*c0 + S1*c1) >> 4
+}
+
+__device__ __forceinline__ unsigned orbfe_vblend(const PyrRowLut R, const unsigned (&Tt)[4], const unsigned (&Tb)[4]) {
+  unsigned out = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const unsigned B = sj[j] >= 32 ? hi >> (sj[j] - 32) : __funnelshift_r(lo, hi, sj[j]);
-    T[j] = __dp2a_lo(W.cpack[j], B, 0u) >> 4;  // (S0*c0 + S1*c1) >> 4
+    const unsigned v = (__umulhi(R.b0, Tt[j]) + __umulhi(R.b1, Tb[j]) + 2u) >> 2;  // ((b0*(T0>>4))>>16 + (b1*(T1>>4))>>16 + 2) >> 2
+    out |= v << (8 * j);
   }
+  return out;
 }
 
 __global__ void __launch_bounds__(ORBFE_PYR_THREADS)
 k_pyramid_resize(const __grid_constant__ Geom g, const int level, uint8_t* __restrict__ pyr,
-                 const ResizeLut* __restrict__ lut, const PyrWordLut* __restrict__ wlut) {
+                 const PyrRowLut* __restrict__ rlut, const PyrWordLut* __restrict__ wlut) {
   const LevelGeom& L = g.lv[level];
   const LevelGeom& P = g.lv[level - 1];
   const int slot = blockIdx.y;
@@ -123,45 +136,29 @@ k_pyramid_resize(const __grid_constant__ Geom g, const int level, uint8_t* __res
   if (py0 >= ph) return;
   const int wx = min(tx * 32 + lane, L.pyrWords - 1);  // duplicate lanes rewrite the last word with the same value
   const PyrWordLut W = wlut[L.wlutOff + wx];
-  int sj[4];
+  unsigned sel[4], cp[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) sj[j] = (int)((W.offs >> (8 * j)) & 0xffu);
+  for (int j = 0; j < 4; ++j) { sel[j] = (W.sel >> (8 * j)) & 0xffu; cp[j] = W.cpack[j]; }
   const int spitchW = P.pitch >> 2;
-  const unsigned* src = reinterpret_cast<const unsigned*>(pyr + (size_t)slot * g.pyrStride + P.planeOff);
-  unsigned* dst = reinterpret_cast<unsigned*>(pyr + (size_t)slot * g.pyrStride + L.planeOff) + wx;
+  const unsigned* src = reinterpret_cast<const unsigned*>(pyr + (size_t)slot * g.pyrStride + P.planeOff) + (size_t)ORBFE_EDGE * spitchW;
   const int dpitchW = L.pitch >> 2;
-  unsigned Ta[4] = {0, 0, 0, 0}, Tb[4] = {0, 0, 0, 0};
+  unsigned* dst = reinterpret_cast<unsigned*>(pyr + (size_t)slot * g.pyrStride + L.planeOff) + (size_t)py0 * dpitchW + wx;
+  const PyrRowLut* rl = rlut + L.rlutOff + py0;
+  unsigned TA[4] = {0, 0, 0, 0}, TB[4] = {0, 0, 0, 0};
   int ra = -1, rb = -1;
-  const int pyEnd = min(py0 + ORBFE_PYR_ROWS, ph);
-  for (int py = py0; py < pyEnd; ++py) {
-    const int y = orbfe_reflect101(py - ORBFE_EDGE, L.h);
-    const ResizeLut ly = lut[L.lutYOff + y];
-    const int s0 = ly.ofs, s1 = min(ly.ofs + 1, P.h - 1);
-    // warp-uniform row cache
-    if (s0 == rb) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { const unsigned t = Ta[j]; Ta[j] = Tb[j]; Tb[j] = t; }
-      const int t = ra; ra = rb; rb = t;
-    } else if (s0 != ra) {
-      orbfe_hrow(src + (size_t)(s0 + ORBFE_EDGE) * spitchW, W, sj, Ta);
-      ra = s0;
+  const int nrows = min(ORBFE_PYR_ROWS, ph - py0);
+  for (int r = 0; r < nrows; r += 2) {
+    {  // even row: top = TA, bottom = TB
+      const PyrRowLut R = rl[r];
+      if (ra != R.s0) { orbfe_hrow(src + (size_t)R.s0 * spitchW, W.srcW, W.sh, sel, cp, TA); ra = R.s0; }
+      if (rb != R.s1) { orbfe_hrow(src + (size_t)R.s1 * spitchW, W.srcW, W.sh, sel, cp, TB); rb = R.s1; }
+      dst[(size_t)r * dpitchW] = orbfe_vblend(R, TA, TB);
     }
-    if (s1 != rb) {
-      if (s1 == ra) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) Tb[j] = Ta[j];
-      } else {
-        orbfe_hrow(src + (size_t)(s1 + ORBFE_EDGE) * spitchW, W, sj, Tb);
-      }
-      rb = s1;
+    if (r + 1 < nrows) {  // odd row: roles swapped, so a "+1 source row" step re-uses TB as the top row
+      const PyrRowLut R = rl[r + 1];
+      if (rb != R.s0) { orbfe_hrow(src + (size_t)R.s0 * spitchW, W.srcW, W.sh, sel, cp, TB); rb = R.s0; }
+      if (ra != R.s1) { orbfe_hrow(src + (size_t)R.s1 * spitchW, W.srcW, W.sh, sel, cp, TA); ra = R.s1; }
+      dst[(size_t)(r + 1) * dpitchW] = orbfe_vblend(R, TB, TA);
     }
-    const unsigned b0 = (unsigned)ly.c0 << 16, b1 = (unsigned)ly.c1 << 16;
-    unsigned out = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const unsigned v = (__umulhi(b0, Ta[j]) + __umulhi(b1, Tb[j]) + 2u) >> 2;  // ((b0*(T0>>4))>>16 + (b1*(T1>>4))>>16 + 2) >> 2
-      out |= v << (8 * j);
-    }
-    dst[(size_t)py * dpitchW] = out;
   }
 }

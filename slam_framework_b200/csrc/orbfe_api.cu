@@ -71,6 +71,7 @@ struct orbfe_extractor {
   int* d_nKp = nullptr;
   ResizeLut* d_lut = nullptr;
   PyrWordLut* d_wlut = nullptr;
+  PyrRowLut* d_rlut = nullptr;
   int* d_err = nullptr;
   // stereo
   StereoPair* d_pairs = nullptr;
@@ -135,7 +136,7 @@ static void free_arena(orbfe_extractor* ex) {
   cudaFree(ex->oct.cand); cudaFree(ex->oct.knode); cudaFree(ex->oct.cellStart); cudaFree(ex->oct.nodes);
   cudaFree(ex->oct.childCnt); cudaFree(ex->oct.childSlot); cudaFree(ex->oct.best); cudaFree(ex->oct.finSeq);
   cudaFree(ex->oct.finKey); cudaFree(ex->d_lvlKp); cudaFree(ex->d_lvlCnt); cudaFree(ex->d_kps); cudaFree(ex->d_desc);
-  cudaFree(ex->d_nKp); cudaFree(ex->d_lut); cudaFree(ex->d_wlut); ex->d_wlut = nullptr; cudaFree(ex->d_err); cudaFree(ex->d_pairs); cudaFree(ex->d_uR);
+  cudaFree(ex->d_nKp); cudaFree(ex->d_lut); cudaFree(ex->d_wlut); ex->d_wlut = nullptr; cudaFree(ex->d_rlut); ex->d_rlut = nullptr; cudaFree(ex->d_err); cudaFree(ex->d_pairs); cudaFree(ex->d_uR);
   cudaFree(ex->d_depth); cudaFree(ex->d_sad); cudaFree(ex->d_nMatched); cudaFree(ex->d_rowStart); cudaFree(ex->d_rowItems);
   ex->d_rowStart = ex->d_rowItems = nullptr;
   cudaFreeHost(ex->h_n); cudaFreeHost(ex->h_kps); cudaFreeHost(ex->h_desc); cudaFreeHost(ex->h_uR);
@@ -170,6 +171,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   int maxCw = 8, maxInnerH = 1, fastBase = 0, maxQueue = 1;
   std::vector<ResizeLut> lut;
   std::vector<PyrWordLut> wlut;
+  std::vector<PyrRowLut> rlut;
   for (int l = 0; l < nl; ++l) {
     LevelGeom& L = g.lv[l];
     // level size (orb_extractor.cpp:1055-1056)
@@ -217,17 +219,29 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
         }
         words[k].srcW = mn >> 2;
         words[k].sh = 8 * (mn & 3);
-        words[k].offs = 0;
+        words[k].sel = 0;
         for (int j = 0; j < 4; ++j) {
-          const int pj = sb[j] - mn;
+          const int pj = sb[j] - mn;  // offset of the pixel's left source byte inside the aligned 8-byte window
           if (pj + 1 > 7) ok = false;
-          words[k].offs |= (unsigned)(8 * pj) << (8 * j);
+          words[k].sel |= (unsigned)((pj & 7) | (((pj + 1) & 7) << 4)) << (8 * j);
         }
         if ((words[k].srcW + 2) * 4 + 3 >= P.pitch) ok = false;  // the 3-word window must stay inside the row
       }
       if (ok) {
         wlut.insert(wlut.end(), words.begin(), words.end());
         L.fastResize = 1;
+        // per padded destination row: source rows + vertical coefficients of its REFLECT_101 image row
+        L.rlutOff = (int)rlut.size();
+        const ResizeLut* ly = lut.data() + L.lutYOff;
+        for (int py = 0; py < L.h + 2 * ORBFE_EDGE; ++py) {
+          int y = py - ORBFE_EDGE;
+          while (y < 0 || y >= L.h) y = y < 0 ? -y : 2 * (L.h - 1) - y;
+          if (L.h == 1) y = 0;
+          PyrRowLut R;
+          R.s0 = ly[y].ofs; R.s1 = std::min(ly[y].ofs + 1, P.h - 1);
+          R.b0 = (unsigned)(unsigned short)ly[y].c0 << 16; R.b1 = (unsigned)(unsigned short)ly[y].c1 << 16;
+          rlut.push_back(R);
+        }
       }
     }
     L.pyrBlocks = (L.pyrWords * (L.h + 2 * ORBFE_EDGE) + ORBFE_PYR_THREADS - 1) / ORBFE_PYR_THREADS;
@@ -251,7 +265,16 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
     L.cellListOff = (unsigned)cellListOff;
     cellListOff += (size_t)L.nCols * L.nRows * L.cellCap;
     // FAST CTAs: a band segment of fG cells (tile <= ~256 px wide)
-    L.fG = std::max(1, std::min(ORBFE_FAST_MAXG / 2, 256 / L.wCell));
+    // cells per CTA: minimise 32-lane word iterations per cell (tile width fG*wCell+6 px + <=3 alignment)
+    L.fG = 1;
+    {
+      double best = 1e30;
+      for (int fg = 1; fg <= ORBFE_FAST_MAXG / 2 && fg * L.wCell + 9 <= 300; ++fg) {
+        const int words = (fg * L.wCell + 9 + 3) / 4;
+        const double cost = (double)((words + 31) / 32) / fg;
+        if (cost <= best) { best = cost; L.fG = fg; }
+      }
+    }
     L.fSegs = L.nCols > 0 ? (L.nCols + L.fG - 1) / L.fG : 0;
     L.fastBase = fastBase;
     fastBase += L.fSegs * L.nRows;
@@ -331,6 +354,9 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   CUDA_TRY(cudaMalloc(&ex->d_wlut, std::max<size_t>(wlut.size(), 1) * sizeof(PyrWordLut)));
   if (!wlut.empty())
     CUDA_TRY(cudaMemcpyAsync(ex->d_wlut, wlut.data(), wlut.size() * sizeof(PyrWordLut), cudaMemcpyHostToDevice, ex->stream));
+  CUDA_TRY(cudaMalloc(&ex->d_rlut, std::max<size_t>(rlut.size(), 1) * sizeof(PyrRowLut)));
+  if (!rlut.empty())
+    CUDA_TRY(cudaMemcpyAsync(ex->d_rlut, rlut.data(), rlut.size() * sizeof(PyrRowLut), cudaMemcpyHostToDevice, ex->stream));
   CUDA_TRY(cudaMalloc(&ex->d_err, sizeof(int)));
   CUDA_TRY(cudaMalloc(&ex->d_pairs, S * sizeof(StereoPair)));
   CUDA_TRY(cudaMalloc(&ex->d_uR, S * g.totalOut * sizeof(float)));
@@ -387,7 +413,7 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
     if (L.fastResize) {
       const int tasks = ((L.pyrWords + 31) / 32) * ((L.h + 2 * ORBFE_EDGE + ORBFE_PYR_ROWS - 1) / ORBFE_PYR_ROWS);
       ORBFE_LAUNCH(ex, k_pyramid_resize, dim3((tasks + ORBFE_PYR_THREADS / 32 - 1) / (ORBFE_PYR_THREADS / 32), n),
-                   dim3(ORBFE_PYR_THREADS), 0, g, l, ex->d_pyr, ex->d_lut, ex->d_wlut);
+                   dim3(ORBFE_PYR_THREADS), 0, g, l, ex->d_pyr, ex->d_rlut, ex->d_wlut);
     } else {
       ORBFE_LAUNCH(ex, k_pyramid_level, dim3(L.pyrBlocks, n), dim3(ORBFE_PYR_THREADS), 0, g, l, ex->d_img, ex->d_pyr,
                    ex->d_lut);

@@ -33,7 +33,7 @@ struct LevelGeom {
   unsigned planeOff;     // byte offset of the padded plane inside a slot's pyramid block
   unsigned blurOff;      // byte offset of the blurred plane inside a slot's blur block
   int lutXOff, lutYOff;  // offsets into the resize LUT (entries)
-  int wlutOff, fastResize;  // per-word LUT of the fast resize kernel; 0 => generic k_pyramid_level
+  int wlutOff, rlutOff, fastResize;  // per-word LUT of the fast resize kernel; 0 => generic k_pyramid_level
   int area2;             // exact 2x decimation (OpenCV executes INTER_AREA)
   // FAST grid (orb_extractor.cpp:714-728)
   int nCols, nRows, wCell, hCell, maxBX, maxBY;

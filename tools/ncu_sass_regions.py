@@ -6,6 +6,10 @@ rep, kre = sys.argv[1], sys.argv[2]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 H = rows[1]; data = rows[2:]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0   # n-th launch matching the regex
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+lo = starts[which]; hi = starts[which + 1] if which + 1 < len(starts) else len(rows)
+H = rows[lo + 1]; data = rows[lo + 2:hi]
 ie, so, ss = H.index("Instructions Executed"), H.index("Source"), H.index("# Samples")
 data = [r for r in data if len(r) == len(H)]
 tot = sum(int(r[ie] or 0) for r in data)
