@@ -112,9 +112,41 @@ __device__ __forceinline__ int orbfe_fast_score3(const uint8_t* p, int tp) {
   return max(bright, -dark) - 1;
 }
 
+// two KITTI-shaped entries of the queue per lane: the same min/max networks on packed u16x2 lanes
+// (VIMNMX3.U16x2); differences are biased by +256 so that they stay positive 16-bit values
+__device__ __forceinline__ void orbfe_fast_score3_x2(const uint8_t* p0, const uint8_t* p1, int tp, int& s0, int& s1) {
+  const unsigned bias = (256u - p0[0]) | ((256u - p1[0]) << 16);
+  unsigned d[16];
+#define ORBFE_D(k, off) d[k] = ((unsigned)p0[off] | ((unsigned)p1[off] << 16)) + bias
+  ORBFE_D(0, 3 * tp);       ORBFE_D(1, 3 * tp + 1);   ORBFE_D(2, 2 * tp + 2);   ORBFE_D(3, tp + 3);
+  ORBFE_D(4, 3);            ORBFE_D(5, -tp + 3);      ORBFE_D(6, -2 * tp + 2);  ORBFE_D(7, -3 * tp + 1);
+  ORBFE_D(8, -3 * tp);      ORBFE_D(9, -3 * tp - 1);  ORBFE_D(10, -2 * tp - 2); ORBFE_D(11, -tp - 3);
+  ORBFE_D(12, -3);          ORBFE_D(13, tp - 3);      ORBFE_D(14, 2 * tp - 2);  ORBFE_D(15, 3 * tp - 1);
+#undef ORBFE_D
+  unsigned lo3[16], hi3[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    lo3[i] = __vimin3_u16x2(d[i], d[(i + 1) & 15], d[(i + 2) & 15]);
+    hi3[i] = __vimax3_u16x2(d[i], d[(i + 1) & 15], d[(i + 2) & 15]);
+  }
+  unsigned bright = 0u, dark = 0xffffffffu;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    bright = __vmaxu2(bright, __vimin3_u16x2(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]));
+    dark = __vminu2(dark, __vimax3_u16x2(hi3[i], hi3[(i + 3) & 15], hi3[(i + 6) & 15]));
+  }
+  s0 = max((int)(bright & 0xffffu) - 256, 256 - (int)(dark & 0xffffu)) - 1;
+  s1 = max((int)(bright >> 16) - 256, 256 - (int)(dark >> 16)) - 1;
+}
+
+// PW = compile-time tile pitch in words (64: the queue code IS the byte offset, row*pitch is a shift);
+// PW = 0: run-time pitch (cells wider than the fixed tile)
+template <int PW>
 __global__ void __launch_bounds__(ORBFE_FAST_THREADS)
 k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, int* __restrict__ cellCnt,
-             unsigned* __restrict__ cellList, const int pitchW, const int maxRows, const int queueCap) {
+             unsigned* __restrict__ cellList, const int pitchWArg, const int maxRows, const int queueCap) {
+  const int pitchW = PW ? PW : pitchWArg;
+  const int xbits = PW ? 8 : 9;  // queue code = y << xbits | x
   ORBFE_DYN_SMEM(smem);
   unsigned* tileW = reinterpret_cast<unsigned*>(smem);               // [maxRows][pitchW] pixels
   unsigned* scoreW = tileW + (size_t)maxRows * pitchW;               // [maxRows][pitchW] corner scores
@@ -201,30 +233,36 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
         }
         unsigned m = (f0 | f8) & (f4 | f12) & 0x80808080u;  // two adjacent compass points differ by > th
         if (m == 0u) continue;
+        if (xb < ix0 || xb + 3 >= ix1 || round == 1) {  // edge words of the band / fallback round: per-byte filter
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int x = xb + b;
-          if (x < ix0 || x >= ix1 || (round == 1 && s_any[s_colCell[x]])) m &= ~(0x80u << (8 * b));
+          for (int b = 0; b < 4; ++b) {
+            const int x = xb + b;
+            if (x < ix0 || x >= ix1 || (round == 1 && s_any[s_colCell[x]])) m &= ~(0x80u << (8 * b));
+          }
         }
         const int n = __popc(m);
         if (n == 0) continue;
         int pos = atomicAdd(&s_qn, n);
 #pragma unroll
         for (int b = 0; b < 4; ++b)
-          if ((m >> (8 * b + 7)) & 1u) { if (pos < queueCap) queue[pos] = (unsigned short)((y << 9) | (xb + b)); ++pos; }
+          if ((m >> (8 * b + 7)) & 1u) { if (pos < queueCap) queue[pos] = (unsigned short)((y << xbits) | (xb + b)); ++pos; }
       }
     __syncthreads();
     // ---- 2. exact score on the queue; corner at th <=> score >= th
     const int qn = min(s_qn, queueCap);
-    for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
-      const int code = queue[e], x = code & 511, y = code >> 9;
-      const int s = orbfe_fast_score3(tileB + y * pitchB + x, pitchB);
-      if (s >= th) scoreB[y * pitchB + x] = (uint8_t)s;
+    const int xmask = (1 << xbits) - 1;
+    for (int e = 2 * tid; e < qn; e += 2 * ORBFE_FAST_THREADS) {  // two queue entries per lane
+      const int c0 = queue[e], c1 = queue[min(e + 1, qn - 1)];
+      const int o0 = (c0 >> xbits) * pitchB + (c0 & xmask), o1 = (c1 >> xbits) * pitchB + (c1 & xmask);
+      int s0, s1;
+      orbfe_fast_score3_x2(tileB + o0, tileB + o1, pitchB, s0, s1);
+      if (s0 >= th) scoreB[o0] = (uint8_t)s0;
+      if (s1 >= th) scoreB[o1] = (uint8_t)s1;
     }
     __syncthreads();
     // ---- 3. NMS inside the cell; survivors -> bit plane + row masks; keypoint found => no fallback
     for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
-      const int code = queue[e], x = code & 511, y = code >> 9;
+      const int code = queue[e], x = code & xmask, y = code >> xbits;
       const uint8_t* c = scoreB + y * pitchB + x;
       const int s = c[0];
       if (s == 0) continue;
