@@ -46,20 +46,23 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force=False, verbose=False):
-    """Compile liborbfe.so if sources are newer; returns its path."""
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """Compile liborbfe.so if sources are newer; returns its path.  `out`/`defines` build a tuning
+    variant (-DNAME=VALUE) next to the product library for A/B runs (ORBFE_LIB=...)."""
+    global LIB
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    target = out or LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
+          ["-o", target + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building liborbfe.so")
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
-    os.replace(LIB + ".tmp", LIB)
-    return LIB
+    os.replace(target + ".tmp", target)
+    return target
 
 
 if __name__ == "__main__":

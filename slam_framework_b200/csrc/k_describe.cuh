@@ -15,7 +15,13 @@
 #pragma once
 #include "orbfe_common.cuh"
 
+#ifndef ORBFE_DESC_THREADS
 #define ORBFE_DESC_THREADS 64
+#endif
+#ifndef ORBFE_DESC_UNROLL
+#define ORBFE_DESC_UNROLL 2
+#endif
+constexpr int kDescUnroll = ORBFE_DESC_UNROLL;  // keypoints processed per loop iteration (memory-level parallelism)
 
 // global (L1-cached) rather than __constant__: each lane reads ITS 32 bytes, and per-lane addresses in
 // the constant bank are serialised by the address-divergence unit (58 % ADU busy in the ncu profile)
@@ -128,6 +134,7 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
   int my10 = 0, my01 = 0;
   const int u = lane - ORBFE_HALF_PATCH;
   const int au = u < 0 ? -u : u;
+#pragma unroll kDescUnroll
   for (int k = 0; k < nk; ++k) {
     const int lv = __shfl_sync(0xffffffffu, level, k);
     const int cx = __shfl_sync(0xffffffffu, kx, k), cy = __shfl_sync(0xffffffffu, ky, k);
@@ -187,6 +194,7 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
   }
   const uint8_t* blurSlot = blur + (size_t)slot * g.blurStride;
   uint8_t* dOut = desc + ((size_t)slot * g.totalOut + base) * 32;
+#pragma unroll kDescUnroll
   for (int k = 0; k < nk; ++k) {
     const int lv = __shfl_sync(0xffffffffu, level, k);
     const int cx = __shfl_sync(0xffffffffu, kx, k), cy = __shfl_sync(0xffffffffu, ky, k);

@@ -14,6 +14,15 @@
 
 #define ORBFE_FAST_THREADS 256
 #define ORBFE_FAST_MAXG 16
+#ifndef ORBFE_FAST_FGCAP
+#define ORBFE_FAST_FGCAP 8   // upper bound of cells per CTA
+#endif
+#ifndef ORBFE_FAST_X2
+#define ORBFE_FAST_X2 0  // 1: two queue entries per lane on packed u16x2 networks (fewer instructions, but 64 regs => 4 CTAs/SM: slower)
+#endif
+#ifndef ORBFE_FAST_PITCHW
+#define ORBFE_FAST_PITCHW 61  // compile-time tile pitch (words) of the common geometry; odd => no column bank conflicts
+#endif
 
 // 16-bit mask has a circular run of >= 9 set bits
 __device__ __forceinline__ bool orbfe_has_run9(unsigned m) {
@@ -139,14 +148,14 @@ __device__ __forceinline__ void orbfe_fast_score3_x2(const uint8_t* p0, const ui
   s1 = max((int)(bright >> 16) - 256, 256 - (int)(dark >> 16)) - 1;
 }
 
-// PW = compile-time tile pitch in words (64: the queue code IS the byte offset, row*pitch is a shift);
-// PW = 0: run-time pitch (cells wider than the fixed tile)
+// PW = compile-time tile pitch in words (ring offsets become immediates); PW = 0: run-time pitch
+// (cells wider than the fixed tile)
 template <int PW>
 __global__ void __launch_bounds__(ORBFE_FAST_THREADS)
 k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, int* __restrict__ cellCnt,
              unsigned* __restrict__ cellList, const int pitchWArg, const int maxRows, const int queueCap) {
   const int pitchW = PW ? PW : pitchWArg;
-  const int xbits = PW ? 8 : 9;  // queue code = y << xbits | x
+  const int xbits = 9;  // queue code = y << xbits | x
   ORBFE_DYN_SMEM(smem);
   unsigned* tileW = reinterpret_cast<unsigned*>(smem);               // [maxRows][pitchW] pixels
   unsigned* scoreW = tileW + (size_t)maxRows * pitchW;               // [maxRows][pitchW] corner scores
@@ -251,6 +260,14 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
     // ---- 2. exact score on the queue; corner at th <=> score >= th
     const int qn = min(s_qn, queueCap);
     const int xmask = (1 << xbits) - 1;
+#if !ORBFE_FAST_X2
+    for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
+      const int c0 = queue[e];
+      const int o0 = (c0 >> xbits) * pitchB + (c0 & xmask);
+      const int s0 = orbfe_fast_score3(tileB + o0, pitchB);
+      if (s0 >= th) scoreB[o0] = (uint8_t)s0;
+    }
+#else
     for (int e = 2 * tid; e < qn; e += 2 * ORBFE_FAST_THREADS) {  // two queue entries per lane
       const int c0 = queue[e], c1 = queue[min(e + 1, qn - 1)];
       const int o0 = (c0 >> xbits) * pitchB + (c0 & xmask), o1 = (c1 >> xbits) * pitchB + (c1 & xmask);
@@ -259,6 +276,7 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
       if (s0 >= th) scoreB[o0] = (uint8_t)s0;
       if (s1 >= th) scoreB[o1] = (uint8_t)s1;
     }
+#endif
     __syncthreads();
     // ---- 3. NMS inside the cell; survivors -> bit plane + row masks; keypoint found => no fallback
     for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {

@@ -269,7 +269,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
     L.fG = 1;
     {
       double best = 1e30;
-      for (int fg = 1; fg <= ORBFE_FAST_MAXG / 2 && fg * L.wCell + 9 <= 300; ++fg) {
+      for (int fg = 1; fg <= ORBFE_FAST_FGCAP && fg * L.wCell + 9 <= 300; ++fg) {
         const int words = (fg * L.wCell + 9 + 3) / 4;
         const double cost = (double)((words + 31) / 32) / fg;
         if (cost <= best) { best = cost; L.fG = fg; }
@@ -323,7 +323,8 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   g.totalFast = fastBase;
   if (maxCw > 511 || maxInnerH + 6 > 127) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too large for the 16-bit queue code");
   ex->fastTilePitch = align_up(maxCw, 4) / 4 + 1;  // words
-  if (ex->fastTilePitch <= 64) ex->fastTilePitch = 64;  // compile-time pitch specialisation (k_fast_cells<64>)
+  ex->fastTilePitch |= 1;                          // odd word pitch: vertically adjacent pixels fall in different banks
+  if (ex->fastTilePitch <= ORBFE_FAST_PITCHW) ex->fastTilePitch = ORBFE_FAST_PITCHW;  // compile-time specialisation
   ex->fastMaxInnerH = maxInnerH + 6;              // tile rows
   ex->fastQueueCap = maxQueue;
   if (ex->fastMaxInnerH > 32 * ORBFE_FAST_ROWWORDS) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too tall");
@@ -383,7 +384,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   CUDA_TRY(cudaMemsetAsync(ex->d_nMatched, 0, S * sizeof(int), ex->stream));
   CUDA_TRY(cudaStreamSynchronize(ex->stream));  // `lut` goes out of scope
 #ifndef ORBFE_EMU
-  CUDA_TRY(cudaFuncSetAttribute(k_fast_cells<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
+  CUDA_TRY(cudaFuncSetAttribute(k_fast_cells<ORBFE_FAST_PITCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
   CUDA_TRY(cudaFuncSetAttribute(k_fast_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
   CUDA_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octSmem));
   CUDA_TRY(cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->rowSmem));
@@ -423,7 +424,7 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
   }
   if ((rc = stage_event(ex, 1))) return rc;
   if (g.totalFast > 0) {
-    auto kfast = ex->fastTilePitch == 64 ? k_fast_cells<64> : k_fast_cells<0>;
+    auto kfast = ex->fastTilePitch == ORBFE_FAST_PITCHW ? k_fast_cells<ORBFE_FAST_PITCHW> : k_fast_cells<0>;
     ORBFE_LAUNCH(ex, kfast, dim3(g.totalFast, n), dim3(ORBFE_FAST_THREADS), ex->fastSmem, g, ex->d_pyr,
                  ex->d_cellCnt, ex->d_cellList, ex->fastTilePitch, ex->fastMaxInnerH, ex->fastQueueCap);
   }

@@ -57,7 +57,7 @@ def load(path=None, _test_emulation=False):
     """Loads the C-ABI library.  `path=None` = the in-tree product build (compiled on demand with
     nvcc).  The emulated test build under tests/emu is refused unless a test asks for it."""
     if path is None:
-        path = _build.LIB
+        path = os.environ.get("ORBFE_LIB") or _build.LIB  # ORBFE_LIB: A/B-test another nvcc build of the same sources
         if not os.path.exists(path):
             _build.build()
     path = os.path.abspath(path)
