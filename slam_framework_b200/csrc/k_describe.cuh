@@ -106,12 +106,14 @@ __device__ __forceinline__ float orbfe_sincosf(float y, int is_cos) {
 __global__ void __launch_bounds__(ORBFE_DESC_THREADS)
 k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                   const unsigned* __restrict__ lvlKp, const int* __restrict__ lvlCnt, orbfe_kp_dev* __restrict__ kps,
-                  uint8_t* __restrict__ desc, int* __restrict__ nKp) {
+                  uint8_t* __restrict__ desc, int* __restrict__ nKp, const int kpw) {
   const int slot = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * (ORBFE_DESC_THREADS / 32) + (threadIdx.x >> 5);
   const int* cnt = lvlCnt + (size_t)slot * g.nlevels;
-  const int base = wglobal * 32;
+  // kpw keypoints per warp: 32 for large batches (the lane-parallel phase is fully used), fewer when
+  // only a frame or two is in flight so that the keypoints spread over more warps (latency)
+  const int base = wglobal * kpw;
   // this lane's keypoint: packed position base+lane -> (level, index inside the level)
   int level = -1, idx = base + lane, total = 0;
   for (int l = 0; l < g.nlevels; ++l) {
@@ -120,9 +122,10 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     if (level < 0) idx -= c;
     total += c;
   }
+  if (lane >= kpw) level = -1;
   if (wglobal == 0 && lane == 0) nKp[slot] = total;
   if (base >= total) return;  // whole warp exits together
-  const int nk = min(32, total - base);
+  const int nk = min(kpw, total - base);
   int kx = 0, ky = 0, resp = 0;
   if (level >= 0) {
     const unsigned pk = lvlKp[(size_t)slot * g.totalOut + g.lv[level].outOff + idx];

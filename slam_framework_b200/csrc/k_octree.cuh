@@ -64,8 +64,10 @@ k_octree(const __grid_constant__ Geom g, const int* __restrict__ cellCnt, const 
   int* cellStart = sc.cellStart + (size_t)slot * g.totalCells + L.cellBase;
   OctNode* genA = sc.nodes + (size_t)slot * 2 * g.nodeStride + 2 * (size_t)L.nodeOff;
   OctNode* genB = genA + L.nodeCap;
-  int* childCnt = sc.childCnt + (size_t)slot * g.nodeStride + L.nodeOff;
-  int* childSlot = sc.childSlot + (size_t)slot * g.nodeStride + L.nodeOff;
+  // per-child key counters and child slots live in shared memory: thousands of keys hit a handful of
+  // counters in the first passes, which serialises global (L2) atomics for tens of microseconds
+  int* childCnt = reinterpret_cast<int*>(s_sort + g.sortCap);
+  int* childSlot = childCnt + g.maxNodeCap;
   unsigned long long* best = sc.best + (size_t)slot * (g.nodeStride * 5 / 4 + 16 * ORBFE_MAX_LEVELS) + (size_t)L.nodeOff * 5 / 4 + 16 * level;
   int* finSeq = sc.finSeq + (size_t)slot * g.totalOut + L.outOff;
   int* finKey = sc.finKey + (size_t)slot * g.totalOut + L.outOff;

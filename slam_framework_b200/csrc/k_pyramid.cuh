@@ -103,9 +103,16 @@ struct PyrRowLut {
   unsigned b0, b1;   // vertical coefficients << 16
 };
 
+template <bool NC>
+__device__ __forceinline__ unsigned orbfe_ldw(const unsigned* p) {
+  if (NC) return __ldg(p);
+  return *p;  // the tail kernel reads planes it wrote itself: coherent path
+}
+
+template <bool NC>
 __device__ __forceinline__ void orbfe_hrow(const unsigned* __restrict__ srow, const int srcW, const int sh,
                                            const unsigned (&sel)[4], const unsigned (&cp)[4], unsigned (&T)[4]) {
-  const unsigned w0 = __ldg(srow + srcW), w1 = __ldg(srow + srcW + 1), w2 = __ldg(srow + srcW + 2);
+  const unsigned w0 = orbfe_ldw<NC>(srow + srcW), w1 = orbfe_ldw<NC>(srow + srcW + 1), w2 = orbfe_ldw<NC>(srow + srcW + 2);
   const unsigned lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
 #pragma unroll
   for (int j = 0; j < 4; ++j) T[j] = __dp2a_lo(cp[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;  // (S0*c0 + S1*c1) >> 4
@@ -121,14 +128,13 @@ __device__ __forceinline__ unsigned orbfe_vblend(const PyrRowLut R, const unsign
   return out;
 }
 
-__global__ void __launch_bounds__(ORBFE_PYR_THREADS)
-k_pyramid_resize(const __grid_constant__ Geom g, const int level, uint8_t* __restrict__ pyr,
-                 const PyrRowLut* __restrict__ rlut, const PyrWordLut* __restrict__ wlut) {
+// one warp strip (32 words x ORBFE_PYR_ROWS rows) of level `level` of image `slot`
+template <bool NC>
+__device__ __forceinline__ void orbfe_resize_strip(const Geom& g, const int level, const int slot, const int task, const int lane,
+                                                   uint8_t* __restrict__ pyr, const PyrRowLut* __restrict__ rlut,
+                                                   const PyrWordLut* __restrict__ wlut) {
   const LevelGeom& L = g.lv[level];
   const LevelGeom& P = g.lv[level - 1];
-  const int slot = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int task = blockIdx.x * (ORBFE_PYR_THREADS / 32) + (threadIdx.x >> 5);
   const int strips = (L.pyrWords + 31) >> 5;
   const int ph = L.h + 2 * ORBFE_EDGE;
   const int ty = task / strips, tx = task - ty * strips;
@@ -150,15 +156,39 @@ k_pyramid_resize(const __grid_constant__ Geom g, const int level, uint8_t* __res
   for (int r = 0; r < nrows; r += 2) {
     {  // even row: top = TA, bottom = TB
       const PyrRowLut R = rl[r];
-      if (ra != R.s0) { orbfe_hrow(src + (size_t)R.s0 * spitchW, W.srcW, W.sh, sel, cp, TA); ra = R.s0; }
-      if (rb != R.s1) { orbfe_hrow(src + (size_t)R.s1 * spitchW, W.srcW, W.sh, sel, cp, TB); rb = R.s1; }
+      if (ra != R.s0) { orbfe_hrow<NC>(src + (size_t)R.s0 * spitchW, W.srcW, W.sh, sel, cp, TA); ra = R.s0; }
+      if (rb != R.s1) { orbfe_hrow<NC>(src + (size_t)R.s1 * spitchW, W.srcW, W.sh, sel, cp, TB); rb = R.s1; }
       dst[(size_t)r * dpitchW] = orbfe_vblend(R, TA, TB);
     }
     if (r + 1 < nrows) {  // odd row: roles swapped, so a "+1 source row" step re-uses TB as the top row
       const PyrRowLut R = rl[r + 1];
-      if (rb != R.s0) { orbfe_hrow(src + (size_t)R.s0 * spitchW, W.srcW, W.sh, sel, cp, TB); rb = R.s0; }
-      if (ra != R.s1) { orbfe_hrow(src + (size_t)R.s1 * spitchW, W.srcW, W.sh, sel, cp, TA); ra = R.s1; }
+      if (rb != R.s0) { orbfe_hrow<NC>(src + (size_t)R.s0 * spitchW, W.srcW, W.sh, sel, cp, TB); rb = R.s0; }
+      if (ra != R.s1) { orbfe_hrow<NC>(src + (size_t)R.s1 * spitchW, W.srcW, W.sh, sel, cp, TA); ra = R.s1; }
       dst[(size_t)(r + 1) * dpitchW] = orbfe_vblend(R, TB, TA);
     }
+  }
+}
+
+__global__ void __launch_bounds__(ORBFE_PYR_THREADS)
+k_pyramid_resize(const __grid_constant__ Geom g, const int level, uint8_t* __restrict__ pyr,
+                 const PyrRowLut* __restrict__ rlut, const PyrWordLut* __restrict__ wlut) {
+  const int task = blockIdx.x * (ORBFE_PYR_THREADS / 32) + (threadIdx.x >> 5);
+  orbfe_resize_strip<true>(g, level, blockIdx.y, task, threadIdx.x & 31, pyr, rlut, wlut);
+}
+
+// The small top levels (a few thousand words each) are launch-latency bound as separate kernels: one
+// 1024-thread CTA per image walks levels firstLevel..nlevels-1 with a block barrier between levels
+// (level l reads the plane level l-1 this same CTA just wrote, hence the coherent loads).
+#define ORBFE_PYR_TAIL_THREADS 1024
+__global__ void __launch_bounds__(ORBFE_PYR_TAIL_THREADS)
+k_pyramid_tail(const __grid_constant__ Geom g, const int firstLevel, uint8_t* pyr, const PyrRowLut* __restrict__ rlut,
+               const PyrWordLut* __restrict__ wlut) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int level = firstLevel; level < g.nlevels; ++level) {
+    const LevelGeom& L = g.lv[level];
+    const int tasks = ((L.pyrWords + 31) >> 5) * ((L.h + 2 * ORBFE_EDGE + ORBFE_PYR_ROWS - 1) / ORBFE_PYR_ROWS);
+    for (int task = wid; task < tasks; task += ORBFE_PYR_TAIL_THREADS / 32)
+      orbfe_resize_strip<false>(g, level, blockIdx.y, task, lane, pyr, rlut, wlut);
+    __syncthreads();
   }
 }

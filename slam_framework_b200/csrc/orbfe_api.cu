@@ -55,6 +55,7 @@ struct orbfe_extractor {
   Geom g{};
   bool configured = false;
   int fastTilePitch = 0, fastMaxInnerH = 0, fastQueueCap = 0;
+  int pyrTailStart = ORBFE_MAX_LEVELS;
   size_t fastSmem = 0, octSmem = 0;
   // device arena
   uint8_t* d_img = nullptr;
@@ -314,10 +315,19 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   g.cellListStride = (unsigned)std::max<size_t>(cellListOff, 1);
   g.candStride = (unsigned)candOff;
   g.nodeStride = (unsigned)nodeOff;
+  // tail of the pyramid handled by k_pyramid_tail: the trailing run of small fast-resize levels
+  ex->pyrTailStart = nl;
+  for (int l = nl - 1; l >= 1; --l) {
+    if (!g.lv[l].fastResize || g.lv[l].w * g.lv[l].h > 131072) break;
+    ex->pyrTailStart = l;
+  }
+  if (nl - ex->pyrTailStart < 2) ex->pyrTailStart = nl;  // not worth a separate kernel
   int sc = 1;
   while (sc < maxSort) sc <<= 1;
   g.sortCap = sc;
-  ex->octSmem = (size_t)sc * sizeof(unsigned long long);
+  g.maxNodeCap = 0;
+  for (int l = 0; l < nl; ++l) g.maxNodeCap = std::max(g.maxNodeCap, g.lv[l].nodeCap);
+  ex->octSmem = (size_t)sc * sizeof(unsigned long long) + 2 * (size_t)g.maxNodeCap * sizeof(int);
   if (ex->octSmem > 200 * 1024)
     return orbfe_fail(ORBFE_ERR_INVALID, "nfeatures per level too large for the shared-memory sort (%d)", maxSort);
   g.totalFast = fastBase;
@@ -413,6 +423,10 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
   if ((rc = stage_event(ex, 0))) return rc;
   for (int l = 0; l < g.nlevels; ++l) {
     const LevelGeom& L = g.lv[l];
+    if (l == ex->pyrTailStart) {  // small top levels: one CTA per image, block barrier between levels
+      ORBFE_LAUNCH(ex, k_pyramid_tail, dim3(1, n), dim3(ORBFE_PYR_TAIL_THREADS), 0, g, l, ex->d_pyr, ex->d_rlut, ex->d_wlut);
+      break;
+    }
     if (L.fastResize) {
       const int tasks = ((L.pyrWords + 31) / 32) * ((L.h + 2 * ORBFE_EDGE + ORBFE_PYR_ROWS - 1) / ORBFE_PYR_ROWS);
       ORBFE_LAUNCH(ex, k_pyramid_resize, dim3((tasks + ORBFE_PYR_THREADS / 32 - 1) / (ORBFE_PYR_THREADS / 32), n),
@@ -435,9 +449,12 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
   ORBFE_LAUNCH(ex, k_blur, dim3((g.totalTiles + ORBFE_BLUR_THREADS / 32 - 1) / (ORBFE_BLUR_THREADS / 32), n),
                dim3(ORBFE_BLUR_THREADS), 0, g, ex->d_pyr, ex->d_blur);  // one warp per strip
   if ((rc = stage_event(ex, 4))) return rc;
-  ORBFE_LAUNCH(ex, k_orient_describe, dim3((g.totalOut + ORBFE_DESC_THREADS - 1) / ORBFE_DESC_THREADS, n),  // 32 keypoints per warp
-               dim3(ORBFE_DESC_THREADS), 0, g, ex->d_pyr, ex->d_blur, ex->d_lvlKp, ex->d_lvlCnt, ex->d_kps, ex->d_desc,
-               ex->d_nKp);
+  {
+    const int kpw = n >= 16 ? 32 : (n >= 4 ? 8 : 4);  // keypoints per warp (see k_orient_describe)
+    const int warps = (g.totalOut + kpw - 1) / kpw, wpc = ORBFE_DESC_THREADS / 32;
+    ORBFE_LAUNCH(ex, k_orient_describe, dim3((warps + wpc - 1) / wpc, n), dim3(ORBFE_DESC_THREADS), 0, g, ex->d_pyr, ex->d_blur,
+                 ex->d_lvlKp, ex->d_lvlCnt, ex->d_kps, ex->d_desc, ex->d_nKp, kpw);
+  }
   if ((rc = stage_event(ex, 5))) return rc;
   CUDA_TRY(cudaGetLastError());
   return ORBFE_OK;

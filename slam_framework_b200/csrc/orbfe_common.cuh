@@ -61,6 +61,7 @@ struct Geom {
   int imgPitch;
   int totalCells, totalTiles, totalOut, totalPyrBlocks, totalFast;
   int sortCap;           // power of two >= max(outCap, N) over levels
+  int maxNodeCap;        // max over levels of nodeCap
   unsigned imgStride, pyrStride, blurStride, cellListStride, candStride, nodeStride;
   LevelGeom lv[ORBFE_MAX_LEVELS];
 };

@@ -47,3 +47,9 @@ def test_stereo_kitti_pair(emu):
 def test_batch_stereo_two_pairs(emu):
     pairs = [synth.stereo_pair(160, 500, seed=s) for s in (3, 4)]
     assert P.check_batch_stereo(emu, pairs, nfeatures=600) > 50
+
+
+def test_batch_of_16_small_frames_uses_wide_descriptor_path(emu):
+    """>= 16 images in flight switch k_orient_describe to 32 keypoints per warp"""
+    pairs = [synth.stereo_pair(100, 320, seed=s) for s in range(8)]
+    assert P.check_batch_stereo(emu, pairs, nfeatures=300) > 20

@@ -83,6 +83,15 @@ def test_batch_is_deterministic_and_slot_independent(lib):
         ex.run_stereo(n, P.KITTI["bf"], P.KITTI["bf"] / P.KITTI["fx"])
         b = ex.download(2 * n, ex.make_buffers(2 * n, stereo=True))
         outs.append(b)
+    # slot 0 against the oracle: this batch size runs the 32-keypoints-per-warp descriptor path
+    import oracle_lib as O
+    oL, oR = O.Extractor(), O.Extractor()
+    okl, odl = oL.extract(l)
+    okr, odr = oR.extract(r)
+    P.assert_kps_equal(outs[0]["kps"][0, :outs[0]["n"][0]], okl, "slot 0")
+    assert np.array_equal(outs[0]["desc"][0, :outs[0]["n"][0]], odl)
+    _, our, _ = O.stereo_match(oL, oR, okl, odl, okr, odr, P.KITTI["bf"], P.KITTI["bf"] / P.KITTI["fx"])
+    assert np.array_equal(outs[0]["ur"][0, :outs[0]["n"][0]], our)
     for b in outs:
         n0 = b["n"][0]
         for p in range(n):
