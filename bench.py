@@ -349,6 +349,18 @@ def run_ours(args):
         latency = {"p50_ms_per_frame": statistics.median(lat), "min_ms": min(lat), "runs": len(lat),
                    "path": "2x orbfe_extract (two host threads) + orbfe_stereo_match, host in/out"}
         eL.close(); eR.close()
+        # the same pair as ONE batched call sequence on one handle (upload 2 frames, run, stereo, download)
+        e1 = orbfe.ORBextractor(NFEATURES, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_images=2, lib=L)
+        b1 = e1.make_buffers(2, stereo=True)
+        lat2 = []
+        for it in range(60):
+            t0 = time.perf_counter()
+            e1.upload([l, r]); e1.run(2); e1.run_stereo(1, BF, baseline); e1.download(2, b1)
+            if it >= 10:
+                lat2.append((time.perf_counter() - t0) * 1e3)
+        latency["fused_p50_ms_per_frame"] = statistics.median(lat2)
+        latency["fused_path"] = "orbfe_upload(2) + orbfe_run + orbfe_run_stereo + orbfe_download on one handle"
+        e1.close()
 
     # ---- CPU baseline (oracle port on the host cores; bounded sample) ----------------------------------
     cpu = None

@@ -82,7 +82,8 @@ k_pyramid_level(const __grid_constant__ Geom g, const int level, const uint8_t* 
 }
 
 // ---- fast resize path (levels >= 1, scale factor <= 2, not the exact-2x INTER_AREA case) ------------
-// One warp = 32 consecutive words of the PADDED destination plane x ORBFE_PYR_ROWS rows.  Everything that
+// One warp = 32 consecutive words of the PADDED destination plane x stripRows rows (8 for batches; 2 when
+// only a frame or two is in flight: a strip is a chain of dependent loads, short chains = low latency).  Everything that
 // depends only on the column lives in registers for the whole strip (host-built PyrWordLut: source word,
 // byte shift, PRMT selectors and the packed 11-bit coefficient pairs); everything that depends only on
 // the row comes from one 16-byte PyrRowLut entry (source rows of the REFLECTED destination row, vertical
@@ -131,14 +132,14 @@ __device__ __forceinline__ unsigned orbfe_vblend(const PyrRowLut R, const unsign
 // one warp strip (32 words x ORBFE_PYR_ROWS rows) of level `level` of image `slot`
 template <bool NC>
 __device__ __forceinline__ void orbfe_resize_strip(const Geom& g, const int level, const int slot, const int task, const int lane,
-                                                   uint8_t* __restrict__ pyr, const PyrRowLut* __restrict__ rlut,
-                                                   const PyrWordLut* __restrict__ wlut) {
+                                                   const int stripRows, uint8_t* __restrict__ pyr,
+                                                   const PyrRowLut* __restrict__ rlut, const PyrWordLut* __restrict__ wlut) {
   const LevelGeom& L = g.lv[level];
   const LevelGeom& P = g.lv[level - 1];
   const int strips = (L.pyrWords + 31) >> 5;
   const int ph = L.h + 2 * ORBFE_EDGE;
   const int ty = task / strips, tx = task - ty * strips;
-  const int py0 = ty * ORBFE_PYR_ROWS;
+  const int py0 = ty * stripRows;
   if (py0 >= ph) return;
   const int wx = min(tx * 32 + lane, L.pyrWords - 1);  // duplicate lanes rewrite the last word with the same value
   const PyrWordLut W = wlut[L.wlutOff + wx];
@@ -152,7 +153,7 @@ __device__ __forceinline__ void orbfe_resize_strip(const Geom& g, const int leve
   const PyrRowLut* rl = rlut + L.rlutOff + py0;
   unsigned TA[4] = {0, 0, 0, 0}, TB[4] = {0, 0, 0, 0};
   int ra = -1, rb = -1;
-  const int nrows = min(ORBFE_PYR_ROWS, ph - py0);
+  const int nrows = min(stripRows, ph - py0);
   for (int r = 0; r < nrows; r += 2) {
     {  // even row: top = TA, bottom = TB
       const PyrRowLut R = rl[r];
@@ -170,25 +171,9 @@ __device__ __forceinline__ void orbfe_resize_strip(const Geom& g, const int leve
 }
 
 __global__ void __launch_bounds__(ORBFE_PYR_THREADS)
-k_pyramid_resize(const __grid_constant__ Geom g, const int level, uint8_t* __restrict__ pyr,
+k_pyramid_resize(const __grid_constant__ Geom g, const int level, const int stripRows, uint8_t* __restrict__ pyr,
                  const PyrRowLut* __restrict__ rlut, const PyrWordLut* __restrict__ wlut) {
   const int task = blockIdx.x * (ORBFE_PYR_THREADS / 32) + (threadIdx.x >> 5);
-  orbfe_resize_strip<true>(g, level, blockIdx.y, task, threadIdx.x & 31, pyr, rlut, wlut);
+  orbfe_resize_strip<true>(g, level, blockIdx.y, task, threadIdx.x & 31, stripRows, pyr, rlut, wlut);
 }
 
-// The small top levels (a few thousand words each) are launch-latency bound as separate kernels: one
-// 1024-thread CTA per image walks levels firstLevel..nlevels-1 with a block barrier between levels
-// (level l reads the plane level l-1 this same CTA just wrote, hence the coherent loads).
-#define ORBFE_PYR_TAIL_THREADS 1024
-__global__ void __launch_bounds__(ORBFE_PYR_TAIL_THREADS)
-k_pyramid_tail(const __grid_constant__ Geom g, const int firstLevel, uint8_t* pyr, const PyrRowLut* __restrict__ rlut,
-               const PyrWordLut* __restrict__ wlut) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int level = firstLevel; level < g.nlevels; ++level) {
-    const LevelGeom& L = g.lv[level];
-    const int tasks = ((L.pyrWords + 31) >> 5) * ((L.h + 2 * ORBFE_EDGE + ORBFE_PYR_ROWS - 1) / ORBFE_PYR_ROWS);
-    for (int task = wid; task < tasks; task += ORBFE_PYR_TAIL_THREADS / 32)
-      orbfe_resize_strip<false>(g, level, blockIdx.y, task, lane, pyr, rlut, wlut);
-    __syncthreads();
-  }
-}

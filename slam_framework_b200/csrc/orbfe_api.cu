@@ -55,7 +55,6 @@ struct orbfe_extractor {
   Geom g{};
   bool configured = false;
   int fastTilePitch = 0, fastMaxInnerH = 0, fastQueueCap = 0;
-  int pyrTailStart = ORBFE_MAX_LEVELS;
   size_t fastSmem = 0, octSmem = 0;
   // device arena
   uint8_t* d_img = nullptr;
@@ -315,13 +314,6 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   g.cellListStride = (unsigned)std::max<size_t>(cellListOff, 1);
   g.candStride = (unsigned)candOff;
   g.nodeStride = (unsigned)nodeOff;
-  // tail of the pyramid handled by k_pyramid_tail: the trailing run of small fast-resize levels
-  ex->pyrTailStart = nl;
-  for (int l = nl - 1; l >= 1; --l) {
-    if (!g.lv[l].fastResize || g.lv[l].w * g.lv[l].h > 131072) break;
-    ex->pyrTailStart = l;
-  }
-  if (nl - ex->pyrTailStart < 2) ex->pyrTailStart = nl;  // not worth a separate kernel
   int sc = 1;
   while (sc < maxSort) sc <<= 1;
   g.sortCap = sc;
@@ -423,14 +415,11 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
   if ((rc = stage_event(ex, 0))) return rc;
   for (int l = 0; l < g.nlevels; ++l) {
     const LevelGeom& L = g.lv[l];
-    if (l == ex->pyrTailStart) {  // small top levels: one CTA per image, block barrier between levels
-      ORBFE_LAUNCH(ex, k_pyramid_tail, dim3(1, n), dim3(ORBFE_PYR_TAIL_THREADS), 0, g, l, ex->d_pyr, ex->d_rlut, ex->d_wlut);
-      break;
-    }
     if (L.fastResize) {
-      const int tasks = ((L.pyrWords + 31) / 32) * ((L.h + 2 * ORBFE_EDGE + ORBFE_PYR_ROWS - 1) / ORBFE_PYR_ROWS);
+      const int stripRows = n >= 8 ? ORBFE_PYR_ROWS : 2;
+      const int tasks = ((L.pyrWords + 31) / 32) * ((L.h + 2 * ORBFE_EDGE + stripRows - 1) / stripRows);
       ORBFE_LAUNCH(ex, k_pyramid_resize, dim3((tasks + ORBFE_PYR_THREADS / 32 - 1) / (ORBFE_PYR_THREADS / 32), n),
-                   dim3(ORBFE_PYR_THREADS), 0, g, l, ex->d_pyr, ex->d_rlut, ex->d_wlut);
+                   dim3(ORBFE_PYR_THREADS), 0, g, l, stripRows, ex->d_pyr, ex->d_rlut, ex->d_wlut);
     } else {
       ORBFE_LAUNCH(ex, k_pyramid_level, dim3(L.pyrBlocks, n), dim3(ORBFE_PYR_THREADS), 0, g, l, ex->d_img, ex->d_pyr,
                    ex->d_lut);
