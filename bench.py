@@ -323,8 +323,19 @@ def run_ours(args):
                          "stereo_search": 2 * (28 + 32) * kp_img, "stereo_median": 12 * kp_img}[dom] * n_img)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     whole = alg["extract_total"] * n_img / (ms / args.steps * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per image x images per launch)
+        import glob
+        tf = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]
+        tj = json.load(open(tf))
+        if dom in tj["dram_bytes_per_image"]:
+            traffic = tj["dram_bytes_per_image"][dom] * n_img / stage_launches[dom]
+            traffic_src = os.path.basename(tf) + f" (captured at {tj['n_images_in_capture']} images per launch, scaled per image)"
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "note": "the dominant kernel (grid FAST) is ALU-bound: its HBM fraction is low by nature, see profiles/",
                 "alg_bytes_per_launch": dom_bytes // stage_launches[dom], "launch_ms": dom_ms / stage_launches[dom],
                 "whole_step": {"alg_bytes": alg["extract_total"] * n_img, "gbs": whole, "frac": whole / peak},
                 "stages": per_stage}
