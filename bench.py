@@ -151,7 +151,7 @@ def run_reference(args):
         return
     cores = host_cores()
     pairs = make_pairs(min(8, max(2, cores)), 0)
-    per_step = max(cores, 4)
+    per_step = 8 * max(cores, 4)  # ~0.4 s of host work per step: thread start-up is amortised
     for _ in range(max(args.warmup, 1)):
         cpu_reference_throughput(pairs, per_step, cores)
     t0 = time.perf_counter()
