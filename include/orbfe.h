@@ -95,6 +95,11 @@ int orbfe_pyramid_level(orbfe_extractor* ex, int slot, int level, uint8_t* dst, 
  * recommended). */
 int orbfe_upload(orbfe_extractor* ex, int first_slot, const uint8_t* const* imgs, int n_imgs, int w,
                  int h, size_t stride);
+/* same for 3- or 4-channel 8-bit colour frames: converts to gray on the device as cv::cvtColor
+ * (CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY) does in Tracker::GrabImageStereo before the Frame
+ * is built (src/core/tracker.cpp:110-127); rgb_order = the config's camera.rgb flag (1: R first). */
+int orbfe_upload_color(orbfe_extractor* ex, int first_slot, const uint8_t* const* imgs, int n_imgs, int w, int h,
+                       size_t stride, int channels, int rgb_order);
 /* enqueue the full extractor on slots [0, n_imgs); results stay on the device */
 int orbfe_run(orbfe_extractor* ex, int n_imgs);
 /* enqueue Frame::ComputeStereoMatches for pairs p = (slot 2p, slot 2p+1), p < n_pairs */

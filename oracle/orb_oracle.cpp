@@ -451,6 +451,16 @@ int orc_fast9(const uint8_t* img, int w, int h, int stride, int th, int nms, orc
   return (int)v.size();
 }
 float orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+// cv::cvtColor(RGB2GRAY / BGR2GRAY / RGBA2GRAY / BGRA2GRAY) on 8-bit images (call sites
+// src/core/tracker.cpp:110-127): OpenCV 4.x fixed point, 15 fractional bits,
+// gray = (R*9798 + G*19235 + B*3735 + 16384) >> 15  (pinned against cv2 4.13; OpenCV 3.x used 14 bits)
+void orc_cvt_gray(const uint8_t* src, size_t n_px, int channels, int rgb_order, uint8_t* dst) {
+  for (size_t i = 0; i < n_px; ++i) {
+    const uint8_t* p = src + i * (size_t)channels;
+    const int r = rgb_order ? p[0] : p[2], g = p[1], b = rgb_order ? p[2] : p[0];
+    dst[i] = (uint8_t)((r * 9798 + g * 19235 + b * 3735 + 16384) >> 15);
+  }
+}
 int orc_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
 
 // ORBextractor::ORBextractor (orb_extractor.cpp:351-411)

@@ -14,6 +14,7 @@
 #include "k_blur.cuh"
 #include "k_describe.cuh"
 #include "k_stereo.cuh"
+#include "k_gray.cuh"
 #include "orbfe_host.h"
 
 #include <cmath>
@@ -58,6 +59,8 @@ struct orbfe_extractor {
   size_t fastSmem = 0, octSmem = 0;
   // device arena
   uint8_t* d_img = nullptr;
+  uint8_t* d_color = nullptr;       // staging of colour frames (orbfe_upload_color), allocated on first use
+  size_t colorStride = 0;
   uint8_t* d_pyr = nullptr;
   uint8_t* d_blur = nullptr;
   int* d_cellCnt = nullptr;
@@ -132,6 +135,7 @@ static void build_resize_lut(int dn, int sn, ResizeLut* out) {
 }
 
 static void free_arena(orbfe_extractor* ex) {
+  cudaFree(ex->d_color); ex->d_color = nullptr; ex->colorStride = 0;
   cudaFree(ex->d_img); cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_cellCnt); cudaFree(ex->d_cellList);
   cudaFree(ex->oct.cand); cudaFree(ex->oct.knode); cudaFree(ex->oct.cellStart); cudaFree(ex->oct.nodes);
   cudaFree(ex->oct.childCnt); cudaFree(ex->oct.childSlot); cudaFree(ex->oct.best); cudaFree(ex->oct.finSeq);
@@ -587,6 +591,37 @@ int orbfe_upload(orbfe_extractor* ex, int first_slot, const uint8_t* const* imgs
       CUDA_TRY(cudaMemcpy2DAsync(ex->d_img + (size_t)(first_slot + i) * ex->g.imgStride, ex->g.imgPitch, imgs[i], stride,
                                  (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ex->stream));
   }
+  return ORBFE_OK;
+}
+
+int orbfe_upload_color(orbfe_extractor* ex, int first_slot, const uint8_t* const* imgs, int n_imgs, int w, int h,
+                       size_t stride, int channels, int rgb_order) {
+  int rc = check_images(ex, first_slot, n_imgs);
+  if (rc) return rc;
+  if (!imgs || w <= 0 || h <= 0 || (channels != 3 && channels != 4) || stride < (size_t)w * channels)
+    return orbfe_fail(ORBFE_ERR_INVALID, "bad colour image arguments");
+  CUDA_TRY(cudaSetDevice(ex->device));
+  if ((rc = configure(ex, w, h))) return rc;
+  const size_t rowBytes = (size_t)w * channels, bytes = rowBytes * h;
+  const size_t cstride = align_up_sz(bytes, 16) + 16;
+  if (!ex->d_color || ex->colorStride < cstride) {
+    CUDA_TRY(cudaStreamSynchronize(ex->stream));
+    cudaFree(ex->d_color);
+    ex->d_color = nullptr;
+    CUDA_TRY(cudaMalloc(&ex->d_color, (size_t)ex->S * cstride));
+    ex->colorStride = cstride;
+  }
+  for (int i = 0; i < n_imgs; ++i) {
+    if (!imgs[i]) return orbfe_fail(ORBFE_ERR_INVALID, "null image %d", i);
+    uint8_t* d = ex->d_color + (size_t)(first_slot + i) * ex->colorStride;
+    if (stride == rowBytes) CUDA_TRY(cudaMemcpyAsync(d, imgs[i], bytes, cudaMemcpyHostToDevice, ex->stream));
+    else CUDA_TRY(cudaMemcpy2DAsync(d, rowBytes, imgs[i], stride, rowBytes, (size_t)h, cudaMemcpyHostToDevice, ex->stream));
+  }
+  const int nWords = (w * h + 3) / 4;
+  ORBFE_LAUNCH(ex, k_gray, dim3((nWords + ORBFE_GRAY_THREADS - 1) / ORBFE_GRAY_THREADS, n_imgs), dim3(ORBFE_GRAY_THREADS), 0,
+               ex->d_color + (size_t)first_slot * ex->colorStride, ex->colorStride, ex->d_img + (size_t)first_slot * ex->g.imgStride,
+               (size_t)ex->g.imgStride, nWords, channels, rgb_order ? 1 : 0);
+  CUDA_TRY(cudaGetLastError());
   return ORBFE_OK;
 }
 

@@ -39,7 +39,7 @@ class _Params(C.Structure):
 EXPORTS = [
     "orbfe_last_error", "orbfe_version", "orbfe_device_count", "orbfe_extractor_create", "orbfe_extractor_destroy",
     "orbfe_extractor_tables", "orbfe_extractor_max_keypoints", "orbfe_extract", "orbfe_extract_batch",
-    "orbfe_pyramid_level", "orbfe_upload", "orbfe_run", "orbfe_run_stereo", "orbfe_download", "orbfe_download_async",
+    "orbfe_pyramid_level", "orbfe_upload", "orbfe_upload_color", "orbfe_run", "orbfe_run_stereo", "orbfe_download", "orbfe_download_async",
     "orbfe_sync",
     "orbfe_event_record", "orbfe_event_elapsed_ms", "orbfe_set_stage_timing", "orbfe_stage_summary",
     "orbfe_launch_count",
@@ -82,6 +82,7 @@ def load(path=None, _test_emulation=False):
     L.orbfe_extract_batch.argtypes = [vp, vp, i, i, i, sz, vp, vp, i, vp]
     L.orbfe_pyramid_level.argtypes = [vp, i, i, vp, sz, vp, vp]
     L.orbfe_upload.argtypes = [vp, i, vp, i, i, i, sz]
+    L.orbfe_upload_color.argtypes = [vp, i, vp, i, i, i, sz, i, i]
     L.orbfe_run.argtypes = [vp, i]
     L.orbfe_run_stereo.argtypes = [vp, i, f, f]
     L.orbfe_download.argtypes = [vp, i, vp, vp, i, vp, vp, vp]
@@ -226,6 +227,16 @@ class ORBextractor:
         arr = self._ptr_array(imgs)
         im = imgs[0]
         _check(self.L, self.L.orbfe_upload(self.h, first_slot, arr, len(imgs), im.shape[1], im.shape[0], im.strides[0]))
+
+    def upload_color(self, imgs, rgb=True, first_slot=0):
+        """colour frames (h, w, 3|4) u8: gray conversion on the device (cv::cvtColor, tracker.cpp:110-127)"""
+        arr = (vp * len(imgs))()
+        im = imgs[0]
+        for i, a in enumerate(imgs):
+            assert a.dtype == np.uint8 and a.ndim == 3 and a.shape == im.shape and a.strides[2] == 1 and a.strides[1] == a.shape[2]
+            arr[i] = a.ctypes.data
+        _check(self.L, self.L.orbfe_upload_color(self.h, first_slot, arr, len(imgs), im.shape[1], im.shape[0], im.strides[0],
+                                                im.shape[2], int(rgb)))
 
     def upload_ptrs(self, ptr_array, n, w, h, stride, first_slot=0):
         _check(self.L, self.L.orbfe_upload(self.h, first_slot, ptr_array, n, w, h, stride))

@@ -66,6 +66,14 @@ def main():
     out["atan_y"] = ys
     out["atan_x"] = xs
     out["atan_deg"] = np.array([cv2.fastAtan2(float(y), float(x)) for y, x in zip(ys, xs)], np.float32)
+    # --- cvtColor to gray (tracker.cpp:110-127)
+    col3 = rng.integers(0, 256, (33, 47, 3), dtype=np.uint8)
+    col4 = rng.integers(0, 256, (21, 50, 4), dtype=np.uint8)
+    out["gray_src3"], out["gray_src4"] = col3, col4
+    out["gray_rgb"] = cv2.cvtColor(col3, cv2.COLOR_RGB2GRAY)
+    out["gray_bgr"] = cv2.cvtColor(col3, cv2.COLOR_BGR2GRAY)
+    out["gray_rgba"] = cv2.cvtColor(col4, cv2.COLOR_RGBA2GRAY)
+    out["gray_bgra"] = cv2.cvtColor(col4, cv2.COLOR_BGRA2GRAY)
     np.savez_compressed(os.path.join(HERE, "cv2_primitives.npz"), **out)
     print("wrote", os.path.join(HERE, "cv2_primitives.npz"))
 

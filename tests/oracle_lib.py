@@ -35,6 +35,7 @@ def lib():
         L.orc_border_reflect101.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_gaussian7x7.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int]
         L.orc_fast9.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_int]
+        L.orc_cvt_gray.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, vp]
         L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
         L.orc_fast_atan2.restype = C.c_float
         L.orc_descriptor_distance.argtypes = [vp, vp]
@@ -100,6 +101,13 @@ def fast9(img, threshold, nms=True):
     out = np.zeros(cap, KP_DTYPE)
     n = lib().orc_fast9(_p(img), img.shape[1], img.shape[0], img.strides[0], threshold, int(nms), _p(out), cap)
     return out[:n]
+
+
+def cvt_gray(img, rgb_order=True):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty(img.shape[:2], np.uint8)
+    lib().orc_cvt_gray(_p(img), img.shape[0] * img.shape[1], img.shape[2], int(rgb_order), _p(out))
+    return out
 
 
 def fast_atan2(y, x):

@@ -53,3 +53,21 @@ def test_batch_of_16_small_frames_uses_wide_descriptor_path(emu):
     """>= 16 images in flight switch k_orient_describe to 32 keypoints per warp"""
     pairs = [synth.stereo_pair(100, 320, seed=s) for s in range(8)]
     assert P.check_batch_stereo(emu, pairs, nfeatures=300) > 20
+
+
+@pytest.mark.parametrize("channels,rgb", [(3, True), (3, False), (4, True), (4, False)])
+def test_colour_upload_matches_cvtcolor_then_extract(emu, channels, rgb):
+    """N4: colour frames converted on the device == oracle cvtColor + extraction of the gray frame"""
+    import oracle_lib as O
+    rng = np.random.default_rng(channels)
+    gray = synth.frame(101, 323, seed=6).astype(np.int32)
+    col = np.clip(gray[..., None] + rng.integers(-25, 26, (101, 323, channels)), 0, 255).astype(np.uint8)
+    ex = orbfe.ORBextractor(300, lib=emu, max_images=2)
+    ex.upload_color([col, col[:, ::-1].copy()], rgb=rgb)
+    ex.run(2)
+    b = ex.download(2, ex.make_buffers(2))
+    ref = O.cvt_gray(col, rgb)
+    assert np.array_equal(ex.pyramid_level(0, 0), ref)
+    ok, od = O.Extractor(300).extract(ref)
+    P.assert_kps_equal(b["kps"][0, :b["n"][0]], ok)
+    assert np.array_equal(b["desc"][0, :b["n"][0]], od)

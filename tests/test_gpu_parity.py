@@ -167,3 +167,28 @@ def test_tracking_search_by_projection_lastframe(lib):
     scale = eL.GetScaleFactors()
     assert P.check_search_by_projection_lastframe(lib, kl, dl, scale, 1241, 376, seed=8, u_right=ur, th=7.0) > 1000
     assert P.check_search_by_projection_mappoints(lib, kl, dl, scale, 1241, 376, 5000, seed=9, u_right=ur) > 500
+
+
+@pytest.mark.parametrize("channels,rgb", [(3, True), (3, False), (4, True), (4, False)])
+def test_colour_frames_converted_on_device(lib, channels, rgb):
+    """N4 (tracker.cpp:110-127): KITTI image_2/image_3 are colour PNGs; gray conversion on the GPU"""
+    import oracle_lib as O
+    rng = np.random.default_rng(channels)
+    gray = synth.frame(seed=12).astype(np.int32)
+    col = np.clip(gray[..., None] + rng.integers(-25, 26, (376, 1241, channels)), 0, 255).astype(np.uint8)
+    ex = orbfe.ORBextractor(lib=lib, max_images=2)
+    ex.upload_color([col, col[:, ::-1].copy()], rgb=rgb)
+    ex.run(2)
+    b = ex.download(2, ex.make_buffers(2))
+    ref = O.cvt_gray(col, rgb)
+    try:
+        import cv2
+        code = {(3, True): cv2.COLOR_RGB2GRAY, (3, False): cv2.COLOR_BGR2GRAY, (4, True): cv2.COLOR_RGBA2GRAY,
+                (4, False): cv2.COLOR_BGRA2GRAY}[(channels, rgb)]
+        assert np.array_equal(cv2.cvtColor(col, code), ref)
+    except ImportError:
+        pass
+    assert np.array_equal(ex.pyramid_level(0, 0), ref)
+    ok, od = O.Extractor().extract(ref)
+    P.assert_kps_equal(b["kps"][0, :b["n"][0]], ok)
+    assert np.array_equal(b["desc"][0, :b["n"][0]], od)

@@ -130,3 +130,10 @@ def test_live_cv2_percell_fast_equals_oracle_candidates():
         ref = np.array(out, np.float32).reshape(-1, 3)
         assert np.array_equal(c["x"], ref[:, 0]) and np.array_equal(c["y"], ref[:, 1])
         assert np.array_equal(c["response"], ref[:, 2])
+
+
+def test_cvt_gray_golden(golden):
+    assert np.array_equal(O.cvt_gray(golden["gray_src3"], True), golden["gray_rgb"])
+    assert np.array_equal(O.cvt_gray(golden["gray_src3"], False), golden["gray_bgr"])
+    assert np.array_equal(O.cvt_gray(golden["gray_src4"], True), golden["gray_rgba"])
+    assert np.array_equal(O.cvt_gray(golden["gray_src4"], False), golden["gray_bgra"])
