@@ -81,6 +81,45 @@ k_pyramid_level(const __grid_constant__ Geom g, const int level, const uint8_t* 
   *reinterpret_cast<unsigned*>(plane + (size_t)py * L.pitch + 4 * wx) = out;
 }
 
+// ---- level 0: copy of the input frame into its padded plane (copyMakeBorder REFLECT_101, :1071) -------
+// One CTA = one padded row of one image; a thread writes 16-byte chunks.  Interior chunks are 5 aligned
+// words of the (tightly packed, arbitrarily aligned) image row + 4 funnel shifts; chunks that touch the
+// 19-px border take the per-byte reflected path.
+#define ORBFE_PYR0_THREADS 128
+__global__ void __launch_bounds__(ORBFE_PYR0_THREADS)
+k_pyramid_level0(const __grid_constant__ Geom g, const uint8_t* __restrict__ img, uint8_t* __restrict__ pyr) {
+  const LevelGeom& L = g.lv[0];
+  const int py = blockIdx.x, slot = blockIdx.y;
+  const int y = orbfe_reflect101(py - ORBFE_EDGE, L.h);
+  const size_t rowByte = (size_t)slot * g.imgStride + (size_t)y * g.imgPitch;
+  const uint8_t* src = img + rowByte;
+  uint4* dst = reinterpret_cast<uint4*>(pyr + (size_t)slot * g.pyrStride + L.planeOff + (size_t)py * L.pitch);
+  const int pw = L.w + 2 * ORBFE_EDGE;
+  for (int c = threadIdx.x; 16 * c < pw; c += ORBFE_PYR0_THREADS) {
+    const int x0 = 16 * c - ORBFE_EDGE;
+    unsigned o[4];
+    if (x0 >= 0 && x0 + 15 < L.w) {
+      const size_t a = rowByte + (size_t)x0;
+      const unsigned* s4 = reinterpret_cast<const unsigned*>(img) + (a >> 2);
+      const int sh = 8 * (int)(a & 3);
+      const unsigned w0 = __ldg(s4), w1 = __ldg(s4 + 1), w2 = __ldg(s4 + 2), w3 = __ldg(s4 + 3), w4 = __ldg(s4 + 4);
+      o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh);
+      o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        o[q] = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int x = orbfe_reflect101(min(16 * c + 4 * q + b, pw - 1) - ORBFE_EDGE, L.w);
+          o[q] |= (unsigned)__ldg(src + x) << (8 * b);
+        }
+      }
+    }
+    dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ---- fast resize path (levels >= 1, scale factor <= 2, not the exact-2x INTER_AREA case) ------------
 // One warp = 32 consecutive words of the PADDED destination plane x stripRows rows (8 for batches; 2 when
 // only a frame or two is in flight: a strip is a chain of dependent loads, short chains = low latency).  Everything that

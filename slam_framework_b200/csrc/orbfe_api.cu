@@ -419,12 +419,16 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
   if ((rc = stage_event(ex, 0))) return rc;
   for (int l = 0; l < g.nlevels; ++l) {
     const LevelGeom& L = g.lv[l];
+    if (l == 0) {
+      ORBFE_LAUNCH(ex, k_pyramid_level0, dim3(L.h + 2 * ORBFE_EDGE, n), dim3(ORBFE_PYR0_THREADS), 0, g, ex->d_img, ex->d_pyr);
+      continue;
+    }
     if (L.fastResize) {
       // a strip is a chain of dependent loads: long strips (row re-use) only when the launch still fills
       // the GPU with warps several times over; otherwise short strips, more warps, less latency
       const int strips = (L.pyrWords + 31) / 32, ph = L.h + 2 * ORBFE_EDGE;
       int stripRows = ORBFE_PYR_ROWS;
-      while (stripRows > 2 && (long long)strips * ((ph + stripRows - 1) / stripRows) * n < 4LL * 148 * 64) stripRows >>= 1;
+      while (stripRows > 2 && (long long)strips * ((ph + stripRows - 1) / stripRows) * n < 1LL * 148 * 64) stripRows >>= 1;
       const int tasks = ((L.pyrWords + 31) / 32) * ((L.h + 2 * ORBFE_EDGE + stripRows - 1) / stripRows);
       ORBFE_LAUNCH(ex, k_pyramid_resize, dim3((tasks + ORBFE_PYR_THREADS / 32 - 1) / (ORBFE_PYR_THREADS / 32), n),
                    dim3(ORBFE_PYR_THREADS), 0, g, l, stripRows, ex->d_pyr, ex->d_rlut, ex->d_wlut);
