@@ -106,7 +106,7 @@ __device__ __forceinline__ float orbfe_sincosf(float y, int is_cos) {
 __global__ void __launch_bounds__(ORBFE_DESC_THREADS)
 k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                   const unsigned* __restrict__ lvlKp, const int* __restrict__ lvlCnt, orbfe_kp_dev* __restrict__ kps,
-                  uint8_t* __restrict__ desc, int* __restrict__ nKp, const int kpw) {
+                  uint8_t* __restrict__ desc, int* __restrict__ nKp, const int kpw, const uint2* __restrict__ icw) {
   const int slot = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * (ORBFE_DESC_THREADS / 32) + (threadIdx.x >> 5);
@@ -133,27 +133,34 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     resp = ORBFE_PS(pk);
   }
   const uint8_t* pyrSlot = pyr + (size_t)slot * g.pyrStride;
-  // ---- E5: intensity centroid on the unblurred level
+  // ---- E5: intensity centroid on the unblurred level.  Lane = patch row v (31 rows); the row's 31 bytes lie in
+  // 9 aligned words; per-byte weights (u+15 inside the disc, 0 outside) and the 0/1 disc mask come from a
+  // host-built table indexed by (alignment of the row start, |v|), so a row costs 9 x (LDG + 2 IDP.4A):
+  // m10 = sum(u*I) = sum((u+15)*I) - 15*sum(I),  m01 = sum_v v * sum_u I.
   int my10 = 0, my01 = 0;
-  const int u = lane - ORBFE_HALF_PATCH;
-  const int au = u < 0 ? -u : u;
+  const int v = lane - ORBFE_HALF_PATCH;
+  const int av = v < 0 ? -v : v;
 #pragma unroll kDescUnroll
   for (int k = 0; k < nk; ++k) {
     const int lv = __shfl_sync(0xffffffffu, level, k);
     const int cx = __shfl_sync(0xffffffffu, kx, k), cy = __shfl_sync(0xffffffffu, ky, k);
     const LevelGeom& L = g.lv[lv];
-    const uint8_t* center = pyrSlot + L.planeOff + (size_t)(cy + ORBFE_EDGE) * L.pitch + cx + ORBFE_EDGE;
     int m10 = 0, m01 = 0;
     if (lane < 31) {
+      const int col = cx + ORBFE_EDGE - ORBFE_HALF_PATCH;  // padded column of the row's first pixel
+      const unsigned* rowp = reinterpret_cast<const unsigned*>(pyrSlot + L.planeOff) +
+                             (((size_t)(cy + ORBFE_EDGE + v) * L.pitch + col) >> 2);
+      const uint2* wt = icw + ((col & 3) * 16 + av) * 9;
+      unsigned su = 0, s1 = 0;
 #pragma unroll
-      for (int v = -ORBFE_HALF_PATCH; v <= ORBFE_HALF_PATCH; ++v) {
-        const int av = v < 0 ? -v : v;
-        if (au <= c_umax[av]) {  // av is a compile-time constant after unrolling: uniform bank read
-          const int val = __ldg(center + v * L.pitch + u);
-          m10 += u * val;
-          m01 += v * val;
-        }
+      for (int i = 0; i < 9; ++i) {
+        const unsigned w = __ldg(rowp + i);
+        const uint2 t = __ldg(wt + i);
+        su = __dp4a(w, t.x, su);
+        s1 = __dp4a(w, t.y, s1);
       }
+      m10 = (int)su - ORBFE_HALF_PATCH * (int)s1;
+      m01 = v * (int)s1;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -82,9 +82,10 @@ k_pyramid_level(const __grid_constant__ Geom g, const int level, const uint8_t* 
 }
 
 // ---- level 0: copy of the input frame into its padded plane (copyMakeBorder REFLECT_101, :1071) -------
-// One CTA = one padded row of one image; a thread writes 16-byte chunks.  Interior chunks are 5 aligned
-// words of the (tightly packed, arbitrarily aligned) image row + 4 funnel shifts; chunks that touch the
-// 19-px border take the per-byte reflected path.
+// One CTA = one padded row of one image.  Interior 16-byte chunks: 5 aligned words of the (tightly packed,
+// arbitrarily aligned) image row + 4 funnel shifts, one uint4 store.  The few chunks that touch the 19-px
+// border are then filled byte by byte by the whole CTA (one byte per thread), so that no warp runs a
+// 16-byte serial border path next to its interior lanes.
 #define ORBFE_PYR0_THREADS 128
 __global__ void __launch_bounds__(ORBFE_PYR0_THREADS)
 k_pyramid_level0(const __grid_constant__ Geom g, const uint8_t* __restrict__ img, uint8_t* __restrict__ pyr) {
@@ -93,30 +94,24 @@ k_pyramid_level0(const __grid_constant__ Geom g, const uint8_t* __restrict__ img
   const int y = orbfe_reflect101(py - ORBFE_EDGE, L.h);
   const size_t rowByte = (size_t)slot * g.imgStride + (size_t)y * g.imgPitch;
   const uint8_t* src = img + rowByte;
-  uint4* dst = reinterpret_cast<uint4*>(pyr + (size_t)slot * g.pyrStride + L.planeOff + (size_t)py * L.pitch);
+  uint8_t* drow = pyr + (size_t)slot * g.pyrStride + L.planeOff + (size_t)py * L.pitch;
+  uint4* dst = reinterpret_cast<uint4*>(drow);
   const int pw = L.w + 2 * ORBFE_EDGE;
-  for (int c = threadIdx.x; 16 * c < pw; c += ORBFE_PYR0_THREADS) {
-    const int x0 = 16 * c - ORBFE_EDGE;
-    unsigned o[4];
-    if (x0 >= 0 && x0 + 15 < L.w) {
-      const size_t a = rowByte + (size_t)x0;
-      const unsigned* s4 = reinterpret_cast<const unsigned*>(img) + (a >> 2);
-      const int sh = 8 * (int)(a & 3);
-      const unsigned w0 = __ldg(s4), w1 = __ldg(s4 + 1), w2 = __ldg(s4 + 2), w3 = __ldg(s4 + 3), w4 = __ldg(s4 + 4);
-      o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh);
-      o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        o[q] = 0;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int x = orbfe_reflect101(min(16 * c + 4 * q + b, pw - 1) - ORBFE_EDGE, L.w);
-          o[q] |= (unsigned)__ldg(src + x) << (8 * b);
-        }
-      }
-    }
-    dst[c] = make_uint4(o[0], o[1], o[2], o[3]);
+  // interior chunks: c in [cLo, cHi): 16c-19 >= 0 and 16c-19+15 < w
+  const int cLo = (ORBFE_EDGE + 15) >> 4, cHi = max(cLo, (L.w + ORBFE_EDGE - 16) / 16 + 1);
+  for (int c = cLo + threadIdx.x; c < cHi; c += ORBFE_PYR0_THREADS) {
+    const size_t a = rowByte + (size_t)(16 * c - ORBFE_EDGE);
+    const unsigned* s4 = reinterpret_cast<const unsigned*>(img) + (a >> 2);
+    const int sh = 8 * (int)(a & 3);
+    const unsigned w0 = __ldg(s4), w1 = __ldg(s4 + 1), w2 = __ldg(s4 + 2), w3 = __ldg(s4 + 3), w4 = __ldg(s4 + 4);
+    dst[c] = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                        __funnelshift_r(w3, w4, sh));
+  }
+  // border bytes: padded columns [0, 16*cLo) and [16*cHi, pitch)
+  const int nLeft = 16 * cLo, nRight = L.pitch - 16 * cHi;
+  for (int t = threadIdx.x; t < nLeft + nRight; t += ORBFE_PYR0_THREADS) {
+    const int px = t < nLeft ? t : 16 * cHi + (t - nLeft);
+    drow[px] = __ldg(src + orbfe_reflect101(min(px, pw - 1) - ORBFE_EDGE, L.w));
   }
 }
 

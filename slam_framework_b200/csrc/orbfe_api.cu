@@ -76,6 +76,7 @@ struct orbfe_extractor {
   PyrWordLut* d_wlut = nullptr;
   PyrRowLut* d_rlut = nullptr;
   int* d_err = nullptr;
+  uint2* d_icw = nullptr;           // IC_Angle per-byte weight table (k_orient_describe)
   // stereo
   StereoPair* d_pairs = nullptr;
   float* d_uR = nullptr;
@@ -140,7 +141,7 @@ static void free_arena(orbfe_extractor* ex) {
   cudaFree(ex->oct.cand); cudaFree(ex->oct.knode); cudaFree(ex->oct.cellStart); cudaFree(ex->oct.nodes);
   cudaFree(ex->oct.childCnt); cudaFree(ex->oct.childSlot); cudaFree(ex->oct.best); cudaFree(ex->oct.finSeq);
   cudaFree(ex->oct.finKey); cudaFree(ex->d_lvlKp); cudaFree(ex->d_lvlCnt); cudaFree(ex->d_kps); cudaFree(ex->d_desc);
-  cudaFree(ex->d_nKp); cudaFree(ex->d_lut); cudaFree(ex->d_wlut); ex->d_wlut = nullptr; cudaFree(ex->d_rlut); ex->d_rlut = nullptr; cudaFree(ex->d_err); cudaFree(ex->d_pairs); cudaFree(ex->d_uR);
+  cudaFree(ex->d_icw); ex->d_icw = nullptr; cudaFree(ex->d_nKp); cudaFree(ex->d_lut); cudaFree(ex->d_wlut); ex->d_wlut = nullptr; cudaFree(ex->d_rlut); ex->d_rlut = nullptr; cudaFree(ex->d_err); cudaFree(ex->d_pairs); cudaFree(ex->d_uR);
   cudaFree(ex->d_depth); cudaFree(ex->d_sad); cudaFree(ex->d_nMatched); cudaFree(ex->d_rowStart); cudaFree(ex->d_rowItems);
   ex->d_rowStart = ex->d_rowItems = nullptr;
   cudaFreeHost(ex->h_n); cudaFreeHost(ex->h_kps); cudaFreeHost(ex->h_desc); cudaFreeHost(ex->h_uR);
@@ -366,6 +367,24 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   if (!rlut.empty())
     CUDA_TRY(cudaMemcpyAsync(ex->d_rlut, rlut.data(), rlut.size() * sizeof(PyrRowLut), cudaMemcpyHostToDevice, ex->stream));
   CUDA_TRY(cudaMalloc(&ex->d_err, sizeof(int)));
+  {
+    // IC_Angle weights (orb_extractor.cpp:18-45, umax :393-410): byte p of the 36-byte aligned window of patch
+    // row v holds pixel u = p - a - 15 (a = alignment of the row start); weight u+15 and mask 1 inside the disc
+    static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    std::vector<uint2> icw(4 * 16 * 9);
+    for (int a = 0; a < 4; ++a)
+      for (int av = 0; av < 16; ++av)
+        for (int i = 0; i < 9; ++i) {
+          unsigned wu = 0, w1 = 0;
+          for (int b = 0; b < 4; ++b) {
+            const int u = 4 * i + b - a - ORBFE_HALF_PATCH;
+            if (u >= -umax[av] && u <= umax[av]) { wu |= (unsigned)(u + ORBFE_HALF_PATCH) << (8 * b); w1 |= 1u << (8 * b); }
+          }
+          icw[(a * 16 + av) * 9 + i] = make_uint2(wu, w1);
+        }
+    CUDA_TRY(cudaMalloc(&ex->d_icw, icw.size() * sizeof(uint2)));
+    CUDA_TRY(cudaMemcpy(ex->d_icw, icw.data(), icw.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  }
   CUDA_TRY(cudaMalloc(&ex->d_pairs, S * sizeof(StereoPair)));
   CUDA_TRY(cudaMalloc(&ex->d_uR, S * g.totalOut * sizeof(float)));
   CUDA_TRY(cudaMalloc(&ex->d_depth, S * g.totalOut * sizeof(float)));
@@ -454,7 +473,7 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
     const int kpw = n >= 16 ? 32 : (n >= 4 ? 8 : 4);  // keypoints per warp (see k_orient_describe)
     const int warps = (g.totalOut + kpw - 1) / kpw, wpc = ORBFE_DESC_THREADS / 32;
     ORBFE_LAUNCH(ex, k_orient_describe, dim3((warps + wpc - 1) / wpc, n), dim3(ORBFE_DESC_THREADS), 0, g, ex->d_pyr, ex->d_blur,
-                 ex->d_lvlKp, ex->d_lvlCnt, ex->d_kps, ex->d_desc, ex->d_nKp, kpw);
+                 ex->d_lvlKp, ex->d_lvlCnt, ex->d_kps, ex->d_desc, ex->d_nKp, kpw, ex->d_icw);
   }
   if ((rc = stage_event(ex, 5))) return rc;
   CUDA_TRY(cudaGetLastError());
