@@ -21,6 +21,7 @@
 #ifndef ORBFE_DESC_UNROLL
 #define ORBFE_DESC_UNROLL 2
 #endif
+#define ORBFE_DESC_PW 12  // words per staged patch row (48 B >= 37 + 3 alignment bytes)
 constexpr int kDescUnroll = ORBFE_DESC_UNROLL;  // keypoints processed per loop iteration (memory-level parallelism)
 
 // global (L1-cached) rather than __constant__: each lane reads ITS 32 bytes, and per-lane addresses in
@@ -103,7 +104,10 @@ __device__ __forceinline__ float orbfe_sincosf(float y, int is_cos) {
 //   phase 3  per keypoint, lane i builds descriptor byte i; the lane's 16 pattern points live in
 //            registers for all 32 keypoints (per-lane constant-bank reads are serialised by the
 //            address-divergence unit, so they are paid once per warp, not once per keypoint).
-__global__ void __launch_bounds__(ORBFE_DESC_THREADS)
+#ifndef ORBFE_DESC_MINB
+#define ORBFE_DESC_MINB 12  // caps registers at 85: 24 warps/SM (A/B measured, see profiles)
+#endif
+__global__ void __launch_bounds__(ORBFE_DESC_THREADS, ORBFE_DESC_MINB)
 k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                   const unsigned* __restrict__ lvlKp, const int* __restrict__ lvlCnt, orbfe_kp_dev* __restrict__ kps,
                   uint8_t* __restrict__ desc, int* __restrict__ nKp, const int kpw, const uint2* __restrict__ icw) {
@@ -133,35 +137,41 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     resp = ORBFE_PS(pk);
   }
   const uint8_t* pyrSlot = pyr + (size_t)slot * g.pyrStride;
-  // ---- E5: intensity centroid on the unblurred level.  Lane = patch row v (31 rows); the row's 31 bytes lie in
-  // 9 aligned words; per-byte weights (u+15 inside the disc, 0 outside) and the 0/1 disc mask come from a
-  // host-built table indexed by (alignment of the row start, |v|), so a row costs 9 x (LDG + 2 IDP.4A):
-  // m10 = sum(u*I) = sum((u+15)*I) - 15*sum(I),  m01 = sum_v v * sum_u I.
+  // ---- E5: intensity centroid on the unblurred level.  A patch row's 31 bytes lie in 9 aligned words; lanes
+  // = (row within a group of 3, word), so one load instruction touches 3 rows (few L1 wavefronts) and the
+  // patch takes 11 of them.  Per-byte weights (u+15 inside the disc, 0 outside) and the 0/1 disc mask come
+  // from a host-built table indexed by (alignment of the row start, |v|, word):
+  // m10 = sum(u*I) = sum((u+15)*I) - 15*sum(I),  m01 = sum_v v * sum_u I  (exact integer sums).
   int my10 = 0, my01 = 0;
-  const int v = lane - ORBFE_HALF_PATCH;
-  const int av = v < 0 ? -v : v;
+  const int rg = lane / 9, wi = lane - 9 * rg;  // lanes 27..31 idle in this phase
 #pragma unroll kDescUnroll
   for (int k = 0; k < nk; ++k) {
     const int lv = __shfl_sync(0xffffffffu, level, k);
     const int cx = __shfl_sync(0xffffffffu, kx, k), cy = __shfl_sync(0xffffffffu, ky, k);
     const LevelGeom& L = g.lv[lv];
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-      const int col = cx + ORBFE_EDGE - ORBFE_HALF_PATCH;  // padded column of the row's first pixel
-      const unsigned* rowp = reinterpret_cast<const unsigned*>(pyrSlot + L.planeOff) +
-                             (((size_t)(cy + ORBFE_EDGE + v) * L.pitch + col) >> 2);
-      const uint2* wt = icw + ((col & 3) * 16 + av) * 9;
-      unsigned su = 0, s1 = 0;
+    const int col = cx + ORBFE_EDGE - ORBFE_HALF_PATCH;  // padded column of a row's first pixel
+    const int pitchW = L.pitch >> 2;
+    const unsigned* p0 = reinterpret_cast<const unsigned*>(pyrSlot + L.planeOff) +
+                         (size_t)(cy + ORBFE_EDGE - ORBFE_HALF_PATCH) * pitchW + (col >> 2) + wi;
+    const uint2* wt = icw + (col & 3) * (16 * 9) + wi;
+    unsigned su = 0, s1 = 0;
+    int m01 = 0;
+    if (rg < 3) {
 #pragma unroll
-      for (int i = 0; i < 9; ++i) {
-        const unsigned w = __ldg(rowp + i);
-        const uint2 t = __ldg(wt + i);
-        su = __dp4a(w, t.x, su);
-        s1 = __dp4a(w, t.y, s1);
+      for (int it = 0; it < 11; ++it) {
+        const int r = 3 * it + rg;  // patch row 0..30 (v = r - 15)
+        if (r < 31) {
+          const int v = r - ORBFE_HALF_PATCH;
+          const unsigned w = __ldg(p0 + (size_t)r * pitchW);
+          const uint2 t = __ldg(wt + (v < 0 ? -v : v) * 9);
+          su = __dp4a(w, t.x, su);
+          const unsigned rs = __dp4a(w, t.y, 0u);
+          s1 += rs;
+          m01 += v * (int)rs;
+        }
       }
-      m10 = (int)su - ORBFE_HALF_PATCH * (int)s1;
-      m01 = v * (int)s1;
     }
+    int m10 = (int)su - ORBFE_HALF_PATCH * (int)s1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       m10 += __shfl_xor_sync(0xffffffffu, m10, o);
@@ -202,6 +212,7 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
       py[t] = (float)(signed char)((w[t >> 1] >> (16 * (t & 1) + 8)) & 0xffu);
     }
   }
+  __shared__ unsigned s_patch[ORBFE_DESC_THREADS / 32][2][37 * ORBFE_DESC_PW];
   const uint8_t* blurSlot = blur + (size_t)slot * g.blurStride;
   uint8_t* dOut = desc + ((size_t)slot * g.totalOut + base) * 32;
 #pragma unroll kDescUnroll
@@ -215,8 +226,21 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     unsigned val = 0;
     // the pattern reaches 18 px (|offset| <= 18 after rotation): keypoints at least 19 px inside the level
     // need no edge handling (warp-uniform branch; ~97 % of the keypoints)
-    if (cx >= 19 && cy >= 19 && cx < W - 19 && cy < Hh - 19) {
-      const uint8_t* centre = bplane + (size_t)cy * bp + cx;
+    const int pbase = (cx - 18) & ~3;  // first staged column (word aligned)
+    if (cx >= 18 && cy >= 18 && cx + 18 < W && cy + 18 < Hh && pbase + 4 * ORBFE_DESC_PW <= bp) {
+      // the 37 x 37 sampling window is staged in shared memory with coalesced word loads; the 512 scattered
+      // byte reads then cost ~3 bank-conflict wavefronts each instead of one L1 wavefront per touched line
+      unsigned* patch = s_patch[threadIdx.x >> 5][k & 1];
+      const unsigned* gsrc = reinterpret_cast<const unsigned*>(bplane + (size_t)(cy - 18) * bp + pbase);
+      const int bpW = bp >> 2;
+#pragma unroll
+      for (int i = 0; i < (37 * ORBFE_DESC_PW + 31) / 32; ++i) {
+        const int t = 32 * i + lane;
+        const int row = t / ORBFE_DESC_PW, wc = t - row * ORBFE_DESC_PW;
+        if (t < 37 * ORBFE_DESC_PW) patch[t] = __ldg(gsrc + (size_t)row * bpW + wc);
+      }
+      __syncwarp();
+      const uint8_t* centre = reinterpret_cast<const uint8_t*>(patch) + 18 * (4 * ORBFE_DESC_PW) + (cx - pbase);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         int tv[2];
@@ -225,7 +249,7 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
           const float x = px[2 * t + h], y = py[2 * t + h];
           const int iy = __float2int_rn(__fadd_rn(__fmul_rn(x, sb), __fmul_rn(y, ca)));
           const int ix = __float2int_rn(__fsub_rn(__fmul_rn(x, ca), __fmul_rn(y, sb)));
-          tv[h] = (int)__ldg(centre + iy * bp + ix);
+          tv[h] = (int)centre[iy * (4 * ORBFE_DESC_PW) + ix];
         }
         val |= (unsigned)(tv[0] < tv[1]) << t;
       }

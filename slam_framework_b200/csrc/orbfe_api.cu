@@ -470,7 +470,8 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
                dim3(ORBFE_BLUR_THREADS), 0, g, ex->d_pyr, ex->d_blur);  // one warp per strip
   if ((rc = stage_event(ex, 4))) return rc;
   {
-    const int kpw = n >= 16 ? 32 : (n >= 4 ? 8 : 4);  // keypoints per warp (see k_orient_describe)
+    int kpw = n >= 4 ? 8 : 4;  // keypoints per warp (see k_orient_describe; measured: 8 beats 32 even at 128 frames)
+    if (const char* e = getenv("ORBFE_TUNE_KPW")) { const int v = atoi(e); if (v >= 1 && v <= 32) kpw = v; }  // tuning only
     const int warps = (g.totalOut + kpw - 1) / kpw, wpc = ORBFE_DESC_THREADS / 32;
     ORBFE_LAUNCH(ex, k_orient_describe, dim3((warps + wpc - 1) / wpc, n), dim3(ORBFE_DESC_THREADS), 0, g, ex->d_pyr, ex->d_blur,
                  ex->d_lvlKp, ex->d_lvlCnt, ex->d_kps, ex->d_desc, ex->d_nKp, kpw, ex->d_icw);
