@@ -98,27 +98,32 @@ __device__ __forceinline__ int orbfe_fast_score(const uint8_t* p, int tp, int th
 //      visiting only rows that hold a survivor.
 #define ORBFE_FAST_ROWWORDS 3  // survivor row masks: up to 96 tile rows
 
-// exact FAST-9/16 corner score of the pixel at p (shared-memory tile, byte pitch tp)
+// exact FAST-9/16 corner score of the pixel at p (shared-memory tile, byte pitch tp):
+//   score + 1 = max( max_arc min_9 (ring - v),  max_arc min_9 (v - ring) ).
+// Both halves run through ONE min3/min3/max3 network on packed u16x2 lanes (VIMNMX3.U16x2): the low half
+// carries (ring - v) + 256, the high half (v - ring) + 256, both in [1, 511]; the packing is one IMAD per
+// ring pixel:  (d + 256) | (256 - d) << 16  ==  C + ring * (1 - 65536)  with C folding the centre value.
 __device__ __forceinline__ int orbfe_fast_score3(const uint8_t* p, int tp) {
-  const int v = p[0];
-  int d[16];
-  d[0] = p[3 * tp] - v;       d[1] = p[3 * tp + 1] - v;   d[2] = p[2 * tp + 2] - v;   d[3] = p[tp + 3] - v;
-  d[4] = p[3] - v;            d[5] = p[-tp + 3] - v;      d[6] = p[-2 * tp + 2] - v;  d[7] = p[-3 * tp + 1] - v;
-  d[8] = p[-3 * tp] - v;      d[9] = p[-3 * tp - 1] - v;  d[10] = p[-2 * tp - 2] - v; d[11] = p[-tp - 3] - v;
-  d[12] = p[-3] - v;          d[13] = p[tp - 3] - v;      d[14] = p[2 * tp - 2] - v;  d[15] = p[3 * tp - 1] - v;
-  int lo3[16], hi3[16];
+  const unsigned K = 1u - 65536u;                                  // d -> d in the low half, -d in the high half
+  const unsigned C = (256u | (256u << 16)) - (unsigned)p[0] * K;   // centre folded in
+  unsigned d[16];
+#define ORBFE_D(k, off) d[k] = (unsigned)p[off] * K + C
+  ORBFE_D(0, 3 * tp);       ORBFE_D(1, 3 * tp + 1);   ORBFE_D(2, 2 * tp + 2);   ORBFE_D(3, tp + 3);
+  ORBFE_D(4, 3);            ORBFE_D(5, -tp + 3);      ORBFE_D(6, -2 * tp + 2);  ORBFE_D(7, -3 * tp + 1);
+  ORBFE_D(8, -3 * tp);      ORBFE_D(9, -3 * tp - 1);  ORBFE_D(10, -2 * tp - 2); ORBFE_D(11, -tp - 3);
+  ORBFE_D(12, -3);          ORBFE_D(13, tp - 3);      ORBFE_D(14, 2 * tp - 2);  ORBFE_D(15, 3 * tp - 1);
+#undef ORBFE_D
+  unsigned m3[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    lo3[i] = __vimin3_s32(d[i], d[(i + 1) & 15], d[(i + 2) & 15]);
-    hi3[i] = __vimax3_s32(d[i], d[(i + 1) & 15], d[(i + 2) & 15]);
-  }
-  int bright = -512, dark = 512;  // max_arc min_9 (d)   /   min_arc max_9 (d)
+  for (int i = 0; i < 16; ++i) m3[i] = __vimin3_u16x2(d[i], d[(i + 1) & 15], d[(i + 2) & 15]);
+  unsigned m9[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    bright = max(bright, __vimin3_s32(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]));
-    dark = min(dark, __vimax3_s32(hi3[i], hi3[(i + 3) & 15], hi3[(i + 6) & 15]));
-  }
-  return max(bright, -dark) - 1;
+  for (int i = 0; i < 16; ++i) m9[i] = __vimin3_u16x2(m3[i], m3[(i + 3) & 15], m3[(i + 6) & 15]);
+  unsigned best = __vimax3_u16x2(m9[0], m9[1], m9[2]);
+#pragma unroll
+  for (int i = 3; i < 15; i += 2) best = __vimax3_u16x2(best, m9[i], m9[i + 1]);
+  best = __vmaxu2(best, m9[15]);
+  return (int)max(best & 0xffffu, best >> 16) - 257;
 }
 
 // two KITTI-shaped entries of the queue per lane: the same min/max networks on packed u16x2 lanes
@@ -278,24 +283,33 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
     }
 #endif
     __syncthreads();
-    // ---- 3. NMS inside the cell; survivors -> bit plane + row masks; keypoint found => no fallback
-    for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
-      const int code = queue[e], x = code & xmask, y = code >> xbits;
-      const uint8_t* c = scoreB + y * pitchB + x;
-      const int s = c[0];
-      if (s == 0) continue;
-      const int jl = s_colCell[x];
-      const int cx0 = ix0 + jl * L.wCell, cx1 = min(cx0 + L.wCell, ix1);
-      const bool hasL = x > cx0, hasR = x + 1 < cx1;  // rows outside the inner band hold score 0 already
-      bool keep = s > c[-pitchB] && s > c[pitchB];
-      if (hasL) keep = keep && s > c[-1] && s > c[-pitchB - 1] && s > c[pitchB - 1];
-      if (hasR) keep = keep && s > c[1] && s > c[-pitchB + 1] && s > c[pitchB + 1];
-      if (keep) {
-        atomicOr(&bitsW[y * bitsP + (x >> 5)], 1u << (x & 31));
-        atomicOr(&s_rowmask[jl][y >> 5], 1u << (y & 31));
-        s_any[jl] = 1;
+    // ---- 3. NMS inside the cell by scanning the (sparse) score plane word by word; survivors -> bit plane
+    //         + row masks; a keypoint found => no fallback for that cell.  Re-scanning cells that already
+    //         have keypoints in round 2 is idempotent (their scores did not change).
+    for (int y = 3 + wid; y < rows - 3; y += ORBFE_FAST_THREADS / 32)
+      for (int wi = lane; wi < nWi; wi += 32) {
+        const int wx = w0 + wi;
+        const unsigned sw = scoreW[y * pitchW + wx];
+        if (sw == 0u) continue;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+          const int s = (sw >> (8 * bb)) & 0xff;
+          if (s == 0) continue;
+          const int x = 4 * wx + bb;
+          const uint8_t* c = scoreB + y * pitchB + x;
+          const int jl = s_colCell[x];
+          const int cx0 = ix0 + jl * L.wCell, cx1 = min(cx0 + L.wCell, ix1);
+          const bool hasL = x > cx0, hasR = x + 1 < cx1;  // rows outside the inner band hold score 0 already
+          bool keep = s > c[-pitchB] && s > c[pitchB];
+          if (hasL) keep = keep && s > c[-1] && s > c[-pitchB - 1] && s > c[pitchB - 1];
+          if (hasR) keep = keep && s > c[1] && s > c[-pitchB + 1] && s > c[pitchB + 1];
+          if (keep) {
+            atomicOr(&bitsW[y * bitsP + (x >> 5)], 1u << (x & 31));
+            atomicOr(&s_rowmask[jl][y >> 5], 1u << (y & 31));
+            s_any[jl] = 1;
+          }
+        }
       }
-    }
     __syncthreads();
   }
   // ---- 4. ordered emission, one warp per cell, only rows that hold a survivor
