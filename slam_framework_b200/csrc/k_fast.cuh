@@ -283,33 +283,24 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
     }
 #endif
     __syncthreads();
-    // ---- 3. NMS inside the cell by scanning the (sparse) score plane word by word; survivors -> bit plane
-    //         + row masks; a keypoint found => no fallback for that cell.  Re-scanning cells that already
-    //         have keypoints in round 2 is idempotent (their scores did not change).
-    for (int y = 3 + wid; y < rows - 3; y += ORBFE_FAST_THREADS / 32)
-      for (int wi = lane; wi < nWi; wi += 32) {
-        const int wx = w0 + wi;
-        const unsigned sw = scoreW[y * pitchW + wx];
-        if (sw == 0u) continue;
-#pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-          const int s = (sw >> (8 * bb)) & 0xff;
-          if (s == 0) continue;
-          const int x = 4 * wx + bb;
-          const uint8_t* c = scoreB + y * pitchB + x;
-          const int jl = s_colCell[x];
-          const int cx0 = ix0 + jl * L.wCell, cx1 = min(cx0 + L.wCell, ix1);
-          const bool hasL = x > cx0, hasR = x + 1 < cx1;  // rows outside the inner band hold score 0 already
-          bool keep = s > c[-pitchB] && s > c[pitchB];
-          if (hasL) keep = keep && s > c[-1] && s > c[-pitchB - 1] && s > c[pitchB - 1];
-          if (hasR) keep = keep && s > c[1] && s > c[-pitchB + 1] && s > c[pitchB + 1];
-          if (keep) {
-            atomicOr(&bitsW[y * bitsP + (x >> 5)], 1u << (x & 31));
-            atomicOr(&s_rowmask[jl][y >> 5], 1u << (y & 31));
-            s_any[jl] = 1;
-          }
-        }
+    // ---- 3. NMS inside the cell; survivors -> bit plane + row masks; keypoint found => no fallback
+    for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
+      const int code = queue[e], x = code & xmask, y = code >> xbits;
+      const uint8_t* c = scoreB + y * pitchB + x;
+      const int s = c[0];
+      if (s == 0) continue;
+      const int jl = s_colCell[x];
+      const int cx0 = ix0 + jl * L.wCell, cx1 = min(cx0 + L.wCell, ix1);
+      const bool hasL = x > cx0, hasR = x + 1 < cx1;  // rows outside the inner band hold score 0 already
+      bool keep = s > c[-pitchB] && s > c[pitchB];
+      if (hasL) keep = keep && s > c[-1] && s > c[-pitchB - 1] && s > c[pitchB - 1];
+      if (hasR) keep = keep && s > c[1] && s > c[-pitchB + 1] && s > c[pitchB + 1];
+      if (keep) {
+        atomicOr(&bitsW[y * bitsP + (x >> 5)], 1u << (x & 31));
+        atomicOr(&s_rowmask[jl][y >> 5], 1u << (y & 31));
+        s_any[jl] = 1;
       }
+    }
     __syncthreads();
   }
   // ---- 4. ordered emission, one warp per cell, only rows that hold a survivor
