@@ -15,7 +15,9 @@
 #include "orbfe_common.cuh"
 #include "k_describe.cuh"
 
+#ifndef ORBFE_ST_THREADS
 #define ORBFE_ST_THREADS 256
+#endif
 
 struct StereoPair {
   const uint8_t* pyrL;          // slot base of the left / right pyramid block
@@ -84,7 +86,10 @@ __device__ __forceinline__ int orbfe_hamming256(const uint4 a0, const uint4 a1, 
          __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
-__global__ void __launch_bounds__(ORBFE_ST_THREADS)
+#ifndef ORBFE_ST_MINB
+#define ORBFE_ST_MINB 6  // <= 42 registers: 48 warps/SM hide the L2 latency of the gathers (A/B measured)
+#endif
+__global__ void __launch_bounds__(ORBFE_ST_THREADS, ORBFE_ST_MINB)
 k_stereo_search(const __grid_constant__ Geom g, const StereoPair* __restrict__ pairs, const float bf, const float baseline,
                 const int maxKp) {
   const StereoPair P = pairs[blockIdx.y];
