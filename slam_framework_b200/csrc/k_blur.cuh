@@ -25,7 +25,10 @@
 
 __device__ __forceinline__ unsigned orbfe_dp4a_u8(unsigned a, unsigned b, unsigned c) { return __dp4a(a, b, c); }
 
-__global__ void __launch_bounds__(ORBFE_BLUR_THREADS)
+#ifndef ORBFE_BLUR_MINB
+#define ORBFE_BLUR_MINB 1
+#endif
+__global__ void __launch_bounds__(ORBFE_BLUR_THREADS, ORBFE_BLUR_MINB)
 k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur) {
   const int slot = blockIdx.y;
   const int lane = threadIdx.x & 31;

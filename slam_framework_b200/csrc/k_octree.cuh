@@ -44,7 +44,10 @@ struct OctScratch {      // per-slot strided device arrays (bases for slot 0)
   int* finKey;           // totalOut per slot
 };
 
-__global__ void __launch_bounds__(ORBFE_OCT_THREADS)
+#ifndef ORBFE_OCT_MINB
+#define ORBFE_OCT_MINB 4  // <= 32 registers: 4 CTAs (64 warps) per SM for this latency-bound kernel (A/B measured)
+#endif
+__global__ void __launch_bounds__(ORBFE_OCT_THREADS, ORBFE_OCT_MINB)
 k_octree(const __grid_constant__ Geom g, const int* __restrict__ cellCnt, const unsigned* __restrict__ cellList,
          const OctScratch sc, unsigned* __restrict__ lvlKp, int* __restrict__ lvlCnt, int* __restrict__ errFlag) {
   ORBFE_DYN_SMEM(smem);

@@ -204,7 +204,10 @@ __device__ __forceinline__ void orbfe_resize_strip(const Geom& g, const int leve
   }
 }
 
-__global__ void __launch_bounds__(ORBFE_PYR_THREADS)
+#ifndef ORBFE_PYR_MINB
+#define ORBFE_PYR_MINB 1
+#endif
+__global__ void __launch_bounds__(ORBFE_PYR_THREADS, ORBFE_PYR_MINB)
 k_pyramid_resize(const __grid_constant__ Geom g, const int level, const int stripRows, uint8_t* __restrict__ pyr,
                  const PyrRowLut* __restrict__ rlut, const PyrWordLut* __restrict__ wlut) {
   const int task = blockIdx.x * (ORBFE_PYR_THREADS / 32) + (threadIdx.x >> 5);
