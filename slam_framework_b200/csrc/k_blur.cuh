@@ -18,7 +18,9 @@
 
 #define ORBFE_BLUR_THREADS 128
 #define ORBFE_BLUR_WORDS 30   // output words per warp strip (32 loaded - 2 for the right neighbours)
-#define ORBFE_BLUR_ROWS 32    // output rows per warp strip
+#ifndef ORBFE_BLUR_ROWS
+#define ORBFE_BLUR_ROWS 64    // output rows per warp strip (6 halo rows re-read per strip)
+#endif
 // legacy tile macros (geometry fields tilesX/tilesY/tileBase now count warp strips)
 #define ORBFE_BLUR_TW (4 * ORBFE_BLUR_WORDS)
 #define ORBFE_BLUR_TH ORBFE_BLUR_ROWS
@@ -76,13 +78,12 @@ k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t*
         H[s][3] = orbfe_dp4a_u8(__funnelshift_r(w1, w2, 24), KB, orbfe_dp4a_u8(__funnelshift_r(w0, w1, 24), KA, 0u));
         if (r >= 6 && writer) {
           // window rows r-6..r live in H[(s+1)%7] (oldest) .. H[s] (newest)
-          unsigned out = 0;
+          unsigned acc[4];  // V + 32768 < 2^24: the rounded result is byte 2 of the accumulator
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const unsigned acc = 18u * (H[(s + 1) % 7][j] + H[s][j]) + 34u * (H[(s + 2) % 7][j] + H[(s + 6) % 7][j]) +
-                                 48u * (H[(s + 3) % 7][j] + H[(s + 5) % 7][j]) + 56u * H[(s + 4) % 7][j];
-            out |= ((acc + 32768u) >> 16) << (8 * j);
-          }
+          for (int j = 0; j < 4; ++j)
+            acc[j] = 56u * H[(s + 4) % 7][j] + 32768u + 18u * (H[(s + 1) % 7][j] + H[s][j]) +
+                     34u * (H[(s + 2) % 7][j] + H[(s + 6) % 7][j]) + 48u * (H[(s + 3) % 7][j] + H[(s + 5) % 7][j]);
+          const unsigned out = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
           // bpitch is a multiple of 16: the word store is aligned; bytes past w land in row padding
           *reinterpret_cast<unsigned*>(dst + (size_t)(r - 6) * L.bpitch) = out;
         }
