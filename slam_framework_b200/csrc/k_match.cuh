@@ -337,6 +337,128 @@ k_match_resolve(const ResolveArgs A, const MatchScratch S) {
   if (lane == 0) A.result[0] = nmatches;
 }
 
+// ---- phase B, parallel form for the SearchByProjection routines (modes 1, 2) --------------------------
+// The only coupling between queries is the occupancy feedback: query q skips a keypoint that holds a map
+// point with observations, i.e. that was occupied on entry or was taken by an EARLIER accepted query
+// q' < q with hasObs(q') (orb_matcher.cpp:59-63 + :97, :1398-1402 + :1424).  Define
+//     firstOwner[kp] = min { q' : accepted(q'), hasObs(q'), best(q') = kp };
+// then occupied_before_q(kp) = occupiedIn[kp] || firstOwner[kp] < q, and the serial result is the unique
+// fixed point of  best = F(firstOwner(best)).  Jacobi iteration from "no owners" reaches it: after
+// iteration t the first t queries are final (induction on q), and in practice chains are 2-4 long.
+// One kernel launch per iteration, one warp per query; iterations after convergence return at once.
+struct JacobiState {
+  int* best;      // nQ: keypoint taken by the query in the previous iteration (-1 none, -2 not evaluated yet)
+  int* own;       // 3 x nKp rotating firstOwner buffers (0x7f7f7f7f = none)
+  int* changed;   // per-iteration "some query changed its answer" flags
+};
+
+__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
+k_match_iterate(const ResolveArgs A, const MatchScratch S, const JacobiState J, const int t) {
+  if (S.cursor[1]) return;                       // candidate buffer overflowed: the host re-runs
+  if (t > 0 && J.changed[t - 1] == 0) return;    // converged
+  const int lane = threadIdx.x & 31;
+  const int gtid = blockIdx.x * ORBFE_MATCH_THREADS + threadIdx.x, gsz = gridDim.x * ORBFE_MATCH_THREADS;
+  int* ownClear = J.own + (size_t)((t + 2) % 3) * A.nKp;   // becomes the write target of iteration t+1
+  for (int i = gtid; i < A.nKp; i += gsz) ownClear[i] = 0x7f7f7f7f;
+  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
+  if (q >= A.nQ) return;
+  const int* ownPrev = J.own + (size_t)(t % 3) * A.nKp;
+  int* ownNext = J.own + (size_t)((t + 1) % 3) * A.nKp;
+  const int cnt = S.qCnt[q], off = S.qOff[q];
+  unsigned best = 0xffffffffu, second = 0xffffffffu;
+  for (int c = lane; c < cnt; c += 32) {
+    const uint2 cd = S.cand[off + c];
+    const int dist = (int)(cd.y & 0xffffu);
+    if (dist < 256 && !A.occupiedIn[cd.x] && !(ownPrev[cd.x] < q)) {
+      const unsigned key = ((unsigned)dist << 20) | (unsigned)c;
+      if (key < best) { second = best; best = key; } else if (key < second) second = key;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const unsigned os = __shfl_xor_sync(0xffffffffu, second, o);
+    orbfe_merge2(best, second, ob, os);
+  }
+  if (lane != 0) return;
+  int newBest = -1;
+  if (best != 0xffffffffu) {
+    const int bestDist = (int)(best >> 20);
+    const uint2 bc = S.cand[off + (int)(best & 0xfffffu)];
+    bool accept = bestDist <= 100;  // TH_HIGH
+    if (accept && A.mode == ORBFE_MODE_MAPPOINTS && second != 0xffffffffu) {
+      const uint2 sc = S.cand[off + (int)(second & 0xfffffu)];
+      if ((bc.y >> 16) == (sc.y >> 16) && (float)bestDist > __fmul_rn(A.nnratio, (float)(int)(second >> 20))) accept = false;
+    }
+    if (accept) newBest = (int)bc.x;
+  }
+  if (t == 0 || newBest != J.best[q]) { J.best[q] = newBest; J.changed[t] = 1; }
+  if (newBest >= 0 && A.hasObs[q]) atomicMin(&ownNext[newBest], q);
+}
+
+// after convergence: F.SetMapPoint results (the LAST accepted query on a keypoint wins), the match count and
+// the rotation-consistency check (one CTA)
+__global__ void __launch_bounds__(1024)
+k_match_finalize(const ResolveArgs A, const MatchScratch S, const JacobiState J) {
+  __shared__ int s_hist[ORBFE_HISTO_LENGTH];
+  __shared__ int s_ind[3];
+  __shared__ int s_n;
+  if (S.cursor[1]) return;
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int i = tid; i < A.nKp; i += T) A.out[i] = -1;
+  if (tid < ORBFE_HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  const bool ori = A.checkOri && A.mode == ORBFE_MODE_LASTFRAME;
+  const float factor = 1.0f / ORBFE_HISTO_LENGTH;  // orb_matcher.cpp:1322 (the reference's bin-width bug, kept)
+  int mine = 0;
+  for (int q = tid; q < A.nQ; q += T) {
+    const int b = J.best[q];
+    int bin = -1;
+    if (b >= 0) {
+      ++mine;
+      atomicMax(&A.out[b], q);
+      if (ori) {
+        float rot = __fsub_rn(A.qAngle[q], A.kp[b].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == ORBFE_HISTO_LENGTH) bin = 0;
+        atomicAdd(&s_hist[bin], 1);
+      }
+    }
+    A.evBin[q] = bin;
+  }
+  if (mine) atomicAdd(&s_n, mine);
+  __syncthreads();
+  if (ori) {
+    if (tid == 0) {  // ComputeThreeMaxima (orb_matcher.cpp:1584-1625)
+      int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+      for (int i = 0; i < ORBFE_HISTO_LENGTH; i++) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+      s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+    }
+    __syncthreads();
+    int removed = 0;
+    for (int q = tid; q < A.nQ; q += T) {
+      const int bin = A.evBin[q];
+      if (bin >= 0 && bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) {
+        A.out[J.best[q]] = -1;  // CurrentFrame.SetMapPoint(idx, NULL); nmatches-- (:1441-1446)
+        ++removed;
+      }
+    }
+    // every atomicMax above is complete (barrier) before any thread writes -1
+    if (removed) atomicSub(&s_n, removed);
+    __syncthreads();
+  }
+  if (tid == 0) A.result[0] = s_n;
+}
+
 // ---- OrbMatcher::DescriptorDistance, batched (orb_matcher.cpp:1630-1646) --------------------------
 __global__ void __launch_bounds__(256)
 k_descriptor_distance(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, const int n, int* __restrict__ d) {

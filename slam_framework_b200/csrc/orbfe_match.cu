@@ -47,6 +47,10 @@ struct orbfe_frame {
   int outCap = 0;
   uint2* d_cand = nullptr;
   int candCap = 0;
+  int* d_jbest = nullptr;   // Jacobi resolve state (k_match_iterate)
+  int* d_jown = nullptr;
+  int* d_jchanged = nullptr;
+  int jCap = 0;
   int* d_cursor = nullptr;  // [0] cursor [1] overflow [2] nmatches
   int* h_res = nullptr;     // pinned, 4 ints
   FrameGrid grid() const {
@@ -116,7 +120,7 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, int mode, float nnra
   if (f->candCap == 0 && (rc = ensure_cand(f, std::max(nq * 48 + 4096, 1 << 16)))) return rc;
   const size_t stateInts = mode == ORBFE_MODE_INIT ? 2 * (size_t)f->n : (size_t)f->n;
   const size_t smem = std::max<size_t>(stateInts * sizeof(int), 16);
-  if (smem > 200 * 1024) return orbfe_fail(ORBFE_ERR_INVALID, "frame has too many keypoints (%d) for the resolve kernel", f->n);
+  if (mode == ORBFE_MODE_INIT && smem > 200 * 1024) return orbfe_fail(ORBFE_ERR_INVALID, "frame has too many keypoints (%d) for the resolve kernel", f->n);
   cudaStream_t st = f->stream;
   const size_t q4 = (size_t)nq * sizeof(float);
   CUDA_TRY(cudaMemcpyAsync(f->d_qx, Q.x.data(), q4, cudaMemcpyHostToDevice, st));
@@ -133,6 +137,14 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, int mode, float nnra
 #ifndef ORBFE_EMU
   CUDA_TRY(cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
+  const bool jacobi = mode != ORBFE_MODE_INIT;  // SearchForInitialization keeps the serial one-warp resolve
+  if (jacobi && nq > f->jCap) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(regrow(&f->d_jbest, (size_t)nq + 256));
+    CUDA_TRY(regrow(&f->d_jchanged, (size_t)nq + 256 + 16));
+    f->jCap = nq + 256;
+  }
+  if (jacobi && !f->d_jown) CUDA_TRY(regrow(&f->d_jown, 3 * (size_t)std::max(f->n, 1)));
   for (int attempt = 0; attempt < 8; ++attempt) {
     CUDA_TRY(cudaMemsetAsync(f->d_cursor, 0, 4 * sizeof(int), st));
     MatchQueries MQ;
@@ -147,9 +159,26 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, int mode, float nnra
     if (nq > 0)
       MATCH_LAUNCH(f, k_match_candidates, dim3((nq + ORBFE_MATCH_THREADS / 32 - 1) / (ORBFE_MATCH_THREADS / 32)),
                    dim3(ORBFE_MATCH_THREADS), 0, f->grid(), MQ, S);
-    MATCH_LAUNCH(f, k_match_resolve, dim3(1), dim3(32), smem, A, S);
+    if (!jacobi) {
+      MATCH_LAUNCH(f, k_match_resolve, dim3(1), dim3(32), smem, A, S);
+    } else {
+      JacobiState J;
+      J.best = f->d_jbest; J.own = f->d_jown; J.changed = f->d_jchanged;
+      CUDA_TRY(cudaMemsetAsync(f->d_jown, 0x7f, 3 * (size_t)std::max(f->n, 1) * sizeof(int), st));
+      CUDA_TRY(cudaMemsetAsync(f->d_jchanged, 0, ((size_t)nq + 16) * sizeof(int), st));
+      const int grid = std::max(1, (nq + ORBFE_MATCH_THREADS / 32 - 1) / (ORBFE_MATCH_THREADS / 32));
+      const int chunk = 8;
+      int t = 0;
+      for (;;) {  // iterations are launched in chunks; converged iterations return immediately
+        for (int k = 0; k < chunk && t <= nq; ++k, ++t) MATCH_LAUNCH(f, k_match_iterate, dim3(grid), dim3(ORBFE_MATCH_THREADS), 0, A, S, J, t);
+        CUDA_TRY(cudaMemcpyAsync(f->h_res + 3, f->d_jchanged + (t - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (f->h_res[3] == 0 || t > nq) break;  // a fixed point is reached after at most nq iterations
+      }
+      MATCH_LAUNCH(f, k_match_finalize, dim3(1), dim3(1024), 0, A, S, J);
+    }
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(f->h_res, f->d_cursor, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(f->h_res, f->d_cursor, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (!f->h_res[1]) {
       if (out_n > 0) CUDA_TRY(cudaMemcpy(out, f->d_out, (size_t)out_n * sizeof(int), cudaMemcpyDeviceToHost));
@@ -197,7 +226,7 @@ int orbfe_frame_destroy(orbfe_frame* f) {
   cudaFree(f->d_qx); cudaFree(f->d_qy); cudaFree(f->d_qr); cudaFree(f->d_qxr); cudaFree(f->d_qAngle); cudaFree(f->d_qMinL);
   cudaFree(f->d_qMaxL); cudaFree(f->d_qOff); cudaFree(f->d_qCnt); cudaFree(f->d_evBin); cudaFree(f->d_evIdx);
   cudaFree(f->d_qValid); cudaFree(f->d_qDesc); cudaFree(f->d_qHasObs); cudaFree(f->d_occ); cudaFree(f->d_out);
-  cudaFree(f->d_cand); cudaFree(f->d_cursor);
+  cudaFree(f->d_cand); cudaFree(f->d_cursor); cudaFree(f->d_jbest); cudaFree(f->d_jown); cudaFree(f->d_jchanged);
   cudaFreeHost(f->h_res);
   if (f->stream) cudaStreamDestroy(f->stream);
   delete f;

@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Secondary measurement: the matcher rows (M2-M4) of SURVEY.md 8 on the GPU next to the CPU oracle, on the
+BASELINE config-4 / config-5 shapes.  Wall clock of the C-ABI call (host arrays in, host arrays out), median of
+`reps` calls; prints one JSON line.  usage: python tools/bench_matchers.py [--reps 20]"""
+import argparse, json, os, statistics, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import oracle_lib as O
+import parity_common as P
+from slam_framework_b200 import orbfe, synth
+
+
+def med(f, reps):
+    f()
+    t = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); f(); t.append((time.perf_counter() - t0) * 1e3)
+    return statistics.median(t)
+
+
+def main():
+    ap = argparse.ArgumentParser(); ap.add_argument("--reps", type=int, default=20); a = ap.parse_args()
+    L = orbfe.load()
+    out = {}
+    # config 5: 1080p, 8000 features, 20k projected map points
+    for (h, w) in ((1080, 1920), (2160, 3840)):
+        img = synth.frame(h, w, seed=w)
+        ex = orbfe.ORBextractor(8000, lib=L)
+        kps, desc = ex.Compute(img)
+        t_ext = med(lambda: ex.Compute(img), 5)
+        oe = O.Extractor(8000)
+        t0 = time.perf_counter(); oe.extract(img); t_ext_cpu = (time.perf_counter() - t0) * 1e3
+        scale = ex.GetScaleFactors()
+        F, OF = P.make_frames(kps, desc, scale, w, h, L)
+        mp = P.synth_map_points(kps, desc, np.random.default_rng(3), 20000)
+        args = (mp["valid"], mp["px"], mp["py"], mp["pxr"], mp["lvl"], mp["view"], mp["desc"], mp["has_obs"], mp["occupied"])
+        m = orbfe.OrbMatcher(0.8)
+        n, asg = m.SearchByProjectionMapPoints(F, *args, 1)
+        on, oasg = O.search_by_projection_mappoints(OF, *args, 1, 0.8)
+        assert n == on and np.array_equal(asg, oasg)
+        out[f"config5_{w}x{h}"] = {
+            "extract_8000_ms_gpu": t_ext, "extract_8000_ms_cpu_oracle_1thread": t_ext_cpu, "keypoints": len(kps),
+            "search_by_projection_20k_ms_gpu": med(lambda: m.SearchByProjectionMapPoints(F, *args, 1), a.reps),
+            "search_by_projection_20k_ms_cpu_oracle_1thread": med(lambda: O.search_by_projection_mappoints(OF, *args, 1, 0.8), 5),
+            "matches": n}
+        ex.close()
+    # config 4: mono, 4000 features, SearchForInitialization
+    a_img, b_img = synth.shifted_frame(21, dx=8, dy=4)
+    ex = orbfe.ORBextractor(4000, lib=L)
+    k1, d1 = ex.Compute(a_img); k2, d2 = ex.Compute(b_img)
+    scale = ex.GetScaleFactors()
+    F1, OF1 = P.make_frames(k1, d1, scale, 1241, 376, L); F2, OF2 = P.make_frames(k2, d2, scale, 1241, 376, L)
+    prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+    m = orbfe.OrbMatcher(0.9, True)
+    n, m12, _ = m.SearchForInitialization(F1, F2, prev, 100)
+    on, om12, _ = O.search_for_initialization(OF1, OF2, prev, 100, 0.9, True)
+    assert n == on and np.array_equal(m12, om12)
+    out["config4_mono_4000"] = {
+        "extract_4000_ms_gpu": med(lambda: ex.Compute(a_img), 10),
+        "search_for_initialization_ms_gpu": med(lambda: m.SearchForInitialization(F1, F2, prev, 100), a.reps),
+        "search_for_initialization_ms_cpu_oracle_1thread": med(lambda: O.search_for_initialization(OF1, OF2, prev, 100, 0.9, True), 5),
+        "matches": n}
+    # tracking: SearchByProjection(Cur, Last) on a KITTI frame
+    l, r = synth.stereo_pair(seed=31)
+    ex2 = orbfe.ORBextractor(lib=L)
+    kl, dl = ex2.Compute(l)
+    F, OF = P.make_frames(kl, dl, ex2.GetScaleFactors(), 1241, 376, L)
+    rng = np.random.default_rng(8); nk = len(kl)
+    u = (kl["x"] + rng.uniform(-5, 5, nk)).astype(np.float32); v = (kl["y"] + rng.uniform(-5, 5, nk)).astype(np.float32)
+    iz = rng.uniform(0.01, 0.2, nk).astype(np.float32); octv = kl["octave"].astype(np.int32); ang = kl["angle"].copy()
+    valid = np.ones(nk, np.uint8); has = np.ones(nk, np.uint8); occ = np.zeros(nk, np.uint8)
+    m = orbfe.OrbMatcher(0.9, True)
+    la = (valid, u, v, iz, octv, ang, dl, has, P.KITTI["bf"], 0, 0, occ, 7.0)
+    n, asg = m.SearchByProjectionLastFrame(F, *la)
+    on, oasg = O.search_by_projection_lastframe(OF, *la, True)
+    assert n == on and np.array_equal(asg, oasg)
+    out["tracking_kitti_2000"] = {"search_by_projection_lastframe_ms_gpu": med(lambda: m.SearchByProjectionLastFrame(F, *la), a.reps),
+                                  "search_by_projection_lastframe_ms_cpu_oracle_1thread": med(lambda: O.search_by_projection_lastframe(OF, *la, True), 5),
+                                  "frame_create_ms_gpu": med(lambda: orbfe.Frame(kl, dl, ex2.GetScaleFactors(), (0, 1241, 0, 376), lib=L).close(), a.reps),
+                                  "matches": n}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
