@@ -183,6 +183,23 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa, orig_aff = None, None
+    try:
+        orig_aff = os.sched_getaffinity(0)
+    except Exception:
+        pass
+    try:  # NUMA: run (and first-touch the pinned staging buffers) on the cores closest to this rank's GPU
+        import pynvml
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            numa = len(cpus)
+    except Exception:
+        pass
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -376,6 +393,8 @@ def run_ours(args):
     # ---- CPU baseline (oracle port on the host cores; bounded sample) ----------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
+        if orig_aff:
+            os.sched_setaffinity(0, orig_aff)  # the CPU baseline uses every host core again
         cores = host_cores()
         v1, s1, _, _ = cpu_reference_throughput(pairs, cores, cores)
         reps = int(min(max(12.0 / max(s1, 1e-3), 1), 400))  # ~12 s of host work
@@ -389,7 +408,7 @@ def run_ours(args):
            "dtype": "u8", "data": "synthetic",
            "config": {"workload": "configs[1]: synthetic KITTI-size stereo pair (1241x376), L+R ORB extraction "
                                   "(nFeatures 2000, 8 levels, 1.2, FAST 20/7) + ComputeStereoMatches, batched",
-                      "pairs_per_step_per_gpu": B, "distinct_pairs": distinct, "parallelism": f"frames sharded x{world}, no collective",
+                      "pairs_per_step_per_gpu": B, "distinct_pairs": distinct, "parallelism": f"frames sharded x{world}, no collective", "host_affinity_cores": numa,
                       "l2": "per-step working set (images+pyramids+blur) ~%d MB > 126 MB L2" % ((n_img * (H * W + 2 * 1738559)) >> 20)},
            "gpu_launches": int(launches),
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
