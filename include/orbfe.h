@@ -196,6 +196,18 @@ int orbfe_search_by_projection_lastframe(orbfe_frame* cur, int n_last, const uin
                                          float th, int check_orientation, int32_t* assigned,
                                          int* n_matches);
 
+/* OrbMatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (orb_matcher.cpp:133-262).
+ * f = the Frame (descriptors + keypoint angles).  KeyFrame side: n_kf descriptors / undistorted keypoint angles,
+ * kf_valid[i] = GetMapPointMatches()[i] != NULL && !isBad().  The two DBoW2 FeatureVectors (std::map<NodeId,
+ * vector<unsigned>>) are passed flattened: node ids ascending, start offsets (n_nodes+1) into the feature indices.
+ * matched_kf_idx[k] (out, NumKeypoints entries) = index of the KeyFrame feature whose map point
+ * vpMapPointMatches[k] receives, else -1. */
+int orbfe_search_by_bow(orbfe_frame* f, int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid,
+                        int kf_nnodes, const uint32_t* kf_node_ids, const int32_t* kf_node_start,
+                        const uint32_t* kf_feat_idx, int f_nnodes, const uint32_t* f_node_ids,
+                        const int32_t* f_node_start, const uint32_t* f_feat_idx, float nnratio,
+                        int check_orientation, int32_t* matched_kf_idx, int* n_matches);
+
 #ifdef __cplusplus
 }
 #endif

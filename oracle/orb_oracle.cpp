@@ -996,4 +996,63 @@ int orc_search_by_projection_lastframe(const orc_frame* C, int nLast, const uint
   return nmatches;
 }
 
+// OrbMatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (orb_matcher.cpp:133-262).  The DBoW2
+// FeatureVectors (std::map<NodeId, vector<unsigned>>) arrive flattened (ids ascending + offsets + indices).
+int orc_search_by_bow(const orc_frame* F, int nKF, const uint8_t* kfDesc, const float* kfAngle, const uint8_t* kfValid,
+                      int kfNodes, const uint32_t* kfIds, const int* kfStart, const uint32_t* kfIdx, int fNodes,
+                      const uint32_t* fIds, const int* fStart, const uint32_t* fIdx, float nnratio, int checkOri,
+                      int* matchedKf) {
+  (void)nKF;
+  const int TH_LOW = 50;
+  int nmatches = 0;
+  for (int i = 0; i < F->n; ++i) matchedKf[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  int a = 0, b = 0;
+  while (a < kfNodes && b < fNodes) {
+    if (kfIds[a] == fIds[b]) {
+      for (int k = kfStart[a]; k < kfStart[a + 1]; ++k) {
+        const unsigned realIdxKF = kfIdx[k];
+        if (!kfValid[realIdxKF]) continue;
+        const uint8_t* dKF = kfDesc + (size_t)realIdxKF * 32;
+        int bestDist1 = 256, bestIdxF = -1, bestDist2 = 256;
+        for (int j = fStart[b]; j < fStart[b + 1]; ++j) {
+          const unsigned realIdxF = fIdx[j];
+          if (matchedKf[realIdxF] >= 0) continue;
+          const int dist = descriptor_distance(dKF, F->desc.data() + (size_t)realIdxF * 32);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdxF = (int)realIdxF; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 <= TH_LOW) {
+          if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+            matchedKf[bestIdxF] = (int)realIdxKF;
+            if (checkOri) {
+              float rot = kfAngle[realIdxKF] - F->kps[bestIdxF].angle;
+              if (rot < 0.0) rot += 360.0f;
+              int bin = (int)std::round(rot * factor);
+              if (bin == HISTO_LENGTH) bin = 0;
+              rotHist[bin].push_back(bestIdxF);
+            }
+            nmatches++;
+          }
+        }
+      }
+      ++a; ++b;
+    } else if (kfIds[a] < fIds[b]) {
+      ++a;  // lower_bound(Fit->first) on a sorted map == advance until >=
+    } else {
+      ++b;
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx : rotHist[i]) { matchedKf[idx] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
+
 }  // extern "C"

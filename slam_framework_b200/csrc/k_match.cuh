@@ -182,7 +182,7 @@ k_match_candidates(const FrameGrid F, const MatchQueries Q, const MatchScratch S
 }
 
 // ---- phase B: serial-order resolve, one warp ------------------------------------------------------
-enum { ORBFE_MODE_INIT = 0, ORBFE_MODE_MAPPOINTS = 1, ORBFE_MODE_LASTFRAME = 2 };
+enum { ORBFE_MODE_INIT = 0, ORBFE_MODE_MAPPOINTS = 1, ORBFE_MODE_LASTFRAME = 2, ORBFE_MODE_BOW = 3 };
 
 struct ResolveArgs {
   int mode;
@@ -337,6 +337,29 @@ k_match_resolve(const ResolveArgs A, const MatchScratch S) {
   if (lane == 0) A.result[0] = nmatches;
 }
 
+// ---- phase A for SearchByBoW (orb_matcher.cpp:133-262): the candidates of a KeyFrame feature are the Frame
+// features of the same vocabulary node, in the node's own order (DBoW2 FeatureVector); no filtering, so the
+// list offsets are known on the host.  One warp per query.
+__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
+k_match_candidates_bow(const FrameGrid F, const uint8_t* __restrict__ qDescAll, const int* __restrict__ qDescIdx,
+                       const unsigned* __restrict__ featIdx, const int* __restrict__ qSrcOff, const int nQ,
+                       const MatchScratch S) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
+  if (q >= nQ) return;
+  const int cnt = S.qCnt[q], off = S.qOff[q], src = qSrcOff[q];
+  const uint8_t* qd = qDescAll + (size_t)qDescIdx[q] * 32;
+  const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(qd)), a1 = __ldg(reinterpret_cast<const uint4*>(qd) + 1);
+  for (int c = lane; c < cnt; c += 32) {
+    const int idx = (int)featIdx[src + c];
+    const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(F.desc + (size_t)idx * 32));
+    const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(F.desc + (size_t)idx * 32) + 1);
+    const int dist = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                     __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+    S.cand[off + c] = make_uint2((unsigned)idx, (unsigned)dist);
+  }
+}
+
 // ---- phase B, parallel form for the SearchByProjection routines (modes 1, 2) --------------------------
 // The only coupling between queries is the occupancy feedback: query q skips a keypoint that holds a map
 // point with observations, i.e. that was occupied on entry or was taken by an EARLIER accepted query
@@ -369,7 +392,7 @@ k_match_iterate(const ResolveArgs A, const MatchScratch S, const JacobiState J, 
   for (int c = lane; c < cnt; c += 32) {
     const uint2 cd = S.cand[off + c];
     const int dist = (int)(cd.y & 0xffffu);
-    if (dist < 256 && !A.occupiedIn[cd.x] && !(ownPrev[cd.x] < q)) {
+    if (dist < 256 && !(A.occupiedIn && A.occupiedIn[cd.x]) && !(ownPrev[cd.x] < q)) {
       const unsigned key = ((unsigned)dist << 20) | (unsigned)c;
       if (key < best) { second = best; best = key; } else if (key < second) second = key;
     }
@@ -386,6 +409,10 @@ k_match_iterate(const ResolveArgs A, const MatchScratch S, const JacobiState J, 
     const int bestDist = (int)(best >> 20);
     const uint2 bc = S.cand[off + (int)(best & 0xfffffu)];
     bool accept = bestDist <= 100;  // TH_HIGH
+    if (A.mode == ORBFE_MODE_BOW) {  // SearchByBoW: bestDist1 <= TH_LOW && bestDist1 < mfNNratio * bestDist2 (:187-189)
+      const float d2 = second == 0xffffffffu ? 256.0f : (float)(int)(second >> 20);
+      accept = bestDist <= 50 && (float)bestDist < __fmul_rn(A.nnratio, d2);
+    }
     if (accept && A.mode == ORBFE_MODE_MAPPOINTS && second != 0xffffffffu) {
       const uint2 sc = S.cand[off + (int)(second & 0xfffffu)];
       if ((bc.y >> 16) == (sc.y >> 16) && (float)bestDist > __fmul_rn(A.nnratio, (float)(int)(second >> 20))) accept = false;
@@ -393,7 +420,7 @@ k_match_iterate(const ResolveArgs A, const MatchScratch S, const JacobiState J, 
     if (accept) newBest = (int)bc.x;
   }
   if (t == 0 || newBest != J.best[q]) { J.best[q] = newBest; J.changed[t] = 1; }
-  if (newBest >= 0 && A.hasObs[q]) atomicMin(&ownNext[newBest], q);
+  if (newBest >= 0 && (A.mode == ORBFE_MODE_BOW || A.hasObs[q])) atomicMin(&ownNext[newBest], q);
 }
 
 // after convergence: F.SetMapPoint results (the LAST accepted query on a keypoint wins), the match count and
@@ -409,7 +436,7 @@ k_match_finalize(const ResolveArgs A, const MatchScratch S, const JacobiState J)
   if (tid < ORBFE_HISTO_LENGTH) s_hist[tid] = 0;
   if (tid == 0) s_n = 0;
   __syncthreads();
-  const bool ori = A.checkOri && A.mode == ORBFE_MODE_LASTFRAME;
+  const bool ori = A.checkOri && (A.mode == ORBFE_MODE_LASTFRAME || A.mode == ORBFE_MODE_BOW);
   const float factor = 1.0f / ORBFE_HISTO_LENGTH;  // orb_matcher.cpp:1322 (the reference's bin-width bug, kept)
   int mine = 0;
   for (int q = tid; q < A.nQ; q += T) {

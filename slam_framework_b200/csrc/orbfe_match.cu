@@ -403,4 +403,99 @@ int orbfe_search_by_projection_lastframe(orbfe_frame* cur, int n_last, const uin
   return run_search(cur, Q, ORBFE_MODE_LASTFRAME, 0.f, check_orientation, occupied, assigned, cur->n, n_matches);
 }
 
+// OrbMatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (orb_matcher.cpp:133-262)
+int orbfe_search_by_bow(orbfe_frame* f, int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid,
+                        int kf_nnodes, const uint32_t* kf_node_ids, const int32_t* kf_node_start, const uint32_t* kf_feat_idx,
+                        int f_nnodes, const uint32_t* f_node_ids, const int32_t* f_node_start, const uint32_t* f_feat_idx,
+                        float nnratio, int check_orientation, int32_t* matched_kf_idx, int* n_matches) {
+  if (!f || !matched_kf_idx || n_kf < 0 || kf_nnodes < 0 || f_nnodes < 0) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
+  if (n_kf && (!kf_desc || !kf_angle || !kf_valid)) return orbfe_fail(ORBFE_ERR_INVALID, "null keyframe array");
+  if ((kf_nnodes && (!kf_node_ids || !kf_node_start || !kf_feat_idx)) || (f_nnodes && (!f_node_ids || !f_node_start || !f_feat_idx)))
+    return orbfe_fail(ORBFE_ERR_INVALID, "null feature-vector array");
+  if (n_matches) *n_matches = 0;
+  for (int i = 0; i < f->n; ++i) matched_kf_idx[i] = -1;
+  // queries in the reference's visiting order: common nodes ascending (the two-iterator walk with
+  // lower_bound, :152-236, is a sorted-set intersection), KeyFrame features in node order
+  std::vector<int> qKf, qSrc, qCnt, qOff;
+  std::vector<float> qAng;
+  int a = 0, b = 0, total = 0;
+  while (a < kf_nnodes && b < f_nnodes) {
+    if (kf_node_ids[a] == f_node_ids[b]) {
+      const int fo = f_node_start[b], fc = f_node_start[b + 1] - fo;
+      for (int k = kf_node_start[a]; k < kf_node_start[a + 1]; ++k) {
+        const int real = (int)kf_feat_idx[k];
+        if (real < 0 || real >= n_kf) return orbfe_fail(ORBFE_ERR_INVALID, "keyframe feature index %d out of range", real);
+        if (!kf_valid[real]) continue;  // no map point / bad map point (:162-168)
+        qKf.push_back(real); qSrc.push_back(fo); qCnt.push_back(fc); qOff.push_back(total); qAng.push_back(kf_angle[real]);
+        total += fc;
+      }
+      ++a; ++b;
+    } else if (kf_node_ids[a] < f_node_ids[b]) ++a;
+    else ++b;
+  }
+  const int nq = (int)qKf.size();
+  if (nq == 0 || f->n == 0) return ORBFE_OK;
+  const int nfi = f_node_start[f_nnodes];
+  for (int k = 0; k < nfi; ++k)
+    if ((int)f_feat_idx[k] < 0 || (int)f_feat_idx[k] >= f->n) return orbfe_fail(ORBFE_ERR_INVALID, "frame feature index out of range");
+  CUDA_TRY(cudaSetDevice(f->device));
+  int rc;
+  if ((rc = ensure_queries(f, std::max(nq, n_kf)))) return rc;
+  if ((rc = ensure_out(f, std::max(f->n, nfi)))) return rc;
+  if ((rc = ensure_cand(f, total + 16))) return rc;
+  cudaStream_t st = f->stream;
+  if (nq > f->jCap) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(regrow(&f->d_jbest, (size_t)nq + 256));
+    CUDA_TRY(regrow(&f->d_jchanged, (size_t)nq + 256 + 16));
+    f->jCap = nq + 256;
+  }
+  if (!f->d_jown) CUDA_TRY(regrow(&f->d_jown, 3 * (size_t)std::max(f->n, 1)));
+  // scratch re-use: d_qDesc <- all keyframe descriptors, d_qMinL <- descriptor index, d_qMaxL <- source offset,
+  // d_out (as unsigned) <- the Frame's feature-vector indices until the finalize kernel overwrites it
+  unsigned* d_featIdx = nullptr;
+  CUDA_TRY(cudaMalloc(&d_featIdx, (size_t)std::max(nfi, 1) * sizeof(unsigned)));
+  auto done = [&](int code) { cudaFree(d_featIdx); return code; };
+  cudaError_t e = cudaMemcpyAsync(f->d_qDesc, kf_desc, (size_t)n_kf * 32, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qMinL, qKf.data(), (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qMaxL, qSrc.data(), (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qOff, qOff.data(), (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qCnt, qCnt.data(), (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qAngle, qAng.data(), (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_featIdx, f_feat_idx, (size_t)nfi * sizeof(unsigned), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->d_cursor, 0, 4 * sizeof(int), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->d_jown, 0x7f, 3 * (size_t)std::max(f->n, 1) * sizeof(int), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->d_jchanged, 0, ((size_t)nq + 16) * sizeof(int), st);
+  if (e != cudaSuccess) return done(orbfe_fail(ORBFE_ERR_CUDA, "SearchByBoW upload failed: %s", cudaGetErrorString(e)));
+  MatchScratch S;
+  S.cand = f->d_cand; S.qOff = f->d_qOff; S.qCnt = f->d_qCnt; S.cursor = f->d_cursor; S.capacity = f->candCap;
+  ResolveArgs A;
+  A.mode = ORBFE_MODE_BOW; A.nQ = nq; A.nKp = f->n; A.nnratio = nnratio; A.checkOri = check_orientation; A.hasObs = nullptr;
+  A.occupiedIn = nullptr; A.qAngle = f->d_qAngle; A.kp = f->d_kp; A.out = f->d_out; A.evBin = f->d_evBin; A.evIdx = f->d_evIdx;
+  A.result = f->d_cursor + 2;
+  JacobiState J;
+  J.best = f->d_jbest; J.own = f->d_jown; J.changed = f->d_jchanged;
+  const int grid = (nq + ORBFE_MATCH_THREADS / 32 - 1) / (ORBFE_MATCH_THREADS / 32);
+  MATCH_LAUNCH(f, k_match_candidates_bow, dim3(grid), dim3(ORBFE_MATCH_THREADS), 0, f->grid(), f->d_qDesc, f->d_qMinL, d_featIdx,
+               f->d_qMaxL, nq, S);
+  int t = 0;
+  for (;;) {
+    for (int k = 0; k < 8 && t <= nq; ++k, ++t) MATCH_LAUNCH(f, k_match_iterate, dim3(grid), dim3(ORBFE_MATCH_THREADS), 0, A, S, J, t);
+    e = cudaMemcpyAsync(f->h_res + 3, f->d_jchanged + (t - 1), sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(orbfe_fail(ORBFE_ERR_CUDA, "SearchByBoW resolve failed: %s", cudaGetErrorString(e)));
+    if (f->h_res[3] == 0 || t > nq) break;
+  }
+  MATCH_LAUNCH(f, k_match_finalize, dim3(1), dim3(1024), 0, A, S, J);
+  e = cudaGetLastError();
+  std::vector<int> assigned((size_t)f->n);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(f->h_res, f->d_cursor, 3 * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(assigned.data(), f->d_out, (size_t)f->n * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return done(orbfe_fail(ORBFE_ERR_CUDA, "SearchByBoW failed: %s", cudaGetErrorString(e)));
+  for (int i = 0; i < f->n; ++i) matched_kf_idx[i] = assigned[i] >= 0 ? qKf[assigned[i]] : -1;  // query -> keyframe feature
+  if (n_matches) *n_matches = f->h_res[2];
+  return done(ORBFE_OK);
+}
+
 }  // extern "C"

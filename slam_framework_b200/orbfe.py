@@ -46,7 +46,7 @@ EXPORTS = [
     "orbfe_debug_candidates", "orbfe_debug_level_keypoints", "orbfe_debug_blurred", "orbfe_stereo_match",
     "orbfe_descriptor_distance", "orbfe_frame_create", "orbfe_frame_destroy", "orbfe_features_in_area",
     "orbfe_search_for_initialization", "orbfe_search_by_projection_mappoints",
-    "orbfe_search_by_projection_lastframe",
+    "orbfe_search_by_projection_lastframe", "orbfe_search_by_bow",
 ]
 
 _libs = {}
@@ -62,6 +62,8 @@ def load(path=None, _test_emulation=False):
             _build.build()
     path = os.path.abspath(path)
     if path in _libs:
+        if b"EMULATED" in _libs[path].orbfe_version() and not _test_emulation:
+            raise OrbfeError("refusing to load the emulated TEST build as the product library")
         return _libs[path]
     try:
         L = C.CDLL(path)
@@ -103,6 +105,7 @@ def load(path=None, _test_emulation=False):
     L.orbfe_search_for_initialization.argtypes = [vp, vp, vp, vp, i, f, i, vp]
     L.orbfe_search_by_projection_mappoints.argtypes = [vp, i] + [vp] * 9 + [i, f, vp, vp]
     L.orbfe_search_by_projection_lastframe.argtypes = [vp, i] + [vp] * 8 + [f, i, i, vp, f, i, vp, vp]
+    L.orbfe_search_by_bow.argtypes = [vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, f, i, vp, vp]
     _libs[path] = L
     return L
 
@@ -401,3 +404,29 @@ class OrbMatcher:
                                                                 _p(a(occupied, np.uint8)), th, int(self.checkOri),
                                                                 _p(assigned), C.byref(n)))
         return n.value, assigned
+
+
+def flatten_feature_vector(fv):
+    """DBoW2::FeatureVector (dict node id -> list of feature indices) -> (ids ascending, starts, indices)"""
+    ids = np.array(sorted(fv), np.uint32)
+    starts = np.zeros(len(ids) + 1, np.int32)
+    idx = []
+    for k, n in enumerate(ids):
+        idx.extend(fv[int(n)])
+        starts[k + 1] = len(idx)
+    return ids, starts, np.array(idx, np.uint32)
+
+
+def SearchByBoW(F, kf_desc, kf_angle, kf_valid, kf_fv, f_fv, nnratio=0.7, checkOri=True):
+    """OrbMatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (orb_matcher.cpp:133-262).  kf_fv / f_fv are
+    the DBoW2 feature vectors as dicts; returns (nmatches, matched_kf_idx[NumKeypoints])."""
+    kd = np.ascontiguousarray(kf_desc, np.uint8)
+    ka = np.ascontiguousarray(kf_angle, np.float32)
+    kv = np.ascontiguousarray(kf_valid, np.uint8)
+    ki, ks, kx = flatten_feature_vector(kf_fv)
+    fi, fs, fx = flatten_feature_vector(f_fv)
+    out = np.zeros(len(F.kps), np.int32)
+    n = C.c_int()
+    _check(F.L, F.L.orbfe_search_by_bow(F.h, len(kd), _p(kd), _p(ka), _p(kv), len(ki), _p(ki), _p(ks), _p(kx), len(fi), _p(fi),
+                                        _p(fs), _p(fx), nnratio, int(checkOri), _p(out), C.byref(n)))
+    return n.value, out

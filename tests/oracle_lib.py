@@ -62,6 +62,7 @@ def lib():
         L.orc_search_by_projection_mappoints.argtypes = [vp, C.c_int] + [vp] * 9 + [C.c_int, C.c_float, vp]
         L.orc_search_by_projection_lastframe.argtypes = [vp, C.c_int] + [vp] * 8 + [C.c_float, C.c_int, C.c_int, vp,
                                                                                  C.c_float, C.c_int, vp]
+        L.orc_search_by_bow.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, vp]
         L.orc_bench_stereo_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                              C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
         L.orc_bench_stereo_batch.restype = C.c_double
@@ -244,3 +245,15 @@ def search_by_projection_lastframe(cur, valid, u, v, invzc, octave, angle, mp_de
         _p(a(has_obs, np.uint8)), bf, int(forward), int(backward), _p(a(occupied, np.uint8)), th, int(check_ori),
         _p(assigned))
     return n, assigned
+
+
+def search_by_bow(f, kf_desc, kf_angle, kf_valid, kf_fv, f_fv, nnratio=0.7, check_ori=True):
+    from slam_framework_b200.orbfe import flatten_feature_vector
+    kd = np.ascontiguousarray(kf_desc, np.uint8); ka = np.ascontiguousarray(kf_angle, np.float32)
+    kv = np.ascontiguousarray(kf_valid, np.uint8)
+    ki, ks, kx = flatten_feature_vector(kf_fv)
+    fi, fs, fx = flatten_feature_vector(f_fv)
+    out = np.zeros(len(f.kps), np.int32)
+    n = lib().orc_search_by_bow(f.h, len(kd), _p(kd), _p(ka), _p(kv), len(ki), _p(ki), _p(ks), _p(kx), len(fi), _p(fi), _p(fs),
+                                _p(fx), nnratio, int(check_ori), _p(out))
+    return n, out

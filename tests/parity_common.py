@@ -196,3 +196,32 @@ def check_search_by_projection_lastframe(lib, kps, desc, scale, w, h, seed=0, u_
             assert np.array_equal(asg, oasg)
             tot += m
     return tot
+
+
+def synth_feature_vector(desc, rng, n_nodes=97, noise=0.03):
+    """stand-in for DBoW2::FeatureVector (the vocabulary file is a missing blob): node id = a hash of the first
+    descriptor bytes, so similar descriptors mostly share a node; a few features are moved to random nodes"""
+    node = (desc[:, 0].astype(np.int64) * 7 + (desc[:, 1] >> 5)) % n_nodes
+    flip = rng.uniform(0, 1, len(desc)) < noise
+    node[flip] = rng.integers(0, n_nodes, flip.sum())
+    fv = {}
+    for i in rng.permutation(len(desc)) if False else range(len(desc)):
+        fv.setdefault(int(node[i]) * 3 + 1, []).append(i)  # sparse, unsorted-looking ids
+    return fv
+
+
+def check_search_by_bow(lib, kps_f, desc_f, kps_kf, desc_kf, scale, w, h, seed=0, nnratio=0.7):
+    """SearchByBoW(KeyFrame, Frame): the keyframe side = another frame's features, ~70 % with map points"""
+    rng = np.random.default_rng(seed)
+    F, OF = make_frames(kps_f, desc_f, scale, w, h, lib)
+    fv_f = synth_feature_vector(desc_f, rng)
+    fv_kf = synth_feature_vector(desc_kf, rng)
+    valid = (rng.uniform(0, 1, len(kps_kf)) < 0.7).astype(np.uint8)
+    tot = 0
+    for ori in (True, False):
+        n, m = orbfe.SearchByBoW(F, desc_kf, kps_kf["angle"], valid, fv_kf, fv_f, nnratio, ori)
+        on, om = O.search_by_bow(OF, desc_kf, kps_kf["angle"], valid, fv_kf, fv_f, nnratio, ori)
+        assert n == on, f"SearchByBoW ori={ori}: {n} vs oracle {on}"
+        assert np.array_equal(m, om)
+        tot += n
+    return tot

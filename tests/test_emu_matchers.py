@@ -58,3 +58,12 @@ def test_empty_frames(emu):
     assert len(F.GetFeaturesInArea(10, 10, 5)) == 0
     n, m, _ = orbfe.OrbMatcher(0.9).SearchForInitialization(F, F, np.zeros((0, 2), np.float32), 100)
     assert n == 0 and len(m) == 0
+
+
+def test_search_by_bow(emu):
+    a, b = synth.shifted_frame(5, 200, 640, dx=6, dy=3)
+    ka, da = oracle_extract(a, 1200)
+    kb, db = oracle_extract(b, 1200)
+    scale = O.Extractor(1200).tables()["scale"]
+    assert P.check_search_by_bow(emu, kb, db, ka, da, scale, 640, 200, seed=3) > 60
+    assert P.check_search_by_bow(emu, ka, da, ka, da, scale, 640, 200, seed=4, nnratio=0.75) > 300  # frame vs itself

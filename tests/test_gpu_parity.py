@@ -192,3 +192,15 @@ def test_colour_frames_converted_on_device(lib, channels, rgb):
     ok, od = O.Extractor().extract(ref)
     P.assert_kps_equal(b["kps"][0, :b["n"][0]], ok)
     assert np.array_equal(b["desc"][0, :b["n"][0]], od)
+
+
+def test_n1_search_by_bow_keyframe_frame(lib):
+    """SearchByBoW(KeyFrame, Frame) on the same kernels (TrackReferenceKeyFrame, tracker.cpp:657-694)"""
+    a, b = synth.shifted_frame(41, dx=6, dy=3)
+    ex = gpu_extract(lib)
+    ka, da = ex(a, 2000)
+    kb, db = ex(b, 2000)
+    import oracle_lib as O
+    scale = O.Extractor().tables()["scale"]
+    assert P.check_search_by_bow(lib, kb, db, ka, da, scale, 1241, 376, seed=3) > 200
+    assert P.check_search_by_bow(lib, ka, da, ka, da, scale, 1241, 376, seed=4, nnratio=0.75) > 1000
