@@ -208,6 +208,65 @@ int orbfe_search_by_bow(orbfe_frame* f, int n_kf, const uint8_t* kf_desc, const 
                         const int32_t* f_node_start, const uint32_t* f_feat_idx, float nnratio,
                         int check_orientation, int32_t* matched_kf_idx, int* n_matches);
 
+/* ---- the remaining OrbMatcher searches.  Convention as above: the cv::Mat geometry of each routine
+ * (projection with Rcw/tcw or the Sim3, depth / distance-invariance / viewing-angle gates, MapPoint::PredictScale)
+ * stays in the caller (include/orbfe_shim.hpp); valid[i] = "map point i passed every gate that precedes
+ * GetFeaturesInArea", (u, v) its projection and pred_level its nPredictedLevel. ------------------------------- */
+
+/* OrbMatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) (orb_matcher.cpp:384-497).
+ * matched_in[k] = vpMatched[k] != NULL on entry; matched[k] (out) = index iMP of the point written to vpMatched[k]
+ * by this call, else -1. */
+int orbfe_search_by_projection_sim3(orbfe_frame* kf, int n_mp, const uint8_t* valid, const float* u, const float* v,
+                                    const int32_t* pred_level, const uint8_t* mp_desc, const uint8_t* matched_in, int th,
+                                    int32_t* matched, int* n_matches);
+
+/* OrbMatcher::SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist) (orb_matcher.cpp:1455-1582).
+ * Per KeyFrame feature i: valid = map point && !isBad() && !sAlreadyFound.count() && distance-invariance gate
+ * (:1505); the image-bound gate (:1490-1495) is applied here.  kf_angle = pKF->undistorted_keypoints[i].angle.
+ * occupied[k] = CurrentFrame.GetMapPoint(k) != NULL.  assigned[k] (out) = i or -1. */
+int orbfe_search_by_projection_keyframe(orbfe_frame* cur, int n_kf, const uint8_t* valid, const float* u, const float* v,
+                                        const int32_t* pred_level, const float* kf_angle, const uint8_t* mp_desc,
+                                        const uint8_t* occupied, float th, int orb_dist, int check_orientation,
+                                        int32_t* assigned, int* n_matches);
+
+/* OrbMatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (orb_matcher.cpp:804-954), the search part: ur = u - bf*invz
+ * (:849); best_idx[i] (out) = keypoint with bestDist <= TH_LOW for map point i, else -1.  The caller then walks i in
+ * order and applies Replace / AddObservation / AddMapPoint (:933-949), re-checking isBad()/IsInKeyFrame (:828) first
+ * (the graph edits never feed back into the search, which reads only keypoints and descriptors). */
+int orbfe_fuse(orbfe_frame* kf, int n_mp, const uint8_t* valid, const float* u, const float* v, const float* ur,
+               const int32_t* pred_level, const uint8_t* mp_desc, float th, int32_t* best_idx, int* n_fused);
+/* OrbMatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) (orb_matcher.cpp:956-1079), the search part */
+int orbfe_fuse_sim3(orbfe_frame* kf, int n_mp, const uint8_t* valid, const float* u, const float* v,
+                    const int32_t* pred_level, const uint8_t* mp_desc, float th, int32_t* best_idx, int* n_fused);
+
+/* OrbMatcher::SearchBySim3 (orb_matcher.cpp:1081-1310).  Side 1 = the NumKeypoints(kf1) map-point slots of KF1
+ * projected into KF2 (valid1 = map point && !vbAlreadyMatched1 && !isBad() && gates :1147-1167), side 2 likewise
+ * into KF1.  match12[i1] (out) = idx2 when the two searches agree (:1291-1307), else -1. */
+int orbfe_search_by_sim3(orbfe_frame* kf1, orbfe_frame* kf2, const uint8_t* valid1, const float* u1, const float* v1,
+                         const int32_t* pred_level1, const uint8_t* mp_desc1, const uint8_t* valid2, const float* u2,
+                         const float* v2, const int32_t* pred_level2, const uint8_t* mp_desc2, float th, int32_t* match12,
+                         int* n_found);
+
+/* OrbMatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (orb_matcher.cpp:499-632).  kf2 = the second
+ * KeyFrame's handle; side 1 arrays as in orbfe_search_by_bow; valid1/valid2 = map point && !isBad().
+ * matches12[i1] (out, n1 entries) = idx2 whose map point vpMatches12[i1] receives, else -1. */
+int orbfe_search_by_bow_keyframes(orbfe_frame* kf2, int n1, const uint8_t* desc1, const float* angle1, const uint8_t* valid1,
+                                  const uint8_t* valid2, int nnodes1, const uint32_t* node_ids1, const int32_t* node_start1,
+                                  const uint32_t* feat_idx1, int nnodes2, const uint32_t* node_ids2, const int32_t* node_start2,
+                                  const uint32_t* feat_idx2, float nnratio, int check_orientation, int32_t* matches12,
+                                  int* n_matches);
+
+/* OrbMatcher::SearchForTriangulation (orb_matcher.cpp:634-802).  valid1/valid2 = the feature has NO map point;
+ * stereo1[i] = pKF1->right_coords[i] >= 0 (side 2 reads the handle's u_right); F12 = 9 floats row-major; (ex, ey) =
+ * the epipole of :643-649.  matches12[i1] (out) = idx2 or -1; vMatchedPairs = the pairs (i1, matches12[i1] >= 0) in
+ * ascending i1 (:794-799). */
+int orbfe_search_for_triangulation(orbfe_frame* kf2, int n1, const orbfe_keypoint* kps1_un, const uint8_t* desc1,
+                                   const uint8_t* valid1, const uint8_t* stereo1, const uint8_t* valid2, int nnodes1,
+                                   const uint32_t* node_ids1, const int32_t* node_start1, const uint32_t* feat_idx1,
+                                   int nnodes2, const uint32_t* node_ids2, const int32_t* node_start2,
+                                   const uint32_t* feat_idx2, const float* F12, float ex, float ey, int only_stereo,
+                                   int check_orientation, int32_t* matches12, int* n_matches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,10 @@
 //                                       bodies of the OrbMatcher routines, orb_matcher.cpp:264-382, 13-111,
 //                                       1312-1453 (templates over the reference's Frame / MapPoint types,
 //                                       using only their public accessors, src/data/frame.h:104-190)
+//   orbfe::SearchByBoW x2 / SearchForTriangulation / SearchByProjection(KeyFrame*, Scw, ...) /
+//   orbfe::SearchByProjectionKeyFrame / Fuse x2 / SearchBySim3
+//                                       the other OrbMatcher routines, orb_matcher.cpp:133-262, 499-632,
+//                                       634-802, 384-497, 1455-1582, 804-954, 956-1079, 1081-1310
 //
 // There is no CPU fallback: a failing C-ABI call throws std::runtime_error with orbfe_last_error().
 #ifndef ORBFE_SHIM_HPP_
@@ -31,6 +35,8 @@
 
 #include <cmath>
 #include <stdexcept>
+#include <type_traits>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -262,6 +268,272 @@ inline std::vector<int32_t> DescriptorDistances(const cv::Mat& a, const cv::Mat&
   std::vector<int32_t> d((size_t)a.rows);
   check(orbfe_descriptor_distance(device, desc_rows(a, ta), desc_rows(b, tb), a.rows, d.data()), "orbfe_descriptor_distance");
   return d;
+}
+
+// ---- the remaining OrbMatcher routines -------------------------------------------------------------
+// Pattern: the adapter gathers what the routine reads from the reference's objects, the caller supplies a `gate`
+// functor that runs the reference's OWN cv::Mat geometry for map point i (projection, depth sign, IsInImage,
+// distance invariance, viewing angle, PredictScale -- e.g. orb_matcher.cpp:414-451) and returns false where the
+// reference `continue`s before GetFeaturesInArea; the search runs on the GPU; the adapter applies the side effects in
+// the reference's order.  KeyFrame's image bounds are private statics (keyframe.h:181-184): pass them in.
+
+template <class KeyFrameT>
+class DeviceKeyFrame {
+ public:
+  DeviceKeyFrame(const KeyFrameT& kf, float minX, float maxX, float minY, float maxY, int device = 0) : h_(nullptr) {
+    std::vector<uint8_t> tmp;
+    check(orbfe_frame_create(device, (int)kf.undistorted_keypoints.size(), as_pod(kf.undistorted_keypoints),
+                             desc_rows(kf.descriptors, tmp), kf.right_coords.empty() ? nullptr : kf.right_coords.data(), minX,
+                             maxX, minY, maxY, (int)kf.scale_factors.size(), kf.scale_factors.data(), &h_),
+          "orbfe_frame_create");
+  }
+  ~DeviceKeyFrame() { orbfe_frame_destroy(h_); }
+  DeviceKeyFrame(const DeviceKeyFrame&) = delete;
+  DeviceKeyFrame& operator=(const DeviceKeyFrame&) = delete;
+  orbfe_frame* get() const { return h_; }
+ private:
+  orbfe_frame* h_;
+};
+struct ImageBounds { float minX, maxX, minY, maxY; };
+
+// DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>) flattened for the C ABI
+struct FlatFeatureVector {
+  std::vector<uint32_t> ids, idx;
+  std::vector<int32_t> start;
+  template <class FeatureVectorT>
+  explicit FlatFeatureVector(const FeatureVectorT& fv) {
+    start.push_back(0);
+    for (typename FeatureVectorT::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+      ids.push_back((uint32_t)it->first);
+      for (size_t k = 0; k < it->second.size(); ++k) idx.push_back((uint32_t)it->second[k]);
+      start.push_back((int32_t)idx.size());
+    }
+  }
+  int n() const { return (int)ids.size(); }
+};
+
+// per map point: gate result, projection, predicted level, representative descriptor
+struct ProjectedPoints {
+  std::vector<uint8_t> valid, desc;
+  std::vector<float> u, v, ur;
+  std::vector<int32_t> level;
+  explicit ProjectedPoints(size_t n) : valid(n, 0), desc(n * 32, 0), u(n, 0.f), v(n, 0.f), ur(n, 0.f), level(n, 0) {}
+  template <class MapPointT>
+  void take_descriptor(size_t i, MapPointT* p) {
+    const cv::Mat d = p->GetDescriptor();
+    std::memcpy(desc.data() + i * 32, d.data, 32);
+  }
+};
+
+// Body of OrbMatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (orb_matcher.cpp:133-262)
+template <class KeyFrameT, class FrameT, class MapPointT>
+int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches, float mfNNratio, bool mbCheckOrientation) {
+  const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
+  const int nkf = (int)vpMapPointsKF.size(), nf = F.NumKeypoints();
+  vpMapPointMatches.assign((size_t)nf, static_cast<MapPointT*>(nullptr));
+  std::vector<uint8_t> valid(nkf, 0), tmp;
+  std::vector<float> ang(nkf, 0.f);
+  for (int i = 0; i < nkf; ++i) {
+    valid[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();  // :162-168
+    ang[i] = pKF->undistorted_keypoints[i].angle;
+  }
+  const FlatFeatureVector fk(pKF->feature_vec), ff(F.GetFeatureVector());
+  DeviceFrame<FrameT> dF(F);
+  std::vector<int32_t> m((size_t)nf, -1);
+  int n = 0;
+  check(orbfe_search_by_bow(dF.get(), nkf, desc_rows(pKF->descriptors, tmp), ang.data(), valid.data(), fk.n(), fk.ids.data(),
+                            fk.start.data(), fk.idx.data(), ff.n(), ff.ids.data(), ff.start.data(), ff.idx.data(), mfNNratio,
+                            mbCheckOrientation ? 1 : 0, m.data(), &n),
+        "orbfe_search_by_bow");
+  for (int k = 0; k < nf; ++k)
+    if (m[k] >= 0) vpMapPointMatches[k] = vpMapPointsKF[m[k]];
+  return n;
+}
+
+// Body of OrbMatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (orb_matcher.cpp:499-632)
+template <class KeyFrameT, class MapPointT>
+int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, const ImageBounds& b, float mfNNratio,
+                bool mbCheckOrientation) {
+  const std::vector<MapPointT*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
+  const int n1 = (int)mp1.size(), n2 = (int)mp2.size();
+  vpMatches12.assign((size_t)n1, static_cast<MapPointT*>(nullptr));
+  std::vector<uint8_t> v1(n1, 0), v2(n2, 0), tmp;
+  std::vector<float> ang(n1, 0.f);
+  for (int i = 0; i < n1; ++i) { v1[i] = mp1[i] && !mp1[i]->isBad(); ang[i] = pKF1->undistorted_keypoints[i].angle; }
+  for (int i = 0; i < n2; ++i) v2[i] = mp2[i] && !mp2[i]->isBad();
+  const FlatFeatureVector f1(pKF1->feature_vec), f2(pKF2->feature_vec);
+  DeviceKeyFrame<KeyFrameT> d2(*pKF2, b.minX, b.maxX, b.minY, b.maxY);
+  std::vector<int32_t> m((size_t)n1, -1);
+  int n = 0;
+  check(orbfe_search_by_bow_keyframes(d2.get(), n1, desc_rows(pKF1->descriptors, tmp), ang.data(), v1.data(), v2.data(), f1.n(),
+                                      f1.ids.data(), f1.start.data(), f1.idx.data(), f2.n(), f2.ids.data(), f2.start.data(),
+                                      f2.idx.data(), mfNNratio, mbCheckOrientation ? 1 : 0, m.data(), &n),
+        "orbfe_search_by_bow_keyframes");
+  for (int i = 0; i < n1; ++i)
+    if (m[i] >= 0) vpMatches12[i] = mp2[m[i]];
+  return n;
+}
+
+// Body of OrbMatcher::SearchForTriangulation (orb_matcher.cpp:634-802).  F12 = the 9 floats of the fundamental matrix
+// (row-major), (ex, ey) = the epipole computed at :643-649 with the reference's cv::Mat arithmetic.
+template <class KeyFrameT>
+int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, const float F12[9], float ex, float ey,
+                           std::vector<std::pair<size_t, size_t> >& vMatchedPairs, bool bOnlyStereo, const ImageBounds& b,
+                           bool mbCheckOrientation) {
+  const int n1 = (int)pKF1->undistorted_keypoints.size(), n2 = (int)pKF2->undistorted_keypoints.size();
+  std::vector<uint8_t> v1(n1, 0), s1(n1, 0), v2(n2, 0), tmp;
+  for (int i = 0; i < n1; ++i) { v1[i] = !pKF1->GetMapPoint(i); s1[i] = pKF1->right_coords[i] >= 0; }  // :678-684
+  for (int i = 0; i < n2; ++i) v2[i] = !pKF2->GetMapPoint(i);                                           // :701-705
+  const FlatFeatureVector f1(pKF1->feature_vec), f2(pKF2->feature_vec);
+  DeviceKeyFrame<KeyFrameT> d2(*pKF2, b.minX, b.maxX, b.minY, b.maxY);
+  std::vector<int32_t> m((size_t)n1, -1);
+  int n = 0;
+  check(orbfe_search_for_triangulation(d2.get(), n1, as_pod(pKF1->undistorted_keypoints), desc_rows(pKF1->descriptors, tmp),
+                                       v1.data(), s1.data(), v2.data(), f1.n(), f1.ids.data(), f1.start.data(), f1.idx.data(),
+                                       f2.n(), f2.ids.data(), f2.start.data(), f2.idx.data(), F12, ex, ey, bOnlyStereo ? 1 : 0,
+                                       mbCheckOrientation ? 1 : 0, m.data(), &n),
+        "orbfe_search_for_triangulation");
+  vMatchedPairs.clear();
+  vMatchedPairs.reserve((size_t)(n > 0 ? n : 0));
+  for (int i = 0; i < n1; ++i)
+    if (m[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)m[i]));  // :794-799
+  return n;
+}
+
+// Body of OrbMatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) (orb_matcher.cpp:384-497).
+// gate(i, u, v, level): the reference's :408-451 for vpPoints[i] (incl. isBad / spAlreadyFound).
+template <class KeyFrameT, class MapPointT, class GateFn>
+int SearchByProjection(KeyFrameT* pKF, const std::vector<MapPointT*>& vpPoints, std::vector<MapPointT*>& vpMatched, int th,
+                       const ImageBounds& b, GateFn gate) {
+  const size_t n = vpPoints.size(), nkp = vpMatched.size();
+  ProjectedPoints P(n);
+  for (size_t i = 0; i < n; ++i)
+    if (gate(i, P.u[i], P.v[i], P.level[i])) { P.valid[i] = 1; P.take_descriptor(i, vpPoints[i]); }
+  std::vector<uint8_t> in(nkp, 0);
+  for (size_t k = 0; k < nkp; ++k) in[k] = vpMatched[k] != nullptr;
+  DeviceKeyFrame<KeyFrameT> d(*pKF, b.minX, b.maxX, b.minY, b.maxY);
+  std::vector<int32_t> m(nkp, -1);
+  int nm = 0;
+  check(orbfe_search_by_projection_sim3(d.get(), (int)n, P.valid.data(), P.u.data(), P.v.data(), P.level.data(), P.desc.data(),
+                                        in.data(), th, m.data(), &nm),
+        "orbfe_search_by_projection_sim3");
+  for (size_t k = 0; k < nkp; ++k)
+    if (m[k] >= 0) vpMatched[k] = vpPoints[m[k]];  // :490
+  return nm;
+}
+
+// Body of OrbMatcher::SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist) (orb_matcher.cpp:1455-1582).
+// gate(i, u, v, level): :1473-1508 for pKF's map point i except the image-bound test (done by the library).
+template <class FrameT, class KeyFrameT, class GateFn>
+int SearchByProjectionKeyFrame(FrameT& CurrentFrame, KeyFrameT* pKF, float th, int ORBdist, bool mbCheckOrientation, GateFn gate) {
+  typedef typename std::remove_reference<decltype(*pKF->GetMapPointMatches()[0])>::type MapPointT;
+  const std::vector<MapPointT*> vpMPs = pKF->GetMapPointMatches();
+  const size_t n = vpMPs.size();
+  const int nkp = CurrentFrame.NumKeypoints();
+  ProjectedPoints P(n);
+  std::vector<float> ang(n, 0.f);
+  for (size_t i = 0; i < n; ++i)
+    if (gate(i, P.u[i], P.v[i], P.level[i])) {
+      P.valid[i] = 1; P.take_descriptor(i, vpMPs[i]); ang[i] = pKF->undistorted_keypoints[i].angle;
+    }
+  std::vector<uint8_t> occ((size_t)nkp, 0);
+  for (int k = 0; k < nkp; ++k) occ[k] = CurrentFrame.GetMapPoint(k) != nullptr;  // :1526
+  DeviceFrame<FrameT> d(CurrentFrame);
+  std::vector<int32_t> a((size_t)nkp, -1);
+  int nm = 0;
+  check(orbfe_search_by_projection_keyframe(d.get(), (int)n, P.valid.data(), P.u.data(), P.v.data(), P.level.data(), ang.data(),
+                                            P.desc.data(), occ.data(), th, ORBdist, mbCheckOrientation ? 1 : 0, a.data(), &nm),
+        "orbfe_search_by_projection_keyframe");
+  for (int k = 0; k < nkp; ++k)
+    if (a[k] >= 0) CurrentFrame.SetMapPoint(k, vpMPs[a[k]]);  // :1543 (rotation-rejected ones come back as -1, :1574)
+  return nm;
+}
+
+// Body of OrbMatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (orb_matcher.cpp:804-954).
+// gate(i, u, v, ur, level): :823-866 for vpMapPoints[i].  The graph edits of :933-949 are applied here in the
+// reference's order; a point an earlier edit made bad or put into pKF is skipped exactly as :828 would.
+template <class KeyFrameT, class MapPointT, class GateFn>
+int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, float th, const ImageBounds& b, GateFn gate) {
+  const size_t n = vpMapPoints.size();
+  ProjectedPoints P(n);
+  for (size_t i = 0; i < n; ++i)
+    if (vpMapPoints[i] && gate(i, P.u[i], P.v[i], P.ur[i], P.level[i])) { P.valid[i] = 1; P.take_descriptor(i, vpMapPoints[i]); }
+  DeviceKeyFrame<KeyFrameT> d(*pKF, b.minX, b.maxX, b.minY, b.maxY);
+  std::vector<int32_t> best(n, -1);
+  check(orbfe_fuse(d.get(), (int)n, P.valid.data(), P.u.data(), P.v.data(), P.ur.data(), P.level.data(), P.desc.data(), th,
+                   best.data(), nullptr),
+        "orbfe_fuse");
+  int nFused = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (best[i] < 0) continue;
+    MapPointT* pMP = vpMapPoints[i];
+    if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;  // :828, re-evaluated after the earlier edits
+    MapPointT* pMPinKF = pKF->GetMapPoint(best[i]);
+    if (pMPinKF) {
+      if (!pMPinKF->isBad()) {
+        if (pMPinKF->NumObservations() > pMP->NumObservations()) pMP->Replace(pMPinKF);
+        else pMPinKF->Replace(pMP);
+      }
+    } else {
+      pMP->AddObservation(pKF, best[i]);
+      pKF->AddMapPoint(pMP, best[i]);
+    }
+    nFused++;
+  }
+  return nFused;
+}
+
+// Body of OrbMatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) (orb_matcher.cpp:956-1079).
+// gate(i, u, v, level): :981-1025 for vpPoints[i] (incl. isBad / spAlreadyFound).
+template <class KeyFrameT, class MapPointT, class GateFn>
+int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpPoints, float th, std::vector<MapPointT*>& vpReplacePoint,
+         const ImageBounds& b, GateFn gate) {
+  const size_t n = vpPoints.size();
+  ProjectedPoints P(n);
+  for (size_t i = 0; i < n; ++i)
+    if (gate(i, P.u[i], P.v[i], P.level[i])) { P.valid[i] = 1; P.take_descriptor(i, vpPoints[i]); }
+  DeviceKeyFrame<KeyFrameT> d(*pKF, b.minX, b.maxX, b.minY, b.maxY);
+  std::vector<int32_t> best(n, -1);
+  check(orbfe_fuse_sim3(d.get(), (int)n, P.valid.data(), P.u.data(), P.v.data(), P.level.data(), P.desc.data(), th, best.data(),
+                        nullptr),
+        "orbfe_fuse_sim3");
+  int nFused = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (best[i] < 0) continue;
+    MapPointT* pMP = vpPoints[i];
+    MapPointT* pMPinKF = pKF->GetMapPoint(best[i]);
+    if (pMPinKF) {
+      if (!pMPinKF->isBad()) vpReplacePoint[i] = pMPinKF;
+    } else {
+      pMP->AddObservation(pKF, best[i]);
+      pKF->AddMapPoint(pMP, best[i]);
+    }
+    nFused++;
+  }
+  return nFused;
+}
+
+// Body of OrbMatcher::SearchBySim3 (orb_matcher.cpp:1081-1310).  gate1(i1, u, v, level): :1134-1170 (KF1's point
+// into KF2, incl. vbAlreadyMatched1); gate2(i2, ...): :1214-1250.
+template <class KeyFrameT, class MapPointT, class Gate1, class Gate2>
+int SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, float th, const ImageBounds& b,
+                 Gate1 gate1, Gate2 gate2) {
+  const std::vector<MapPointT*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
+  const size_t N1 = mp1.size(), N2 = mp2.size();
+  ProjectedPoints P1(N1), P2(N2);
+  for (size_t i = 0; i < N1; ++i)
+    if (mp1[i] && gate1(i, P1.u[i], P1.v[i], P1.level[i])) { P1.valid[i] = 1; P1.take_descriptor(i, mp1[i]); }
+  for (size_t i = 0; i < N2; ++i)
+    if (mp2[i] && gate2(i, P2.u[i], P2.v[i], P2.level[i])) { P2.valid[i] = 1; P2.take_descriptor(i, mp2[i]); }
+  DeviceKeyFrame<KeyFrameT> d1(*pKF1, b.minX, b.maxX, b.minY, b.maxY), d2(*pKF2, b.minX, b.maxX, b.minY, b.maxY);
+  std::vector<int32_t> m(N1, -1);
+  int nFound = 0;
+  check(orbfe_search_by_sim3(d1.get(), d2.get(), P1.valid.data(), P1.u.data(), P1.v.data(), P1.level.data(), P1.desc.data(),
+                             P2.valid.data(), P2.u.data(), P2.v.data(), P2.level.data(), P2.desc.data(), th, m.data(), &nFound),
+        "orbfe_search_by_sim3");
+  for (size_t i = 0; i < N1; ++i)
+    if (m[i] >= 0) vpMatches12[i] = mp2[m[i]];  // :1303
+  return nFound;
 }
 
 }  // namespace orbfe

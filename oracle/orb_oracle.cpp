@@ -806,6 +806,21 @@ void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, in
 const int HISTO_LENGTH = 30;
 }  // namespace
 
+namespace {
+struct FV { int n; const uint32_t* ids; const int* start; const uint32_t* idx; };
+// the two-iterator walk over the common vocabulary nodes (orb_matcher.cpp:152-236, :527-609, :670-768);
+// lower_bound on a sorted map == advance until >=
+template <class Fn>
+void for_common_nodes(const FV& A, const FV& B, Fn fn) {
+  int a = 0, b = 0;
+  while (a < A.n && b < B.n) {
+    if (A.ids[a] == B.ids[b]) { fn(a, b); ++a; ++b; }
+    else if (A.ids[a] < B.ids[b]) ++a;
+    else ++b;
+  }
+}
+}  // namespace
+
 extern "C" {
 
 orc_frame* orc_frame_create(int n, const orc_keypoint* kps, const uint8_t* desc, const float* uR, float minX,
@@ -1050,6 +1065,284 @@ int orc_search_by_bow(const orc_frame* F, int nKF, const uint8_t* kfDesc, const 
     for (int i = 0; i < HISTO_LENGTH; i++) {
       if (i == ind1 || i == ind2 || i == ind3) continue;
       for (int idx : rotHist[i]) { matchedKf[idx] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
+
+
+// ---- the remaining OrbMatcher searches.  As in include/orbfe.h the cv::Mat geometry that precedes
+// GetFeaturesInArea is the caller's: valid[i] says the map point passed those gates, (u, v) is its projection. ----
+
+
+// OrbMatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (orb_matcher.cpp:384-497)
+int orc_search_by_projection_sim3(const orc_frame* KF, int nMP, const uint8_t* valid, const float* us, const float* vs,
+                                  const int* predLevel, const uint8_t* mpDesc, const uint8_t* matchedIn, int th, int* matched) {
+  const int TH_LOW = 50;
+  std::vector<uint8_t> vpMatched(matchedIn, matchedIn + KF->n);
+  for (int i = 0; i < KF->n; ++i) matched[i] = -1;
+  int nmatches = 0;
+  for (int iMP = 0; iMP < nMP; iMP++) {
+    if (!valid[iMP]) continue;                                 // :411-449
+    const int nPredictedLevel = predLevel[iMP];
+    const float radius = th * KF->scale[nPredictedLevel];      // :454
+    const std::vector<size_t> vIndices = features_in_area(KF, us[iMP], vs[iMP], radius, -1, -1);
+    if (vIndices.empty()) continue;
+    const uint8_t* dMP = mpDesc + (size_t)iMP * 32;
+    int bestDist = 256, bestIdx = -1;
+    for (size_t idx : vIndices) {
+      if (vpMatched[idx]) continue;                            // :469
+      const int kpLevel = KF->kps[idx].octave;
+      if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+      const int dist = descriptor_distance(dMP, KF->desc.data() + idx * 32);
+      if (dist < bestDist) { bestDist = dist; bestIdx = (int)idx; }
+    }
+    if (bestDist <= TH_LOW) { vpMatched[bestIdx] = 1; matched[bestIdx] = iMP; nmatches++; }
+  }
+  return nmatches;
+}
+
+// OrbMatcher::SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist) (orb_matcher.cpp:1455-1582)
+int orc_search_by_projection_keyframe(const orc_frame* C, int nKF, const uint8_t* valid, const float* us, const float* vs,
+                                      const int* predLevel, const float* kfAngle, const uint8_t* mpDesc,
+                                      const uint8_t* occupied, float th, int ORBdist, int checkOri, int* assigned) {
+  int nmatches = 0;
+  std::vector<uint8_t> hasMP(occupied, occupied + C->n);
+  for (int i = 0; i < C->n; ++i) assigned[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  for (int i = 0; i < nKF; i++) {
+    if (!valid[i]) continue;
+    const float u = us[i], v = vs[i];
+    if (u < C->minX || u > C->maxX) continue;                  // :1490-1495
+    if (v < C->minY || v > C->maxY) continue;
+    const int nPredictedLevel = predLevel[i];
+    const float radius = th * C->scale[nPredictedLevel];       // :1511
+    const std::vector<size_t> vIndices2 = features_in_area(C, u, v, radius, nPredictedLevel - 1, nPredictedLevel + 1);
+    if (vIndices2.empty()) continue;
+    const uint8_t* dMP = mpDesc + (size_t)i * 32;
+    int bestDist = 256, bestIdx2 = -1;
+    for (size_t i2 : vIndices2) {
+      if (hasMP[i2]) continue;                                 // :1526
+      const int dist = descriptor_distance(dMP, C->desc.data() + i2 * 32);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = (int)i2; }
+    }
+    if (bestDist <= ORBdist) {
+      hasMP[bestIdx2] = 1; assigned[bestIdx2] = i; ++nmatches;
+      if (checkOri) {
+        float rot = kfAngle[i] - C->kps[bestIdx2].angle;
+        if (rot < 0.0) rot += 360.0f;
+        int bin = (int)std::round(rot * factor);
+        if (bin == HISTO_LENGTH) bin = 0;
+        rotHist[bin].push_back(bestIdx2);
+      }
+    }
+  }
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++)
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int idx : rotHist[i]) { assigned[idx] = -1; --nmatches; }
+  }
+  return nmatches;
+}
+
+// the scan of OrbMatcher::Fuse(KeyFrame*, vpMapPoints, th) (orb_matcher.cpp:866-931; ur != NULL) and of
+// Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) (:1025-1061; ur == NULL): best keypoint per map point
+int orc_fuse(const orc_frame* KF, int nMP, const uint8_t* valid, const float* us, const float* vs, const float* urs,
+             const int* predLevel, const uint8_t* mpDesc, float th, int* bestIdxOut) {
+  const int TH_LOW = 50;
+  int nFused = 0;
+  for (int i = 0; i < nMP; i++) {
+    bestIdxOut[i] = -1;
+    if (!valid[i]) continue;
+    const float u = us[i], v = vs[i];
+    const int nPredictedLevel = predLevel[i];
+    const float radius = th * KF->scale[nPredictedLevel];
+    const std::vector<size_t> vIndices = features_in_area(KF, u, v, radius, -1, -1);
+    if (vIndices.empty()) continue;
+    const uint8_t* dMP = mpDesc + (size_t)i * 32;
+    int bestDist = urs ? 256 : INT_MAX, bestIdx = -1;
+    for (size_t idx : vIndices) {
+      const KP& kp = KF->kps[idx];
+      const int kpLevel = kp.octave;
+      if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+      if (urs) {
+        const float invSigma2 = 1.0f / (kpLevel == 0 ? 1.0f : KF->scale[kpLevel] * KF->scale[kpLevel]);  // orb_extractor.cpp:363,372
+        if (KF->uR[idx] >= 0) {  // reprojection error in stereo (:893-906)
+          const float ex = u - kp.x, ey = v - kp.y, er = urs[i] - KF->uR[idx];
+          const float e2 = ex * ex + ey * ey + er * er;
+          if (e2 * invSigma2 > 7.8) continue;
+        } else {
+          const float ex = u - kp.x, ey = v - kp.y;
+          const float e2 = ex * ex + ey * ey;
+          if (e2 * invSigma2 > 5.99) continue;
+        }
+      }
+      const int dist = descriptor_distance(dMP, KF->desc.data() + idx * 32);
+      if (dist < bestDist) { bestDist = dist; bestIdx = (int)idx; }
+    }
+    if (bestDist <= TH_LOW) { bestIdxOut[i] = bestIdx; nFused++; }
+  }
+  return nFused;
+}
+
+// OrbMatcher::SearchBySim3 (orb_matcher.cpp:1081-1310)
+int orc_search_by_sim3(const orc_frame* KF1, const orc_frame* KF2, const uint8_t* valid1, const float* u1, const float* v1,
+                       const int* lvl1, const uint8_t* desc1, const uint8_t* valid2, const float* u2, const float* v2,
+                       const int* lvl2, const uint8_t* desc2, float th, int* match12) {
+  const int TH_HIGH = 100;
+  const int N1 = KF1->n, N2 = KF2->n;
+  std::vector<int> vnMatch1(N1, -1), vnMatch2(N2, -1);
+  auto side = [&](const orc_frame* dst, int N, const uint8_t* valid, const float* us, const float* vs, const int* lvl,
+                  const uint8_t* mpDesc, std::vector<int>& vnMatch) {
+    for (int i = 0; i < N; i++) {
+      if (!valid[i]) continue;
+      const int nPredictedLevel = lvl[i];
+      const float radius = th * dst->scale[nPredictedLevel];
+      const std::vector<size_t> vIndices = features_in_area(dst, us[i], vs[i], radius, -1, -1);
+      if (vIndices.empty()) continue;
+      const uint8_t* dMP = mpDesc + (size_t)i * 32;
+      int bestDist = INT_MAX, bestIdx = -1;
+      for (size_t idx : vIndices) {
+        const KP& kp = dst->kps[idx];
+        if (kp.octave < nPredictedLevel - 1 || kp.octave > nPredictedLevel) continue;
+        const int dist = descriptor_distance(dMP, dst->desc.data() + idx * 32);
+        if (dist < bestDist) { bestDist = dist; bestIdx = (int)idx; }
+      }
+      if (bestDist <= TH_HIGH) vnMatch[i] = bestIdx;
+    }
+  };
+  side(KF2, N1, valid1, u1, v1, lvl1, desc1, vnMatch1);  // :1132-1209
+  side(KF1, N2, valid2, u2, v2, lvl2, desc2, vnMatch2);  // :1212-1289
+  int nFound = 0;
+  for (int i1 = 0; i1 < N1; i1++) {                      // :1291-1307
+    match12[i1] = -1;
+    const int idx2 = vnMatch1[i1];
+    if (idx2 >= 0 && vnMatch2[idx2] == i1) { match12[i1] = idx2; nFound++; }
+  }
+  return nFound;
+}
+
+// OrbMatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (orb_matcher.cpp:499-632)
+int orc_search_by_bow_keyframes(const orc_frame* KF2, int n1, const uint8_t* desc1, const float* angle1, const uint8_t* valid1,
+                                const uint8_t* valid2, int nodes1, const uint32_t* ids1, const int* start1, const uint32_t* idx1v,
+                                int nodes2, const uint32_t* ids2, const int* start2, const uint32_t* idx2v, float nnratio,
+                                int checkOri, int* matches12) {
+  const int TH_LOW = 50;
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  std::vector<uint8_t> vbMatched2(KF2->n, 0);
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  int nmatches = 0;
+  const FV A{nodes1, ids1, start1, idx1v}, B{nodes2, ids2, start2, idx2v};
+  for_common_nodes(A, B, [&](int a, int b) {
+    for (int k1 = start1[a]; k1 < start1[a + 1]; ++k1) {
+      const size_t idx1 = idx1v[k1];
+      if (!valid1[idx1]) continue;                                    // :535-539
+      const uint8_t* d1 = desc1 + idx1 * 32;
+      int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+      for (int k2 = start2[b]; k2 < start2[b + 1]; ++k2) {
+        const size_t idx2 = idx2v[k2];
+        if (vbMatched2[idx2] || !valid2[idx2]) continue;              // :553-557
+        const int dist = descriptor_distance(d1, KF2->desc.data() + idx2 * 32);
+        if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = (int)idx2; }
+        else if (dist < bestDist2) bestDist2 = dist;
+      }
+      if (bestDist1 < TH_LOW) {                                       // strict here (:575), '<=' in the Frame overload
+        if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+          matches12[idx1] = bestIdx2;
+          vbMatched2[bestIdx2] = 1;
+          if (checkOri) {
+            float rot = angle1[idx1] - KF2->kps[bestIdx2].angle;
+            if (rot < 0.0) rot += 360.0f;
+            int bin = (int)std::round(rot * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            rotHist[bin].push_back((int)idx1);
+          }
+          nmatches++;
+        }
+      }
+    }
+  });
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx : rotHist[i]) { matches12[idx] = -1; nmatches--; }
+    }
+  }
+  return nmatches;
+}
+
+// OrbMatcher::SearchForTriangulation (orb_matcher.cpp:634-802) with CheckDistEpipolarLine (:114-131).  The
+// reference never sets vbMatched2[bestIdx2] (the assignment of upstream ORB-SLAM2 is absent at :737-741), so a
+// KeyFrame-2 feature may be paired with several KeyFrame-1 features; restated as is.
+int orc_search_for_triangulation(const orc_frame* KF2, int n1, const orc_keypoint* kps1, const uint8_t* desc1,
+                                 const uint8_t* valid1, const uint8_t* stereo1, const uint8_t* valid2, int nodes1,
+                                 const uint32_t* ids1, const int* start1, const uint32_t* idx1v, int nodes2,
+                                 const uint32_t* ids2, const int* start2, const uint32_t* idx2v, const float* F12, float ex,
+                                 float ey, int onlyStereo, int checkOri, int* matches12) {
+  const int TH_LOW = 50;
+  int nmatches = 0;
+  std::vector<uint8_t> vbMatched2(KF2->n, 0);
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  const float factor = 1.0f / HISTO_LENGTH;
+  const FV A{nodes1, ids1, start1, idx1v}, B{nodes2, ids2, start2, idx2v};
+  for_common_nodes(A, B, [&](int a, int b) {
+    for (int k1 = start1[a]; k1 < start1[a + 1]; ++k1) {
+      const size_t idx1 = idx1v[k1];
+      if (!valid1[idx1]) continue;                 // already a MapPoint (:681)
+      const bool bStereo1 = stereo1[idx1] != 0;
+      if (onlyStereo && !bStereo1) continue;
+      const orc_keypoint& kp1 = kps1[idx1];
+      const uint8_t* d1 = desc1 + idx1 * 32;
+      int bestDist = TH_LOW, bestIdx2 = -1;
+      for (int k2 = start2[b]; k2 < start2[b + 1]; ++k2) {
+        const size_t idx2 = idx2v[k2];
+        if (vbMatched2[idx2] || !valid2[idx2]) continue;
+        const bool bStereo2 = KF2->uR[idx2] >= 0;
+        if (onlyStereo && !bStereo2) continue;
+        const int dist = descriptor_distance(d1, KF2->desc.data() + idx2 * 32);
+        if (dist > TH_LOW || dist > bestDist) continue;
+        const KP& kp2 = KF2->kps[idx2];
+        if (!bStereo1 && !bStereo2) {
+          const float distex = ex - kp2.x, distey = ey - kp2.y;
+          if (distex * distex + distey * distey < 100 * KF2->scale[kp2.octave]) continue;
+        }
+        // CheckDistEpipolarLine (:114-131): l = x1' F12
+        const float la = kp1.x * F12[0] + kp1.y * F12[3] + F12[6];
+        const float lb = kp1.x * F12[1] + kp1.y * F12[4] + F12[7];
+        const float lc = kp1.x * F12[2] + kp1.y * F12[5] + F12[8];
+        const float num = la * kp2.x + lb * kp2.y + lc;
+        const float den = la * la + lb * lb;
+        if (den == 0) continue;
+        const float dsqr = num * num / den;
+        const float sigma2 = kp2.octave == 0 ? 1.0f : KF2->scale[kp2.octave] * KF2->scale[kp2.octave];  // orb_extractor.cpp:363
+        if (dsqr < 3.84 * sigma2) { bestIdx2 = (int)idx2; bestDist = dist; }
+      }
+      if (bestIdx2 >= 0) {
+        matches12[idx1] = bestIdx2;
+        nmatches++;
+        if (checkOri) {
+          float rot = kp1.angle - KF2->kps[bestIdx2].angle;
+          if (rot < 0.0) rot += 360.0f;
+          int bin = (int)std::round(rot * factor);
+          if (bin == HISTO_LENGTH) bin = 0;
+          rotHist[bin].push_back((int)idx1);
+        }
+      }
+    }
+  });
+  if (checkOri) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx : rotHist[i]) { matches12[idx] = -1; nmatches--; }
     }
   }
   return nmatches;

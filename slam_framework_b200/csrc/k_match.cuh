@@ -34,7 +34,8 @@ struct FrameGrid {
   const float* uR;          // n (stereo right coordinate, <= 0: none)
   const int* cellStart;     // ORBFE_GRID_CELLS + 1, ix-major
   const int* cellItems;     // keypoint indices
-  int n;
+  const float* lvl;         // 3 x nlevels: scale_factors, level_sigma_sq, inv_level_sigma_sq (orb_extractor.cpp:356-372)
+  int n, nlevels;
   float minX, minY, gw, gh;
 };
 
@@ -48,8 +49,9 @@ struct MatchQueries {
   const uint8_t* valid;
   const uint8_t* desc;      // n x 32
   int n;
-  int checkUR;
+  int filter;               // per-candidate filter: 0 none, 1 stereo-right consistency (:65-70, :1404-1411), 2 Fuse chi2 (:893-917)
 };
+enum { ORBFE_FILTER_NONE = 0, ORBFE_FILTER_UR = 1, ORBFE_FILTER_FUSE = 2 };
 
 struct MatchScratch {
   uint2* cand;              // x = keypoint index, y = distance | octave << 16
@@ -145,7 +147,8 @@ k_match_candidates(const FrameGrid F, const MatchQueries Q, const MatchScratch S
   }
   const int minL = Q.minLevel[q], maxL = Q.maxLevel[q];
   const bool checkLevels = (minL > 0) || (maxL >= 0);  // frame.cpp:372 (quirk kept)
-  const float xr = Q.checkUR ? Q.xr[q] : 0.f;
+  const float xr = Q.filter ? Q.xr[q] : 0.f;
+  const float* invSigma2 = F.lvl + 2 * F.nlevels;
   const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(Q.desc + (size_t)q * 32));
   const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(Q.desc + (size_t)q * 32) + 1);
   int count = 0;
@@ -162,9 +165,20 @@ k_match_candidates(const FrameGrid F, const MatchQueries Q, const MatchScratch S
         if (checkLevels && (oct < minL || (maxL >= 0 && oct > maxL))) ok = false;
         const float dx = __fsub_rn(k.x, x), dy = __fsub_rn(k.y, y);
         if (!(fabsf(dx) < r && fabsf(dy) < r)) ok = false;
-        if (ok && Q.checkUR) {  // orb_matcher.cpp:65-70 / :1404-1411
+        if (ok && Q.filter == ORBFE_FILTER_UR) {  // orb_matcher.cpp:65-70 / :1404-1411
           const float u = F.uR[idx];
           if (u > 0 && fabsf(__fsub_rn(xr, u)) > r) ok = false;
+        } else if (ok && Q.filter == ORBFE_FILTER_FUSE) {  // reprojection error gate of Fuse (orb_matcher.cpp:893-917)
+          const float kpr = F.uR[idx];
+          const float ex = __fsub_rn(x, k.x), ey = __fsub_rn(y, k.y);
+          float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+          double lim = 5.99;
+          if (kpr >= 0) {
+            const float er = __fsub_rn(xr, kpr);
+            e2 = __fadd_rn(e2, __fmul_rn(er, er));
+            lim = 7.8;
+          }
+          if ((double)__fmul_rn(e2, invSigma2[oct]) > lim) ok = false;
         }
       }
       const unsigned bal = __ballot_sync(0xffffffffu, ok);
@@ -182,7 +196,9 @@ k_match_candidates(const FrameGrid F, const MatchQueries Q, const MatchScratch S
 }
 
 // ---- phase B: serial-order resolve, one warp ------------------------------------------------------
-enum { ORBFE_MODE_INIT = 0, ORBFE_MODE_MAPPOINTS = 1, ORBFE_MODE_LASTFRAME = 2, ORBFE_MODE_BOW = 3 };
+enum { ORBFE_MODE_INIT = 0, ORBFE_MODE_MAPPOINTS = 1, ORBFE_MODE_LASTFRAME = 2, ORBFE_MODE_BOW = 3, ORBFE_MODE_GENERIC = 4 };
+enum { ORBFE_FEEDBACK_NONE = 0, ORBFE_FEEDBACK_HASOBS = 1, ORBFE_FEEDBACK_ALL = 2 };   // who occupies a keypoint once accepted
+enum { ORBFE_RATIO_NONE = 0, ORBFE_RATIO_SAMELEVEL = 1, ORBFE_RATIO_BOW = 2 };         // second-best test
 
 struct ResolveArgs {
   int mode;
@@ -197,6 +213,12 @@ struct ResolveArgs {
   int* evBin;                 // per query: histogram bin of its acceptance, or -1
   int* evIdx;                 // per query: mode 0 -> query index, mode 2 -> keypoint index
   int* result;                // [0] nmatches
+  // parallel resolve (k_match_iterate / k_match_finalize), set per routine by the host:
+  int thAccept;               // accept bestDist <= thAccept (TH_HIGH 100, TH_LOW 50, ORBdist, ...)
+  int ratio;                  // ORBFE_RATIO_*
+  int feedback;               // ORBFE_FEEDBACK_*
+  int tieLast;                // equal distances: the LAST candidate wins (SearchForTriangulation's 'dist>bestDist' skip, :717)
+  int perQuery;               // out[] is indexed by query (value = keypoint) instead of by keypoint (value = query)
 };
 
 // 2 smallest of the union of two sorted pairs
@@ -337,27 +359,84 @@ k_match_resolve(const ResolveArgs A, const MatchScratch S) {
   if (lane == 0) A.result[0] = nmatches;
 }
 
-// ---- phase A for SearchByBoW (orb_matcher.cpp:133-262): the candidates of a KeyFrame feature are the Frame
-// features of the same vocabulary node, in the node's own order (DBoW2 FeatureVector); no filtering, so the
-// list offsets are known on the host.  One warp per query.
+// ---- phase A for the vocabulary-node searches: SearchByBoW(KeyFrame, Frame) (orb_matcher.cpp:133-262),
+// SearchByBoW(KeyFrame, KeyFrame) (:499-632) and SearchForTriangulation (:634-802).  The candidates of a query
+// feature are the searched frame's features of the same vocabulary node, in the node's own order (DBoW2
+// FeatureVector), so the list offsets are known on the host.  Candidates rejected by a static filter keep
+// their slot with distance 0xffff (the resolve kernels ignore distances >= 256).  One warp per query.
+struct BowFilter {
+  const uint8_t* valid2;    // per searched keypoint: usable as a candidate (null = all); :551-557, :701-705
+  int tri;                  // 1 = SearchForTriangulation: stereo / epipole / epipolar-line gates
+  int onlyStereo;           // bOnlyStereo (:686-688, :709-711)
+  const float* qx;          // per query: kp1.pt.x, kp1.pt.y (undistorted)
+  const float* qy;
+  const uint8_t* qStereo;   // per query: pKF1->right_coords[idx1] >= 0
+  float F12[9];             // row-major fundamental matrix
+  float ex, ey;             // epipole in the second image (:643-649)
+};
+
 __global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
 k_match_candidates_bow(const FrameGrid F, const uint8_t* __restrict__ qDescAll, const int* __restrict__ qDescIdx,
                        const unsigned* __restrict__ featIdx, const int* __restrict__ qSrcOff, const int nQ,
-                       const MatchScratch S) {
+                       const MatchScratch S, const BowFilter B) {
   const int lane = threadIdx.x & 31;
   const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
   if (q >= nQ) return;
   const int cnt = S.qCnt[q], off = S.qOff[q], src = qSrcOff[q];
   const uint8_t* qd = qDescAll + (size_t)qDescIdx[q] * 32;
   const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(qd)), a1 = __ldg(reinterpret_cast<const uint4*>(qd) + 1);
+  float la = 0.f, lb = 0.f, lc = 0.f, den = 0.f;
+  bool stereo1 = false;
+  if (B.tri) {  // epipolar line in the second image l = x1' F12 (CheckDistEpipolarLine, orb_matcher.cpp:114-123)
+    const float x1 = B.qx[q], y1 = B.qy[q];
+    la = __fadd_rn(__fadd_rn(__fmul_rn(x1, B.F12[0]), __fmul_rn(y1, B.F12[3])), B.F12[6]);
+    lb = __fadd_rn(__fadd_rn(__fmul_rn(x1, B.F12[1]), __fmul_rn(y1, B.F12[4])), B.F12[7]);
+    lc = __fadd_rn(__fadd_rn(__fmul_rn(x1, B.F12[2]), __fmul_rn(y1, B.F12[5])), B.F12[8]);
+    den = __fadd_rn(__fmul_rn(la, la), __fmul_rn(lb, lb));
+    stereo1 = B.qStereo[q] != 0;
+  }
   for (int c = lane; c < cnt; c += 32) {
     const int idx = (int)featIdx[src + c];
     const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(F.desc + (size_t)idx * 32));
     const uint4 b1 = __ldg(reinterpret_cast<const uint4*>(F.desc + (size_t)idx * 32) + 1);
-    const int dist = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
-                     __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-    S.cand[off + c] = make_uint2((unsigned)idx, (unsigned)dist);
+    int dist = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+               __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+    bool ok = !(B.valid2 && !B.valid2[idx]);
+    if (ok && B.tri) {
+      const MatchKp k2 = F.kp[idx];
+      const bool stereo2 = F.uR[idx] >= 0;
+      if (B.onlyStereo && !stereo2) ok = false;
+      if (ok && !stereo1 && !stereo2) {  // too close to the epipole (:722-728)
+        const float dx = __fsub_rn(B.ex, k2.x), dy = __fsub_rn(B.ey, k2.y);
+        if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < __fmul_rn(100.0f, F.lvl[k2.octave])) ok = false;
+      }
+      if (ok) {  // CheckDistEpipolarLine (:121-130)
+        const float num = __fadd_rn(__fadd_rn(__fmul_rn(la, k2.x), __fmul_rn(lb, k2.y)), lc);
+        if (den == 0) ok = false;
+        else {
+          const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+          ok = (double)dsqr < __dmul_rn(3.84, (double)F.lvl[F.nlevels + k2.octave]);
+        }
+      }
+    }
+    S.cand[off + c] = make_uint2((unsigned)idx, ok ? (unsigned)dist : 0xffffu);
   }
+}
+
+// SearchBySim3 agreement check (orb_matcher.cpp:1291-1307): match12[i1] = idx2 iff vnMatch1[i1] == idx2 and
+// vnMatch2[idx2] == i1
+__global__ void __launch_bounds__(256)
+k_sim3_agree(const int* __restrict__ vnMatch1, const int n1, const int* __restrict__ vnMatch2, const int n2,
+             int* __restrict__ match12, int* __restrict__ nFound) {
+  const int i1 = blockIdx.x * 256 + threadIdx.x;
+  bool hit = false;
+  if (i1 < n1) {
+    const int idx2 = vnMatch1[i1];
+    hit = idx2 >= 0 && idx2 < n2 && vnMatch2[idx2] == i1;
+    match12[i1] = hit ? idx2 : -1;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, hit);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(nFound, __popc(bal));
 }
 
 // ---- phase B, parallel form for the SearchByProjection routines (modes 1, 2) --------------------------
@@ -393,7 +472,7 @@ k_match_iterate(const ResolveArgs A, const MatchScratch S, const JacobiState J, 
     const uint2 cd = S.cand[off + c];
     const int dist = (int)(cd.y & 0xffffu);
     if (dist < 256 && !(A.occupiedIn && A.occupiedIn[cd.x]) && !(ownPrev[cd.x] < q)) {
-      const unsigned key = ((unsigned)dist << 20) | (unsigned)c;
+      const unsigned key = ((unsigned)dist << 20) | (unsigned)(A.tieLast ? 0xfffff - c : c);
       if (key < best) { second = best; best = key; } else if (key < second) second = key;
     }
   }
@@ -407,20 +486,22 @@ k_match_iterate(const ResolveArgs A, const MatchScratch S, const JacobiState J, 
   int newBest = -1;
   if (best != 0xffffffffu) {
     const int bestDist = (int)(best >> 20);
-    const uint2 bc = S.cand[off + (int)(best & 0xfffffu)];
-    bool accept = bestDist <= 100;  // TH_HIGH
-    if (A.mode == ORBFE_MODE_BOW) {  // SearchByBoW: bestDist1 <= TH_LOW && bestDist1 < mfNNratio * bestDist2 (:187-189)
+    const int bpos = (int)(best & 0xfffffu), spos = (int)(second & 0xfffffu);
+    const uint2 bc = S.cand[off + (A.tieLast ? 0xfffff - bpos : bpos)];
+    bool accept = bestDist <= A.thAccept;
+    if (A.ratio == ORBFE_RATIO_BOW) {  // SearchByBoW: bestDist1 < mfNNratio * bestDist2 (:187-189, :575-577)
       const float d2 = second == 0xffffffffu ? 256.0f : (float)(int)(second >> 20);
-      accept = bestDist <= 50 && (float)bestDist < __fmul_rn(A.nnratio, d2);
+      accept = accept && (float)bestDist < __fmul_rn(A.nnratio, d2);
     }
-    if (accept && A.mode == ORBFE_MODE_MAPPOINTS && second != 0xffffffffu) {
-      const uint2 sc = S.cand[off + (int)(second & 0xfffffu)];
+    if (accept && A.ratio == ORBFE_RATIO_SAMELEVEL && second != 0xffffffffu) {
+      const uint2 sc = S.cand[off + (A.tieLast ? 0xfffff - spos : spos)];
       if ((bc.y >> 16) == (sc.y >> 16) && (float)bestDist > __fmul_rn(A.nnratio, (float)(int)(second >> 20))) accept = false;
     }
     if (accept) newBest = (int)bc.x;
   }
   if (t == 0 || newBest != J.best[q]) { J.best[q] = newBest; J.changed[t] = 1; }
-  if (newBest >= 0 && (A.mode == ORBFE_MODE_BOW || A.hasObs[q])) atomicMin(&ownNext[newBest], q);
+  if (newBest >= 0 && (A.feedback == ORBFE_FEEDBACK_ALL || (A.feedback == ORBFE_FEEDBACK_HASOBS && A.hasObs[q])))
+    atomicMin(&ownNext[newBest], q);
 }
 
 // after convergence: F.SetMapPoint results (the LAST accepted query on a keypoint wins), the match count and
@@ -432,19 +513,21 @@ k_match_finalize(const ResolveArgs A, const MatchScratch S, const JacobiState J)
   __shared__ int s_n;
   if (S.cursor[1]) return;
   const int tid = threadIdx.x, T = blockDim.x;
-  for (int i = tid; i < A.nKp; i += T) A.out[i] = -1;
+  if (!A.perQuery)
+    for (int i = tid; i < A.nKp; i += T) A.out[i] = -1;
   if (tid < ORBFE_HISTO_LENGTH) s_hist[tid] = 0;
   if (tid == 0) s_n = 0;
   __syncthreads();
-  const bool ori = A.checkOri && (A.mode == ORBFE_MODE_LASTFRAME || A.mode == ORBFE_MODE_BOW);
+  const bool ori = A.checkOri != 0;
   const float factor = 1.0f / ORBFE_HISTO_LENGTH;  // orb_matcher.cpp:1322 (the reference's bin-width bug, kept)
   int mine = 0;
   for (int q = tid; q < A.nQ; q += T) {
     const int b = J.best[q];
     int bin = -1;
+    if (A.perQuery) A.out[q] = b;
     if (b >= 0) {
       ++mine;
-      atomicMax(&A.out[b], q);
+      if (!A.perQuery) atomicMax(&A.out[b], q);
       if (ori) {
         float rot = __fsub_rn(A.qAngle[q], A.kp[b].angle);
         if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
@@ -475,7 +558,7 @@ k_match_finalize(const ResolveArgs A, const MatchScratch S, const JacobiState J)
     for (int q = tid; q < A.nQ; q += T) {
       const int bin = A.evBin[q];
       if (bin >= 0 && bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) {
-        A.out[J.best[q]] = -1;  // CurrentFrame.SetMapPoint(idx, NULL); nmatches-- (:1441-1446)
+        A.out[A.perQuery ? q : J.best[q]] = -1;  // CurrentFrame.SetMapPoint(idx, NULL); nmatches-- (:1441-1446); vMatches12[idx1] = -1 (:784)
         ++removed;
       }
     }

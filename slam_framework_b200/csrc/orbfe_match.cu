@@ -35,6 +35,7 @@ struct orbfe_frame {
   MatchKp* d_kp = nullptr;
   uint8_t* d_desc = nullptr;
   float* d_uR = nullptr;
+  float* d_lvl = nullptr;   // scale_factors | level_sigma_sq | inv_level_sigma_sq
   int* d_cellStart = nullptr;
   int* d_cellItems = nullptr;
   // query scratch (grown on demand)
@@ -56,6 +57,7 @@ struct orbfe_frame {
   FrameGrid grid() const {
     FrameGrid G;
     G.kp = d_kp; G.desc = d_desc; G.uR = d_uR; G.cellStart = d_cellStart; G.cellItems = d_cellItems; G.n = n;
+    G.lvl = d_lvl; G.nlevels = nlevels;
     G.minX = minX; G.minY = minY; G.gw = gw; G.gh = gh;
     return G;
   }
@@ -101,17 +103,34 @@ struct HostQueries {
   const uint8_t* desc = nullptr;    // nq x 32 (host)
   const uint8_t* hasObs = nullptr;  // nq (host) or null
   int n = 0;
-  bool checkUR = false;
+  int filter = ORBFE_FILTER_NONE;
   void resize(int nq) {
     n = nq; x.assign(nq, 0.f); y.assign(nq, 0.f); r.assign(nq, 0.f); xr.assign(nq, 0.f); angle.assign(nq, 0.f);
     minL.assign(nq, -1); maxL.assign(nq, -1); valid.assign(nq, 0);
   }
 };
 
+// what couples / accepts the queries of one search routine (ResolveArgs fields, k_match.cuh)
+struct SearchSpec {
+  int mode = ORBFE_MODE_GENERIC;
+  float nnratio = 0.f;
+  int checkOri = 0;
+  int thAccept = 100;
+  int ratio = ORBFE_RATIO_NONE;
+  int feedback = ORBFE_FEEDBACK_NONE;
+  int tieLast = 0;
+  int perQuery = 0;
+};
+static void fill_args(ResolveArgs& A, const SearchSpec& sp) {
+  A.mode = sp.mode; A.nnratio = sp.nnratio; A.checkOri = sp.checkOri; A.thAccept = sp.thAccept; A.ratio = sp.ratio;
+  A.feedback = sp.feedback; A.tieLast = sp.tieLast; A.perQuery = sp.perQuery;
+}
+
 // uploads the queries, runs phase A + phase B on `f` (the searched frame); out_n entries of d_out come
-// back in `out`; *nmatches gets the count
-static int run_search(orbfe_frame* f, const HostQueries& Q, int mode, float nnratio, int checkOri, const uint8_t* occupied,
+// back in `out` (may be null: the result stays in f->d_out); *nmatches gets the count
+static int run_search(orbfe_frame* f, const HostQueries& Q, const SearchSpec& sp, const uint8_t* occupied,
                       int32_t* out, int out_n, int* nmatches) {
+  const int mode = sp.mode;
   CUDA_TRY(cudaSetDevice(f->device));
   int rc;
   const int nq = Q.n;
@@ -149,12 +168,13 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, int mode, float nnra
     CUDA_TRY(cudaMemsetAsync(f->d_cursor, 0, 4 * sizeof(int), st));
     MatchQueries MQ;
     MQ.x = f->d_qx; MQ.y = f->d_qy; MQ.r = f->d_qr; MQ.xr = f->d_qxr; MQ.minLevel = f->d_qMinL; MQ.maxLevel = f->d_qMaxL;
-    MQ.valid = f->d_qValid; MQ.desc = f->d_qDesc; MQ.n = nq; MQ.checkUR = Q.checkUR ? 1 : 0;
+    MQ.valid = f->d_qValid; MQ.desc = f->d_qDesc; MQ.n = nq; MQ.filter = Q.filter;
     MatchScratch S;
     S.cand = f->d_cand; S.qOff = f->d_qOff; S.qCnt = f->d_qCnt; S.cursor = f->d_cursor; S.capacity = f->candCap;
     ResolveArgs A;
-    A.mode = mode; A.nQ = nq; A.nKp = f->n; A.nnratio = nnratio; A.checkOri = checkOri; A.hasObs = f->d_qHasObs;
-    A.occupiedIn = f->d_occ; A.qAngle = f->d_qAngle; A.kp = f->d_kp; A.out = f->d_out; A.evBin = f->d_evBin;
+    fill_args(A, sp);
+    A.nQ = nq; A.nKp = f->n; A.hasObs = f->d_qHasObs;
+    A.occupiedIn = (occupied || mode == ORBFE_MODE_INIT) ? f->d_occ : nullptr; A.qAngle = f->d_qAngle; A.kp = f->d_kp; A.out = f->d_out; A.evBin = f->d_evBin;
     A.evIdx = f->d_evIdx; A.result = f->d_cursor + 2;
     if (nq > 0)
       MATCH_LAUNCH(f, k_match_candidates, dim3((nq + ORBFE_MATCH_THREADS / 32 - 1) / (ORBFE_MATCH_THREADS / 32)),
@@ -169,7 +189,9 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, int mode, float nnra
       const int grid = std::max(1, (nq + ORBFE_MATCH_THREADS / 32 - 1) / (ORBFE_MATCH_THREADS / 32));
       const int chunk = 8;
       int t = 0;
-      for (;;) {  // iterations are launched in chunks; converged iterations return immediately
+      if (sp.feedback == ORBFE_FEEDBACK_NONE) {  // independent queries: one evaluation is the answer
+        MATCH_LAUNCH(f, k_match_iterate, dim3(grid), dim3(ORBFE_MATCH_THREADS), 0, A, S, J, 0);
+      } else for (;;) {  // iterations are launched in chunks; converged iterations return immediately
         for (int k = 0; k < chunk && t <= nq; ++k, ++t) MATCH_LAUNCH(f, k_match_iterate, dim3(grid), dim3(ORBFE_MATCH_THREADS), 0, A, S, J, t);
         CUDA_TRY(cudaMemcpyAsync(f->h_res + 3, f->d_jchanged + (t - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -181,7 +203,7 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, int mode, float nnra
     CUDA_TRY(cudaMemcpyAsync(f->h_res, f->d_cursor, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     if (!f->h_res[1]) {
-      if (out_n > 0) CUDA_TRY(cudaMemcpy(out, f->d_out, (size_t)out_n * sizeof(int), cudaMemcpyDeviceToHost));
+      if (out_n > 0 && out) CUDA_TRY(cudaMemcpy(out, f->d_out, (size_t)out_n * sizeof(int), cudaMemcpyDeviceToHost));
       if (nmatches) *nmatches = f->h_res[2];
       return ORBFE_OK;
     }
@@ -222,7 +244,7 @@ int orbfe_frame_destroy(orbfe_frame* f) {
   if (!f) return ORBFE_OK;
   cudaSetDevice(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
-  cudaFree(f->d_kp); cudaFree(f->d_desc); cudaFree(f->d_uR); cudaFree(f->d_cellStart); cudaFree(f->d_cellItems);
+  cudaFree(f->d_kp); cudaFree(f->d_desc); cudaFree(f->d_uR); cudaFree(f->d_lvl); cudaFree(f->d_cellStart); cudaFree(f->d_cellItems);
   cudaFree(f->d_qx); cudaFree(f->d_qy); cudaFree(f->d_qr); cudaFree(f->d_qxr); cudaFree(f->d_qAngle); cudaFree(f->d_qMinL);
   cudaFree(f->d_qMaxL); cudaFree(f->d_qOff); cudaFree(f->d_qCnt); cudaFree(f->d_evBin); cudaFree(f->d_evIdx);
   cudaFree(f->d_qValid); cudaFree(f->d_qDesc); cudaFree(f->d_qHasObs); cudaFree(f->d_occ); cudaFree(f->d_out);
@@ -253,6 +275,12 @@ int orbfe_frame_create(int device, int n, const orbfe_keypoint* kps_un, const ui
   f->scale.assign(scale_factors, scale_factors + nlevels);
   f->hkp.resize(n);
   std::vector<float> ur(n, -1.0f);
+  std::vector<float> lvl(3 * (size_t)nlevels);  // ORBextractor tables (orb_extractor.cpp:356-372), float arithmetic
+  for (int l = 0; l < nlevels; ++l) {
+    lvl[l] = scale_factors[l];
+    lvl[nlevels + l] = l == 0 ? 1.0f : scale_factors[l] * scale_factors[l];
+    lvl[2 * nlevels + l] = 1.0f / lvl[nlevels + l];
+  }
   for (int i = 0; i < n; ++i) {
     f->hkp[i] = MatchKp{kps_un[i].x, kps_un[i].y, kps_un[i].angle, kps_un[i].octave};
     if (kps_un[i].octave < 0 || kps_un[i].octave >= nlevels) {
@@ -271,6 +299,8 @@ int orbfe_frame_create(int device, int n, const orbfe_keypoint* kps_un, const ui
   if (e == cudaSuccess) e = cudaMalloc(&f->d_kp, n1 * sizeof(MatchKp));
   if (e == cudaSuccess) e = cudaMalloc(&f->d_desc, n1 * 32);
   if (e == cudaSuccess) e = cudaMalloc(&f->d_uR, n1 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_lvl, lvl.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_lvl, lvl.data(), lvl.size() * sizeof(float), cudaMemcpyHostToDevice, f->stream);
   if (e == cudaSuccess) e = cudaMalloc(&f->d_cellStart, (ORBFE_GRID_CELLS + 1) * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&f->d_cellItems, n1 * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&f->d_occ, n1);
@@ -331,7 +361,9 @@ int orbfe_search_for_initialization(orbfe_frame* f1, orbfe_frame* f2, float* pre
   }
   Q.desc = desc1.data();
   int nm = 0;
-  const int rc = run_search(f2, Q, ORBFE_MODE_INIT, nnratio, check_orientation, nullptr, matches12, n1, &nm);
+  SearchSpec sp;
+  sp.mode = ORBFE_MODE_INIT; sp.nnratio = nnratio; sp.checkOri = check_orientation;
+  const int rc = run_search(f2, Q, sp, nullptr, matches12, n1, &nm);
   if (rc) return rc;
   for (int i = 0; i < n1; ++i)  // :377-379
     if (matches12[i] >= 0) {
@@ -366,8 +398,11 @@ int orbfe_search_by_projection_mappoints(orbfe_frame* f, int n_mp, const uint8_t
     Q.xr[i] = proj_xr[i];
     Q.minL[i] = lvl - 1; Q.maxL[i] = lvl;
   }
-  Q.desc = mp_desc; Q.hasObs = has_obs; Q.checkUR = true;
-  return run_search(f, Q, ORBFE_MODE_MAPPOINTS, nnratio, 0, occupied, assigned, f->n, n_matches);
+  Q.desc = mp_desc; Q.hasObs = has_obs; Q.filter = ORBFE_FILTER_UR;
+  SearchSpec sp;  // TH_HIGH, ratio test against a second best of the same level (:87-97), SetMapPoint feedback (:59-63)
+  sp.mode = ORBFE_MODE_MAPPOINTS; sp.nnratio = nnratio; sp.thAccept = 100; sp.ratio = ORBFE_RATIO_SAMELEVEL;
+  sp.feedback = ORBFE_FEEDBACK_HASOBS;
+  return run_search(f, Q, sp, occupied, assigned, f->n, n_matches);
 }
 
 int orbfe_search_by_projection_lastframe(orbfe_frame* cur, int n_last, const uint8_t* valid, const float* u, const float* v,
@@ -399,49 +434,208 @@ int orbfe_search_by_projection_lastframe(orbfe_frame* cur, int n_last, const uin
     Q.xr[i] = u[i] - prod;                                        // :1406 (no FMA)
     Q.angle[i] = last_angle[i];
   }
-  Q.desc = mp_desc; Q.hasObs = has_obs; Q.checkUR = true;
-  return run_search(cur, Q, ORBFE_MODE_LASTFRAME, 0.f, check_orientation, occupied, assigned, cur->n, n_matches);
+  Q.desc = mp_desc; Q.hasObs = has_obs; Q.filter = ORBFE_FILTER_UR;
+  SearchSpec sp;
+  sp.mode = ORBFE_MODE_LASTFRAME; sp.checkOri = check_orientation; sp.thAccept = 100; sp.feedback = ORBFE_FEEDBACK_HASOBS;
+  return run_search(cur, Q, sp, occupied, assigned, cur->n, n_matches);
 }
 
-// OrbMatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (orb_matcher.cpp:133-262)
-int orbfe_search_by_bow(orbfe_frame* f, int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid,
-                        int kf_nnodes, const uint32_t* kf_node_ids, const int32_t* kf_node_start, const uint32_t* kf_feat_idx,
-                        int f_nnodes, const uint32_t* f_node_ids, const int32_t* f_node_start, const uint32_t* f_feat_idx,
-                        float nnratio, int check_orientation, int32_t* matched_kf_idx, int* n_matches) {
-  if (!f || !matched_kf_idx || n_kf < 0 || kf_nnodes < 0 || f_nnodes < 0) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
-  if (n_kf && (!kf_desc || !kf_angle || !kf_valid)) return orbfe_fail(ORBFE_ERR_INVALID, "null keyframe array");
-  if ((kf_nnodes && (!kf_node_ids || !kf_node_start || !kf_feat_idx)) || (f_nnodes && (!f_node_ids || !f_node_start || !f_feat_idx)))
-    return orbfe_fail(ORBFE_ERR_INVALID, "null feature-vector array");
+// ---- the other projection searches of OrbMatcher: same window-Hamming kernels, different gates ----
+
+// OrbMatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) (orb_matcher.cpp:384-497)
+int orbfe_search_by_projection_sim3(orbfe_frame* kf, int n_mp, const uint8_t* valid, const float* u, const float* v,
+                                    const int32_t* pred_level, const uint8_t* mp_desc, const uint8_t* matched_in, int th,
+                                    int32_t* matched, int* n_matches) {
+  if (!kf || !matched || n_mp < 0) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
+  if (n_mp && (!valid || !u || !v || !pred_level || !mp_desc)) return orbfe_fail(ORBFE_ERR_INVALID, "null map-point array");
+  if (kf->n && !matched_in) return orbfe_fail(ORBFE_ERR_INVALID, "null matched array");
   if (n_matches) *n_matches = 0;
-  for (int i = 0; i < f->n; ++i) matched_kf_idx[i] = -1;
-  // queries in the reference's visiting order: common nodes ascending (the two-iterator walk with
-  // lower_bound, :152-236, is a sorted-set intersection), KeyFrame features in node order
-  std::vector<int> qKf, qSrc, qCnt, qOff;
-  std::vector<float> qAng;
+  HostQueries Q;
+  Q.resize(n_mp);
+  for (int i = 0; i < n_mp; ++i) {
+    if (!valid[i]) continue;
+    const int lvl = pred_level[i];
+    if (lvl < 0 || lvl >= kf->nlevels) return orbfe_fail(ORBFE_ERR_INVALID, "map point %d: predicted level %d out of range", i, lvl);
+    Q.valid[i] = 1;
+    Q.x[i] = u[i]; Q.y[i] = v[i];
+    Q.r[i] = th * kf->scale[lvl];             // :454
+    Q.minL[i] = lvl - 1; Q.maxL[i] = lvl;     // :474 (maxL >= 0, so the grid's level gate is exactly this test)
+  }
+  Q.desc = mp_desc;
+  SearchSpec sp;  // bestDist<=TH_LOW (:488); vpMatched[bestIdx]=pMP occupies the keypoint for later points (:469, :490)
+  sp.thAccept = 50; sp.feedback = ORBFE_FEEDBACK_ALL;
+  return run_search(kf, Q, sp, matched_in, matched, kf->n, n_matches);
+}
+
+// OrbMatcher::SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist) (orb_matcher.cpp:1455-1582)
+int orbfe_search_by_projection_keyframe(orbfe_frame* cur, int n_kf, const uint8_t* valid, const float* u, const float* v,
+                                        const int32_t* pred_level, const float* kf_angle, const uint8_t* mp_desc,
+                                        const uint8_t* occupied, float th, int orb_dist, int check_orientation,
+                                        int32_t* assigned, int* n_matches) {
+  if (!cur || !assigned || n_kf < 0) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
+  if (n_kf && (!valid || !u || !v || !pred_level || !kf_angle || !mp_desc)) return orbfe_fail(ORBFE_ERR_INVALID, "null keyframe array");
+  if (cur->n && !occupied) return orbfe_fail(ORBFE_ERR_INVALID, "null occupied array");
+  if (n_matches) *n_matches = 0;
+  HostQueries Q;
+  Q.resize(n_kf);
+  for (int i = 0; i < n_kf; ++i) {
+    if (!valid[i]) continue;
+    if (u[i] < cur->minX || u[i] > cur->maxX) continue;   // :1490-1495
+    if (v[i] < cur->minY || v[i] > cur->maxY) continue;
+    const int lvl = pred_level[i];
+    if (lvl < 0 || lvl >= cur->nlevels) return orbfe_fail(ORBFE_ERR_INVALID, "keyframe point %d: predicted level %d out of range", i, lvl);
+    Q.valid[i] = 1;
+    Q.x[i] = u[i]; Q.y[i] = v[i];
+    Q.r[i] = th * cur->scale[lvl];                        // :1511
+    Q.minL[i] = lvl - 1; Q.maxL[i] = lvl + 1;             // :1513
+    Q.angle[i] = kf_angle[i];
+  }
+  Q.desc = mp_desc;
+  SearchSpec sp;  // bestDist<=ORBdist (:1541); SetMapPoint occupies the keypoint (:1526, :1543)
+  sp.thAccept = orb_dist; sp.feedback = ORBFE_FEEDBACK_ALL; sp.checkOri = check_orientation;
+  return run_search(cur, Q, sp, occupied, assigned, cur->n, n_matches);
+}
+
+// the search part of both Fuse overloads: per map point the keypoint it would be fused into, else -1
+static int fuse_core(orbfe_frame* kf, int n_mp, const uint8_t* valid, const float* u, const float* v, const float* ur,
+                     const int32_t* pred_level, const uint8_t* mp_desc, float th, int32_t* best_idx, int* n_fused) {
+  if (!kf || n_mp < 0 || (n_mp && !best_idx)) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
+  if (n_mp && (!valid || !u || !v || !pred_level || !mp_desc)) return orbfe_fail(ORBFE_ERR_INVALID, "null map-point array");
+  if (n_fused) *n_fused = 0;
+  HostQueries Q;
+  Q.resize(n_mp);
+  for (int i = 0; i < n_mp; ++i) {
+    if (!valid[i]) continue;
+    const int lvl = pred_level[i];
+    if (lvl < 0 || lvl >= kf->nlevels) return orbfe_fail(ORBFE_ERR_INVALID, "map point %d: predicted level %d out of range", i, lvl);
+    Q.valid[i] = 1;
+    Q.x[i] = u[i]; Q.y[i] = v[i];
+    if (ur) Q.xr[i] = ur[i];
+    Q.r[i] = th * kf->scale[lvl];             // :869, :1028
+    Q.minL[i] = lvl - 1; Q.maxL[i] = lvl;     // :890, :1046
+  }
+  Q.desc = mp_desc;
+  Q.filter = ur ? ORBFE_FILTER_FUSE : ORBFE_FILTER_NONE;
+  SearchSpec sp;  // bestDist<=TH_LOW (:931, :1061); the scan reads no state another map point writes
+  sp.thAccept = 50; sp.perQuery = 1;
+  return run_search(kf, Q, sp, nullptr, best_idx, n_mp, n_fused);
+}
+
+// OrbMatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (orb_matcher.cpp:804-954)
+int orbfe_fuse(orbfe_frame* kf, int n_mp, const uint8_t* valid, const float* u, const float* v, const float* ur,
+               const int32_t* pred_level, const uint8_t* mp_desc, float th, int32_t* best_idx, int* n_fused) {
+  if (n_mp && !ur) return orbfe_fail(ORBFE_ERR_INVALID, "null ur array");
+  return fuse_core(kf, n_mp, valid, u, v, ur, pred_level, mp_desc, th, best_idx, n_fused);
+}
+
+// OrbMatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) (orb_matcher.cpp:956-1079)
+int orbfe_fuse_sim3(orbfe_frame* kf, int n_mp, const uint8_t* valid, const float* u, const float* v,
+                    const int32_t* pred_level, const uint8_t* mp_desc, float th, int32_t* best_idx, int* n_fused) {
+  return fuse_core(kf, n_mp, valid, u, v, nullptr, pred_level, mp_desc, th, best_idx, n_fused);
+}
+
+// OrbMatcher::SearchBySim3 (orb_matcher.cpp:1081-1310)
+int orbfe_search_by_sim3(orbfe_frame* kf1, orbfe_frame* kf2, const uint8_t* valid1, const float* u1, const float* v1,
+                         const int32_t* pred_level1, const uint8_t* mp_desc1, const uint8_t* valid2, const float* u2,
+                         const float* v2, const int32_t* pred_level2, const uint8_t* mp_desc2, float th, int32_t* match12,
+                         int* n_found) {
+  if (!kf1 || !kf2) return orbfe_fail(ORBFE_ERR_INVALID, "null frame");
+  if (kf1->device != kf2->device) return orbfe_fail(ORBFE_ERR_INVALID, "keyframes live on different devices");
+  const int n1 = kf1->n, n2 = kf2->n;
+  if ((n1 && (!valid1 || !u1 || !v1 || !pred_level1 || !mp_desc1 || !match12)) || (n2 && (!valid2 || !u2 || !v2 || !pred_level2 || !mp_desc2)))
+    return orbfe_fail(ORBFE_ERR_INVALID, "null array");
+  if (n_found) *n_found = 0;
+  if (n1 == 0) return ORBFE_OK;
+  SearchSpec sp;  // bestDist<=TH_HIGH (:1205, :1285), no coupling between map points
+  sp.thAccept = 100; sp.perQuery = 1;
+  // map points of KF1 searched in KF2 (:1132-1209), then map points of KF2 searched in KF1 (:1212-1289)
+  for (int side = 0; side < 2; ++side) {
+    orbfe_frame* dst = side == 0 ? kf2 : kf1;
+    const int n = side == 0 ? n1 : n2;
+    const uint8_t* valid = side == 0 ? valid1 : valid2;
+    const float *u = side == 0 ? u1 : u2, *v = side == 0 ? v1 : v2;
+    const int32_t* pl = side == 0 ? pred_level1 : pred_level2;
+    HostQueries Q;
+    Q.resize(n);
+    for (int i = 0; i < n; ++i) {
+      if (!valid[i]) continue;
+      const int lvl = pl[i];
+      if (lvl < 0 || lvl >= dst->nlevels) return orbfe_fail(ORBFE_ERR_INVALID, "map point %d: predicted level %d out of range", i, lvl);
+      Q.valid[i] = 1;
+      Q.x[i] = u[i]; Q.y[i] = v[i];
+      Q.r[i] = th * dst->scale[lvl];          // :1173, :1253
+      Q.minL[i] = lvl - 1; Q.maxL[i] = lvl;   // :1191, :1271
+    }
+    Q.desc = side == 0 ? mp_desc1 : mp_desc2;
+    const int rc = run_search(dst, Q, sp, nullptr, nullptr, n, nullptr);
+    if (rc) return rc;
+  }
+  // agreement (:1291-1307): vnMatch1 = kf2->d_out (n1), vnMatch2 = kf1->d_out (n2); both streams are idle here
+  CUDA_TRY(cudaSetDevice(kf1->device));
+  CUDA_TRY(cudaMemsetAsync(kf1->d_cursor + 3, 0, sizeof(int), kf1->stream));
+  MATCH_LAUNCH(kf1, k_sim3_agree, dim3((n1 + 255) / 256), dim3(256), 0, kf2->d_out, n1, kf1->d_out, n2, kf2->d_evIdx, kf1->d_cursor + 3);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(kf1->h_res + 3, kf1->d_cursor + 3, sizeof(int), cudaMemcpyDeviceToHost, kf1->stream));
+  CUDA_TRY(cudaMemcpyAsync(match12, kf2->d_evIdx, (size_t)n1 * sizeof(int), cudaMemcpyDeviceToHost, kf1->stream));
+  CUDA_TRY(cudaStreamSynchronize(kf1->stream));
+  if (n_found) *n_found = kf1->h_res[3];
+  return ORBFE_OK;
+}
+
+// ---- the vocabulary-node searches -----------------------------------------------------------------------------
+// flattened DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>): node ids ascending, n_nodes+1 offsets
+struct FeatVec {
+  int nnodes;
+  const uint32_t* ids;
+  const int32_t* start;
+  const uint32_t* idx;
+};
+struct BowHost {            // optional gates, see BowFilter (k_match.cuh)
+  const uint8_t* valid2 = nullptr;
+  int tri = 0, onlyStereo = 0;
+  const orbfe_keypoint* kps1 = nullptr;
+  const uint8_t* stereo1 = nullptr;
+  const float* F12 = nullptr;
+  float ex = 0, ey = 0;
+};
+
+// queries = the valid features of side 1 in the reference's visiting order (common nodes ascending -- the two-iterator
+// walk with lower_bound is a sorted-set intersection -- then the node's own feature order); candidates of a query = the
+// features of the same node on the searched frame `f`.  out: per searched keypoint (perQuery = 0) or per query.
+static int bow_core(orbfe_frame* f, int n1, const uint8_t* desc1, const float* angle1, const uint8_t* valid1, const FeatVec& fv1,
+                    const FeatVec& fv2, const SearchSpec& sp, const BowHost& bh, std::vector<int>& qFeat, std::vector<int>& result,
+                    int* n_matches) {
+  if (n_matches) *n_matches = 0;
+  qFeat.clear();
+  std::vector<int> qSrc, qCnt, qOff;
+  std::vector<float> qAng, qX, qY;
+  std::vector<uint8_t> qSt;
   int a = 0, b = 0, total = 0;
-  while (a < kf_nnodes && b < f_nnodes) {
-    if (kf_node_ids[a] == f_node_ids[b]) {
-      const int fo = f_node_start[b], fc = f_node_start[b + 1] - fo;
-      for (int k = kf_node_start[a]; k < kf_node_start[a + 1]; ++k) {
-        const int real = (int)kf_feat_idx[k];
-        if (real < 0 || real >= n_kf) return orbfe_fail(ORBFE_ERR_INVALID, "keyframe feature index %d out of range", real);
-        if (!kf_valid[real]) continue;  // no map point / bad map point (:162-168)
-        qKf.push_back(real); qSrc.push_back(fo); qCnt.push_back(fc); qOff.push_back(total); qAng.push_back(kf_angle[real]);
+  while (a < fv1.nnodes && b < fv2.nnodes) {
+    if (fv1.ids[a] == fv2.ids[b]) {
+      const int fo = fv2.start[b], fc = fv2.start[b + 1] - fo;
+      for (int k = fv1.start[a]; k < fv1.start[a + 1]; ++k) {
+        const int real = (int)fv1.idx[k];
+        if (real < 0 || real >= n1) return orbfe_fail(ORBFE_ERR_INVALID, "feature index %d out of range", real);
+        if (!valid1[real]) continue;
+        qFeat.push_back(real); qSrc.push_back(fo); qCnt.push_back(fc); qOff.push_back(total); qAng.push_back(angle1[real]);
+        if (bh.tri) { qX.push_back(bh.kps1[real].x); qY.push_back(bh.kps1[real].y); qSt.push_back(bh.stereo1[real] ? 1 : 0); }
         total += fc;
       }
       ++a; ++b;
-    } else if (kf_node_ids[a] < f_node_ids[b]) ++a;
+    } else if (fv1.ids[a] < fv2.ids[b]) ++a;
     else ++b;
   }
-  const int nq = (int)qKf.size();
+  const int nq = (int)qFeat.size();
+  result.assign(sp.perQuery ? nq : f->n, -1);
   if (nq == 0 || f->n == 0) return ORBFE_OK;
-  const int nfi = f_node_start[f_nnodes];
+  const int nfi = fv2.start[fv2.nnodes];
   for (int k = 0; k < nfi; ++k)
-    if ((int)f_feat_idx[k] < 0 || (int)f_feat_idx[k] >= f->n) return orbfe_fail(ORBFE_ERR_INVALID, "frame feature index out of range");
+    if ((int)fv2.idx[k] < 0 || (int)fv2.idx[k] >= f->n) return orbfe_fail(ORBFE_ERR_INVALID, "searched-frame feature index out of range");
   CUDA_TRY(cudaSetDevice(f->device));
   int rc;
-  if ((rc = ensure_queries(f, std::max(nq, n_kf)))) return rc;
-  if ((rc = ensure_out(f, std::max(f->n, nfi)))) return rc;
+  if ((rc = ensure_queries(f, std::max(nq, n1)))) return rc;
+  if ((rc = ensure_out(f, std::max(std::max(f->n, nfi), nq)))) return rc;
   if ((rc = ensure_cand(f, total + 16))) return rc;
   cudaStream_t st = f->stream;
   if (nq > f->jCap) {
@@ -451,51 +645,142 @@ int orbfe_search_by_bow(orbfe_frame* f, int n_kf, const uint8_t* kf_desc, const 
     f->jCap = nq + 256;
   }
   if (!f->d_jown) CUDA_TRY(regrow(&f->d_jown, 3 * (size_t)std::max(f->n, 1)));
-  // scratch re-use: d_qDesc <- all keyframe descriptors, d_qMinL <- descriptor index, d_qMaxL <- source offset,
-  // d_out (as unsigned) <- the Frame's feature-vector indices until the finalize kernel overwrites it
+  // scratch re-use: d_qDesc <- all side-1 descriptors, d_qMinL <- descriptor index, d_qMaxL <- source offset,
+  // d_qx/d_qy/d_qValid <- kp1 coordinates / stereo flags (triangulation), d_occ <- valid2
   unsigned* d_featIdx = nullptr;
   CUDA_TRY(cudaMalloc(&d_featIdx, (size_t)std::max(nfi, 1) * sizeof(unsigned)));
   auto done = [&](int code) { cudaFree(d_featIdx); return code; };
-  cudaError_t e = cudaMemcpyAsync(f->d_qDesc, kf_desc, (size_t)n_kf * 32, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qMinL, qKf.data(), (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, st);
+  cudaError_t e = cudaMemcpyAsync(f->d_qDesc, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qMinL, qFeat.data(), (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qMaxL, qSrc.data(), (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qOff, qOff.data(), (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qCnt, qCnt.data(), (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qAngle, qAng.data(), (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_featIdx, f_feat_idx, (size_t)nfi * sizeof(unsigned), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_featIdx, fv2.idx, (size_t)nfi * sizeof(unsigned), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && bh.tri) e = cudaMemcpyAsync(f->d_qx, qX.data(), (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && bh.tri) e = cudaMemcpyAsync(f->d_qy, qY.data(), (size_t)nq * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && bh.tri) e = cudaMemcpyAsync(f->d_qValid, qSt.data(), (size_t)nq, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && bh.valid2) e = cudaMemcpyAsync(f->d_occ, bh.valid2, (size_t)f->n, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(f->d_cursor, 0, 4 * sizeof(int), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(f->d_jown, 0x7f, 3 * (size_t)std::max(f->n, 1) * sizeof(int), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(f->d_jchanged, 0, ((size_t)nq + 16) * sizeof(int), st);
-  if (e != cudaSuccess) return done(orbfe_fail(ORBFE_ERR_CUDA, "SearchByBoW upload failed: %s", cudaGetErrorString(e)));
+  if (e != cudaSuccess) return done(orbfe_fail(ORBFE_ERR_CUDA, "vocabulary-node search upload failed: %s", cudaGetErrorString(e)));
   MatchScratch S;
   S.cand = f->d_cand; S.qOff = f->d_qOff; S.qCnt = f->d_qCnt; S.cursor = f->d_cursor; S.capacity = f->candCap;
   ResolveArgs A;
-  A.mode = ORBFE_MODE_BOW; A.nQ = nq; A.nKp = f->n; A.nnratio = nnratio; A.checkOri = check_orientation; A.hasObs = nullptr;
-  A.occupiedIn = nullptr; A.qAngle = f->d_qAngle; A.kp = f->d_kp; A.out = f->d_out; A.evBin = f->d_evBin; A.evIdx = f->d_evIdx;
-  A.result = f->d_cursor + 2;
+  fill_args(A, sp);
+  A.nQ = nq; A.nKp = f->n; A.hasObs = nullptr; A.occupiedIn = nullptr; A.qAngle = f->d_qAngle; A.kp = f->d_kp; A.out = f->d_out;
+  A.evBin = f->d_evBin; A.evIdx = f->d_evIdx; A.result = f->d_cursor + 2;
+  BowFilter B;
+  B.valid2 = bh.valid2 ? f->d_occ : nullptr; B.tri = bh.tri; B.onlyStereo = bh.onlyStereo; B.qx = f->d_qx; B.qy = f->d_qy;
+  B.qStereo = f->d_qValid; B.ex = bh.ex; B.ey = bh.ey;
+  for (int k = 0; k < 9; ++k) B.F12[k] = bh.F12 ? bh.F12[k] : 0.f;
   JacobiState J;
   J.best = f->d_jbest; J.own = f->d_jown; J.changed = f->d_jchanged;
   const int grid = (nq + ORBFE_MATCH_THREADS / 32 - 1) / (ORBFE_MATCH_THREADS / 32);
   MATCH_LAUNCH(f, k_match_candidates_bow, dim3(grid), dim3(ORBFE_MATCH_THREADS), 0, f->grid(), f->d_qDesc, f->d_qMinL, d_featIdx,
-               f->d_qMaxL, nq, S);
-  int t = 0;
-  for (;;) {
-    for (int k = 0; k < 8 && t <= nq; ++k, ++t) MATCH_LAUNCH(f, k_match_iterate, dim3(grid), dim3(ORBFE_MATCH_THREADS), 0, A, S, J, t);
-    e = cudaMemcpyAsync(f->h_res + 3, f->d_jchanged + (t - 1), sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return done(orbfe_fail(ORBFE_ERR_CUDA, "SearchByBoW resolve failed: %s", cudaGetErrorString(e)));
-    if (f->h_res[3] == 0 || t > nq) break;
+               f->d_qMaxL, nq, S, B);
+  if (sp.feedback == ORBFE_FEEDBACK_NONE) {
+    MATCH_LAUNCH(f, k_match_iterate, dim3(grid), dim3(ORBFE_MATCH_THREADS), 0, A, S, J, 0);
+  } else {
+    int t = 0;
+    for (;;) {
+      for (int k = 0; k < 8 && t <= nq; ++k, ++t) MATCH_LAUNCH(f, k_match_iterate, dim3(grid), dim3(ORBFE_MATCH_THREADS), 0, A, S, J, t);
+      e = cudaMemcpyAsync(f->h_res + 3, f->d_jchanged + (t - 1), sizeof(int), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return done(orbfe_fail(ORBFE_ERR_CUDA, "vocabulary-node resolve failed: %s", cudaGetErrorString(e)));
+      if (f->h_res[3] == 0 || t > nq) break;
+    }
   }
   MATCH_LAUNCH(f, k_match_finalize, dim3(1), dim3(1024), 0, A, S, J);
   e = cudaGetLastError();
-  std::vector<int> assigned((size_t)f->n);
   if (e == cudaSuccess) e = cudaMemcpyAsync(f->h_res, f->d_cursor, 3 * sizeof(int), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(assigned.data(), f->d_out, (size_t)f->n * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(result.data(), f->d_out, result.size() * sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return done(orbfe_fail(ORBFE_ERR_CUDA, "SearchByBoW failed: %s", cudaGetErrorString(e)));
-  for (int i = 0; i < f->n; ++i) matched_kf_idx[i] = assigned[i] >= 0 ? qKf[assigned[i]] : -1;  // query -> keyframe feature
+  if (e != cudaSuccess) return done(orbfe_fail(ORBFE_ERR_CUDA, "vocabulary-node search failed: %s", cudaGetErrorString(e)));
   if (n_matches) *n_matches = f->h_res[2];
   return done(ORBFE_OK);
+}
+
+static int check_featvec(const FeatVec& fv) {
+  if (fv.nnodes < 0 || (fv.nnodes && (!fv.ids || !fv.start || !fv.idx))) return orbfe_fail(ORBFE_ERR_INVALID, "bad feature-vector arrays");
+  return ORBFE_OK;
+}
+
+// OrbMatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (orb_matcher.cpp:133-262)
+int orbfe_search_by_bow(orbfe_frame* f, int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_valid,
+                        int kf_nnodes, const uint32_t* kf_node_ids, const int32_t* kf_node_start, const uint32_t* kf_feat_idx,
+                        int f_nnodes, const uint32_t* f_node_ids, const int32_t* f_node_start, const uint32_t* f_feat_idx,
+                        float nnratio, int check_orientation, int32_t* matched_kf_idx, int* n_matches) {
+  if (!f || !matched_kf_idx || n_kf < 0) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
+  if (n_kf && (!kf_desc || !kf_angle || !kf_valid)) return orbfe_fail(ORBFE_ERR_INVALID, "null keyframe array");
+  const FeatVec fv1{kf_nnodes, kf_node_ids, kf_node_start, kf_feat_idx}, fv2{f_nnodes, f_node_ids, f_node_start, f_feat_idx};
+  int rc;
+  if ((rc = check_featvec(fv1)) || (rc = check_featvec(fv2))) return rc;
+  SearchSpec sp;  // bestDist1<=TH_LOW && bestDist1 < mfNNratio*bestDist2 (:187-189); vpMapPointMatches[realIdxF] occupies (:173, :191)
+  sp.mode = ORBFE_MODE_BOW; sp.nnratio = nnratio; sp.checkOri = check_orientation; sp.thAccept = 50; sp.ratio = ORBFE_RATIO_BOW;
+  sp.feedback = ORBFE_FEEDBACK_ALL;
+  std::vector<int> qFeat, assigned;
+  if ((rc = bow_core(f, n_kf, kf_desc, kf_angle, kf_valid, fv1, fv2, sp, BowHost(), qFeat, assigned, n_matches))) return rc;
+  for (int i = 0; i < f->n; ++i) matched_kf_idx[i] = assigned[i] >= 0 ? qFeat[assigned[i]] : -1;  // query -> keyframe feature
+  return ORBFE_OK;
+}
+
+// OrbMatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (orb_matcher.cpp:499-632)
+int orbfe_search_by_bow_keyframes(orbfe_frame* kf2, int n1, const uint8_t* desc1, const float* angle1, const uint8_t* valid1,
+                                  const uint8_t* valid2, int nnodes1, const uint32_t* node_ids1, const int32_t* node_start1,
+                                  const uint32_t* feat_idx1, int nnodes2, const uint32_t* node_ids2, const int32_t* node_start2,
+                                  const uint32_t* feat_idx2, float nnratio, int check_orientation, int32_t* matches12,
+                                  int* n_matches) {
+  if (!kf2 || n1 < 0 || (n1 && !matches12)) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
+  if (n1 && (!desc1 || !angle1 || !valid1)) return orbfe_fail(ORBFE_ERR_INVALID, "null keyframe-1 array");
+  if (kf2->n && !valid2) return orbfe_fail(ORBFE_ERR_INVALID, "null keyframe-2 validity array");
+  const FeatVec fv1{nnodes1, node_ids1, node_start1, feat_idx1}, fv2{nnodes2, node_ids2, node_start2, feat_idx2};
+  int rc;
+  if ((rc = check_featvec(fv1)) || (rc = check_featvec(fv2))) return rc;
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  SearchSpec sp;  // bestDist1<TH_LOW (strict, :575) && ratio (:577); vbMatched2 occupies (:553, :580)
+  sp.mode = ORBFE_MODE_BOW; sp.nnratio = nnratio; sp.checkOri = check_orientation; sp.thAccept = 49; sp.ratio = ORBFE_RATIO_BOW;
+  sp.feedback = ORBFE_FEEDBACK_ALL;
+  BowHost bh;
+  bh.valid2 = valid2;
+  std::vector<int> qFeat, assigned;
+  if ((rc = bow_core(kf2, n1, desc1, angle1, valid1, fv1, fv2, sp, bh, qFeat, assigned, n_matches))) return rc;
+  // every KeyFrame-2 feature is taken at most once and every KeyFrame-1 feature is one query: invert
+  for (int i2 = 0; i2 < kf2->n && i2 < (int)assigned.size(); ++i2)
+    if (assigned[i2] >= 0) matches12[qFeat[assigned[i2]]] = i2;
+  return ORBFE_OK;
+}
+
+// OrbMatcher::SearchForTriangulation (orb_matcher.cpp:634-802)
+int orbfe_search_for_triangulation(orbfe_frame* kf2, int n1, const orbfe_keypoint* kps1_un, const uint8_t* desc1,
+                                   const uint8_t* valid1, const uint8_t* stereo1, const uint8_t* valid2, int nnodes1,
+                                   const uint32_t* node_ids1, const int32_t* node_start1, const uint32_t* feat_idx1,
+                                   int nnodes2, const uint32_t* node_ids2, const int32_t* node_start2,
+                                   const uint32_t* feat_idx2, const float* F12, float ex, float ey, int only_stereo,
+                                   int check_orientation, int32_t* matches12, int* n_matches) {
+  if (!kf2 || n1 < 0 || !F12 || (n1 && !matches12)) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
+  if (n1 && (!kps1_un || !desc1 || !valid1 || !stereo1)) return orbfe_fail(ORBFE_ERR_INVALID, "null keyframe-1 array");
+  if (kf2->n && !valid2) return orbfe_fail(ORBFE_ERR_INVALID, "null keyframe-2 validity array");
+  const FeatVec fv1{nnodes1, node_ids1, node_start1, feat_idx1}, fv2{nnodes2, node_ids2, node_start2, feat_idx2};
+  int rc;
+  if ((rc = check_featvec(fv1)) || (rc = check_featvec(fv2))) return rc;
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  std::vector<uint8_t> v1(n1);
+  std::vector<float> ang(n1);
+  for (int i = 0; i < n1; ++i) {
+    v1[i] = valid1[i] && !(only_stereo && !stereo1[i]);  // :681-688
+    ang[i] = kps1_un[i].angle;
+  }
+  SearchSpec sp;  // dist<=TH_LOW, ties go to the LAST candidate ('dist>bestDist' skip, :717); this reference never sets
+  sp.thAccept = 50; sp.tieLast = 1; sp.perQuery = 1; sp.checkOri = check_orientation;  // vbMatched2, so no coupling
+  BowHost bh;
+  bh.valid2 = valid2; bh.tri = 1; bh.onlyStereo = only_stereo; bh.kps1 = kps1_un; bh.stereo1 = stereo1; bh.F12 = F12;
+  bh.ex = ex; bh.ey = ey;
+  std::vector<int> qFeat, res;
+  if ((rc = bow_core(kf2, n1, desc1, ang.data(), v1.data(), fv1, fv2, sp, bh, qFeat, res, n_matches))) return rc;
+  for (size_t q = 0; q < qFeat.size() && q < res.size(); ++q) matches12[qFeat[q]] = res[q];
+  return ORBFE_OK;
 }
 
 }  // extern "C"

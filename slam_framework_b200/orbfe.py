@@ -47,6 +47,8 @@ EXPORTS = [
     "orbfe_descriptor_distance", "orbfe_frame_create", "orbfe_frame_destroy", "orbfe_features_in_area",
     "orbfe_search_for_initialization", "orbfe_search_by_projection_mappoints",
     "orbfe_search_by_projection_lastframe", "orbfe_search_by_bow",
+    "orbfe_search_by_projection_sim3", "orbfe_search_by_projection_keyframe", "orbfe_fuse", "orbfe_fuse_sim3",
+    "orbfe_search_by_sim3", "orbfe_search_by_bow_keyframes", "orbfe_search_for_triangulation",
 ]
 
 _libs = {}
@@ -106,6 +108,13 @@ def load(path=None, _test_emulation=False):
     L.orbfe_search_by_projection_mappoints.argtypes = [vp, i] + [vp] * 9 + [i, f, vp, vp]
     L.orbfe_search_by_projection_lastframe.argtypes = [vp, i] + [vp] * 8 + [f, i, i, vp, f, i, vp, vp]
     L.orbfe_search_by_bow.argtypes = [vp, i, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, f, i, vp, vp]
+    L.orbfe_search_by_projection_sim3.argtypes = [vp, i] + [vp] * 6 + [i, vp, vp]
+    L.orbfe_search_by_projection_keyframe.argtypes = [vp, i] + [vp] * 7 + [f, i, i, vp, vp]
+    L.orbfe_fuse.argtypes = [vp, i] + [vp] * 6 + [f, vp, vp]
+    L.orbfe_fuse_sim3.argtypes = [vp, i] + [vp] * 5 + [f, vp, vp]
+    L.orbfe_search_by_sim3.argtypes = [vp, vp] + [vp] * 10 + [f, vp, vp]
+    L.orbfe_search_by_bow_keyframes.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, f, i, vp, vp]
+    L.orbfe_search_for_triangulation.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, f, f, i, i, vp, vp]
     _libs[path] = L
     return L
 
@@ -429,4 +438,86 @@ def SearchByBoW(F, kf_desc, kf_angle, kf_valid, kf_fv, f_fv, nnratio=0.7, checkO
     n = C.c_int()
     _check(F.L, F.L.orbfe_search_by_bow(F.h, len(kd), _p(kd), _p(ka), _p(kv), len(ki), _p(ki), _p(ks), _p(kx), len(fi), _p(fi),
                                         _p(fs), _p(fx), nnratio, int(checkOri), _p(out), C.byref(n)))
+    return n.value, out
+
+
+# ---- the remaining OrbMatcher searches; argument conventions of include/orbfe.h ---------------
+def _a(x, t):
+    return np.ascontiguousarray(x, t)
+
+
+def SearchByProjectionSim3(KF, valid, u, v, pred_level, mp_desc, matched_in, th):
+    """SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (orb_matcher.cpp:384-497) -> (nmatches, matched[N])"""
+    out = np.zeros(len(KF.kps), np.int32)
+    n = C.c_int()
+    args = [_a(valid, np.uint8), _a(u, np.float32), _a(v, np.float32), _a(pred_level, np.int32), _a(mp_desc, np.uint8),
+            _a(matched_in, np.uint8)]
+    _check(KF.L, KF.L.orbfe_search_by_projection_sim3(KF.h, len(args[0]), *[_p(x) for x in args], int(th), _p(out), C.byref(n)))
+    return n.value, out
+
+
+def SearchByProjectionKeyFrame(Cur, valid, u, v, pred_level, kf_angle, mp_desc, occupied, th, ORBdist, checkOri=True):
+    """SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist) (orb_matcher.cpp:1455-1582)"""
+    out = np.zeros(len(Cur.kps), np.int32)
+    n = C.c_int()
+    args = [_a(valid, np.uint8), _a(u, np.float32), _a(v, np.float32), _a(pred_level, np.int32), _a(kf_angle, np.float32),
+            _a(mp_desc, np.uint8), _a(occupied, np.uint8)]
+    _check(Cur.L, Cur.L.orbfe_search_by_projection_keyframe(Cur.h, len(args[0]), *[_p(x) for x in args], float(th), int(ORBdist),
+                                                           int(checkOri), _p(out), C.byref(n)))
+    return n.value, out
+
+
+def Fuse(KF, valid, u, v, ur, pred_level, mp_desc, th):
+    """the search of Fuse(KeyFrame*, vpMapPoints, th) (orb_matcher.cpp:804-954); ur=None: Fuse(KeyFrame*, Scw, ...)
+    (:956-1079) -> (nFused, best_idx[n_mp])"""
+    n_mp = len(valid)
+    out = np.zeros(n_mp, np.int32)
+    n = C.c_int()
+    args = [_a(valid, np.uint8), _a(u, np.float32), _a(v, np.float32)]
+    tail = [_a(pred_level, np.int32), _a(mp_desc, np.uint8)]
+    if ur is None:
+        _check(KF.L, KF.L.orbfe_fuse_sim3(KF.h, n_mp, *[_p(x) for x in args + tail], float(th), _p(out), C.byref(n)))
+    else:
+        args.append(_a(ur, np.float32))
+        _check(KF.L, KF.L.orbfe_fuse(KF.h, n_mp, *[_p(x) for x in args + tail], float(th), _p(out), C.byref(n)))
+    return n.value, out
+
+
+def SearchBySim3(KF1, KF2, side1, side2, th):
+    """SearchBySim3 (orb_matcher.cpp:1081-1310); side = (valid, u, v, pred_level, mp_desc) -> (nFound, match12[N1])"""
+    def pack(sd):
+        return [_a(sd[0], np.uint8), _a(sd[1], np.float32), _a(sd[2], np.float32), _a(sd[3], np.int32), _a(sd[4], np.uint8)]
+    a1, a2 = pack(side1), pack(side2)
+    out = np.zeros(len(KF1.kps), np.int32)
+    n = C.c_int()
+    _check(KF1.L, KF1.L.orbfe_search_by_sim3(KF1.h, KF2.h, *[_p(x) for x in a1 + a2], float(th), _p(out), C.byref(n)))
+    return n.value, out
+
+
+def SearchByBoWKeyFrames(KF2, desc1, angle1, valid1, valid2, fv1, fv2, nnratio=0.8, checkOri=True):
+    """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (orb_matcher.cpp:499-632) -> (nmatches, matches12[N1])"""
+    d1, a1, v1, v2 = _a(desc1, np.uint8), _a(angle1, np.float32), _a(valid1, np.uint8), _a(valid2, np.uint8)
+    i1, s1, x1 = flatten_feature_vector(fv1)
+    i2, s2, x2 = flatten_feature_vector(fv2)
+    out = np.zeros(len(d1), np.int32)
+    n = C.c_int()
+    _check(KF2.L, KF2.L.orbfe_search_by_bow_keyframes(KF2.h, len(d1), _p(d1), _p(a1), _p(v1), _p(v2), len(i1), _p(i1), _p(s1),
+                                                     _p(x1), len(i2), _p(i2), _p(s2), _p(x2), nnratio, int(checkOri), _p(out),
+                                                     C.byref(n)))
+    return n.value, out
+
+
+def SearchForTriangulation(KF2, kps1, desc1, valid1, stereo1, valid2, fv1, fv2, F12, ex, ey, onlyStereo=False, checkOri=True):
+    """SearchForTriangulation (orb_matcher.cpp:634-802) -> (nmatches, matches12[N1]); vMatchedPairs =
+    [(i, matches12[i]) for i if matches12[i] >= 0]"""
+    k1, d1 = _a(kps1, KP_DTYPE), _a(desc1, np.uint8)
+    v1, st1, v2 = _a(valid1, np.uint8), _a(stereo1, np.uint8), _a(valid2, np.uint8)
+    i1, s1, x1 = flatten_feature_vector(fv1)
+    i2, s2, x2 = flatten_feature_vector(fv2)
+    F = _a(np.asarray(F12, np.float32).reshape(9), np.float32)
+    out = np.zeros(len(k1), np.int32)
+    n = C.c_int()
+    _check(KF2.L, KF2.L.orbfe_search_for_triangulation(KF2.h, len(k1), _p(k1), _p(d1), _p(v1), _p(st1), _p(v2), len(i1), _p(i1),
+                                                      _p(s1), _p(x1), len(i2), _p(i2), _p(s2), _p(x2), _p(F), float(ex), float(ey),
+                                                      int(onlyStereo), int(checkOri), _p(out), C.byref(n)))
     return n.value, out

@@ -63,6 +63,14 @@ def lib():
         L.orc_search_by_projection_lastframe.argtypes = [vp, C.c_int] + [vp] * 8 + [C.c_float, C.c_int, C.c_int, vp,
                                                                                  C.c_float, C.c_int, vp]
         L.orc_search_by_bow.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp, C.c_float, C.c_int, vp]
+        L.orc_search_by_projection_sim3.argtypes = [vp, C.c_int] + [vp] * 6 + [C.c_int, vp]
+        L.orc_search_by_projection_keyframe.argtypes = [vp, C.c_int] + [vp] * 7 + [C.c_float, C.c_int, C.c_int, vp]
+        L.orc_fuse.argtypes = [vp, C.c_int] + [vp] * 6 + [C.c_float, vp]
+        L.orc_search_by_sim3.argtypes = [vp, vp] + [vp] * 10 + [C.c_float, vp]
+        L.orc_search_by_bow_keyframes.argtypes = [vp, C.c_int, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
+                                                  C.c_float, C.c_int, vp]
+        L.orc_search_for_triangulation.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
+                                                   vp, C.c_float, C.c_float, C.c_int, C.c_int, vp]
         L.orc_bench_stereo_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                              C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
         L.orc_bench_stereo_batch.restype = C.c_double
@@ -256,4 +264,66 @@ def search_by_bow(f, kf_desc, kf_angle, kf_valid, kf_fv, f_fv, nnratio=0.7, chec
     out = np.zeros(len(f.kps), np.int32)
     n = lib().orc_search_by_bow(f.h, len(kd), _p(kd), _p(ka), _p(kv), len(ki), _p(ki), _p(ks), _p(kx), len(fi), _p(fi), _p(fs),
                                 _p(fx), nnratio, int(check_ori), _p(out))
+    return n, out
+
+
+def _a(x, t):
+    return np.ascontiguousarray(x, t)
+
+
+def search_by_projection_sim3(kf, valid, u, v, pred_level, mp_desc, matched_in, th):
+    out = np.zeros(len(kf.kps), np.int32)
+    args = [_a(valid, np.uint8), _a(u, np.float32), _a(v, np.float32), _a(pred_level, np.int32), _a(mp_desc, np.uint8),
+            _a(matched_in, np.uint8)]
+    n = lib().orc_search_by_projection_sim3(kf.h, len(args[0]), *[_p(x) for x in args], int(th), _p(out))
+    return n, out
+
+
+def search_by_projection_keyframe(cur, valid, u, v, pred_level, kf_angle, mp_desc, occupied, th, orb_dist, check_ori=True):
+    out = np.zeros(len(cur.kps), np.int32)
+    args = [_a(valid, np.uint8), _a(u, np.float32), _a(v, np.float32), _a(pred_level, np.int32), _a(kf_angle, np.float32),
+            _a(mp_desc, np.uint8), _a(occupied, np.uint8)]
+    n = lib().orc_search_by_projection_keyframe(cur.h, len(args[0]), *[_p(x) for x in args], th, int(orb_dist), int(check_ori),
+                                                _p(out))
+    return n, out
+
+
+def fuse(kf, valid, u, v, ur, pred_level, mp_desc, th):
+    out = np.zeros(len(valid), np.int32)
+    urp = None if ur is None else _a(ur, np.float32)
+    args = [_a(valid, np.uint8), _a(u, np.float32), _a(v, np.float32), urp, _a(pred_level, np.int32), _a(mp_desc, np.uint8)]
+    n = lib().orc_fuse(kf.h, len(valid), *[_p(x) for x in args], th, _p(out))
+    return n, out
+
+
+def search_by_sim3(kf1, kf2, side1, side2, th):
+    def pack(sd):
+        return [_a(sd[0], np.uint8), _a(sd[1], np.float32), _a(sd[2], np.float32), _a(sd[3], np.int32), _a(sd[4], np.uint8)]
+    out = np.zeros(len(kf1.kps), np.int32)
+    n = lib().orc_search_by_sim3(kf1.h, kf2.h, *[_p(x) for x in pack(side1) + pack(side2)], th, _p(out))
+    return n, out
+
+
+def search_by_bow_keyframes(kf2, desc1, angle1, valid1, valid2, fv1, fv2, nnratio=0.8, check_ori=True):
+    from slam_framework_b200.orbfe import flatten_feature_vector
+    d1, a1, v1, v2 = _a(desc1, np.uint8), _a(angle1, np.float32), _a(valid1, np.uint8), _a(valid2, np.uint8)
+    i1, s1, x1 = flatten_feature_vector(fv1)
+    i2, s2, x2 = flatten_feature_vector(fv2)
+    out = np.zeros(len(d1), np.int32)
+    n = lib().orc_search_by_bow_keyframes(kf2.h, len(d1), _p(d1), _p(a1), _p(v1), _p(v2), len(i1), _p(i1), _p(s1), _p(x1),
+                                          len(i2), _p(i2), _p(s2), _p(x2), nnratio, int(check_ori), _p(out))
+    return n, out
+
+
+def search_for_triangulation(kf2, kps1, desc1, valid1, stereo1, valid2, fv1, fv2, F12, ex, ey, only_stereo=False, check_ori=True):
+    from slam_framework_b200.orbfe import flatten_feature_vector
+    k1, d1 = _a(kps1, KP_DTYPE), _a(desc1, np.uint8)
+    v1, st1, v2 = _a(valid1, np.uint8), _a(stereo1, np.uint8), _a(valid2, np.uint8)
+    i1, s1, x1 = flatten_feature_vector(fv1)
+    i2, s2, x2 = flatten_feature_vector(fv2)
+    F = _a(np.asarray(F12, np.float32).reshape(9), np.float32)
+    out = np.zeros(len(k1), np.int32)
+    n = lib().orc_search_for_triangulation(kf2.h, len(k1), _p(k1), _p(d1), _p(v1), _p(st1), _p(v2), len(i1), _p(i1), _p(s1),
+                                           _p(x1), len(i2), _p(i2), _p(s2), _p(x2), _p(F), ex, ey, int(only_stereo),
+                                           int(check_ori), _p(out))
     return n, out

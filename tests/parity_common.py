@@ -225,3 +225,137 @@ def check_search_by_bow(lib, kps_f, desc_f, kps_kf, desc_kf, scale, w, h, seed=0
         assert np.array_equal(m, om)
         tot += n
     return tot
+
+
+# ---- N1: the remaining OrbMatcher searches -----------------------------------------------------------------
+def _proj_points(kps, desc, rng, n_mp, jitter=3.0, flip_max=60):
+    """map points 'seen' near random keypoints: projection = keypoint + jitter, descriptor = the keypoint's with
+    0..flip_max flipped bits, predicted level = octave (+1 w.p. 1/2); ~10 % fail the geometric gates"""
+    n = len(kps)
+    src = rng.integers(0, n, n_mp)
+    d = desc[src].copy()
+    for i in range(n_mp):
+        for b in rng.choice(256, rng.integers(0, flip_max + 1), replace=False):
+            d[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    lvl = np.minimum(kps["octave"][src] + rng.integers(0, 2, n_mp), 7).astype(np.int32)
+    u = (kps["x"][src] + rng.uniform(-jitter, jitter, n_mp)).astype(np.float32)
+    v = (kps["y"][src] + rng.uniform(-jitter, jitter, n_mp)).astype(np.float32)
+    valid = (rng.uniform(0, 1, n_mp) < 0.9).astype(np.uint8)
+    return dict(src=src, valid=valid, u=u, v=v, lvl=lvl, desc=d)
+
+
+def check_search_by_projection_sim3(lib, kps, desc, scale, w, h, n_mp, seed=0, th=10):
+    rng = np.random.default_rng(seed)
+    F, OF = make_frames(kps, desc, scale, w, h, lib)
+    mp = _proj_points(kps, desc, rng, n_mp)
+    matched_in = (rng.uniform(0, 1, len(kps)) < 0.2).astype(np.uint8)
+    n, m = orbfe.SearchByProjectionSim3(F, mp["valid"], mp["u"], mp["v"], mp["lvl"], mp["desc"], matched_in, th)
+    on, om = O.search_by_projection_sim3(OF, mp["valid"], mp["u"], mp["v"], mp["lvl"], mp["desc"], matched_in, th)
+    assert n == on, f"SearchByProjection(KF, Scw): {n} vs oracle {on}"
+    assert np.array_equal(m, om)
+    return n
+
+
+def check_search_by_projection_keyframe(lib, kps, desc, scale, w, h, n_kf, seed=0, th=10.0, orb_dist=100):
+    rng = np.random.default_rng(seed)
+    F, OF = make_frames(kps, desc, scale, w, h, lib)
+    mp = _proj_points(kps, desc, rng, n_kf, jitter=4.0)
+    mp["u"][:6] = [-5.0, w + 3.0, 10.0, 10.0, 0.0, float(w)]      # bounds gate (:1490-1495): first two rejected by u
+    mp["v"][2:4] = [-1.0, h + 0.5]
+    ang = ((kps["angle"][mp["src"]] + rng.choice([0.0, 0.0, 0.0, 30.0, 200.0], n_kf)) % 360).astype(np.float32)
+    occupied = (rng.uniform(0, 1, len(kps)) < 0.15).astype(np.uint8)
+    tot = 0
+    for ori in (True, False):
+        for od in (orb_dist, 64):
+            n, a = orbfe.SearchByProjectionKeyFrame(F, mp["valid"], mp["u"], mp["v"], mp["lvl"], ang, mp["desc"], occupied, th, od, ori)
+            on, oa = O.search_by_projection_keyframe(OF, mp["valid"], mp["u"], mp["v"], mp["lvl"], ang, mp["desc"], occupied, th, od, ori)
+            assert n == on, f"SearchByProjection(Frame, KF) ori={ori} ORBdist={od}: {n} vs oracle {on}"
+            assert np.array_equal(a, oa)
+            tot += n
+    return tot
+
+
+def check_fuse(lib, kps, desc, scale, w, h, n_mp, seed=0, th=3.0, u_right=None):
+    rng = np.random.default_rng(seed)
+    F, OF = make_frames(kps, desc, scale, w, h, lib, u_right)
+    mp = _proj_points(kps, desc, rng, n_mp, jitter=2.5)
+    ur = (mp["u"] - rng.uniform(0, 40, n_mp)).astype(np.float32)
+    if u_right is not None:  # most stereo keypoints see a consistent right coordinate, some do not (chi2 gate)
+        has = u_right[mp["src"]] >= 0
+        ur[has] = (u_right[mp["src"]][has] + rng.uniform(-2.5, 2.5, has.sum())).astype(np.float32)
+    tot = 0
+    for urs in (ur, None):
+        n, b = orbfe.Fuse(F, mp["valid"], mp["u"], mp["v"], urs, mp["lvl"], mp["desc"], th)
+        on, ob = O.fuse(OF, mp["valid"], mp["u"], mp["v"], urs, mp["lvl"], mp["desc"], th)
+        assert n == on, f"Fuse (ur {'given' if urs is not None else 'none'}): {n} vs oracle {on}"
+        assert np.array_equal(b, ob)
+        tot += n
+    return tot
+
+
+def check_search_by_sim3(lib, k1, d1, k2, d2, scale, w, h, seed=0, th=7.5, shift=(0.0, 0.0)):
+    """KF2 = KF1's scene displaced by `shift`: a map point of KF1 projects at kp - shift in KF2 and back"""
+    rng = np.random.default_rng(seed)
+    F1, OF1 = make_frames(k1, d1, scale, w, h, lib)
+    F2, OF2 = make_frames(k2, d2, scale, w, h, lib)
+
+    def side(k, d, sgn):
+        n = len(k)
+        dd = d.copy()
+        dd[:, 3] ^= rng.integers(0, 4, n).astype(np.uint8)
+        u = (k["x"] - sgn * shift[0] + rng.uniform(-2, 2, n)).astype(np.float32)
+        v = (k["y"] - sgn * shift[1] + rng.uniform(-2, 2, n)).astype(np.float32)
+        lvl = np.minimum(k["octave"] + rng.integers(0, 2, n), 7).astype(np.int32)
+        valid = (rng.uniform(0, 1, n) < 0.8).astype(np.uint8)
+        return (valid, u, v, lvl, dd)
+    s1, s2 = side(k1, d1, 1.0), side(k2, d2, -1.0)
+    n, m = orbfe.SearchBySim3(F1, F2, s1, s2, th)
+    on, om = O.search_by_sim3(OF1, OF2, s1, s2, th)
+    assert n == on, f"SearchBySim3: {n} vs oracle {on}"
+    assert np.array_equal(m, om)
+    return n
+
+
+def check_search_by_bow_keyframes(lib, k1, d1, k2, d2, scale, w, h, seed=0, nnratio=0.8):
+    rng = np.random.default_rng(seed)
+    dup = rng.permutation(len(k2))[: len(k2) // 5]   # exact duplicates => equal distances: the FIRST candidate wins, ratio test fails
+    k2, d2 = np.concatenate([k2, k2[dup]]), np.concatenate([d2, d2[dup]])
+    F2, OF2 = make_frames(k2, d2, scale, w, h, lib)
+    fv1, fv2 = synth_feature_vector(d1, rng), synth_feature_vector(d2, rng)
+    v1 = (rng.uniform(0, 1, len(k1)) < 0.7).astype(np.uint8)
+    v2 = (rng.uniform(0, 1, len(k2)) < 0.7).astype(np.uint8)
+    tot = 0
+    for ori in (True, False):
+        n, m = orbfe.SearchByBoWKeyFrames(F2, d1, k1["angle"], v1, v2, fv1, fv2, nnratio, ori)
+        on, om = O.search_by_bow_keyframes(OF2, d1, k1["angle"], v1, v2, fv1, fv2, nnratio, ori)
+        assert n == on, f"SearchByBoW(KF, KF) ori={ori}: {n} vs oracle {on}"
+        assert np.array_equal(m, om)
+        tot += n
+    return tot
+
+
+def check_search_for_triangulation(lib, k1, d1, k2, d2, scale, w, h, seed=0, shift=(6.0, 0.0)):
+    """KF2 = KF1 translated sideways by `shift` pixels: the fundamental matrix of a pure image translation
+    (epipolar lines parallel to the shift), plus a generic perturbed one"""
+    rng = np.random.default_rng(seed)
+    dup = rng.permutation(len(k2))[: len(k2) // 5]   # exact duplicates => equal distances: the LAST candidate must win (:717)
+    k2, d2 = np.concatenate([k2, k2[dup]]), np.concatenate([d2, d2[dup]])
+    ur2 = np.where(rng.uniform(0, 1, len(k2)) < 0.5, k2["x"] - rng.uniform(1, 50, len(k2)), -1).astype(np.float32)
+    F2, OF2 = make_frames(k2, d2, scale, w, h, lib, ur2)
+    fv1, fv2 = synth_feature_vector(d1, rng, n_nodes=31), synth_feature_vector(d2, rng, n_nodes=31)
+    v1 = (rng.uniform(0, 1, len(k1)) < 0.8).astype(np.uint8)   # 'no map point yet'
+    v2 = (rng.uniform(0, 1, len(k2)) < 0.8).astype(np.uint8)
+    st1 = (rng.uniform(0, 1, len(k1)) < 0.5).astype(np.uint8)
+    tx, ty = shift
+    Fa = np.array([[0, 0, -ty], [0, 0, tx], [ty, -tx, 0]], np.float32)          # x2' [t]x x1 = 0 for x2 = x1 + t
+    Fb = (Fa + rng.normal(0, 2e-4, (3, 3))).astype(np.float32)
+    tot = 0
+    for F12, (ex, ey) in ((Fa, (1e6, 188.0)), (Fb, (620.0, 188.0))):
+        for only_stereo in (False, True):
+            for ori in (True, False):
+                n, m = orbfe.SearchForTriangulation(F2, k1, d1, v1, st1, v2, fv1, fv2, F12, ex, ey, only_stereo, ori)
+                on, om = O.search_for_triangulation(OF2, k1, d1, v1, st1, v2, fv1, fv2, F12, ex, ey, only_stereo, ori)
+                assert n == on, f"SearchForTriangulation stereo={only_stereo} ori={ori}: {n} vs oracle {on}"
+                assert np.array_equal(m, om)
+                tot += n
+    return tot

@@ -16,6 +16,91 @@ static std::vector<uint8_t> slurp(const char* path, size_t n) {
   fclose(f);
   return v;
 }
+
+// ---- stand-ins for the reference's MapPoint / KeyFrame / Frame (only what the N1 adapters touch:
+// src/data/map_point.h, keyframe.h:64-71,147-170, frame.h:104-190) so that every adapter template is instantiated --------
+#include <map>
+#include <set>
+struct MockKeyFrame;
+struct MockMapPoint {
+  cv::Mat desc;
+  bool bad = false;
+  int nobs = 1;
+  std::set<MockKeyFrame*> in;
+  bool isBad() const { return bad; }
+  cv::Mat GetDescriptor() const { return desc; }
+  int NumObservations() const { return nobs; }
+  bool IsInKeyFrame(MockKeyFrame* kf) const { return in.count(kf) != 0; }
+  void AddObservation(MockKeyFrame* kf, size_t) { in.insert(kf); ++nobs; }
+  void Replace(MockMapPoint* by) { bad = true; by->in.insert(in.begin(), in.end()); }
+};
+struct MockKeyFrame {
+  std::vector<cv::KeyPoint> undistorted_keypoints;
+  cv::Mat descriptors;
+  std::vector<float> right_coords, scale_factors;
+  std::map<unsigned, std::vector<unsigned> > feature_vec;
+  std::vector<MockMapPoint*> mps;
+  std::vector<MockMapPoint*> GetMapPointMatches() const { return mps; }
+  MockMapPoint* GetMapPoint(size_t i) const { return mps[i]; }
+  void AddMapPoint(MockMapPoint* p, size_t i) { mps[i] = p; }
+};
+struct MockFrame {
+  std::vector<cv::KeyPoint> kps;
+  cv::Mat desc;
+  std::vector<float> ur, scale;
+  std::vector<MockMapPoint*> mps;
+  std::map<unsigned, std::vector<unsigned> > fv;
+  float w, h;
+  const std::vector<cv::KeyPoint>& GetUndistortedKeys() const { return kps; }
+  const cv::Mat& GetDescriptors() const { return desc; }
+  const std::vector<float>& StereoCoordRight() const { return ur; }
+  const std::vector<float>& ScaleFactors() const { return scale; }
+  const std::map<unsigned, std::vector<unsigned> >& GetFeatureVector() const { return fv; }
+  float GetMinX() const { return 0; }
+  float GetMaxX() const { return w; }
+  float GetMinY() const { return 0; }
+  float GetMaxY() const { return h; }
+  int NumKeypoints() const { return (int)kps.size(); }
+  MockMapPoint* GetMapPoint(int i) const { return mps[i]; }
+  void SetMapPoint(int i, MockMapPoint* p) { mps[i] = p; }
+};
+
+// KeyFrame = the extracted frame, one map point per keypoint; every routine is asked to find the frame in itself
+static int n1_selfcheck(const std::vector<cv::KeyPoint>& kps, const cv::Mat& desc, const ORBextractor& ex, int W, int H) {
+  const size_t n = kps.size();
+  std::vector<MockMapPoint> pts(n);
+  MockKeyFrame kf;
+  kf.undistorted_keypoints = kps; kf.descriptors = desc; kf.right_coords.assign(n, -1.0f); kf.scale_factors = ex.GetScaleFactors();
+  kf.mps.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    pts[i].desc = desc.row((int)i).clone();
+    kf.mps[i] = &pts[i];
+    kf.feature_vec[desc.ptr((int)i)[0] % 50u].push_back((unsigned)i);
+  }
+  MockFrame F;
+  F.kps = kps; F.desc = desc; F.scale = kf.scale_factors; F.mps.assign(n, nullptr); F.fv = kf.feature_vec; F.w = (float)W; F.h = (float)H;
+  const orbfe::ImageBounds b = {0.f, (float)W, 0.f, (float)H};
+  auto gate = [&](size_t i, float& u, float& v, int32_t& lvl) { u = kps[i].pt.x; v = kps[i].pt.y; lvl = kps[i].octave; return true; };
+  auto gate_ur = [&](size_t i, float& u, float& v, float& ur, int32_t& lvl) { ur = kps[i].pt.x - 10.f; return gate(i, u, v, lvl); };
+  std::vector<MockMapPoint*> m1, m2(n, nullptr), m3(n, nullptr), rep(n, nullptr), mpv(kf.mps);
+  const int a = orbfe::SearchByBoW(&kf, F, m1, 0.9f, true);
+  std::vector<MockMapPoint*> m12;
+  const int c = orbfe::SearchByBoW(&kf, &kf, m12, b, 0.9f, true);
+  MockKeyFrame bare = kf;                       // no map points: everything is a triangulation candidate
+  bare.mps.assign(n, nullptr);
+  const float F12[9] = {0, 0, 0, 0, 0, 1, 0, -1, 0};  // pure x-translation: epipolar lines y2 = y1
+  std::vector<std::pair<size_t, size_t> > pairs;
+  const int d = orbfe::SearchForTriangulation(&bare, &bare, F12, 1e6f, 0.f, pairs, false, b, true);
+  const int e = orbfe::SearchByProjection(&kf, mpv, m2, 10, b, gate);
+  const int f = orbfe::SearchByProjectionKeyFrame(F, &kf, 10.f, 100, true, gate);
+  const int g = orbfe::SearchBySim3(&kf, &kf, m3, 7.5f, b, gate, gate);
+  const int h2 = orbfe::Fuse(&kf, mpv, 3.f, rep, b, gate);
+  MockKeyFrame other = kf;                      // Fuse(KF, points): the points are not yet in `other`
+  const int h1 = orbfe::Fuse(&other, mpv, 3.f, b, gate_ur);
+  printf("%zu %d %d %d %d %d %d %d %d\n", n, a, c, d, e, f, g, h1, h2);
+  return 0;
+}
+
 template <class T>
 static void dump(const std::string& path, const T* p, size_t n) {
   FILE* f = fopen(path.c_str(), "wb");
@@ -27,6 +112,16 @@ int main(int argc, char** argv) {
   if (argc == 2 && std::string(argv[1]) == "--link-check") {
     printf("%s devices=%d\n", orbfe_version(), orbfe_device_count());
     return 0;
+  }
+  if (argc == 5 && std::string(argv[1]) == "--n1") {  // shim_demo --n1 W H image.raw
+    const int W = atoi(argv[2]), H = atoi(argv[3]);
+    std::vector<uint8_t> im = slurp(argv[4], (size_t)W * H);
+    cv::Mat img(H, W, CV_8UC1, im.data());
+    ORBextractor ex(1000, 1.2f, 8, 20, 7);
+    std::vector<cv::KeyPoint> k;
+    cv::Mat dsc;
+    ex(img, cv::Mat(), k, dsc);
+    return n1_selfcheck(k, dsc, ex, W, H);
   }
   if (argc != 6) return 1;
   const int W = atoi(argv[1]), H = atoi(argv[2]);

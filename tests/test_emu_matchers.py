@@ -67,3 +67,44 @@ def test_search_by_bow(emu):
     scale = O.Extractor(1200).tables()["scale"]
     assert P.check_search_by_bow(emu, kb, db, ka, da, scale, 640, 200, seed=3) > 60
     assert P.check_search_by_bow(emu, ka, da, ka, da, scale, 640, 200, seed=4, nnratio=0.75) > 300  # frame vs itself
+
+
+# ---- N1: the remaining OrbMatcher searches -----------------------------------------------------------------
+@pytest.fixture(scope="module")
+def two_frames():
+    a, b = synth.shifted_frame(7, 200, 640, dx=6, dy=0)
+    ka, da = oracle_extract(a, 1200)
+    kb, db = oracle_extract(b, 1200)
+    return ka, da, kb, db, O.Extractor(1200).tables()["scale"]
+
+
+def test_search_by_projection_sim3(emu, two_frames):
+    ka, da, _, _, scale = two_frames
+    assert P.check_search_by_projection_sim3(emu, ka, da, scale, 640, 200, 2500, seed=11) > 150
+
+
+def test_search_by_projection_keyframe(emu, two_frames):
+    ka, da, _, _, scale = two_frames
+    assert P.check_search_by_projection_keyframe(emu, ka, da, scale, 640, 200, 1500, seed=12) > 400
+
+
+def test_fuse(emu, two_frames):
+    ka, da, _, _, scale = two_frames
+    rng = np.random.default_rng(5)
+    ur = np.where(rng.uniform(0, 1, len(ka)) < 0.6, ka["x"] - rng.uniform(1, 60, len(ka)), -1).astype(np.float32)
+    assert P.check_fuse(emu, ka, da, scale, 640, 200, 2500, seed=13, u_right=ur) > 300
+
+
+def test_search_by_sim3(emu, two_frames):
+    ka, da, kb, db, scale = two_frames
+    assert P.check_search_by_sim3(emu, ka, da, kb, db, scale, 640, 200, seed=14, shift=(6.0, 0.0)) > 100
+
+
+def test_search_by_bow_keyframes(emu, two_frames):
+    ka, da, kb, db, scale = two_frames
+    assert P.check_search_by_bow_keyframes(emu, ka, da, kb, db, scale, 640, 200, seed=15) > 60
+
+
+def test_search_for_triangulation(emu, two_frames):
+    ka, da, kb, db, scale = two_frames
+    assert P.check_search_for_triangulation(emu, ka, da, kb, db, scale, 640, 200, seed=16) > 100

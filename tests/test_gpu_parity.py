@@ -204,3 +204,40 @@ def test_n1_search_by_bow_keyframe_frame(lib):
     scale = O.Extractor().tables()["scale"]
     assert P.check_search_by_bow(lib, kb, db, ka, da, scale, 1241, 376, seed=3) > 200
     assert P.check_search_by_bow(lib, ka, da, ka, da, scale, 1241, 376, seed=4, nnratio=0.75) > 1000
+
+
+@pytest.fixture(scope="module")
+def kitti_two_frames(lib):
+    import oracle_lib as O
+    a, b = synth.shifted_frame(43, dx=6, dy=0)
+    ex = gpu_extract(lib)
+    ka, da = ex(a, 2000)
+    kb, db = ex(b, 2000)
+    return ka, da, kb, db, O.Extractor().tables()["scale"]
+
+
+def test_n1_search_by_projection_loop_and_relocalisation(lib, kitti_two_frames):
+    """SearchByProjection(KF, Scw, ...) (loop closing, :384-497) and SearchByProjection(Frame, KF, ...) (relocalisation,
+    :1455-1582)"""
+    ka, da, _, _, scale = kitti_two_frames
+    assert P.check_search_by_projection_sim3(lib, ka, da, scale, 1241, 376, 6000, seed=51) > 400
+    assert P.check_search_by_projection_keyframe(lib, ka, da, scale, 1241, 376, 2500, seed=52) > 1000
+
+
+def test_n1_fuse_both_overloads(lib, kitti_two_frames):
+    """the searches of Fuse (:804-954 with the stereo chi2 gate, :956-1079 without)"""
+    ka, da, _, _, scale = kitti_two_frames
+    rng = np.random.default_rng(53)
+    ur = np.where(rng.uniform(0, 1, len(ka)) < 0.6, ka["x"] - rng.uniform(1, 60, len(ka)), -1).astype(np.float32)
+    assert P.check_fuse(lib, ka, da, scale, 1241, 376, 8000, seed=54, u_right=ur) > 1000
+
+
+def test_n1_search_by_sim3(lib, kitti_two_frames):
+    ka, da, kb, db, scale = kitti_two_frames
+    assert P.check_search_by_sim3(lib, ka, da, kb, db, scale, 1241, 376, seed=55, shift=(6.0, 0.0)) > 300
+
+
+def test_n1_search_by_bow_keyframes_and_triangulation(lib, kitti_two_frames):
+    ka, da, kb, db, scale = kitti_two_frames
+    assert P.check_search_by_bow_keyframes(lib, ka, da, kb, db, scale, 1241, 376, seed=56) > 150
+    assert P.check_search_for_triangulation(lib, ka, da, kb, db, scale, 1241, 376, seed=57) > 300

@@ -49,3 +49,17 @@ def test_shim_matches_oracle(tmp_path):
     assert np.array_equal(np.fromfile(tmp_path / "o.ur", np.float32), our)
     assert np.array_equal(np.fromfile(tmp_path / "o.depth", np.float32), odp)
     assert np.array_equal(np.fromfile(tmp_path / "o.pyr3", np.uint8).reshape(ph, pw), oL.pyramid_level(3))
+
+
+@pytest.mark.gpu
+def test_shim_n1_adapters_find_a_frame_in_itself(tmp_path):
+    """every N1 adapter of orbfe_shim.hpp (SearchByBoW x2, SearchForTriangulation, SearchByProjection x2, SearchBySim3,
+    Fuse x2) instantiated over stand-in KeyFrame / MapPoint / Frame types and run on the GPU: a frame searched in itself
+    must match (nearly) every keypoint to itself"""
+    img = synth.frame(240, 800, seed=5)
+    img.tofile(tmp_path / "i.raw")
+    out = subprocess.check_output([build_demo(), "--n1", "800", "240", str(tmp_path / "i.raw")], text=True)
+    n, bow_f, bow_kf, tri, proj_kf, proj_f, sim3, fuse1, fuse2 = map(int, out.split())
+    assert n > 500
+    for got in (bow_f, bow_kf, tri, proj_kf, proj_f, sim3, fuse1, fuse2):
+        assert got > 0.5 * n, out
