@@ -267,6 +267,30 @@ int orbfe_search_for_triangulation(orbfe_frame* kf2, int n1, const orbfe_keypoin
                                    const uint32_t* feat_idx2, const float* F12, float ex, float ey, int only_stereo,
                                    int check_orientation, int32_t* matches12, int* n_matches);
 
+/* ---- ORB vocabulary / bag of words: Frame::ComputeBoW (src/data/frame.cpp:258-263), KeyFrame::ComputeBoW
+ * (src/data/keyframe.cpp:127-137) -> DBoW2 TemplatedVocabulary<FORB>::transform(features, BowVector&, FeatureVector&,
+ * levelsup) (third_party/DBoW2/DBoW2/TemplatedVocabulary.h:1124-1250, FORB.cpp:81-101). -------------------------- */
+typedef struct orbfe_vocabulary orbfe_vocabulary;
+
+/* The tree as TemplatedVocabulary::loadFromTextFile builds it (TemplatedVocabulary.h:1335-1422): header k L scoring
+ * weighting (ScoringType / WeightingType of BowVector.h:36-53); n_nodes entries, node 0 = root (its array entries are
+ * ignored); node i >= 1: parent[i] < i, is_leaf[i] (takes the next word id), 32 descriptor bytes, weight. */
+int orbfe_vocabulary_create(int device, int k, int L, int scoring, int weighting, int n_nodes, const int32_t* parent,
+                            const uint8_t* is_leaf, const uint8_t* desc, const double* weight, orbfe_vocabulary** out);
+/* the ORBvoc.txt format read by system.cpp / loadFromTextFile */
+int orbfe_vocabulary_load_text(const char* path, int device, orbfe_vocabulary** out);
+int orbfe_vocabulary_destroy(orbfe_vocabulary* v);
+int orbfe_vocabulary_info(const orbfe_vocabulary* v, int* k, int* L, int* scoring, int* weighting, int* n_nodes, int* n_words);
+
+/* transform(): desc = n x 32 descriptor rows (host).  Per feature (optional, may be NULL): word_id[n], node_id[n] (the node
+ * `levelsup` levels above the leaves).  BowVector = bow_words[*n_bow] ascending with bow_values (after the weighting and
+ * normalisation the vocabulary's scoring asks for).  FeatureVector = fv_nodes[*n_fv] ascending, fv_start[*n_fv + 1]
+ * offsets into fv_idx (feature indices ascending inside a node) -- the flattened form orbfe_search_by_bow* take.
+ * Output capacities: n entries each (fv_start: n + 1).  Features whose word weight is 0 (stopped words) are skipped. */
+int orbfe_bow_transform(orbfe_vocabulary* v, int n, const uint8_t* desc, int levelsup, uint32_t* word_id, uint32_t* node_id,
+                        uint32_t* bow_words, double* bow_values, int* n_bow, uint32_t* fv_nodes, int32_t* fv_start,
+                        uint32_t* fv_idx, int* n_fv);
+
 #ifdef __cplusplus
 }
 #endif

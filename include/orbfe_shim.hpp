@@ -536,5 +536,48 @@ int SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMa
   return nFound;
 }
 
+// ---- OrbVocabulary: the transform path of DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>
+// (src/orb_features/orb_vocabulary.h; used by Frame::ComputeBoW frame.cpp:258-263 and KeyFrame::ComputeBoW
+// keyframe.cpp:127-137).  BowVectorT / FeatureVectorT are DBoW2::BowVector / DBoW2::FeatureVector (std::map subclasses).
+class OrbVocabulary {
+ public:
+  explicit OrbVocabulary(int device = 0) : device_(device), h_(nullptr) {}
+  ~OrbVocabulary() { orbfe_vocabulary_destroy(h_); }
+  OrbVocabulary(const OrbVocabulary&) = delete;
+  OrbVocabulary& operator=(const OrbVocabulary&) = delete;
+  bool loadFromTextFile(const std::string& filename) {  // TemplatedVocabulary.h:1335
+    orbfe_vocabulary_destroy(h_);
+    h_ = nullptr;
+    return orbfe_vocabulary_load_text(filename.c_str(), device_, &h_) == ORBFE_OK;
+  }
+  bool empty() const {
+    int words = 0;
+    return !h_ || orbfe_vocabulary_info(h_, nullptr, nullptr, nullptr, nullptr, nullptr, &words) != ORBFE_OK || words == 0;
+  }
+  // transform(features, v, fv, levelsup) (TemplatedVocabulary.h:1124); features = Converter::toDescriptorVector(descriptors_)
+  template <class BowVectorT, class FeatureVectorT>
+  void transform(const std::vector<cv::Mat>& features, BowVectorT& v, FeatureVectorT& fv, int levelsup) const {
+    v.clear();
+    fv.clear();
+    const int n = (int)features.size();
+    if (empty() || n == 0) return;
+    std::vector<uint8_t> d((size_t)n * 32);
+    for (int i = 0; i < n; ++i) std::memcpy(d.data() + (size_t)i * 32, features[i].data, 32);
+    std::vector<uint32_t> bw((size_t)n), fn((size_t)n), fi((size_t)n);
+    std::vector<double> bv((size_t)n);
+    std::vector<int32_t> fs((size_t)n + 1);
+    int nb = 0, nf = 0;
+    check(orbfe_bow_transform(h_, n, d.data(), levelsup, nullptr, nullptr, bw.data(), bv.data(), &nb, fn.data(), fs.data(), fi.data(), &nf),
+          "orbfe_bow_transform");
+    for (int u = 0; u < nb; ++u) v.insert(v.end(), typename BowVectorT::value_type(bw[u], bv[u]));
+    for (int f = 0; f < nf; ++f)
+      fv.insert(fv.end(), typename FeatureVectorT::value_type(fn[f], std::vector<unsigned int>(fi.begin() + fs[f], fi.begin() + fs[f + 1])));
+  }
+  orbfe_vocabulary* handle() const { return h_; }
+ private:
+  int device_;
+  orbfe_vocabulary* h_;
+};
+
 }  // namespace orbfe
 #endif  // ORBFE_SHIM_HPP_

@@ -1349,3 +1349,120 @@ int orc_search_for_triangulation(const orc_frame* KF2, int n1, const orc_keypoin
 }
 
 }  // extern "C"
+
+// ===========================================================================================
+// N3: DBoW2 TemplatedVocabulary<FORB>::transform (third_party/DBoW2/DBoW2/TemplatedVocabulary.h) restated with the
+// reference's own containers (BowVector = std::map<WordId, double>, FeatureVector = std::map<NodeId, vector<unsigned>>).
+#include <map>
+struct orc_vocabulary {
+  struct Node {                       // TemplatedVocabulary.h:295-322
+    double weight = 0;
+    std::vector<unsigned> children;
+    uint8_t descriptor[32] = {0};
+    unsigned word_id = 0;
+    bool isLeaf() const { return children.empty(); }
+  };
+  int k = 0, L = 0, scoring = 0, weighting = 0;
+  std::vector<Node> nodes;
+  int nwords = 0;
+};
+
+namespace {
+// transform(feature, word_id, weight, nid, levelsup) (TemplatedVocabulary.h:1198-1248)
+void voc_transform_one(const orc_vocabulary* V, const uint8_t* feature, unsigned& word_id, double& weight, unsigned* nid, int levelsup) {
+  const int nid_level = V->L - levelsup;
+  if (nid_level <= 0 && nid != nullptr) *nid = 0;  // root
+  unsigned final_id = 0;
+  int current_level = 0;
+  do {
+    ++current_level;
+    const std::vector<unsigned>& nodes = V->nodes[final_id].children;
+    final_id = nodes[0];
+    double best_d = descriptor_distance(feature, V->nodes[final_id].descriptor);  // FORB::distance (FORB.cpp:81-101)
+    for (size_t c = 1; c < nodes.size(); ++c) {
+      const unsigned id = nodes[c];
+      const double d = descriptor_distance(feature, V->nodes[id].descriptor);
+      if (d < best_d) { best_d = d; final_id = id; }
+    }
+    if (nid != nullptr && current_level == nid_level) *nid = final_id;
+  } while (!V->nodes[final_id].isLeaf());
+  word_id = V->nodes[final_id].word_id;
+  weight = V->nodes[final_id].weight;
+}
+}  // namespace
+
+extern "C" {
+
+// the tree loadFromTextFile builds (TemplatedVocabulary.h:1372-1417)
+orc_vocabulary* orc_vocabulary_create(int k, int L, int scoring, int weighting, int n_nodes, const int* parent,
+                                      const uint8_t* is_leaf, const uint8_t* desc, const double* weight) {
+  orc_vocabulary* V = new orc_vocabulary();
+  V->k = k; V->L = L; V->scoring = scoring; V->weighting = weighting;
+  V->nodes.resize(n_nodes);
+  for (int nid = 1; nid < n_nodes; ++nid) {
+    V->nodes[parent[nid]].children.push_back((unsigned)nid);
+    std::memcpy(V->nodes[nid].descriptor, desc + (size_t)nid * 32, 32);
+    V->nodes[nid].weight = weight[nid];
+    if (is_leaf[nid]) V->nodes[nid].word_id = (unsigned)V->nwords++;
+  }
+  return V;
+}
+void orc_vocabulary_destroy(orc_vocabulary* V) { delete V; }
+
+// transform(features, BowVector&, FeatureVector&, levelsup) (TemplatedVocabulary.h:1124-1190) with BowVector::addWeight /
+// addIfNotExist / normalize (BowVector.cpp:34-87) and FeatureVector::addFeature (FeatureVector.cpp:32-47).
+// Where the reference leaves `nid` unwritten (leaf above nid_level) it is indeterminate there; defined as 0 here.
+int orc_bow_transform(const orc_vocabulary* V, int n, const uint8_t* desc, int levelsup, unsigned* word_out, unsigned* node_out,
+                      unsigned* bow_words, double* bow_values, int* n_bow, unsigned* fv_nodes, int* fv_start, unsigned* fv_idx,
+                      int* n_fv) {
+  std::map<unsigned, double> v;
+  std::map<unsigned, std::vector<unsigned>> fv;
+  *n_bow = 0; *n_fv = 0; fv_start[0] = 0;
+  if (V->nwords == 0) return 0;  // empty()
+  // mustNormalize (ScoringObject.h:73-90)
+  const bool must = V->scoring != 5;
+  const bool l2 = V->scoring == 1;
+  for (int i = 0; i < n; ++i) {
+    unsigned id = 0, nid = 0;
+    double w = 0;
+    voc_transform_one(V, desc + (size_t)i * 32, id, w, &nid, levelsup);
+    if (word_out) word_out[i] = id;
+    if (node_out) node_out[i] = nid;
+    if (w > 0) {  // not stopped
+      if (V->weighting == 0 || V->weighting == 1) {  // TF_IDF, TF: addWeight
+        auto vit = v.lower_bound(id);
+        if (vit != v.end() && !(v.key_comp()(id, vit->first))) vit->second += w;
+        else v.insert(vit, std::make_pair(id, w));
+      } else {  // IDF, BINARY: addIfNotExist
+        auto vit = v.lower_bound(id);
+        if (vit == v.end() || v.key_comp()(id, vit->first)) v.insert(vit, std::make_pair(id, w));
+      }
+      fv[nid].push_back((unsigned)i);
+    }
+  }
+  if ((V->weighting == 0 || V->weighting == 1) && !v.empty() && !must) {
+    const double nd = (double)v.size();
+    for (auto& e : v) e.second /= nd;
+  }
+  if (must) {  // BowVector::normalize
+    double norm = 0.0;
+    if (!l2) { for (auto& e : v) norm += std::fabs(e.second); }
+    else { for (auto& e : v) norm += e.second * e.second; norm = std::sqrt(norm); }
+    if (norm > 0.0) for (auto& e : v) e.second /= norm;
+  }
+  int u = 0;
+  for (auto& e : v) { bow_words[u] = e.first; bow_values[u] = e.second; ++u; }
+  *n_bow = u;
+  int f = 0, p = 0;
+  for (auto& e : fv) {
+    fv_nodes[f] = e.first;
+    fv_start[f] = p;
+    for (unsigned idx : e.second) fv_idx[p++] = idx;
+    ++f;
+  }
+  fv_start[f] = p;
+  *n_fv = f;
+  return u;
+}
+
+}  // extern "C"

@@ -49,6 +49,8 @@ EXPORTS = [
     "orbfe_search_by_projection_lastframe", "orbfe_search_by_bow",
     "orbfe_search_by_projection_sim3", "orbfe_search_by_projection_keyframe", "orbfe_fuse", "orbfe_fuse_sim3",
     "orbfe_search_by_sim3", "orbfe_search_by_bow_keyframes", "orbfe_search_for_triangulation",
+    "orbfe_vocabulary_create", "orbfe_vocabulary_load_text", "orbfe_vocabulary_destroy", "orbfe_vocabulary_info",
+    "orbfe_bow_transform",
 ]
 
 _libs = {}
@@ -115,6 +117,11 @@ def load(path=None, _test_emulation=False):
     L.orbfe_search_by_sim3.argtypes = [vp, vp] + [vp] * 10 + [f, vp, vp]
     L.orbfe_search_by_bow_keyframes.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, f, i, vp, vp]
     L.orbfe_search_for_triangulation.argtypes = [vp, i, vp, vp, vp, vp, vp, i, vp, vp, vp, i, vp, vp, vp, vp, f, f, i, i, vp, vp]
+    L.orbfe_vocabulary_create.argtypes = [i, i, i, i, i, i, vp, vp, vp, vp, C.POINTER(vp)]
+    L.orbfe_vocabulary_load_text.argtypes = [C.c_char_p, i, C.POINTER(vp)]
+    L.orbfe_vocabulary_destroy.argtypes = [vp]
+    L.orbfe_vocabulary_info.argtypes = [vp] + [vp] * 6
+    L.orbfe_bow_transform.argtypes = [vp, i, vp, i] + [vp] * 9
     _libs[path] = L
     return L
 
@@ -521,3 +528,60 @@ def SearchForTriangulation(KF2, kps1, desc1, valid1, stereo1, valid2, fv1, fv2, 
                                                       _p(s1), _p(x1), len(i2), _p(i2), _p(s2), _p(x2), _p(F), float(ex), float(ey),
                                                       int(onlyStereo), int(checkOri), _p(out), C.byref(n)))
     return n.value, out
+
+
+class OrbVocabulary:
+    """Mirror of OrbVocabulary = DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB> for the transform path (SURVEY 8f N3).
+    Build it from node arrays (`parent`, `is_leaf`, `desc`, `weight`, node 0 = root) or with loadFromTextFile (ORBvoc.txt)."""
+
+    def __init__(self, k, L, scoring, weighting, parent, is_leaf, desc, weight, device=0, lib=None, _handle=None):
+        self.L_ = lib or load()
+        if _handle is not None:
+            self.h = _handle
+            return
+        parent = np.ascontiguousarray(parent, np.int32)
+        is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        weight = np.ascontiguousarray(weight, np.float64)
+        self.h = vp()
+        _check(self.L_, self.L_.orbfe_vocabulary_create(device, k, L, scoring, weighting, len(parent), _p(parent), _p(is_leaf),
+                                                       _p(desc), _p(weight), C.byref(self.h)))
+
+    @classmethod
+    def loadFromTextFile(cls, path, device=0, lib=None):
+        L = lib or load()
+        h = vp()
+        _check(L, L.orbfe_vocabulary_load_text(str(path).encode(), device, C.byref(h)))
+        return cls(0, 0, 0, 0, None, None, None, None, lib=L, _handle=h)
+
+    def info(self):
+        v = [C.c_int() for _ in range(6)]
+        _check(self.L_, self.L_.orbfe_vocabulary_info(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("k", "L", "scoring", "weighting", "nodes", "words"), [x.value for x in v]))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L_.orbfe_vocabulary_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def transform(self, desc, levelsup=4):
+        """-> dict(word_id, node_id, bow = (words, values), fv = (nodes, start, idx)); Frame::ComputeBoW uses levelsup 4"""
+        d = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        word, node = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        bw, bv = np.zeros(n, np.uint32), np.zeros(n, np.float64)
+        fn, fs, fi = np.zeros(n, np.uint32), np.zeros(n + 1, np.int32), np.zeros(n, np.uint32)
+        nb, nf = C.c_int(), C.c_int()
+        _check(self.L_, self.L_.orbfe_bow_transform(self.h, n, _p(d), int(levelsup), _p(word), _p(node), _p(bw), _p(bv), C.byref(nb),
+                                                   _p(fn), _p(fs), _p(fi), C.byref(nf)))
+        nb, nf = nb.value, nf.value
+        return dict(word_id=word, node_id=node, bow=(bw[:nb].copy(), bv[:nb].copy()),
+                    fv=(fn[:nf].copy(), fs[:nf + 1].copy(), fi[:fs[nf]].copy()))
+
+
+def feature_vector_dict(fv):
+    """flattened FeatureVector (nodes, start, idx) -> {node: [feature indices]} as orbfe.SearchByBoW* take"""
+    nodes, start, idx = fv
+    return {int(nodes[k]): [int(x) for x in idx[start[k]:start[k + 1]]] for k in range(len(nodes))}

@@ -28,4 +28,16 @@ P.check_search_by_projection_mappoints(L, kps, desc, scale, 800, 240, 3000, seed
 P.check_search_by_projection_lastframe(L, kps, desc, scale, 800, 240, seed=7, u_right=ur)
 a, b = synth.shifted_frame(3, 200, 640, dx=8, dy=4)
 P.check_search_for_initialization(L, a, b, lambda im, nf: O.Extractor(nf).extract(im), nfeatures=1500)
+# N1: the remaining OrbMatcher searches; N3: vocabulary transform
+ka, da = O.Extractor(1000).extract(a)
+kb, db = O.Extractor(1000).extract(b)
+P.check_search_by_bow(L, kb, db, ka, da, scale, 640, 200, seed=3)
+P.check_search_by_projection_sim3(L, ka, da, scale, 640, 200, 2000, seed=11)
+P.check_search_by_projection_keyframe(L, ka, da, scale, 640, 200, 1200, seed=12)
+P.check_fuse(L, ka, da, scale, 640, 200, 2000, seed=13, u_right=np.where(rng.uniform(0, 1, len(ka)) < 0.6, ka["x"] - 20, -1).astype(np.float32))
+P.check_search_by_sim3(L, ka, da, kb, db, scale, 640, 200, seed=14, shift=(8.0, 4.0))
+P.check_search_by_bow_keyframes(L, ka, da, kb, db, scale, 640, 200, seed=15)
+P.check_search_for_triangulation(L, ka, da, kb, db, scale, 640, 200, seed=16)
+P.check_bow_transform(L, da, seed=21, k=10, L=3)
+P.check_bow_transform(L, da[:257], seed=22, k=4, L=5)
 print("ASAN-RUN-OK")

@@ -71,6 +71,10 @@ def lib():
                                                   C.c_float, C.c_int, vp]
         L.orc_search_for_triangulation.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp,
                                                    vp, C.c_float, C.c_float, C.c_int, C.c_int, vp]
+        L.orc_vocabulary_create.argtypes = [C.c_int] * 5 + [vp] * 4
+        L.orc_vocabulary_create.restype = vp
+        L.orc_vocabulary_destroy.argtypes = [vp]
+        L.orc_bow_transform.argtypes = [vp, C.c_int, vp, C.c_int] + [vp] * 9
         L.orc_bench_stereo_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                              C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
         L.orc_bench_stereo_batch.restype = C.c_double
@@ -327,3 +331,27 @@ def search_for_triangulation(kf2, kps1, desc1, valid1, stereo1, valid2, fv1, fv2
                                            _p(x1), len(i2), _p(i2), _p(s2), _p(x2), _p(F), ex, ey, int(only_stereo),
                                            int(check_ori), _p(out))
     return n, out
+
+
+class Vocabulary:
+    def __init__(self, k, L, scoring, weighting, parent, is_leaf, desc, weight):
+        self.arrays = (_a(parent, np.int32), _a(is_leaf, np.uint8), _a(desc, np.uint8), _a(weight, np.float64))
+        self.h = lib().orc_vocabulary_create(k, L, scoring, weighting, len(self.arrays[0]), *[_p(x) for x in self.arrays])
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_vocabulary_destroy(self.h)
+            self.h = None
+
+    def transform(self, desc, levelsup=4):
+        d = _a(desc, np.uint8).reshape(-1, 32)
+        n = len(d)
+        word, node = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        bw, bv = np.zeros(n, np.uint32), np.zeros(n, np.float64)
+        fn, fs, fi = np.zeros(n, np.uint32), np.zeros(n + 1, np.int32), np.zeros(n, np.uint32)
+        nb, nf = C.c_int(), C.c_int()
+        lib().orc_bow_transform(self.h, n, _p(d), int(levelsup), _p(word), _p(node), _p(bw), _p(bv), C.byref(nb), _p(fn), _p(fs),
+                                _p(fi), C.byref(nf))
+        nb, nf = nb.value, nf.value
+        return dict(word_id=word, node_id=node, bow=(bw[:nb].copy(), bv[:nb].copy()),
+                    fv=(fn[:nf].copy(), fs[:nf + 1].copy(), fi[:fs[nf]].copy()))

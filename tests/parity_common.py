@@ -359,3 +359,96 @@ def check_search_for_triangulation(lib, k1, d1, k2, d2, scale, w, h, seed=0, shi
                 assert np.array_equal(m, om)
                 tot += n
     return tot
+
+
+# ---- N3: vocabulary transform (Frame::ComputeBoW) ------------------------------------------------------------
+def synth_vocabulary(rng, k=10, L=3, stop_frac=0.05, prune_frac=0.08, seed_desc=None):
+    """a random k-ary tree of depth <= L in the arrays of loadFromTextFile (node 0 = root): a child's descriptor is its
+    parent's with ~25 random bits flipped (so descents are decided by small distance gaps and ties do occur), some
+    subtrees are pruned early (leaves above level L, as k-means leaves them), some words are stopped (weight 0).  The real
+    ORBvoc.txt (k=10, L=6, ~1.08M nodes) is a missing blob; this has the same structure at test size."""
+    parent, leaf, desc, weight = [0], [0], [np.zeros(32, np.uint8)], [0.0]
+    frontier = [(0, 0, rng.integers(0, 256, 32, dtype=np.uint8) if seed_desc is None else seed_desc)]
+    while frontier:
+        nxt = []
+        for nid, lvl, d in frontier:
+            nchild = k if rng.uniform() > 0.1 else int(rng.integers(2, k + 1))
+            for _ in range(nchild):
+                cd = d.copy()
+                for b in rng.choice(256, int(rng.integers(10, 40)), replace=False):
+                    cd[b >> 3] ^= np.uint8(1 << (b & 7))
+                cid = len(parent)
+                is_leaf = (lvl + 1 == L) or (lvl + 1 >= 1 and rng.uniform() < prune_frac)
+                parent.append(nid); leaf.append(1 if is_leaf else 0); desc.append(cd)
+                weight.append(0.0 if (is_leaf and rng.uniform() < stop_frac) else (float(rng.uniform(0.1, 9.0)) if is_leaf else 0.0))
+                if not is_leaf:
+                    nxt.append((cid, lvl + 1, cd))
+        frontier = nxt
+    # loadFromTextFile appends nodes in file order; parents must precede children (true for ORBvoc.txt and here)
+    return (np.array(parent, np.int32), np.array(leaf, np.uint8), np.stack(desc), np.array(weight, np.float64))
+
+
+def write_vocabulary_text(path, k, L, scoring, weighting, arrays):
+    parent, leaf, desc, weight = arrays
+    with open(path, "w") as f:
+        f.write(f"{k} {L} {scoring} {weighting}\n")
+        for i in range(1, len(parent)):
+            f.write(f"{parent[i]} {leaf[i]} " + " ".join(str(int(b)) for b in desc[i]) + f" {float(weight[i])!r}\n")
+
+
+def assert_bow_equal(got, ref, what=""):
+    for key in ("word_id", "node_id"):
+        assert np.array_equal(got[key], ref[key]), f"{what}: {key} differs"
+    assert np.array_equal(got["bow"][0], ref["bow"][0]), f"{what}: BowVector words differ"
+    assert np.array_equal(got["bow"][1], ref["bow"][1]), f"{what}: BowVector values are not bit-identical"
+    for j, name in enumerate(("nodes", "start", "idx")):
+        assert np.array_equal(got["fv"][j], ref["fv"][j]), f"{what}: FeatureVector {name} differ"
+
+
+def check_bow_transform(lib, desc, seed=0, k=10, L=3, tmp_path=None):
+    """every weighting x the three normalisations, levelsup in (0, 1, 2, L, L+1); optionally through the text file"""
+    rng = np.random.default_rng(seed)
+    arrays = synth_vocabulary(rng, k, L, seed_desc=desc[0].copy() if len(desc) else None)
+    words = 0
+    for scoring, weighting in ((0, 0), (1, 0), (5, 0), (0, 1), (5, 1), (0, 2), (1, 3)):
+        V = orbfe.OrbVocabulary(k, L, scoring, weighting, *arrays, lib=lib)
+        OV = O.Vocabulary(k, L, scoring, weighting, *arrays)
+        assert V.info()["nodes"] == len(arrays[0]) and V.info()["words"] == int(arrays[1].sum())
+        for levelsup in (0, 1, 2, L, L + 1):
+            got, ref = V.transform(desc, levelsup), OV.transform(desc, levelsup)
+            assert_bow_equal(got, ref, f"scoring {scoring} weighting {weighting} levelsup {levelsup}")
+        words += len(ref["bow"][0])
+        if scoring in (0, 1) and len(ref["bow"][1]):
+            nrm = np.abs(ref["bow"][1]).sum() if scoring == 0 else np.sqrt((ref["bow"][1] ** 2).sum())
+            assert abs(nrm - 1.0) < 1e-9
+        V.close()
+    if tmp_path is not None:
+        path = str(tmp_path / "voc.txt")
+        write_vocabulary_text(path, k, L, 0, 0, arrays)
+        V = orbfe.OrbVocabulary.loadFromTextFile(path, lib=lib)
+        assert_bow_equal(V.transform(desc, 1), O.Vocabulary(k, L, 0, 0, *arrays).transform(desc, 1), "text file")
+        V.close()
+    return words
+
+
+def synth_vocabulary_uniform(rng, k=10, L=6, seed_desc=None, flip_bits=24):
+    """ORBvoc-sized uniform k-ary tree (k=10, L=6 -> 1 111 111 nodes, 10^6 words) built level by level with numpy;
+    same array format as synth_vocabulary"""
+    root = rng.integers(0, 256, 32, dtype=np.uint8) if seed_desc is None else seed_desc
+    parent, leaf, desc, weight = [np.zeros(1, np.int32)], [np.zeros(1, np.uint8)], [np.zeros((1, 32), np.uint8)], [np.zeros(1)]
+    prev_ids, prev_desc, next_id = np.zeros(1, np.int64), root[None, :], 1
+    for lvl in range(1, L + 1):
+        n = len(prev_ids) * k
+        par = np.repeat(prev_ids, k)
+        bits = rng.integers(0, 256, (n, flip_bits))
+        mask = np.zeros((n, 32), np.uint8)
+        np.bitwise_or.at(mask, (np.repeat(np.arange(n), flip_bits), (bits >> 3).ravel()), (1 << (bits & 7)).astype(np.uint8).ravel())
+        d = np.repeat(prev_desc, k, axis=0) ^ mask
+        ids = np.arange(next_id, next_id + n, dtype=np.int64)
+        # node ids must follow loadFromTextFile order (a parent precedes its children): level order satisfies it
+        parent.append(par.astype(np.int32)); desc.append(d)
+        is_leaf = lvl == L
+        leaf.append(np.full(n, 1 if is_leaf else 0, np.uint8))
+        weight.append(rng.uniform(0.1, 12.0, n) * (rng.uniform(0, 1, n) > 0.01) if is_leaf else np.zeros(n))
+        prev_ids, prev_desc, next_id = ids, d, next_id + n
+    return (np.concatenate(parent), np.concatenate(leaf), np.concatenate(desc), np.concatenate(weight).astype(np.float64))

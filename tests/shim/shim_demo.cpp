@@ -101,6 +101,23 @@ static int n1_selfcheck(const std::vector<cv::KeyPoint>& kps, const cv::Mat& des
   return 0;
 }
 
+// Frame::ComputeBoW through the shim's OrbVocabulary: prints |BowVector|, |FeatureVector|, sum of the BoW values
+static int bow_check(const char* vocfile, const cv::Mat& desc) {
+  orbfe::OrbVocabulary voc;
+  if (!voc.loadFromTextFile(vocfile)) { fprintf(stderr, "%s\n", orbfe_last_error()); return 3; }
+  std::vector<cv::Mat> rows;
+  for (int i = 0; i < desc.rows; ++i) rows.push_back(desc.row(i));
+  std::map<unsigned, double> bow;
+  std::map<unsigned, std::vector<unsigned> > fv;
+  voc.transform(rows, bow, fv, 1);
+  double sum = 0;
+  size_t nfeat = 0;
+  for (std::map<unsigned, double>::const_iterator it = bow.begin(); it != bow.end(); ++it) sum += it->second;
+  for (std::map<unsigned, std::vector<unsigned> >::const_iterator it = fv.begin(); it != fv.end(); ++it) nfeat += it->second.size();
+  printf("%zu %zu %zu %.17g\n", bow.size(), fv.size(), nfeat, sum);
+  return 0;
+}
+
 template <class T>
 static void dump(const std::string& path, const T* p, size_t n) {
   FILE* f = fopen(path.c_str(), "wb");
@@ -122,6 +139,16 @@ int main(int argc, char** argv) {
     cv::Mat dsc;
     ex(img, cv::Mat(), k, dsc);
     return n1_selfcheck(k, dsc, ex, W, H);
+  }
+  if (argc == 6 && std::string(argv[1]) == "--bow") {  // shim_demo --bow W H image.raw voc.txt
+    const int W = atoi(argv[2]), H = atoi(argv[3]);
+    std::vector<uint8_t> im = slurp(argv[4], (size_t)W * H);
+    cv::Mat img(H, W, CV_8UC1, im.data());
+    ORBextractor ex(1000, 1.2f, 8, 20, 7);
+    std::vector<cv::KeyPoint> k;
+    cv::Mat dsc;
+    ex(img, cv::Mat(), k, dsc);
+    return bow_check(argv[5], dsc);
   }
   if (argc != 6) return 1;
   const int W = atoi(argv[1]), H = atoi(argv[2]);

@@ -108,3 +108,24 @@ def test_search_by_bow_keyframes(emu, two_frames):
 def test_search_for_triangulation(emu, two_frames):
     ka, da, kb, db, scale = two_frames
     assert P.check_search_for_triangulation(emu, ka, da, kb, db, scale, 640, 200, seed=16) > 100
+
+
+# ---- N3: Frame::ComputeBoW -----------------------------------------------------------------------------------
+def test_bow_transform(emu, two_frames, tmp_path):
+    ka, da, _, _, _ = two_frames
+    assert P.check_bow_transform(emu, da, seed=21, k=10, L=3, tmp_path=tmp_path) > 1000
+    assert P.check_bow_transform(emu, da[:300], seed=22, k=4, L=5) > 300
+
+
+def test_bow_transform_degenerate(emu):
+    rng = np.random.default_rng(3)
+    arrays = P.synth_vocabulary(rng, 3, 2)
+    V = orbfe.OrbVocabulary(3, 2, 0, 0, *arrays, lib=emu)
+    out = V.transform(np.zeros((0, 32), np.uint8))
+    assert len(out["bow"][0]) == 0 and len(out["fv"][0]) == 0
+    one = rng.integers(0, 256, (1, 32), dtype=np.uint8)
+    P.assert_bow_equal(V.transform(one, 1), O.Vocabulary(3, 2, 0, 0, *arrays).transform(one, 1))
+    # all words stopped: nothing survives
+    arrays0 = (arrays[0], arrays[1], arrays[2], np.zeros_like(arrays[3]))
+    out = orbfe.OrbVocabulary(3, 2, 0, 0, *arrays0, lib=emu).transform(rng.integers(0, 256, (50, 32), dtype=np.uint8))
+    assert len(out["bow"][0]) == 0 and len(out["fv"][0]) == 0

@@ -241,3 +241,30 @@ def test_n1_search_by_bow_keyframes_and_triangulation(lib, kitti_two_frames):
     ka, da, kb, db, scale = kitti_two_frames
     assert P.check_search_by_bow_keyframes(lib, ka, da, kb, db, scale, 1241, 376, seed=56) > 150
     assert P.check_search_for_triangulation(lib, ka, da, kb, db, scale, 1241, 376, seed=57) > 300
+
+
+def test_n3_bow_transform_orbvoc_sized_vocabulary(lib, kitti_two_frames, tmp_path):
+    """SURVEY 8f N3: Frame::ComputeBoW = DBoW2 transform(features, BowVector, FeatureVector, 4) on a k=10, L=6 tree
+    (the shape of ORBvoc.txt, which is a missing blob) + the small irregular trees and the text-file loader"""
+    import oracle_lib as O
+    ka, da, kb, db, _ = kitti_two_frames
+    rng = np.random.default_rng(61)
+    arrays = P.synth_vocabulary_uniform(rng, 10, 6, seed_desc=da[0].copy())
+    assert len(arrays[0]) == 1111111
+    V = orbfe.OrbVocabulary(10, 6, 0, 0, *arrays, lib=lib)
+    OV = O.Vocabulary(10, 6, 0, 0, *arrays)
+    for d in (da, db):
+        got, ref = V.transform(d, 4), OV.transform(d, 4)
+        P.assert_bow_equal(got, ref, "ORBvoc-sized")
+        assert len(ref["bow"][0]) > 100 and len(ref["fv"][0]) > 20
+    # the FeatureVectors drive SearchByBoW exactly as Tracking::TrackReferenceKeyFrame does (tracker.cpp:657-694)
+    fa, fb = orbfe.feature_vector_dict(V.transform(da, 4)["fv"]), orbfe.feature_vector_dict(V.transform(db, 4)["fv"])
+    scale = O.Extractor().tables()["scale"]
+    F, OF = P.make_frames(kb, db, scale, 1241, 376, lib)
+    valid = np.ones(len(ka), np.uint8)
+    n, m = orbfe.SearchByBoW(F, da, ka["angle"], valid, fa, fb, 0.7, True)
+    on, om = O.search_by_bow(OF, da, ka["angle"], valid, fa, fb, 0.7, True)
+    assert n == on and np.array_equal(m, om)
+    V.close()
+    assert P.check_bow_transform(lib, da, seed=62, k=10, L=3, tmp_path=tmp_path) > 1000
+    assert P.check_bow_transform(lib, db[:500], seed=63, k=4, L=5) > 300

@@ -63,3 +63,24 @@ def test_shim_n1_adapters_find_a_frame_in_itself(tmp_path):
     assert n > 500
     for got in (bow_f, bow_kf, tri, proj_kf, proj_f, sim3, fuse1, fuse2):
         assert got > 0.5 * n, out
+
+
+@pytest.mark.gpu
+def test_shim_vocabulary_transform(tmp_path):
+    """orbfe::OrbVocabulary (loadFromTextFile + transform into std::map containers) == the oracle"""
+    import oracle_lib as O
+    import parity_common as P
+    img = synth.frame(240, 800, seed=6)
+    img.tofile(tmp_path / "i.raw")
+    kps, desc = O.Extractor(1000).extract(img)
+    rng = np.random.default_rng(9)
+    arrays = P.synth_vocabulary(rng, 10, 3, seed_desc=desc[0].copy())
+    P.write_vocabulary_text(str(tmp_path / "voc.txt"), 10, 3, 0, 0, arrays)
+    out = subprocess.check_output([build_demo(), "--bow", "800", "240", str(tmp_path / "i.raw"), str(tmp_path / "voc.txt")], text=True)
+    nb, nf, nfeat, total = out.split()
+    ref = O.Vocabulary(10, 3, 0, 0, *arrays).transform(desc, 1)
+    assert int(nb) == len(ref["bow"][0]) and int(nf) == len(ref["fv"][0]) and int(nfeat) == len(ref["fv"][2])
+    s = 0.0
+    for v in ref["bow"][1]:
+        s += float(v)
+    assert float(total) == s

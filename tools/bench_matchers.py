@@ -80,6 +80,43 @@ def main():
                                   "search_by_projection_lastframe_ms_cpu_oracle_1thread": med(lambda: O.search_by_projection_lastframe(OF, *la, True), 5),
                                   "frame_create_ms_gpu": med(lambda: orbfe.Frame(kl, dl, ex2.GetScaleFactors(), (0, 1241, 0, 376), lib=L).close(), a.reps),
                                   "matches": n}
+    # N1 / N3: the other searches and the vocabulary transform on KITTI-sized keyframes (2000 features)
+    a_img, b_img = synth.shifted_frame(43, dx=6, dy=0)
+    ka, da = ex2.Compute(a_img); kb, db = ex2.Compute(b_img)
+    scale = ex2.GetScaleFactors()
+    FA, OFA = P.make_frames(ka, da, scale, 1241, 376, L); FB, OFB = P.make_frames(kb, db, scale, 1241, 376, L)
+    rng = np.random.default_rng(5)
+    mp = P._proj_points(ka, da, rng, 6000)
+    ur = (mp["u"] - rng.uniform(0, 40, 6000)).astype(np.float32)
+    fu = (mp["valid"], mp["u"], mp["v"], ur, mp["lvl"], mp["desc"], 3.0)
+    assert np.array_equal(orbfe.Fuse(FA, *fu)[1], O.fuse(OFA, *fu)[1])
+    matched_in = np.zeros(len(ka), np.uint8)
+    sp = (mp["valid"], mp["u"], mp["v"], mp["lvl"], mp["desc"], matched_in, 10)
+    assert np.array_equal(orbfe.SearchByProjectionSim3(FA, *sp)[1], O.search_by_projection_sim3(OFA, *sp)[1])
+    varr = P.synth_vocabulary_uniform(np.random.default_rng(61), 10, 6, seed_desc=da[0].copy())
+    V, OV = orbfe.OrbVocabulary(10, 6, 0, 0, *varr, lib=L), O.Vocabulary(10, 6, 0, 0, *varr)
+    ta, tb = V.transform(da, 4), V.transform(db, 4)
+    P.assert_bow_equal(ta, OV.transform(da, 4))
+    fva, fvb = orbfe.feature_vector_dict(ta["fv"]), orbfe.feature_vector_dict(tb["fv"])
+    ones_a, ones_b = np.ones(len(ka), np.uint8), np.ones(len(kb), np.uint8)
+    bk = (da, ka["angle"], ones_a, ones_b, fva, fvb, 0.8, True)
+    assert np.array_equal(orbfe.SearchByBoWKeyFrames(FB, *bk)[1], O.search_by_bow_keyframes(OFB, *bk)[1])
+    F12 = np.array([[0, 0, 0], [0, 0, 6.0], [0, -6.0, 0]], np.float32)
+    tr = (ka, da, ones_a, np.zeros(len(ka), np.uint8), ones_b, fva, fvb, F12, 1e6, 188.0, False, True)
+    assert np.array_equal(orbfe.SearchForTriangulation(FB, *tr)[1], O.search_for_triangulation(OFB, *tr)[1])
+    out["n1_n3_kitti_2000"] = {
+        "bow_transform_k10_L6_ms_gpu": med(lambda: V.transform(da, 4), a.reps),
+        "bow_transform_k10_L6_ms_cpu_oracle_1thread": med(lambda: OV.transform(da, 4), 5),
+        "fuse_6000pts_ms_gpu": med(lambda: orbfe.Fuse(FA, *fu), a.reps),
+        "fuse_6000pts_ms_cpu_oracle_1thread": med(lambda: O.fuse(OFA, *fu), 5),
+        "search_by_projection_sim3_6000pts_ms_gpu": med(lambda: orbfe.SearchByProjectionSim3(FA, *sp), a.reps),
+        "search_by_projection_sim3_6000pts_ms_cpu_oracle_1thread": med(lambda: O.search_by_projection_sim3(OFA, *sp), 5),
+        "search_by_bow_keyframes_ms_gpu": med(lambda: orbfe.SearchByBoWKeyFrames(FB, *bk), a.reps),
+        "search_by_bow_keyframes_ms_cpu_oracle_1thread": med(lambda: O.search_by_bow_keyframes(OFB, *bk), 5),
+        "search_for_triangulation_ms_gpu": med(lambda: orbfe.SearchForTriangulation(FB, *tr), a.reps),
+        "search_for_triangulation_ms_cpu_oracle_1thread": med(lambda: O.search_for_triangulation(OFB, *tr), 5),
+        "note": "wall clock of one C-ABI call, host arrays in/out (includes H2D/D2H and the flattening of the feature vectors "
+                "in the Python wrapper on both arms)"}
     print(json.dumps(out))
 
 
