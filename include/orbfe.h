@@ -291,6 +291,28 @@ int orbfe_bow_transform(orbfe_vocabulary* v, int n, const uint8_t* desc, int lev
                         uint32_t* bow_words, double* bow_values, int* n_bow, uint32_t* fv_nodes, int32_t* fv_start,
                         uint32_t* fv_idx, int* n_fv);
 
+/* ---- the Frame tail ------------------------------------------------------------------------------- */
+/* Frame::UndistortKeyPoints (src/data/frame.cpp:614-641): cv::undistortPoints(mat, mat, K, dist, cv::Mat(), K) on the
+ * keypoint coordinates, every other cv::KeyPoint field copied.  (fx, fy, cx, cy) = calib_mat_ (CV_32F); dist_coeffs =
+ * dist_coeff_ (k1 k2 p1 p2 [k3 ...], up to 12 used; a tilted-sensor model is rejected).  dist_coeffs[0] == 0 copies the
+ * keypoints unchanged, as the reference does (:616-619). */
+int orbfe_undistort_keypoints(int device, int n, const orbfe_keypoint* kps, float fx, float fy, float cx, float cy,
+                              const float* dist_coeffs, int n_dist, orbfe_keypoint* kps_un);
+
+/* Frame::IsInFrustum (src/data/frame.cpp:277-337) + MapPoint::PredictScale (src/data/map_point.cpp:382-396) for n map
+ * points in one launch = the loop of Tracker::SearchLocalPoints (src/core/tracker.cpp:1196-1211).  world_pos / normal:
+ * n x 3 floats (GetWorldPos / GetNormal); min_dist / max_dist = Get{Min,Max}DistanceInvariance(); Rcw (row-major 3x3),
+ * tcw, Ow = the frame pose (frame.cpp:270-275).  Outputs = the track_* fields (:328-334), zero where in_view[i] == 0;
+ * they are the arrays orbfe_search_by_projection_mappoints takes.  AssignFeaturesToGrid (frame.cpp:234-248), the third
+ * piece of this row, is the grid orbfe_frame_create builds on the device. */
+int orbfe_is_in_frustum(int device, int n, const float* world_pos, const float* normal, const float* min_dist,
+                        const float* max_dist, const float* Rcw, const float* tcw, const float* Ow, float fx, float fy,
+                        float cx, float cy, float bf, float min_x, float max_x, float min_y, float max_y,
+                        float log_scale_factor, int n_levels, float viewing_cos_limit, uint8_t* in_view, float* proj_x,
+                        float* proj_y, float* proj_xr, int32_t* scale_level, float* view_cos, int* n_in_view);
+/* parity tap: std::log(float) as PredictScale evaluates it (glibc logf restated on the device), y[i] = logf(x[i]) */
+int orbfe_debug_logf(int device, int n, const float* x, float* y);
+
 #ifdef __cplusplus
 }
 #endif

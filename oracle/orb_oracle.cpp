@@ -1466,3 +1466,97 @@ int orc_bow_transform(const orc_vocabulary* V, int n, const uint8_t* desc, int l
 }
 
 }  // extern "C"
+
+// ===========================================================================================
+// N2: the Frame tail -- Frame::UndistortKeyPoints (frame.cpp:614-641) and Frame::IsInFrustum (frame.cpp:277-337)
+// with MapPoint::PredictScale (map_point.cpp:382-396).  The cv::Mat arithmetic is restated from OpenCV and pinned
+// against cv2 (tests/golden/cv2_frame_tail.npz): gemm 3x3 * 3x1 + 3x1 in float (products and sums in float, in k
+// order), cv::norm with a double accumulator; Mat::dot (double accumulator, not exposed through cv2) is restated
+// from modules/core/src/matmul (dotProd_) and is unpinned.
+extern "C" {
+
+// cv::undistortPoints(src, dst, K, dist, cv::Mat(), K) for CV_32FC2 points (calib3d cvUndistortPointsInternal, 5 fixed
+// iterations, double arithmetic); K = fx, fy, cx, cy as floats (calib_mat_ is CV_32F); dist = n_dist (4, 5, 8, 12 or 14)
+// float coefficients k1 k2 p1 p2 [k3 [k4 k5 k6 [s1 s2 s3 s4 [tauX tauY]]]] (tilt must be 0).
+// Frame::UndistortKeyPoints copies the keypoints unchanged when dist[0] == 0 (frame.cpp:616-619).
+void orc_undistort_points(int n, const float* xy_in, float fxf, float fyf, float cxf, float cyf, const float* dist, int n_dist,
+                          float* xy_out) {
+  if (n_dist < 1 || dist[0] == 0.0f) { std::memcpy(xy_out, xy_in, (size_t)n * 2 * sizeof(float)); return; }
+  double k[14] = {0};
+  for (int i = 0; i < n_dist && i < 14; ++i) k[i] = dist[i];
+  const double fx = fxf, fy = fyf, cx = cxf, cy = cyf, ifx = 1. / fx, ify = 1. / fy;
+  // RR = P * R with R = I and P = K (cvMatMul on 3x3 doubles: sum over k in order; zeros and ones are exact)
+  const double RR[3][3] = {{fx, 0, cx}, {0, fy, cy}, {0, 0, 1}};
+  for (int i = 0; i < n; ++i) {
+    double x = xy_in[2 * i], y = xy_in[2 * i + 1];
+    const double u = x, v = y;
+    x = (x - cx) * ifx;
+    y = (y - cy) * ify;
+    const double x0 = x, y0 = y;  // the tilt compensation is the identity for tauX = tauY = 0
+    for (int j = 0; j < 5; ++j) {
+      const double r2 = x * x + y * y;
+      const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+      if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+      const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+      const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+      x = (x0 - deltaX) * icdist;
+      y = (y0 - deltaY) * icdist;
+    }
+    const double xx = RR[0][0] * x + RR[0][1] * y + RR[0][2];
+    const double yy = RR[1][0] * x + RR[1][1] * y + RR[1][2];
+    const double ww = 1. / (RR[2][0] * x + RR[2][1] * y + RR[2][2]);
+    xy_out[2 * i] = (float)(xx * ww);
+    xy_out[2 * i + 1] = (float)(yy * ww);
+  }
+}
+
+// Frame::IsInFrustum for n map points (the loop of Tracker::SearchLocalPoints, core/tracker.cpp:1196-1211).
+// world/normal: n x 3; Rcw row-major; outputs = the track_* fields (frame.cpp:328-334).  Returns the number in view.
+int orc_is_in_frustum(int n, const float* world, const float* normal, const float* min_dist, const float* max_dist,
+                      const float* Rcw, const float* tcw, const float* Ow, float fx, float fy, float cx, float cy, float bf,
+                      float min_x, float max_x, float min_y, float max_y, float log_scale_factor, int n_levels,
+                      float viewing_cos_limit, uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* level,
+                      float* view_cos) {
+  int count = 0;
+  for (int i = 0; i < n; ++i) {
+    in_view[i] = 0; proj_x[i] = 0; proj_y[i] = 0; proj_xr[i] = 0; level[i] = 0; view_cos[i] = 0;
+    const float* P = world + 3 * (size_t)i;
+    float Pc[3];
+    for (int r = 0; r < 3; ++r) {  // Rcw_*P + tcw_ (cv::gemm small-matrix path: float products, float sums)
+      const float t0 = Rcw[3 * r] * P[0] + Rcw[3 * r + 1] * P[1] + Rcw[3 * r + 2] * P[2];
+      Pc[r] = (float)((double)t0 * 1.0 + (double)tcw[r] * 1.0);
+    }
+    const float PcX = Pc[0], PcY = Pc[1], PcZ = Pc[2];
+    if (PcZ < 0.0f) continue;
+    const float invz = 1.0f / PcZ;
+    const float u = fx * PcX * invz + cx;
+    const float v = fy * PcY * invz + cy;
+    if (u < min_x || u > max_x) continue;
+    if (v < min_y || v > max_y) continue;
+    const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+    double s = 0;  // cv::norm(PO): normL2Sqr with a double accumulator, then sqrt
+    for (int c = 0; c < 3; ++c) { const double e = PO[c]; s += e * e; }
+    const float dist = (float)std::sqrt(s);
+    if (dist < min_dist[i] || dist > max_dist[i]) continue;
+    const float* Pn = normal + 3 * (size_t)i;
+    double dot = 0;  // Mat::dot: dotProd_ accumulates (double)a*b
+    for (int c = 0; c < 3; ++c) dot += (double)PO[c] * Pn[c];
+    const float viewCos = (float)(dot / dist);
+    if (viewCos < viewing_cos_limit) continue;
+    // MapPoint::PredictScale (map_point.cpp:382-396)
+    const float ratio = max_dist[i] / dist;
+    int nScale = (int)std::ceil(std::log(ratio) / log_scale_factor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= n_levels) nScale = n_levels - 1;
+    in_view[i] = 1;
+    proj_x[i] = u;
+    proj_xr[i] = u - bf * invz;
+    proj_y[i] = v;
+    level[i] = nScale;
+    view_cos[i] = viewCos;
+    ++count;
+  }
+  return count;
+}
+
+}  // extern "C"

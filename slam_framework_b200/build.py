@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "liborbfe.so")
-SOURCES = ["orbfe_api.cu", "orbfe_match.cu", "orbfe_bow.cu"]
+SOURCES = ["orbfe_api.cu", "orbfe_match.cu", "orbfe_bow.cu", "orbfe_frame.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",            # IEEE parity with the reference's CPU path: no fused multiply-add

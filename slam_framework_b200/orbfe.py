@@ -50,7 +50,7 @@ EXPORTS = [
     "orbfe_search_by_projection_sim3", "orbfe_search_by_projection_keyframe", "orbfe_fuse", "orbfe_fuse_sim3",
     "orbfe_search_by_sim3", "orbfe_search_by_bow_keyframes", "orbfe_search_for_triangulation",
     "orbfe_vocabulary_create", "orbfe_vocabulary_load_text", "orbfe_vocabulary_destroy", "orbfe_vocabulary_info",
-    "orbfe_bow_transform",
+    "orbfe_bow_transform", "orbfe_undistort_keypoints", "orbfe_is_in_frustum", "orbfe_debug_logf",
 ]
 
 _libs = {}
@@ -122,6 +122,9 @@ def load(path=None, _test_emulation=False):
     L.orbfe_vocabulary_destroy.argtypes = [vp]
     L.orbfe_vocabulary_info.argtypes = [vp] + [vp] * 6
     L.orbfe_bow_transform.argtypes = [vp, i, vp, i] + [vp] * 9
+    L.orbfe_undistort_keypoints.argtypes = [i, i, vp, f, f, f, f, vp, i, vp]
+    L.orbfe_is_in_frustum.argtypes = [i, i] + [vp] * 7 + [f] * 10 + [i, f] + [vp] * 7
+    L.orbfe_debug_logf.argtypes = [i, i, vp, vp]
     _libs[path] = L
     return L
 
@@ -585,3 +588,38 @@ def feature_vector_dict(fv):
     """flattened FeatureVector (nodes, start, idx) -> {node: [feature indices]} as orbfe.SearchByBoW* take"""
     nodes, start, idx = fv
     return {int(nodes[k]): [int(x) for x in idx[start[k]:start[k + 1]]] for k in range(len(nodes))}
+
+
+def UndistortKeyPoints(kps, fx, fy, cx, cy, dist_coeffs, device=0, lib=None):
+    """Frame::UndistortKeyPoints (frame.cpp:614-641) -> undistorted_keypoints_ (same dtype as kps)"""
+    L = lib or load()
+    k = np.ascontiguousarray(kps, KP_DTYPE)
+    d = np.ascontiguousarray(dist_coeffs, np.float32)
+    out = np.zeros_like(k)
+    _check(L, L.orbfe_undistort_keypoints(device, len(k), _p(k), fx, fy, cx, cy, _p(d), len(d), _p(out)))
+    return out
+
+
+def IsInFrustum(world, normal, min_dist, max_dist, Rcw, tcw, Ow, fx, fy, cx, cy, bf, bounds, log_scale_factor, n_levels,
+                viewingCosLimit=0.5, device=0, lib=None):
+    """Frame::IsInFrustum over a batch (frame.cpp:277-337) -> (n_in_view, dict of the track_* arrays)"""
+    L = lib or load()
+    w, nrm = _a(world, np.float32).reshape(-1, 3), _a(normal, np.float32).reshape(-1, 3)
+    n = len(w)
+    out = dict(in_view=np.zeros(n, np.uint8), proj_x=np.zeros(n, np.float32), proj_y=np.zeros(n, np.float32),
+               proj_xr=np.zeros(n, np.float32), level=np.zeros(n, np.int32), view_cos=np.zeros(n, np.float32))
+    cnt = C.c_int()
+    _check(L, L.orbfe_is_in_frustum(device, n, _p(w), _p(nrm), _p(_a(min_dist, np.float32)), _p(_a(max_dist, np.float32)),
+                                    _p(_a(Rcw, np.float32).reshape(9)), _p(_a(tcw, np.float32).reshape(3)),
+                                    _p(_a(Ow, np.float32).reshape(3)), fx, fy, cx, cy, bf, bounds[0], bounds[1], bounds[2], bounds[3],
+                                    log_scale_factor, n_levels, viewingCosLimit, _p(out["in_view"]), _p(out["proj_x"]),
+                                    _p(out["proj_y"]), _p(out["proj_xr"]), _p(out["level"]), _p(out["view_cos"]), C.byref(cnt)))
+    return cnt.value, out
+
+
+def debug_logf(x, device=0, lib=None):
+    L = lib or load()
+    x = _a(x, np.float32)
+    y = np.zeros_like(x)
+    _check(L, L.orbfe_debug_logf(device, len(x), _p(x), _p(y)))
+    return y

@@ -40,4 +40,7 @@ P.check_search_by_bow_keyframes(L, ka, da, kb, db, scale, 640, 200, seed=15)
 P.check_search_for_triangulation(L, ka, da, kb, db, scale, 640, 200, seed=16)
 P.check_bow_transform(L, da, seed=21, k=10, L=3)
 P.check_bow_transform(L, da[:257], seed=22, k=4, L=5)
+# N2: the Frame tail
+P.check_undistort_keypoints(L, ka, seed=31)
+P.check_is_in_frustum(L, 5000, seed=32)
 print("ASAN-RUN-OK")

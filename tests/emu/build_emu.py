@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "slam_framework_b200", "csrc")
 LIB = os.path.join(HERE, "liborbfe_emu_TESTONLY.so")
-SOURCES = ["orbfe_api.cu", "orbfe_match.cu", "orbfe_bow.cu"]
+SOURCES = ["orbfe_api.cu", "orbfe_match.cu", "orbfe_bow.cu", "orbfe_frame.cu"]
 
 
 def build(force=False):

@@ -452,3 +452,87 @@ def synth_vocabulary_uniform(rng, k=10, L=6, seed_desc=None, flip_bits=24):
         weight.append(rng.uniform(0.1, 12.0, n) * (rng.uniform(0, 1, n) > 0.01) if is_leaf else np.zeros(n))
         prev_ids, prev_desc, next_id = ids, d, next_id + n
     return (np.concatenate(parent), np.concatenate(leaf), np.concatenate(desc), np.concatenate(weight).astype(np.float64))
+
+
+# ---- N2: the Frame tail ------------------------------------------------------------------------------------------
+def check_undistort_keypoints(lib, kps, seed=0):
+    rng = np.random.default_rng(seed)
+    cams = [(718.856, 718.856, 607.1928, 185.2157, [-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05]),
+            (517.306408, 516.469215, 318.643040, 255.313989, [0.262383, -0.953104, -0.005358, 0.002628, 1.163314]),
+            (458.654, 457.296, 367.215, 248.375, [-0.2834, 0.0739, 0.00019, 1.76e-05, 0.0, 0.01, -0.02, 0.003]),
+            (400.0, 410.0, 320.0, 240.0, [0.9, -2.0, 0.01, 0.01, 5.0]),      # reaches the icdist < 0 branch
+            (718.856, 718.856, 607.1928, 185.2157, [0.0, 0.0, 0.0, 0.0])]     # KITTI: identity short-circuit
+    k = kps.copy()
+    k["x"] += rng.uniform(-0.5, 0.5, len(k)).astype(np.float32)  # sub-pixel coordinates as well
+    for fx, fy, cx, cy, dist in cams:
+        got = orbfe.UndistortKeyPoints(k, fx, fy, cx, cy, dist, lib=lib)
+        ref = O.undistort_points(np.stack([k["x"], k["y"]], 1), fx, fy, cx, cy, dist)
+        assert np.array_equal(got["x"], ref[:, 0]) and np.array_equal(got["y"], ref[:, 1]), f"undistort {dist}"
+        for f in ("size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(got[f], k[f])
+    return len(k)
+
+
+def synth_local_map(rng, n, fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, w=1241, h=376):
+    """a camera pose + n local map points: most in front of the camera and inside the image, some behind it, outside
+    the image, out of the scale-invariance range, or seen from too oblique an angle"""
+    ang = rng.uniform(-0.2, 0.2, 3)
+    Rx = np.array([[1, 0, 0], [0, np.cos(ang[0]), -np.sin(ang[0])], [0, np.sin(ang[0]), np.cos(ang[0])]])
+    Ry = np.array([[np.cos(ang[1]), 0, np.sin(ang[1])], [0, 1, 0], [-np.sin(ang[1]), 0, np.cos(ang[1])]])
+    Rz = np.array([[np.cos(ang[2]), -np.sin(ang[2]), 0], [np.sin(ang[2]), np.cos(ang[2]), 0], [0, 0, 1]])
+    R = (Rz @ Ry @ Rx).astype(np.float32)
+    t = rng.normal(0, 2, 3).astype(np.float32)
+    Ow = (-R.T.astype(np.float64) @ t.astype(np.float64)).astype(np.float32)
+    z = rng.uniform(-5, 80, n)
+    x = (rng.uniform(-0.15 * w, 1.15 * w, n) - cx) / fx * z
+    y = (rng.uniform(-0.15 * h, 1.15 * h, n) - cy) / fy * z
+    Pc = np.stack([x, y, z], 1)
+    Pw = ((Pc - t) @ R.astype(np.float64)).astype(np.float32)      # Pw = R^T (Pc - t)
+    PO = Pw - Ow
+    d = np.linalg.norm(PO, axis=1)
+    nrm = PO / np.maximum(d[:, None], 1e-6) + rng.normal(0, 0.6, (n, 3))
+    nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    maxd = (d * rng.uniform(0.7, 4.0, n)).astype(np.float32)
+    mind = (maxd / np.float32(1.2 ** 7) * rng.uniform(0.5, 1.2, n)).astype(np.float32)
+    # some points sit EXACTLY on a level boundary of PredictScale: ratio = 1.2^k
+    kk = rng.integers(0, 8, n)
+    onb = rng.uniform(0, 1, n) < 0.05
+    maxd[onb] = (d[onb].astype(np.float32) * np.float32(1.2) ** kk[onb].astype(np.float32)).astype(np.float32)
+    return dict(world=Pw, normal=nrm, min_dist=mind, max_dist=maxd, Rcw=R, tcw=t, Ow=Ow, fx=fx, fy=fy, cx=cx, cy=cy,
+                bounds=(0.0, float(w), 0.0, float(h)))
+
+
+def check_is_in_frustum(lib, n=20000, seed=0):
+    rng = np.random.default_rng(seed)
+    m = synth_local_map(rng, n)
+    lsf = float(np.log(np.float32(1.2)).astype(np.float32))   # log_scale_factor_ = log(scale_factor_) as float
+    args = (m["world"], m["normal"], m["min_dist"], m["max_dist"], m["Rcw"], m["tcw"], m["Ow"], m["fx"], m["fy"], m["cx"], m["cy"],
+            KITTI["bf"], m["bounds"], lsf, 8, 0.5)
+    cnt, got = orbfe.IsInFrustum(*args, lib=lib)
+    ocnt, ref = O.is_in_frustum(*args)
+    assert cnt == ocnt, f"IsInFrustum: {cnt} vs oracle {ocnt}"
+    for key in ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos"):
+        assert np.array_equal(got[key], ref[key]), f"IsInFrustum: {key} differs"
+    assert 0.1 * n < cnt < 0.9 * n
+    assert len(np.unique(ref["level"][ref["in_view"] == 1])) >= 6
+    return cnt
+
+
+def check_logf(lib, n=400000, seed=0):
+    """device restatement of glibc logf == this machine's libm logf (what PredictScale's std::log(float) calls)"""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0x00800000, 0x7f800000, n, dtype=np.uint32)           # every positive normal exponent
+    x = np.concatenate([bits.view(np.float32), rng.uniform(0.05, 40.0, n).astype(np.float32),
+                        (np.float32(1.2) ** np.arange(-8, 9)).astype(np.float32), np.array([1.0, 1e-40, 3e-39], np.float32)])
+    ref = np.zeros_like(x)
+    # vectorised libm call: logf through numpy would use its own SIMD log, so call libm per element in C via ctypes arrays
+    libm.logf.restype = ctypes.c_float
+    libm.logf.argtypes = [ctypes.c_float]
+    step = max(1, len(x) // 60000)   # a 60k-element sample keeps the ctypes loop short; the full set goes through the oracle
+    idx = np.arange(0, len(x), step)
+    ref_s = np.array([libm.logf(float(v)) for v in x[idx]], np.float32)
+    got = orbfe.debug_logf(x, lib=lib)
+    assert np.array_equal(got[idx].view(np.uint32), ref_s.view(np.uint32)), "logf restatement differs from libm"
+    return len(idx)

@@ -16,7 +16,7 @@ def test_kernels_are_asan_clean(tmp_path):
     if not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("libasan not available")
     objs = []
-    for s in ("orbfe_api", "orbfe_match", "orbfe_bow"):
+    for s in ("orbfe_api", "orbfe_match", "orbfe_bow", "orbfe_frame"):
         o = str(tmp_path / (s + ".o"))
         subprocess.check_call(["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-fsanitize=address", "-fno-omit-frame-pointer",
                                "-ffp-contract=off", "-fno-strict-aliasing", "-DORBFE_EMU", "-include",

@@ -129,3 +129,19 @@ def test_bow_transform_degenerate(emu):
     arrays0 = (arrays[0], arrays[1], arrays[2], np.zeros_like(arrays[3]))
     out = orbfe.OrbVocabulary(3, 2, 0, 0, *arrays0, lib=emu).transform(rng.integers(0, 256, (50, 32), dtype=np.uint8))
     assert len(out["bow"][0]) == 0 and len(out["fv"][0]) == 0
+
+
+# ---- N2: the Frame tail --------------------------------------------------------------------------------------------
+def test_undistort_keypoints(emu, two_frames):
+    ka = two_frames[0]
+    assert P.check_undistort_keypoints(emu, ka, seed=31) > 500
+    assert len(orbfe.UndistortKeyPoints(ka[:0], 700.0, 700.0, 600.0, 180.0, [0.1, 0, 0, 0], lib=emu)) == 0
+
+
+def test_is_in_frustum(emu):
+    assert P.check_is_in_frustum(emu, 20000, seed=32) > 2000
+    assert P.check_is_in_frustum(emu, 333, seed=33) > 30
+
+
+def test_glibc_logf_restatement_matches_libm(emu):
+    assert P.check_logf(emu, 200000, seed=5) > 50000

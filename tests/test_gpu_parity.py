@@ -268,3 +268,41 @@ def test_n3_bow_transform_orbvoc_sized_vocabulary(lib, kitti_two_frames, tmp_pat
     V.close()
     assert P.check_bow_transform(lib, da, seed=62, k=10, L=3, tmp_path=tmp_path) > 1000
     assert P.check_bow_transform(lib, db[:500], seed=63, k=4, L=5) > 300
+
+
+def test_n2_frame_tail(lib, kitti_two_frames):
+    """SURVEY 8f N2: UndistortKeyPoints (cv::undistortPoints, pinned to cv2), IsInFrustum over 50k local map points with
+    PredictScale's logf, and the frustum -> SearchByProjection pipeline of Tracker::SearchLocalPoints"""
+    import oracle_lib as O
+    ka, da, _, _, scale = kitti_two_frames
+    assert P.check_undistort_keypoints(lib, ka, seed=71) > 1500
+    assert P.check_is_in_frustum(lib, 50000, seed=72) > 5000
+    assert P.check_logf(lib, 400000, seed=73) > 50000
+    # SearchLocalPoints: map points = the frame's own keypoints back-projected at random depths, seen from a nearby pose
+    rng = np.random.default_rng(74)
+    n = len(ka)
+    fx = fy = 718.856; cx, cy = 607.1928, 185.2157
+    z = rng.uniform(4, 60, n)
+    Pw = np.stack([(ka["x"] - cx) / fx * z, (ka["y"] - cy) / fy * z, z], 1).astype(np.float32)
+    R = np.eye(3, dtype=np.float32)
+    t = np.array([0.05, -0.02, 0.1], np.float32)
+    Ow = (-t).astype(np.float32)
+    nrm = (-(Pw - Ow) / np.linalg.norm(Pw - Ow, axis=1, keepdims=True)).astype(np.float32) * np.float32(-1.0)
+    d = np.linalg.norm(Pw - Ow, axis=1).astype(np.float32)
+    maxd = (d * np.float32(1.2) ** ka["octave"].astype(np.float32)).astype(np.float32) * np.float32(1.05)
+    mind = (maxd / np.float32(1.2 ** 8)).astype(np.float32)
+    lsf = float(np.log(np.float32(1.2)).astype(np.float32))
+    args = (Pw, nrm, mind, maxd, R, t, Ow, fx, fy, cx, cy, P.KITTI["bf"], (0.0, 1241.0, 0.0, 376.0), lsf, 8, 0.5)
+    cnt, tr = orbfe.IsInFrustum(*args, lib=lib)
+    ocnt, otr = O.is_in_frustum(*args)
+    assert cnt == ocnt and cnt > 0.8 * n
+    for key in tr:
+        assert np.array_equal(tr[key], otr[key]), key
+    F, OF = P.make_frames(ka, da, scale, 1241, 376, lib)
+    has_obs, occ = np.ones(n, np.uint8), np.zeros(n, np.uint8)
+    m = orbfe.OrbMatcher(0.8)
+    nm, asg = m.SearchByProjectionMapPoints(F, tr["in_view"], tr["proj_x"], tr["proj_y"], tr["proj_xr"], tr["level"], tr["view_cos"],
+                                            da, has_obs, occ, 1)
+    onm, oasg = O.search_by_projection_mappoints(OF, otr["in_view"], otr["proj_x"], otr["proj_y"], otr["proj_xr"], otr["level"],
+                                                 otr["view_cos"], da, has_obs, occ, 1, 0.8)
+    assert nm == onm and np.array_equal(asg, oasg) and nm > 0.5 * n

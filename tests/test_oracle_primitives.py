@@ -137,3 +137,67 @@ def test_cvt_gray_golden(golden):
     assert np.array_equal(O.cvt_gray(golden["gray_src3"], False), golden["gray_bgr"])
     assert np.array_equal(O.cvt_gray(golden["gray_src4"], True), golden["gray_rgba"])
     assert np.array_equal(O.cvt_gray(golden["gray_src4"], False), golden["gray_bgra"])
+
+
+# ---- N2: the OpenCV arithmetic of the Frame tail (tests/golden/make_golden_frame_tail.py) -----------------------
+@pytest.fixture(scope="module")
+def golden_tail():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_frame_tail.npz"))
+
+
+def test_undistort_points_golden(golden_tail):
+    g = golden_tail
+    for c in range(int(g["und_cases"])):
+        K, d = g[f"und_{c}_K"], g[f"und_{c}_dist"]
+        got = O.undistort_points(g[f"und_{c}_src"], K[0, 0], K[1, 1], K[0, 2], K[1, 2], d)
+        assert np.array_equal(got, g[f"und_{c}_dst"]), f"camera {c}: {(got != g[f'und_{c}_dst']).any(1).sum()} points differ"
+    # Frame::UndistortKeyPoints short-circuit (frame.cpp:616-619): dist[0] == 0 => unchanged
+    src = g["und_0_src"]
+    assert np.array_equal(O.undistort_points(src, 700.0, 700.0, 600.0, 180.0, np.zeros(4, np.float32)), src)
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+def test_undistort_points_live_cv2():
+    rng = np.random.default_rng(77)
+    for _ in range(5):
+        fx, fy = rng.uniform(300, 900, 2)
+        cx, cy = rng.uniform(200, 700), rng.uniform(100, 400)
+        d = np.array([rng.uniform(-0.4, 0.4), rng.uniform(-0.3, 0.3), rng.uniform(-0.01, 0.01), rng.uniform(-0.01, 0.01),
+                      rng.uniform(-0.1, 0.1)], np.float32)
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+        pts = np.stack([rng.uniform(0, 1241, 2000), rng.uniform(0, 376, 2000)], 1).astype(np.float32)
+        ref = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, d, None, K).reshape(-1, 2)
+        assert np.array_equal(O.undistort_points(pts, K[0, 0], K[1, 1], K[0, 2], K[1, 2], d), ref)
+
+
+def test_frustum_gemm_and_norm_golden(golden_tail):
+    """Rcw*P + tcw and cv::norm(PO) as Frame::IsInFrustum evaluates them: the oracle's projection must reproduce cv2's
+    gemm bit for bit (checked through proj = PcX/PcZ with fx = 1, cx = 0) and its distance cv2's norm (through the
+    min/max distance gate)."""
+    g = golden_tail
+    R, P, t, ref = g["gemm_R"], g["gemm_P"], g["gemm_t"], g["gemm_out"]
+    n = len(R)
+    ok = 0
+    for i in range(n):
+        Pc = ref[i, :, 0]
+        if Pc[2] <= 0:
+            continue
+        w = P[i, :, 0][None, :]
+        nrm = np.array([[0, 0, 1]], np.float32)
+        big = (-1e30, 1e30, -1e30, 1e30)
+        _, out = O.is_in_frustum(w, nrm, [0.0], [1e30], R[i], t[i, :, 0], np.zeros(3, np.float32), 1.0, 1.0, 0.0, 0.0, 0.0, big,
+                                 np.float32(np.log(np.float32(1.2))), 8, -2.0)
+        invz = np.float32(1.0) / Pc[2]
+        assert out["in_view"][0] == 1
+        assert out["proj_x"][0] == np.float32(np.float32(np.float32(1.0) * Pc[0]) * invz) + np.float32(0.0), i
+        assert out["proj_y"][0] == np.float32(np.float32(np.float32(1.0) * Pc[1]) * invz) + np.float32(0.0), i
+        # distance gate straddling cv2's norm: dist = (float)norm must pass [dist, dist] and fail (dist, inf)
+        dist = np.float32(g["norm_out"][i])
+        c1, _ = O.is_in_frustum(w, nrm, [dist], [dist], R[i], t[i, :, 0], np.zeros(3, np.float32), 1.0, 1.0, 0.0, 0.0, 0.0, big,
+                                np.float32(0.18), 8, -2.0)
+        c2, _ = O.is_in_frustum(w, nrm, [np.nextafter(dist, np.float32(np.inf))], [1e30], R[i], t[i, :, 0], np.zeros(3, np.float32),
+                                1.0, 1.0, 0.0, 0.0, 0.0, big, np.float32(0.18), 8, -2.0)
+        assert c1 == 1 and c2 == 0, i
+        ok += 1
+    assert ok > 500
