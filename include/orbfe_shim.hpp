@@ -536,6 +536,58 @@ int SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMa
   return nFound;
 }
 
+// ---- the Frame tail -------------------------------------------------------------------------------
+// Body of Frame::UndistortKeyPoints (frame.cpp:614-641): K = calib_mat_ (fx, fy, cx, cy), dist = dist_coeff_ as floats.
+inline void UndistortKeyPoints(const std::vector<cv::KeyPoint>& keypoints, float fx, float fy, float cx, float cy,
+                               const std::vector<float>& dist_coeff, std::vector<cv::KeyPoint>& undistorted_keypoints,
+                               int device = 0) {
+  undistorted_keypoints.resize(keypoints.size());
+  check(orbfe_undistort_keypoints(device, (int)keypoints.size(), as_pod(keypoints), fx, fy, cx, cy, dist_coeff.data(),
+                                  (int)dist_coeff.size(), reinterpret_cast<orbfe_keypoint*>(undistorted_keypoints.data())),
+        "orbfe_undistort_keypoints");
+}
+
+// The visibility loop of Tracker::SearchLocalPoints (core/tracker.cpp:1196-1211): Frame::IsInFrustum (frame.cpp:277-337)
+// for every candidate local map point in one launch.  fetch(i, P[3], Pn[3], minDist, maxDist) copies GetWorldPos(),
+// GetNormal(), Get{Min,Max}DistanceInvariance() of vpMapPoints[i] and returns false for points the loop skips
+// (last_frame_id_seen == frame id || isBad(), :1202-1205).  Rcw (row-major) / tcw / Ow = Frame::Rcw_, tcw_, Ow_.
+// Writes the track_* fields exactly as IsInFrustum does and returns the number of visible points (nToMatch).
+template <class MapPointT, class FetchFn>
+int IsInFrustumBatch(const std::vector<MapPointT*>& vpMapPoints, const float Rcw[9], const float tcw[3], const float Ow[3],
+                     float fx, float fy, float cx, float cy, float baseline_fx, const ImageBounds& b, float log_scale_factor,
+                     int scale_levels, float viewingCosLimit, FetchFn fetch, int device = 0) {
+  const size_t n = vpMapPoints.size();
+  std::vector<float> P, Pn, mn, mx;
+  std::vector<size_t> idx;
+  for (size_t i = 0; i < n; ++i) {
+    float p[3], q[3], a = 0, c = 0;
+    if (!fetch(i, p, q, a, c)) continue;
+    vpMapPoints[i]->track_is_in_view = false;  // frame.cpp:278
+    idx.push_back(i);
+    P.insert(P.end(), p, p + 3); Pn.insert(Pn.end(), q, q + 3); mn.push_back(a); mx.push_back(c);
+  }
+  const int m = (int)idx.size();
+  std::vector<uint8_t> in((size_t)m);
+  std::vector<float> u((size_t)m), v((size_t)m), ur((size_t)m), vc((size_t)m);
+  std::vector<int32_t> lvl((size_t)m);
+  int cnt = 0;
+  check(orbfe_is_in_frustum(device, m, P.data(), Pn.data(), mn.data(), mx.data(), Rcw, tcw, Ow, fx, fy, cx, cy, baseline_fx, b.minX,
+                            b.maxX, b.minY, b.maxY, log_scale_factor, scale_levels, viewingCosLimit, in.data(), u.data(), v.data(),
+                            ur.data(), lvl.data(), vc.data(), &cnt),
+        "orbfe_is_in_frustum");
+  for (int j = 0; j < m; ++j) {
+    if (!in[j]) continue;
+    MapPointT* pMP = vpMapPoints[idx[j]];  // frame.cpp:328-334
+    pMP->track_is_in_view = true;
+    pMP->track_projected_x = u[j];
+    pMP->track_projected_x_right = ur[j];
+    pMP->track_projected_y = v[j];
+    pMP->track_scale_level = lvl[j];
+    pMP->track_view_cos = vc[j];
+  }
+  return cnt;
+}
+
 // ---- OrbVocabulary: the transform path of DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>
 // (src/orb_features/orb_vocabulary.h; used by Frame::ComputeBoW frame.cpp:258-263 and KeyFrame::ComputeBoW
 // keyframe.cpp:127-137).  BowVectorT / FeatureVectorT are DBoW2::BowVector / DBoW2::FeatureVector (std::map subclasses).

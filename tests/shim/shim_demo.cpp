@@ -26,6 +26,9 @@ struct MockMapPoint {
   cv::Mat desc;
   bool bad = false;
   int nobs = 1;
+  bool track_is_in_view = false;  // map_point.h tracking fields written by Frame::IsInFrustum
+  float track_projected_x = 0, track_projected_y = 0, track_projected_x_right = 0, track_view_cos = 0;
+  int track_scale_level = 0;
   std::set<MockKeyFrame*> in;
   bool isBad() const { return bad; }
   cv::Mat GetDescriptor() const { return desc; }
@@ -97,7 +100,26 @@ static int n1_selfcheck(const std::vector<cv::KeyPoint>& kps, const cv::Mat& des
   const int h2 = orbfe::Fuse(&kf, mpv, 3.f, rep, b, gate);
   MockKeyFrame other = kf;                      // Fuse(KF, points): the points are not yet in `other`
   const int h1 = orbfe::Fuse(&other, mpv, 3.f, b, gate_ur);
-  printf("%zu %d %d %d %d %d %d %d %d\n", n, a, c, d, e, f, g, h1, h2);
+  // N2: undistortion with a real distortion model, and the SearchLocalPoints visibility loop (identity pose, points
+  // back-projected 10 m in front of the camera: every one must be visible at its own pixel)
+  std::vector<cv::KeyPoint> und;
+  orbfe::UndistortKeyPoints(kps, 718.856f, 718.856f, 607.1928f, 185.2157f, std::vector<float>{-0.2834f, 0.0739f, 0.0002f, 0.00002f}, und);
+  int moved = 0;
+  for (size_t i = 0; i < n; ++i) moved += und[i].pt.x != kps[i].pt.x || und[i].pt.y != kps[i].pt.y;
+  const float I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Z3[3] = {0, 0, 0};
+  const float fx = 718.856f, cx0 = 607.1928f, cy0 = 185.2157f;
+  auto fetch = [&](size_t i, float* Pw, float* Pn, float& mn, float& mx) {
+    Pw[0] = (kps[i].pt.x - cx0) / fx * 10.f; Pw[1] = (kps[i].pt.y - cy0) / fx * 10.f; Pw[2] = 10.f;
+    const float len = std::sqrt(Pw[0] * Pw[0] + Pw[1] * Pw[1] + Pw[2] * Pw[2]);
+    for (int c2 = 0; c2 < 3; ++c2) Pn[c2] = Pw[c2] / len;
+    mn = 1.f; mx = 40.f;
+    return true;
+  };
+  const int vis = orbfe::IsInFrustumBatch(mpv, I3, Z3, Z3, fx, fx, cx0, cy0, 386.1448f, b, std::log(1.2f), 8, 0.5f, fetch);
+  int near_px = 0;
+  for (size_t i = 0; i < n; ++i)
+    near_px += pts[i].track_is_in_view && std::fabs(pts[i].track_projected_x - kps[i].pt.x) < 0.01f && pts[i].track_view_cos > 0.99f;
+  printf("%zu %d %d %d %d %d %d %d %d %d %d %d\n", n, a, c, d, e, f, g, h1, h2, moved, vis, near_px);
   return 0;
 }
 

@@ -59,10 +59,12 @@ def test_shim_n1_adapters_find_a_frame_in_itself(tmp_path):
     img = synth.frame(240, 800, seed=5)
     img.tofile(tmp_path / "i.raw")
     out = subprocess.check_output([build_demo(), "--n1", "800", "240", str(tmp_path / "i.raw")], text=True)
-    n, bow_f, bow_kf, tri, proj_kf, proj_f, sim3, fuse1, fuse2 = map(int, out.split())
+    n, bow_f, bow_kf, tri, proj_kf, proj_f, sim3, fuse1, fuse2, moved, visible, at_pixel = map(int, out.split())
     assert n > 500
     for got in (bow_f, bow_kf, tri, proj_kf, proj_f, sim3, fuse1, fuse2):
         assert got > 0.5 * n, out
+    # N2 adapters: a real distortion model moves (nearly) every keypoint; every back-projected point is visible at its pixel
+    assert moved > 0.9 * n and visible == n and at_pixel == n, out
 
 
 @pytest.mark.gpu
