@@ -49,7 +49,8 @@ struct OctScratch {      // per-slot strided device arrays (bases for slot 0)
 #endif
 __global__ void __launch_bounds__(ORBFE_OCT_THREADS, ORBFE_OCT_MINB)
 k_octree(const __grid_constant__ Geom g, const int* __restrict__ cellCnt, const unsigned* __restrict__ cellList,
-         const OctScratch sc, unsigned* __restrict__ lvlKp, int* __restrict__ lvlCnt, int* __restrict__ errFlag) {
+         const OctScratch sc, unsigned* __restrict__ lvlKp, int* __restrict__ lvlCnt, int* __restrict__ errFlag,
+         const int stageCap) {
   ORBFE_DYN_SMEM(smem);
   unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(smem);  // g.sortCap entries
   __shared__ int s_scan[33];
@@ -64,6 +65,9 @@ k_octree(const __grid_constant__ Geom g, const int* __restrict__ cellCnt, const 
   const unsigned* cl = cellList + (size_t)slot * g.cellListStride + L.cellListOff;
   unsigned* cand = sc.cand + (size_t)slot * g.candStride + L.candOff;
   int* knode = sc.knode + (size_t)slot * g.candStride + L.candOff;
+  // the key arrays are walked three times per generation with dependent loads: when the level's candidates fit
+  // (stageCap entries, the common case) they live in shared memory instead of L2
+  unsigned* const candG = cand;  // still written: orbfe_debug_candidates (per-stage parity tap) reads it
   int* cellStart = sc.cellStart + (size_t)slot * g.totalCells + L.cellBase;
   OctNode* genA = sc.nodes + (size_t)slot * 2 * g.nodeStride + 2 * (size_t)L.nodeOff;
   OctNode* genB = genA + L.nodeCap;
@@ -89,11 +93,19 @@ k_octree(const __grid_constant__ Geom g, const int* __restrict__ cellCnt, const 
     int run = orbfe_block_exscan(sum, s_scan, &total);
     for (int c = c0; c < c1; ++c) { cellStart[c] = run; run += cc[c]; }
     n = total;
+    if (n <= stageCap) {
+      cand = reinterpret_cast<unsigned*>(childSlot + g.maxNodeCap);
+      knode = reinterpret_cast<int*>(cand + stageCap);
+    }
     __syncthreads();
     const int lane = tid & 31, wid = tid >> 5;
     for (int c = wid; c < nCells; c += T / 32) {
       const int cn = cc[c], st = cellStart[c];
-      for (int k = lane; k < cn; k += 32) cand[st + k] = cl[(size_t)c * L.cellCap + k];
+      for (int k = lane; k < cn; k += 32) {
+        const unsigned v = cl[(size_t)c * L.cellCap + k];
+        cand[st + k] = v;
+        if (cand != candG) candG[st + k] = v;
+      }
     }
     __syncthreads();
   }

@@ -57,6 +57,7 @@ struct orbfe_extractor {
   bool configured = false;
   int fastTilePitch = 0, fastMaxInnerH = 0, fastQueueCap = 0;
   size_t fastSmem = 0, octSmem = 0;
+  int octStageCap = 0;
   // device arena
   uint8_t* d_img = nullptr;
   uint8_t* d_color = nullptr;       // staging of colour frames (orbfe_upload_color), allocated on first use
@@ -325,6 +326,13 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   g.maxNodeCap = 0;
   for (int l = 0; l < nl; ++l) g.maxNodeCap = std::max(g.maxNodeCap, g.lv[l].nodeCap);
   ex->octSmem = (size_t)sc * sizeof(unsigned long long) + 2 * (size_t)g.maxNodeCap * sizeof(int);
+  // shared-memory staging of a level's candidate keys (k_octree): as many entries as keep 4 CTAs per SM resident
+  ex->octStageCap = 0;
+  {
+    const size_t budget = 50 * 1024;
+    if (ex->octSmem + 8 * 1024 <= budget) ex->octStageCap = (int)((budget - ex->octSmem) / 8);
+    ex->octSmem += (size_t)ex->octStageCap * 8;
+  }
   if (ex->octSmem > 200 * 1024)
     return orbfe_fail(ORBFE_ERR_INVALID, "nfeatures per level too large for the shared-memory sort (%d)", maxSort);
   g.totalFast = fastBase;
@@ -464,7 +472,7 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
   }
   if ((rc = stage_event(ex, 2))) return rc;
   ORBFE_LAUNCH(ex, k_octree, dim3(g.nlevels, n), dim3(ORBFE_OCT_THREADS), ex->octSmem, g, ex->d_cellCnt, ex->d_cellList,
-               ex->oct, ex->d_lvlKp, ex->d_lvlCnt, ex->d_err);
+               ex->oct, ex->d_lvlKp, ex->d_lvlCnt, ex->d_err, ex->octStageCap);
   if ((rc = stage_event(ex, 3))) return rc;
   ORBFE_LAUNCH(ex, k_blur, dim3((g.totalTiles + ORBFE_BLUR_THREADS / 32 - 1) / (ORBFE_BLUR_THREADS / 32), n),
                dim3(ORBFE_BLUR_THREADS), 0, g, ex->d_pyr, ex->d_blur);  // one warp per strip
