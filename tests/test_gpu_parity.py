@@ -306,3 +306,46 @@ def test_n2_frame_tail(lib, kitti_two_frames):
     onm, oasg = O.search_by_projection_mappoints(OF, otr["in_view"], otr["proj_x"], otr["proj_y"], otr["proj_xr"], otr["level"],
                                                  otr["view_cos"], da, has_obs, occ, 1, 0.8)
     assert nm == onm and np.array_equal(asg, oasg) and nm > 0.5 * n
+
+
+def test_config3_full_length_sequence_sharded_properties(lib):
+    """BASELINE config 3 at its full size: 4541 stereo pairs (KITTI-00 length) cut into 8 rank shards and processed in
+    64-pair batches through the device-resident path.  Size-independent properties: every pair's outputs depend only on
+    its content (same digest wherever it lands in a batch or shard), the shards cover every index exactly once, and a
+    sample of pairs equals the oracle."""
+    import oracle_lib as O
+    from slam_framework_b200 import shard
+    n_total, distinct, B = 4541, 40, 64
+    pairs = [synth.stereo_pair(seed=300 + s) for s in range(distinct)]
+    ex = orbfe.ORBextractor(lib=lib, max_images=2 * B)
+    bf, base = P.KITTI["bf"], P.KITTI["bf"] / P.KITTI["fx"]
+    seen, first, total_matches = set(), {}, 0
+    for rank in range(8):
+        lo, hi = shard.shard_range(n_total, rank, 8)
+        for b0 in range(lo, hi, B):
+            idx = list(range(b0, min(b0 + B, hi)))
+            ex.upload([im for i in idx for im in pairs[i % distinct]])
+            ex.run(2 * len(idx))
+            ex.run_stereo(len(idx), bf, base)
+            out = ex.download(2 * len(idx), ex.make_buffers(2 * len(idx), stereo=True))
+            for p, i in enumerate(idx):
+                assert i not in seen
+                seen.add(i)
+                nl, nr = out["n"][2 * p], out["n"][2 * p + 1]
+                dg = shard.digest([out["kps"][2 * p, :nl], out["desc"][2 * p, :nl], out["kps"][2 * p + 1, :nr],
+                                   out["desc"][2 * p + 1, :nr], out["ur"][2 * p, :nl], out["depth"][2 * p, :nl]])
+                key = i % distinct
+                if key not in first:
+                    first[key] = dg
+                    if key % 13 == 0:  # oracle spot checks
+                        oL, oR = O.Extractor(), O.Extractor()
+                        okl, odl = oL.extract(pairs[key][0]); okr, odr = oR.extract(pairs[key][1])
+                        P.assert_kps_equal(out["kps"][2 * p, :nl], okl, f"pair {i} left")
+                        assert np.array_equal(out["desc"][2 * p + 1, :nr], odr)
+                        _, our, odp = O.stereo_match(oL, oR, okl, odl, okr, odr, bf, base)
+                        assert np.array_equal(out["ur"][2 * p, :nl], our) and np.array_equal(out["depth"][2 * p, :nl], odp)
+                assert dg == first[key], f"pair {i} (content {key}) differs from its first occurrence"
+                total_matches += int((out["ur"][2 * p, :nl] >= 0).sum())
+    assert seen == set(range(n_total))
+    assert total_matches > 300 * n_total
+    ex.close()
