@@ -388,12 +388,16 @@ def synth_vocabulary(rng, k=10, L=3, stop_frac=0.05, prune_frac=0.08, seed_desc=
     return (np.array(parent, np.int32), np.array(leaf, np.uint8), np.stack(desc), np.array(weight, np.float64))
 
 
-def write_vocabulary_text(path, k, L, scoring, weighting, arrays):
+def write_vocabulary_text(path, k, L, scoring, weighting, arrays, trailing_newline=False):
+    """the ORBvoc.txt format of TemplatedVocabulary::saveToTextFile / loadFromTextFile.  No newline after the last node by
+    default: the reference's `while(!f.eof())` loop (TemplatedVocabulary.h:1375) would turn a final empty line into a bogus
+    extra child of the root with an uninitialised descriptor (indeterminate); the product loader ignores blank lines."""
     parent, leaf, desc, weight = arrays
+    lines = [f"{k} {L} {scoring} {weighting}"]
+    for i in range(1, len(parent)):
+        lines.append(f"{parent[i]} {leaf[i]} " + " ".join(str(int(b)) for b in desc[i]) + f" {float(weight[i])!r}")
     with open(path, "w") as f:
-        f.write(f"{k} {L} {scoring} {weighting}\n")
-        for i in range(1, len(parent)):
-            f.write(f"{parent[i]} {leaf[i]} " + " ".join(str(int(b)) for b in desc[i]) + f" {float(weight[i])!r}\n")
+        f.write("\n".join(lines) + ("\n" if trailing_newline else ""))
 
 
 def assert_bow_equal(got, ref, what=""):
