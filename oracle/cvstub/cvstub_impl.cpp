@@ -61,3 +61,18 @@ void KeyPointsFilter::retainBest(std::vector<KeyPoint>&, int) {
 }
 
 }  // namespace cv
+
+namespace cv {
+// cv::undistortPoints(src, dst, K, dist, Mat(), K) on an N x 2 CV_32F matrix (frame.cpp:629-631): the oracle's cv2-pinned
+// implementation (tests/golden/cv2_frame_tail.npz)
+void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const Mat& dist, const Mat& R, const Mat& P) {
+  if (!R.empty() || P.empty() || src.type() != CV_32F || src.cols != 2) { fprintf(stderr, "cvstub: unsupported undistortPoints\n"); abort(); }
+  std::vector<float> in((size_t)src.rows * 2), out((size_t)src.rows * 2), d;
+  for (int i = 0; i < src.rows; ++i) { in[2 * i] = src.at<float>(i, 0); in[2 * i + 1] = src.at<float>(i, 1); }
+  const int nd = dist.rows * dist.cols;
+  for (int i = 0; i < nd; ++i) d.push_back(dist.at<float>(i));
+  orc_undistort_points(src.rows, in.data(), K.at<float>(0, 0), K.at<float>(1, 1), K.at<float>(0, 2), K.at<float>(1, 2), d.data(), nd, out.data());
+  dst.create(src.rows, 2, CV_32F);
+  for (int i = 0; i < src.rows; ++i) { dst.at<float>(i, 0) = out[2 * i]; dst.at<float>(i, 1) = out[2 * i + 1]; }
+}
+}  // namespace cv

@@ -9,6 +9,11 @@
 #define ORACLE_CVSTUB_CORE_HPP_
 
 #include <algorithm>
+#include <array>
+#include <cfloat>
+#include <climits>
+#include <limits>
+#include <numeric>
 #include <cassert>
 #include <cmath>
 #include <cstddef>
@@ -77,6 +82,20 @@ struct KeyPoint {
       : pt(x, y), size(size_), angle(angle_), response(response_), octave(octave_), class_id(class_id_) {}
 };
 
+template <class T>
+struct Point3_ {
+  T x, y, z;
+  Point3_() : x(0), y(0), z(0) {}
+  Point3_(T x_, T y_, T z_) : x(x_), y(y_), z(z_) {}
+};
+typedef Point3_<float> Point3f;
+typedef Point3_<double> Point3d;
+
+enum { NORM_INF = 1, NORM_L1 = 2, NORM_L2 = 4 };
+
+class Mat;
+class _OutputArray;
+
 struct MatStep {
   size_t v;
   MatStep(size_t s = 0) : v(s) {}
@@ -128,15 +147,23 @@ class Mat {
   Mat rowRange(int a, int b) const { Mat m = *this; m.rows = b - a; m.data = data + (size_t)a * step; return m; }
   Mat colRange(int a, int b) const { Mat m = *this; m.cols = b - a; m.data = data + (size_t)a * esz(type_); return m; }
   Mat row(int r) const { return rowRange(r, r + 1); }
+  Mat col(int c) const { return colRange(c, c + 1); }
+  // single-index access of a vector (n x 1 or 1 x n)
+  template <class T> T& at(int i) { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
+  template <class T> const T& at(int i) const { return cols == 1 ? at<T>(i, 0) : at<T>(0, i); }
+  // channels are not modelled: an N x 2 CV_32F matrix IS the N x 1 two-channel view undistortPoints takes (frame.cpp:629-631)
+  Mat reshape(int) const { return *this; }
+  Mat t() const;                                   // CV_32F
+  double dot(const Mat& m) const;                  // CV_32F, dotProd_: double accumulator over (double)a*b
+  void convertTo(Mat& dst, int type) const;        // CV_8U -> CV_32F
+  void copyTo(const _OutputArray& dst) const;
+  static Mat ones(int r, int c, int type);
+  static Mat eye(int r, int c, int type);
   Mat operator()(const Rect& r) const { return rowRange(r.y, r.y + r.height).colRange(r.x, r.x + r.width); }
   Mat clone() const {
     Mat m(rows, cols, type_);
     for (int r = 0; r < rows; ++r) std::memcpy(m.ptr(r), ptr(r), (size_t)cols * esz(type_));
     return m;
-  }
-  void copyTo(Mat& dst) const {
-    dst.create(rows, cols, type_);
-    for (int r = 0; r < rows; ++r) std::memcpy(dst.ptr(r), ptr(r), (size_t)cols * esz(type_));
   }
   static MatZerosExpr zeros(int r, int c, int type) { MatZerosExpr e = {r, c, type}; return e; }
   Mat(const MatZerosExpr& e) : rows(0), cols(0), step(0), data(nullptr), type_(e.type) { *this = e; }
@@ -163,14 +190,132 @@ class _InputArray {
 class _OutputArray {
  public:
   _OutputArray(Mat& m) : m_(&m) {}
+  _OutputArray(const Mat& roi) : tmp_(roi), m_(&tmp_) {}  // a temporary ROI header: writes land in the parent matrix
   void create(int r, int c, int t) const { m_->create(r, c, t); }
   void release() const { m_->release(); }
   Mat getMat() const { return *m_; }
+  Mat& ref() const { return *m_; }
  private:
+  mutable Mat tmp_;
   Mat* m_;
 };
 typedef const _InputArray& InputArray;
 typedef const _OutputArray& OutputArray;
+
+// ---- CV_32F algebra used by src/data/*.cpp and orb_matcher.cpp.  Evaluated eagerly (no MatExpr).  Arithmetic follows what cv2
+// does for the shapes that matter here (tests/golden/cv2_frame_tail.npz): matrix product = float products and float sums in k
+// order; norm / dot = double accumulators.  Transposed products are formed on the explicit transpose.
+inline void Mat::copyTo(const _OutputArray& o) const {
+  Mat& dst = o.ref();
+  dst.create(rows, cols, type_);
+  for (int r = 0; r < rows; ++r) std::memcpy(dst.ptr(r), ptr(r), (size_t)cols * esz(type_));
+}
+inline Mat Mat::t() const {
+  Mat m(cols, rows, CV_32F);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) m.at<float>(c, r) = at<float>(r, c);
+  return m;
+}
+inline double Mat::dot(const Mat& m) const {
+  double s = 0;
+  const int n = rows * cols;
+  for (int i = 0; i < n; ++i) s += (double)at<float>(i / cols, i % cols) * (double)m.at<float>(i / m.cols, i % m.cols);
+  return s;
+}
+inline void Mat::convertTo(Mat& dst, int type) const {
+  Mat out(rows, cols, type);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) {
+      const float v = type_ == CV_32F ? at<float>(r, c) : (float)at<uchar>(r, c);
+      if (type == CV_32F) out.at<float>(r, c) = v; else out.at<uchar>(r, c) = (uchar)v;
+    }
+  dst = out;
+}
+inline Mat Mat::ones(int r, int c, int type) {
+  Mat m(r, c, type);
+  for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) m.at<float>(i, j) = 1.0f;
+  return m;
+}
+inline Mat Mat::eye(int r, int c, int type) {
+  Mat m(r, c, type);
+  for (int i = 0; i < r; ++i) for (int j = 0; j < c; ++j) m.at<float>(i, j) = i == j ? 1.0f : 0.0f;
+  return m;
+}
+template <class F> inline Mat mat_map2(const Mat& a, const Mat& b, F f) {
+  Mat m(a.rows, a.cols, CV_32F);
+  for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) m.at<float>(r, c) = f(a.at<float>(r, c), b.at<float>(r, c));
+  return m;
+}
+template <class F> inline Mat mat_map1(const Mat& a, F f) {
+  Mat m(a.rows, a.cols, CV_32F);
+  for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) m.at<float>(r, c) = f(a.at<float>(r, c));
+  return m;
+}
+inline Mat operator+(const Mat& a, const Mat& b) { return mat_map2(a, b, [](float x, float y) { return x + y; }); }
+inline Mat operator-(const Mat& a, const Mat& b) { return mat_map2(a, b, [](float x, float y) { return x - y; }); }
+inline Mat operator-(const Mat& a) { return mat_map1(a, [](float x) { return -x; }); }
+inline Mat operator*(const Mat& a, double s) { return mat_map1(a, [s](float x) { return (float)(x * s); }); }
+inline Mat operator*(double s, const Mat& a) { return a * s; }
+inline Mat operator/(const Mat& a, double s) { return mat_map1(a, [s](float x) { return (float)(x * (1.0 / s)); }); }  // scale 1/s, as MatExpr does
+inline Mat operator*(const Mat& a, const Mat& b) {  // cv::gemm, small-matrix float path
+  Mat m(a.rows, b.cols, CV_32F);
+  for (int i = 0; i < a.rows; ++i)
+    for (int j = 0; j < b.cols; ++j) {
+      float s = a.at<float>(i, 0) * b.at<float>(0, j);
+      for (int k = 1; k < a.cols; ++k) s = s + a.at<float>(i, k) * b.at<float>(k, j);
+      m.at<float>(i, j) = s;
+    }
+  return m;
+}
+inline double norm(const Mat& a, int type = NORM_L2) {
+  double s = 0;
+  for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) { const double v = a.at<float>(r, c); s += type == NORM_L1 ? std::fabs(v) : v * v; }
+  return type == NORM_L1 ? s : std::sqrt(s);
+}
+inline double norm(const Mat& a, const Mat& b, int type = NORM_L2) {
+  double s = 0;
+  for (int r = 0; r < a.rows; ++r)
+    for (int c = 0; c < a.cols; ++c) {
+      const double v = (double)(a.at<float>(r, c) - b.at<float>(r, c));  // the difference is formed in float (normDiffL1_32f)
+      s += type == NORM_L1 ? std::fabs(v) : v * v;
+    }
+  return type == NORM_L1 ? s : std::sqrt(s);
+}
+
+// cv::Mat_<float>(r, c) << a, b, c  (frame.cpp:606, keyframe.cpp:93,485)
+template <class T> class Mat_;
+template <class T>
+class MatCommaInitializer_ {
+ public:
+  MatCommaInitializer_(Mat_<T>* m, T v);
+  MatCommaInitializer_& operator,(T v);
+  operator Mat_<T>() const;
+  operator Mat() const;
+ private:
+  Mat_<T>* m_;
+  int i_;
+};
+template <class T>
+class Mat_ : public Mat {
+ public:
+  Mat_() {}
+  Mat_(int r, int c) : Mat(r, c, CV_32F) {}
+  Mat_(const Mat& m) : Mat(m) {}
+  T& operator()(int r, int c) { return this->template at<T>(r, c); }
+  const T& operator()(int r, int c) const { return this->template at<T>(r, c); }
+  T& operator()(int i) { return this->template at<T>(i); }
+};
+template <class T> inline MatCommaInitializer_<T>::MatCommaInitializer_(Mat_<T>* m, T v) : m_(m), i_(0) { m_->template at<T>(0, 0) = v; i_ = 1; }
+template <class T> inline MatCommaInitializer_<T>& MatCommaInitializer_<T>::operator,(T v) {
+  m_->template at<T>(i_ / m_->cols, i_ % m_->cols) = v; ++i_; return *this;
+}
+template <class T> inline MatCommaInitializer_<T>::operator Mat_<T>() const { return *m_; }
+template <class T> inline MatCommaInitializer_<T>::operator Mat() const { return *m_; }
+template <class T, class V> inline MatCommaInitializer_<T> operator<<(const Mat_<T>& m, V v) {
+  return MatCommaInitializer_<T>(const_cast<Mat_<T>*>(&m), (T)v);
+}
+
+void undistortPoints(const Mat& src, Mat& dst, const Mat& K, const Mat& dist, const Mat& R, const Mat& P);
 
 enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_WRAP = 3, BORDER_REFLECT_101 = 4, BORDER_DEFAULT = 4,
        BORDER_ISOLATED = 16 };

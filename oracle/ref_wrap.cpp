@@ -7,6 +7,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <mutex>
 #include <new>
 #include <sys/mman.h>
 
@@ -15,37 +17,34 @@
 // ADDRESS: with a general-purpose malloc that order depends on which freed chunks get reused.  This library is linked with
 // -Bsymbolic-functions and replaces operator new by a bump allocator, so that addresses grow in allocation order and the
 // tie-break becomes "later-created node = higher address" -- the definition the oracle and the CUDA path use (DESIGN.md
-// section 2, item 1).  The extractor entry points switch it on and rewind it on return (all their allocations are dead by then).
+// section 2, item 1).  The C++ runtime is linked statically into this library (Makefile.ref), so every allocation of the reference code and of the
+// library internals it calls goes through these operators; memory is only reclaimed by the entry points that rewind.
 namespace {
 char* g_base = nullptr;
-size_t g_off = 0;
+std::atomic<size_t> g_off(0);
 const size_t kArena = (size_t)1 << 36;  // virtual reservation, committed lazily
-inline void* arena_alloc(size_t n) {
-  if (!g_base) {
-    g_base = static_cast<char*>(mmap(nullptr, kArena, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0));
-    if (g_base == MAP_FAILED) { g_base = nullptr; return nullptr; }
-  }
-  const size_t a = (g_off + 15) & ~(size_t)15;
-  if (a + n > kArena) return nullptr;
-  g_off = a + n;
+std::once_flag g_once;
+inline void* arena_alloc(size_t n) {  // thread-safe: Frame's stereo constructor extracts on two std::threads (frame.cpp:86-89)
+  std::call_once(g_once, []() {
+    void* p = mmap(nullptr, kArena, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    g_base = p == MAP_FAILED ? nullptr : static_cast<char*>(p);
+  });
+  if (!g_base) return nullptr;
+  const size_t need = (n + 15) & ~(size_t)15;
+  const size_t a = g_off.fetch_add(need);
+  if (a + need > kArena) return nullptr;
   return g_base + a;
 }
 inline bool in_arena(void* p) { return g_base && p >= g_base && p < g_base + kArena; }
-bool g_on = false;  // the arena serves only the extractor entry points: the vocabulary code shares std::string / iostream
-                    // buffers with libstdc++ (which frees with its own operator delete), so it stays on malloc
+}  // namespace
+// rewinds the arena on scope exit: only for entry points whose allocations are all dead by then (ref_orb_extract)
 struct ArenaScope {
   size_t mark;
-  ArenaScope() : mark(g_off) { g_on = true; }
-  ~ArenaScope() { g_on = false; g_off = mark; }
+  ArenaScope() : mark(g_off.load()) {}
+  ~ArenaScope() { g_off.store(mark); }
 };
-inline void* any_alloc(size_t n) {
-  void* p = g_on ? arena_alloc(n ? n : 1) : malloc(n ? n : 1);
-  if (!p) throw std::bad_alloc();
-  return p;
-}
-}  // namespace
-void* operator new(size_t n) { return any_alloc(n); }
-void* operator new[](size_t n) { return any_alloc(n); }
+void* operator new(size_t n) { void* p = arena_alloc(n ? n : 1); if (!p) throw std::bad_alloc(); return p; }
+void* operator new[](size_t n) { void* p = arena_alloc(n ? n : 1); if (!p) throw std::bad_alloc(); return p; }
 void operator delete(void* p) noexcept { if (p && !in_arena(p)) free(p); }
 void operator delete[](void* p) noexcept { if (p && !in_arena(p)) free(p); }
 void operator delete(void* p, size_t) noexcept { if (p && !in_arena(p)) free(p); }
@@ -75,7 +74,6 @@ int ref_orb_extract(int nfeatures, float scale_factor, int nlevels, int ini_th, 
 
 // the extractor's scale tables (orb_extractor.cpp:356-390)
 void ref_orb_tables(int nfeatures, float scale_factor, int nlevels, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2) {
-  ArenaScope scope;
   ORBextractor ex(nfeatures, scale_factor, nlevels, 20, 7);
   for (int i = 0; i < nlevels; ++i) {
     scale[i] = ex.GetScaleFactors()[i]; inv_scale[i] = ex.GetInverseScaleFactors()[i];

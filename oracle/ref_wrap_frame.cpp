@@ -1,0 +1,224 @@
+// oracle/ref_wrap_frame.cpp -- TEST INFRASTRUCTURE ONLY: C entry points around the reference's OWN Frame / MapPoint / KeyFrame /
+// OrbMatcher classes (src/data/*.cpp, src/orb_features/orb_matcher.cpp), compiled unmodified from /root/reference into
+// oracle/_ref/libslam_ref.so by oracle/Makefile.ref.  Nothing here restates reference logic: the wrappers build the reference's
+// objects from test inputs, call the reference's functions and copy the results out.
+#include "data/frame.h"
+#include "data/keyframe.h"
+#include "data/map.h"
+#include "data/map_point.h"
+#include "orb_features/orb_matcher.h"
+#include "util/converter.h"
+
+#include <cstring>
+#include <map>
+#include <memory>
+#include <new>
+
+// util/converter.cpp:3-10 needs Eigen/g2o for its other members; this is the one the compiled files use
+std::vector<cv::Mat> Converter::toDescriptorVector(const cv::Mat& Descriptors) {
+  std::vector<cv::Mat> vDesc;
+  vDesc.reserve(Descriptors.rows);
+  for (int j = 0; j < Descriptors.rows; ++j) vDesc.push_back(Descriptors.row(j));
+  return vDesc;
+}
+
+namespace {
+struct RefFrame {
+  alignas(Frame) unsigned char storage[sizeof(Frame)];
+  bool live = false;
+  std::shared_ptr<ORBextractor> exL, exR;
+  std::shared_ptr<Map> map;
+  std::vector<std::unique_ptr<MapPoint>> owned;
+  std::unique_ptr<KeyFrame> kf;  // observer used to give map points observations
+  Frame* f() { return reinterpret_cast<Frame*>(storage); }
+  ~RefFrame() { kf.reset(); owned.clear(); if (live) f()->~Frame(); }
+};
+cv::Mat make_K(float fx, float fy, float cx, float cy) {
+  cv::Mat K = cv::Mat::eye(3, 3, CV_32F);
+  K.at<float>(0, 0) = fx; K.at<float>(1, 1) = fy; K.at<float>(0, 2) = cx; K.at<float>(1, 2) = cy;
+  return K;
+}
+cv::Mat make_pose(const float* t) {  // identity rotation, translation t
+  cv::Mat T = cv::Mat::eye(4, 4, CV_32F);
+  for (int i = 0; i < 3; ++i) T.at<float>(i, 3) = t ? t[i] : 0.f;
+  return T;
+}
+cv::Mat make_vec3(const float* p) {
+  cv::Mat m(3, 1, CV_32F);
+  for (int i = 0; i < 3; ++i) m.at<float>(i) = p[i];
+  return m;
+}
+KeyFrame* observer(RefFrame* R) {
+  if (!R->kf) R->kf.reset(new KeyFrame(*R->f(), R->map, std::shared_ptr<KeyframeDatabase>()));
+  return R->kf.get();
+}
+}  // namespace
+
+extern "C" {
+
+// Frame's stereo constructor (frame.cpp:61-111): two ORBextractor::Compute on two std::threads, UndistortKeyPoints,
+// ComputeStereoMatches, AssignFeaturesToGrid.  ComputeStereoMatches reads baseline_ before the constructor sets it
+// (frame.cpp:436 vs :108): the Frame is constructed twice in the same storage, so that the second construction finds the value
+// the first one left there (= bf / fx) -- which is what happens to Tracker's frame objects from the second frame on.
+void* ref_frame_stereo(const unsigned char* left, const unsigned char* right, int w, int h, int nfeatures, float sf, int nl, int ini,
+                       int mn, float fx, float fy, float cx, float cy, float bf, float th_depth) {
+  RefFrame* R = new RefFrame();
+  std::memset(R->storage, 0, sizeof(R->storage));
+  R->exL.reset(new ORBextractor(nfeatures, sf, nl, ini, mn));
+  R->exR.reset(new ORBextractor(nfeatures, sf, nl, ini, mn));
+  R->map = std::make_shared<Map>();
+  cv::Mat imL(h, w, CV_8UC1, const_cast<unsigned char*>(left)), imR(h, w, CV_8UC1, const_cast<unsigned char*>(right));
+  cv::Mat K = make_K(fx, fy, cx, cy), D = cv::Mat::zeros(4, 1, CV_32F);
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass) R->f()->~Frame();
+    new (R->storage) Frame(imL, imR, 0.0, R->exL, R->exR, std::shared_ptr<OrbVocabulary>(), K, D, bf, th_depth);
+  }
+  R->live = true;
+  R->f()->SetPose(make_pose(nullptr));
+  return R;
+}
+
+// Frame's monocular constructor (frame.cpp:163-205)
+void* ref_frame_mono(const unsigned char* img, int w, int h, int nfeatures, float sf, int nl, int ini, int mn, float fx, float fy,
+                     float cx, float cy, float bf, float th_depth) {
+  RefFrame* R = new RefFrame();
+  std::memset(R->storage, 0, sizeof(R->storage));
+  R->exL.reset(new ORBextractor(nfeatures, sf, nl, ini, mn));
+  R->map = std::make_shared<Map>();
+  cv::Mat im(h, w, CV_8UC1, const_cast<unsigned char*>(img));
+  cv::Mat K = make_K(fx, fy, cx, cy), D = cv::Mat::zeros(4, 1, CV_32F);
+  new (R->storage) Frame(im, 0.0, R->exL, std::shared_ptr<OrbVocabulary>(), K, D, bf, th_depth);
+  R->live = true;
+  R->f()->SetPose(make_pose(nullptr));
+  return R;
+}
+void ref_frame_destroy(void* p) { delete static_cast<RefFrame*>(p); }
+void ref_frame_set_translation(void* p, const float* t) { static_cast<RefFrame*>(p)->f()->SetPose(make_pose(t)); }
+int ref_frame_n(void* p) { return static_cast<RefFrame*>(p)->f()->NumKeypoints(); }
+int ref_frame_n_right(void* p) { return (int)static_cast<RefFrame*>(p)->f()->GetRightKeys().size(); }
+int ref_frame_levels(void* p) { return static_cast<RefFrame*>(p)->f()->GetScaleLevel(); }
+
+// keypoints_ / undistorted_keypoints_ / descriptors_ / stereo_coords_ / depths_ / bounds / scale factors
+void ref_frame_get(void* p, void* kps, void* kps_un, unsigned char* desc, float* u_right, float* depth, float* bounds, float* scale,
+                   float* misc /* baseline, log_scale_factor */) {
+  Frame* F = static_cast<RefFrame*>(p)->f();
+  const int n = F->NumKeypoints();
+  if (kps && n) std::memcpy(kps, F->GetKeys().data(), (size_t)n * sizeof(cv::KeyPoint));
+  if (kps_un && n) std::memcpy(kps_un, F->GetUndistortedKeys().data(), (size_t)n * sizeof(cv::KeyPoint));
+  if (desc) for (int i = 0; i < n; ++i) std::memcpy(desc + (size_t)i * 32, F->GetDescriptors().ptr(i), 32);
+  if (u_right && !F->StereoCoordRight().empty()) std::memcpy(u_right, F->StereoCoordRight().data(), (size_t)n * sizeof(float));
+  if (depth && !F->StereoDepth().empty()) std::memcpy(depth, F->StereoDepth().data(), (size_t)n * sizeof(float));
+  if (bounds) { bounds[0] = F->GetMinX(); bounds[1] = F->GetMaxX(); bounds[2] = F->GetMinY(); bounds[3] = F->GetMaxY(); }
+  if (scale) for (int l = 0; l < F->GetScaleLevel(); ++l) scale[l] = F->ScaleFactors()[l];
+  if (misc) { misc[0] = F->GetBaseline(); misc[1] = F->GetLogScaleFactor(); }
+}
+void ref_frame_get_right(void* p, void* kps, unsigned char* desc) {
+  Frame* F = static_cast<RefFrame*>(p)->f();
+  const int n = (int)F->GetRightKeys().size();
+  if (n) std::memcpy(kps, F->GetRightKeys().data(), (size_t)n * sizeof(cv::KeyPoint));
+  for (int i = 0; i < n; ++i) std::memcpy(desc + (size_t)i * 32, F->GetRightDescriptors().ptr(i), 32);
+}
+
+// Frame::GetFeaturesInArea (frame.cpp:348-403)
+int ref_features_in_area(void* p, float x, float y, float r, int min_level, int max_level, int* out, int cap) {
+  const std::vector<size_t> v = static_cast<RefFrame*>(p)->f()->GetFeaturesInArea(x, y, r, min_level, max_level);
+  for (size_t i = 0; i < v.size() && (int)i < cap; ++i) out[i] = (int)v[i];
+  return (int)v.size();
+}
+
+// OrbMatcher::SearchForInitialization (orb_matcher.cpp:264-382)
+int ref_search_for_initialization(void* p1, void* p2, float* prev_matched_xy, int* matches12, int window, float nnratio, int check_ori) {
+  Frame *F1 = static_cast<RefFrame*>(p1)->f(), *F2 = static_cast<RefFrame*>(p2)->f();
+  const int n1 = F1->NumKeypoints();
+  std::vector<cv::Point2f> prev((size_t)n1);
+  for (int i = 0; i < n1; ++i) prev[i] = cv::Point2f(prev_matched_xy[2 * i], prev_matched_xy[2 * i + 1]);
+  std::vector<int> m12;
+  OrbMatcher matcher(nnratio, check_ori != 0);
+  const int n = matcher.SearchForInitialization(*F1, *F2, prev, m12, window);
+  for (int i = 0; i < n1; ++i) { matches12[i] = m12[i]; prev_matched_xy[2 * i] = prev[i].x; prev_matched_xy[2 * i + 1] = prev[i].y; }
+  return n;
+}
+
+// builds n map points whose descriptor_ is desc[i] (through the MapPoint(pos, map, frame, idx) constructor on a scratch copy of
+// the frame whose descriptor row 0 is overwritten) at world position pos[i]; has_obs[i] adds one observation
+static void make_points(RefFrame* R, int n, const float* pos, const unsigned char* desc, const unsigned char* has_obs,
+                        std::vector<MapPoint*>& out) {
+  Frame scratch(*R->f());
+  KeyFrame* kf = observer(R);
+  out.assign((size_t)n, nullptr);
+  for (int i = 0; i < n; ++i) {
+    std::memcpy(scratch.GetDescriptors().data, desc + (size_t)i * 32, 32);
+    const float far[3] = {0.f, 0.f, 10.f};
+    MapPoint* mp = new MapPoint(make_vec3(pos ? pos + 3 * i : far), R->map, &scratch, 0);
+    if (has_obs && has_obs[i]) mp->AddObservation(kf, 0);
+    R->owned.emplace_back(mp);
+    out[(size_t)i] = mp;
+  }
+}
+static void set_occupied(RefFrame* R, const unsigned char* occupied) {
+  Frame* F = R->f();
+  const int n = F->NumKeypoints();
+  std::vector<MapPoint*> one;
+  const unsigned char zero[32] = {0}, yes = 1;
+  make_points(R, 1, nullptr, zero, &yes, one);
+  for (int k = 0; k < n; ++k) F->SetMapPoint(k, occupied && occupied[k] ? one[0] : nullptr);
+}
+
+// OrbMatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (orb_matcher.cpp:13-111): the track_* fields are set
+// directly (as Frame::IsInFrustum would)
+int ref_search_by_projection_mappoints(void* p, int n_mp, const unsigned char* valid, const float* px, const float* py,
+                                       const float* pxr, const int* level, const float* view_cos, const unsigned char* desc,
+                                       const unsigned char* has_obs, const unsigned char* occupied, int th, float nnratio,
+                                       int* assigned) {
+  RefFrame* R = static_cast<RefFrame*>(p);
+  Frame* F = R->f();
+  std::vector<MapPoint*> pts;
+  make_points(R, n_mp, nullptr, desc, has_obs, pts);
+  std::map<MapPoint*, int> index;
+  for (int i = 0; i < n_mp; ++i) {
+    MapPoint* m = pts[i];
+    m->track_is_in_view = valid[i] != 0;
+    m->track_projected_x = px[i]; m->track_projected_y = py[i]; m->track_projected_x_right = pxr[i];
+    m->track_scale_level = level[i]; m->track_view_cos = view_cos[i];
+    index[m] = i;
+  }
+  set_occupied(R, occupied);
+  OrbMatcher matcher(nnratio, true);
+  const int n = matcher.SearchByProjection(*F, pts, th);
+  for (int k = 0; k < F->NumKeypoints(); ++k) {
+    std::map<MapPoint*, int>::const_iterator it = index.find(F->GetMapPoint(k));
+    assigned[k] = it == index.end() ? -1 : it->second;
+  }
+  return n;
+}
+
+// OrbMatcher::SearchByProjection(Frame& Cur, const Frame& Last, th, bMono) (orb_matcher.cpp:1312-1453).  Cur has the identity
+// pose, so the projection of :1346-1356 is (fx*X/Z+cx, fy*Y/Z+cy) of the given world positions; Last's translation last_t
+// selects bForward / bBackward (:1330-1335).  valid[i] = Last has a (non-outlier) map point at keypoint i.
+int ref_search_by_projection_lastframe(void* pcur, void* plast, const unsigned char* valid, const float* world_pos,
+                                       const unsigned char* desc, const unsigned char* has_obs, const float* last_t,
+                                       const unsigned char* occupied, float th, int mono, int check_ori, int* assigned) {
+  RefFrame *RC = static_cast<RefFrame*>(pcur), *RL = static_cast<RefFrame*>(plast);
+  Frame *C = RC->f(), *Lf = RL->f();
+  const int nl = Lf->NumKeypoints();
+  std::vector<MapPoint*> pts;
+  make_points(RC, nl, world_pos, desc, has_obs, pts);
+  std::map<MapPoint*, int> index;
+  for (int i = 0; i < nl; ++i) {
+    Lf->SetMapPoint(i, valid[i] ? pts[i] : nullptr);
+    Lf->SetOutlier(i, false);
+    index[pts[i]] = i;
+  }
+  Lf->SetPose(make_pose(last_t));
+  C->SetPose(make_pose(nullptr));
+  set_occupied(RC, occupied);
+  OrbMatcher matcher(0.9f, check_ori != 0);
+  const int n = matcher.SearchByProjection(*C, *Lf, th, mono != 0);
+  for (int k = 0; k < C->NumKeypoints(); ++k) {
+    std::map<MapPoint*, int>::const_iterator it = index.find(C->GetMapPoint(k));
+    assigned[k] = it == index.end() ? -1 : it->second;
+  }
+  return n;
+}
+
+}  // extern "C"

@@ -34,6 +34,20 @@ def lib():
         L.ref_voc_load_text.restype = vp
         L.ref_voc_destroy.argtypes = [vp]
         L.ref_voc_transform.argtypes = [vp, C.c_int, vp, C.c_int] + [vp] * 7
+        L.ref_frame_stereo.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int] + [C.c_float] * 6
+        L.ref_frame_stereo.restype = vp
+        L.ref_frame_mono.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int] + [C.c_float] * 6
+        L.ref_frame_mono.restype = vp
+        L.ref_frame_destroy.argtypes = [vp]
+        L.ref_frame_set_translation.argtypes = [vp, vp]
+        for fn in (L.ref_frame_n, L.ref_frame_n_right, L.ref_frame_levels):
+            fn.argtypes = [vp]
+        L.ref_frame_get.argtypes = [vp] * 9
+        L.ref_frame_get_right.argtypes = [vp] * 3
+        L.ref_features_in_area.argtypes = [vp, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, vp, C.c_int]
+        L.ref_search_for_initialization.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_int]
+        L.ref_search_by_projection_mappoints.argtypes = [vp, C.c_int] + [vp] * 9 + [C.c_int, C.c_float, vp]
+        L.ref_search_by_projection_lastframe.argtypes = [vp, vp] + [vp] * 6 + [C.c_float, C.c_int, C.c_int, vp]
         _lib = L
     return _lib
 
@@ -80,3 +94,68 @@ class Vocabulary:
         lib().ref_voc_transform(self.h, n, _p(d), int(levelsup), _p(bw), _p(bv), C.byref(nb), _p(fn), _p(fs), _p(fi), C.byref(nf))
         nb, nf = nb.value, nf.value
         return dict(bow=(bw[:nb].copy(), bv[:nb].copy()), fv=(fn[:nf].copy(), fs[:nf + 1].copy(), fi[:fs[nf]].copy()))
+
+
+class Frame:
+    """the reference's Frame built by its own stereo / monocular constructor (frame.cpp:61-111, 163-205)"""
+
+    def __init__(self, left, right=None, nfeatures=2000, params=(1.2, 8, 20, 7), fx=718.856, fy=718.856, cx=607.1928, cy=185.2157,
+                 bf=386.1448, th_depth=35.0):
+        left = np.ascontiguousarray(left, np.uint8)
+        h, w = left.shape
+        sf, nl, ini, mn = params
+        if right is None:
+            self.h = lib().ref_frame_mono(left.ctypes.data, w, h, nfeatures, sf, nl, ini, mn, fx, fy, cx, cy, bf, th_depth)
+        else:
+            right = np.ascontiguousarray(right, np.uint8)
+            self.h = lib().ref_frame_stereo(left.ctypes.data, right.ctypes.data, w, h, nfeatures, sf, nl, ini, mn, fx, fy, cx, cy, bf,
+                                            th_depth)
+        n, nl_ = lib().ref_frame_n(self.h), lib().ref_frame_levels(self.h)
+        self.n = n
+        self.kps, self.kps_un = np.zeros(n, KP_DTYPE), np.zeros(n, KP_DTYPE)
+        self.desc = np.zeros((n, 32), np.uint8)
+        self.u_right, self.depth = np.full(n, -1, np.float32), np.full(n, -1, np.float32)
+        self.bounds, self.scale, self.misc = np.zeros(4, np.float32), np.zeros(nl_, np.float32), np.zeros(2, np.float32)
+        lib().ref_frame_get(self.h, _p(self.kps), _p(self.kps_un), _p(self.desc), _p(self.u_right) if right is not None else None,
+                            _p(self.depth) if right is not None else None, _p(self.bounds), _p(self.scale), _p(self.misc))
+        if right is not None:
+            nr = lib().ref_frame_n_right(self.h)
+            self.kps_right, self.desc_right = np.zeros(nr, KP_DTYPE), np.zeros((nr, 32), np.uint8)
+            lib().ref_frame_get_right(self.h, _p(self.kps_right), _p(self.desc_right))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_frame_destroy(self.h)
+            self.h = None
+
+    def features_in_area(self, x, y, r, min_level=-1, max_level=-1):
+        out = np.zeros(self.n + 1, np.int32)
+        n = lib().ref_features_in_area(self.h, x, y, r, min_level, max_level, _p(out), len(out))
+        return out[:n].copy()
+
+
+def _a(x, t):
+    return np.ascontiguousarray(x, t)
+
+
+def search_for_initialization(F1, F2, prev_matched, window, nnratio, check_ori):
+    pm = _a(prev_matched, np.float32).copy()
+    m12 = np.zeros(F1.n, np.int32)
+    n = lib().ref_search_for_initialization(F1.h, F2.h, _p(pm), _p(m12), window, nnratio, int(check_ori))
+    return n, m12, pm
+
+
+def search_by_projection_mappoints(F, valid, px, py, pxr, level, viewcos, mp_desc, has_obs, occupied, th, nnratio):
+    assigned = np.zeros(F.n, np.int32)
+    args = [_a(valid, np.uint8), _a(px, np.float32), _a(py, np.float32), _a(pxr, np.float32), _a(level, np.int32),
+            _a(viewcos, np.float32), _a(mp_desc, np.uint8), _a(has_obs, np.uint8), _a(occupied, np.uint8)]
+    n = lib().ref_search_by_projection_mappoints(F.h, len(args[0]), *[_p(x) for x in args], int(th), nnratio, _p(assigned))
+    return n, assigned
+
+
+def search_by_projection_lastframe(Cur, Last, valid, world_pos, mp_desc, has_obs, last_t, occupied, th, mono, check_ori):
+    assigned = np.zeros(Cur.n, np.int32)
+    n = lib().ref_search_by_projection_lastframe(Cur.h, Last.h, _p(_a(valid, np.uint8)), _p(_a(world_pos, np.float32)),
+                                                 _p(_a(mp_desc, np.uint8)), _p(_a(has_obs, np.uint8)), _p(_a(last_t, np.float32)),
+                                                 _p(_a(occupied, np.uint8)), th, int(mono), int(check_ori), _p(assigned))
+    return n, assigned

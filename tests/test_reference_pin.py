@@ -82,3 +82,107 @@ def test_vocabulary_transform_against_dbow2(tmp_path):
             assert np.array_equal(got["bow"][1], ref["bow"][1]), "BowVector values are not bit-identical to DBoW2's"
             for j in range(3):
                 assert np.array_equal(got["fv"][j], ref["fv"][j]), ("FeatureVector", j, levelsup)
+
+
+# ---- the reference's Frame / OrbMatcher (src/data/frame.cpp, src/orb_features/orb_matcher.cpp) --------------------------
+CAM = dict(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, bf=386.1448)
+
+
+def oracle_frame_of(F):
+    """oracle Frame over the reference Frame's own undistorted keypoints / descriptors / stereo coordinates / bounds"""
+    return O.Frame(F.kps_un, F.desc, F.scale, tuple(float(b) for b in F.bounds), F.u_right)
+
+
+@pytest.mark.parametrize("seed,shape,nf", [(3, (376, 1241), 2000), (11, (376, 1241), 2000), (5, (240, 800), 1000), (8, (376, 1241), 1000)])
+def test_stereo_frame_constructor(seed, shape, nf):
+    """Frame's stereo constructor end to end -- two ORBextractor::Compute on two threads, UndistortKeyPoints,
+    ComputeStereoMatches (frame.cpp:406-577: row table, Hamming search, SAD sub-pixel refinement, median cut) -- against
+    the oracle's extract + stereo_match"""
+    l, r = synth.stereo_pair(*shape, seed=seed)
+    F = R.Frame(l, r, nfeatures=nf)
+    oL, oR = O.Extractor(nf), O.Extractor(nf)
+    okl, odl = oL.extract(l)
+    okr, odr = oR.extract(r)
+    for f in okl.dtype.names:
+        assert np.array_equal(F.kps[f], okl[f]) and np.array_equal(F.kps_right[f], okr[f]), f
+    assert np.array_equal(F.desc, odl) and np.array_equal(F.desc_right, odr)
+    bf, fx = np.float32(CAM["bf"]), np.float32(CAM["fx"])
+    assert F.misc[0] == bf / fx                                       # baseline_ = baseline_fx_ / fx_ (frame.cpp:108)
+    n, ur, dp = O.stereo_match(oL, oR, okl, odl, okr, odr, float(bf), float(bf / fx))
+    assert n == int((F.u_right >= 0).sum()) and n > 100
+    assert np.array_equal(F.u_right, ur), f"{(F.u_right != ur).sum()} stereo coordinates differ from the reference"
+    assert np.array_equal(F.depth, dp)
+
+
+def test_frame_grid_get_features_in_area():
+    F = R.Frame(synth.frame(seed=2))
+    OF = oracle_frame_of(F)
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        x, y = rng.uniform(-30, 1271), rng.uniform(-30, 406)
+        r = float(rng.choice([2.5, 8.0, 30.0, 100.0]))
+        lo, hi = [(-1, -1), (0, 0), (1, 3), (2, -1), (0, 7), (-1, 2)][rng.integers(0, 6)]
+        assert np.array_equal(F.features_in_area(x, y, r, lo, hi), OF.features_in_area(x, y, r, lo, hi)), (x, y, r, lo, hi)
+
+
+def test_search_for_initialization():
+    for seed, (dx, dy) in ((21, (8, 4)), (22, (-8, -4))):
+        a, b = synth.shifted_frame(seed, dx=dx, dy=dy)
+        F1, F2 = R.Frame(a, nfeatures=4000), R.Frame(b, nfeatures=4000)
+        O1, O2 = oracle_frame_of(F1), oracle_frame_of(F2)
+        prev = np.stack([F1.kps_un["x"], F1.kps_un["y"]], 1).astype(np.float32)
+        for window, ratio, ori in ((100, 0.9, True), (50, 0.9, False), (30, 0.7, True)):
+            n, m12, pm = R.search_for_initialization(F1, F2, prev, window, ratio, ori)
+            on, om12, opm = O.search_for_initialization(O1, O2, prev, window, ratio, ori)
+            assert n == on and n > 50, (n, on)
+            assert np.array_equal(m12, om12) and np.array_equal(pm, opm)
+            prev = pm
+
+
+def test_search_by_projection_mappoints():
+    l, r = synth.stereo_pair(seed=31)
+    F = R.Frame(l, r)
+    OF = oracle_frame_of(F)
+    for seed, n_mp, th in ((5, 5000, 1), (6, 3000, 3), (7, 20000, 1)):
+        mp = P.synth_map_points(F.kps_un, F.desc, np.random.default_rng(seed), n_mp, F.u_right)
+        args = (mp["valid"], mp["px"], mp["py"], mp["pxr"], mp["lvl"], mp["view"], mp["desc"], mp["has_obs"], mp["occupied"])
+        n, asg = R.search_by_projection_mappoints(F, *args, th, 0.8)
+        on, oasg = O.search_by_projection_mappoints(OF, *args, th, 0.8)
+        assert n == on and n > 300, (n, on)
+        assert np.array_equal(asg, oasg), f"{(asg != oasg).sum()} assignments differ from the reference"
+
+
+def test_search_by_projection_lastframe():
+    l, r = synth.stereo_pair(seed=33)
+    cur, last = R.Frame(l, r), R.Frame(l, r)
+    OC = oracle_frame_of(cur)
+    n = cur.n
+    rng = np.random.default_rng(9)
+    fx, cx, cy, bf = (np.float32(CAM[k]) for k in ("fx", "cx", "cy", "bf"))
+    z = rng.uniform(3, 60, n).astype(np.float32)
+    z[:7] = -5.0                                                            # behind the camera (:1353)
+    xw = ((last.kps_un["x"] + rng.uniform(-5, 5, n).astype(np.float32) - cx) / fx * z).astype(np.float32)
+    yw = ((last.kps_un["y"] + rng.uniform(-5, 5, n).astype(np.float32) - cy) / fx * z).astype(np.float32)
+    xw[7:12] *= 40                                                          # out of the image (:1359-1366)
+    world = np.stack([xw, yw, z], 1).astype(np.float32)
+    # the projection of :1346-1356 with the identity pose, in the reference's own float / double steps
+    invzc = (1.0 / z.astype(np.float64)).astype(np.float32)
+    u = (fx * xw) * invzc + cx
+    v = (fx * yw) * invzc + cy
+    d = last.desc.copy()
+    d[:, 0] ^= rng.integers(0, 256, n).astype(np.uint8)
+    valid = (rng.uniform(0, 1, n) < 0.9).astype(np.uint8)
+    has_obs = (rng.uniform(0, 1, n) < 0.7).astype(np.uint8)
+    occupied = (rng.uniform(0, 1, n) < 0.05).astype(np.uint8)
+    octv, ang = last.kps["octave"].astype(np.int32), last.kps_un["angle"].copy()
+    base = float(cur.misc[0])
+    for last_t, mono in (((0, 0, 0), False), ((0, 0, 2 * base), False), ((0, 0, -2 * base), False), ((0, 0, 2 * base), True)):
+        # tlc = Rlw*twc + tlw = tlw for identity rotations and the current frame at the origin (:1330-1335)
+        fwd = int(last_t[2] > base and not mono)
+        bwd = int(-last_t[2] > base and not mono)
+        for ori in (True, False):
+            m, asg = R.search_by_projection_lastframe(cur, last, valid, world, d, has_obs, np.array(last_t, np.float32), occupied, 7.0,
+                                                      mono, ori)
+            om, oasg = O.search_by_projection_lastframe(OC, valid, u, v, invzc, octv, ang, d, has_obs, float(bf), fwd, bwd, occupied, 7.0, ori)
+            assert m == om and m > 300, (m, om, last_t, mono, ori)
+            assert np.array_equal(asg, oasg)
