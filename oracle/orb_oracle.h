@@ -10,13 +10,14 @@
  * GaussianBlur, fastAtan2, cvRound), whose arithmetic lives in the un-vendored
  * third-party dependency OpenCV 3.x (find_package(OpenCV 3.0 REQUIRED), CMakeLists.txt:45).
  *
- * PARITY PIN: the reference ships no tests, fixtures or golden vectors for this path and
- * cannot be compiled here (OpenCV C++/Eigen/catkin absent).  The OpenCV primitives are
- * pinned bit-exactly against the Python cv2 4.13.0 build of the same library
- * (tests/test_oracle_primitives.py + tests/golden/ fixtures, generated by
- * tests/golden/make_golden.py).  The control logic above the primitives (grid loop,
- * quad-tree, stereo search, matchers) is restated from the reference sources line by line
- * but is *unpinned by the reference itself* ("parity unpinned" at that level).
+ * PARITY PIN (two layers): the OpenCV primitives are pinned bit-exactly
+ * against the Python cv2 4.13.0 build of the same library (tests/test_oracle_primitives.py +
+ * tests/golden/ fixtures and their generator scripts).  The control logic above them (grid
+ * loop, quad-tree, orientation / descriptor loops, stereo search, grid lookup, the three
+ * matchers of section 8a, DBoW2 transform) is pinned against the reference's OWN sources,
+ * compiled unmodified from /root/reference into oracle/_ref by oracle/Makefile.ref against the
+ * OpenCV stand-in oracle/cvstub (tests/test_reference_pin.py, bit-exact).  Unpinned: the N1
+ * matcher routines (same kernels, restated line by line) and cv::Mat::dot in IsInFrustum.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  The product (slam_framework_b200/) never links or calls it.
