@@ -349,3 +349,35 @@ def test_config3_full_length_sequence_sharded_properties(lib):
     assert seen == set(range(n_total))
     assert total_matches > 300 * n_total
     ex.close()
+
+
+def test_cuda_path_equals_the_references_own_code(lib):
+    """no oracle in between: the sm_100a path against oracle/_ref/libslam_ref.so = the reference's own orb_extractor.cpp +
+    frame.cpp compiled unmodified (oracle/Makefile.ref; the prebuilt file travels to the GPU box).  Frame's stereo
+    constructor there runs both extractions, UndistortKeyPoints and ComputeStereoMatches."""
+    import reference_lib as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libslam_ref.so not present")
+    for seed in (3, 17):
+        l, r = synth.stereo_pair(seed=seed)
+        F = R.Frame(l, r)
+        eL, eR = orbfe.ORBextractor(lib=lib), orbfe.ORBextractor(lib=lib)
+        kl, dl = eL.Compute(l)
+        kr, dr = eR.Compute(r)
+        for f in P.KP_FIELDS:
+            assert np.array_equal(kl[f], F.kps[f]) and np.array_equal(kr[f], F.kps_right[f]), f
+        assert np.array_equal(dl, F.desc) and np.array_equal(dr, F.desc_right)
+        bf, fx = np.float32(P.KITTI["bf"]), np.float32(P.KITTI["fx"])
+        n, ur, dp = orbfe.ComputeStereoMatches(eL, eR, kl, dl, kr, dr, float(bf), float(bf / fx))
+        assert n == int((F.u_right >= 0).sum()) and n > 500
+        assert np.array_equal(ur, F.u_right) and np.array_equal(dp, F.depth)
+        eL.close(); eR.close()
+    # 8000 features on a 1080p frame (config 5) against ORBextractor::Compute itself
+    img = synth.frame(1080, 1920, seed=3)
+    ex = orbfe.ORBextractor(8000, lib=lib)
+    k, d = ex.Compute(img)
+    rk, rd = R.extract(img, 8000)
+    for f in P.KP_FIELDS:
+        assert np.array_equal(k[f], rk[f]), f
+    assert np.array_equal(d, rd)
+    ex.close()
