@@ -301,13 +301,15 @@ int orbfe_undistort_keypoints(int device, int n, const orbfe_keypoint* kps, floa
 
 /* Frame::IsInFrustum (src/data/frame.cpp:277-337) + MapPoint::PredictScale (src/data/map_point.cpp:382-396) for n map
  * points in one launch = the loop of Tracker::SearchLocalPoints (src/core/tracker.cpp:1196-1211).  world_pos / normal:
- * n x 3 floats (GetWorldPos / GetNormal); min_dist / max_dist = Get{Min,Max}DistanceInvariance(); Rcw (row-major 3x3),
+ * n x 3 floats (GetWorldPos / GetNormal); min_dist / max_dist = Get{Min,Max}DistanceInvariance() (the range gate, :306-314);
+ * max_dist_raw = MapPoint::max_dist_ itself, which PredictScale divides by the distance (map_point.cpp:386; the class has
+ * no getter for it: INTEGRATION.md section 4); Rcw (row-major 3x3),
  * tcw, Ow = the frame pose (frame.cpp:270-275).  Outputs = the track_* fields (:328-334), zero where in_view[i] == 0;
  * they are the arrays orbfe_search_by_projection_mappoints takes.  AssignFeaturesToGrid (frame.cpp:234-248), the third
  * piece of this row, is the grid orbfe_frame_create builds on the device. */
 int orbfe_is_in_frustum(int device, int n, const float* world_pos, const float* normal, const float* min_dist,
-                        const float* max_dist, const float* Rcw, const float* tcw, const float* Ow, float fx, float fy,
-                        float cx, float cy, float bf, float min_x, float max_x, float min_y, float max_y,
+                        const float* max_dist, const float* max_dist_raw, const float* Rcw, const float* tcw, const float* Ow,
+                        float fx, float fy, float cx, float cy, float bf, float min_x, float max_x, float min_y, float max_y,
                         float log_scale_factor, int n_levels, float viewing_cos_limit, uint8_t* in_view, float* proj_x,
                         float* proj_y, float* proj_xr, int32_t* scale_level, float* view_cos, int* n_in_view);
 /* parity tap: std::log(float) as PredictScale evaluates it (glibc logf restated on the device), y[i] = logf(x[i]) */

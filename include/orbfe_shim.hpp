@@ -548,8 +548,9 @@ inline void UndistortKeyPoints(const std::vector<cv::KeyPoint>& keypoints, float
 }
 
 // The visibility loop of Tracker::SearchLocalPoints (core/tracker.cpp:1196-1211): Frame::IsInFrustum (frame.cpp:277-337)
-// for every candidate local map point in one launch.  fetch(i, P[3], Pn[3], minDist, maxDist) copies GetWorldPos(),
-// GetNormal(), Get{Min,Max}DistanceInvariance() of vpMapPoints[i] and returns false for points the loop skips
+// for every candidate local map point in one launch.  fetch(i, P[3], Pn[3], minDist, maxDist, maxDistRaw) copies GetWorldPos(),
+// GetNormal(), Get{Min,Max}DistanceInvariance() and max_dist_ (what PredictScale divides, map_point.cpp:386; needs a one-line
+// getter on MapPoint) of vpMapPoints[i] and returns false for points the loop skips
 // (last_frame_id_seen == frame id || isBad(), :1202-1205).  Rcw (row-major) / tcw / Ow = Frame::Rcw_, tcw_, Ow_.
 // Writes the track_* fields exactly as IsInFrustum does and returns the number of visible points (nToMatch).
 template <class MapPointT, class FetchFn>
@@ -557,21 +558,21 @@ int IsInFrustumBatch(const std::vector<MapPointT*>& vpMapPoints, const float Rcw
                      float fx, float fy, float cx, float cy, float baseline_fx, const ImageBounds& b, float log_scale_factor,
                      int scale_levels, float viewingCosLimit, FetchFn fetch, int device = 0) {
   const size_t n = vpMapPoints.size();
-  std::vector<float> P, Pn, mn, mx;
+  std::vector<float> P, Pn, mn, mx, raw;
   std::vector<size_t> idx;
   for (size_t i = 0; i < n; ++i) {
-    float p[3], q[3], a = 0, c = 0;
-    if (!fetch(i, p, q, a, c)) continue;
+    float p[3], q[3], a = 0, c = 0, r = 0;
+    if (!fetch(i, p, q, a, c, r)) continue;
     vpMapPoints[i]->track_is_in_view = false;  // frame.cpp:278
     idx.push_back(i);
-    P.insert(P.end(), p, p + 3); Pn.insert(Pn.end(), q, q + 3); mn.push_back(a); mx.push_back(c);
+    P.insert(P.end(), p, p + 3); Pn.insert(Pn.end(), q, q + 3); mn.push_back(a); mx.push_back(c); raw.push_back(r);
   }
   const int m = (int)idx.size();
   std::vector<uint8_t> in((size_t)m);
   std::vector<float> u((size_t)m), v((size_t)m), ur((size_t)m), vc((size_t)m);
   std::vector<int32_t> lvl((size_t)m);
   int cnt = 0;
-  check(orbfe_is_in_frustum(device, m, P.data(), Pn.data(), mn.data(), mx.data(), Rcw, tcw, Ow, fx, fy, cx, cy, baseline_fx, b.minX,
+  check(orbfe_is_in_frustum(device, m, P.data(), Pn.data(), mn.data(), mx.data(), raw.data(), Rcw, tcw, Ow, fx, fy, cx, cy, baseline_fx, b.minX,
                             b.maxX, b.minY, b.maxY, log_scale_factor, scale_levels, viewingCosLimit, in.data(), u.data(), v.data(),
                             ur.data(), lvl.data(), vc.data(), &cnt),
         "orbfe_is_in_frustum");

@@ -1511,8 +1511,10 @@ void orc_undistort_points(int n, const float* xy_in, float fxf, float fyf, float
 }
 
 // Frame::IsInFrustum for n map points (the loop of Tracker::SearchLocalPoints, core/tracker.cpp:1196-1211).
-// world/normal: n x 3; Rcw row-major; outputs = the track_* fields (frame.cpp:328-334).  Returns the number in view.
+// world/normal: n x 3; min_dist / max_dist = Get{Min,Max}DistanceInvariance() (0.8f * min_dist_, 1.2f * max_dist_), max_dist_raw =
+// MapPoint::max_dist_ itself; Rcw row-major; outputs = the track_* fields (frame.cpp:328-334).  Returns the number in view.
 int orc_is_in_frustum(int n, const float* world, const float* normal, const float* min_dist, const float* max_dist,
+                      const float* max_dist_raw,
                       const float* Rcw, const float* tcw, const float* Ow, float fx, float fy, float cx, float cy, float bf,
                       float min_x, float max_x, float min_y, float max_y, float log_scale_factor, int n_levels,
                       float viewing_cos_limit, uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* level,
@@ -1544,7 +1546,7 @@ int orc_is_in_frustum(int n, const float* world, const float* normal, const floa
     const float viewCos = (float)(dot / dist);
     if (viewCos < viewing_cos_limit) continue;
     // MapPoint::PredictScale (map_point.cpp:382-396)
-    const float ratio = max_dist[i] / dist;
+    const float ratio = max_dist_raw[i] / dist;  // PredictScale divides the RAW max_dist_, not 1.2f * max_dist_ (map_point.cpp:386 vs :363)
     int nScale = (int)std::ceil(std::log(ratio) / log_scale_factor);
     if (nScale < 0) nScale = 0;
     else if (nScale >= n_levels) nScale = n_levels - 1;

@@ -182,6 +182,7 @@ int orc_bow_transform(const orc_vocabulary* v, int n, const uint8_t* desc, int l
 void orc_undistort_points(int n, const float* xy_in, float fx, float fy, float cx, float cy, const float* dist, int n_dist,
                           float* xy_out);
 int orc_is_in_frustum(int n, const float* world, const float* normal, const float* min_dist, const float* max_dist,
+                      const float* max_dist_raw,
                       const float* Rcw, const float* tcw, const float* Ow, float fx, float fy, float cx, float cy, float bf,
                       float min_x, float max_x, float min_y, float max_y, float log_scale_factor, int n_levels,
                       float viewing_cos_limit, uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr, int* level,

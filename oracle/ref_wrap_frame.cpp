@@ -8,6 +8,8 @@
 #include "data/map_point.h"
 #include "orb_features/orb_matcher.h"
 #include "util/converter.h"
+#include "DBoW2/FORB.h"
+#include "DBoW2/TemplatedVocabulary.h"
 
 #include <cstring>
 #include <map>
@@ -22,7 +24,10 @@ std::vector<cv::Mat> Converter::toDescriptorVector(const cv::Mat& Descriptors) {
   return vDesc;
 }
 
+typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> RefVoc;
 namespace {
+RefVoc* g_voc = nullptr;  // vocabulary handed to the Frames constructed next (ref_set_vocabulary); not owned
+std::shared_ptr<OrbVocabulary> voc_ptr() { return std::shared_ptr<OrbVocabulary>(g_voc, [](OrbVocabulary*) {}); }
 struct RefFrame {
   alignas(Frame) unsigned char storage[sizeof(Frame)];
   bool live = false;
@@ -71,10 +76,11 @@ void* ref_frame_stereo(const unsigned char* left, const unsigned char* right, in
   cv::Mat K = make_K(fx, fy, cx, cy), D = cv::Mat::zeros(4, 1, CV_32F);
   for (int pass = 0; pass < 2; ++pass) {
     if (pass) R->f()->~Frame();
-    new (R->storage) Frame(imL, imR, 0.0, R->exL, R->exR, std::shared_ptr<OrbVocabulary>(), K, D, bf, th_depth);
+    new (R->storage) Frame(imL, imR, 0.0, R->exL, R->exR, voc_ptr(), K, D, bf, th_depth);
   }
   R->live = true;
   R->f()->SetPose(make_pose(nullptr));
+  if (g_voc) R->f()->ComputeBoW();  // frame.cpp:258-263
   return R;
 }
 
@@ -87,12 +93,14 @@ void* ref_frame_mono(const unsigned char* img, int w, int h, int nfeatures, floa
   R->map = std::make_shared<Map>();
   cv::Mat im(h, w, CV_8UC1, const_cast<unsigned char*>(img));
   cv::Mat K = make_K(fx, fy, cx, cy), D = cv::Mat::zeros(4, 1, CV_32F);
-  new (R->storage) Frame(im, 0.0, R->exL, std::shared_ptr<OrbVocabulary>(), K, D, bf, th_depth);
+  new (R->storage) Frame(im, 0.0, R->exL, voc_ptr(), K, D, bf, th_depth);
   R->live = true;
   R->f()->SetPose(make_pose(nullptr));
+  if (g_voc) R->f()->ComputeBoW();
   return R;
 }
 void ref_frame_destroy(void* p) { delete static_cast<RefFrame*>(p); }
+void ref_set_vocabulary(void* voc) { g_voc = static_cast<RefVoc*>(voc); }
 void ref_frame_set_translation(void* p, const float* t) { static_cast<RefFrame*>(p)->f()->SetPose(make_pose(t)); }
 int ref_frame_n(void* p) { return static_cast<RefFrame*>(p)->f()->NumKeypoints(); }
 int ref_frame_n_right(void* p) { return (int)static_cast<RefFrame*>(p)->f()->GetRightKeys().size(); }
@@ -219,6 +227,146 @@ int ref_search_by_projection_lastframe(void* pcur, void* plast, const unsigned c
     assigned[k] = it == index.end() ? -1 : it->second;
   }
   return n;
+}
+
+
+// ---- vocabulary-node searches on the reference's own KeyFrame objects -----------------------------------
+
+// Frame::ComputeBoW (frame.cpp:258-263) with the vocabulary loaded by ref_voc_load_text; outputs flattened like
+// ref_voc_transform
+// what Frame::ComputeBoW (frame.cpp:258-263) left in bow_vec_ / feature_vec_, flattened like ref_voc_transform
+void ref_frame_get_bow(void* p, unsigned* bow_words, double* bow_values, int* n_bow, unsigned* fv_nodes, int* fv_start,
+                       unsigned* fv_idx, int* n_fv) {
+  Frame* F = static_cast<RefFrame*>(p)->f();
+  const DBoW2::BowVector& bv = F->GetBowVector();
+  const DBoW2::FeatureVector& fv = F->GetFeatureVector();
+  int u = 0;
+  for (DBoW2::BowVector::const_iterator it = bv.begin(); it != bv.end(); ++it, ++u) { bow_words[u] = it->first; bow_values[u] = it->second; }
+  *n_bow = u;
+  int f = 0, q = 0;
+  for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it, ++f) {
+    fv_nodes[f] = it->first;
+    fv_start[f] = q;
+    for (size_t k = 0; k < it->second.size(); ++k) fv_idx[q++] = it->second[k];
+  }
+  fv_start[f] = q;
+  *n_fv = f;
+}
+
+struct RefKeyFrame {
+  RefFrame* owner;
+  std::unique_ptr<KeyFrame> kf;
+  std::vector<MapPoint*> pts;  // the map point created for keypoint i (or null)
+};
+
+// KeyFrame(frame, map, kfdb) (keyframe.cpp:20-80) + KeyFrame::ComputeBoW (:127-137); valid[i] gives
+// keypoint i a (good) map point, bad[i] makes it isBad()
+void* ref_keyframe_create(void* pframe, const unsigned char* valid, const unsigned char* bad, const float* translation) {
+  RefFrame* R = static_cast<RefFrame*>(pframe);
+  RefKeyFrame* K = new RefKeyFrame();
+  K->owner = R;
+  K->kf.reset(new KeyFrame(*R->f(), R->map, std::shared_ptr<KeyframeDatabase>()));  // copies the frame's bow_vec_ / feature_vec_
+  if (R->f()->GetVocabulary()) K->kf->ComputeBoW();                                  // keyframe.cpp:127-137 (no-op when filled)
+  K->kf->SetPose(make_pose(translation));
+  const int n = R->f()->NumKeypoints();
+  K->pts.assign((size_t)n, nullptr);
+  if (valid) {
+    std::vector<unsigned char> d((size_t)n * 32);
+    for (int i = 0; i < n; ++i) std::memcpy(d.data() + (size_t)i * 32, K->kf->descriptors.ptr(i), 32);
+    std::vector<MapPoint*> pts;
+    make_points(R, n, nullptr, d.data(), nullptr, pts);
+    for (int i = 0; i < n; ++i)
+      if (valid[i]) {
+        K->pts[i] = pts[i];
+        K->kf->AddMapPoint(pts[i], i);
+        pts[i]->AddObservation(K->kf.get(), i);
+        if (bad && bad[i]) pts[i]->SetBadFlag();
+      }
+  }
+  return K;
+}
+void ref_keyframe_destroy(void* p) { delete static_cast<RefKeyFrame*>(p); }
+
+// OrbMatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (orb_matcher.cpp:133-262).  The Frame's feature vector is
+// private state filled by Frame::ComputeBoW, which needs the vocabulary passed to the constructor: ref_frame_*_voc below.
+int ref_search_by_bow_kf_f(void* pkf, void* pframe, float nnratio, int check_ori, int* matched_kf_idx) {
+  RefKeyFrame* K = static_cast<RefKeyFrame*>(pkf);
+  Frame* F = static_cast<RefFrame*>(pframe)->f();
+  std::map<MapPoint*, int> index;
+  for (size_t i = 0; i < K->pts.size(); ++i) if (K->pts[i]) index[K->pts[i]] = (int)i;
+  std::vector<MapPoint*> matches;
+  OrbMatcher matcher(nnratio, check_ori != 0);
+  const int n = matcher.SearchByBoW(K->kf.get(), *F, matches);
+  for (int k = 0; k < F->NumKeypoints(); ++k) {
+    std::map<MapPoint*, int>::const_iterator it = index.find(matches[k]);
+    matched_kf_idx[k] = it == index.end() ? -1 : it->second;
+  }
+  return n;
+}
+
+// OrbMatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (orb_matcher.cpp:499-632)
+int ref_search_by_bow_kf_kf(void* pkf1, void* pkf2, float nnratio, int check_ori, int* matches12) {
+  RefKeyFrame *K1 = static_cast<RefKeyFrame*>(pkf1), *K2 = static_cast<RefKeyFrame*>(pkf2);
+  std::map<MapPoint*, int> index2;
+  for (size_t i = 0; i < K2->pts.size(); ++i) if (K2->pts[i]) index2[K2->pts[i]] = (int)i;
+  std::vector<MapPoint*> m12;
+  OrbMatcher matcher(nnratio, check_ori != 0);
+  const int n = matcher.SearchByBoW(K1->kf.get(), K2->kf.get(), m12);
+  for (size_t i = 0; i < m12.size(); ++i) {
+    std::map<MapPoint*, int>::const_iterator it = index2.find(m12[i]);
+    matches12[i] = it == index2.end() ? -1 : it->second;
+  }
+  return n;
+}
+
+// OrbMatcher::SearchForTriangulation (orb_matcher.cpp:634-802); the epipole is computed inside from the two poses
+int ref_search_for_triangulation(void* pkf1, void* pkf2, const float* F12, int only_stereo, float nnratio, int check_ori, int* matches12) {
+  RefKeyFrame *K1 = static_cast<RefKeyFrame*>(pkf1), *K2 = static_cast<RefKeyFrame*>(pkf2);
+  cv::Mat F(3, 3, CV_32F);
+  for (int i = 0; i < 9; ++i) F.at<float>(i / 3, i % 3) = F12[i];
+  std::vector<std::pair<size_t, size_t> > pairs;
+  OrbMatcher matcher(nnratio, check_ori != 0);
+  const int n = matcher.SearchForTriangulation(K1->kf.get(), K2->kf.get(), F, pairs, only_stereo != 0);
+  const int n1 = K1->owner->f()->NumKeypoints();
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  for (size_t k = 0; k < pairs.size(); ++k) matches12[pairs[k].first] = (int)pairs[k].second;
+  return n;
+}
+
+// Frame::IsInFrustum (frame.cpp:277-337) for n map points created (MapPoint(pos, map, frame, idx), map_point.cpp:40-80) while the
+// frame sits at the origin, then tested from the pose `translation`.  idx[i] = the keypoint whose octave sets the point's
+// scale range.  Also returns what the point holds (normal, min / max distance) so that the oracle can be fed the same.
+int ref_is_in_frustum(void* pframe, int n, const float* world_pos, const int* idx, const float* translation, float viewing_cos_limit,
+                      float* normal_out, float* min_dist_out, float* max_dist_out, float* ow_out, unsigned char* in_view, float* proj_x,
+                      float* proj_y, float* proj_xr, int* level, float* view_cos) {
+  RefFrame* R = static_cast<RefFrame*>(pframe);
+  Frame* F = R->f();
+  F->SetPose(make_pose(nullptr));
+  std::vector<MapPoint*> pts((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    pts[i] = new MapPoint(make_vec3(world_pos + 3 * i), R->map, F, idx[i]);
+    R->owned.emplace_back(pts[i]);
+  }
+  F->SetPose(make_pose(translation));
+  const cv::Mat Ow = F->GetCameraCenter();
+  for (int c = 0; c < 3; ++c) ow_out[c] = Ow.at<float>(c);
+  int count = 0;
+  for (int i = 0; i < n; ++i) {
+    MapPoint* m = pts[i];
+    const cv::Mat nrm = m->GetNormal();
+    for (int c = 0; c < 3; ++c) normal_out[3 * i + c] = nrm.at<float>(c);
+    min_dist_out[i] = m->GetMinDistanceInvariance();
+    max_dist_out[i] = m->GetMaxDistanceInvariance();
+    const bool ok = F->IsInFrustum(m, viewing_cos_limit);
+    in_view[i] = ok ? 1 : 0;
+    proj_x[i] = ok ? m->track_projected_x : 0.f;
+    proj_y[i] = ok ? m->track_projected_y : 0.f;
+    proj_xr[i] = ok ? m->track_projected_x_right : 0.f;
+    level[i] = ok ? m->track_scale_level : 0;
+    view_cos[i] = ok ? m->track_view_cos : 0.f;
+    count += ok;
+  }
+  return count;
 }
 
 }  // extern "C"

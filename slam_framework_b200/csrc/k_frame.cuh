@@ -106,7 +106,8 @@ struct FrustumArgs {
 
 __global__ void __launch_bounds__(256)
 k_is_in_frustum(const FrustumArgs A, const int n, const float* __restrict__ world, const float* __restrict__ normal,
-                const float* __restrict__ minDist, const float* __restrict__ maxDist, uint8_t* __restrict__ inView,
+                const float* __restrict__ minDist, const float* __restrict__ maxDist, const float* __restrict__ maxDistRaw,
+                uint8_t* __restrict__ inView,
                 float* __restrict__ projX, float* __restrict__ projY, float* __restrict__ projXR, int* __restrict__ level,
                 float* __restrict__ viewCosOut, int* __restrict__ count) {
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -135,7 +136,7 @@ k_is_in_frustum(const FrustumArgs A, const int n, const float* __restrict__ worl
       if (viewCos < A.viewingCosLimit) ok = false;
     }
     if (ok) {
-      const float ratio = __fdiv_rn(maxDist[i], dist);
+      const float ratio = __fdiv_rn(maxDistRaw[i], dist);  // max_dist_ itself, not the 1.2x invariance bound (map_point.cpp:386)
       nScale = (int)ceilf(__fdiv_rn(orbfe_glibc_logf(ratio), A.logScaleFactor));
       if (nScale < 0) nScale = 0;
       else if (nScale >= A.nLevels) nScale = A.nLevels - 1;

@@ -69,12 +69,12 @@ int orbfe_undistort_keypoints(int device, int n, const orbfe_keypoint* kps, floa
 }
 
 int orbfe_is_in_frustum(int device, int n, const float* world_pos, const float* normal, const float* min_dist,
-                        const float* max_dist, const float* Rcw, const float* tcw, const float* Ow, float fx, float fy,
-                        float cx, float cy, float bf, float min_x, float max_x, float min_y, float max_y,
+                        const float* max_dist, const float* max_dist_raw, const float* Rcw, const float* tcw, const float* Ow,
+                        float fx, float fy, float cx, float cy, float bf, float min_x, float max_x, float min_y, float max_y,
                         float log_scale_factor, int n_levels, float viewing_cos_limit, uint8_t* in_view, float* proj_x,
                         float* proj_y, float* proj_xr, int32_t* scale_level, float* view_cos, int* n_in_view) {
   if (n < 0 || !Rcw || !tcw || !Ow || n_levels < 1) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
-  if (n && (!world_pos || !normal || !min_dist || !max_dist || !in_view || !proj_x || !proj_y || !proj_xr || !scale_level || !view_cos))
+  if (n && (!world_pos || !normal || !min_dist || !max_dist || !max_dist_raw || !in_view || !proj_x || !proj_y || !proj_xr || !scale_level || !view_cos))
     return orbfe_fail(ORBFE_ERR_INVALID, "null array");
   if (n_in_view) *n_in_view = 0;
   int rc;
@@ -88,10 +88,10 @@ int orbfe_is_in_frustum(int device, int n, const float* world_pos, const float* 
   F.logScaleFactor = log_scale_factor; F.viewingCosLimit = viewing_cos_limit; F.nLevels = n_levels;
   const size_t N = (size_t)n;
   DeviceArena A;
-  A.cap = 2 * DeviceArena::pad(N * 12) + 7 * DeviceArena::pad(N * 4) + DeviceArena::pad(N) + 256;
+  A.cap = 2 * DeviceArena::pad(N * 12) + 8 * DeviceArena::pad(N * 4) + DeviceArena::pad(N) + 256;
   CUDA_TRY(cudaMalloc(&A.base, A.cap));
   float* d_w = A.take<float>(N * 3); float* d_n = A.take<float>(N * 3);
-  float* d_min = A.take<float>(N); float* d_max = A.take<float>(N);
+  float* d_min = A.take<float>(N); float* d_max = A.take<float>(N); float* d_raw = A.take<float>(N);
   float* d_px = A.take<float>(N); float* d_py = A.take<float>(N); float* d_pxr = A.take<float>(N); float* d_vc = A.take<float>(N);
   int* d_lvl = A.take<int>(N);
   uint8_t* d_in = A.take<uint8_t>(N);
@@ -100,8 +100,9 @@ int orbfe_is_in_frustum(int device, int n, const float* world_pos, const float* 
   CUDA_TRY(cudaMemcpy(d_n, normal, N * 12, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(d_min, min_dist, N * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(d_max, max_dist, N * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(d_raw, max_dist_raw, N * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemset(d_cnt, 0, sizeof(int)));
-  FRAME_LAUNCH(k_is_in_frustum, dim3((n + 255) / 256), dim3(256), F, n, d_w, d_n, d_min, d_max, d_in, d_px, d_py, d_pxr, d_lvl,
+  FRAME_LAUNCH(k_is_in_frustum, dim3((n + 255) / 256), dim3(256), F, n, d_w, d_n, d_min, d_max, d_raw, d_in, d_px, d_py, d_pxr, d_lvl,
                d_vc, d_cnt);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpy(in_view, d_in, N, cudaMemcpyDeviceToHost));

@@ -123,7 +123,7 @@ def load(path=None, _test_emulation=False):
     L.orbfe_vocabulary_info.argtypes = [vp] + [vp] * 6
     L.orbfe_bow_transform.argtypes = [vp, i, vp, i] + [vp] * 9
     L.orbfe_undistort_keypoints.argtypes = [i, i, vp, f, f, f, f, vp, i, vp]
-    L.orbfe_is_in_frustum.argtypes = [i, i] + [vp] * 7 + [f] * 10 + [i, f] + [vp] * 7
+    L.orbfe_is_in_frustum.argtypes = [i, i] + [vp] * 8 + [f] * 10 + [i, f] + [vp] * 7
     L.orbfe_debug_logf.argtypes = [i, i, vp, vp]
     _libs[path] = L
     return L
@@ -600,7 +600,7 @@ def UndistortKeyPoints(kps, fx, fy, cx, cy, dist_coeffs, device=0, lib=None):
     return out
 
 
-def IsInFrustum(world, normal, min_dist, max_dist, Rcw, tcw, Ow, fx, fy, cx, cy, bf, bounds, log_scale_factor, n_levels,
+def IsInFrustum(world, normal, min_dist, max_dist, max_dist_raw, Rcw, tcw, Ow, fx, fy, cx, cy, bf, bounds, log_scale_factor, n_levels,
                 viewingCosLimit=0.5, device=0, lib=None):
     """Frame::IsInFrustum over a batch (frame.cpp:277-337) -> (n_in_view, dict of the track_* arrays)"""
     L = lib or load()
@@ -609,7 +609,7 @@ def IsInFrustum(world, normal, min_dist, max_dist, Rcw, tcw, Ow, fx, fy, cx, cy,
     out = dict(in_view=np.zeros(n, np.uint8), proj_x=np.zeros(n, np.float32), proj_y=np.zeros(n, np.float32),
                proj_xr=np.zeros(n, np.float32), level=np.zeros(n, np.int32), view_cos=np.zeros(n, np.float32))
     cnt = C.c_int()
-    _check(L, L.orbfe_is_in_frustum(device, n, _p(w), _p(nrm), _p(_a(min_dist, np.float32)), _p(_a(max_dist, np.float32)),
+    _check(L, L.orbfe_is_in_frustum(device, n, _p(w), _p(nrm), _p(_a(min_dist, np.float32)), _p(_a(max_dist, np.float32)), _p(_a(max_dist_raw, np.float32)),
                                     _p(_a(Rcw, np.float32).reshape(9)), _p(_a(tcw, np.float32).reshape(3)),
                                     _p(_a(Ow, np.float32).reshape(3)), fx, fy, cx, cy, bf, bounds[0], bounds[1], bounds[2], bounds[3],
                                     log_scale_factor, n_levels, viewingCosLimit, _p(out["in_view"]), _p(out["proj_x"]),

@@ -77,7 +77,7 @@ def lib():
         L.orc_bow_transform.argtypes = [vp, C.c_int, vp, C.c_int] + [vp] * 9
         L.orc_undistort_points.argtypes = [C.c_int, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, C.c_int, vp]
         L.orc_undistort_points.restype = None
-        L.orc_is_in_frustum.argtypes = [C.c_int] + [vp] * 7 + [C.c_float] * 10 + [C.c_int, C.c_float] + [vp] * 6
+        L.orc_is_in_frustum.argtypes = [C.c_int] + [vp] * 8 + [C.c_float] * 10 + [C.c_int, C.c_float] + [vp] * 6
         L.orc_bench_stereo_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                                              C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, vp, vp]
         L.orc_bench_stereo_batch.restype = C.c_double
@@ -368,13 +368,13 @@ def undistort_points(xy, fx, fy, cx, cy, dist):
     return out
 
 
-def is_in_frustum(world, normal, min_dist, max_dist, Rcw, tcw, Ow, fx, fy, cx, cy, bf, bounds, log_scale_factor, n_levels,
+def is_in_frustum(world, normal, min_dist, max_dist, max_dist_raw, Rcw, tcw, Ow, fx, fy, cx, cy, bf, bounds, log_scale_factor, n_levels,
                   viewing_cos_limit=0.5):
     w, nrm = _a(world, np.float32).reshape(-1, 3), _a(normal, np.float32).reshape(-1, 3)
     n = len(w)
     out = dict(in_view=np.zeros(n, np.uint8), proj_x=np.zeros(n, np.float32), proj_y=np.zeros(n, np.float32),
                proj_xr=np.zeros(n, np.float32), level=np.zeros(n, np.int32), view_cos=np.zeros(n, np.float32))
-    cnt = lib().orc_is_in_frustum(n, _p(w), _p(nrm), _p(_a(min_dist, np.float32)), _p(_a(max_dist, np.float32)),
+    cnt = lib().orc_is_in_frustum(n, _p(w), _p(nrm), _p(_a(min_dist, np.float32)), _p(_a(max_dist, np.float32)), _p(_a(max_dist_raw, np.float32)),
                                   _p(_a(Rcw, np.float32).reshape(9)), _p(_a(tcw, np.float32).reshape(3)), _p(_a(Ow, np.float32).reshape(3)),
                                   fx, fy, cx, cy, bf, bounds[0], bounds[1], bounds[2], bounds[3], log_scale_factor, n_levels,
                                   viewing_cos_limit, _p(out["in_view"]), _p(out["proj_x"]), _p(out["proj_y"]), _p(out["proj_xr"]),

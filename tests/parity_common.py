@@ -502,7 +502,10 @@ def synth_local_map(rng, n, fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, w=
     kk = rng.integers(0, 8, n)
     onb = rng.uniform(0, 1, n) < 0.05
     maxd[onb] = (d[onb].astype(np.float32) * np.float32(1.2) ** kk[onb].astype(np.float32)).astype(np.float32)
-    return dict(world=Pw, normal=nrm, min_dist=mind, max_dist=maxd, Rcw=R, tcw=t, Ow=Ow, fx=fx, fy=fy, cx=cx, cy=cy,
+    # the reference holds max_dist_ / min_dist_ and exposes 1.2f * max_dist_ / 0.8f * min_dist_ (map_point.cpp:356-364)
+    raw = maxd
+    maxd, mind = (np.float32(1.2) * raw).astype(np.float32), (np.float32(0.8) * mind).astype(np.float32)
+    return dict(world=Pw, normal=nrm, min_dist=mind, max_dist=maxd, max_dist_raw=raw, Rcw=R, tcw=t, Ow=Ow, fx=fx, fy=fy, cx=cx, cy=cy,
                 bounds=(0.0, float(w), 0.0, float(h)))
 
 
@@ -510,7 +513,7 @@ def check_is_in_frustum(lib, n=20000, seed=0):
     rng = np.random.default_rng(seed)
     m = synth_local_map(rng, n)
     lsf = float(np.log(np.float32(1.2)).astype(np.float32))   # log_scale_factor_ = log(scale_factor_) as float
-    args = (m["world"], m["normal"], m["min_dist"], m["max_dist"], m["Rcw"], m["tcw"], m["Ow"], m["fx"], m["fy"], m["cx"], m["cy"],
+    args = (m["world"], m["normal"], m["min_dist"], m["max_dist"], m["max_dist_raw"], m["Rcw"], m["tcw"], m["Ow"], m["fx"], m["fy"], m["cx"], m["cy"],
             KITTI["bf"], m["bounds"], lsf, 8, 0.5)
     cnt, got = orbfe.IsInFrustum(*args, lib=lib)
     ocnt, ref = O.is_in_frustum(*args)

@@ -48,6 +48,15 @@ def lib():
         L.ref_search_for_initialization.argtypes = [vp, vp, vp, vp, C.c_int, C.c_float, C.c_int]
         L.ref_search_by_projection_mappoints.argtypes = [vp, C.c_int] + [vp] * 9 + [C.c_int, C.c_float, vp]
         L.ref_search_by_projection_lastframe.argtypes = [vp, vp] + [vp] * 6 + [C.c_float, C.c_int, C.c_int, vp]
+        L.ref_set_vocabulary.argtypes = [vp]
+        L.ref_frame_get_bow.argtypes = [vp] * 8
+        L.ref_keyframe_create.argtypes = [vp, vp, vp, vp]
+        L.ref_keyframe_create.restype = vp
+        L.ref_keyframe_destroy.argtypes = [vp]
+        L.ref_search_by_bow_kf_f.argtypes = [vp, vp, C.c_float, C.c_int, vp]
+        L.ref_search_by_bow_kf_kf.argtypes = [vp, vp, C.c_float, C.c_int, vp]
+        L.ref_search_for_triangulation.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_int, vp]
+        L.ref_is_in_frustum.argtypes = [vp, C.c_int, vp, vp, vp, C.c_float] + [vp] * 10
         _lib = L
     return _lib
 
@@ -159,3 +168,64 @@ def search_by_projection_lastframe(Cur, Last, valid, world_pos, mp_desc, has_obs
                                                  _p(_a(mp_desc, np.uint8)), _p(_a(has_obs, np.uint8)), _p(_a(last_t, np.float32)),
                                                  _p(_a(occupied, np.uint8)), th, int(mono), int(check_ori), _p(assigned))
     return n, assigned
+
+
+def set_vocabulary(voc):
+    """Frames constructed from now on carry this vocabulary and run Frame::ComputeBoW (None: no vocabulary)"""
+    lib().ref_set_vocabulary(voc.h if voc is not None else None)
+
+
+def frame_bow(F):
+    n = F.n
+    bw, bv = np.zeros(n, np.uint32), np.zeros(n, np.float64)
+    fn, fs, fi = np.zeros(n, np.uint32), np.zeros(n + 1, np.int32), np.zeros(n, np.uint32)
+    nb, nf = C.c_int(), C.c_int()
+    lib().ref_frame_get_bow(F.h, _p(bw), _p(bv), C.byref(nb), _p(fn), _p(fs), _p(fi), C.byref(nf))
+    nb, nf = nb.value, nf.value
+    return dict(bow=(bw[:nb].copy(), bv[:nb].copy()), fv=(fn[:nf].copy(), fs[:nf + 1].copy(), fi[:fs[nf]].copy()))
+
+
+class KeyFrame:
+    """the reference's KeyFrame built from a reference Frame; valid[i] gives keypoint i a map point, bad[i] flags it bad"""
+
+    def __init__(self, F, valid=None, bad=None, translation=(0.0, 0.0, 0.0)):
+        self.F = F
+        v = None if valid is None else _a(valid, np.uint8)
+        b = None if bad is None else _a(bad, np.uint8)
+        self.h = lib().ref_keyframe_create(F.h, _p(v), _p(b), _p(_a(translation, np.float32)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_keyframe_destroy(self.h)
+            self.h = None
+
+
+def search_by_bow_kf_f(KF, F, nnratio, check_ori):
+    out = np.zeros(F.n, np.int32)
+    n = lib().ref_search_by_bow_kf_f(KF.h, F.h, nnratio, int(check_ori), _p(out))
+    return n, out
+
+
+def search_by_bow_kf_kf(KF1, KF2, nnratio, check_ori):
+    out = np.zeros(KF1.F.n, np.int32)
+    n = lib().ref_search_by_bow_kf_kf(KF1.h, KF2.h, nnratio, int(check_ori), _p(out))
+    return n, out
+
+
+def search_for_triangulation(KF1, KF2, F12, only_stereo, check_ori):
+    out = np.zeros(KF1.F.n, np.int32)
+    F = _a(np.asarray(F12, np.float32).reshape(9), np.float32)
+    n = lib().ref_search_for_triangulation(KF1.h, KF2.h, _p(F), int(only_stereo), 0.6, int(check_ori), _p(out))
+    return n, out
+
+
+def is_in_frustum(F, world, idx, translation, viewing_cos_limit=0.5):
+    w = _a(world, np.float32).reshape(-1, 3)
+    n = len(w)
+    nrm, mn, mx, ow = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(3, np.float32)
+    out = dict(in_view=np.zeros(n, np.uint8), proj_x=np.zeros(n, np.float32), proj_y=np.zeros(n, np.float32),
+               proj_xr=np.zeros(n, np.float32), level=np.zeros(n, np.int32), view_cos=np.zeros(n, np.float32))
+    cnt = lib().ref_is_in_frustum(F.h, n, _p(w), _p(_a(idx, np.int32)), _p(_a(translation, np.float32)), viewing_cos_limit, _p(nrm), _p(mn),
+                                  _p(mx), _p(ow), _p(out["in_view"]), _p(out["proj_x"]), _p(out["proj_y"]), _p(out["proj_xr"]),
+                                  _p(out["level"]), _p(out["view_cos"]))
+    return cnt, out, dict(normal=nrm, min_dist=mn, max_dist=mx, Ow=ow)

@@ -108,11 +108,11 @@ static int n1_selfcheck(const std::vector<cv::KeyPoint>& kps, const cv::Mat& des
   for (size_t i = 0; i < n; ++i) moved += und[i].pt.x != kps[i].pt.x || und[i].pt.y != kps[i].pt.y;
   const float I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Z3[3] = {0, 0, 0};
   const float fx = 718.856f, cx0 = 607.1928f, cy0 = 185.2157f;
-  auto fetch = [&](size_t i, float* Pw, float* Pn, float& mn, float& mx) {
+  auto fetch = [&](size_t i, float* Pw, float* Pn, float& mn, float& mx, float& raw) {
     Pw[0] = (kps[i].pt.x - cx0) / fx * 10.f; Pw[1] = (kps[i].pt.y - cy0) / fx * 10.f; Pw[2] = 10.f;
     const float len = std::sqrt(Pw[0] * Pw[0] + Pw[1] * Pw[1] + Pw[2] * Pw[2]);
     for (int c2 = 0; c2 < 3; ++c2) Pn[c2] = Pw[c2] / len;
-    mn = 1.f; mx = 40.f;
+    mn = 1.f; mx = 40.f; raw = 40.f / 1.2f;
     return true;
   };
   const int vis = orbfe::IsInFrustumBatch(mpv, I3, Z3, Z3, fx, fx, cx0, cy0, 386.1448f, b, std::log(1.2f), 8, 0.5f, fetch);

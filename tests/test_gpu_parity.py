@@ -292,7 +292,7 @@ def test_n2_frame_tail(lib, kitti_two_frames):
     maxd = (d * np.float32(1.2) ** ka["octave"].astype(np.float32)).astype(np.float32) * np.float32(1.05)
     mind = (maxd / np.float32(1.2 ** 8)).astype(np.float32)
     lsf = float(np.log(np.float32(1.2)).astype(np.float32))
-    args = (Pw, nrm, mind, maxd, R, t, Ow, fx, fy, cx, cy, P.KITTI["bf"], (0.0, 1241.0, 0.0, 376.0), lsf, 8, 0.5)
+    args = (Pw, nrm, mind, (np.float32(1.2) * maxd).astype(np.float32), maxd, R, t, Ow, fx, fy, cx, cy, P.KITTI["bf"], (0.0, 1241.0, 0.0, 376.0), lsf, 8, 0.5)
     cnt, tr = orbfe.IsInFrustum(*args, lib=lib)
     ocnt, otr = O.is_in_frustum(*args)
     assert cnt == ocnt and cnt > 0.8 * n

@@ -186,7 +186,7 @@ def test_frustum_gemm_and_norm_golden(golden_tail):
         w = P[i, :, 0][None, :]
         nrm = np.array([[0, 0, 1]], np.float32)
         big = (-1e30, 1e30, -1e30, 1e30)
-        _, out = O.is_in_frustum(w, nrm, [0.0], [1e30], R[i], t[i, :, 0], np.zeros(3, np.float32), 1.0, 1.0, 0.0, 0.0, 0.0, big,
+        _, out = O.is_in_frustum(w, nrm, [0.0], [1e30], [1e30], R[i], t[i, :, 0], np.zeros(3, np.float32), 1.0, 1.0, 0.0, 0.0, 0.0, big,
                                  np.float32(np.log(np.float32(1.2))), 8, -2.0)
         invz = np.float32(1.0) / Pc[2]
         assert out["in_view"][0] == 1
@@ -194,9 +194,9 @@ def test_frustum_gemm_and_norm_golden(golden_tail):
         assert out["proj_y"][0] == np.float32(np.float32(np.float32(1.0) * Pc[1]) * invz) + np.float32(0.0), i
         # distance gate straddling cv2's norm: dist = (float)norm must pass [dist, dist] and fail (dist, inf)
         dist = np.float32(g["norm_out"][i])
-        c1, _ = O.is_in_frustum(w, nrm, [dist], [dist], R[i], t[i, :, 0], np.zeros(3, np.float32), 1.0, 1.0, 0.0, 0.0, 0.0, big,
+        c1, _ = O.is_in_frustum(w, nrm, [dist], [dist], [dist], R[i], t[i, :, 0], np.zeros(3, np.float32), 1.0, 1.0, 0.0, 0.0, 0.0, big,
                                 np.float32(0.18), 8, -2.0)
-        c2, _ = O.is_in_frustum(w, nrm, [np.nextafter(dist, np.float32(np.inf))], [1e30], R[i], t[i, :, 0], np.zeros(3, np.float32),
+        c2, _ = O.is_in_frustum(w, nrm, [np.nextafter(dist, np.float32(np.inf))], [1e30], [1e30], R[i], t[i, :, 0], np.zeros(3, np.float32),
                                 1.0, 1.0, 0.0, 0.0, 0.0, big, np.float32(0.18), 8, -2.0)
         assert c1 == 1 and c2 == 0, i
         ok += 1

@@ -186,3 +186,118 @@ def test_search_by_projection_lastframe():
             om, oasg = O.search_by_projection_lastframe(OC, valid, u, v, invzc, octv, ang, d, has_obs, float(bf), fwd, bwd, occupied, 7.0, ori)
             assert m == om and m > 300, (m, om, last_t, mono, ori)
             assert np.array_equal(asg, oasg)
+
+
+# ---- N1 / N2 / N3 on the reference's own KeyFrame, MapPoint and vocabulary objects ----------------------------------------------
+@pytest.fixture(scope="module")
+def bow_scene(tmp_path_factory):
+    """two stereo Frames of a shifted scene built WITH a vocabulary (so Frame::ComputeBoW / KeyFrame::ComputeBoW fill the feature
+    vectors the reference's matchers walk), and the same vocabulary on the oracle side"""
+    a, b = synth.shifted_frame(43, dx=6, dy=0)
+    rng = np.random.default_rng(12)
+    arrays = P.synth_vocabulary_uniform(rng, 6, 5, seed_desc=None)
+    path = tmp_path_factory.mktemp("voc") / "voc_6_5.txt"
+    P.write_vocabulary_text(str(path), 6, 5, 0, 0, arrays)
+    V = R.Vocabulary(path)
+    R.set_vocabulary(V)
+    try:
+        FA, FB = R.Frame(a, a), R.Frame(b, b)   # stereo constructors (right image = left: every keypoint gets a right coordinate)
+    finally:
+        R.set_vocabulary(None)
+    OV = O.Vocabulary(6, 5, 0, 0, *arrays)
+    return dict(FA=FA, FB=FB, V=V, OV=OV)
+
+
+def test_frame_compute_bow(bow_scene):
+    """Frame::ComputeBoW (frame.cpp:258-263) inside the reference Frame == oracle transform(desc, 4)"""
+    for F in (bow_scene["FA"], bow_scene["FB"]):
+        got, ref = bow_scene["OV"].transform(F.desc, 4), R.frame_bow(F)
+        assert len(ref["bow"][0]) > 100 and len(ref["fv"][0]) >= 6
+        assert np.array_equal(got["bow"][0], ref["bow"][0]) and np.array_equal(got["bow"][1], ref["bow"][1])
+        for j in range(3):
+            assert np.array_equal(got["fv"][j], ref["fv"][j])
+
+
+def _fv_dict(OV, desc):
+    from slam_framework_b200.orbfe import feature_vector_dict
+    return feature_vector_dict(OV.transform(desc, 4)["fv"])
+
+
+def test_search_by_bow_keyframe_frame_and_keyframe_keyframe(bow_scene):
+    FA, FB, OV = bow_scene["FA"], bow_scene["FB"], bow_scene["OV"]
+    rng = np.random.default_rng(3)
+    va = (rng.uniform(0, 1, FA.n) < 0.7).astype(np.uint8)
+    vb = (rng.uniform(0, 1, FB.n) < 0.7).astype(np.uint8)
+    bad_a = ((rng.uniform(0, 1, FA.n) < 0.05) & (va == 1)).astype(np.uint8)
+    bad_b = ((rng.uniform(0, 1, FB.n) < 0.05) & (vb == 1)).astype(np.uint8)
+    KA, KB = R.KeyFrame(FA, va, bad_a), R.KeyFrame(FB, vb, bad_b)
+    fva, fvb = _fv_dict(OV, FA.desc), _fv_dict(OV, FB.desc)
+    OFB = oracle_frame_of(FB)
+    ok_a, ok_b = va & (1 - bad_a), vb & (1 - bad_b)
+    for ratio, ori in ((0.7, True), (0.9, False)):
+        n, m = R.search_by_bow_kf_f(KA, FB, ratio, ori)                      # orb_matcher.cpp:133-262
+        on, om = O.search_by_bow(OFB, FA.desc, FA.kps_un["angle"], ok_a, fva, fvb, ratio, ori)
+        assert n == on and n > 100, (n, on)
+        assert np.array_equal(m, om)
+        n, m = R.search_by_bow_kf_kf(KA, KB, ratio, ori)                     # orb_matcher.cpp:499-632
+        on, om = O.search_by_bow_keyframes(OFB, FA.desc, FA.kps_un["angle"], ok_a, ok_b, fva, fvb, ratio, ori)
+        assert n == on and n > 50, (n, on)
+        assert np.array_equal(m, om)
+
+
+def test_search_for_triangulation(bow_scene):
+    """orb_matcher.cpp:634-802 with CheckDistEpipolarLine; the epipole is formed inside from the two KeyFrame poses"""
+    FA, FB, OV = bow_scene["FA"], bow_scene["FB"], bow_scene["OV"]
+    fva, fvb = _fv_dict(OV, FA.desc), _fv_dict(OV, FB.desc)
+    rng = np.random.default_rng(4)
+    has_a = (rng.uniform(0, 1, FA.n) < 0.2).astype(np.uint8)                # features that already have a map point are skipped
+    has_b = (rng.uniform(0, 1, FB.n) < 0.2).astype(np.uint8)
+    fx, cx, cy = (np.float32(CAM[k]) for k in ("fx", "cx", "cy"))
+    OFB = oracle_frame_of(FB)
+    stereo_a = (FA.u_right >= 0).astype(np.uint8)
+    for t2 in ((-0.5, 0.0, 0.05), (0.3, 0.02, 1.0)):
+        KA, KB = R.KeyFrame(FA, has_a), R.KeyFrame(FB, has_b, translation=t2)
+        # epipole (:643-649): Cw = Ow of KF1 = 0, C2 = R2w*Cw + t2w = t2w (identity rotations)
+        C2 = np.array(t2, np.float32)
+        invz = np.float32(1.0) / C2[2]
+        ex, ey = fx * C2[0] * invz + cx, fx * C2[1] * invz + cy
+        tx, ty = 6.0, 0.0
+        Fa = np.array([[0, 0, -ty], [0, 0, tx], [ty, -tx, 0]], np.float32)   # epipolar lines of a sideways image shift
+        Fb = (Fa + rng.normal(0, 2e-4, (3, 3))).astype(np.float32)
+        counts = []
+        for F12 in (Fa, Fb):
+            for only_stereo in (False, True):
+                for ori in (True, False):
+                    n, m = R.search_for_triangulation(KA, KB, F12, only_stereo, ori)
+                    on, om = O.search_for_triangulation(OFB, FA.kps_un, FA.desc, 1 - has_a, stereo_a, 1 - has_b, fva, fvb, F12, float(ex),
+                                                        float(ey), only_stereo, ori)
+                    assert n == on, (n, on, t2, only_stereo, ori)
+                    assert np.array_equal(m, om)
+                    counts.append(n)
+        assert max(counts) > 100 and sum(c > 0 for c in counts) >= 4, counts
+
+
+def test_is_in_frustum_against_frame_and_mappoint():
+    """Frame::IsInFrustum + MapPoint::PredictScale on the reference's own objects (frame.cpp:277-337, map_point.cpp:40-80,
+    382-396) vs the oracle fed the same normals / distance ranges"""
+    l, r = synth.stereo_pair(seed=35)
+    F = R.Frame(l, r)
+    rng = np.random.default_rng(6)
+    n = 6000
+    fx, cx, cy, bf = (np.float32(CAM[k]) for k in ("fx", "cx", "cy", "bf"))
+    z = rng.uniform(-3, 70, n)
+    world = np.stack([(rng.uniform(-200, 1441, n) - cx) / fx * z, (rng.uniform(-80, 456, n) - cy) / fx * z, z], 1).astype(np.float32)
+    idx = rng.integers(0, F.n, n).astype(np.int32)
+    for t in ((0.0, 0.0, 0.0), (0.4, -0.1, 2.5), (-1.0, 0.3, -6.0)):
+        cnt, got, held = R.is_in_frustum(F, world, idx, t)
+        # max_dist_ itself has no getter: it is dist * scale_factors[octave] of the creating frame at the origin
+        # (map_point.cpp:66-72), re-derived here and checked against the 1.2f * max_dist_ the point reports
+        w64 = world.astype(np.float64)
+        raw = (np.sqrt(w64[:, 0] ** 2 + w64[:, 1] ** 2 + w64[:, 2] ** 2).astype(np.float32) * F.scale[F.kps_un["octave"][idx]]).astype(np.float32)
+        assert np.array_equal((np.float32(1.2) * raw).astype(np.float32), held["max_dist"])
+        ocnt, ref = O.is_in_frustum(world, held["normal"], held["min_dist"], held["max_dist"], raw, np.eye(3, dtype=np.float32),
+                                    np.array(t, np.float32), held["Ow"], float(fx), float(fx), float(cx), float(cy), float(bf),
+                                    tuple(float(b) for b in F.bounds), float(F.misc[1]), 8, 0.5)
+        assert cnt == ocnt and cnt > 500, (cnt, ocnt, t)
+        for key in got:
+            assert np.array_equal(got[key], ref[key]), (key, t)
