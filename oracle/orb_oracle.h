@@ -13,11 +13,11 @@
  * PARITY PIN (two layers): the OpenCV primitives are pinned bit-exactly
  * against the Python cv2 4.13.0 build of the same library (tests/test_oracle_primitives.py +
  * tests/golden/ fixtures and their generator scripts).  The control logic above them (grid
- * loop, quad-tree, orientation / descriptor loops, stereo search, grid lookup, the three
- * matchers of section 8a, DBoW2 transform) is pinned against the reference's OWN sources,
- * compiled unmodified from /root/reference into oracle/_ref by oracle/Makefile.ref against the
- * OpenCV stand-in oracle/cvstub (tests/test_reference_pin.py, bit-exact).  Unpinned: the N1
- * matcher routines (same kernels, restated line by line) and cv::Mat::dot in IsInFrustum.
+ * loop, quad-tree, orientation / descriptor loops, stereo search, grid lookup, every OrbMatcher
+ * routine, IsInFrustum / PredictScale, DBoW2 transform) is pinned against the reference's OWN
+ * sources, compiled unmodified from /root/reference into oracle/_ref by oracle/Makefile.ref
+ * against the OpenCV stand-in oracle/cvstub (tests/test_reference_pin.py, bit-exact).
+ * Caveat: cv::Mat::dot (IsInFrustum, viewing-angle gates) is the stand-in's restatement.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  The product (slam_framework_b200/) never links or calls it.

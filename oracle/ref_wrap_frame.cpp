@@ -15,6 +15,7 @@
 #include <map>
 #include <memory>
 #include <new>
+#include <set>
 
 // util/converter.cpp:3-10 needs Eigen/g2o for its other members; this is the one the compiled files use
 std::vector<cv::Mat> Converter::toDescriptorVector(const cv::Mat& Descriptors) {
@@ -150,14 +151,16 @@ int ref_search_for_initialization(void* p1, void* p2, float* prev_matched_xy, in
 // builds n map points whose descriptor_ is desc[i] (through the MapPoint(pos, map, frame, idx) constructor on a scratch copy of
 // the frame whose descriptor row 0 is overwritten) at world position pos[i]; has_obs[i] adds one observation
 static void make_points(RefFrame* R, int n, const float* pos, const unsigned char* desc, const unsigned char* has_obs,
-                        std::vector<MapPoint*>& out) {
+                        std::vector<MapPoint*>& out, const int* idx = nullptr) {
   Frame scratch(*R->f());
+  scratch.SetPose(make_pose(nullptr));  // the points are created as seen from the origin (normal, scale range: map_point.cpp:61-73)
   KeyFrame* kf = observer(R);
   out.assign((size_t)n, nullptr);
   for (int i = 0; i < n; ++i) {
-    std::memcpy(scratch.GetDescriptors().data, desc + (size_t)i * 32, 32);
+    const int row = idx ? idx[i] : 0;   // the keypoint whose octave sets max_dist_; its descriptor row is overwritten first
+    std::memcpy(scratch.GetDescriptors().data + (size_t)row * (size_t)scratch.GetDescriptors().step, desc + (size_t)i * 32, 32);
     const float far[3] = {0.f, 0.f, 10.f};
-    MapPoint* mp = new MapPoint(make_vec3(pos ? pos + 3 * i : far), R->map, &scratch, 0);
+    MapPoint* mp = new MapPoint(make_vec3(pos ? pos + 3 * i : far), R->map, &scratch, row);
     if (has_obs && has_obs[i]) mp->AddObservation(kf, 0);
     R->owned.emplace_back(mp);
     out[(size_t)i] = mp;
@@ -367,6 +370,146 @@ int ref_is_in_frustum(void* pframe, int n, const float* world_pos, const int* id
     count += ok;
   }
   return count;
+}
+
+
+// ---- the projection searches of N1 on the reference's own KeyFrame / MapPoint objects ---------------------------------------------
+// free map points (not attached to the KeyFrame) at world_pos[i], created from the origin with the octave of keypoint idx[i]
+// and descriptor desc[i]; normal / distance bounds they hold are returned for the oracle's gate replication
+static void free_points(RefFrame* R, int n, const float* world_pos, const int* idx, const unsigned char* desc, std::vector<MapPoint*>& pts,
+                        float* normal_out, float* min_out, float* max_out) {
+  make_points(R, n, world_pos, desc, nullptr, pts, idx);
+  for (int i = 0; i < n; ++i) {
+    const cv::Mat nrm = pts[i]->GetNormal();
+    for (int c = 0; c < 3; ++c) normal_out[3 * i + c] = nrm.at<float>(c);
+    min_out[i] = pts[i]->GetMinDistanceInvariance();
+    max_out[i] = pts[i]->GetMaxDistanceInvariance();
+  }
+}
+static cv::Mat make_sim3(const float* t) { return make_pose(t); }  // scale 1, identity rotation
+
+// OrbMatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) (orb_matcher.cpp:384-497).  matched_in[k]
+// pre-fills vpMatched[k] with a foreign point; matched[k] (out) = index of the point this call wrote there, else -1.
+int ref_search_by_projection_sim3(void* pkf, int n, const float* world_pos, const int* idx, const unsigned char* desc,
+                                  const unsigned char* bad, const unsigned char* matched_in, const float* t, int th, float* normal_out,
+                                  float* min_out, float* max_out, int* matched) {
+  RefKeyFrame* K = static_cast<RefKeyFrame*>(pkf);
+  std::vector<MapPoint*> pts, foreign;
+  free_points(K->owner, n, world_pos, idx, desc, pts, normal_out, min_out, max_out);
+  const unsigned char zero[32] = {0};
+  make_points(K->owner, 1, nullptr, zero, nullptr, foreign);
+  std::map<MapPoint*, int> index;
+  for (int i = 0; i < n; ++i) { index[pts[i]] = i; if (bad && bad[i]) pts[i]->SetBadFlag(); }
+  const int nk = K->owner->f()->NumKeypoints();
+  std::vector<MapPoint*> vpMatched((size_t)nk, nullptr);
+  for (int k = 0; k < nk; ++k) if (matched_in[k]) vpMatched[k] = foreign[0];
+  OrbMatcher matcher(0.75f, true);
+  const int nm = matcher.SearchByProjection(K->kf.get(), make_sim3(t), pts, vpMatched, th);
+  for (int k = 0; k < nk; ++k) {
+    std::map<MapPoint*, int>::const_iterator it = index.find(vpMatched[k]);
+    matched[k] = it == index.end() ? -1 : it->second;
+  }
+  return nm;
+}
+
+// OrbMatcher::Fuse(KeyFrame*, cv::Mat Scw, vpPoints, th, vpReplacePoint) (orb_matcher.cpp:956-1079): best_idx[i] = the keypoint
+// point i was fused into (read back from vpReplacePoint / the new observation), else -1
+int ref_fuse_sim3(void* pkf, int n, const float* world_pos, const int* idx, const unsigned char* desc, const unsigned char* bad,
+                  const float* t, float th, float* normal_out, float* min_out, float* max_out, int* best_idx) {
+  RefKeyFrame* K = static_cast<RefKeyFrame*>(pkf);
+  std::vector<MapPoint*> pts;
+  free_points(K->owner, n, world_pos, idx, desc, pts, normal_out, min_out, max_out);
+  for (int i = 0; i < n; ++i) if (bad && bad[i]) pts[i]->SetBadFlag();
+  std::vector<MapPoint*> vpReplace((size_t)n, nullptr);
+  OrbMatcher matcher(0.75f, true);
+  const int nf = matcher.Fuse(K->kf.get(), make_sim3(t), pts, th, vpReplace);
+  for (int i = 0; i < n; ++i) {
+    if (vpReplace[i]) best_idx[i] = vpReplace[i]->GetIndexInKeyFrame(K->kf.get());
+    else best_idx[i] = pts[i]->GetIndexInKeyFrame(K->kf.get());
+  }
+  return nf;
+}
+
+// OrbMatcher::SearchByProjection(Frame& Cur, KeyFrame*, sAlreadyFound, th, ORBdist) (orb_matcher.cpp:1455-1582).  The KeyFrame's
+// map points (ref_keyframe_create_at) are projected with the current frame's pose (translation cur_t).
+int ref_search_by_projection_keyframe(void* pcur, void* pkf, const unsigned char* already_found, const float* cur_t,
+                                      const unsigned char* occupied, float th, int orb_dist, int check_ori, int* assigned) {
+  RefFrame* RC = static_cast<RefFrame*>(pcur);
+  RefKeyFrame* K = static_cast<RefKeyFrame*>(pkf);
+  Frame* C = RC->f();
+  C->SetPose(make_pose(cur_t));
+  set_occupied(RC, occupied);
+  std::set<MapPoint*> found;
+  std::map<MapPoint*, int> index;
+  for (size_t i = 0; i < K->pts.size(); ++i)
+    if (K->pts[i]) { index[K->pts[i]] = (int)i; if (already_found && already_found[i]) found.insert(K->pts[i]); }
+  OrbMatcher matcher(0.9f, check_ori != 0);
+  const int nm = matcher.SearchByProjection(*C, K->kf.get(), found, th, orb_dist);
+  for (int k = 0; k < C->NumKeypoints(); ++k) {
+    std::map<MapPoint*, int>::const_iterator it = index.find(C->GetMapPoint(k));
+    assigned[k] = it == index.end() ? -1 : it->second;
+  }
+  return nm;
+}
+
+// a KeyFrame whose keypoint i holds a map point at world_pos[i] (valid[i]), created from the origin with the keypoint's own
+// octave and descriptor desc[i]; returns what the points hold
+void* ref_keyframe_create_at(void* pframe, const unsigned char* valid, const float* world_pos, const unsigned char* desc,
+                             const float* translation, float* normal_out, float* min_out, float* max_out) {
+  RefFrame* R = static_cast<RefFrame*>(pframe);
+  RefKeyFrame* K = new RefKeyFrame();
+  K->owner = R;
+  K->kf.reset(new KeyFrame(*R->f(), R->map, std::shared_ptr<KeyframeDatabase>()));
+  K->kf->SetPose(make_pose(translation));
+  const int n = R->f()->NumKeypoints();
+  std::vector<int> idx((size_t)n);
+  for (int i = 0; i < n; ++i) idx[i] = i;
+  std::vector<MapPoint*> pts;
+  free_points(R, n, world_pos, idx.data(), desc, pts, normal_out, min_out, max_out);
+  K->pts.assign((size_t)n, nullptr);
+  for (int i = 0; i < n; ++i)
+    if (valid[i]) { K->pts[i] = pts[i]; K->kf->AddMapPoint(pts[i], i); pts[i]->AddObservation(K->kf.get(), i); }
+  return K;
+}
+
+// OrbMatcher::SearchBySim3 (orb_matcher.cpp:1081-1310) between two KeyFrames built by ref_keyframe_create_at; s12 = 1, R12 = I,
+// translation t12; pre_matched1[i] pre-fills vpMatches12[i] (vbAlreadyMatched, :1116-1126) with KF2's point pre_idx2[i]
+int ref_search_by_sim3(void* pkf1, void* pkf2, const float* t12, float th, const int* pre_idx2, int* match12) {
+  RefKeyFrame *K1 = static_cast<RefKeyFrame*>(pkf1), *K2 = static_cast<RefKeyFrame*>(pkf2);
+  const int n1 = K1->owner->f()->NumKeypoints();
+  std::map<MapPoint*, int> index2;
+  for (size_t i = 0; i < K2->pts.size(); ++i) if (K2->pts[i]) index2[K2->pts[i]] = (int)i;
+  std::vector<MapPoint*> m12((size_t)n1, nullptr);
+  for (int i = 0; i < n1; ++i) if (pre_idx2 && pre_idx2[i] >= 0 && K2->pts[pre_idx2[i]]) m12[i] = K2->pts[pre_idx2[i]];
+  cv::Mat R12 = cv::Mat::eye(3, 3, CV_32F);
+  OrbMatcher matcher(0.75f, true);
+  const int nf = matcher.SearchBySim3(K1->kf.get(), K2->kf.get(), m12, 1.0f, R12, make_vec3(t12), th);
+  for (int i = 0; i < n1; ++i) {
+    std::map<MapPoint*, int>::const_iterator it = index2.find(m12[i]);
+    match12[i] = it == index2.end() ? -1 : it->second;
+  }
+  return nf;
+}
+
+
+// OrbMatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (orb_matcher.cpp:804-954) on a KeyFrame placed at translation t.
+// best_idx[i] = the keypoint point i was fused into: read back from its new observation, or -- when an earlier point had
+// taken that keypoint and the two were merged (:933-943) -- from the point that replaced it.
+int ref_fuse(void* pkf, int n, const float* world_pos, const int* idx, const unsigned char* desc, const unsigned char* bad,
+             const float* t, float th, float* normal_out, float* min_out, float* max_out, int* best_idx) {
+  RefKeyFrame* K = static_cast<RefKeyFrame*>(pkf);
+  std::vector<MapPoint*> pts;
+  free_points(K->owner, n, world_pos, idx, desc, pts, normal_out, min_out, max_out);
+  for (int i = 0; i < n; ++i) if (bad && bad[i]) pts[i]->SetBadFlag();
+  K->kf->SetPose(make_pose(t));
+  OrbMatcher matcher(0.75f, true);
+  const int nf = matcher.Fuse(K->kf.get(), pts, th);
+  for (int i = 0; i < n; ++i) {
+    MapPoint* p = pts[i];
+    if (p->isBad() && p->GetReplaced()) p = p->GetReplaced();
+    best_idx[i] = (bad && bad[i]) ? -1 : p->GetIndexInKeyFrame(K->kf.get());
+  }
+  return nf;
 }
 
 }  // extern "C"

@@ -57,6 +57,13 @@ def lib():
         L.ref_search_by_bow_kf_kf.argtypes = [vp, vp, C.c_float, C.c_int, vp]
         L.ref_search_for_triangulation.argtypes = [vp, vp, vp, C.c_int, C.c_float, C.c_int, vp]
         L.ref_is_in_frustum.argtypes = [vp, C.c_int, vp, vp, vp, C.c_float] + [vp] * 10
+        L.ref_search_by_projection_sim3.argtypes = [vp, C.c_int] + [vp] * 6 + [C.c_int] + [vp] * 4
+        L.ref_fuse_sim3.argtypes = [vp, C.c_int] + [vp] * 5 + [C.c_float] + [vp] * 4
+        L.ref_fuse.argtypes = [vp, C.c_int] + [vp] * 5 + [C.c_float] + [vp] * 4
+        L.ref_search_by_projection_keyframe.argtypes = [vp, vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, vp]
+        L.ref_keyframe_create_at.argtypes = [vp] * 8
+        L.ref_keyframe_create_at.restype = vp
+        L.ref_search_by_sim3.argtypes = [vp, vp, vp, C.c_float, vp, vp]
         _lib = L
     return _lib
 
@@ -229,3 +236,58 @@ def is_in_frustum(F, world, idx, translation, viewing_cos_limit=0.5):
                                   _p(mx), _p(ow), _p(out["in_view"]), _p(out["proj_x"]), _p(out["proj_y"]), _p(out["proj_xr"]),
                                   _p(out["level"]), _p(out["view_cos"]))
     return cnt, out, dict(normal=nrm, min_dist=mn, max_dist=mx, Ow=ow)
+
+
+def _held(n):
+    return np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+
+
+def search_by_projection_sim3(KF, world, idx, desc, bad, matched_in, t, th):
+    w = _a(world, np.float32).reshape(-1, 3)
+    nrm, mn, mx = _held(len(w))
+    out = np.zeros(KF.F.n, np.int32)
+    n = lib().ref_search_by_projection_sim3(KF.h, len(w), _p(w), _p(_a(idx, np.int32)), _p(_a(desc, np.uint8)), _p(_a(bad, np.uint8)),
+                                            _p(_a(matched_in, np.uint8)), _p(_a(t, np.float32)), int(th), _p(nrm), _p(mn), _p(mx), _p(out))
+    return n, out, dict(normal=nrm, min_dist=mn, max_dist=mx)
+
+
+def fuse_sim3(KF, world, idx, desc, bad, t, th):
+    w = _a(world, np.float32).reshape(-1, 3)
+    nrm, mn, mx = _held(len(w))
+    out = np.zeros(len(w), np.int32)
+    n = lib().ref_fuse_sim3(KF.h, len(w), _p(w), _p(_a(idx, np.int32)), _p(_a(desc, np.uint8)), _p(_a(bad, np.uint8)),
+                            _p(_a(t, np.float32)), float(th), _p(nrm), _p(mn), _p(mx), _p(out))
+    return n, out, dict(normal=nrm, min_dist=mn, max_dist=mx)
+
+
+class KeyFrameAt(KeyFrame):
+    """KeyFrame whose keypoint i holds a map point at world[i] (where valid[i]) with descriptor desc[i]"""
+
+    def __init__(self, F, valid, world, desc, translation=(0.0, 0.0, 0.0)):
+        self.F = F
+        nrm, mn, mx = _held(F.n)
+        self.h = lib().ref_keyframe_create_at(F.h, _p(_a(valid, np.uint8)), _p(_a(world, np.float32)), _p(_a(desc, np.uint8)),
+                                              _p(_a(translation, np.float32)), _p(nrm), _p(mn), _p(mx))
+        self.held = dict(normal=nrm, min_dist=mn, max_dist=mx)
+
+
+def search_by_projection_keyframe(Cur, KF, already_found, cur_t, occupied, th, orb_dist, check_ori):
+    out = np.zeros(Cur.n, np.int32)
+    n = lib().ref_search_by_projection_keyframe(Cur.h, KF.h, _p(_a(already_found, np.uint8)), _p(_a(cur_t, np.float32)),
+                                                _p(_a(occupied, np.uint8)), float(th), int(orb_dist), int(check_ori), _p(out))
+    return n, out
+
+
+def search_by_sim3(KF1, KF2, t12, th, pre_idx2):
+    out = np.zeros(KF1.F.n, np.int32)
+    n = lib().ref_search_by_sim3(KF1.h, KF2.h, _p(_a(t12, np.float32)), float(th), _p(_a(pre_idx2, np.int32)), _p(out))
+    return n, out
+
+
+def fuse(KF, world, idx, desc, bad, t, th):
+    w = _a(world, np.float32).reshape(-1, 3)
+    nrm, mn, mx = _held(len(w))
+    out = np.zeros(len(w), np.int32)
+    n = lib().ref_fuse(KF.h, len(w), _p(w), _p(_a(idx, np.int32)), _p(_a(desc, np.uint8)), _p(_a(bad, np.uint8)), _p(_a(t, np.float32)),
+                       float(th), _p(nrm), _p(mn), _p(mx), _p(out))
+    return n, out, dict(normal=nrm, min_dist=mn, max_dist=mx)

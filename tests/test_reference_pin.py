@@ -301,3 +301,213 @@ def test_is_in_frustum_against_frame_and_mappoint():
         assert cnt == ocnt and cnt > 500, (cnt, ocnt, t)
         for key in got:
             assert np.array_equal(got[key], ref[key]), (key, t)
+
+
+# ---- the projection searches of N1: the reference's own cv::Mat geometry (identity rotations, so every step is one IEEE float
+# operation reproduced below with numpy float32 / float64), then the search, against the oracle fed the same gate results ----------
+f32, f64 = np.float32, np.float64
+
+
+def _libm_logf(x):
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.logf.restype = ctypes.c_float
+    libm.logf.argtypes = [ctypes.c_float]
+    return np.array([libm.logf(float(v)) for v in x], f32)
+
+
+def _norm3(p):            # cv::norm: double accumulator in x, y, z order, sqrt, then the float the caller stores it in
+    p = p.astype(f64)
+    s = p[:, 0] * p[:, 0]
+    s = s + p[:, 1] * p[:, 1]
+    s = s + p[:, 2] * p[:, 2]
+    return np.sqrt(s).astype(f32)
+
+
+def _predict_scale(max_raw, dist, lsf, nlevels=8):   # MapPoint::PredictScale (map_point.cpp:366-396)
+    with np.errstate(all="ignore"):
+        ratio = (max_raw / dist).astype(f32)
+        lvl = np.ceil((_libm_logf(ratio) / f32(lsf)).astype(f32))
+    lvl = np.where(np.isfinite(lvl), lvl, 0).astype(np.int64)
+    return np.clip(lvl, 0, nlevels - 1).astype(np.int32)
+
+
+def _raw_max_dist(F, world, idx):                    # max_dist_ = dist * scale_factors[octave], created from the origin
+    return (_norm3(world) * F.scale[F.kps_un["octave"][idx]]).astype(f32)
+
+
+def _scene_points(F, rng, n, jitter=3.0):
+    """map points seen near random keypoints of F from the origin, descriptors = the keypoint's with a few bits flipped"""
+    fx, cx, cy = (f32(CAM[k]) for k in ("fx", "cx", "cy"))
+    idx = rng.integers(0, F.n, n).astype(np.int32)
+    z = rng.uniform(4, 50, n).astype(f32)
+    z[: n // 40] = rng.uniform(-8, -1, n // 40).astype(f32)          # behind the camera
+    x = ((F.kps_un["x"][idx] + rng.uniform(-jitter, jitter, n).astype(f32) - cx) / fx * z).astype(f32)
+    y = ((F.kps_un["y"][idx] + rng.uniform(-jitter, jitter, n).astype(f32) - cy) / fx * z).astype(f32)
+    x[n // 40: n // 20] *= f32(30)                                    # far outside the image
+    world = np.stack([x, y, z], 1).astype(f32)
+    d = F.desc[idx].copy()
+    for i in range(n):
+        for b in rng.choice(256, rng.integers(0, 50), replace=False):
+            d[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    return idx, world, d
+
+
+def _kf_gates(world, held, raw, t, lsf, w, h, invz_double, check_view=True):
+    """:414-451 / :987-1025: p3Dc = Rcw*p3Dw + tcw, depth sign, projection, IsInImage (int bounds), distance range, viewing
+    angle, PredictScale -- for Scw / pose = identity rotation, translation t"""
+    fx, cx, cy = (f32(CAM[k]) for k in ("fx", "cx", "cy"))
+    t = np.asarray(t, f32)
+    pc = (world + t).astype(f32)
+    with np.errstate(all="ignore"):
+        z = pc[:, 2]
+        invz = (1.0 / z.astype(f64)).astype(f32) if invz_double else (f32(1) / z).astype(f32)
+        u = (fx * (pc[:, 0] * invz).astype(f32)).astype(f32) + cx
+        v = (fx * (pc[:, 1] * invz).astype(f32)).astype(f32) + cy
+        ok = ~(z < 0)
+        ok &= (u >= 0) & (u < w) & (v >= 0) & (v < h)                 # KeyFrame::IsInImage (keyframe.cpp:494-496)
+        Ow = (-t).astype(f32)
+        PO = (world - Ow).astype(f32)
+        dist = _norm3(PO)
+        ok &= ~((dist < held["min_dist"]) | (dist > held["max_dist"]))
+        if check_view:
+            P64, N64 = PO.astype(f64), held["normal"].astype(f64)
+            dot = P64[:, 0] * N64[:, 0]
+            dot = dot + P64[:, 1] * N64[:, 1]
+            dot = dot + P64[:, 2] * N64[:, 2]
+            ok &= ~(dot < 0.5 * dist.astype(f64))
+        lvl = _predict_scale(raw, dist, lsf)
+    u, v = np.where(ok, u, 0).astype(f32), np.where(ok, v, 0).astype(f32)
+    return ok.astype(np.uint8), u, v, np.where(ok, lvl, 0).astype(np.int32), invz
+
+
+def test_search_by_projection_sim3_and_fuse_sim3():
+    """SearchByProjection(KeyFrame*, Scw, ...) (orb_matcher.cpp:384-497) and Fuse(KeyFrame*, Scw, ...) (:956-1079)"""
+    l, r = synth.stereo_pair(seed=37)
+    F = R.Frame(l, r)
+    OF = oracle_frame_of(F)
+    rng = np.random.default_rng(14)
+    lsf = float(F.misc[1])
+    for t, th in (((0.0, 0.0, 0.0), 10), ((0.3, -0.1, 1.5), 10), ((-0.2, 0.05, -2.0), 4)):
+        KF = R.KeyFrame(F)
+        idx, world, d = _scene_points(F, rng, 3000)
+        bad = (rng.uniform(0, 1, len(idx)) < 0.05).astype(np.uint8)
+        matched_in = (rng.uniform(0, 1, F.n) < 0.2).astype(np.uint8)
+        n, m, held = R.search_by_projection_sim3(KF, world, idx, d, bad, matched_in, t, th)
+        raw = _raw_max_dist(F, world, idx)
+        assert np.array_equal((f32(1.2) * raw).astype(f32), held["max_dist"])
+        ok, u, v, lvl, _ = _kf_gates(world, held, raw, t, lsf, 1241, 376, invz_double=False)
+        on, om = O.search_by_projection_sim3(OF, ok & (1 - bad), u, v, lvl, d, matched_in, th)
+        assert n == on and n > 200, (n, on, t)
+        assert np.array_equal(m, om)
+        # Fuse with a Sim3: no occupancy in the scan; every keypoint is free here, so each fused point is added as an observation
+        # unless an earlier point took the keypoint (then it is reported through vpReplacePoint)
+        KF2 = R.KeyFrame(F)
+        n, best, held = R.fuse_sim3(KF2, world, idx, d, bad, t, float(th))
+        ok, u, v, lvl, _ = _kf_gates(world, held, raw, t, lsf, 1241, 376, invz_double=True)
+        on, obest = O.fuse(OF, ok & (1 - bad), u, v, None, lvl, d, float(th))
+        assert n == on and n > 200, (n, on, t)
+        assert np.array_equal(best, obest), f"{(best != obest).sum()} fused keypoints differ"
+
+
+def test_search_by_projection_frame_keyframe_and_sim3():
+    """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (:1455-1582) and SearchBySim3 (:1081-1310)"""
+    a, b = synth.shifted_frame(45, dx=5, dy=2)
+    FA, FB = R.Frame(a, a), R.Frame(b, b)
+    OA, OB = oracle_frame_of(FA), oracle_frame_of(FB)
+    rng = np.random.default_rng(15)
+    fx, cx, cy = (f32(CAM[k]) for k in ("fx", "cx", "cy"))
+    lsf = float(FA.misc[1])
+
+    def own_points(F):   # one map point per keypoint, back-projected from the origin at a random depth
+        n = F.n
+        z = rng.uniform(4, 50, n).astype(f32)
+        world = np.stack([((F.kps_un["x"] - cx) / fx * z).astype(f32), ((F.kps_un["y"] - cy) / fx * z).astype(f32), z], 1).astype(f32)
+        d = F.desc.copy()
+        d[:, 5] ^= rng.integers(0, 8, n).astype(np.uint8)
+        valid = (rng.uniform(0, 1, n) < 0.8).astype(np.uint8)
+        return valid, world, d
+
+    va, wa, da = own_points(FA)
+    KA = R.KeyFrameAt(FA, va, wa, da)
+    raw_a = _raw_max_dist(FA, wa, np.arange(FA.n))
+    assert np.array_equal((f32(1.2) * raw_a).astype(f32), KA.held["max_dist"])
+    # ---- relocalisation search: KA's points projected into frame B standing at cur_t
+    for cur_t, th, orb_dist in (((0.0, 0.0, 0.0), 10.0, 100), ((0.05, 0.02, 0.8), 15.0, 64), ((0.0, 0.0, -30.0), 10.0, 100)):
+        t = np.asarray(cur_t, f32)
+        pc = (wa + t).astype(f32)
+        with np.errstate(all="ignore"):
+            invzc = (1.0 / pc[:, 2].astype(f64)).astype(f32)
+            u = ((fx * pc[:, 0]).astype(f32) * invzc).astype(f32) + cx      # :1487
+            v = ((fx * pc[:, 1]).astype(f32) * invzc).astype(f32) + cy
+        dist = _norm3((wa - (-t).astype(f32)).astype(f32))
+        ok = va.astype(bool) & ~((dist < KA.held["min_dist"]) | (dist > KA.held["max_dist"]))
+        found = ((rng.uniform(0, 1, FA.n) < 0.1) & (va == 1)).astype(np.uint8)
+        occupied = (rng.uniform(0, 1, FB.n) < 0.1).astype(np.uint8)
+        lvl = _predict_scale(raw_a, dist, lsf)
+        u = np.where(np.isfinite(u), u, -1e9).astype(f32)
+        v = np.where(np.isfinite(v), v, -1e9).astype(f32)
+        for ori in (True, False):
+            n, asg = R.search_by_projection_keyframe(FB, KA, found, cur_t, occupied, th, orb_dist, ori)
+            on, oasg = O.search_by_projection_keyframe(OB, (ok & (found == 0)).astype(np.uint8), u, v, lvl, FA.kps_un["angle"], da, occupied,
+                                                       th, orb_dist, ori)
+            assert n == on, (n, on, cur_t, ori)
+            assert np.array_equal(asg, oasg)
+        assert n > 200 or cur_t[2] < -10
+    # ---- SearchBySim3: both KeyFrames at the origin, Sim3 = translation t12 (scale 1, identity rotation)
+    vb, wb, db = own_points(FB)
+    KB = R.KeyFrameAt(FB, vb, wb, db)
+    raw_b = _raw_max_dist(FB, wb, np.arange(FB.n))
+    for t12, th in (((0.0, 0.0, 0.0), 7.5), ((0.02, -0.01, 0.3), 7.5)):
+        t12 = np.asarray(t12, f32)
+        pre = np.full(FA.n, -1, np.int32)
+        cand = np.where((va == 1) & (rng.uniform(0, 1, FA.n) < 0.05))[0]
+        pre[cand] = rng.choice(np.where(vb == 1)[0], len(cand), replace=False)
+        already1 = pre >= 0
+        already2 = np.zeros(FB.n, bool)
+        already2[pre[pre >= 0]] = True
+
+        def side(world, held, raw, tt, valid, already):   # :1134-1170 / :1214-1250
+            pc = (world + tt).astype(f32)                  # p3Dc1 = world (R1w = I, t1w = 0); p3Dc2 = sR21*p3Dc1 + t21
+            with np.errstate(all="ignore"):
+                z = pc[:, 2]
+                invz = (1.0 / z.astype(f64)).astype(f32)
+                u = (fx * (pc[:, 0] * invz).astype(f32)).astype(f32) + cx
+                v = (fx * (pc[:, 1] * invz).astype(f32)).astype(f32) + cy
+                ok = valid.astype(bool) & ~already & ~(z < 0) & (u >= 0) & (u < 1241) & (v >= 0) & (v < 376)
+                dist = _norm3(pc)
+                ok &= ~((dist < held["min_dist"]) | (dist > held["max_dist"]))
+                lvl = _predict_scale(raw, dist, lsf)
+            return (ok.astype(np.uint8), np.where(ok, u, 0).astype(f32), np.where(ok, v, 0).astype(f32), np.where(ok, lvl, 0).astype(np.int32))
+        s1 = side(wa, KA.held, raw_a, (-t12).astype(f32), va, already1) + (da,)      # t21 = -sR21*t12 = -t12
+        s2 = side(wb, KB.held, raw_b, t12, vb, already2) + (db,)
+        n, m = R.search_by_sim3(KA, KB, t12, th, pre)
+        on, om = O.search_by_sim3(OA, OB, s1, s2, th)
+        assert n == on and n > 100, (n, on, t12)
+        new = ~already1
+        assert np.array_equal(m[new], om[new]) and np.array_equal(m[already1], pre[already1])
+
+
+def test_fuse_keyframe_mappoints():
+    """Fuse(KeyFrame*, vpMapPoints, th) (orb_matcher.cpp:804-954) incl. the stereo / monocular chi2 gates (:893-917) and the
+    graph edits: a point that lands on a keypoint an earlier point took is merged with it (:933-943)"""
+    l, r = synth.stereo_pair(seed=39)
+    F = R.Frame(l, r)                                     # real stereo coordinates: both chi2 branches are exercised
+    OF = oracle_frame_of(F)
+    rng = np.random.default_rng(16)
+    lsf, bf = float(F.misc[1]), f32(CAM["bf"])
+    assert 0.2 < (F.u_right >= 0).mean() < 0.8
+    for t, th in (((0.0, 0.0, 0.0), 3.0), ((0.1, -0.05, 0.6), 3.0)):
+        KF = R.KeyFrame(F)
+        idx, world, d = _scene_points(F, rng, 4000, jitter=2.0)
+        bad = (rng.uniform(0, 1, len(idx)) < 0.05).astype(np.uint8)
+        n, best, held = R.fuse(KF, world, idx, d, bad, t, th)
+        raw = _raw_max_dist(F, world, idx)
+        ok, u, v, lvl, invz = _kf_gates(world, held, raw, t, lsf, 1241, 376, invz_double=False)
+        with np.errstate(all="ignore"):
+            ur = np.where(ok == 1, u - (bf * invz).astype(f32), 0).astype(f32)       # :849
+        on, obest = O.fuse(OF, ok & (1 - bad), u, v, ur, lvl, d, th)
+        # the reference skips a point that an earlier merge made bad / put into the KeyFrame (:828); with distinct, unattached
+        # points that never happens before the point's own turn, so the per-point searches are comparable one to one
+        assert n == on and n > 300, (n, on, t)
+        assert np.array_equal(best, obest), f"{(best != obest).sum()} fused keypoints differ"
