@@ -15,8 +15,9 @@ so ranks share nothing (no collective on the data path): weak scaling.
           memory -> orbfe_run -> orbfe_run_stereo -> orbfe_download to host arrays), host<->device
           copies inside the timed region, wall clock, max over ranks.
   roofline      : per-stage CUDA-event times of the timed region against the measured HBM peak.
-  cpu_baseline  : the oracle (CPU restatement of the reference path; the reference itself cannot be
-                  built here) on the box's host cores, bounded sample; rank 0 at N=1 only.
+  cpu_baseline  : the oracle port (CPU restatement of the reference path) on the box's host cores, bounded sample; rank 0 at
+                  N=1 only.  The reference's own sources built against the OpenCV stand-in (oracle/_ref) are timed beside it
+                  (`reference_build_value`); the faster of the two is the baseline.
 """
 import argparse
 import ctypes
@@ -142,6 +143,30 @@ def cpu_reference_throughput(pairs, n_pairs, threads, pair_threads=1):
     return n_pairs / sec, sec, kps.value, mt.value
 
 
+def ref_build_throughput(pairs, n_pairs, workers):
+    """the reference's OWN sources (oracle/_ref/libslam_ref.so: Frame's stereo constructor = 2 extraction threads +
+    ComputeStereoMatches per pair) over n_pairs pairs; None when that library is not present"""
+    try:
+        import reference_lib as R
+        if not R.available():
+            return None
+        L = R.lib()
+    except Exception:
+        return None
+    L.ref_bench_stereo_batch.restype = ctypes.c_double
+    L.ref_bench_stereo_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_float] + [ctypes.c_int] * 3 + \
+        [ctypes.c_float] * 5 + [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lp = (ctypes.c_void_p * n_pairs)()
+    rp = (ctypes.c_void_p * n_pairs)()
+    for i in range(n_pairs):
+        l, r = pairs[i % len(pairs)]
+        lp[i], rp[i] = l.ctypes.data, r.ctypes.data
+    kps, mt = ctypes.c_long(), ctypes.c_long()
+    sec = L.ref_bench_stereo_batch(lp, rp, n_pairs, W, H, NFEATURES, SCALE, NLEVELS, INI_TH, MIN_TH, FX, FX, 607.1928, 185.2157, BF,
+                                   workers, ctypes.byref(kps), ctypes.byref(mt))
+    return n_pairs / sec
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores.  The reference's own
     sources do compile here against a stand-in OpenCV layer (oracle/_ref), but that build runs our
@@ -163,12 +188,21 @@ def run_reference(args):
     sec = time.perf_counter() - t0
     val = done / sec
     sample = f"{per_step} stereo pairs per step x {args.steps} steps, one oracle worker per host core"
+    # the reference's own sources (oracle/_ref), timed beside the port on a smaller sample: workers x 2 extraction threads
+    ref_build = ref_build_throughput(pairs, 2 * max(cores, 4), max(cores // 2, 1))
+    kind = "port"
+    if ref_build is not None and ref_build > val:  # report the faster of the two CPU implementations
+        val, kind = ref_build, "reference"
+        sample = f"{2 * max(cores, 4)} stereo pairs through oracle/_ref (the reference's own sources), {max(cores // 2, 1)} workers x 2 threads"
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
            "config": {"workload": "configs[1]: synthetic KITTI-size stereo pair, L+R ORB extraction + ComputeStereoMatches",
                       "pairs_per_step": per_step, "nfeatures": NFEATURES, "levels": NLEVELS},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                            "port_value": done / sec, "reference_build_value": ref_build,
+                            "note": "port = oracle restatement; reference_build = the reference's own sources compiled against the "
+                                    "OpenCV stand-in (oracle/_ref); the two are bit-identical, the faster one is the baseline"},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -401,8 +435,14 @@ def run_ours(args):
         reps = int(min(max(12.0 / max(s1, 1e-3), 1), 400))  # ~12 s of host work
         n = cores * reps
         v, sec, ckps, cmt = cpu_reference_throughput(pairs, n, cores)
+        rb = ref_build_throughput(pairs, 2 * max(cores, 4), max(cores // 2, 1))
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} stereo pairs ({sec:.1f} s), one oracle worker per host core; the port is faster than the reference's own sources built in oracle/_ref, so it is the conservative baseline"}
+               "sample": f"{n} stereo pairs ({sec:.1f} s), one oracle worker per host core", "port_value": v,
+               "reference_build_value": rb,
+               "note": "reference_build = the reference's own sources compiled against the OpenCV stand-in (oracle/_ref), "
+                       "bit-identical to the port; the faster of the two is the baseline"}
+        if rb is not None and rb > v:
+            cpu["value"], cpu["kind"] = rb, "reference"
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -24,6 +24,7 @@ char* g_base = nullptr;
 std::atomic<size_t> g_off(0);
 const size_t kArena = (size_t)1 << 36;  // virtual reservation, committed lazily
 std::once_flag g_once;
+std::atomic<int> g_malloc_mode(0);  // > 0: plain malloc/free (throughput runs: the arena never reclaims memory)
 inline void* arena_alloc(size_t n) {  // thread-safe: Frame's stereo constructor extracts on two std::threads (frame.cpp:86-89)
   std::call_once(g_once, []() {
     void* p = mmap(nullptr, kArena, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
@@ -43,8 +44,14 @@ struct ArenaScope {
   ArenaScope() : mark(g_off.load()) {}
   ~ArenaScope() { g_off.store(mark); }
 };
-void* operator new(size_t n) { void* p = arena_alloc(n ? n : 1); if (!p) throw std::bad_alloc(); return p; }
-void* operator new[](size_t n) { void* p = arena_alloc(n ? n : 1); if (!p) throw std::bad_alloc(); return p; }
+static inline void* any_alloc(size_t n) {
+  void* p = g_malloc_mode.load(std::memory_order_relaxed) > 0 ? malloc(n ? n : 1) : arena_alloc(n ? n : 1);
+  if (!p) throw std::bad_alloc();
+  return p;
+}
+void* operator new(size_t n) { return any_alloc(n); }
+void* operator new[](size_t n) { return any_alloc(n); }
+extern "C" void ref_set_malloc_mode(int on) { g_malloc_mode.store(on); }
 void operator delete(void* p) noexcept { if (p && !in_arena(p)) free(p); }
 void operator delete[](void* p) noexcept { if (p && !in_arena(p)) free(p); }
 void operator delete(void* p, size_t) noexcept { if (p && !in_arena(p)) free(p); }

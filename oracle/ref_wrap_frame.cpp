@@ -11,8 +11,11 @@
 #include "DBoW2/FORB.h"
 #include "DBoW2/TemplatedVocabulary.h"
 
+#include <atomic>
+#include <chrono>
 #include <cstring>
 #include <map>
+#include <thread>
 #include <memory>
 #include <new>
 #include <set>
@@ -510,6 +513,44 @@ int ref_fuse(void* pkf, int n, const float* world_pos, const int* idx, const uns
     best_idx[i] = (bad && bad[i]) ? -1 : p->GetIndexInKeyFrame(K->kf.get());
   }
   return nf;
+}
+
+
+// Throughput of the reference's own stereo front-end (Frame's stereo constructor: 2 extraction threads + ComputeStereoMatches) over
+// n_pairs pairs with n_workers concurrent constructions; wall seconds.  bench.py --impl reference only.  Runs on malloc/free
+// (ref_set_malloc_mode): timing does not depend on the quad-tree tie-break, and the bump arena never reclaims memory.
+extern "C" void ref_set_malloc_mode(int on);
+double ref_bench_stereo_batch(const unsigned char* const* left, const unsigned char* const* right, int n_pairs, int w, int h,
+                              int nfeatures, float sf, int nl, int ini, int mn, float fx, float fy, float cx, float cy, float bf,
+                              int n_workers, long* total_kps, long* total_matches) {
+  ref_set_malloc_mode(1);
+  std::atomic<int> next(0);
+  std::atomic<long> kps(0), matches(0);
+  const auto t0 = std::chrono::steady_clock::now();
+  auto worker = [&]() {
+    std::shared_ptr<ORBextractor> exL(new ORBextractor(nfeatures, sf, nl, ini, mn)), exR(new ORBextractor(nfeatures, sf, nl, ini, mn));
+    cv::Mat K = make_K(fx, fy, cx, cy), D = cv::Mat::zeros(4, 1, CV_32F);
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n_pairs) break;
+      cv::Mat imL(h, w, CV_8UC1, const_cast<unsigned char*>(left[i])), imR(h, w, CV_8UC1, const_cast<unsigned char*>(right[i]));
+      Frame F(imL, imR, 0.0, exL, exR, std::shared_ptr<OrbVocabulary>(), K, D, bf, 35.0f);
+      kps += F.NumKeypoints() + (long)F.GetRightKeys().size();
+      long m = 0;
+      for (size_t k = 0; k < F.StereoCoordRight().size(); ++k) m += F.StereoCoordRight()[k] >= 0;
+      matches += m;
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_workers; ++t) pool.emplace_back(worker);
+    for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  ref_set_malloc_mode(0);
+  if (total_kps) *total_kps = kps.load();
+  if (total_matches) *total_matches = matches.load();
+  return std::chrono::duration<double>(t1 - t0).count();
 }
 
 }  // extern "C"
