@@ -569,6 +569,139 @@ k_match_finalize(const ResolveArgs A, const MatchScratch S, const JacobiState J)
   if (tid == 0) A.result[0] = s_n;
 }
 
+// ---- SearchForInitialization, parallel form (orb_matcher.cpp:264-382) ----------------------------------------------------
+// The coupling between queries is vMatchedDistance: query q skips a candidate c when an EARLIER accepted query q' < q took c
+// at a distance <= dist(q, c) (:306-307; every accept on c lowers vMatchedDistance[c], so the value q sees is the minimum over
+// the earlier acceptors).  As for the projection searches, the serial result is the unique fixed point of
+//     acc = F(acceptors(acc) restricted to q' < q)
+// and Jacobi iteration from "no acceptors" reaches it (query q is final after q+1 iterations; chains are a few links long in
+// practice).  Each keypoint keeps the (query, distance) pairs of its acceptors of the previous iteration in ORBFE_INIT_SLOTS
+// slots; a keypoint with more acceptors than that raises `overflow` and the host falls back to the one-warp serial kernel.
+#define ORBFE_INIT_SLOTS 8
+struct InitJacobi {
+  int* acc;        // nQ: accepted target | distance << 22 of the previous iteration (-1 none, -2 not evaluated yet)
+  int* cnt;        // 3 x nKp rotating acceptor counts
+  uint2* slots;    // 3 x nKp x ORBFE_INIT_SLOTS rotating (query, distance)
+  int* changed;    // per-iteration "some query changed its answer" flags
+  int* overflow;
+};
+
+__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
+k_init_iterate(const ResolveArgs A, const MatchScratch S, const InitJacobi J, const int t) {
+  if (S.cursor[1]) return;
+  if (t > 0 && J.changed[t - 1] == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int gtid = blockIdx.x * ORBFE_MATCH_THREADS + threadIdx.x, gsz = gridDim.x * ORBFE_MATCH_THREADS;
+  int* cntClear = J.cnt + (size_t)((t + 2) % 3) * A.nKp;
+  for (int i = gtid; i < A.nKp; i += gsz) cntClear[i] = 0;
+  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
+  if (q >= A.nQ) return;
+  const int* cntPrev = J.cnt + (size_t)(t % 3) * A.nKp;
+  const uint2* slotPrev = J.slots + (size_t)(t % 3) * A.nKp * ORBFE_INIT_SLOTS;
+  int* cntNext = J.cnt + (size_t)((t + 1) % 3) * A.nKp;
+  uint2* slotNext = J.slots + (size_t)((t + 1) % 3) * A.nKp * ORBFE_INIT_SLOTS;
+  const int cnt = S.qCnt[q], off = S.qOff[q];
+  unsigned best = 0xffffffffu, second = 0xffffffffu;
+  for (int c = lane; c < cnt; c += 32) {
+    const uint2 cd = S.cand[off + c];
+    const int dist = (int)(cd.y & 0xffffu);
+    int matched = 0x7fffffff;  // vMatchedDistance[i2] as query q sees it
+    const int na = min(cntPrev[cd.x], ORBFE_INIT_SLOTS);
+    for (int k = 0; k < na; ++k) {
+      const uint2 a = slotPrev[(size_t)cd.x * ORBFE_INIT_SLOTS + k];
+      if ((int)a.x < q) matched = min(matched, (int)a.y);
+    }
+    if (!(matched <= dist)) {
+      const unsigned key = ((unsigned)dist << 20) | (unsigned)c;
+      if (key < best) { second = best; best = key; } else if (key < second) second = key;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const unsigned os = __shfl_xor_sync(0xffffffffu, second, o);
+    orbfe_merge2(best, second, ob, os);
+  }
+  if (lane != 0) return;
+  int acc = -1;
+  if (best != 0xffffffffu) {
+    const int bestDist = (int)(best >> 20);
+    const float d2 = second == 0xffffffffu ? (float)0x7fffffff : (float)(int)(second >> 20);
+    if (bestDist <= 50 && (float)bestDist < __fmul_rn(d2, A.nnratio)) {  // :320-322
+      const int idx = (int)S.cand[off + (int)(best & 0xfffffu)].x;
+      acc = idx | (bestDist << 22);
+      const int slot = atomicAdd(&cntNext[idx], 1);
+      if (slot < ORBFE_INIT_SLOTS) slotNext[(size_t)idx * ORBFE_INIT_SLOTS + slot] = make_uint2((unsigned)q, (unsigned)bestDist);
+      else *J.overflow = 1;
+    }
+  }
+  if (t == 0 || acc != J.acc[q]) { J.acc[q] = acc; J.changed[t] = 1; }
+}
+
+// after convergence: vnMatches12 (the LAST accepted query on a keypoint owns it, :325-333), nmatches, rotation check (:339-374;
+// the histogram counts every accept, stolen ones included, exactly as rotHist does)
+__global__ void __launch_bounds__(1024)
+k_init_finalize(const ResolveArgs A, const MatchScratch S, const InitJacobi J, int* __restrict__ owner) {
+  __shared__ int s_hist[ORBFE_HISTO_LENGTH];
+  __shared__ int s_ind[3];
+  __shared__ int s_n;
+  if (S.cursor[1] || *J.overflow) return;
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int i = tid; i < A.nKp; i += T) owner[i] = -1;
+  for (int q = tid; q < A.nQ; q += T) A.out[q] = -1;
+  if (tid < ORBFE_HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (int q = tid; q < A.nQ; q += T) {
+    const int acc = J.acc[q];
+    if (acc >= 0) atomicMax(&owner[acc & 0x3fffff], q);
+  }
+  __syncthreads();
+  const float factor = 1.0f / ORBFE_HISTO_LENGTH;  // orb_matcher.cpp:275 (the reference's bin-width bug, kept)
+  int mine = 0;
+  for (int q = tid; q < A.nQ; q += T) {
+    const int acc = J.acc[q];
+    int bin = -1;
+    if (acc >= 0) {
+      const int idx = acc & 0x3fffff;
+      if (owner[idx] == q) { A.out[q] = idx; ++mine; }
+      if (A.checkOri) {
+        float rot = __fsub_rn(A.qAngle[q], A.kp[idx].angle);
+        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+        bin = (int)roundf(__fmul_rn(rot, factor));
+        if (bin == ORBFE_HISTO_LENGTH) bin = 0;
+        atomicAdd(&s_hist[bin], 1);
+      }
+    }
+    A.evBin[q] = bin;
+  }
+  if (mine) atomicAdd(&s_n, mine);
+  __syncthreads();
+  if (A.checkOri) {
+    if (tid == 0) {  // ComputeThreeMaxima (orb_matcher.cpp:1584-1625)
+      int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+      for (int i = 0; i < ORBFE_HISTO_LENGTH; i++) {
+        const int s = s_hist[i];
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+      }
+      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+      s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+    }
+    __syncthreads();
+    int removed = 0;
+    for (int q = tid; q < A.nQ; q += T) {
+      const int bin = A.evBin[q];
+      if (bin >= 0 && bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2] && A.out[q] >= 0) { A.out[q] = -1; ++removed; }  // :364-370
+    }
+    if (removed) atomicSub(&s_n, removed);
+    __syncthreads();
+  }
+  if (tid == 0) A.result[0] = s_n;
+}
+
 // ---- OrbMatcher::DescriptorDistance, batched (orb_matcher.cpp:1630-1646) --------------------------
 __global__ void __launch_bounds__(256)
 k_descriptor_distance(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, const int n, int* __restrict__ d) {

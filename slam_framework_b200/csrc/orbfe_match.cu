@@ -52,6 +52,8 @@ struct orbfe_frame {
   int* d_jown = nullptr;
   int* d_jchanged = nullptr;
   int jCap = 0;
+  uint2* d_islots = nullptr;  // SearchForInitialization Jacobi: acceptor slots (3 x n x ORBFE_INIT_SLOTS)
+  int* d_iowner = nullptr;
   int* d_cursor = nullptr;  // [0] cursor [1] overflow [2] nmatches
   int* h_res = nullptr;     // pinned, 4 ints
   FrameGrid grid() const {
@@ -156,14 +158,20 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, const SearchSpec& sp
 #ifndef ORBFE_EMU
   CUDA_TRY(cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-  const bool jacobi = mode != ORBFE_MODE_INIT;  // SearchForInitialization keeps the serial one-warp resolve
-  if (jacobi && nq > f->jCap) {
+  const bool jacobi = mode != ORBFE_MODE_INIT;
+  const bool initJacobi = mode == ORBFE_MODE_INIT && f->n < (1 << 22) && nq > 0;  // parallel SearchForInitialization (k_init_iterate)
+  if ((jacobi || initJacobi) && nq > f->jCap) {
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(regrow(&f->d_jbest, (size_t)nq + 256));
     CUDA_TRY(regrow(&f->d_jchanged, (size_t)nq + 256 + 16));
     f->jCap = nq + 256;
   }
-  if (jacobi && !f->d_jown) CUDA_TRY(regrow(&f->d_jown, 3 * (size_t)std::max(f->n, 1)));
+  if ((jacobi || initJacobi) && !f->d_jown) CUDA_TRY(regrow(&f->d_jown, 3 * (size_t)std::max(f->n, 1)));
+  if (initJacobi && !f->d_islots) {
+    CUDA_TRY(regrow(&f->d_islots, 3 * (size_t)std::max(f->n, 1) * ORBFE_INIT_SLOTS));
+    CUDA_TRY(regrow(&f->d_iowner, (size_t)std::max(f->n, 1)));
+  }
+  bool serialInit = !initJacobi;
   for (int attempt = 0; attempt < 8; ++attempt) {
     CUDA_TRY(cudaMemsetAsync(f->d_cursor, 0, 4 * sizeof(int), st));
     MatchQueries MQ;
@@ -179,7 +187,28 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, const SearchSpec& sp
     if (nq > 0)
       MATCH_LAUNCH(f, k_match_candidates, dim3((nq + ORBFE_MATCH_THREADS / 32 - 1) / (ORBFE_MATCH_THREADS / 32)),
                    dim3(ORBFE_MATCH_THREADS), 0, f->grid(), MQ, S);
-    if (!jacobi) {
+    if (!jacobi && !serialInit) {
+      // SearchForInitialization: Jacobi iterations over the vMatchedDistance coupling, then one finalize CTA
+      InitJacobi IJ;
+      IJ.acc = f->d_jbest; IJ.cnt = f->d_jown; IJ.slots = f->d_islots; IJ.changed = f->d_jchanged; IJ.overflow = f->d_cursor + 3;
+      CUDA_TRY(cudaMemsetAsync(f->d_jown, 0, 3 * (size_t)std::max(f->n, 1) * sizeof(int), st));
+      CUDA_TRY(cudaMemsetAsync(f->d_jchanged, 0, ((size_t)nq + 16) * sizeof(int), st));
+      const int grid = std::max(1, (nq + ORBFE_MATCH_THREADS / 32 - 1) / (ORBFE_MATCH_THREADS / 32));
+      int t = 0;
+      for (;;) {
+        for (int k = 0; k < 8 && t <= nq; ++k, ++t) MATCH_LAUNCH(f, k_init_iterate, dim3(grid), dim3(ORBFE_MATCH_THREADS), 0, A, S, IJ, t);
+        CUDA_TRY(cudaMemcpyAsync(f->h_res + 3, f->d_jchanged + (t - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (f->h_res[3] == 0 || t > nq) break;
+      }
+      MATCH_LAUNCH(f, k_init_finalize, dim3(1), dim3(1024), 0, A, S, IJ, f->d_iowner);
+      CUDA_TRY(cudaMemcpyAsync(f->h_res + 3, f->d_cursor + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (f->h_res[3]) {  // a keypoint had more than ORBFE_INIT_SLOTS acceptors: exact serial resolve instead
+        serialInit = true;
+        MATCH_LAUNCH(f, k_match_resolve, dim3(1), dim3(32), smem, A, S);
+      }
+    } else if (!jacobi) {
       MATCH_LAUNCH(f, k_match_resolve, dim3(1), dim3(32), smem, A, S);
     } else {
       JacobiState J;
@@ -248,7 +277,7 @@ int orbfe_frame_destroy(orbfe_frame* f) {
   cudaFree(f->d_qx); cudaFree(f->d_qy); cudaFree(f->d_qr); cudaFree(f->d_qxr); cudaFree(f->d_qAngle); cudaFree(f->d_qMinL);
   cudaFree(f->d_qMaxL); cudaFree(f->d_qOff); cudaFree(f->d_qCnt); cudaFree(f->d_evBin); cudaFree(f->d_evIdx);
   cudaFree(f->d_qValid); cudaFree(f->d_qDesc); cudaFree(f->d_qHasObs); cudaFree(f->d_occ); cudaFree(f->d_out);
-  cudaFree(f->d_cand); cudaFree(f->d_cursor); cudaFree(f->d_jbest); cudaFree(f->d_jown); cudaFree(f->d_jchanged);
+  cudaFree(f->d_cand); cudaFree(f->d_cursor); cudaFree(f->d_jbest); cudaFree(f->d_jown); cudaFree(f->d_jchanged); cudaFree(f->d_islots); cudaFree(f->d_iowner);
   cudaFreeHost(f->h_res);
   if (f->stream) cudaStreamDestroy(f->stream);
   delete f;

@@ -145,3 +145,33 @@ def test_is_in_frustum(emu):
 
 def test_glibc_logf_restatement_matches_libm(emu):
     assert P.check_logf(emu, 200000, seed=5) > 50000
+
+
+def test_search_for_initialization_acceptor_overflow_falls_back_to_serial(emu):
+    """20 queries take the same keypoint one after the other at ever smaller distances (each accept lowers vMatchedDistance):
+    more acceptors than the parallel resolve keeps per keypoint, so it must hand over to the serial kernel; plus a longer
+    stealing chain inside the slot budget"""
+    scale = O.Extractor().tables()["scale"]
+    rng = np.random.default_rng(7)
+    base = rng.integers(0, 256, 32, dtype=np.uint8)
+    for n1 in (20, 6):
+        k2 = np.zeros(3, orbfe.KP_DTYPE)
+        k2["x"], k2["y"], k2["angle"] = [100, 140, 300], [80, 90, 200], [10, 20, 30]
+        d2 = np.stack([base, ~base, rng.integers(0, 256, 32, dtype=np.uint8)])
+        k1 = np.zeros(n1, orbfe.KP_DTYPE)
+        k1["x"], k1["y"] = 102 + np.arange(n1) % 3, 81
+        k1["angle"] = (np.arange(n1) * 7) % 360
+        d1 = np.repeat(base[None, :], n1, 0)
+        for i in range(n1):            # distance to `base` = n1 - i: strictly decreasing along the query order
+            for b in range(n1 - i):
+                d1[i, b >> 3] ^= np.uint8(1 << (b & 7))
+        bounds = (0.0, 640.0, 0.0, 480.0)
+        F1, F2 = orbfe.Frame(k1, d1, scale, bounds, lib=emu), orbfe.Frame(k2, d2, scale, bounds, lib=emu)
+        O1, O2 = O.Frame(k1, d1, scale, bounds), O.Frame(k2, d2, scale, bounds)
+        prev = np.stack([k1["x"], k1["y"]], 1).astype(np.float32)
+        for ori in (True, False):
+            n, m12, pm = orbfe.OrbMatcher(0.9, ori).SearchForInitialization(F1, F2, prev, 100)
+            on, om12, opm = O.search_for_initialization(O1, O2, prev, 100, 0.9, ori)
+            assert n == on and np.array_equal(m12, om12) and np.array_equal(pm, opm)
+            if not ori:   # the last (closest) query owns the keypoint; with the rotation check its lone bin survives or not as in the oracle
+                assert n == 1 and m12[n1 - 1] == 0 and (m12[: n1 - 1] == -1).all()
