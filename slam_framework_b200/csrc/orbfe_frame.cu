@@ -27,13 +27,36 @@ static int check_device(int device) {
   return ORBFE_OK;
 }
 
-// one allocation carved into aligned pieces; freed on scope exit
+// Per-thread, per-device scratch block carved into aligned pieces.  These entry points are stateless calls made once per frame:
+// a cudaMalloc / cudaFree pair per call would cost more than the kernels, so the block is kept and only ever grows (a thread that
+// switches devices re-allocates).  Calls are synchronous, so the block is free again when they return.
+struct ScratchCache {
+  int device = -1;
+  char* base = nullptr;
+  size_t cap = 0;
+  ~ScratchCache() { /* the CUDA context may be gone at thread exit: the block is left to process teardown */ }
+};
+static thread_local ScratchCache t_scratch;
+
 struct DeviceArena {
   char* base = nullptr;
   size_t used = 0, cap = 0;
-  ~DeviceArena() { cudaFree(base); }
   static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
   template <class T> T* take(size_t count) { T* p = reinterpret_cast<T*>(base + used); used += pad(count * sizeof(T)); return p; }
+  // binds the arena to the calling thread's cached block of `device`, growing it to `bytes`
+  cudaError_t acquire(int device, size_t bytes) {
+    ScratchCache& c = t_scratch;
+    if (c.device != device || c.cap < bytes) {
+      if (c.base && c.device == device) cudaFree(c.base);
+      c.base = nullptr; c.cap = 0; c.device = device;
+      const size_t want = bytes + bytes / 2 + 4096;
+      const cudaError_t e = cudaMalloc(&c.base, want);
+      if (e != cudaSuccess) { c.base = nullptr; return e; }
+      c.cap = want;
+    }
+    base = c.base; cap = c.cap; used = 0;
+    return cudaSuccess;
+  }
 };
 
 extern "C" {
@@ -57,8 +80,7 @@ int orbfe_undistort_keypoints(int device, int n, const orbfe_keypoint* kps, floa
   for (int i = 0; i < 14; ++i) U.k[i] = i < n_dist ? (double)dist_coeffs[i] : 0.0;
   static_assert(sizeof(orbfe_keypoint) == 28, "keypoint layout");
   DeviceArena A;
-  A.cap = 2 * DeviceArena::pad((size_t)n * sizeof(orbfe_keypoint));
-  CUDA_TRY(cudaMalloc(&A.base, A.cap));
+  CUDA_TRY(A.acquire(device, 2 * DeviceArena::pad((size_t)n * sizeof(orbfe_keypoint))));
   float* d_in = A.take<float>((size_t)n * 7);
   float* d_out = A.take<float>((size_t)n * 7);
   CUDA_TRY(cudaMemcpy(d_in, kps, (size_t)n * sizeof(orbfe_keypoint), cudaMemcpyHostToDevice));
@@ -88,8 +110,7 @@ int orbfe_is_in_frustum(int device, int n, const float* world_pos, const float* 
   F.logScaleFactor = log_scale_factor; F.viewingCosLimit = viewing_cos_limit; F.nLevels = n_levels;
   const size_t N = (size_t)n;
   DeviceArena A;
-  A.cap = 2 * DeviceArena::pad(N * 12) + 8 * DeviceArena::pad(N * 4) + DeviceArena::pad(N) + 256;
-  CUDA_TRY(cudaMalloc(&A.base, A.cap));
+  CUDA_TRY(A.acquire(device, 2 * DeviceArena::pad(N * 12) + 8 * DeviceArena::pad(N * 4) + DeviceArena::pad(N) + 256));
   float* d_w = A.take<float>(N * 3); float* d_n = A.take<float>(N * 3);
   float* d_min = A.take<float>(N); float* d_max = A.take<float>(N); float* d_raw = A.take<float>(N);
   float* d_px = A.take<float>(N); float* d_py = A.take<float>(N); float* d_pxr = A.take<float>(N); float* d_vc = A.take<float>(N);
@@ -124,8 +145,7 @@ int orbfe_debug_logf(int device, int n, const float* x, float* y) {
   if (n == 0) return ORBFE_OK;
   CUDA_TRY(cudaSetDevice(device));
   DeviceArena A;
-  A.cap = 2 * DeviceArena::pad((size_t)n * 4);
-  CUDA_TRY(cudaMalloc(&A.base, A.cap));
+  CUDA_TRY(A.acquire(device, 2 * DeviceArena::pad((size_t)n * 4)));
   float* d_x = A.take<float>(n);
   float* d_y = A.take<float>(n);
   CUDA_TRY(cudaMemcpy(d_x, x, (size_t)n * 4, cudaMemcpyHostToDevice));

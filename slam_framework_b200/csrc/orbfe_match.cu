@@ -52,6 +52,8 @@ struct orbfe_frame {
   int* d_jown = nullptr;
   int* d_jchanged = nullptr;
   int jCap = 0;
+  unsigned* d_featIdx = nullptr;  // vocabulary-node searches: the searched frame's flattened feature-vector indices
+  int featIdxCap = 0;
   uint2* d_islots = nullptr;  // SearchForInitialization Jacobi: acceptor slots (3 x n x ORBFE_INIT_SLOTS)
   int* d_iowner = nullptr;
   int* d_cursor = nullptr;  // [0] cursor [1] overflow [2] nmatches
@@ -277,7 +279,7 @@ int orbfe_frame_destroy(orbfe_frame* f) {
   cudaFree(f->d_qx); cudaFree(f->d_qy); cudaFree(f->d_qr); cudaFree(f->d_qxr); cudaFree(f->d_qAngle); cudaFree(f->d_qMinL);
   cudaFree(f->d_qMaxL); cudaFree(f->d_qOff); cudaFree(f->d_qCnt); cudaFree(f->d_evBin); cudaFree(f->d_evIdx);
   cudaFree(f->d_qValid); cudaFree(f->d_qDesc); cudaFree(f->d_qHasObs); cudaFree(f->d_occ); cudaFree(f->d_out);
-  cudaFree(f->d_cand); cudaFree(f->d_cursor); cudaFree(f->d_jbest); cudaFree(f->d_jown); cudaFree(f->d_jchanged); cudaFree(f->d_islots); cudaFree(f->d_iowner);
+  cudaFree(f->d_cand); cudaFree(f->d_cursor); cudaFree(f->d_jbest); cudaFree(f->d_jown); cudaFree(f->d_jchanged); cudaFree(f->d_islots); cudaFree(f->d_iowner); cudaFree(f->d_featIdx);
   cudaFreeHost(f->h_res);
   if (f->stream) cudaStreamDestroy(f->stream);
   delete f;
@@ -676,9 +678,13 @@ static int bow_core(orbfe_frame* f, int n1, const uint8_t* desc1, const float* a
   if (!f->d_jown) CUDA_TRY(regrow(&f->d_jown, 3 * (size_t)std::max(f->n, 1)));
   // scratch re-use: d_qDesc <- all side-1 descriptors, d_qMinL <- descriptor index, d_qMaxL <- source offset,
   // d_qx/d_qy/d_qValid <- kp1 coordinates / stereo flags (triangulation), d_occ <- valid2
-  unsigned* d_featIdx = nullptr;
-  CUDA_TRY(cudaMalloc(&d_featIdx, (size_t)std::max(nfi, 1) * sizeof(unsigned)));
-  auto done = [&](int code) { cudaFree(d_featIdx); return code; };
+  if (nfi > f->featIdxCap) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(regrow(&f->d_featIdx, (size_t)nfi + 256));
+    f->featIdxCap = nfi + 256;
+  }
+  unsigned* d_featIdx = f->d_featIdx;
+  auto done = [&](int code) { return code; };
   cudaError_t e = cudaMemcpyAsync(f->d_qDesc, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qMinL, qFeat.data(), (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_qMaxL, qSrc.data(), (size_t)nq * sizeof(int), cudaMemcpyHostToDevice, st);
