@@ -101,10 +101,6 @@ int orbfe_vocabulary_create(int device, int k, int L, int scoring, int weighting
   if (k < 0 || k > 20 || L < 1 || L > 10 || scoring < 0 || scoring > 5 || weighting < 0 || weighting > 3)  // :1356
     return orbfe_fail(ORBFE_ERR_INVALID, "not a vocabulary header: k=%d L=%d scoring=%d weighting=%d", k, L, scoring, weighting);
   if (n_nodes < 1 || (n_nodes > 1 && (!parent || !is_leaf || !desc || !weight))) return orbfe_fail(ORBFE_ERR_INVALID, "bad node arrays");
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 0; }
-  if (device < 0 || device >= ndev)
-    return orbfe_fail(ORBFE_ERR_CUDA, "CUDA device %d not available (%d visible); this library has no CPU path", device, ndev);
   std::vector<int> cnt(n_nodes + 1, 0), child(n_nodes > 1 ? n_nodes - 1 : 0);
   std::vector<unsigned> word(n_nodes, 0);
   int nWords = 0;
@@ -118,6 +114,10 @@ int orbfe_vocabulary_create(int device, int k, int L, int scoring, int weighting
     std::vector<int> fill(cnt.begin(), cnt.end() - 1);
     for (int i = 1; i < n_nodes; ++i) child[fill[parent[i]]++] = i;
   }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 0; }
+  if (device < 0 || device >= ndev)
+    return orbfe_fail(ORBFE_ERR_CUDA, "CUDA device %d not available (%d visible); this library has no CPU path", device, ndev);
   orbfe_vocabulary* v = new (std::nothrow) orbfe_vocabulary();
   if (!v) return orbfe_fail(ORBFE_ERR_NOMEM, "out of host memory");
   v->device = device; v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting; v->nNodes = n_nodes; v->nWords = nWords;

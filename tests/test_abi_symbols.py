@@ -51,3 +51,41 @@ def test_product_loader_refuses_emulated_build():
     from emu import build_emu
     with pytest.raises(orbfe.OrbfeError):
         orbfe.load(build_emu.build())
+
+
+def test_every_stateless_entry_point_fails_loudly_without_device():
+    """frame / vocabulary / frame-tail entry points: no CUDA device => an error, never a CPU result"""
+    import numpy as np
+    L = orbfe.load()
+    if L.orbfe_device_count() > 0:
+        pytest.skip("CUDA device present")
+    kps = np.zeros(4, orbfe.KP_DTYPE)
+    desc = np.zeros((4, 32), np.uint8)
+    scale = np.array([1.0, 1.2], np.float32)
+    with pytest.raises(orbfe.OrbfeError):
+        orbfe.Frame(kps, desc, scale, (0, 100, 0, 100), lib=L)
+    with pytest.raises(orbfe.OrbfeError):
+        orbfe.DescriptorDistance(desc, desc, lib=L)
+    with pytest.raises(orbfe.OrbfeError):
+        orbfe.OrbVocabulary(2, 1, 0, 0, [0, 0, 0], [0, 1, 1], np.zeros((3, 32), np.uint8), [0.0, 1.0, 1.0], lib=L)
+    with pytest.raises(orbfe.OrbfeError):
+        orbfe.UndistortKeyPoints(kps, 500.0, 500.0, 320.0, 240.0, [0.1, 0.0, 0.0, 0.0], lib=L)
+    with pytest.raises(orbfe.OrbfeError):
+        orbfe.IsInFrustum(np.ones((2, 3), np.float32), np.ones((2, 3), np.float32), [0.1, 0.1], [9.0, 9.0], [8.0, 8.0], np.eye(3),
+                          np.zeros(3), np.zeros(3), 500.0, 500.0, 320.0, 240.0, 40.0, (0, 640, 0, 480), 0.18, 8, lib=L)
+    with pytest.raises(orbfe.OrbfeError):
+        orbfe.debug_logf(np.ones(4, np.float32), lib=L)
+
+
+def test_argument_validation_precedes_everything():
+    """bad arguments are rejected with a message (no device needed to see it)"""
+    import numpy as np
+    L = orbfe.load()
+    with pytest.raises(orbfe.OrbfeError, match="vocabulary header"):
+        orbfe.OrbVocabulary(25, 6, 0, 0, [0], [0], np.zeros((1, 32), np.uint8), [0.0], lib=L)          # k > 20 (TemplatedVocabulary.h:1356)
+    with pytest.raises(orbfe.OrbfeError, match="precede"):
+        orbfe.OrbVocabulary(2, 1, 0, 0, [0, 2, 0], [0, 1, 1], np.zeros((3, 32), np.uint8), [0.0, 1.0, 1.0], lib=L)
+    with pytest.raises(orbfe.OrbfeError, match="tilted"):
+        orbfe.UndistortKeyPoints(np.zeros(1, orbfe.KP_DTYPE), 500.0, 500.0, 320.0, 240.0, [0.1] * 12 + [0.01, 0.0], lib=L)
+    with pytest.raises(orbfe.OrbfeError, match="vocabulary text file|cannot open"):
+        orbfe.OrbVocabulary.loadFromTextFile("/nonexistent/ORBvoc.txt", lib=L)
