@@ -312,6 +312,17 @@ int orbfe_is_in_frustum(int device, int n, const float* world_pos, const float* 
                         float fx, float fy, float cx, float cy, float bf, float min_x, float max_x, float min_y, float max_y,
                         float log_scale_factor, int n_levels, float viewing_cos_limit, uint8_t* in_view, float* proj_x,
                         float* proj_y, float* proj_xr, int32_t* scale_level, float* view_cos, int* n_in_view);
+/* Tracker::SearchLocalPoints (src/core/tracker.cpp:1196-1226) in one call: IsInFrustum over the n candidate local map points
+ * (arguments as orbfe_is_in_frustum; the image bounds, level count and scale factors are the frame handle's) chained on the
+ * device into OrbMatcher::SearchByProjection(Frame&, vpMapPoints, th) (arguments as orbfe_search_by_projection_mappoints).
+ * in_view[n] / scale_level[n] (optional outputs) = track_is_in_view / track_scale_level; assigned[k] = map point given to
+ * keypoint k, else -1. */
+int orbfe_search_local_points(orbfe_frame* f, int n, const float* world_pos, const float* normal, const float* min_dist,
+                              const float* max_dist, const float* max_dist_raw, const float* Rcw, const float* tcw, const float* Ow,
+                              float fx, float fy, float cx, float cy, float bf, float log_scale_factor, float viewing_cos_limit,
+                              const uint8_t* mp_desc, const uint8_t* has_obs, const uint8_t* occupied, int th, float nnratio,
+                              uint8_t* in_view, int32_t* scale_level, int32_t* assigned, int* n_in_view, int* n_matches);
+
 /* parity tap: std::log(float) as PredictScale evaluates it (glibc logf restated on the device), y[i] = logf(x[i]) */
 int orbfe_debug_logf(int device, int n, const float* x, float* y);
 

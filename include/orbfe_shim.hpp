@@ -589,6 +589,45 @@ int IsInFrustumBatch(const std::vector<MapPointT*>& vpMapPoints, const float Rcw
   return cnt;
 }
 
+// Body of Tracker::SearchLocalPoints' two loops (core/tracker.cpp:1196-1226) in one device-resident call: the visibility test
+// of IsInFrustumBatch chained into SearchByProjection(Frame&, vpMapPoints, th).  fetch as in IsInFrustumBatch.  Writes
+// track_is_in_view / track_scale_level and F.SetMapPoint exactly as the two reference routines do; returns nToMatch and the
+// number of matches through n_matches.
+template <class FrameT, class MapPointT, class FetchFn>
+int SearchLocalPoints(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, const float Rcw[9], const float tcw[3], const float Ow[3],
+                      int th, float mfNNratio, float viewingCosLimit, FetchFn fetch, int* n_matches = nullptr) {
+  const size_t n = vpMapPoints.size();
+  std::vector<float> P, Pn, mn, mx, raw;
+  std::vector<uint8_t> desc, has_obs;
+  std::vector<size_t> idx;
+  for (size_t i = 0; i < n; ++i) {
+    float p[3], q[3], a = 0, c = 0, r = 0;
+    if (!fetch(i, p, q, a, c, r)) continue;
+    vpMapPoints[i]->track_is_in_view = false;
+    idx.push_back(i);
+    P.insert(P.end(), p, p + 3); Pn.insert(Pn.end(), q, q + 3); mn.push_back(a); mx.push_back(c); raw.push_back(r);
+    const cv::Mat d = vpMapPoints[i]->GetDescriptor();
+    desc.insert(desc.end(), d.data, d.data + 32);
+    has_obs.push_back(vpMapPoints[i]->NumObservations() > 0);
+  }
+  const int m = (int)idx.size(), nkp = (int)F.GetUndistortedKeys().size();
+  std::vector<uint8_t> occupied((size_t)nkp, 0), in((size_t)m);
+  for (int k = 0; k < nkp; ++k) occupied[k] = F.GetMapPoint(k) && F.GetMapPoint(k)->NumObservations() > 0;  // orb_matcher.cpp:59-63
+  std::vector<int32_t> lvl((size_t)m), assigned((size_t)nkp, -1);
+  DeviceFrame<FrameT> dF(F);
+  int nv = 0, nm = 0;
+  check(orbfe_search_local_points(dF.get(), m, P.data(), Pn.data(), mn.data(), mx.data(), raw.data(), Rcw, tcw, Ow, F.GetFx(), F.GetFy(),
+                                  F.GetCx(), F.GetCy(), F.GetBaselineFx(), F.GetLogScaleFactor(), viewingCosLimit, desc.data(),
+                                  has_obs.data(), occupied.data(), th, mfNNratio, in.data(), lvl.data(), assigned.data(), &nv, &nm),
+        "orbfe_search_local_points");
+  for (int j = 0; j < m; ++j)
+    if (in[j]) { vpMapPoints[idx[j]]->track_is_in_view = true; vpMapPoints[idx[j]]->track_scale_level = lvl[j]; }
+  for (int k = 0; k < nkp; ++k)
+    if (assigned[k] >= 0) F.SetMapPoint(k, vpMapPoints[idx[assigned[k]]]);
+  if (n_matches) *n_matches = nm;
+  return nv;
+}
+
 // ---- OrbVocabulary: the transform path of DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>
 // (src/orb_features/orb_vocabulary.h; used by Frame::ComputeBoW frame.cpp:258-263 and KeyFrame::ComputeBoW
 // keyframe.cpp:127-137).  BowVectorT / FeatureVectorT are DBoW2::BowVector / DBoW2::FeatureVector (std::map subclasses).

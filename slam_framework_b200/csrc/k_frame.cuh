@@ -10,6 +10,8 @@
 // below (sysdeps/ieee754/flt-32/e_logf.c, glibc >= 2.27; checked against libm on 22M inputs, tests/test_oracle_primitives.py).
 #pragma once
 #include "orbfe_common.cuh"
+// (kernels are `static`: this header is included by orbfe_frame.cu and by orbfe_match.cu, which chains the frustum test into
+// the projection search without a host round trip)
 
 __device__ __forceinline__ double orbfe_dm(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double orbfe_da(double a, double b) { return __dadd_rn(a, b); }
@@ -55,7 +57,7 @@ struct UndistortArgs {
   double k[14];
 };
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_undistort_points(const UndistortArgs U, const int n, const float* __restrict__ kpIn, float* __restrict__ kpOut,
                    const int strideFloats) {
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -104,7 +106,7 @@ struct FrustumArgs {
   int nLevels;
 };
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_is_in_frustum(const FrustumArgs A, const int n, const float* __restrict__ world, const float* __restrict__ normal,
                 const float* __restrict__ minDist, const float* __restrict__ maxDist, const float* __restrict__ maxDistRaw,
                 uint8_t* __restrict__ inView,
@@ -156,8 +158,32 @@ k_is_in_frustum(const FrustumArgs A, const int n, const float* __restrict__ worl
 }
 
 // parity tap: the logf restatement over an array (tests sweep it against libm)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_debug_logf(const float* __restrict__ x, const int n, float* __restrict__ y) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i < n) y[i] = orbfe_glibc_logf(x[i]);
+}
+
+// Tracker::SearchLocalPoints glue (core/tracker.cpp:1213-1226 -> orb_matcher.cpp:29-52): the frustum outputs become the window
+// queries of SearchByProjection(Frame&, vpMapPoints, th) on the device: radius = RadiusByViewingCos(viewCos) [* th] *
+// scale_factors[level], levels [level-1, level], stereo-right consistency against track_projected_x_right.
+static __global__ void __launch_bounds__(256)
+k_frustum_to_queries(const int n, const uint8_t* __restrict__ inView, const float* __restrict__ projX, const float* __restrict__ projY,
+                     const float* __restrict__ projXR, const int* __restrict__ level, const float* __restrict__ viewCos,
+                     const float* __restrict__ scale, const int th, uint8_t* __restrict__ qValid, float* __restrict__ qx,
+                     float* __restrict__ qy, float* __restrict__ qr, float* __restrict__ qxr, int* __restrict__ qMinL,
+                     int* __restrict__ qMaxL) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const bool ok = inView[i] != 0;
+  const int lvl = level[i];
+  float r = ((double)viewCos[i] > 0.998) ? 2.5f : 4.0f;  // RadiusByViewingCos (orb_matcher.cpp:105-111)
+  if (th != 1) r = __fmul_rn(r, (float)th);               // :43-44
+  qValid[i] = ok ? 1 : 0;
+  qx[i] = projX[i];
+  qy[i] = projY[i];
+  qr[i] = ok ? __fmul_rn(r, scale[lvl]) : 0.f;            // :46
+  qxr[i] = projXR[i];
+  qMinL[i] = lvl - 1;
+  qMaxL[i] = lvl;
 }

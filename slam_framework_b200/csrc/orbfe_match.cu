@@ -5,6 +5,7 @@
 #include "../../include/orbfe.h"
 
 #include "k_match.cuh"
+#include "k_frame.cuh"
 #include "orbfe_host.h"
 
 #include <cmath>
@@ -52,6 +53,8 @@ struct orbfe_frame {
   int* d_jown = nullptr;
   int* d_jchanged = nullptr;
   int jCap = 0;
+  char* d_lp = nullptr;           // orbfe_search_local_points: frustum inputs / outputs
+  size_t lpCap = 0;
   unsigned* d_featIdx = nullptr;  // vocabulary-node searches: the searched frame's flattened feature-vector indices
   int featIdxCap = 0;
   uint2* d_islots = nullptr;  // SearchForInitialization Jacobi: acceptor slots (3 x n x ORBFE_INIT_SLOTS)
@@ -108,6 +111,7 @@ struct HostQueries {
   const uint8_t* hasObs = nullptr;  // nq (host) or null
   int n = 0;
   int filter = ORBFE_FILTER_NONE;
+  bool onDevice = false;            // x, y, r, xr, minL, maxL, valid are already in the frame's device arrays (n set by hand)
   void resize(int nq) {
     n = nq; x.assign(nq, 0.f); y.assign(nq, 0.f); r.assign(nq, 0.f); xr.assign(nq, 0.f); angle.assign(nq, 0.f);
     minL.assign(nq, -1); maxL.assign(nq, -1); valid.assign(nq, 0);
@@ -146,14 +150,16 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, const SearchSpec& sp
   if (mode == ORBFE_MODE_INIT && smem > 200 * 1024) return orbfe_fail(ORBFE_ERR_INVALID, "frame has too many keypoints (%d) for the resolve kernel", f->n);
   cudaStream_t st = f->stream;
   const size_t q4 = (size_t)nq * sizeof(float);
-  CUDA_TRY(cudaMemcpyAsync(f->d_qx, Q.x.data(), q4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(f->d_qy, Q.y.data(), q4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(f->d_qr, Q.r.data(), q4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(f->d_qxr, Q.xr.data(), q4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(f->d_qAngle, Q.angle.data(), q4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(f->d_qMinL, Q.minL.data(), q4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(f->d_qMaxL, Q.maxL.data(), q4, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(f->d_qValid, Q.valid.data(), (size_t)nq, cudaMemcpyHostToDevice, st));
+  if (!Q.onDevice) {
+    CUDA_TRY(cudaMemcpyAsync(f->d_qx, Q.x.data(), q4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(f->d_qy, Q.y.data(), q4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(f->d_qr, Q.r.data(), q4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(f->d_qxr, Q.xr.data(), q4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(f->d_qAngle, Q.angle.data(), q4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(f->d_qMinL, Q.minL.data(), q4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(f->d_qMaxL, Q.maxL.data(), q4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(f->d_qValid, Q.valid.data(), (size_t)nq, cudaMemcpyHostToDevice, st));
+  }
   CUDA_TRY(cudaMemcpyAsync(f->d_qDesc, Q.desc, (size_t)nq * 32, cudaMemcpyHostToDevice, st));
   if (Q.hasObs) CUDA_TRY(cudaMemcpyAsync(f->d_qHasObs, Q.hasObs, (size_t)nq, cudaMemcpyHostToDevice, st));
   if (occupied) CUDA_TRY(cudaMemcpyAsync(f->d_occ, occupied, (size_t)f->n, cudaMemcpyHostToDevice, st));
@@ -279,7 +285,7 @@ int orbfe_frame_destroy(orbfe_frame* f) {
   cudaFree(f->d_qx); cudaFree(f->d_qy); cudaFree(f->d_qr); cudaFree(f->d_qxr); cudaFree(f->d_qAngle); cudaFree(f->d_qMinL);
   cudaFree(f->d_qMaxL); cudaFree(f->d_qOff); cudaFree(f->d_qCnt); cudaFree(f->d_evBin); cudaFree(f->d_evIdx);
   cudaFree(f->d_qValid); cudaFree(f->d_qDesc); cudaFree(f->d_qHasObs); cudaFree(f->d_occ); cudaFree(f->d_out);
-  cudaFree(f->d_cand); cudaFree(f->d_cursor); cudaFree(f->d_jbest); cudaFree(f->d_jown); cudaFree(f->d_jchanged); cudaFree(f->d_islots); cudaFree(f->d_iowner); cudaFree(f->d_featIdx);
+  cudaFree(f->d_cand); cudaFree(f->d_cursor); cudaFree(f->d_jbest); cudaFree(f->d_jown); cudaFree(f->d_jchanged); cudaFree(f->d_islots); cudaFree(f->d_iowner); cudaFree(f->d_featIdx); cudaFree(f->d_lp);
   cudaFreeHost(f->h_res);
   if (f->stream) cudaStreamDestroy(f->stream);
   delete f;
@@ -816,6 +822,73 @@ int orbfe_search_for_triangulation(orbfe_frame* kf2, int n1, const orbfe_keypoin
   if ((rc = bow_core(kf2, n1, desc1, ang.data(), v1.data(), fv1, fv2, sp, bh, qFeat, res, n_matches))) return rc;
   for (size_t q = 0; q < qFeat.size() && q < res.size(); ++q) matches12[qFeat[q]] = res[q];
   return ORBFE_OK;
+}
+
+
+// Tracker::SearchLocalPoints (core/tracker.cpp:1196-1226): Frame::IsInFrustum over the candidate local map points
+// (frame.cpp:277-337) chained into OrbMatcher::SearchByProjection(Frame&, vpMapPoints, th) (orb_matcher.cpp:13-111) on the
+// device: the track_* arrays are produced and consumed in HBM.
+int orbfe_search_local_points(orbfe_frame* f, int n, const float* world_pos, const float* normal, const float* min_dist,
+                              const float* max_dist, const float* max_dist_raw, const float* Rcw, const float* tcw, const float* Ow,
+                              float fx, float fy, float cx, float cy, float bf, float log_scale_factor, float viewing_cos_limit,
+                              const uint8_t* mp_desc, const uint8_t* has_obs, const uint8_t* occupied, int th, float nnratio,
+                              uint8_t* in_view, int32_t* scale_level, int32_t* assigned, int* n_in_view, int* n_matches) {
+  if (!f || n < 0 || !assigned || !Rcw || !tcw || !Ow) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");
+  if (n && (!world_pos || !normal || !min_dist || !max_dist || !max_dist_raw || !mp_desc || !has_obs))
+    return orbfe_fail(ORBFE_ERR_INVALID, "null map-point array");
+  if (f->n && !occupied) return orbfe_fail(ORBFE_ERR_INVALID, "null occupied array");
+  if (n_in_view) *n_in_view = 0;
+  if (n_matches) *n_matches = 0;
+  CUDA_TRY(cudaSetDevice(f->device));
+  int rc;
+  if ((rc = ensure_queries(f, n))) return rc;
+  cudaStream_t st = f->stream;
+  const size_t N = (size_t)std::max(n, 1);
+  // inputs of the frustum test + its outputs: one scratch block (grow-only, owned by the frame handle)
+  const size_t need = (2 * 3 + 3 + 3) * N * sizeof(float) + N * sizeof(int) + N + 64;
+  if (need > f->lpCap) {
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(regrow(&f->d_lp, need + need / 2));
+    f->lpCap = need + need / 2;
+  }
+  float* d_w = reinterpret_cast<float*>(f->d_lp);
+  float* d_n = d_w + 3 * N;
+  float* d_min = d_n + 3 * N; float* d_max = d_min + N; float* d_raw = d_max + N;
+  float* d_px = d_raw + N; float* d_py = d_px + N; float* d_vc = d_py + N;
+  int* d_lvl = reinterpret_cast<int*>(d_vc + N);
+  uint8_t* d_in = reinterpret_cast<uint8_t*>(d_lvl + N);
+  FrustumArgs FA;
+  for (int i = 0; i < 9; ++i) FA.R[i] = Rcw[i];
+  for (int i = 0; i < 3; ++i) { FA.t[i] = tcw[i]; FA.Ow[i] = Ow[i]; }
+  FA.fx = fx; FA.fy = fy; FA.cx = cx; FA.cy = cy; FA.bf = bf; FA.minX = f->minX; FA.maxX = f->maxX; FA.minY = f->minY; FA.maxY = f->maxY;
+  FA.logScaleFactor = log_scale_factor; FA.viewingCosLimit = viewing_cos_limit; FA.nLevels = f->nlevels;
+  if (n) {
+    CUDA_TRY(cudaMemcpyAsync(d_w, world_pos, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_n, normal, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_min, min_dist, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_max, max_dist, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_raw, max_dist_raw, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(f->d_cursor + 3, 0, sizeof(int), st));
+    const dim3 grid((n + 255) / 256), block(256);
+    // projected x_right lands directly in the query array the candidate kernel reads
+    MATCH_LAUNCH(f, k_is_in_frustum, grid, block, 0, FA, n, d_w, d_n, d_min, d_max, d_raw, d_in, d_px, d_py, f->d_qxr, d_lvl, d_vc,
+                 f->d_cursor + 3);
+    MATCH_LAUNCH(f, k_frustum_to_queries, grid, block, 0, n, d_in, d_px, d_py, f->d_qxr, d_lvl, d_vc, f->d_lvl, th, f->d_qValid,
+                 f->d_qx, f->d_qy, f->d_qr, f->d_qxr, f->d_qMinL, f->d_qMaxL);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(f->h_res + 3, f->d_cursor + 3, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (in_view) CUDA_TRY(cudaMemcpyAsync(in_view, d_in, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (scale_level) CUDA_TRY(cudaMemcpyAsync(scale_level, d_lvl, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (n_in_view) *n_in_view = f->h_res[3];
+  }
+  HostQueries Q;
+  Q.n = n; Q.onDevice = true;
+  Q.desc = mp_desc; Q.hasObs = has_obs; Q.filter = ORBFE_FILTER_UR;
+  SearchSpec sp;
+  sp.mode = ORBFE_MODE_MAPPOINTS; sp.nnratio = nnratio; sp.thAccept = 100; sp.ratio = ORBFE_RATIO_SAMELEVEL;
+  sp.feedback = ORBFE_FEEDBACK_HASOBS;
+  return run_search(f, Q, sp, occupied, assigned, f->n, n_matches);
 }
 
 }  // extern "C"

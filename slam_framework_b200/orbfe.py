@@ -50,7 +50,7 @@ EXPORTS = [
     "orbfe_search_by_projection_sim3", "orbfe_search_by_projection_keyframe", "orbfe_fuse", "orbfe_fuse_sim3",
     "orbfe_search_by_sim3", "orbfe_search_by_bow_keyframes", "orbfe_search_for_triangulation",
     "orbfe_vocabulary_create", "orbfe_vocabulary_load_text", "orbfe_vocabulary_destroy", "orbfe_vocabulary_info",
-    "orbfe_bow_transform", "orbfe_undistort_keypoints", "orbfe_is_in_frustum", "orbfe_debug_logf",
+    "orbfe_bow_transform", "orbfe_undistort_keypoints", "orbfe_is_in_frustum", "orbfe_debug_logf", "orbfe_search_local_points",
 ]
 
 _libs = {}
@@ -125,6 +125,7 @@ def load(path=None, _test_emulation=False):
     L.orbfe_undistort_keypoints.argtypes = [i, i, vp, f, f, f, f, vp, i, vp]
     L.orbfe_is_in_frustum.argtypes = [i, i] + [vp] * 8 + [f] * 10 + [i, f] + [vp] * 7
     L.orbfe_debug_logf.argtypes = [i, i, vp, vp]
+    L.orbfe_search_local_points.argtypes = [vp, i] + [vp] * 8 + [f] * 7 + [vp] * 3 + [i, f] + [vp] * 5
     _libs[path] = L
     return L
 
@@ -623,3 +624,19 @@ def debug_logf(x, device=0, lib=None):
     y = np.zeros_like(x)
     _check(L, L.orbfe_debug_logf(device, len(x), _p(x), _p(y)))
     return y
+
+
+def SearchLocalPoints(F, world, normal, min_dist, max_dist, max_dist_raw, Rcw, tcw, Ow, fx, fy, cx, cy, bf, log_scale_factor,
+                      mp_desc, has_obs, occupied, th=1, nnratio=0.8, viewingCosLimit=0.5):
+    """Tracker::SearchLocalPoints (core/tracker.cpp:1196-1226): IsInFrustum chained into SearchByProjection on the device
+    -> (n_in_view, n_matches, in_view[n], scale_level[n], assigned[NumKeypoints])"""
+    w, nrm = _a(world, np.float32).reshape(-1, 3), _a(normal, np.float32).reshape(-1, 3)
+    n = len(w)
+    in_view, lvl, assigned = np.zeros(n, np.uint8), np.zeros(n, np.int32), np.zeros(len(F.kps), np.int32)
+    nv, nm = C.c_int(), C.c_int()
+    _check(F.L, F.L.orbfe_search_local_points(
+        F.h, n, _p(w), _p(nrm), _p(_a(min_dist, np.float32)), _p(_a(max_dist, np.float32)), _p(_a(max_dist_raw, np.float32)),
+        _p(_a(Rcw, np.float32).reshape(9)), _p(_a(tcw, np.float32).reshape(3)), _p(_a(Ow, np.float32).reshape(3)), fx, fy, cx, cy, bf,
+        log_scale_factor, viewingCosLimit, _p(_a(mp_desc, np.uint8)), _p(_a(has_obs, np.uint8)), _p(_a(occupied, np.uint8)), int(th),
+        nnratio, _p(in_view), _p(lvl), _p(assigned), C.byref(nv), C.byref(nm)))
+    return nv.value, nm.value, in_view, lvl, assigned

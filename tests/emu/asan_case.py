@@ -43,4 +43,5 @@ P.check_bow_transform(L, da[:257], seed=22, k=4, L=5)
 # N2: the Frame tail
 P.check_undistort_keypoints(L, ka, seed=31)
 P.check_is_in_frustum(L, 5000, seed=32)
+P.check_search_local_points(L, ka, da, scale, 640, 200, seed=42, n_extra=700)
 print("ASAN-RUN-OK")

@@ -543,3 +543,46 @@ def check_logf(lib, n=400000, seed=0):
     got = orbfe.debug_logf(x, lib=lib)
     assert np.array_equal(got[idx].view(np.uint32), ref_s.view(np.uint32)), "logf restatement differs from libm"
     return len(idx)
+
+
+def check_search_local_points(lib, kps, desc, scale, w, h, seed=0, u_right=None, th=1, n_extra=2000):
+    """Tracker::SearchLocalPoints in one device-resident call == oracle IsInFrustum followed by oracle SearchByProjection"""
+    rng = np.random.default_rng(seed)
+    F, OF = make_frames(kps, desc, scale, w, h, lib, u_right)
+    fx = fy = np.float32(718.856); cx, cy = np.float32(607.1928), np.float32(185.2157)
+    n0 = len(kps)
+    src = np.concatenate([np.arange(n0), rng.integers(0, n0, n_extra)])
+    n = len(src)
+    z = rng.uniform(3, 70, n).astype(np.float32)
+    z[rng.uniform(0, 1, n) < 0.03] = -4.0
+    jx, jy = rng.uniform(-2.5, 2.5, n).astype(np.float32), rng.uniform(-2.5, 2.5, n).astype(np.float32)
+    world = np.stack([(kps["x"][src] + jx - cx) / fx * z, (kps["y"][src] + jy - cy) / fy * z, z], 1).astype(np.float32)
+    t = np.array([0.03, -0.01, 0.2], np.float32)
+    R = np.eye(3, dtype=np.float32)
+    Ow = (-t).astype(np.float32)
+    PO = world - Ow
+    d = np.linalg.norm(PO, axis=1).astype(np.float32)
+    nrm = (PO / np.maximum(d[:, None], 1e-6) + rng.normal(0, 0.3, (n, 3))).astype(np.float32)
+    nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
+    raw = (d * scale[np.minimum(kps["octave"][src] + rng.integers(0, 2, n), len(scale) - 1)]).astype(np.float32)
+    maxd = (np.float32(1.2) * raw).astype(np.float32)
+    mind = (np.float32(0.8) * raw / scale[-1]).astype(np.float32)
+    md = desc[src].copy()
+    for i in range(n):
+        for b in rng.choice(256, rng.integers(0, 40), replace=False):
+            md[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    has_obs = (rng.uniform(0, 1, n) < 0.8).astype(np.uint8)
+    occupied = (rng.uniform(0, 1, n0) < 0.1).astype(np.uint8)
+    lsf = float(np.log(np.float32(1.2)).astype(np.float32))
+    bf = KITTI["bf"]
+    nv, nm, in_view, lvl, asg = orbfe.SearchLocalPoints(F, world, nrm, mind, maxd, raw, R, t, Ow, float(fx), float(fy), float(cx), float(cy),
+                                                        bf, lsf, md, has_obs, occupied, th, 0.8)
+    onv, tr = O.is_in_frustum(world, nrm, mind, maxd, raw, R, t, Ow, float(fx), float(fy), float(cx), float(cy), bf,
+                              (0.0, float(w), 0.0, float(h)), lsf, len(scale), 0.5)
+    onm, oasg = O.search_by_projection_mappoints(OF, tr["in_view"], tr["proj_x"], tr["proj_y"], tr["proj_xr"], tr["level"], tr["view_cos"],
+                                                 md, has_obs, occupied, th, 0.8)
+    assert nv == onv and np.array_equal(in_view, tr["in_view"]), f"in view: {nv} vs oracle {onv}"
+    assert np.array_equal(lvl[in_view == 1], tr["level"][in_view == 1])
+    assert nm == onm, f"SearchLocalPoints: {nm} matches vs oracle {onm}"
+    assert np.array_equal(asg, oasg)
+    return nm

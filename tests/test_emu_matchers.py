@@ -175,3 +175,12 @@ def test_search_for_initialization_acceptor_overflow_falls_back_to_serial(emu):
             assert n == on and np.array_equal(m12, om12) and np.array_equal(pm, opm)
             if not ori:   # the last (closest) query owns the keypoint; with the rotation check its lone bin survives or not as in the oracle
                 assert n == 1 and m12[n1 - 1] == 0 and (m12[: n1 - 1] == -1).all()
+
+
+def test_search_local_points_device_resident(emu, two_frames):
+    ka, da, _, _, scale = two_frames
+    rng = np.random.default_rng(41)
+    ur = np.where(rng.uniform(0, 1, len(ka)) < 0.6, ka["x"] - rng.uniform(1, 60, len(ka)), -1).astype(np.float32)
+    # the synthetic camera of the check is KITTI's; a 640x200 frame sees the upper-left part of its field of view
+    assert P.check_search_local_points(emu, ka, da, scale, 640, 200, seed=42, u_right=ur) > 200
+    assert P.check_search_local_points(emu, ka, da, scale, 640, 200, seed=43, th=3, n_extra=500) > 200

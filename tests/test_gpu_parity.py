@@ -381,3 +381,12 @@ def test_cuda_path_equals_the_references_own_code(lib):
         assert np.array_equal(k[f], rk[f]), f
     assert np.array_equal(d, rd)
     ex.close()
+
+
+def test_n2_search_local_points_device_resident(lib, kitti_two_frames):
+    """Tracker::SearchLocalPoints (core/tracker.cpp:1196-1226) as one call: IsInFrustum chained into SearchByProjection in HBM"""
+    ka, da, _, _, scale = kitti_two_frames
+    rng = np.random.default_rng(81)
+    ur = np.where(rng.uniform(0, 1, len(ka)) < 0.6, ka["x"] - rng.uniform(1, 60, len(ka)), -1).astype(np.float32)
+    assert P.check_search_local_points(lib, ka, da, scale, 1241, 376, seed=82, u_right=ur, n_extra=18000) > 800
+    assert P.check_search_local_points(lib, ka, da, scale, 1241, 376, seed=83, th=5, n_extra=3000) > 800
