@@ -59,6 +59,12 @@ struct MockFrame {
   const std::vector<float>& StereoCoordRight() const { return ur; }
   const std::vector<float>& ScaleFactors() const { return scale; }
   const std::map<unsigned, std::vector<unsigned> >& GetFeatureVector() const { return fv; }
+  float GetFx() const { return 718.856f; }
+  float GetFy() const { return 718.856f; }
+  float GetCx() const { return 607.1928f; }
+  float GetCy() const { return 185.2157f; }
+  float GetBaselineFx() const { return 386.1448f; }
+  float GetLogScaleFactor() const { return std::log(1.2f); }
   float GetMinX() const { return 0; }
   float GetMaxX() const { return w; }
   float GetMinY() const { return 0; }
@@ -119,6 +125,12 @@ static int n1_selfcheck(const std::vector<cv::KeyPoint>& kps, const cv::Mat& des
   int near_px = 0;
   for (size_t i = 0; i < n; ++i)
     near_px += pts[i].track_is_in_view && std::fabs(pts[i].track_projected_x - kps[i].pt.x) < 0.01f && pts[i].track_view_cos > 0.99f;
+  // SearchLocalPoints in one device-resident call: the same points must be visible and (nearly) all matched to their keypoints
+  MockFrame F2 = F;
+  F2.mps.assign(n, nullptr);
+  int nm = 0;
+  const int vis2 = orbfe::SearchLocalPoints(F2, mpv, I3, Z3, Z3, 1, 0.8f, 0.5f, fetch, &nm);
+  if (vis2 != vis || nm < (int)(0.5 * n)) { fprintf(stderr, "SearchLocalPoints: %d visible, %d matched of %zu\n", vis2, nm, n); return 4; }
   printf("%zu %d %d %d %d %d %d %d %d %d %d %d\n", n, a, c, d, e, f, g, h1, h2, moved, vis, near_px);
   return 0;
 }
