@@ -118,7 +118,8 @@ static int n1_selfcheck(const std::vector<cv::KeyPoint>& kps, const cv::Mat& des
     Pw[0] = (kps[i].pt.x - cx0) / fx * 10.f; Pw[1] = (kps[i].pt.y - cy0) / fx * 10.f; Pw[2] = 10.f;
     const float len = std::sqrt(Pw[0] * Pw[0] + Pw[1] * Pw[1] + Pw[2] * Pw[2]);
     for (int c2 = 0; c2 < 3; ++c2) Pn[c2] = Pw[c2] / len;
-    mn = 1.f; mx = 40.f; raw = 40.f / 1.2f;
+    raw = len * std::pow(1.2f, (float)kps[i].octave);  // PredictScale then lands on the keypoint's own octave (or one above)
+    mn = 1.f; mx = 1.2f * raw;
     return true;
   };
   const int vis = orbfe::IsInFrustumBatch(mpv, I3, Z3, Z3, fx, fx, cx0, cy0, 386.1448f, b, std::log(1.2f), 8, 0.5f, fetch);
