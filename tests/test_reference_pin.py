@@ -53,6 +53,12 @@ def test_extractor_other_geometries_and_thresholds():
     assert_same_extraction(low, 2000, what="low contrast")
 
 
+def test_extractor_parameter_sweep():
+    img = synth.frame(seed=14)
+    for nf, par in ((100, (1.2, 8, 20, 7)), (2000, (1.2, 1, 20, 7)), (3000, (1.1, 12, 20, 7)), (500, (1.3, 6, 12, 5)), (2000, (1.2, 8, 7, 7))):
+        assert_same_extraction(img, nf, par, what=f"nfeatures {nf}, {par}")
+
+
 def test_extractor_config5_1080p_8000():
     assert assert_same_extraction(synth.frame(1080, 1920, seed=3), 8000, what="1080p") > 7900
 
