@@ -71,3 +71,11 @@ def test_colour_upload_matches_cvtcolor_then_extract(emu, channels, rgb):
     ok, od = O.Extractor(300).extract(ref)
     P.assert_kps_equal(b["kps"][0, :b["n"][0]], ok)
     assert np.array_equal(b["desc"][0, :b["n"][0]], od)
+
+
+@pytest.mark.parametrize("nf,params", [(300, (1.2, 1, 20, 7)), (600, (1.1, 12, 20, 7)), (400, (1.5, 5, 20, 7)), (400, (2.0, 4, 20, 7)),
+                                       (300, (2.5, 3, 20, 7)), (500, (1.3, 6, 12, 5)), (500, (1.2, 8, 7, 7)), (60, (1.2, 8, 40, 12))])
+def test_extractor_parameter_sweep(emu, nf, params):
+    """other pyramids (1 and 12 levels, scale 1.1 / 1.5, exact 2x = OpenCV's INTER_AREA path, > 2x = generic resize kernel),
+    thresholds (ini == min: no fallback round) and small quotas, stage by stage"""
+    P.check_extract(emu, synth.frame(200, 640, seed=int(params[0] * 10) + params[1]), nfeatures=nf, params=params)

@@ -390,3 +390,11 @@ def test_n2_search_local_points_device_resident(lib, kitti_two_frames):
     ur = np.where(rng.uniform(0, 1, len(ka)) < 0.6, ka["x"] - rng.uniform(1, 60, len(ka)), -1).astype(np.float32)
     assert P.check_search_local_points(lib, ka, da, scale, 1241, 376, seed=82, u_right=ur, n_extra=18000) > 800
     assert P.check_search_local_points(lib, ka, da, scale, 1241, 376, seed=83, th=5, n_extra=3000) > 800
+
+
+@pytest.mark.parametrize("nf,params", [(2000, (1.2, 1, 20, 7)), (3000, (1.1, 12, 20, 7)), (1500, (1.5, 5, 20, 7)), (1000, (2.0, 4, 20, 7)),
+                                       (800, (2.5, 3, 20, 7)), (500, (1.3, 6, 12, 5)), (2000, (1.2, 8, 7, 7)), (100, (1.2, 8, 40, 12))])
+def test_extractor_parameter_sweep(lib, nf, params):
+    """the extractor is not KITTI-specific: 1 and 12 levels, scale 1.1 / 1.5, exact 2x (OpenCV's INTER_AREA path), > 2x (generic
+    resize kernel), other thresholds (ini == min: no fallback round), small quotas -- stage by stage against the oracle"""
+    P.check_extract(lib, synth.frame(seed=int(params[0] * 10) + params[1]), nfeatures=nf, params=params)
