@@ -43,9 +43,9 @@ def check_extract(lib, img, nfeatures=2000, stages=True, params=(1.2, 8, 20, 7))
     return kps, desc
 
 
-def check_stereo(lib, left, right, nfeatures=2000, bf=KITTI["bf"], fx=KITTI["fx"]):
-    eL, eR = orbfe.ORBextractor(nfeatures, lib=lib), orbfe.ORBextractor(nfeatures, lib=lib)
-    oL, oR = O.Extractor(nfeatures), O.Extractor(nfeatures)
+def check_stereo(lib, left, right, nfeatures=2000, bf=KITTI["bf"], fx=KITTI["fx"], params=(1.2, 8, 20, 7)):
+    eL, eR = orbfe.ORBextractor(nfeatures, *params, lib=lib), orbfe.ORBextractor(nfeatures, *params, lib=lib)
+    oL, oR = O.Extractor(nfeatures, *params), O.Extractor(nfeatures, *params)
     kl, dl = eL.Compute(left)
     kr, dr = eR.Compute(right)
     okl, odl = oL.extract(left)

@@ -398,3 +398,11 @@ def test_extractor_parameter_sweep(lib, nf, params):
     """the extractor is not KITTI-specific: 1 and 12 levels, scale 1.1 / 1.5, exact 2x (OpenCV's INTER_AREA path), > 2x (generic
     resize kernel), other thresholds (ini == min: no fallback round), small quotas -- stage by stage against the oracle"""
     P.check_extract(lib, synth.frame(seed=int(params[0] * 10) + params[1]), nfeatures=nf, params=params)
+
+
+@pytest.mark.parametrize("nf,params,bf", [(1500, (1.5, 5, 20, 7), 386.1448), (1000, (2.0, 4, 20, 7), 386.1448), (3000, (1.1, 12, 20, 7), 120.0),
+                                          (2000, (1.2, 1, 20, 7), 386.1448)])
+def test_stereo_parameter_sweep(lib, nf, params, bf):
+    """ComputeStereoMatches on other pyramids (the SAD refinement runs on the keypoint's own level) and another baseline"""
+    l, r = synth.stereo_pair(seed=90 + params[1])
+    assert P.check_stereo(lib, l, r, nfeatures=nf, bf=bf, params=params) > 50

@@ -120,6 +120,21 @@ def test_stereo_frame_constructor(seed, shape, nf):
     assert np.array_equal(F.depth, dp)
 
 
+@pytest.mark.parametrize("nf,params,bf", [(1500, (1.5, 5, 20, 7), 386.1448), (1000, (2.0, 4, 20, 7), 386.1448), (3000, (1.1, 12, 20, 7), 120.0),
+                                          (2000, (1.2, 1, 20, 7), 386.1448)])
+def test_stereo_frame_constructor_parameter_sweep(nf, params, bf):
+    l, r = synth.stereo_pair(seed=90 + params[1])
+    F = R.Frame(l, r, nfeatures=nf, params=params, bf=bf)
+    oL, oR = O.Extractor(nf, *params), O.Extractor(nf, *params)
+    okl, odl = oL.extract(l)
+    okr, odr = oR.extract(r)
+    assert np.array_equal(F.kps, okl) and np.array_equal(F.kps_right, okr) and np.array_equal(F.desc, odl)
+    b, fx = np.float32(bf), np.float32(CAM["fx"])
+    n, ur, dp = O.stereo_match(oL, oR, okl, odl, okr, odr, float(b), float(b / fx))
+    assert n == int((F.u_right >= 0).sum()) and n > 50
+    assert np.array_equal(F.u_right, ur) and np.array_equal(F.depth, dp)
+
+
 def test_frame_grid_get_features_in_area():
     F = R.Frame(synth.frame(seed=2))
     OF = oracle_frame_of(F)
