@@ -423,6 +423,23 @@ def run_ours(args):
                 lat2.append((time.perf_counter() - t0) * 1e3)
         latency["fused_p50_ms_per_frame"] = statistics.median(lat2)
         latency["fused_path"] = "orbfe_upload(2) + orbfe_run + orbfe_run_stereo + orbfe_download on one handle"
+        # the same drop-in path driven from C++ through include/orbfe_shim.hpp (what the reference's Frame constructor would run:
+        # two std::threads with ORBextractor::Compute, then ComputeStereoMatches), without the Python call overhead
+        try:
+            import tempfile
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from test_shim_cpp import build_demo
+            exe = build_demo()
+            with tempfile.TemporaryDirectory() as td:
+                l0, r0 = pairs[0]
+                l0.tofile(os.path.join(td, "l.raw")); r0.tofile(os.path.join(td, "r.raw"))
+                o = subprocess.check_output([exe, "--latency", str(W), str(H), os.path.join(td, "l.raw"), os.path.join(td, "r.raw"), "200"],
+                                            text=True, timeout=120).split()
+            latency["cpp_shim_p50_ms_per_frame"] = float(o[0])
+            latency["cpp_shim_min_ms"] = float(o[1])
+            latency["cpp_shim_path"] = "C++ shim: 2 std::threads x ORBextractor::Compute + orbfe::ComputeStereoMatches, 200 frames"
+        except Exception as e:  # the demo binary is test infrastructure: its absence must not fail the bench
+            latency["cpp_shim_error"] = str(e)[:200]
         e1.close()
 
     # ---- CPU baseline (oracle port on the host cores; bounded sample) ----------------------------------

@@ -5,6 +5,8 @@
 //   shim_demo W H left.raw right.raw out_prefix      |      shim_demo --link-check
 #include "orbfe_shim.hpp"
 
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <thread>
@@ -184,6 +186,35 @@ int main(int argc, char** argv) {
     cv::Mat dsc;
     ex(img, cv::Mat(), k, dsc);
     return bow_check(argv[5], dsc);
+  }
+  if (argc == 7 && std::string(argv[1]) == "--latency") {  // shim_demo --latency W H left.raw right.raw N
+    // the drop-in path exactly as Frame's stereo constructor drives it (frame.cpp:86-99): two std::threads per frame running
+    // ORBextractor::Compute, then ComputeStereoMatches; prints p50 / min / max milliseconds per stereo frame over N frames
+    const int W = atoi(argv[2]), H = atoi(argv[3]), N = atoi(argv[6]);
+    std::vector<uint8_t> l = slurp(argv[4], (size_t)W * H), r = slurp(argv[5], (size_t)W * H);
+    cv::Mat left(H, W, CV_8UC1, l.data()), right(H, W, CV_8UC1, r.data());
+    ORBextractor exL(2000, 1.2f, 8, 20, 7), exR(2000, 1.2f, 8, 20, 7);
+    std::vector<double> ms;
+    size_t nkp = 0, nmatch = 0;
+    for (int it = 0; it < N + 10; ++it) {
+      std::vector<cv::KeyPoint> kl, kr;
+      cv::Mat dl, dr;
+      std::vector<float> ur, depth;
+      const auto t0 = std::chrono::steady_clock::now();
+      std::thread tl([&]() { exL.Compute(left, cv::Mat(), kl, dl); });
+      std::thread tr([&]() { exR.Compute(right, cv::Mat(), kr, dr); });
+      tl.join();
+      tr.join();
+      orbfe::ComputeStereoMatches(exL, exR, kl, kr, dl, dr, 386.1448f, 386.1448f / 718.856f, ur, depth);
+      const auto t1 = std::chrono::steady_clock::now();
+      if (it >= 10) ms.push_back(std::chrono::duration<double, std::milli>(t1 - t0).count());
+      nkp = kl.size() + kr.size();
+      nmatch = 0;
+      for (size_t i = 0; i < ur.size(); ++i) nmatch += ur[i] >= 0;
+    }
+    std::sort(ms.begin(), ms.end());
+    printf("%.4f %.4f %.4f %zu %zu\n", ms[ms.size() / 2], ms.front(), ms.back(), nkp, nmatch);
+    return 0;
   }
   if (argc != 6) return 1;
   const int W = atoi(argv[1]), H = atoi(argv[2]);
