@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""Secondary measurement: the matcher rows (M2-M4) of SURVEY.md 8 on the GPU next to the CPU oracle, on the
+"""TEST-SIDE measurement tool (it loads the oracle as checker and CPU arm, so it lives under tests/).  Secondary measurement: the matcher rows (M2-M4) of SURVEY.md 8 on the GPU next to the CPU oracle, on the
 BASELINE config-4 / config-5 shapes.  Wall clock of the C-ABI call (host arrays in, host arrays out), median of
-`reps` calls; prints one JSON line.  usage: python tools/bench_matchers.py [--reps 20]"""
+`reps` calls; prints one JSON line.  usage: python tests/bench_matchers.py [--reps 20]"""
 import argparse, json, os, statistics, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import oracle_lib as O

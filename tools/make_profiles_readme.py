@@ -61,7 +61,7 @@ desc = {"_bench_n1.json": "bench.py JSON line, N=1", "_bench_n2.json": "bench.py
         "_bench_n4.json": "bench.py JSON line, N=4", "_bench_n8.json": "bench.py JSON line, N=8",
         "_bench_reference.json": "`bench.py --impl reference` JSON line (oracle port on the host cores)",
         "_launches_pairs16.csv": "`ncu --metrics gpu__time_duration.sum --clock-control none` launch list of `bench.py --steps 2 --warmup 3 --pairs 16 --no-cpu --no-latency`",
-        "_matchers.json": "`tools/bench_matchers.py`: matcher rows (M2-M4), N1 routines and the N3 vocabulary transform, wall clock of one C-ABI call on the GPU next to the CPU oracle (1 thread)",
+        "_matchers.json": "`tests/bench_matchers.py`: matcher rows (M2-M4), N1 routines and the N3 vocabulary transform, wall clock of one C-ABI call on the GPU next to the CPU oracle (1 thread)",
         "_ncu_full_summary.txt": "`ncu --set full --clock-control none --import-source on` of the same command, one step, summarised by tools/ncu_summary.py (time, DRAM bytes, occupancy, pipe utilisation, stall reasons per kernel)",
         "_ncu_sass_regions_fast.txt": "hot SASS regions of `k_fast_cells` (tools/ncu_sass_regions.py)"}
 for f in sorted(os.listdir(P)):
