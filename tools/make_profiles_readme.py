@@ -15,7 +15,8 @@ out = [f"# profiles/ — {tag} evidence\n",
        "| quantity | value |", "|---|---|",
        f"| `value` (inputs resident, CUDA events) | **{d['value']:.0f} stereo pairs/s** ({d['ms_per_step']:.3f} ms / 64-pair step) |",
        f"| `e2e` (pinned host in -> host out, 2 handles pipelined) | **{d['e2e']['value']:.0f} stereo pairs/s** ({d['e2e']['h2d_bytes_per_step']/1e6:.1f} MB H2D + {d['e2e']['d2h_bytes_per_step']/1e6:.1f} MB D2H per step) |",
-       f"| p50 latency, one pair, drop-in calls (2x `orbfe_extract` on 2 threads + `orbfe_stereo_match`) | {d['latency']['p50_ms_per_frame']:.3f} ms |",
+       f"| p50 latency, one pair, drop-in calls driven from Python/ctypes (2x `orbfe_extract` on 2 threads + `orbfe_stereo_match`) | {d['latency']['p50_ms_per_frame']:.3f} ms |",
+       f"| p50 latency, one pair, drop-in path driven from C++ (`orbfe_shim.hpp`: 2 `std::thread`s x `ORBextractor::Compute` + `ComputeStereoMatches`) | {d['latency'].get('cpp_shim_p50_ms_per_frame', float('nan')):.3f} ms |",
        f"| p50 latency, one pair, one batched call sequence | {d['latency'].get('fused_p50_ms_per_frame', float('nan')):.3f} ms |",
        f"| CPU baseline (oracle port, {d['cpu_baseline']['cores']} host cores) | {d['cpu_baseline']['value']:.0f} stereo pairs/s ({d['cpu_baseline']['sample']}) |",
        f"| kernel launches in the timed region | {d['gpu_launches']} ({d['gpu_launches']//d['steps']} per step) |",
