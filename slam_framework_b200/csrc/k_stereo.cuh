@@ -32,7 +32,8 @@ struct StereoPair {
   float* depth;
   int* sad;
   int* rowStart;                // S1 row table of the right image: nRows+1 offsets ...
-  int* rowItems;                // ... into right-keypoint indices (k_stereo_rows)
+  uint2* rowItems;              // ... into (right-keypoint index | octave << 24, x as float bits): the search filters on
+                                // octave and x before it touches the descriptor, so they travel with the index
   int rowCap;
 };
 
@@ -74,7 +75,7 @@ k_stereo_rows(const __grid_constant__ Geom g, const StereoPair* __restrict__ pai
     const int minr = max((int)floorf(__fsub_rn(kr.y, r)), 0);
     for (int yi = minr; yi <= maxr; ++yi) {
       const int pos = atomicAdd(&s_cnt[yi], 1);
-      if (pos < P.rowCap) P.rowItems[pos] = iR;
+      if (pos < P.rowCap) P.rowItems[pos] = make_uint2((unsigned)iR | ((unsigned)kr.octave << 24), __float_as_uint(kr.x));
     }
   }
 }
@@ -114,10 +115,11 @@ k_stereo_search(const __grid_constant__ Geom g, const StereoPair* __restrict__ p
     const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(P.descL + (size_t)iL * 32) + 1);
     const int cb = P.rowStart[row], ce = min(P.rowStart[row + 1], P.rowCap);
     for (int c = cb + lane; c < ce; c += 32) {
-      const int iR = P.rowItems[c];  // vRowIndices[row] (frame.cpp:450)
-      const orbfe_kp_dev kr = P.kpR[iR];
-      if (kr.octave < levelL - 1 || kr.octave > levelL + 1) continue;
-      if (kr.x >= minU && kr.x <= maxU) {
+      const uint2 it = P.rowItems[c];  // vRowIndices[row] (frame.cpp:450)
+      const int iR = (int)(it.x & 0xffffffu), octR = (int)(it.x >> 24);
+      const float xR = __uint_as_float(it.y);
+      if (octR < levelL - 1 || octR > levelL + 1) continue;
+      if (xR >= minU && xR <= maxU) {
         const int dist = orbfe_hamming256(a0, a1, P.descR + (size_t)iR * 32);
         if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
       }

@@ -85,7 +85,7 @@ struct orbfe_extractor {
   int* d_sad = nullptr;
   int* d_nMatched = nullptr;
   int* d_rowStart = nullptr;        // per pair: h0 + 1 offsets
-  int* d_rowItems = nullptr;        // per pair: rowCap indices
+  uint2* d_rowItems = nullptr;      // per pair: rowCap (index | octave, x) entries
   int rowCap = 0;
   size_t rowSmem = 0;
   // pinned staging
@@ -144,7 +144,7 @@ static void free_arena(orbfe_extractor* ex) {
   cudaFree(ex->oct.finKey); cudaFree(ex->d_lvlKp); cudaFree(ex->d_lvlCnt); cudaFree(ex->d_kps); cudaFree(ex->d_desc);
   cudaFree(ex->d_icw); ex->d_icw = nullptr; cudaFree(ex->d_nKp); cudaFree(ex->d_lut); cudaFree(ex->d_wlut); ex->d_wlut = nullptr; cudaFree(ex->d_rlut); ex->d_rlut = nullptr; cudaFree(ex->d_err); cudaFree(ex->d_pairs); cudaFree(ex->d_uR);
   cudaFree(ex->d_depth); cudaFree(ex->d_sad); cudaFree(ex->d_nMatched); cudaFree(ex->d_rowStart); cudaFree(ex->d_rowItems);
-  ex->d_rowStart = ex->d_rowItems = nullptr;
+  ex->d_rowStart = nullptr; ex->d_rowItems = nullptr;
   cudaFreeHost(ex->h_n); cudaFreeHost(ex->h_kps); cudaFreeHost(ex->h_desc); cudaFreeHost(ex->h_uR);
   cudaFreeHost(ex->h_depth); cudaFreeHost(ex->h_pairs);
   ex->d_img = ex->d_pyr = ex->d_blur = nullptr; ex->d_cellCnt = nullptr; ex->d_cellList = nullptr;
@@ -402,7 +402,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   ex->rowCap = g.totalOut * (2 * (int)std::ceil(2.0f * ex->scale[nl - 1]) + 3);
   ex->rowSmem = (size_t)(h0 + 1) * sizeof(int);
   CUDA_TRY(cudaMalloc(&ex->d_rowStart, S * (size_t)(h0 + 1) * sizeof(int)));
-  CUDA_TRY(cudaMalloc(&ex->d_rowItems, S * (size_t)ex->rowCap * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->d_rowItems, S * (size_t)ex->rowCap * sizeof(uint2)));
   CUDA_TRY(cudaMallocHost(&ex->h_n, (2 * S + 1) * sizeof(int)));
   memset(ex->h_n, 0, (2 * S + 1) * sizeof(int));
   CUDA_TRY(cudaMallocHost(&ex->h_kps, S * g.totalOut * sizeof(orbfe_kp_dev)));
