@@ -168,7 +168,7 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, const SearchSpec& sp
 #endif
   const bool jacobi = mode != ORBFE_MODE_INIT;
   const bool initJacobi = mode == ORBFE_MODE_INIT && f->n < (1 << 22) && nq > 0;  // parallel SearchForInitialization (k_init_iterate)
-  if ((jacobi || initJacobi) && nq > f->jCap) {
+  if ((jacobi || initJacobi) && (nq > f->jCap || !f->d_jbest)) {
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(regrow(&f->d_jbest, (size_t)nq + 256));
     CUDA_TRY(regrow(&f->d_jchanged, (size_t)nq + 256 + 16));
@@ -675,7 +675,7 @@ static int bow_core(orbfe_frame* f, int n1, const uint8_t* desc1, const float* a
   if ((rc = ensure_out(f, std::max(std::max(f->n, nfi), nq)))) return rc;
   if ((rc = ensure_cand(f, total + 16))) return rc;
   cudaStream_t st = f->stream;
-  if (nq > f->jCap) {
+  if (nq > f->jCap || !f->d_jbest) {
     CUDA_TRY(cudaStreamSynchronize(st));
     CUDA_TRY(regrow(&f->d_jbest, (size_t)nq + 256));
     CUDA_TRY(regrow(&f->d_jchanged, (size_t)nq + 256 + 16));

@@ -586,3 +586,36 @@ def check_search_local_points(lib, kps, desc, scale, w, h, seed=0, u_right=None,
     assert nm == onm, f"SearchLocalPoints: {nm} matches vs oracle {onm}"
     assert np.array_equal(asg, oasg)
     return nm
+
+
+def check_empty_inputs(lib, ka, da, scale):
+    """zero map points / queries / features through every N1-N3 entry point: no crash, empty results"""
+    F = orbfe.Frame(ka, da, scale, (0, 640, 0, 200), lib=lib)
+    E = orbfe.Frame(ka[:0], da[:0], scale, (0, 640, 0, 200), lib=lib)
+    z8, zf, zi = np.zeros(0, np.uint8), np.zeros(0, np.float32), np.zeros(0, np.int32)
+    zd = np.zeros((0, 32), np.uint8)
+    n, m = orbfe.SearchByProjectionSim3(F, z8, zf, zf, zi, zd, np.zeros(len(ka), np.uint8), 10)
+    assert n == 0 and (m == -1).all()
+    n, m = orbfe.SearchByProjectionKeyFrame(F, z8, zf, zf, zi, zf, zd, np.zeros(len(ka), np.uint8), 10.0, 100)
+    assert n == 0 and (m == -1).all()
+    for ur in (zf, None):
+        n, b = orbfe.Fuse(F, z8, zf, zf, ur, zi, zd, 3.0)
+        assert n == 0 and len(b) == 0
+    side0 = (z8, zf, zf, zi, zd)
+    sideF = (np.zeros(len(ka), np.uint8), np.zeros(len(ka), np.float32), np.zeros(len(ka), np.float32), np.zeros(len(ka), np.int32), da)
+    assert orbfe.SearchBySim3(E, F, side0, sideF, 7.5)[0] == 0
+    n, m = orbfe.SearchBySim3(F, E, sideF, side0, 7.5)
+    assert n == 0 and (m == -1).all()
+    assert orbfe.SearchByBoW(F, zd, zf, z8, {}, {}, 0.7, True)[0] == 0
+    assert orbfe.SearchByBoW(E, da, ka["angle"], np.ones(len(ka), np.uint8), {3: [0, 1]}, {}, 0.7, True)[0] == 0
+    n, m = orbfe.SearchByBoWKeyFrames(F, zd, zf, z8, np.ones(len(ka), np.uint8), {}, {1: [0]}, 0.8, True)
+    assert n == 0 and len(m) == 0
+    n, m = orbfe.SearchForTriangulation(F, ka[:0], zd, z8, z8, np.ones(len(ka), np.uint8), {}, {}, np.eye(3), 0.0, 0.0)
+    assert n == 0 and len(m) == 0
+    cnt, out = orbfe.IsInFrustum(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), zf, zf, zf, np.eye(3), np.zeros(3), np.zeros(3),
+                                 700.0, 700.0, 600.0, 180.0, 380.0, (0, 640, 0, 200), 0.18, 8, lib=lib)
+    assert cnt == 0 and len(out["in_view"]) == 0
+    nv, nm, iv, lv, asg = orbfe.SearchLocalPoints(F, np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), zf, zf, zf, np.eye(3), np.zeros(3),
+                                                  np.zeros(3), 700.0, 700.0, 600.0, 180.0, 380.0, 0.18, zd, z8, np.zeros(len(ka), np.uint8))
+    assert nv == 0 and nm == 0 and (asg == -1).all()
+    assert len(orbfe.debug_logf(zf, lib=lib)) == 0

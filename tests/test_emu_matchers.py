@@ -184,3 +184,8 @@ def test_search_local_points_device_resident(emu, two_frames):
     # the synthetic camera of the check is KITTI's; a 640x200 frame sees the upper-left part of its field of view
     assert P.check_search_local_points(emu, ka, da, scale, 640, 200, seed=42, u_right=ur) > 200
     assert P.check_search_local_points(emu, ka, da, scale, 640, 200, seed=43, th=3, n_extra=500) > 200
+
+
+def test_empty_inputs_everywhere(emu, two_frames):
+    ka, da, _, _, scale = two_frames
+    P.check_empty_inputs(emu, ka, da, scale)

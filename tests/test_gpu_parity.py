@@ -406,3 +406,8 @@ def test_stereo_parameter_sweep(lib, nf, params, bf):
     """ComputeStereoMatches on other pyramids (the SAD refinement runs on the keypoint's own level) and another baseline"""
     l, r = synth.stereo_pair(seed=90 + params[1])
     assert P.check_stereo(lib, l, r, nfeatures=nf, bf=bf, params=params) > 50
+
+
+def test_empty_inputs_everywhere(lib, kitti_two_frames):
+    ka, da, _, _, scale = kitti_two_frames
+    P.check_empty_inputs(lib, ka, da, scale)
