@@ -161,6 +161,13 @@ int orbfe_frame_create(int device, int n, const orbfe_keypoint* kps_un, const ui
                        const float* u_right, float min_x, float max_x, float min_y, float max_y,
                        int nlevels, const float* scale_factors, orbfe_frame** out);
 int orbfe_frame_destroy(orbfe_frame* f);
+/* The same handle built from the DEVICE-resident results of extractor slot `slot` (after orbfe_run / orbfe_extract; with
+ * use_stereo the slot's stereo coordinates from orbfe_run_stereo / orbfe_stereo_match are taken as StereoCoordRight()):
+ * keypoints and descriptors go device to device.  Only for cameras whose undistortion is the identity (Frame::
+ * UndistortKeyPoints returns the keypoints unchanged when dist_coeff[0] == 0, frame.cpp:616-619). */
+int orbfe_frame_from_extractor(orbfe_extractor* ex, int slot, int use_stereo, float min_x, float max_x, float min_y, float max_y,
+                               orbfe_frame** out);
+int orbfe_frame_num_keypoints(const orbfe_frame* f);
 /* Frame::GetFeaturesInArea (frame.cpp:348-403): indices in the reference's order */
 int orbfe_features_in_area(orbfe_frame* f, float x, float y, float r, int min_level, int max_level,
                            int32_t* out, int capacity, int* n_out);

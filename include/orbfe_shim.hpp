@@ -187,6 +187,22 @@ class DeviceFrame {
   orbfe_frame* h_;
 };
 
+// The same view built device to device from the extractor that just processed the frame's image (rectified cameras only:
+// UndistortKeyPoints is then the identity, frame.cpp:616-619).  with_stereo: take the stereo coordinates ComputeStereoMatches left
+// on the device for this (left) extractor.
+class DeviceFrameFromExtractor {
+ public:
+  DeviceFrameFromExtractor(ORBextractor& ex, float minX, float maxX, float minY, float maxY, bool with_stereo) : h_(nullptr) {
+    check(orbfe_frame_from_extractor(ex.handle(), 0, with_stereo ? 1 : 0, minX, maxX, minY, maxY, &h_), "orbfe_frame_from_extractor");
+  }
+  ~DeviceFrameFromExtractor() { orbfe_frame_destroy(h_); }
+  DeviceFrameFromExtractor(const DeviceFrameFromExtractor&) = delete;
+  DeviceFrameFromExtractor& operator=(const DeviceFrameFromExtractor&) = delete;
+  orbfe_frame* get() const { return h_; }
+ private:
+  orbfe_frame* h_;
+};
+
 // Body of OrbMatcher::SearchForInitialization (orb_matcher.cpp:264-382).
 template <class FrameT>
 int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,

@@ -105,6 +105,18 @@ k_grid_build(const MatchKp* __restrict__ kp, const int n, const float minX, cons
   }
 }
 
+// extractor output records (cv::KeyPoint layout, 7 x 4 bytes) -> the matcher's view, on the device
+__global__ void __launch_bounds__(256)
+k_kp_to_match(const float* __restrict__ kp7, const int n, MatchKp* __restrict__ out, const float* __restrict__ uRin, float* __restrict__ uRout) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const float* k = kp7 + (size_t)i * 7;
+  MatchKp m;
+  m.x = k[0]; m.y = k[1]; m.angle = k[3]; m.octave = __float_as_int(k[5]);
+  out[i] = m;
+  uRout[i] = uRin ? uRin[i] : -1.0f;
+}
+
 // cell range of a query window (frame.cpp:356-369); returns false if the window misses the grid
 __device__ __forceinline__ bool orbfe_window_cells(const FrameGrid& F, float x, float y, float r, int& x0, int& x1, int& y0,
                                                    int& y1) {

@@ -496,6 +496,20 @@ static int check_images(orbfe_extractor* ex, int first, int n) {
   return ORBFE_OK;
 }
 
+int orbfe_internal_slot_view(orbfe_extractor* ex, int slot, OrbfeSlotView* out) {
+  if (!ex || !out) return orbfe_fail(ORBFE_ERR_INVALID, "null argument");
+  if (!ex->configured || slot < 0 || slot >= ex->S) return orbfe_fail(ORBFE_ERR_INVALID, "slot %d has no extraction results", slot);
+  const Geom& g = ex->g;
+  out->device = ex->device; out->stream = ex->stream;
+  out->kps = ex->d_kps + (size_t)slot * g.totalOut;
+  out->desc = ex->d_desc + (size_t)slot * g.totalOut * 32;
+  out->uR = ex->d_uR ? ex->d_uR + (size_t)slot * g.totalOut : nullptr;
+  out->nKp = ex->d_nKp + slot;
+  out->capacity = g.totalOut; out->nlevels = g.nlevels; out->w = g.w0; out->h = g.h0;
+  for (int l = 0; l < g.nlevels && l < 16; ++l) out->scale[l] = ex->scale[l];
+  return ORBFE_OK;
+}
+
 extern "C" {
 
 const char* orbfe_last_error(void) { return t_last_error.c_str(); }

@@ -4,3 +4,18 @@
 
 // records a thread-local message for orbfe_last_error() and returns `code`
 int orbfe_fail(int code, const char* fmt, ...);
+
+// device-resident view of one slot of an extractor handle (orbfe_api.cu), for entry points of other translation units that
+// consume extraction results without a host round trip (orbfe_frame_from_extractor)
+struct orbfe_extractor;
+struct OrbfeSlotView {
+  int device;
+  void* stream;          // cudaStream_t of the extractor handle
+  const void* kps;       // orbfe_kp_dev[capacity] (28-byte cv::KeyPoint records)
+  const unsigned char* desc;
+  const float* uR;       // stereo right coordinates of the slot (valid after orbfe_run_stereo on a left slot), may be null
+  const int* nKp;        // device: keypoint count of the slot
+  int capacity, nlevels, w, h;
+  float scale[16];
+};
+int orbfe_internal_slot_view(orbfe_extractor* ex, int slot, OrbfeSlotView* out);

@@ -356,6 +356,69 @@ int orbfe_frame_create(int device, int n, const orbfe_keypoint* kps_un, const ui
   return ORBFE_OK;
 }
 
+// A Frame's matcher view built from the DEVICE-resident results of an extractor slot (after orbfe_run / orbfe_extract, and
+// orbfe_run_stereo when use_stereo): keypoints, descriptors and stereo coordinates go device to device, so tracking a frame
+// needs no D2H -> H2D round trip of its own features.  Undistortion must be the identity (rectified input, dist_coeff[0] == 0,
+// frame.cpp:616-619); otherwise build the handle from the undistorted host keypoints with orbfe_frame_create.
+int orbfe_frame_from_extractor(orbfe_extractor* ex, int slot, int use_stereo, float min_x, float max_x, float min_y, float max_y,
+                               orbfe_frame** out) {
+  if (!out) return orbfe_fail(ORBFE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (!(max_x > min_x) || !(max_y > min_y)) return orbfe_fail(ORBFE_ERR_INVALID, "bad image bounds");
+  OrbfeSlotView V;
+  int rc;
+  if ((rc = orbfe_internal_slot_view(ex, slot, &V))) return rc;
+  CUDA_TRY(cudaSetDevice(V.device));
+  CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(V.stream)));
+  int n = 0;
+  CUDA_TRY(cudaMemcpy(&n, V.nKp, sizeof(int), cudaMemcpyDeviceToHost));
+  n = std::max(0, std::min(n, V.capacity));
+  orbfe_frame* f = new (std::nothrow) orbfe_frame();
+  if (!f) return orbfe_fail(ORBFE_ERR_NOMEM, "out of host memory");
+  f->device = V.device; f->n = n; f->nlevels = V.nlevels;
+  f->minX = min_x; f->maxX = max_x; f->minY = min_y; f->maxY = max_y;
+  f->gw = static_cast<float>(max_x - min_x) / ORBFE_GRID_COLS;
+  f->gh = static_cast<float>(max_y - min_y) / ORBFE_GRID_ROWS;
+  f->scale.assign(V.scale, V.scale + V.nlevels);
+  f->hkp.resize(n);
+  std::vector<float> lvl(3 * (size_t)V.nlevels);
+  for (int l = 0; l < V.nlevels; ++l) {
+    lvl[l] = V.scale[l];
+    lvl[V.nlevels + l] = l == 0 ? 1.0f : V.scale[l] * V.scale[l];
+    lvl[2 * V.nlevels + l] = 1.0f / lvl[V.nlevels + l];
+  }
+  auto fail = [&](cudaError_t e) {
+    orbfe_frame_destroy(f);
+    return orbfe_fail(ORBFE_ERR_CUDA, "frame setup failed: %s", cudaGetErrorString(e));
+  };
+  cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+  const size_t n1 = std::max(n, 1);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_kp, n1 * sizeof(MatchKp));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_desc, n1 * 32);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_uR, n1 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_lvl, lvl.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_lvl, lvl.data(), lvl.size() * sizeof(float), cudaMemcpyHostToDevice, f->stream);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_cellStart, (ORBFE_GRID_CELLS + 1) * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_cellItems, n1 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_occ, n1);
+  if (e == cudaSuccess) e = cudaMalloc(&f->d_cursor, 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMallocHost(&f->h_res, 4 * sizeof(int));
+  if (e == cudaSuccess && n) e = cudaMemcpyAsync(f->d_desc, V.desc, (size_t)n * 32, cudaMemcpyDeviceToDevice, f->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(f->d_occ, 0, n1, f->stream);
+  if (e != cudaSuccess) return fail(e);
+  if (n) MATCH_LAUNCH(f, k_kp_to_match, dim3((n + 255) / 256), dim3(256), 0, static_cast<const float*>(V.kps), n, f->d_kp,
+                      use_stereo ? V.uR : nullptr, f->d_uR);
+  MATCH_LAUNCH(f, k_grid_build, dim3(1), dim3(1024), 0, f->d_kp, n, f->minX, f->minY, f->gw, f->gh, f->d_cellStart, f->d_cellItems);
+  e = cudaGetLastError();
+  if (e == cudaSuccess && n) e = cudaMemcpyAsync(f->hkp.data(), f->d_kp, (size_t)n * sizeof(MatchKp), cudaMemcpyDeviceToHost, f->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
+  if (e != cudaSuccess) return fail(e);
+  *out = f;
+  return ORBFE_OK;
+}
+
+int orbfe_frame_num_keypoints(const orbfe_frame* f) { return f ? f->n : 0; }
+
 int orbfe_features_in_area(orbfe_frame* f, float x, float y, float r, int min_level, int max_level, int32_t* out,
                            int capacity, int* n_out) {
   if (!f || !n_out || capacity < 0 || (capacity && !out)) return orbfe_fail(ORBFE_ERR_INVALID, "bad arguments");

@@ -51,6 +51,7 @@ EXPORTS = [
     "orbfe_search_by_sim3", "orbfe_search_by_bow_keyframes", "orbfe_search_for_triangulation",
     "orbfe_vocabulary_create", "orbfe_vocabulary_load_text", "orbfe_vocabulary_destroy", "orbfe_vocabulary_info",
     "orbfe_bow_transform", "orbfe_undistort_keypoints", "orbfe_is_in_frustum", "orbfe_debug_logf", "orbfe_search_local_points",
+    "orbfe_frame_from_extractor", "orbfe_frame_num_keypoints",
 ]
 
 _libs = {}
@@ -105,6 +106,8 @@ def load(path=None, _test_emulation=False):
     L.orbfe_descriptor_distance.argtypes = [i, vp, vp, i, vp]
     L.orbfe_frame_create.argtypes = [i, i, vp, vp, vp, f, f, f, f, i, vp, C.POINTER(vp)]
     L.orbfe_frame_destroy.argtypes = [vp]
+    L.orbfe_frame_from_extractor.argtypes = [vp, i, i, f, f, f, f, C.POINTER(vp)]
+    L.orbfe_frame_num_keypoints.argtypes = [vp]
     L.orbfe_features_in_area.argtypes = [vp, f, f, f, i, i, vp, i, vp]
     L.orbfe_search_for_initialization.argtypes = [vp, vp, vp, vp, i, f, i, vp]
     L.orbfe_search_by_projection_mappoints.argtypes = [vp, i] + [vp] * 9 + [i, f, vp, vp]
@@ -355,6 +358,19 @@ class Frame:
         _check(self.L, self.L.orbfe_frame_create(device, len(self.kps), _p(self.kps), _p(self.desc), _p(self.ur),
                                                 self.bounds[0], self.bounds[1], self.bounds[2], self.bounds[3],
                                                 len(self.scale), _p(self.scale), C.byref(self.h)))
+
+    @classmethod
+    def from_extractor(cls, ex, bounds, slot=0, stereo=False):
+        """the matcher view of the frame whose extraction results sit in slot `slot` of extractor `ex`, built device to
+        device (orbfe_frame_from_extractor); `kps` is a placeholder of the right length, the features never reach the host"""
+        self = cls.__new__(cls)
+        self.L = ex.L
+        self.bounds = tuple(float(b) for b in bounds)
+        self.h = vp()
+        _check(self.L, self.L.orbfe_frame_from_extractor(ex.h, int(slot), int(stereo), *self.bounds, C.byref(self.h)))
+        self.kps = np.zeros(self.L.orbfe_frame_num_keypoints(self.h), KP_DTYPE)
+        self.desc, self.ur, self.scale = None, None, ex.GetScaleFactors()
+        return self
 
     def close(self):
         if getattr(self, "h", None):

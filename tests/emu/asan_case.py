@@ -44,4 +44,7 @@ P.check_bow_transform(L, da[:257], seed=22, k=4, L=5)
 P.check_undistort_keypoints(L, ka, seed=31)
 P.check_is_in_frustum(L, 5000, seed=32)
 P.check_search_local_points(L, ka, da, scale, 640, 200, seed=42, n_extra=700)
+l2, r2 = synth.stereo_pair(120, 400, seed=8)
+P.check_frame_from_extractor(L, l2, r2, nfeatures=400, seed=52)
+P.check_empty_inputs(L, ka, da, scale)
 print("ASAN-RUN-OK")

@@ -619,3 +619,44 @@ def check_empty_inputs(lib, ka, da, scale):
                                                   np.zeros(3), 700.0, 700.0, 600.0, 180.0, 380.0, 0.18, zd, z8, np.zeros(len(ka), np.uint8))
     assert nv == 0 and nm == 0 and (asg == -1).all()
     assert len(orbfe.debug_logf(zf, lib=lib)) == 0
+
+
+def check_frame_from_extractor(lib, left, right, nfeatures=2000, seed=0):
+    """orbfe_frame_from_extractor: the matcher view built device to device from an extractor slot behaves exactly like the one
+    built from the downloaded host arrays (and like the oracle's)"""
+    rng = np.random.default_rng(seed)
+    h, w = left.shape
+    ex = orbfe.ORBextractor(nfeatures, lib=lib, max_images=2)
+    ex.upload([left, right])
+    ex.run(2)
+    ex.run_stereo(1, KITTI["bf"], KITTI["bf"] / KITTI["fx"])
+    b = ex.download(2, ex.make_buffers(2, stereo=True))
+    n = int(b["n"][0])
+    kps, desc, ur = b["kps"][0, :n].copy(), b["desc"][0, :n].copy(), b["ur"][0, :n].copy()
+    scale = ex.GetScaleFactors()
+    bounds = (0.0, float(w), 0.0, float(h))
+    FD = orbfe.Frame.from_extractor(ex, bounds, slot=0, stereo=True)
+    FR = orbfe.Frame.from_extractor(ex, bounds, slot=1, stereo=False)
+    assert len(FD.kps) == n and len(FR.kps) == int(b["n"][1])
+    FH, OF = make_frames(kps, desc, scale, w, h, lib, ur)
+    check_features_in_area(FD, OF, rng, w, h)
+    mp = synth_map_points(kps, desc, rng, 4000, ur)
+    args = (mp["valid"], mp["px"], mp["py"], mp["pxr"], mp["lvl"], mp["view"], mp["desc"], mp["has_obs"], mp["occupied"])
+    m = orbfe.OrbMatcher(0.8)
+    nd, ad = m.SearchByProjectionMapPoints(FD, *args, 1)
+    nh, ah = m.SearchByProjectionMapPoints(FH, *args, 1)
+    on, oa = O.search_by_projection_mappoints(OF, *args, 1, 0.8)
+    assert nd == nh == on and np.array_equal(ad, ah) and np.array_equal(ad, oa)
+    # right-image slot, monocular view: SearchForInitialization between the two device-built frames == host-built ones
+    nr = int(b["n"][1])
+    kr, dr = b["kps"][1, :nr].copy(), b["desc"][1, :nr].copy()
+    FD0 = orbfe.Frame.from_extractor(ex, bounds, slot=0, stereo=False)
+    FH0, OF0 = make_frames(kps, desc, scale, w, h, lib)
+    FHR, OFR = make_frames(kr, dr, scale, w, h, lib)
+    prev = np.stack([kps["x"], kps["y"]], 1).astype(np.float32)
+    r1 = orbfe.OrbMatcher(0.9, True).SearchForInitialization(FD0, FR, prev, 100)
+    r2 = orbfe.OrbMatcher(0.9, True).SearchForInitialization(FH0, FHR, prev, 100)
+    r3 = O.search_for_initialization(OF0, OFR, prev, 100, 0.9, True)
+    assert r1[0] == r2[0] == r3[0] and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[1], r3[1]) and np.array_equal(r1[2], r3[2])
+    ex.close()
+    return nd

@@ -189,3 +189,8 @@ def test_search_local_points_device_resident(emu, two_frames):
 def test_empty_inputs_everywhere(emu, two_frames):
     ka, da, _, _, scale = two_frames
     P.check_empty_inputs(emu, ka, da, scale)
+
+
+def test_frame_from_extractor_device_resident(emu):
+    l, r = synth.stereo_pair(188, 620, seed=6)
+    assert P.check_frame_from_extractor(emu, l, r, nfeatures=800, seed=51) > 100

@@ -411,3 +411,9 @@ def test_stereo_parameter_sweep(lib, nf, params, bf):
 def test_empty_inputs_everywhere(lib, kitti_two_frames):
     ka, da, _, _, scale = kitti_two_frames
     P.check_empty_inputs(lib, ka, da, scale)
+
+
+def test_frame_from_extractor_device_resident(lib):
+    """extract -> matcher view -> searches with the frame's own features never leaving the device"""
+    l, r = synth.stereo_pair(seed=91)
+    assert P.check_frame_from_extractor(lib, l, r, seed=92) > 500
