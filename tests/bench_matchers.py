@@ -117,6 +117,52 @@ def main():
         "search_for_triangulation_ms_cpu_oracle_1thread": med(lambda: O.search_for_triangulation(OFB, *tr), 5),
         "note": "wall clock of one C-ABI call, host arrays in/out (includes H2D/D2H and the flattening of the feature vectors "
                 "in the Python wrapper on both arms)"}
+    # the per-frame tracking front-end end to end, device-resident: stereo pair in -> extraction -> stereo matching -> matcher view
+    # (device to device) -> SearchLocalPoints over 5000 local map points; only the images and the map points cross PCIe
+    lt, rt = synth.stereo_pair(seed=71)
+    ext = orbfe.ORBextractor(lib=L, max_images=2)
+    rngt = np.random.default_rng(72)
+    def extract_pair():
+        ext.upload([lt, rt]); ext.run(2); ext.run_stereo(1, P.KITTI["bf"], P.KITTI["bf"] / P.KITTI["fx"])
+    extract_pair()
+    bt = ext.download(2, ext.make_buffers(2, stereo=True))
+    nt = int(bt["n"][0]); kt, dt = bt["kps"][0, :nt].copy(), bt["desc"][0, :nt].copy()
+    fxk, cxk, cyk = np.float32(718.856), np.float32(607.1928), np.float32(185.2157)
+    src = rngt.integers(0, nt, 5000)
+    zt = rngt.uniform(4, 60, 5000).astype(np.float32)
+    wt = np.stack([(kt["x"][src] - cxk) / fxk * zt, (kt["y"][src] - cyk) / fxk * zt, zt], 1).astype(np.float32)
+    dist = np.linalg.norm(wt, axis=1).astype(np.float32)
+    nrm = (wt / dist[:, None]).astype(np.float32)
+    sc = ext.GetScaleFactors()
+    raw = (dist * sc[kt["octave"][src]]).astype(np.float32)
+    mx, mn = (np.float32(1.2) * raw).astype(np.float32), (np.float32(0.8) * raw / sc[-1]).astype(np.float32)
+    mdesc = dt[src].copy(); hob = np.ones(5000, np.uint8); occ = np.zeros(nt, np.uint8)
+    lsf = float(np.log(np.float32(1.2)).astype(np.float32))
+    I3, Z3 = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
+    def track_frame():
+        extract_pair()
+        Fd = orbfe.Frame.from_extractor(ext, (0.0, 1241.0, 0.0, 376.0), slot=0, stereo=True)
+        r = orbfe.SearchLocalPoints(Fd, wt, nrm, mn, mx, raw, I3, Z3, Z3, float(fxk), float(fxk), float(cxk), float(cyk), P.KITTI["bf"], lsf,
+                                    mdesc, hob, occ, 1, 0.8)
+        Fd.close()
+        return r
+    nv, nm = track_frame()[:2]
+    oL_, oR_ = O.Extractor(), O.Extractor()
+    def track_frame_cpu():
+        okl, odl = oL_.extract(lt); okr, odr = oR_.extract(rt)
+        _, our, _ = O.stereo_match(oL_, oR_, okl, odl, okr, odr, P.KITTI["bf"], P.KITTI["bf"] / P.KITTI["fx"])
+        OFt = O.Frame(okl, odl, sc, (0.0, 1241.0, 0.0, 376.0), our)
+        _, tr = O.is_in_frustum(wt, nrm, mn, mx, raw, I3, Z3, Z3, float(fxk), float(fxk), float(cxk), float(cyk), P.KITTI["bf"],
+                                (0.0, 1241.0, 0.0, 376.0), lsf, 8, 0.5)
+        return O.search_by_projection_mappoints(OFt, tr["in_view"], tr["proj_x"], tr["proj_y"], tr["proj_xr"], tr["level"], tr["view_cos"],
+                                                mdesc, hob, occ, 1, 0.8)
+    onm = track_frame_cpu()[0]
+    assert nm == onm, (nm, onm)
+    out["tracking_frontend_device_resident"] = {
+        "stereo_pair_to_local_map_matches_ms_gpu": med(track_frame, a.reps),
+        "same_on_cpu_oracle_1thread_ms": med(track_frame_cpu, 3),
+        "local_map_points": 5000, "in_view": nv, "matches": nm,
+        "path": "orbfe_upload(2) + orbfe_run + orbfe_run_stereo + orbfe_frame_from_extractor + orbfe_search_local_points"}
     print(json.dumps(out))
 
 
