@@ -167,6 +167,10 @@ int orbfe_frame_destroy(orbfe_frame* f);
  * UndistortKeyPoints returns the keypoints unchanged when dist_coeff[0] == 0, frame.cpp:616-619). */
 int orbfe_frame_from_extractor(orbfe_extractor* ex, int slot, int use_stereo, float min_x, float max_x, float min_y, float max_y,
                                orbfe_frame** out);
+/* per-frame form: refresh a handle made by orbfe_frame_from_extractor with the next frame's results; its device arrays only grow,
+ * so steady-state tracking allocates nothing */
+int orbfe_frame_refresh_from_extractor(orbfe_frame* f, orbfe_extractor* ex, int slot, int use_stereo, float min_x, float max_x,
+                                       float min_y, float max_y);
 int orbfe_frame_num_keypoints(const orbfe_frame* f);
 /* Frame::GetFeaturesInArea (frame.cpp:348-403): indices in the reference's order */
 int orbfe_features_in_area(orbfe_frame* f, float x, float y, float r, int min_level, int max_level,

@@ -30,6 +30,7 @@ struct orbfe_frame {
   int device = 0;
   cudaStream_t stream = nullptr;
   int n = 0, nlevels = 0;
+  int kpCap = 0;  // capacity of the per-keypoint device arrays (handles refreshed from an extractor grow in place)
   float minX = 0, maxX = 0, minY = 0, maxY = 0, gw = 1, gh = 1;
   std::vector<float> scale;
   std::vector<MatchKp> hkp;  // host copy (prevMatched update, validation)
@@ -174,10 +175,10 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, const SearchSpec& sp
     CUDA_TRY(regrow(&f->d_jchanged, (size_t)nq + 256 + 16));
     f->jCap = nq + 256;
   }
-  if ((jacobi || initJacobi) && !f->d_jown) CUDA_TRY(regrow(&f->d_jown, 3 * (size_t)std::max(f->n, 1)));
+  if ((jacobi || initJacobi) && !f->d_jown) CUDA_TRY(regrow(&f->d_jown, 3 * (size_t)std::max(std::max(f->n, f->kpCap), 1)));
   if (initJacobi && !f->d_islots) {
-    CUDA_TRY(regrow(&f->d_islots, 3 * (size_t)std::max(f->n, 1) * ORBFE_INIT_SLOTS));
-    CUDA_TRY(regrow(&f->d_iowner, (size_t)std::max(f->n, 1)));
+    CUDA_TRY(regrow(&f->d_islots, 3 * (size_t)std::max(std::max(f->n, f->kpCap), 1) * ORBFE_INIT_SLOTS));
+    CUDA_TRY(regrow(&f->d_iowner, (size_t)std::max(std::max(f->n, f->kpCap), 1)));
   }
   bool serialInit = !initJacobi;
   for (int attempt = 0; attempt < 8; ++attempt) {
@@ -360,61 +361,81 @@ int orbfe_frame_create(int device, int n, const orbfe_keypoint* kps_un, const ui
 // orbfe_run_stereo when use_stereo): keypoints, descriptors and stereo coordinates go device to device, so tracking a frame
 // needs no D2H -> H2D round trip of its own features.  Undistortion must be the identity (rectified input, dist_coeff[0] == 0,
 // frame.cpp:616-619); otherwise build the handle from the undistorted host keypoints with orbfe_frame_create.
-int orbfe_frame_from_extractor(orbfe_extractor* ex, int slot, int use_stereo, float min_x, float max_x, float min_y, float max_y,
-                               orbfe_frame** out) {
-  if (!out) return orbfe_fail(ORBFE_ERR_INVALID, "null argument");
-  *out = nullptr;
+// (re)fills `f` from the slot; device arrays only ever grow, so a handle refreshed every frame allocates nothing in steady state
+static int frame_fill_from_slot(orbfe_frame* f, orbfe_extractor* ex, int slot, int use_stereo, float min_x, float max_x, float min_y,
+                                float max_y) {
   if (!(max_x > min_x) || !(max_y > min_y)) return orbfe_fail(ORBFE_ERR_INVALID, "bad image bounds");
   OrbfeSlotView V;
   int rc;
   if ((rc = orbfe_internal_slot_view(ex, slot, &V))) return rc;
+  if (f->stream && f->device != V.device) return orbfe_fail(ORBFE_ERR_INVALID, "frame handle and extractor live on different devices");
   CUDA_TRY(cudaSetDevice(V.device));
   CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(V.stream)));
-  int n = 0;
-  CUDA_TRY(cudaMemcpy(&n, V.nKp, sizeof(int), cudaMemcpyDeviceToHost));
-  n = std::max(0, std::min(n, V.capacity));
-  orbfe_frame* f = new (std::nothrow) orbfe_frame();
-  if (!f) return orbfe_fail(ORBFE_ERR_NOMEM, "out of host memory");
-  f->device = V.device; f->n = n; f->nlevels = V.nlevels;
+  if (!f->stream) {
+    f->device = V.device;
+    CUDA_TRY(cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&f->d_cellStart, (ORBFE_GRID_CELLS + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&f->d_cursor, 4 * sizeof(int)));
+    CUDA_TRY(cudaMallocHost(&f->h_res, 4 * sizeof(int)));
+  }
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  CUDA_TRY(cudaMemcpyAsync(f->h_res, V.nKp, sizeof(int), cudaMemcpyDeviceToHost, f->stream));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  const int n = std::max(0, std::min(f->h_res[0], V.capacity));
+  if (n > f->kpCap || !f->d_kp) {  // grow the per-keypoint arrays; the lazily sized resolve buffers follow
+    const size_t c = (size_t)std::max(n, V.capacity > 0 ? std::min(V.capacity, n + n / 4 + 256) : 1);
+    CUDA_TRY(regrow(&f->d_kp, c)); CUDA_TRY(regrow(&f->d_desc, c * 32)); CUDA_TRY(regrow(&f->d_uR, c));
+    CUDA_TRY(regrow(&f->d_cellItems, c)); CUDA_TRY(regrow(&f->d_occ, c));
+    cudaFree(f->d_jown); f->d_jown = nullptr;
+    cudaFree(f->d_islots); f->d_islots = nullptr;
+    cudaFree(f->d_iowner); f->d_iowner = nullptr;
+    f->kpCap = (int)c;
+  }
+  if (f->nlevels != V.nlevels || !f->d_lvl || !std::equal(f->scale.begin(), f->scale.end(), V.scale)) {
+    std::vector<float> lvl(3 * (size_t)V.nlevels);
+    for (int l = 0; l < V.nlevels; ++l) {
+      lvl[l] = V.scale[l];
+      lvl[V.nlevels + l] = l == 0 ? 1.0f : V.scale[l] * V.scale[l];
+      lvl[2 * V.nlevels + l] = 1.0f / lvl[V.nlevels + l];
+    }
+    CUDA_TRY(regrow(&f->d_lvl, lvl.size()));
+    CUDA_TRY(cudaMemcpy(f->d_lvl, lvl.data(), lvl.size() * sizeof(float), cudaMemcpyHostToDevice));
+    f->scale.assign(V.scale, V.scale + V.nlevels);
+    f->nlevels = V.nlevels;
+  }
+  f->n = n;
   f->minX = min_x; f->maxX = max_x; f->minY = min_y; f->maxY = max_y;
   f->gw = static_cast<float>(max_x - min_x) / ORBFE_GRID_COLS;
   f->gh = static_cast<float>(max_y - min_y) / ORBFE_GRID_ROWS;
-  f->scale.assign(V.scale, V.scale + V.nlevels);
   f->hkp.resize(n);
-  std::vector<float> lvl(3 * (size_t)V.nlevels);
-  for (int l = 0; l < V.nlevels; ++l) {
-    lvl[l] = V.scale[l];
-    lvl[V.nlevels + l] = l == 0 ? 1.0f : V.scale[l] * V.scale[l];
-    lvl[2 * V.nlevels + l] = 1.0f / lvl[V.nlevels + l];
-  }
-  auto fail = [&](cudaError_t e) {
-    orbfe_frame_destroy(f);
-    return orbfe_fail(ORBFE_ERR_CUDA, "frame setup failed: %s", cudaGetErrorString(e));
-  };
-  cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
-  const size_t n1 = std::max(n, 1);
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_kp, n1 * sizeof(MatchKp));
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_desc, n1 * 32);
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_uR, n1 * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_lvl, lvl.size() * sizeof(float));
-  if (e == cudaSuccess) e = cudaMemcpyAsync(f->d_lvl, lvl.data(), lvl.size() * sizeof(float), cudaMemcpyHostToDevice, f->stream);
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_cellStart, (ORBFE_GRID_CELLS + 1) * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_cellItems, n1 * sizeof(int));
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_occ, n1);
-  if (e == cudaSuccess) e = cudaMalloc(&f->d_cursor, 4 * sizeof(int));
-  if (e == cudaSuccess) e = cudaMallocHost(&f->h_res, 4 * sizeof(int));
-  if (e == cudaSuccess && n) e = cudaMemcpyAsync(f->d_desc, V.desc, (size_t)n * 32, cudaMemcpyDeviceToDevice, f->stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(f->d_occ, 0, n1, f->stream);
-  if (e != cudaSuccess) return fail(e);
+  if (n) CUDA_TRY(cudaMemcpyAsync(f->d_desc, V.desc, (size_t)n * 32, cudaMemcpyDeviceToDevice, f->stream));
+  CUDA_TRY(cudaMemsetAsync(f->d_occ, 0, (size_t)std::max(n, 1), f->stream));
   if (n) MATCH_LAUNCH(f, k_kp_to_match, dim3((n + 255) / 256), dim3(256), 0, static_cast<const float*>(V.kps), n, f->d_kp,
                       use_stereo ? V.uR : nullptr, f->d_uR);
   MATCH_LAUNCH(f, k_grid_build, dim3(1), dim3(1024), 0, f->d_kp, n, f->minX, f->minY, f->gw, f->gh, f->d_cellStart, f->d_cellItems);
-  e = cudaGetLastError();
-  if (e == cudaSuccess && n) e = cudaMemcpyAsync(f->hkp.data(), f->d_kp, (size_t)n * sizeof(MatchKp), cudaMemcpyDeviceToHost, f->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(f->stream);
-  if (e != cudaSuccess) return fail(e);
+  CUDA_TRY(cudaGetLastError());
+  if (n) CUDA_TRY(cudaMemcpyAsync(f->hkp.data(), f->d_kp, (size_t)n * sizeof(MatchKp), cudaMemcpyDeviceToHost, f->stream));
+  CUDA_TRY(cudaStreamSynchronize(f->stream));
+  return ORBFE_OK;
+}
+
+int orbfe_frame_from_extractor(orbfe_extractor* ex, int slot, int use_stereo, float min_x, float max_x, float min_y, float max_y,
+                               orbfe_frame** out) {
+  if (!out) return orbfe_fail(ORBFE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  orbfe_frame* f = new (std::nothrow) orbfe_frame();
+  if (!f) return orbfe_fail(ORBFE_ERR_NOMEM, "out of host memory");
+  const int rc = frame_fill_from_slot(f, ex, slot, use_stereo, min_x, max_x, min_y, max_y);
+  if (rc) { orbfe_frame_destroy(f); return rc; }
   *out = f;
   return ORBFE_OK;
+}
+
+// the per-frame form: refresh an existing handle (from orbfe_frame_from_extractor) with the next frame's results
+int orbfe_frame_refresh_from_extractor(orbfe_frame* f, orbfe_extractor* ex, int slot, int use_stereo, float min_x, float max_x,
+                                       float min_y, float max_y) {
+  if (!f) return orbfe_fail(ORBFE_ERR_INVALID, "null frame handle");
+  return frame_fill_from_slot(f, ex, slot, use_stereo, min_x, max_x, min_y, max_y);
 }
 
 int orbfe_frame_num_keypoints(const orbfe_frame* f) { return f ? f->n : 0; }
@@ -744,7 +765,7 @@ static int bow_core(orbfe_frame* f, int n1, const uint8_t* desc1, const float* a
     CUDA_TRY(regrow(&f->d_jchanged, (size_t)nq + 256 + 16));
     f->jCap = nq + 256;
   }
-  if (!f->d_jown) CUDA_TRY(regrow(&f->d_jown, 3 * (size_t)std::max(f->n, 1)));
+  if (!f->d_jown) CUDA_TRY(regrow(&f->d_jown, 3 * (size_t)std::max(std::max(f->n, f->kpCap), 1)));
   // scratch re-use: d_qDesc <- all side-1 descriptors, d_qMinL <- descriptor index, d_qMaxL <- source offset,
   // d_qx/d_qy/d_qValid <- kp1 coordinates / stereo flags (triangulation), d_occ <- valid2
   if (nfi > f->featIdxCap) {

@@ -51,7 +51,7 @@ EXPORTS = [
     "orbfe_search_by_sim3", "orbfe_search_by_bow_keyframes", "orbfe_search_for_triangulation",
     "orbfe_vocabulary_create", "orbfe_vocabulary_load_text", "orbfe_vocabulary_destroy", "orbfe_vocabulary_info",
     "orbfe_bow_transform", "orbfe_undistort_keypoints", "orbfe_is_in_frustum", "orbfe_debug_logf", "orbfe_search_local_points",
-    "orbfe_frame_from_extractor", "orbfe_frame_num_keypoints",
+    "orbfe_frame_from_extractor", "orbfe_frame_refresh_from_extractor", "orbfe_frame_num_keypoints",
 ]
 
 _libs = {}
@@ -107,6 +107,7 @@ def load(path=None, _test_emulation=False):
     L.orbfe_frame_create.argtypes = [i, i, vp, vp, vp, f, f, f, f, i, vp, C.POINTER(vp)]
     L.orbfe_frame_destroy.argtypes = [vp]
     L.orbfe_frame_from_extractor.argtypes = [vp, i, i, f, f, f, f, C.POINTER(vp)]
+    L.orbfe_frame_refresh_from_extractor.argtypes = [vp, vp, i, i, f, f, f, f]
     L.orbfe_frame_num_keypoints.argtypes = [vp]
     L.orbfe_features_in_area.argtypes = [vp, f, f, f, i, i, vp, i, vp]
     L.orbfe_search_for_initialization.argtypes = [vp, vp, vp, vp, i, f, i, vp]
@@ -370,6 +371,12 @@ class Frame:
         _check(self.L, self.L.orbfe_frame_from_extractor(ex.h, int(slot), int(stereo), *self.bounds, C.byref(self.h)))
         self.kps = np.zeros(self.L.orbfe_frame_num_keypoints(self.h), KP_DTYPE)
         self.desc, self.ur, self.scale = None, None, ex.GetScaleFactors()
+        return self
+
+    def refresh_from_extractor(self, ex, slot=0, stereo=False):
+        """the next frame's results into the same handle (orbfe_frame_refresh_from_extractor): nothing is allocated in steady state"""
+        _check(self.L, self.L.orbfe_frame_refresh_from_extractor(self.h, ex.h, int(slot), int(stereo), *self.bounds))
+        self.kps = np.zeros(self.L.orbfe_frame_num_keypoints(self.h), KP_DTYPE)
         return self
 
     def close(self):

