@@ -168,6 +168,7 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
   unsigned short* queue = reinterpret_cast<unsigned short*>(bitsW + (size_t)maxRows * (pitchW / 8 + 1));
   __shared__ int s_qn;
   __shared__ int s_any[ORBFE_FAST_MAXG];
+  __shared__ unsigned s_rowmask[ORBFE_FAST_MAXG][ORBFE_FAST_ROWWORDS];
   __shared__ uint8_t s_colCell[512];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int slot = blockIdx.y;
@@ -202,7 +203,11 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
     }
     for (int c = lane; c < bitsP; c += 32) bitsW[r * bitsP + c] = 0u;
   }
-  if (tid < ORBFE_FAST_MAXG) s_any[tid] = 0;
+  if (tid < ORBFE_FAST_MAXG) {
+    s_any[tid] = 0;
+#pragma unroll
+    for (int k = 0; k < ORBFE_FAST_ROWWORDS; ++k) s_rowmask[tid][k] = 0u;
+  }
   for (int x = tid; x < pitchB && x < 512; x += ORBFE_FAST_THREADS)
     s_colCell[x] = (uint8_t)((x >= ix0 && x < ix1) ? (x - ix0) / L.wCell : 0xff);
   const uint8_t* tileB = reinterpret_cast<const uint8_t*>(tileW);
@@ -292,66 +297,38 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
       if (hasR) keep = keep && s > c[1] && s > c[-pitchB + 1] && s > c[pitchB + 1];
       if (keep) {
         atomicOr(&bitsW[y * bitsP + (x >> 5)], 1u << (x & 31));
+        atomicOr(&s_rowmask[jl][y >> 5], 1u << (y & 31));
         s_any[jl] = 1;
       }
     }
     __syncthreads();
   }
-  // ---- 4. ordered emission (the order cv::FAST returns: row-major inside the cell) without walking rows serially:
-  //   a. survivors per (cell, tile row) from the bit plane (a cell spans at most a few 32-bit words of a row);
-  //   b. one warp per cell turns them into an exclusive prefix over the rows (= rank of the row's first survivor);
-  //   c. one thread per word of the bit plane emits its survivors at rank = row prefix + survivors of the same cell
-  //      to the left in the row.
-  unsigned short* rowcnt = queue;  // [cell][tile row]; the queue is dead now and holds at least nj * rows entries
-  for (int e = tid; e < nj * rows; e += ORBFE_FAST_THREADS) {
-    const int jl = e / rows, y = e - jl * rows;
-    const int cx0 = ix0 + jl * L.wCell, cx1 = min(cx0 + L.wCell, ix1);
-    int c = 0;
-    if (cx1 > cx0)
-      for (int w = cx0 >> 5; w <= (cx1 - 1) >> 5; ++w) {
-        unsigned b = bitsW[y * bitsP + w];
-        if (w == (cx0 >> 5)) b &= 0xffffffffu << (cx0 & 31);
-        if (w == ((cx1 - 1) >> 5)) b &= 0xffffffffu >> (31 - ((cx1 - 1) & 31));
-        c += __popc(b);
-      }
-    rowcnt[jl * rows + y] = (unsigned short)c;
-  }
-  __syncthreads();
+  // ---- 4. ordered emission, one warp per cell, only rows that hold a survivor
   for (int jl = wid; jl < nj; jl += ORBFE_FAST_THREADS / 32) {
-    int running = 0;
-    for (int y0 = 0; y0 < rows; y0 += 32) {
-      const int y = y0 + lane;
-      const int v = y < rows ? (int)rowcnt[jl * rows + y] : 0;
-      int inc = v;
+    const int cx0 = ix0 + jl * L.wCell, cx1 = min(cx0 + L.wCell, ix1);
+    unsigned* out = list + (size_t)jl * L.cellCap;
+    int base = 0;
+    if (cx1 > cx0) {
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
+      for (int k = 0; k < ORBFE_FAST_ROWWORDS; ++k) {
+        unsigned rm = s_rowmask[jl][k];
+        while (rm) {
+          const int y = 32 * k + __ffs((int)rm) - 1;
+          rm &= rm - 1;
+          for (int c0 = cx0; c0 < cx1; c0 += 32) {
+            const int x = c0 + lane;
+            const bool emit = x < cx1 && ((bitsW[y * bitsP + (x >> 5)] >> (x & 31)) & 1u);
+            const unsigned bal = __ballot_sync(0xffffffffu, emit);
+            if (emit) {
+              const int pos = base + __popc(bal & ((1u << lane) - 1u));
+              if (pos < L.cellCap)
+                out[pos] = orbfe_pack(x + gx0 - ORBFE_EDGE - ORBFE_MINB, y + iniY - ORBFE_MINB, scoreB[y * pitchB + x]);
+            }
+            base += __popc(bal);
+          }
+        }
       }
-      if (y < rows) rowcnt[jl * rows + y] = (unsigned short)min(running + inc - v, 0xffff);
-      running += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) cnt[jl] = min(running, L.cellCap);
-  }
-  __syncthreads();
-  for (int e = tid; e < rows * bitsP; e += ORBFE_FAST_THREADS) {
-    const int y = e / bitsP, w = e - y * bitsP;
-    unsigned b = bitsW[e];
-    while (b) {
-      const int bit = __ffs((int)b) - 1;
-      b &= b - 1;
-      const int x = 32 * w + bit;
-      const int jl = s_colCell[x];
-      const int cx0 = ix0 + jl * L.wCell;
-      int pos = rowcnt[jl * rows + y];
-      for (int w2 = cx0 >> 5; w2 <= w; ++w2) {  // survivors of this cell to the left in the row
-        unsigned m = bitsW[y * bitsP + w2];
-        if (w2 == (cx0 >> 5)) m &= 0xffffffffu << (cx0 & 31);
-        if (w2 == w) m &= (1u << bit) - 1u;
-        pos += __popc(m);
-      }
-      if (pos < L.cellCap)
-        list[(size_t)jl * L.cellCap + pos] = orbfe_pack(x + gx0 - ORBFE_EDGE - ORBFE_MINB, y + iniY - ORBFE_MINB, scoreB[y * pitchB + x]);
-    }
+    if (lane == 0) cnt[jl] = min(base, L.cellCap);
   }
 }
