@@ -168,6 +168,7 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
   unsigned short* queue = reinterpret_cast<unsigned short*>(bitsW + (size_t)maxRows * (pitchW / 8 + 1));
   __shared__ int s_qn;
   __shared__ int s_any[ORBFE_FAST_MAXG];
+  __shared__ int s_fall[ORBFE_FAST_MAXG];
   __shared__ unsigned s_rowmask[ORBFE_FAST_MAXG][ORBFE_FAST_ROWWORDS];
   __shared__ uint8_t s_colCell[512];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -217,6 +218,7 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
   for (int round = 0; round < 2; ++round) {
     const int th = round == 0 ? g.iniTh : g.minTh;
     if (tid == 0) s_qn = 0;
+    if (tid < ORBFE_FAST_MAXG) s_fall[tid] = !s_any[tid];  // cells in play this round (snapshot: step 3 updates s_any)
     __syncthreads();
     if (round == 1) {  // block-uniform: does any cell of this CTA need the minThFAST fallback?
       bool need = false;
@@ -263,29 +265,39 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, in
       }
     __syncthreads();
     // ---- 2. exact score on the queue; corner at th <=> score >= th
+    // The queue holds queueCap entries, sized so that 6 CTAs fit an SM rather than for the worst case (A/B: FAST -7 %).  A tile
+    // whose pre-test passes more pixels than that (dense noise at minThFAST) is block-uniformly switched to the dense form of
+    // steps 2 and 3: every pixel of the cells in play is scored and NMS-tested, no queue.  Identical results: the pre-test is
+    // only a necessary condition, a pixel it rejects has score < th.
+    const bool dense = s_qn > queueCap;
     const int qn = min(s_qn, queueCap);
     const int xmask = (1 << xbits) - 1;
-#if !ORBFE_FAST_X2
-    for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
-      const int c0 = queue[e];
-      const int o0 = (c0 >> xbits) * pitchB + (c0 & xmask);
+    const int innerW = ix1 - ix0, nWork = dense ? innerW * (rows - 6) : qn;
+    // work item e -> pixel (x, y) of the tile; false = not in play (dense form, cell already has keypoints)
+    auto item = [&](const int e, int& x, int& y) -> bool {
+      if (!dense) {
+        const int code = queue[e];
+        x = code & xmask;
+        y = code >> xbits;
+        return true;
+      }
+      const int yy = e / innerW;
+      x = ix0 + (e - yy * innerW);
+      y = 3 + yy;
+      return round == 0 || s_fall[s_colCell[x]];
+    };
+    for (int e = tid; e < nWork; e += ORBFE_FAST_THREADS) {
+      int x, y;
+      if (!item(e, x, y)) continue;
+      const int o0 = y * pitchB + x;
       const int s0 = orbfe_fast_score3(tileB + o0, pitchB);
       if (s0 >= th) scoreB[o0] = (uint8_t)s0;
     }
-#else
-    for (int e = 2 * tid; e < qn; e += 2 * ORBFE_FAST_THREADS) {  // two queue entries per lane
-      const int c0 = queue[e], c1 = queue[min(e + 1, qn - 1)];
-      const int o0 = (c0 >> xbits) * pitchB + (c0 & xmask), o1 = (c1 >> xbits) * pitchB + (c1 & xmask);
-      int s0, s1;
-      orbfe_fast_score3_x2(tileB + o0, tileB + o1, pitchB, s0, s1);
-      if (s0 >= th) scoreB[o0] = (uint8_t)s0;
-      if (s1 >= th) scoreB[o1] = (uint8_t)s1;
-    }
-#endif
     __syncthreads();
     // ---- 3. NMS inside the cell; survivors -> bit plane + row masks; keypoint found => no fallback
-    for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
-      const int code = queue[e], x = code & xmask, y = code >> xbits;
+    for (int e = tid; e < nWork; e += ORBFE_FAST_THREADS) {
+      int x, y;
+      if (!item(e, x, y)) continue;
       const uint8_t* c = scoreB + y * pitchB + x;
       const int s = c[0];
       if (s == 0) continue;

@@ -341,6 +341,17 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   ex->fastTilePitch |= 1;                          // odd word pitch: vertically adjacent pixels fall in different banks
   if (ex->fastTilePitch <= ORBFE_FAST_PITCHW) ex->fastTilePitch = ORBFE_FAST_PITCHW;  // compile-time specialisation
   ex->fastMaxInnerH = maxInnerH + 6;              // tile rows
+  {
+    // queue capacity: enough for 6 CTAs of this kernel per SM (227 KB usable, 1 KB reserved per CTA) instead of the worst case
+    // (every pixel); a tile that passes more goes to the kernel's dense form.  ORBFE_TEST_FAST_QUEUE_PCT (tests only) forces a
+    // small queue so that ordinary images exercise that form.
+    const size_t planes = (size_t)(maxInnerH + 6) * (2 * ex->fastTilePitch + ex->fastTilePitch / 8 + 1) * 4 + 16;
+    const size_t target = (227 * 1024 - 6 * 1024) / 6 - 1024;
+    int cap = maxQueue;
+    if (planes + 2 * (size_t)maxQueue > target) cap = (int)std::max<size_t>((target > planes ? (target - planes) / 2 : 0), (size_t)maxQueue / 4);
+    if (const char* e = getenv("ORBFE_TEST_FAST_QUEUE_PCT")) { const int pc = atoi(e); if (pc >= 1 && pc <= 100) cap = std::max(maxQueue * pc / 100, 32); }
+    maxQueue = std::min(maxQueue, cap);
+  }
   ex->fastQueueCap = maxQueue;
   if (ex->fastMaxInnerH > 32 * ORBFE_FAST_ROWWORDS) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too tall");
   ex->fastSmem = (size_t)ex->fastMaxInnerH * (2 * ex->fastTilePitch + ex->fastTilePitch / 8 + 1) * 4 + (size_t)maxQueue * 2 + 16;
