@@ -31,6 +31,20 @@ def test_extract_strided_and_noise(emu):
     P.check_extract(emu, big[5:140, 7:400], nfeatures=1000)  # non-contiguous rows, dense texture
 
 
+@pytest.mark.parametrize("pct", [1, 3, 20])
+def test_fast_dense_form_when_the_candidate_queue_overflows(emu, monkeypatch, pct):
+    """k_fast_cells sizes its candidate queue for occupancy, not for the worst case; a tile whose pre-test passes more pixels is
+    scored and NMS-tested densely.  The test hook shrinks the queue so that ordinary frames (both thresholds, fallback cells
+    beside cells with keypoints) and white noise take that form; results must not change."""
+    monkeypatch.setenv("ORBFE_TEST_FAST_QUEUE_PCT", str(pct))
+    P.check_extract(emu, synth.frame(200, 640, seed=2), nfeatures=500)
+    P.check_extract(emu, synth.frame(seed=5))
+    rng = np.random.default_rng(9)
+    P.check_extract(emu, rng.integers(0, 256, (140, 400), dtype=np.uint8), nfeatures=1000)
+    low = (synth.frame(160, 500, seed=3) // 8 + 100).astype(np.uint8)  # low contrast: most cells go to the minThFAST round
+    P.check_extract(emu, low, nfeatures=600)
+
+
 def test_extract_flat_image_yields_nothing(emu):
     ex = orbfe.ORBextractor(lib=emu)
     kps, desc = ex.Compute(np.full((100, 300), 128, np.uint8))

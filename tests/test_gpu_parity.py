@@ -40,6 +40,19 @@ def test_extract_dense_noise_and_strided(lib):
     P.check_extract(lib, big[10:386, 20:1261])  # white noise: ~65k candidates, non-contiguous rows
 
 
+@pytest.mark.parametrize("pct", [1, 5, 30])
+def test_fast_dense_form_when_the_candidate_queue_overflows(lib, monkeypatch, pct):
+    """Same as the emulation test: the queue-overflow (dense) form of k_fast_cells must give identical keypoints."""
+    monkeypatch.setenv("ORBFE_TEST_FAST_QUEUE_PCT", str(pct))
+    P.check_extract(lib, synth.frame(seed=5))
+    rng = np.random.default_rng(9)
+    P.check_extract(lib, rng.integers(0, 256, (376, 1241), dtype=np.uint8))
+    low = (synth.frame(seed=3) // 8 + 100).astype(np.uint8)
+    P.check_extract(lib, low)
+    left, right = synth.stereo_pair(seed=6)
+    P.check_stereo(lib, left, right)
+
+
 def test_flat_and_empty_images(lib):
     ex = orbfe.ORBextractor(lib=lib)
     kps, desc = ex.Compute(np.full((376, 1241), 90, np.uint8))
