@@ -57,7 +57,9 @@ k_octree(const __grid_constant__ Geom g, const int* __restrict__ cellCnt, const 
   __shared__ int s_i[16];
   const int T = ORBFE_OCT_THREADS;
   const int tid = threadIdx.x;
-  const int level = blockIdx.x, slot = blockIdx.y;
+  // grid = (slots, levels): blocks are dispatched x-first, so the long level-0 trees of every image start first and the
+  // short top-level ones fill the tail of the launch
+  const int level = blockIdx.y, slot = blockIdx.x;
   const LevelGeom& L = g.lv[level];
   const int N = L.N;
 

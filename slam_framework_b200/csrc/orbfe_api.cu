@@ -482,7 +482,7 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
                  ex->d_cellCnt, ex->d_cellList, ex->fastTilePitch, ex->fastMaxInnerH, ex->fastQueueCap);
   }
   if ((rc = stage_event(ex, 2))) return rc;
-  ORBFE_LAUNCH(ex, k_octree, dim3(g.nlevels, n), dim3(ORBFE_OCT_THREADS), ex->octSmem, g, ex->d_cellCnt, ex->d_cellList,
+  ORBFE_LAUNCH(ex, k_octree, dim3(n, g.nlevels), dim3(ORBFE_OCT_THREADS), ex->octSmem, g, ex->d_cellCnt, ex->d_cellList,
                ex->oct, ex->d_lvlKp, ex->d_lvlCnt, ex->d_err, ex->octStageCap);
   if ((rc = stage_event(ex, 3))) return rc;
   ORBFE_LAUNCH(ex, k_blur, dim3((g.totalTiles + ORBFE_BLUR_THREADS / 32 - 1) / (ORBFE_BLUR_THREADS / 32), n),
