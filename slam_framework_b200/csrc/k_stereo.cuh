@@ -121,7 +121,9 @@ k_stereo_search(const __grid_constant__ Geom g, const StereoPair* __restrict__ p
       if (octR < levelL - 1 || octR > levelL + 1) continue;
       if (xR >= minU && xR <= maxU) {
         const int dist = orbfe_hamming256(a0, a1, P.descR + (size_t)iR * 32);
-        if (dist < bestDist) { bestDist = dist; bestIdxR = iR; }
+        // the reference scans the row in ascending iR with a strict '<': among equal distances the LOWEST iR wins; the row
+        // table here is filled in atomic order, so the tie rule has to be applied inside the lane too, not only in the reduction
+        if (dist < bestDist || (dist == bestDist && iR < bestIdxR)) { bestDist = dist; bestIdxR = iR; }
       }
     }
   }

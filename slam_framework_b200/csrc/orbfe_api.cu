@@ -113,7 +113,8 @@ struct orbfe_extractor {
 
 #ifdef ORBFE_EMU
 #define ORBFE_LAUNCH(ex, kernel, grid, block, smem, ...)                                           \
-  do { emu::launch(grid, block, smem, [&]() { kernel(__VA_ARGS__); }); (ex)->launches++; } while (0)
+  do { if (getenv("ORBFE_EMU_TRACE")) fprintf(stderr, "launch %s\n", #kernel);                      \
+       emu::launch(grid, block, smem, [&]() { kernel(__VA_ARGS__); }); (ex)->launches++; } while (0)
 #else
 #define ORBFE_LAUNCH(ex, kernel, grid, block, smem, ...)                                           \
   do { kernel<<<grid, block, smem, (ex)->stream>>>(__VA_ARGS__); (ex)->launches++; } while (0)
@@ -217,8 +218,8 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
         int sb[4], mn = 1 << 30;
         for (int j = 0; j < 4; ++j) {
           int x = std::min(4 * k + j, pw - 1) - ORBFE_EDGE;
+          if (L.w == 1) x = 0;  // cv::borderInterpolate: a 1-px axis reflects onto itself (the loop below would not end)
           while (x < 0 || x >= L.w) x = x < 0 ? -x : 2 * (L.w - 1) - x;  // BORDER_REFLECT_101
-          if (L.w == 1) x = 0;
           sb[j] = ORBFE_EDGE + lx[x].ofs;  // byte of the padded source row
           mn = std::min(mn, sb[j]);
           words[k].cpack[j] = (unsigned)(unsigned short)lx[x].c0 | ((unsigned)(unsigned short)lx[x].c1 << 16);
@@ -241,8 +242,8 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
         const ResizeLut* ly = lut.data() + L.lutYOff;
         for (int py = 0; py < L.h + 2 * ORBFE_EDGE; ++py) {
           int y = py - ORBFE_EDGE;
-          while (y < 0 || y >= L.h) y = y < 0 ? -y : 2 * (L.h - 1) - y;
           if (L.h == 1) y = 0;
+          while (y < 0 || y >= L.h) y = y < 0 ? -y : 2 * (L.h - 1) - y;
           PyrRowLut R;
           R.s0 = ly[y].ofs; R.s1 = std::min(ly[y].ofs + 1, P.h - 1);
           R.b0 = (unsigned)(unsigned short)ly[y].c0 << 16; R.b1 = (unsigned)(unsigned short)ly[y].c1 << 16;

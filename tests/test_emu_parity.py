@@ -93,3 +93,11 @@ def test_extractor_parameter_sweep(emu, nf, params):
     """other pyramids (1 and 12 levels, scale 1.1 / 1.5, exact 2x = OpenCV's INTER_AREA path, > 2x = generic resize kernel),
     thresholds (ini == min: no fallback round) and small quotas, stage by stage"""
     P.check_extract(emu, synth.frame(200, 640, seed=int(params[0] * 10) + params[1]), nfeatures=nf, params=params)
+
+
+def test_fuzz_slice_tie_heavy_content_and_random_parameters(emu):
+    """a bounded slice of tests/fuzz_parity.py: checkerboards, gratings, rectangles, dots, saturated / low-contrast frames,
+    odd sizes and random extractor parameters (extraction stage by stage + ComputeStereoMatches)"""
+    import fuzz_parity
+    for seed in range(24):
+        fuzz_parity.run_case(emu, seed, max_side=300)

