@@ -194,3 +194,13 @@ def test_empty_inputs_everywhere(emu, two_frames):
 def test_frame_from_extractor_device_resident(emu):
     l, r = synth.stereo_pair(188, 620, seed=6)
     assert P.check_frame_from_extractor(emu, l, r, nfeatures=800, seed=51) > 100
+
+
+def test_fuzz_slice_matchers_on_tie_heavy_keypoints():
+    """tests/fuzz_matchers.py (every search routine on keypoints from checkerboards / rectangles / gratings: identical
+    descriptors everywhere, so the tie rules decide) -- seeds 0..5 on the emulated build"""
+    import os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "fuzz_matchers.py"), "emu", "6"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "failures 0" in r.stdout

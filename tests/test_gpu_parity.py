@@ -438,3 +438,12 @@ def test_fuzz_slice_tie_heavy_content_and_random_parameters(lib, chunk):
     import fuzz_parity
     for seed in range(5000 + 30 * chunk, 5000 + 30 * (chunk + 1)):
         fuzz_parity.run_case(lib, seed)
+
+
+def test_fuzz_slice_matchers_on_tie_heavy_keypoints():
+    """tests/fuzz_matchers.py on the GPU build: every search routine on keypoints with identical descriptors everywhere"""
+    import os, subprocess, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "fuzz_matchers.py"), "gpu", "9"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "failures 0" in r.stdout
