@@ -4,7 +4,7 @@ the order-dependent parts of the path -- exact score ties (checkerboards, gratin
 plateaus under NMS, cells that fall back to minThFAST next to cells that do not (sparse dots on flat ground),
 saturated and low-contrast frames, tiny and odd-sized images, random extractor parameters.
 
-    python tests/fuzz_parity.py [--cases N] [--seed S] [--emu | --ref] [--max-side PX]
+    python tests/fuzz_parity.py [--cases N] [--seed S] [--emu | --ref] [--batch] [--max-side PX]
 
 --ref checks the ORACLE on the same cases against the reference's own code (oracle/_ref, built by oracle/Makefile.ref; needs
 /root/reference at build time): the stereo Frame constructor end to end.  Cases whose top pyramid level would be smaller than
@@ -115,6 +115,19 @@ def run_case(lib, seed, max_side=700):
     return c
 
 
+def run_batch_case(lib, seed, max_side=700):
+    """the device-resident batch path (upload / run / run_stereo / download) on 2-5 pairs of one geometry, mixed content"""
+    rng = np.random.default_rng(seed)
+    h, w = int(rng.integers(80, max(81, max_side * 2 // 3))), int(rng.integers(120, max(121, max_side)))
+    pairs = []
+    for _ in range(int(rng.integers(2, 6))):
+        img = np.clip(np.rint(content(KINDS[int(rng.integers(len(KINDS)))], h, w + 40, rng)), 0, 255).astype(np.uint8)
+        d = int(rng.integers(0, 40))
+        pairs.append((np.ascontiguousarray(img[:, 40:]), np.ascontiguousarray(img[:, 40 - d:w + 40 - d])))
+    P.check_batch_stereo(lib, pairs, nfeatures=int(rng.choice([200, 1000, 2000])))
+    return dict(kind="batch", left=pairs[0][0], nfeatures=0, params=())
+
+
 def run_case_ref(seed, max_side=700):
     """oracle vs the reference's own Frame constructor; returns None when the case is skipped"""
     import oracle_lib as O
@@ -151,6 +164,7 @@ def main():
     ap.add_argument("--max-side", type=int, default=700)
     ap.add_argument("--emu", action="store_true")
     ap.add_argument("--ref", action="store_true")
+    ap.add_argument("--batch", action="store_true", help="batch path: several pairs of one geometry per case")
     a = ap.parse_args()
     lib = None
     if a.ref:
@@ -163,7 +177,7 @@ def main():
     bad = skipped = 0
     for s in range(a.seed, a.seed + a.cases):
         try:
-            c = run_case_ref(s, a.max_side) if a.ref else run_case(lib, s, a.max_side)
+            c = run_case_ref(s, a.max_side) if a.ref else run_batch_case(lib, s, a.max_side) if a.batch else run_case(lib, s, a.max_side)
             skipped += c is None
         except AssertionError as e:
             c = make_case(s, a.max_side, landscape=a.ref)
