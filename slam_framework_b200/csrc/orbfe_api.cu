@@ -330,7 +330,10 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   // shared-memory staging of a level's candidate keys (k_octree): as many entries as keep 4 CTAs per SM resident
   ex->octStageCap = 0;
   {
-    const size_t budget = 50 * 1024;
+#ifndef ORBFE_OCT_BUDGET_KB
+#define ORBFE_OCT_BUDGET_KB 50
+#endif
+    const size_t budget = ORBFE_OCT_BUDGET_KB * 1024;
     if (ex->octSmem + 8 * 1024 <= budget) ex->octStageCap = (int)((budget - ex->octSmem) / 8);
     ex->octSmem += (size_t)ex->octStageCap * 8;
   }
