@@ -470,6 +470,7 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
       // the GPU with warps several times over; otherwise short strips, more warps, less latency
       const int strips = (L.pyrWords + 31) / 32, ph = L.h + 2 * ORBFE_EDGE;
       int stripRows = ORBFE_PYR_ROWS;
+      if (const char* e = getenv("ORBFE_TUNE_PYR_ROWS")) { const int v = atoi(e); if (v >= 2 && v <= 64) stripRows = v; }  // tuning only; A/B at 64 pairs: 4 -> 0.274 ms, 6 -> 0.265, 8 -> 0.255, 16 -> 0.254
       while (stripRows > 2 && (long long)strips * ((ph + stripRows - 1) / stripRows) * n < 1LL * 148 * 64) stripRows >>= 1;
       const int tasks = ((L.pyrWords + 31) / 32) * ((L.h + 2 * ORBFE_EDGE + stripRows - 1) / stripRows);
       ORBFE_LAUNCH(ex, k_pyramid_resize, dim3((tasks + ORBFE_PYR_THREADS / 32 - 1) / (ORBFE_PYR_THREADS / 32), n),
