@@ -101,11 +101,16 @@ __device__ __forceinline__ float orbfe_sincosf(float y, int is_cos) {
 //            of keypoint k;
 //   phase 2  lane-parallel: fastAtan2 + glibc sincosf (the fp64 polynomial runs once per
 //            keypoint instead of 32x redundantly) + the cv::KeyPoint record;
-//   phase 3  per keypoint, lane i builds descriptor byte i; the lane's 16 pattern points live in
-//            registers for all 32 keypoints (per-lane constant-bank reads are serialised by the
-//            address-divergence unit, so they are paid once per warp, not once per keypoint).
+//   phase 3  per keypoint, lane i builds descriptor byte i; the lane's 16 pattern point pairs are converted to float
+//            once per CTA and kept in shared memory as 8 float4 per lane (per-lane constant-bank reads would be
+//            serialised by the address-divergence unit; 32 registers per lane cost occupancy and load slots).
+#ifndef ORBFE_DESC_PATSMEM
+#define ORBFE_DESC_PATSMEM 1  // pattern points as floats in shared memory instead of 32 registers per lane
+#endif
 #ifndef ORBFE_DESC_MINB
-#define ORBFE_DESC_MINB 12  // caps registers at 85: 24 warps/SM (A/B measured, see profiles)
+// A/B on B200, 64 pairs (pattern in registers -> in smem): MINB 12 0.269 -> 0.249 ms; smem + MINB 14 (72 registers, 28 warps/SM)
+// 0.247; MINB 16 (64 registers, spills) 0.265; MINB 20 0.324; 128-thread CTAs 0.259; deeper keypoint unrolling (3, 4) 0.29-0.31
+#define ORBFE_DESC_MINB 14
 #endif
 __global__ void __launch_bounds__(ORBFE_DESC_THREADS, ORBFE_DESC_MINB)
 k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
@@ -114,6 +119,20 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
   const int slot = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * (ORBFE_DESC_THREADS / 32) + (threadIdx.x >> 5);
+#if ORBFE_DESC_PATSMEM
+  // the pattern as floats in shared memory, one float4 (x0, y0, x1, y1) per comparison and lane: 32 registers less per thread
+  __shared__ float4 s_pat[8][32];
+  if (threadIdx.x < 32) {
+    const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(d_orb_pattern) + 2 * lane);
+    const uint4 p1 = __ldg(reinterpret_cast<const uint4*>(d_orb_pattern) + 2 * lane + 1);
+    const unsigned w[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      s_pat[t][lane] = make_float4((float)(signed char)(w[t] & 0xffu), (float)(signed char)((w[t] >> 8) & 0xffu),
+                                   (float)(signed char)((w[t] >> 16) & 0xffu), (float)(signed char)((w[t] >> 24) & 0xffu));
+  }
+  __syncthreads();
+#endif
   const int* cnt = lvlCnt + (size_t)slot * g.nlevels;
   // kpw keypoints per warp: 32 for large batches (the lane-parallel phase is fully used), fewer when
   // only a frame or two is in flight so that the keypoints spread over more warps (latency)
@@ -201,6 +220,11 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     kps[(size_t)slot * g.totalOut + pos] = kp;
   }
   // ---- E7: rotated BRIEF on the blurred level; lane i -> descriptor byte i
+#if ORBFE_DESC_PATSMEM
+#define ORBFE_DESC_PAT(t) const float4 q_ = s_pat[t][lane]; const float qx_[2] = {q_.x, q_.z}, qy_[2] = {q_.y, q_.w};
+#define ORBFE_DESC_PX(t, h) qx_[h]
+#define ORBFE_DESC_PY(t, h) qy_[h]
+#else
   float px[16], py[16];
   {
     const uint4 p0 = __ldg(reinterpret_cast<const uint4*>(d_orb_pattern) + 2 * lane);
@@ -212,6 +236,10 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
       py[t] = (float)(signed char)((w[t >> 1] >> (16 * (t & 1) + 8)) & 0xffu);
     }
   }
+#define ORBFE_DESC_PAT(t)
+#define ORBFE_DESC_PX(t, h) px[2 * (t) + (h)]
+#define ORBFE_DESC_PY(t, h) py[2 * (t) + (h)]
+#endif
   __shared__ unsigned s_patch[ORBFE_DESC_THREADS / 32][2][37 * ORBFE_DESC_PW];
   const uint8_t* blurSlot = blur + (size_t)slot * g.blurStride;
   uint8_t* dOut = desc + ((size_t)slot * g.totalOut + base) * 32;
@@ -244,9 +272,10 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         int tv[2];
+        ORBFE_DESC_PAT(t)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const float x = px[2 * t + h], y = py[2 * t + h];
+          const float x = ORBFE_DESC_PX(t, h), y = ORBFE_DESC_PY(t, h);
           const int iy = __float2int_rn(__fadd_rn(__fmul_rn(x, sb), __fmul_rn(y, ca)));
           const int ix = __float2int_rn(__fsub_rn(__fmul_rn(x, ca), __fmul_rn(y, sb)));
           tv[h] = (int)centre[iy * (4 * ORBFE_DESC_PW) + ix];
@@ -257,9 +286,10 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         int tv[2];
+        ORBFE_DESC_PAT(t)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const float x = px[2 * t + h], y = py[2 * t + h];
+          const float x = ORBFE_DESC_PX(t, h), y = ORBFE_DESC_PY(t, h);
           const int iy = __float2int_rn(__fadd_rn(__fmul_rn(x, sb), __fmul_rn(y, ca)));
           const int ix = __float2int_rn(__fsub_rn(__fmul_rn(x, ca), __fmul_rn(y, sb)));
           // the reference samples a CONTINUOUS w x h clone (step == w): a column overshoot lands in

@@ -48,12 +48,14 @@ struct int4 { int x, y, z, w; };
 struct short4 { short x, y, z, w; };
 struct uchar4 { unsigned char x, y, z, w; };
 struct float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
 static inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
 static inline int2 make_int2(int a, int b) { return int2{a, b}; }
 static inline int4 make_int4(int a, int b, int c, int d) { return int4{a, b, c, d}; }
 static inline short4 make_short4(short a, short b, short c, short d) { return short4{a, b, c, d}; }
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 
 namespace emu {
 
