@@ -12,7 +12,8 @@
 // One warp = a strip of 30 output words (120 px) x ORBFE_BLUR_ROWS rows.  Lanes load one aligned
 // word per input row (coalesced 128 B), fetch the two following words with shuffles, form the 7-tap
 // horizontal sums with byte funnel-shifts + IDP.4A (2 dp4a per pixel), keep the last 7 rows of sums
-// in registers and emit one 4-pixel word per row: no shared memory, every byte read once per strip.
+// in registers (paired row-wise, so that the column sum is 3 IDP.2A + 1 IMAD) and emit one 4-pixel word per row: no shared
+// memory, every byte read once per strip.
 #pragma once
 #include "orbfe_common.cuh"
 
@@ -54,11 +55,16 @@ k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t*
   const bool writer = lane < ORBFE_BLUR_WORDS && 4 * k < L.w;
   const unsigned KA = 0x38302212u;  // taps 18,34,48,56 (bytes 0..3)
   const unsigned KB = 0x00122230u;  // taps 48,34,18,0
-  unsigned H[7][4];
+  // Vertical pass: consecutive rows' horizontal sums (<= 65280, 16 bits) are paired in one register, P[slot of row a] =
+  // H[a] | H[a+1] << 16, so that the 7-tap column sum is 3 IDP.2A + 1 IMAD instead of 3 adds + 4 IMADs per pixel.
+  const unsigned W01 = 18u | (34u << 8), W23 = 48u | (56u << 8), W45 = 48u | (34u << 8);
+  unsigned P[7][4], Hp[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) Hp[j] = 0u;
 #pragma unroll
   for (int s = 0; s < 7; ++s)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) H[s][j] = 0u;
+    for (int j = 0; j < 4; ++j) P[s][j] = 0u;
   const int total = nrows + 6;
   for (int r0 = 0; r0 < total; r0 += 7) {
     unsigned wl[7];  // the 7 row loads of this group are issued back to back (latency overlap)
@@ -72,17 +78,20 @@ k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t*
         const unsigned w1 = __shfl_down_sync(0xffffffffu, w0, 1);
         const unsigned w2 = __shfl_down_sync(0xffffffffu, w0, 2);
         // horizontal sums of the 4 pixels of this word: bytes j..j+6 of (w0,w1,w2)
-        H[s][0] = orbfe_dp4a_u8(w1, KB, orbfe_dp4a_u8(w0, KA, 0u));
-        H[s][1] = orbfe_dp4a_u8(__funnelshift_r(w1, w2, 8), KB, orbfe_dp4a_u8(__funnelshift_r(w0, w1, 8), KA, 0u));
-        H[s][2] = orbfe_dp4a_u8(__funnelshift_r(w1, w2, 16), KB, orbfe_dp4a_u8(__funnelshift_r(w0, w1, 16), KA, 0u));
-        H[s][3] = orbfe_dp4a_u8(__funnelshift_r(w1, w2, 24), KB, orbfe_dp4a_u8(__funnelshift_r(w0, w1, 24), KA, 0u));
+        unsigned Hn[4];
+        Hn[0] = orbfe_dp4a_u8(w1, KB, orbfe_dp4a_u8(w0, KA, 0u));
+        Hn[1] = orbfe_dp4a_u8(__funnelshift_r(w1, w2, 8), KB, orbfe_dp4a_u8(__funnelshift_r(w0, w1, 8), KA, 0u));
+        Hn[2] = orbfe_dp4a_u8(__funnelshift_r(w1, w2, 16), KB, orbfe_dp4a_u8(__funnelshift_r(w0, w1, 16), KA, 0u));
+        Hn[3] = orbfe_dp4a_u8(__funnelshift_r(w1, w2, 24), KB, orbfe_dp4a_u8(__funnelshift_r(w0, w1, 24), KA, 0u));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { P[(s + 6) % 7][j] = Hn[j] * 65536u + Hp[j]; Hp[j] = Hn[j]; }  // pair (r-1, r)
         if (r >= 6 && writer) {
-          // window rows r-6..r live in H[(s+1)%7] (oldest) .. H[s] (newest)
+          // pairs (r-6,r-5), (r-4,r-3), (r-2,r-1) live in slots s+1, s+3, s+5 (mod 7); row r itself is Hn
           unsigned acc[4];  // V + 32768 < 2^24: the rounded result is byte 2 of the accumulator
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            acc[j] = 56u * H[(s + 4) % 7][j] + 32768u + 18u * (H[(s + 1) % 7][j] + H[s][j]) +
-                     34u * (H[(s + 2) % 7][j] + H[(s + 6) % 7][j]) + 48u * (H[(s + 3) % 7][j] + H[(s + 5) % 7][j]);
+            acc[j] = __dp2a_lo(P[(s + 1) % 7][j], W01, __dp2a_lo(P[(s + 3) % 7][j], W23,
+                     __dp2a_lo(P[(s + 5) % 7][j], W45, 18u * Hn[j] + 32768u)));
           const unsigned out = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
           // bpitch is a multiple of 16: the word store is aligned; bytes past w land in row padding
           *reinterpret_cast<unsigned*>(dst + (size_t)(r - 6) * L.bpitch) = out;
