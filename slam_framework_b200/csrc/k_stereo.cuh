@@ -110,6 +110,7 @@ k_stereo_search(const __grid_constant__ Geom g, const StereoPair* __restrict__ p
   const float minU = __fsub_rn(uL, maxD), maxU = __fsub_rn(uL, minD);
   int bestDist = 100;  // OrbMatcher::TH_HIGH
   int bestIdxR = 0x7fffffff;
+  unsigned bestXbits = 0u;  // x of the best right keypoint travels with the argmin: no dependent kpR load after the search
   if (row >= 0 && row < nRows && !(maxU < 0)) {
     const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(P.descL + (size_t)iL * 32));
     const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(P.descL + (size_t)iL * 32) + 1);
@@ -123,7 +124,7 @@ k_stereo_search(const __grid_constant__ Geom g, const StereoPair* __restrict__ p
         const int dist = orbfe_hamming256(a0, a1, P.descR + (size_t)iR * 32);
         // the reference scans the row in ascending iR with a strict '<': among equal distances the LOWEST iR wins; the row
         // table here is filled in atomic order, so the tie rule has to be applied inside the lane too, not only in the reduction
-        if (dist < bestDist || (dist == bestDist && iR < bestIdxR)) { bestDist = dist; bestIdxR = iR; }
+        if (dist < bestDist || (dist == bestDist && iR < bestIdxR)) { bestDist = dist; bestIdxR = iR; bestXbits = it.y; }
       }
     }
   }
@@ -131,11 +132,12 @@ k_stereo_search(const __grid_constant__ Geom g, const StereoPair* __restrict__ p
   for (int o = 16; o > 0; o >>= 1) {
     const int od = __shfl_xor_sync(0xffffffffu, bestDist, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bestIdxR, o);
-    if (od < bestDist || (od == bestDist && oi < bestIdxR)) { bestDist = od; bestIdxR = oi; }
+    const unsigned ox = __shfl_xor_sync(0xffffffffu, bestXbits, o);
+    if (od < bestDist || (od == bestDist && oi < bestIdxR)) { bestDist = od; bestIdxR = oi; bestXbits = ox; }
   }
   const int thOrbDist = (100 + 50) / 2;
   if (bestDist < thOrbDist) {  // warp-uniform
-    const float uR0 = P.kpR[bestIdxR].x;
+    const float uR0 = __uint_as_float(bestXbits);  // == P.kpR[bestIdxR].x (k_stereo_rows copied it into the row table)
     const LevelGeom& L = g.lv[levelL];
     const float scaleFactor = __fdiv_rn(1.0f, L.scale);  // mvInvScaleFactor (orb_extractor.cpp:371)
     const float scaleduL = roundf(__fmul_rn(kpL.x, scaleFactor));
