@@ -1,109 +1,63 @@
 // k_fast.cuh -- E2+E3: grid FAST-9/16 with adaptive threshold, per-cell NMS and ordered select.
 // Follows the grid loop of ComputeKeyPointsOctTree (orb_extractor.cpp:706-770) and
 // cv::FAST(cell, kps, th, true):
-//   * one CTA per 30-px grid cell; the cell sub-image [iniX,maxX)x[iniY,maxY) is staged in
-//     shared memory; FAST runs on its 3-px inset;
-//   * the corner score (max threshold at which the pixel is still a corner) is computed once at
-//     minThFAST; NMS is strict (>) over the 8 neighbours INSIDE the cell (outside counts 0);
-//   * survivors with score >= iniThFAST are emitted; if there are none, survivors with
-//     score >= minThFAST are emitted instead (the post-NMS emptiness fallback, :753-757);
-//   * emission order is row-major inside the cell (warp ballots + popc prefix), which is the
-//     order cv::FAST returns; cells are consumed in row-major cell order by the quad-tree kernel.
+//   * the corner score (max threshold at which the pixel is still a corner) does not depend on the threshold
+//     passed in; cv::FAST at threshold t == "score >= t" on that score map;
+//   * NMS is strict (>) over the 8 neighbours INSIDE the cell's detection window (outside counts 0);
+//   * survivors with score >= iniThFAST are emitted; a cell with none re-runs at minThFAST (the post-NMS
+//     emptiness fallback, :753-757);
+//   * emission order is row-major inside the cell (the order cv::FAST returns); cells are consumed in row-major
+//     cell order by the quad-tree kernel.
+//
+// One CTA = up to L.fG consecutive grid cells of one cell row of one level of one image.  The cells' detection
+// windows tile the level's inner region exactly (origin (16,16), stride wCell x hCell), so the CTA stages ONE
+// pixel tile, (hCell+6) rows x 256 bytes, with a single TMA box copy (orbfe_tma.cuh) and runs up to two rounds
+// (iniThFAST on every cell, minThFAST on the cells still empty).  Every phase of a round is driven by a
+// compacted work list, so that all 32 lanes of a warp are busy in the expensive steps:
+//   1. 8-point pre-test, 4 pixels per instruction (VABSDIFF4 + carry trick), ONCE per tile for BOTH thresholds (the
+//      absolute differences are shared): a 9-arc of the 16-ring contains at least one point of every antipodal pair,
+//      so a pixel is a corner only if, in each of the pairs (0,8), (4,12), (2,10), (6,14), a ring point differs from
+//      it by more than t.  Branch-free: the flags of up to 16 words accumulate in two registers per thread and
+//      threshold;
+//   2. queue build in two balanced steps: per word item a warp ballot appends the flagged WORDS to a word queue
+//      (round 1: only the bits of cells that found nothing in round 0); then one lane per queued word expands it,
+//      after a warp scan, into the pixel queue Q1;
+//   3. exact corner score (max_arc min_9 of +-(ring - v), packed u16x2 min/max networks) on Q1; corners
+//      (score >= t) go to the score plane and, by warp ballot, to the corner queue Q2;
+//   4. strict 3x3 NMS restricted to the cell on Q2 -> per-cell survivor lists;
+//   5. after both rounds, one warp per cell: a survivor's output slot is the number of survivors of its cell that
+//      precede it in row-major order (counted against the cell's short list): ordered emission without a serial walk.
+// A tile whose pre-test passes more pixels than Q1 holds (dense noise at minThFAST) switches, block-uniformly,
+// to the dense form of steps 3 and 4 (every pixel of the cells in play): identical results, the pre-test is
+// only a necessary condition.
 #pragma once
 #include "orbfe_common.cuh"
+#include "orbfe_tma.cuh"
 
 #define ORBFE_FAST_THREADS 256
-#define ORBFE_FAST_MAXG 16
-#ifndef ORBFE_FAST_FGCAP
-#define ORBFE_FAST_FGCAP 8   // upper bound of cells per CTA
+#define ORBFE_FAST_TP 256       // tile pitch in bytes == TMA box width
+#define ORBFE_FAST_TPW 64       // ... in words
+#define ORBFE_FAST_MAXG 8       // cells per CTA (upper bound)
+// A TMA box must start on a 16-byte boundary of the plane row (measured on B200: any other start coordinate faults with
+// "illegal instruction"), so the tile starts at the 16-byte boundary at or below the column 1 px left of the detection
+// window: window column c is tile column c + 1 + off, off in [0, 15], and the first inner column is 4 + off.
+#define ORBFE_FAST_MAXW 234     // fG * wCell <= 234  (16 + fG*wCell + 6 <= 256)
+#define ORBFE_FAST_MAXROWS 72   // tile rows (hCell + 6 <= 65)
+#ifndef ORBFE_FAST_MINB
+#define ORBFE_FAST_MINB 5
 #endif
-#ifndef ORBFE_FAST_X2
-#define ORBFE_FAST_X2 0  // 1: two queue entries per lane on packed u16x2 networks (fewer instructions, but 64 regs => 4 CTAs/SM: slower)
-#endif
-#ifndef ORBFE_FAST_PITCHW
-#define ORBFE_FAST_PITCHW 61  // compile-time tile pitch (words) of the common geometry; odd => no column bank conflicts
-#endif
 
-// 16-bit mask has a circular run of >= 9 set bits
-__device__ __forceinline__ bool orbfe_has_run9(unsigned m) {
-  unsigned t = m | (m << 16);
-  unsigned a = t & (t >> 1);   // runs of 2
-  a &= a >> 2;                 // runs of 4
-  a &= a >> 4;                 // runs of 8
-  a &= t >> 8;                 // runs of 9
-  return (a & 0xffffu) != 0;
+// per-CTA work descriptor (host-built): level | cell row << 4 | first cell << 16
+__host__ __device__ __forceinline__ unsigned orbfe_fast_task(int level, int i, int j0) {
+  return (unsigned)level | ((unsigned)i << 4) | ((unsigned)j0 << 16);
 }
-
-// max over the 16 circular 9-arcs of the minimum of d[] over the arc
-__device__ __forceinline__ int orbfe_arc_maxmin(const int (&d)[16]) {
-  int m2[16], m4[16], best = -100000;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) m2[i] = min(d[i], d[(i + 1) & 15]);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) m4[i] = min(m2[i], m2[(i + 2) & 15]);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int m8 = min(m4[i], m4[(i + 4) & 15]);
-    best = max(best, min(m8, d[(i + 8) & 15]));
-  }
-  return best;
-}
-
-// FAST corner score of the pixel at p (shared-memory tile, pitch tp); 0 if not a corner at th.
-__device__ __forceinline__ int orbfe_fast_score(const uint8_t* p, int tp, int th) {
-  const int v = p[0];
-  int r[16];
-  r[0] = p[3 * tp];      r[1] = p[3 * tp + 1];  r[2] = p[2 * tp + 2];   r[3] = p[tp + 3];
-  r[4] = p[3];           r[5] = p[-tp + 3];     r[6] = p[-2 * tp + 2];  r[7] = p[-3 * tp + 1];
-  r[8] = p[-3 * tp];     r[9] = p[-3 * tp - 1]; r[10] = p[-2 * tp - 2]; r[11] = p[-tp - 3];
-  r[12] = p[-3];         r[13] = p[tp - 3];     r[14] = p[2 * tp - 2];  r[15] = p[3 * tp - 1];
-  unsigned bm = 0, dm = 0;
-  const int hi = v + th, lo = v - th;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    bm |= (unsigned)(r[k] > hi) << k;
-    dm |= (unsigned)(r[k] < lo) << k;
-  }
-  const bool bright = orbfe_has_run9(bm), dark = orbfe_has_run9(dm);
-  if (!bright && !dark) return 0;
-  int d[16], s = 0;
-  if (bright) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = r[k] - v;
-    s = orbfe_arc_maxmin(d);
-  }
-  if (dark) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) d[k] = v - r[k];
-    s = max(s, orbfe_arc_maxmin(d));
-  }
-  return s - 1;  // >= th by construction
-}
-
-// ---- fused band-segment kernel ----------------------------------------------------------------------
-// One CTA = up to L.fG consecutive grid cells of one cell row of one level of one image.  The cells'
-// detection windows tile the level's inner region exactly (origin (19,19), stride wCell x hCell, SURVEY
-// A.2), so the CTA stages ONE pixel tile (hCell+6 rows x fG*wCell+6 columns, word-aligned, coalesced
-// 4-byte loads) and runs up to two rounds, first at iniThFAST over the whole tile, then at minThFAST
-// over the cells that produced no keypoint (the post-NMS emptiness fallback of :753-757; cv::FAST at
-// threshold t == "score >= t" on the threshold-independent score map):
-//   1. compass pre-test, 4 pixels per instruction (VABSDIFF4 + carry trick): a 9-arc of the 16-ring
-//      always contains two ADJACENT compass points (ring 0/4/8/12), so a pixel without two adjacent
-//      compass points differing from it by more than t cannot be a corner; survivors are compacted
-//      into a shared-memory queue;
-//   2. exact corner score (max_arc min_9 of +-(ring - v), 3-input min/max networks) on the queue only,
-//      all lanes busy; corner at t <=> score >= t;
-//   3. strict 3x3 NMS restricted to the cell (neighbours outside the cell's window count 0);
-//   4. one warp per cell: row-major ordered emission with warp ballots (the order cv::FAST returns),
-//      visiting only rows that hold a survivor.
-#define ORBFE_FAST_ROWWORDS 3  // survivor row masks: up to 96 tile rows
 
 // exact FAST-9/16 corner score of the pixel at p (shared-memory tile, byte pitch tp):
 //   score + 1 = max( max_arc min_9 (ring - v),  max_arc min_9 (v - ring) ).
-// Both halves run through ONE min3/min3/max3 network on packed u16x2 lanes (VIMNMX3.U16x2): the low half
-// carries (ring - v) + 256, the high half (v - ring) + 256, both in [1, 511]; the packing is one IMAD per
-// ring pixel:  (d + 256) | (256 - d) << 16  ==  C + ring * (1 - 65536)  with C folding the centre value.
-__device__ __forceinline__ int orbfe_fast_score3(const uint8_t* p, int tp) {
+// Both halves run through ONE min/max network on packed u16x2 lanes (VIMNMX3.U16x2): the low half carries
+// (ring - v) + 256, the high half (v - ring) + 256, both in [1, 511]; the packing is one IMAD per ring pixel:
+//   (d + 256) | (256 - d) << 16  ==  C + ring * (1 - 65536)  with C folding the centre value.
+__device__ __forceinline__ int orbfe_fast_score3(const uint8_t* p, const int tp) {
   const unsigned K = 1u - 65536u;                                  // d -> d in the low half, -d in the high half
   const unsigned C = (256u | (256u << 16)) - (unsigned)p[0] * K;   // centre folded in
   unsigned d[16];
@@ -116,7 +70,7 @@ __device__ __forceinline__ int orbfe_fast_score3(const uint8_t* p, int tp) {
   // The 16 arcs pair up: with A_k = min d[k+1..k+8] (k even), the arcs starting at k and at k+1 are min(d[k], A_k) and
   // min(A_k, d[k+9]), and the larger of the two is min(A_k, max(d[k], d[k+9])).  A_k is the min of four adjacent pairs
   // p[j] = min(d[2j+1], d[2j+2]):  8 (pairs) + 8 (three pairs) + 8 (max of the two ends) + 8 (min3 of the rest) + 4 (max tree)
-  // = 36 two-lane min/max instructions instead of the 41 of the min3 / min3 / max3 network.
+  // = 36 two-lane min/max instructions.
   unsigned pr[8], s3[8], u[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) pr[j] = __vminu2(d[2 * j + 1], d[(2 * j + 2) & 15]);
@@ -131,221 +85,310 @@ __device__ __forceinline__ int orbfe_fast_score3(const uint8_t* p, int tp) {
   return (int)max(best & 0xffffu, best >> 16) - 257;
 }
 
-// two KITTI-shaped entries of the queue per lane: the same min/max networks on packed u16x2 lanes
-// (VIMNMX3.U16x2); differences are biased by +256 so that they stay positive 16-bit values
-__device__ __forceinline__ void orbfe_fast_score3_x2(const uint8_t* p0, const uint8_t* p1, int tp, int& s0, int& s1) {
-  const unsigned bias = (256u - p0[0]) | ((256u - p1[0]) << 16);
-  unsigned d[16];
-#define ORBFE_D(k, off) d[k] = ((unsigned)p0[off] | ((unsigned)p1[off] << 16)) + bias
-  ORBFE_D(0, 3 * tp);       ORBFE_D(1, 3 * tp + 1);   ORBFE_D(2, 2 * tp + 2);   ORBFE_D(3, tp + 3);
-  ORBFE_D(4, 3);            ORBFE_D(5, -tp + 3);      ORBFE_D(6, -2 * tp + 2);  ORBFE_D(7, -3 * tp + 1);
-  ORBFE_D(8, -3 * tp);      ORBFE_D(9, -3 * tp - 1);  ORBFE_D(10, -2 * tp - 2); ORBFE_D(11, -tp - 3);
-  ORBFE_D(12, -3);          ORBFE_D(13, tp - 3);      ORBFE_D(14, 2 * tp - 2);  ORBFE_D(15, 3 * tp - 1);
-#undef ORBFE_D
-  unsigned lo3[16], hi3[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    lo3[i] = __vimin3_u16x2(d[i], d[(i + 1) & 15], d[(i + 2) & 15]);
-    hi3[i] = __vimax3_u16x2(d[i], d[(i + 1) & 15], d[(i + 2) & 15]);
-  }
-  unsigned bright = 0u, dark = 0xffffffffu;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    bright = __vmaxu2(bright, __vimin3_u16x2(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]));
-    dark = __vminu2(dark, __vimax3_u16x2(hi3[i], hi3[(i + 3) & 15], hi3[(i + 6) & 15]));
-  }
-  s0 = max((int)(bright & 0xffffu) - 256, 256 - (int)(dark & 0xffffu)) - 1;
-  s1 = max((int)(bright >> 16) - 256, 256 - (int)(dark >> 16)) - 1;
+// bytes of tile word wx whose column lies in [c0, c1) -> 0x80 per byte
+__device__ __forceinline__ unsigned orbfe_fast_colmask(const int wx, const int c0, const int c1) {
+  const int lo = max(c0 - 4 * wx, 0), hi = min(c1 - 4 * wx, 4);
+  if (hi <= lo) return 0u;
+  return (0x80808080u >> (8 * (4 - hi))) & (0x80808080u << (8 * lo));
 }
 
-// PW = compile-time tile pitch in words (ring offsets become immediates); PW = 0: run-time pitch
-// (cells wider than the fixed tile)
-template <int PW>
-__global__ void __launch_bounds__(ORBFE_FAST_THREADS)
-k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, int* __restrict__ cellCnt,
-             unsigned* __restrict__ cellList, const int pitchWArg, const int maxRows, const int queueCap) {
-  const int pitchW = PW ? PW : pitchWArg;
-  const int xbits = 9;  // queue code = y << xbits | x
+// warp-aggregated reservation of `cnt` queue slots per lane: returns this lane's first slot
+__device__ __forceinline__ int orbfe_fast_reserve(const int cnt, int* counter, const int lane) {
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  int base = 0;
+  if (lane == 31 && inc > 0) base = atomicAdd(counter, inc);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  return base + inc - cnt;
+}
+
+struct FastSmemLayout {
+  int scoreOff, q1Off, q2Off, listOff, total;  // bytes from the start of dynamic shared memory (tile at 0)
+};
+// Q2 (corners, written by the score step) shares its storage with the word queue (read by the expansion step before):
+// q2Cap >= the number of inner words of a tile
+__host__ __device__ __forceinline__ FastSmemLayout orbfe_fast_layout(const int maxRows, const int q1Cap, const int q2Cap, const int listCap) {
+  FastSmemLayout s;
+  s.scoreOff = maxRows * ORBFE_FAST_TP + 16;            // + 16: the pre-test of the last word reads one word past the tile
+  s.q1Off = s.scoreOff + maxRows * ORBFE_FAST_TP;
+  s.q2Off = s.q1Off + ((q1Cap * 2 + 15) & ~15);
+  s.listOff = s.q2Off + ((q2Cap * 2 + 15) & ~15);
+  s.total = s.listOff + ((ORBFE_FAST_MAXG * listCap * 2 + 15) & ~15);
+  return s;
+}
+
+// step 2a: the flag registers of a thread (acc0: items 0..7, acc1: items 8..15; bit 8b + 7 - (k & 7) = byte b of item k;
+// item k = 2 * it + j is the word (row 3 + wid + 8 it, column wLo + lane + 32 j)) -> word queue entries
+// (y - 3) << 10 | wx << 4 | flags, appended per item by warp ballot
+__device__ __forceinline__ void orbfe_fast_push_words(const unsigned acc0, const unsigned acc1, const int nItems, unsigned short* wq,
+                                                      int* counter, const unsigned baseWord, const int lane) {
+  for (int k = 0; k < nItems; ++k) {
+    const unsigned f = ((k < 8 ? acc0 : acc1) >> (7 - (k & 7))) & 0x01010101u;
+    const unsigned bal = __ballot_sync(0xffffffffu, f != 0u);
+    if (bal == 0u) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (f) {
+      const unsigned nib = (f * 0x00204081u) >> 21;  // bits 0, 8, 16, 24 -> 0..3
+      wq[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(baseWord + ((k >> 1) << 13) + ((k & 1) << 9) + (nib & 15u));
+    }
+  }
+}
+
+// step 2b: word queue -> pixel queue Q1 (codes y << 8 | x), one lane per queued word
+__device__ __forceinline__ void orbfe_fast_expand(const unsigned short* wq, const int nWords, unsigned short* q1, const int q1Cap,
+                                                  int* counter, const int tid, const int lane) {
+  for (int e0 = tid - lane; e0 < nWords; e0 += ORBFE_FAST_THREADS) {
+    const int e = e0 + lane;
+    const unsigned w = e < nWords ? wq[e] : 0u;
+    const unsigned nib = w & 15u;
+    int pos = orbfe_fast_reserve(__popc(nib), counter, lane);
+    const unsigned code = (((w >> 10) + 3u) << 8) | (((w >> 4) & 63u) << 2);
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if ((nib >> b) & 1u) {
+        if (pos < q1Cap) q1[pos] = (unsigned short)(code + b);
+        ++pos;
+      }
+  }
+}
+
+// LOW: both thresholds are below 128 (the usual case; the other instance handles any thresholds)
+template <bool LOW>
+__global__ void __launch_bounds__(ORBFE_FAST_THREADS, ORBFE_FAST_MINB)
+k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, const CUtensorMap* __restrict__ tmaps,
+             const unsigned* __restrict__ tasks, int* __restrict__ cellCnt, unsigned* __restrict__ cellList,
+             const int maxRows, const int q1Cap, const int q2Cap, const int listCap) {
   ORBFE_DYN_SMEM(smem);
-  unsigned* tileW = reinterpret_cast<unsigned*>(smem);               // [maxRows][pitchW] pixels
-  unsigned* scoreW = tileW + (size_t)maxRows * pitchW;               // [maxRows][pitchW] corner scores
-  unsigned* bitsW = scoreW + (size_t)maxRows * pitchW;               // [maxRows][pitchW/8+1] NMS survivor bits
-  unsigned short* queue = reinterpret_cast<unsigned short*>(bitsW + (size_t)maxRows * (pitchW / 8 + 1));
-  __shared__ int s_qn;
-  __shared__ int s_any[ORBFE_FAST_MAXG];
-  __shared__ int s_fall[ORBFE_FAST_MAXG];
-  __shared__ unsigned s_rowmask[ORBFE_FAST_MAXG][ORBFE_FAST_ROWWORDS];
-  __shared__ uint8_t s_colCell[512];
+  const FastSmemLayout lay = orbfe_fast_layout(maxRows, q1Cap, q2Cap, listCap);
+  unsigned* tileW = reinterpret_cast<unsigned*>(smem);
+  const uint8_t* tileB = smem;
+  uint8_t* scoreB = smem + lay.scoreOff;
+  unsigned short* q1 = reinterpret_cast<unsigned short*>(smem + lay.q1Off);
+  unsigned short* q2 = reinterpret_cast<unsigned short*>(smem + lay.q2Off);
+  unsigned short* lists = reinterpret_cast<unsigned short*>(smem + lay.listOff);  // [cell][listCap] survivors y << 8 | x
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ int s_qn[2][3];                         // [round][Q1 / Q2 / word queue] entries pushed
+  __shared__ int s_cellN[ORBFE_FAST_MAXG];           // survivors per cell
+  __shared__ uint8_t s_colCell[ORBFE_FAST_TP];       // tile column -> cell of this CTA (0xff outside the inner band)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int slot = blockIdx.y;
-  int level = 0;
-  for (int l = 1; l < g.nlevels; ++l)
-    if ((int)blockIdx.x >= g.lv[l].fastBase) level = l;
+  const unsigned task = __ldg(tasks + blockIdx.x);
+  const int level = task & 15, i = (task >> 4) & 0xfff, j0 = task >> 16;
   const LevelGeom& L = g.lv[level];
-  const int bi = blockIdx.x - L.fastBase;
-  const int i = bi / L.fSegs, j0 = (bi - i * L.fSegs) * L.fG;
+  const int wCell = L.wCell;
   const int nj = min(L.fG, L.nCols - j0);
   int* cnt = cellCnt + (size_t)slot * g.totalCells + L.cellBase + i * L.nCols + j0;
-  unsigned* list = cellList + (size_t)slot * g.cellListStride + L.cellListOff + (size_t)(i * L.nCols + j0) * L.cellCap;
-  const int iniY = ORBFE_MINB + i * L.hCell, iniX = ORBFE_MINB + j0 * L.wCell;
-  const int maxY = min(iniY + L.hCell + 6, L.maxBY);
-  const int maxX = min(iniX + nj * L.wCell + 6, L.maxBX);
-  const int rows = maxY - iniY;
+  const int iniY = ORBFE_MINB + i * L.hCell, iniX = ORBFE_MINB + j0 * wCell;
+  const int rows = min(iniY + L.hCell + 6, L.maxBY) - iniY;
+  const int winW = min(iniX + nj * wCell + 6, L.maxBX) - iniX;
   // skipped rows/cells (orb_extractor.cpp:735,744) and sub-images too small for FAST yield nothing
-  if (rows < 7 || maxX - iniX < 7) {
+  if (rows < 7 || winW < 7) {
     if (tid < nj) cnt[tid] = 0;
     return;
   }
-  const int pitchB = pitchW * 4, bitsP = pitchW / 8 + 1;
-  const int gx0 = (iniX + ORBFE_EDGE) & ~3;                          // padded-plane column of tile column 0
-  const int tw = (maxX + ORBFE_EDGE - gx0 + 3) >> 2;                  // tile width in words
-  const int ix0 = iniX + 3 + ORBFE_EDGE - gx0, ix1 = maxX - 3 + ORBFE_EDGE - gx0;  // inner columns (tile coords)
-  const uint8_t* src = pyr + (size_t)slot * g.pyrStride + L.planeOff + (size_t)(iniY + ORBFE_EDGE) * L.pitch + gx0;
-  for (int r = wid; r < rows; r += ORBFE_FAST_THREADS / 32) {
-    const unsigned* srow = reinterpret_cast<const unsigned*>(src + (size_t)r * L.pitch);
-    for (int c = lane; c < pitchW; c += 32) {
-      tileW[r * pitchW + c] = c < tw ? __ldg(srow + c) : 0u;
-      scoreW[r * pitchW + c] = 0u;
-    }
-    for (int c = lane; c < bitsP; c += 32) bitsW[r * bitsP + c] = 0u;
+  const int gx0 = (iniX + ORBFE_EDGE - 1) & ~15;   // padded-plane column of tile column 0
+  const int off = iniX + ORBFE_EDGE - 1 - gx0;     // window column c -> tile column c + 1 + off
+  const int ix0 = 4 + off, ix1 = winW - 2 + off;   // inner columns (tile coordinates)
+  if (tid == 0) {
+    orbfe_tile_barrier_init(&s_bar);
+    s_qn[0][0] = s_qn[0][1] = s_qn[0][2] = s_qn[1][0] = s_qn[1][1] = s_qn[1][2] = 0;
   }
-  if (tid < ORBFE_FAST_MAXG) {
-    s_any[tid] = 0;
-#pragma unroll
-    for (int k = 0; k < ORBFE_FAST_ROWWORDS; ++k) s_rowmask[tid][k] = 0u;
+  if (tid < ORBFE_FAST_MAXG) s_cellN[tid] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    OrbfeTmaPlane P;
+    P.base = pyr + L.planeOff; P.sliceStride = g.pyrStride; P.pitch = L.pitch; P.rows = L.h + 2 * ORBFE_EDGE;
+    P.slices = gridDim.y; P.boxW = ORBFE_FAST_TP; P.boxH = maxRows;
+    orbfe_tile_issue(smem, &s_bar, tmaps + level, P, gx0, iniY + ORBFE_EDGE, slot);
   }
-  for (int x = tid; x < pitchB && x < 512; x += ORBFE_FAST_THREADS)
-    s_colCell[x] = (uint8_t)((x >= ix0 && x < ix1) ? (x - ix0) / L.wCell : 0xff);
-  const uint8_t* tileB = reinterpret_cast<const uint8_t*>(tileW);
-  uint8_t* scoreB = reinterpret_cast<uint8_t*>(scoreW);
-  const int w0 = ix0 >> 2, nWi = ((ix1 - 1) >> 2) - w0 + 1;
+  {  // while the tile is in flight: clear the score plane, build the column -> cell table
+    uint4* z = reinterpret_cast<uint4*>(scoreB);
+    for (int k = tid; k < rows * (ORBFE_FAST_TP / 16); k += ORBFE_FAST_THREADS) z[k] = make_uint4(0u, 0u, 0u, 0u);
+    // (x - ix0) / wCell by multiply-shift: exact for x - ix0 < 256 and wCell <= 234
+    s_colCell[tid] = (uint8_t)((tid >= ix0 && tid < ix1) ? ((unsigned)(tid - ix0) * (unsigned)L.wCellMagic) >> 16 : 0xffu);
+  }
+  const int yEnd = rows - 3;                       // inner rows [3, yEnd)
+  const int wLo = ix0 >> 2, nW = (ix1 - 1) >> 2;   // inner words wLo .. nW (wLo >= 1: the pre-test reads word wx - 1)
+  const unsigned mask0 = orbfe_fast_colmask(wLo + lane, ix0, ix1), mask1 = orbfe_fast_colmask(wLo + lane + 32, ix0, ix1);
+  const int thA = g.iniTh, thB = g.minTh;
+  const bool twoRounds = thB < thA;
+  const unsigned KA = (unsigned)(thA < 128 ? 127 - thA : 255 - thA) * 0x01010101u;
+  const unsigned KB = (unsigned)(thB < 128 ? 127 - thB : 255 - thB) * 0x01010101u;
+  const unsigned baseWord = (unsigned)((wid << 10) | ((wLo + lane) << 4));
+  const int nItems = 2 * ((yEnd - 3 + 7) >> 3);    // word items per thread: rows 3 + wid + 8 it, it < nItems / 2
+  orbfe_tile_wait(&s_bar, 0);
+  __syncthreads();
 
-  for (int round = 0; round < 2; ++round) {
-    const int th = round == 0 ? g.iniTh : g.minTh;
-    if (tid == 0) s_qn = 0;
-    if (tid < ORBFE_FAST_MAXG) s_fall[tid] = !s_any[tid];  // cells in play this round (snapshot: step 3 updates s_any)
-    __syncthreads();
-    if (round == 1) {  // block-uniform: does any cell of this CTA need the minThFAST fallback?
-      bool need = false;
-      for (int jl = 0; jl < nj; ++jl) need = need || !s_any[jl];
-      if (!need || g.minTh >= g.iniTh) break;
-    }
-    // ---- 1. compass pre-test on words: flag bit 7 of byte b <=> |ring - centre| > th
-    const unsigned K4 = (unsigned)(th < 128 ? 127 - th : 255 - th) * 0x01010101u;
-    for (int y = 3 + wid; y < rows - 3; y += ORBFE_FAST_THREADS / 32)
-      for (int wi = lane; wi < nWi; wi += 32) {
-        const int wx = w0 + wi, xb = 4 * wx;
-        if (round == 1) {  // only the fallback cells are re-examined
-          const unsigned ca = s_colCell[min(max(xb, ix0), ix1 - 1)], cb = s_colCell[max(min(xb + 3, ix1 - 1), ix0)];
-          if (s_any[ca] && s_any[cb]) continue;
-        }
-        const unsigned* row = tileW + y * pitchW + wx;
-        const unsigned c = row[0], up = row[-3 * pitchW], dn = row[3 * pitchW];
-        const unsigned prev = wx > 0 ? row[-1] : 0u, next = wx + 1 < pitchW ? row[1] : 0u;
-        const unsigned lf = __funnelshift_r(prev, c, 8), rt = __funnelshift_r(c, next, 24);
-        const unsigned a0 = __vabsdiffu4(dn, c), a4 = __vabsdiffu4(rt, c), a8 = __vabsdiffu4(up, c), a12 = __vabsdiffu4(lf, c);
-        unsigned f0, f4, f8, f12;
-        if (th < 128) {
-          f0 = ((a0 & 0x7f7f7f7fu) + K4) | a0;   f4 = ((a4 & 0x7f7f7f7fu) + K4) | a4;
-          f8 = ((a8 & 0x7f7f7f7fu) + K4) | a8;   f12 = ((a12 & 0x7f7f7f7fu) + K4) | a12;
-        } else {
-          f0 = ((a0 & 0x7f7f7f7fu) + K4) & a0;   f4 = ((a4 & 0x7f7f7f7fu) + K4) & a4;
-          f8 = ((a8 & 0x7f7f7f7fu) + K4) & a8;   f12 = ((a12 & 0x7f7f7f7fu) + K4) & a12;
-        }
-        unsigned m = (f0 | f8) & (f4 | f12) & 0x80808080u;  // two adjacent compass points differ by > th
-        if (m == 0u) continue;
-        if (xb < ix0 || xb + 3 >= ix1 || round == 1) {  // edge words of the band / fallback round: per-byte filter
+  // ---- 1. pre-test at both thresholds -> flag registers
+  unsigned a0 = 0u, a1 = 0u, b0 = 0u, b1 = 0u;     // a: iniThFAST, b: minThFAST
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int x = xb + b;
-            if (x < ix0 || x >= ix1 || (round == 1 && s_any[s_colCell[x]])) m &= ~(0x80u << (8 * b));
+  for (int it = 0; it < 8; ++it) {
+    const int y = 3 + wid + 8 * it;
+    if (y < yEnd) {                                // warp-uniform
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int wx = wLo + lane + 32 * j;
+        if (wx <= nW) {
+          const unsigned* row = tileW + y * ORBFE_FAST_TPW + wx;
+          const unsigned c = row[0];
+          const unsigned r0 = row[3 * ORBFE_FAST_TPW], r8 = row[-3 * ORBFE_FAST_TPW];                      // ring 0 (0,3), 8 (0,-3)
+          const unsigned r12 = __funnelshift_r(row[-1], c, 8), r4 = __funnelshift_r(c, row[1], 24);      // ring 12 (-3,0), 4 (3,0)
+          const unsigned* rd = row + 2 * ORBFE_FAST_TPW;
+          const unsigned* ru = row - 2 * ORBFE_FAST_TPW;
+          const unsigned dc = rd[0], uc = ru[0];
+          const unsigned r2 = __funnelshift_r(dc, rd[1], 16), r14 = __funnelshift_r(rd[-1], dc, 16);     // ring 2 (2,2), 14 (-2,2)
+          const unsigned r6 = __funnelshift_r(uc, ru[1], 16), r10 = __funnelshift_r(ru[-1], uc, 16);     // ring 6 (2,-2), 10 (-2,-2)
+          const unsigned d0 = __vabsdiffu4(r0, c), d4 = __vabsdiffu4(r4, c), d8 = __vabsdiffu4(r8, c), d12 = __vabsdiffu4(r12, c);
+          const unsigned d2 = __vabsdiffu4(r2, c), d6 = __vabsdiffu4(r6, c), d10 = __vabsdiffu4(r10, c), d14 = __vabsdiffu4(r14, c);
+          const unsigned l0 = d0 & 0x7f7f7f7fu, l4 = d4 & 0x7f7f7f7fu, l8 = d8 & 0x7f7f7f7fu, l12 = d12 & 0x7f7f7f7fu;
+          const unsigned l2 = d2 & 0x7f7f7f7fu, l6 = d6 & 0x7f7f7f7fu, l10 = d10 & 0x7f7f7f7fu, l14 = d14 & 0x7f7f7f7fu;
+          const unsigned mk = j ? mask1 : mask0;
+          // |d| > th:  th < 128: (|d| & 127) + (127 - th) carries into bit 7, or bit 7 of |d| is set;
+          //            th >= 128: bit 7 of |d| is set AND the low 7 bits exceed th - 128
+#define ORBFE_GT_LO(l, d, K) (((l) + (K)) | (d))
+#define ORBFE_GT_HI(l, d, K) (((l) + (K)) & (d))
+#define ORBFE_PAIRS(GT, K)                                                                                                      \
+  ((GT(l0, d0, K) | GT(l8, d8, K)) & (GT(l4, d4, K) | GT(l12, d12, K)) & (GT(l2, d2, K) | GT(l10, d10, K)) & (GT(l6, d6, K) | GT(l14, d14, K)) & mk)
+          unsigned mA, mB = 0u;
+          if (LOW || thA < 128) mA = ORBFE_PAIRS(ORBFE_GT_LO, KA);
+          else mA = ORBFE_PAIRS(ORBFE_GT_HI, KA);
+          if (twoRounds) {
+            if (LOW || thB < 128) mB = ORBFE_PAIRS(ORBFE_GT_LO, KB);
+            else mB = ORBFE_PAIRS(ORBFE_GT_HI, KB);
           }
+#undef ORBFE_PAIRS
+#undef ORBFE_GT_LO
+#undef ORBFE_GT_HI
+          if (it < 4) { a0 |= mA >> (2 * it + j); b0 |= mB >> (2 * it + j); }
+          else { a1 |= mA >> (2 * (it - 4) + j); b1 |= mB >> (2 * (it - 4) + j); }
         }
-        const int n = __popc(m);
-        if (n == 0) continue;
-        int pos = atomicAdd(&s_qn, n);
+      }
+    }
+  }
+
+  unsigned fallMask = 0u;                          // round 1: cells in play
+  for (int round = 0; round < 2; ++round) {
+    const int th = round == 0 ? thA : thB;
+    int* qn1 = &s_qn[round][0];
+    int* qn2 = &s_qn[round][1];
+    int* qnw = &s_qn[round][2];
+    // ---- 2. flag registers -> Q1
+    if (round == 1) {
+      if (!twoRounds) break;
+      for (int jl = 0; jl < nj; ++jl) fallMask |= (s_cellN[jl] ? 0u : 1u) << jl;
+      if (fallMask == 0u) break;                   // block-uniform
+      // keep the flags of the cells in play: byte b of the items with j = 0 sits in bits 8b + {7,5,3,1}, j = 1 in 8b + {6,4,2,0}
+      unsigned keep = 0u;
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-          if ((m >> (8 * b + 7)) & 1u) { if (pos < queueCap) queue[pos] = (unsigned short)((y << xbits) | (xb + b)); ++pos; }
-      }
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int x = 4 * (wLo + lane + 32 * j) + b;
+          const unsigned c = x < ORBFE_FAST_TP ? s_colCell[x] : 0xffu;
+          if (c != 0xffu && ((fallMask >> c) & 1u)) keep |= (j ? 0x55u : 0xaau) << (8 * b);
+        }
+      a0 = b0 & keep; a1 = b1 & keep;
+    }
+    orbfe_fast_push_words(a0, a1, nItems, q2, qnw, baseWord, lane);   // the word queue lives in Q2's storage
     __syncthreads();
-    // ---- 2. exact score on the queue; corner at th <=> score >= th
-    // The queue holds queueCap entries, sized so that 6 CTAs fit an SM rather than for the worst case (A/B: FAST -7 %).  A tile
-    // whose pre-test passes more pixels than that (dense noise at minThFAST) is block-uniformly switched to the dense form of
-    // steps 2 and 3: every pixel of the cells in play is scored and NMS-tested, no queue.  Identical results: the pre-test is
-    // only a necessary condition, a pixel it rejects has score < th.
-    const bool dense = s_qn > queueCap;
-    const int qn = min(s_qn, queueCap);
-    const int xmask = (1 << xbits) - 1;
-    const int innerW = ix1 - ix0, nWork = dense ? innerW * (rows - 6) : qn;
-    // work item e -> pixel (x, y) of the tile; false = not in play (dense form, cell already has keypoints)
-    auto item = [&](const int e, int& x, int& y) -> bool {
-      if (!dense) {
-        const int code = queue[e];
-        x = code & xmask;
-        y = code >> xbits;
-        return true;
+    orbfe_fast_expand(q2, *qnw, q1, q1Cap, qn1, tid, lane);
+    __syncthreads();
+    // ---- 3. exact score; corner at th <=> score >= th.  Corners -> score plane + Q2 (warp ballot)
+    const bool dense = *qn1 > q1Cap;
+    if (!dense) {
+      const int qn = *qn1;
+      for (int e0 = wid * 32; e0 < qn; e0 += ORBFE_FAST_THREADS) {
+        const int e = e0 + lane;
+        bool corner = false;
+        unsigned short code = 0;
+        if (e < qn) {
+          code = q1[e];
+          const int o = (code >> 8) * ORBFE_FAST_TP + (code & 255);
+          const int s = orbfe_fast_score3(tileB + o, ORBFE_FAST_TP);
+          corner = s >= th;
+          if (corner) scoreB[o] = (uint8_t)s;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, corner);
+        if (bal) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(qn2, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const int pos = base + __popc(bal & ((1u << lane) - 1u));
+          if (corner && pos < q2Cap) q2[pos] = code;
+        }
       }
-      const int yy = e / innerW;
-      x = ix0 + (e - yy * innerW);
-      y = 3 + yy;
-      return round == 0 || s_fall[s_colCell[x]];
-    };
-    for (int e = tid; e < nWork; e += ORBFE_FAST_THREADS) {
-      int x, y;
-      if (!item(e, x, y)) continue;
-      const int o0 = y * pitchB + x;
-      const int s0 = orbfe_fast_score3(tileB + o0, pitchB);
-      if (s0 >= th) scoreB[o0] = (uint8_t)s0;
+    } else {
+      const int innerW = ix1 - ix0, nWork = innerW * (yEnd - 3);
+      for (int e = tid; e < nWork; e += ORBFE_FAST_THREADS) {
+        const int yy = e / innerW, x = ix0 + (e - yy * innerW), y = 3 + yy;
+        if (round == 1 && !((fallMask >> s_colCell[x]) & 1u)) continue;
+        const int o = y * ORBFE_FAST_TP + x;
+        const int s = orbfe_fast_score3(tileB + o, ORBFE_FAST_TP);
+        if (s >= th) scoreB[o] = (uint8_t)s;
+      }
     }
     __syncthreads();
-    // ---- 3. NMS inside the cell; survivors -> bit plane + row masks; keypoint found => no fallback
-    for (int e = tid; e < nWork; e += ORBFE_FAST_THREADS) {
-      int x, y;
-      if (!item(e, x, y)) continue;
-      const uint8_t* c = scoreB + y * pitchB + x;
+    // ---- 4. NMS inside the cell; survivors -> the cell's list
+    const bool denseNms = dense || *qn2 > q2Cap;
+    auto nms = [&](const int x, const int y) {
+      const uint8_t* c = scoreB + y * ORBFE_FAST_TP + x;
       const int s = c[0];
-      if (s == 0) continue;
       const int jl = s_colCell[x];
-      const int cx0 = ix0 + jl * L.wCell, cx1 = min(cx0 + L.wCell, ix1);
-      const bool hasL = x > cx0, hasR = x + 1 < cx1;  // rows outside the inner band hold score 0 already
-      bool keep = s > c[-pitchB] && s > c[pitchB];
-      if (hasL) keep = keep && s > c[-1] && s > c[-pitchB - 1] && s > c[pitchB - 1];
-      if (hasR) keep = keep && s > c[1] && s > c[-pitchB + 1] && s > c[pitchB + 1];
-      if (keep) {
-        atomicOr(&bitsW[y * bitsP + (x >> 5)], 1u << (x & 31));
-        atomicOr(&s_rowmask[jl][y >> 5], 1u << (y & 31));
-        s_any[jl] = 1;
+      const int cx0 = ix0 + jl * wCell, cx1 = min(cx0 + wCell, ix1);
+      // rows outside the inner band hold score 0; columns outside the cell's window count 0
+      const int l0 = x > cx0 ? -1 : 0, r0 = x + 1 < cx1 ? 1 : 0;
+      int m = max((int)c[-ORBFE_FAST_TP], (int)c[ORBFE_FAST_TP]);
+      m = __vimax3_s32(m, (int)c[l0 - ORBFE_FAST_TP], (int)c[l0 + ORBFE_FAST_TP]);
+      m = __vimax3_s32(m, (int)c[r0 - ORBFE_FAST_TP], (int)c[r0 + ORBFE_FAST_TP]);
+      if (l0) m = max(m, (int)c[-1]);
+      if (r0) m = max(m, (int)c[1]);
+      if (s > m) {
+        const int pos = atomicAdd(&s_cellN[jl], 1);
+        if (pos < listCap) lists[jl * listCap + pos] = (unsigned short)((y << 8) | x);
+      }
+    };
+    if (!denseNms) {
+      const int qn = *qn2;
+      for (int e = tid; e < qn; e += ORBFE_FAST_THREADS) {
+        const unsigned code = q2[e];
+        nms(code & 255, code >> 8);
+      }
+    } else {
+      const int nWw = nW - wLo + 1, nWork = nWw * (yEnd - 3);
+      for (int e = tid; e < nWork; e += ORBFE_FAST_THREADS) {
+        const int yy = e / nWw, wx = wLo + (e - yy * nWw), y = 3 + yy;
+        const unsigned s4 = *reinterpret_cast<const unsigned*>(scoreB + y * ORBFE_FAST_TP + 4 * wx);
+        if (s4 == 0u) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int x = 4 * wx + b;
+          if (((s4 >> (8 * b)) & 0xffu) == 0u) continue;
+          if (round == 1 && !((fallMask >> s_colCell[x]) & 1u)) continue;  // round-0 corners were handled in round 0
+          nms(x, y);
+        }
       }
     }
     __syncthreads();
   }
-  // ---- 4. ordered emission, one warp per cell, only rows that hold a survivor
+  // ---- 5. ordered emission, one warp per cell: slot = number of the cell's survivors that precede this one in
+  // row-major order (key y << 8 | x); the lists are short (a few tens of entries)
   for (int jl = wid; jl < nj; jl += ORBFE_FAST_THREADS / 32) {
-    const int cx0 = ix0 + jl * L.wCell, cx1 = min(cx0 + L.wCell, ix1);
-    unsigned* out = list + (size_t)jl * L.cellCap;
-    int base = 0;
-    if (cx1 > cx0) {
-#pragma unroll
-      for (int k = 0; k < ORBFE_FAST_ROWWORDS; ++k) {
-        unsigned rm = s_rowmask[jl][k];
-        while (rm) {
-          const int y = 32 * k + __ffs((int)rm) - 1;
-          rm &= rm - 1;
-          for (int c0 = cx0; c0 < cx1; c0 += 32) {
-            const int x = c0 + lane;
-            const bool emit = x < cx1 && ((bitsW[y * bitsP + (x >> 5)] >> (x & 31)) & 1u);
-            const unsigned bal = __ballot_sync(0xffffffffu, emit);
-            if (emit) {
-              const int pos = base + __popc(bal & ((1u << lane) - 1u));
-              if (pos < L.cellCap)
-                out[pos] = orbfe_pack(x + gx0 - ORBFE_EDGE - ORBFE_MINB, y + iniY - ORBFE_MINB, scoreB[y * pitchB + x]);
-            }
-            base += __popc(bal);
-          }
-        }
-      }
+    const int n = min(s_cellN[jl], min(listCap, L.cellCap));
+    const unsigned short* li = lists + jl * listCap;
+    unsigned* out = cellList + (size_t)slot * g.cellListStride + L.cellListOff + (size_t)(i * L.nCols + j0 + jl) * L.cellCap;
+    for (int e = lane; e < n; e += 32) {
+      const unsigned key = li[e];
+      int rank = 0;
+      for (int f = 0; f < n; ++f) rank += li[f] < key ? 1 : 0;
+      const int x = key & 255, y = key >> 8;
+      out[rank] = orbfe_pack(x - 1 - off + iniX - ORBFE_MINB, y + iniY - ORBFE_MINB, scoreB[y * ORBFE_FAST_TP + x]);
     }
-    if (lane == 0) cnt[jl] = min(base, L.cellCap);
+    if (lane == 0) cnt[jl] = n;
   }
 }

@@ -55,8 +55,10 @@ struct orbfe_extractor {
   int fpl[ORBFE_MAX_LEVELS];
   Geom g{};
   bool configured = false;
-  int fastTilePitch = 0, fastMaxInnerH = 0, fastQueueCap = 0;
+  int fastRows = 0, fastQ1Cap = 0, fastQ2Cap = 0, fastListCap = 0;  // FAST tile rows (TMA box height), queue / list capacities
   size_t fastSmem = 0, octSmem = 0;
+  CUtensorMap* d_tmaps = nullptr;   // per level: the padded pyramid planes of every slot (box = 256 B x fastRows)
+  unsigned* d_fastTasks = nullptr;  // per FAST CTA: level | cell row | first cell
   int octStageCap = 0;
   // device arena
   uint8_t* d_img = nullptr;
@@ -139,6 +141,7 @@ static void build_resize_lut(int dn, int sn, ResizeLut* out) {
 
 static void free_arena(orbfe_extractor* ex) {
   cudaFree(ex->d_color); ex->d_color = nullptr; ex->colorStride = 0;
+  cudaFree(ex->d_tmaps); ex->d_tmaps = nullptr; cudaFree(ex->d_fastTasks); ex->d_fastTasks = nullptr;
   cudaFree(ex->d_img); cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_cellCnt); cudaFree(ex->d_cellList);
   cudaFree(ex->oct.cand); cudaFree(ex->oct.knode); cudaFree(ex->oct.cellStart); cudaFree(ex->oct.nodes);
   cudaFree(ex->oct.childCnt); cudaFree(ex->oct.childSlot); cudaFree(ex->oct.best); cudaFree(ex->oct.finSeq);
@@ -175,7 +178,8 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   g.imgStride = (unsigned)align_up_sz((size_t)w0 * h0, 4);
   size_t pyrOff = 0, blurOff = 0, cellListOff = 0, candOff = 0, nodeOff = 0;
   int cellBase = 0, outOff = 0, tileBase = 0, lutOff = 0, maxSort = 1;
-  int maxCw = 8, maxInnerH = 1, fastBase = 0, maxQueue = 1;
+  int maxInnerH = 1, fastBase = 0, maxQueue = 1, maxCellCap = 1, maxWords = 1;
+  std::vector<unsigned> fastTasks;
   std::vector<ResizeLut> lut;
   std::vector<PyrWordLut> wlut;
   std::vector<PyrRowLut> rlut;
@@ -265,19 +269,19 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
       L.wCell = (int)std::ceil(width / L.nCols);
       L.hCell = (int)std::ceil(height / L.nRows);
     }
+    L.wCellMagic = (65536 + L.wCell - 1) / L.wCell;
     L.cellBase = cellBase;
     cellBase += L.nCols * L.nRows;
     // strict 8-neighbour NMS => survivors are an independent set of the king graph
     L.cellCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
     L.cellListOff = (unsigned)cellListOff;
     cellListOff += (size_t)L.nCols * L.nRows * L.cellCap;
-    // FAST CTAs: a band segment of fG cells (tile <= ~256 px wide)
-    // cells per CTA: minimise 32-lane word iterations per cell (tile width fG*wCell+6 px + <=3 alignment)
+    // FAST CTAs: a band segment of fG cells; the tile (1 + fG*wCell + 6 px) is one 256-byte-wide TMA box
     L.fG = 1;
     {
       double best = 1e30;
-      for (int fg = 1; fg <= ORBFE_FAST_FGCAP && fg * L.wCell + 9 <= 300; ++fg) {
-        const int words = (fg * L.wCell + 9 + 3) / 4;
+      for (int fg = 1; fg <= ORBFE_FAST_MAXG && fg * L.wCell <= ORBFE_FAST_MAXW; ++fg) {
+        const int words = (fg * L.wCell + 3) / 4;  // minimise 32-lane word iterations per cell
         const double cost = (double)((words + 31) / 32) / fg;
         if (cost <= best) { best = cost; L.fG = fg; }
       }
@@ -286,9 +290,13 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
     L.fastBase = fastBase;
     fastBase += L.fSegs * L.nRows;
     if (L.nCols > 0) {
-      maxCw = std::max(maxCw, L.fG * L.wCell + 6 + 3);  // + alignment slack
+      if (L.wCell > ORBFE_FAST_MAXW) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too wide (%d px)", L.wCell);
       maxInnerH = std::max(maxInnerH, L.hCell);
       maxQueue = std::max(maxQueue, L.fG * L.wCell * L.hCell);
+      maxCellCap = std::max(maxCellCap, L.cellCap);
+      maxWords = std::max(maxWords, ((L.fG * L.wCell + 3) / 4 + 2) * L.hCell);  // inner words of a tile (word queue bound)
+      for (int i = 0; i < L.nRows; ++i)
+        for (int s = 0; s < L.fSegs; ++s) fastTasks.push_back(orbfe_fast_task(l, i, s * L.fG));
     }
     // quad-tree (orb_extractor.cpp:480-531)
     L.N = ex->fpl[l];
@@ -340,25 +348,26 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   if (ex->octSmem > 200 * 1024)
     return orbfe_fail(ORBFE_ERR_INVALID, "nfeatures per level too large for the shared-memory sort (%d)", maxSort);
   g.totalFast = fastBase;
-  if (maxCw > 511 || maxInnerH + 6 > 127) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too large for the 16-bit queue code");
-  ex->fastTilePitch = align_up(maxCw, 4) / 4 + 1;  // words
-  ex->fastTilePitch |= 1;                          // odd word pitch: vertically adjacent pixels fall in different banks
-  if (ex->fastTilePitch <= ORBFE_FAST_PITCHW) ex->fastTilePitch = ORBFE_FAST_PITCHW;  // compile-time specialisation
-  ex->fastMaxInnerH = maxInnerH + 6;              // tile rows
+  ex->fastRows = maxInnerH + 6;                   // tile rows == TMA box height
+  if (ex->fastRows > ORBFE_FAST_MAXROWS) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too tall (%d rows)", ex->fastRows);
   {
-    // queue capacity: enough for 6 CTAs of this kernel per SM (227 KB usable, 1 KB reserved per CTA) instead of the worst case
-    // (every pixel); a tile that passes more goes to the kernel's dense form.  ORBFE_TEST_FAST_QUEUE_PCT (tests only) forces a
-    // small queue so that ordinary images exercise that form.
-    const size_t planes = (size_t)(maxInnerH + 6) * (2 * ex->fastTilePitch + ex->fastTilePitch / 8 + 1) * 4 + 16;
-    const size_t target = (227 * 1024 - 6 * 1024) / 6 - 1024;
+    // queue capacities: what lets ORBFE_FAST_CTAS_PER_SM CTAs of this kernel share an SM (227 KB usable, 1 KB reserved and
+    // ~3 KB of static shared memory per CTA) instead of the worst case (every pixel); a tile that passes more goes to the
+    // kernel's dense form.  Q1 (pre-test candidates) gets 2/3, Q2 (corners) 1/3.  ORBFE_TEST_FAST_QUEUE_PCT (tests only)
+    // forces small queues so that ordinary images exercise that form.
+#ifndef ORBFE_FAST_CTAS_PER_SM
+#define ORBFE_FAST_CTAS_PER_SM 5
+#endif
+    ex->fastListCap = maxCellCap;
+    const size_t planes = (size_t)orbfe_fast_layout(ex->fastRows, 0, maxWords, ex->fastListCap).total;
+    const size_t target = (227 * 1024) / ORBFE_FAST_CTAS_PER_SM - 4 * 1024;
     int cap = maxQueue;
-    if (planes + 2 * (size_t)maxQueue > target) cap = (int)std::max<size_t>((target > planes ? (target - planes) / 2 : 0), (size_t)maxQueue / 4);
+    if (planes + 2 * (size_t)maxQueue > target) cap = (int)std::max<size_t>((target > planes ? (target - planes) / 2 : 0), (size_t)maxQueue / 8);
     if (const char* e = getenv("ORBFE_TEST_FAST_QUEUE_PCT")) { const int pc = atoi(e); if (pc >= 1 && pc <= 100) cap = std::max(maxQueue * pc / 100, 32); }
-    maxQueue = std::min(maxQueue, cap);
+    ex->fastQ1Cap = std::min(maxQueue, cap);
+    ex->fastQ2Cap = std::max(ex->fastQ1Cap / 2, maxWords);  // Q2's storage doubles as the word queue
   }
-  ex->fastQueueCap = maxQueue;
-  if (ex->fastMaxInnerH > 32 * ORBFE_FAST_ROWWORDS) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too tall");
-  ex->fastSmem = (size_t)ex->fastMaxInnerH * (2 * ex->fastTilePitch + ex->fastTilePitch / 8 + 1) * 4 + (size_t)maxQueue * 2 + 16;
+  ex->fastSmem = (size_t)orbfe_fast_layout(ex->fastRows, ex->fastQ1Cap, ex->fastQ2Cap, ex->fastListCap).total;
   if (ex->fastSmem > 200 * 1024) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too large");
   ex->bestStride = (size_t)g.nodeStride * 5 / 4 + 16 * ORBFE_MAX_LEVELS;
 
@@ -390,6 +399,22 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   if (!rlut.empty())
     CUDA_TRY(cudaMemcpyAsync(ex->d_rlut, rlut.data(), rlut.size() * sizeof(PyrRowLut), cudaMemcpyHostToDevice, ex->stream));
   CUDA_TRY(cudaMalloc(&ex->d_err, sizeof(int)));
+  CUDA_TRY(cudaMalloc(&ex->d_fastTasks, std::max<size_t>(fastTasks.size(), 1) * sizeof(unsigned)));
+  if (!fastTasks.empty())
+    CUDA_TRY(cudaMemcpyAsync(ex->d_fastTasks, fastTasks.data(), fastTasks.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ex->stream));
+  {
+    // tensor maps of the padded pyramid planes, one per level, every slot as dimension 2 (orbfe_tma.cuh)
+    std::vector<CUtensorMap> maps(nl);
+    for (int l = 0; l < nl; ++l) {
+      OrbfeTmaPlane P;
+      P.base = ex->d_pyr + g.lv[l].planeOff; P.sliceStride = g.pyrStride; P.pitch = g.lv[l].pitch;
+      P.rows = g.lv[l].h + 2 * ORBFE_EDGE; P.slices = (int)S; P.boxW = ORBFE_FAST_TP; P.boxH = ex->fastRows;
+      const int r = orbfe_tma_encode(&maps[l], P);
+      if (r != 0) return orbfe_fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled failed for level %d (%d)", l, r);
+    }
+    CUDA_TRY(cudaMalloc(&ex->d_tmaps, nl * sizeof(CUtensorMap)));
+    CUDA_TRY(cudaMemcpy(ex->d_tmaps, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  }
   {
     // IC_Angle weights (orb_extractor.cpp:18-45, umax :393-410): byte p of the 36-byte aligned window of patch
     // row v holds pixel u = p - a - 15 (a = alignment of the row start); weight u+15 and mask 1 inside the disc
@@ -432,8 +457,8 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   CUDA_TRY(cudaMemsetAsync(ex->d_nMatched, 0, S * sizeof(int), ex->stream));
   CUDA_TRY(cudaStreamSynchronize(ex->stream));  // `lut` goes out of scope
 #ifndef ORBFE_EMU
-  CUDA_TRY(cudaFuncSetAttribute(k_fast_cells<ORBFE_FAST_PITCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
-  CUDA_TRY(cudaFuncSetAttribute(k_fast_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
+  CUDA_TRY(cudaFuncSetAttribute(k_fast_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
+  CUDA_TRY(cudaFuncSetAttribute(k_fast_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
   CUDA_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octSmem));
   CUDA_TRY(cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->rowSmem));
 #endif
@@ -482,9 +507,9 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
   }
   if ((rc = stage_event(ex, 1))) return rc;
   if (g.totalFast > 0) {
-    auto kfast = ex->fastTilePitch == ORBFE_FAST_PITCHW ? k_fast_cells<ORBFE_FAST_PITCHW> : k_fast_cells<0>;
-    ORBFE_LAUNCH(ex, kfast, dim3(g.totalFast, n), dim3(ORBFE_FAST_THREADS), ex->fastSmem, g, ex->d_pyr,
-                 ex->d_cellCnt, ex->d_cellList, ex->fastTilePitch, ex->fastMaxInnerH, ex->fastQueueCap);
+    auto kfast = (g.iniTh < 128 && g.minTh < 128) ? k_fast_cells<true> : k_fast_cells<false>;
+    ORBFE_LAUNCH(ex, kfast, dim3(g.totalFast, n), dim3(ORBFE_FAST_THREADS), ex->fastSmem, g, ex->d_pyr, ex->d_tmaps,
+                 ex->d_fastTasks, ex->d_cellCnt, ex->d_cellList, ex->fastRows, ex->fastQ1Cap, ex->fastQ2Cap, ex->fastListCap);
   }
   if ((rc = stage_event(ex, 2))) return rc;
   ORBFE_LAUNCH(ex, k_octree, dim3(n, g.nlevels), dim3(ORBFE_OCT_THREADS), ex->octSmem, g, ex->d_cellCnt, ex->d_cellList,

@@ -37,6 +37,7 @@ struct LevelGeom {
   int area2;             // exact 2x decimation (OpenCV executes INTER_AREA)
   // FAST grid (orb_extractor.cpp:714-728)
   int nCols, nRows, wCell, hCell, maxBX, maxBY;
+  int wCellMagic;        // ceil(65536 / wCell): n / wCell == (n * magic) >> 16 for n < 256 (k_fast_cells)
   int cellBase, cellCap;
   int fG, fSegs, fastBase;  // FAST CTAs: fG cells per CTA, fSegs CTAs per cell row
   unsigned cellListOff;  // u32 entries
@@ -136,5 +137,5 @@ __device__ __forceinline__ void orbfe_block_sort_desc(unsigned long long* s, int
 #ifdef ORBFE_EMU
 #define ORBFE_DYN_SMEM(name) unsigned char* name = emu::S().dyn_smem
 #else
-#define ORBFE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define ORBFE_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]  // 128: TMA destinations
 #endif
