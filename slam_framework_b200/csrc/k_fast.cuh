@@ -19,9 +19,9 @@
 //      so a pixel is a corner only if, in each of the pairs (0,8), (4,12), (2,10), (6,14), a ring point differs from
 //      it by more than t.  Branch-free: the flags of up to 16 words accumulate in two registers per thread and
 //      threshold;
-//   2. queue build in two balanced steps: per word item a warp ballot appends the flagged WORDS to a word queue
-//      (round 1: only the bits of cells that found nothing in round 0); then one lane per queued word expands it,
-//      after a warp scan, into the pixel queue Q1;
+//   2. one warp-aggregated reservation per warp, then each thread unpacks its flag bits into the candidate queue Q1
+//      (round 1: only the bits of cells that found nothing in round 0).  Measured alternatives: building the queue
+//      with per-item warp ballots (word queue + expansion) costs twice the instructions of the per-thread unpack;
 //   3. exact corner score (max_arc min_9 of +-(ring - v), packed u16x2 min/max networks) on Q1; corners
 //      (score >= t) go to the score plane and, by warp ballot, to the corner queue Q2;
 //   4. strict 3x3 NMS restricted to the cell on Q2 -> per-cell survivor lists;
@@ -34,7 +34,12 @@
 #include "orbfe_common.cuh"
 #include "orbfe_tma.cuh"
 
-#define ORBFE_FAST_THREADS 256
+#ifndef ORBFE_FAST_WARPS
+#define ORBFE_FAST_WARPS 8      // warps per CTA (A/B on B200, 64 pairs: see DESIGN.md)
+#endif
+#define ORBFE_FAST_THREADS (32 * ORBFE_FAST_WARPS)
+#define ORBFE_FAST_ITS (64 / ORBFE_FAST_WARPS)   // row iterations of the pre-test: rows 3 + wid + WARPS * it cover 64 inner rows
+#define ORBFE_FAST_NACC (ORBFE_FAST_ITS / 4)     // flag registers per threshold: 8 word items (4 row iterations x 2 columns) each
 #define ORBFE_FAST_TP 256       // tile pitch in bytes == TMA box width
 #define ORBFE_FAST_TPW 64       // ... in words
 #define ORBFE_FAST_MAXG 8       // cells per CTA (upper bound)
@@ -109,8 +114,6 @@ __device__ __forceinline__ int orbfe_fast_reserve(const int cnt, int* counter, c
 struct FastSmemLayout {
   int scoreOff, q1Off, q2Off, listOff, total;  // bytes from the start of dynamic shared memory (tile at 0)
 };
-// Q2 (corners, written by the score step) shares its storage with the word queue (read by the expansion step before):
-// q2Cap >= the number of inner words of a tile
 __host__ __device__ __forceinline__ FastSmemLayout orbfe_fast_layout(const int maxRows, const int q1Cap, const int q2Cap, const int listCap) {
   FastSmemLayout s;
   s.scoreOff = maxRows * ORBFE_FAST_TP + 16;            // + 16: the pre-test of the last word reads one word past the tile
@@ -121,41 +124,18 @@ __host__ __device__ __forceinline__ FastSmemLayout orbfe_fast_layout(const int m
   return s;
 }
 
-// step 2a: the flag registers of a thread (acc0: items 0..7, acc1: items 8..15; bit 8b + 7 - (k & 7) = byte b of item k;
-// item k = 2 * it + j is the word (row 3 + wid + 8 it, column wLo + lane + 32 j)) -> word queue entries
-// (y - 3) << 10 | wx << 4 | flags, appended per item by warp ballot
-__device__ __forceinline__ void orbfe_fast_push_words(const unsigned acc0, const unsigned acc1, const int nItems, unsigned short* wq,
-                                                      int* counter, const unsigned baseWord, const int lane) {
-  for (int k = 0; k < nItems; ++k) {
-    const unsigned f = ((k < 8 ? acc0 : acc1) >> (7 - (k & 7))) & 0x01010101u;
-    const unsigned bal = __ballot_sync(0xffffffffu, f != 0u);
-    if (bal == 0u) continue;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(counter, __popc(bal));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (f) {
-      const unsigned nib = (f * 0x00204081u) >> 21;  // bits 0, 8, 16, 24 -> 0..3
-      wq[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(baseWord + ((k >> 1) << 13) + ((k & 1) << 9) + (nib & 15u));
-    }
+// step 2: a flag register of a thread (items kBase .. kBase + 7; bit 8b + 7 - (k & 7) = byte b of item k; item k = 2 * it + j
+// is the word (row 3 + wid + WARPS * it, column wLo + lane + 32 j)) -> queue codes y << 8 | x from `pos` on
+__device__ __forceinline__ int orbfe_fast_unpack(unsigned acc, const int kBase, int pos, const int cap, unsigned short* q,
+                                                 const unsigned baseCode) {
+  while (acc) {
+    const int p = __ffs((int)acc) - 1;
+    acc &= acc - 1;
+    const int k = kBase + 7 - (p & 7);
+    if (pos < cap) q[pos] = (unsigned short)(baseCode + (k >> 1) * (ORBFE_FAST_WARPS << 8) + ((k & 1) << 7) + (p >> 3));
+    ++pos;
   }
-}
-
-// step 2b: word queue -> pixel queue Q1 (codes y << 8 | x), one lane per queued word
-__device__ __forceinline__ void orbfe_fast_expand(const unsigned short* wq, const int nWords, unsigned short* q1, const int q1Cap,
-                                                  int* counter, const int tid, const int lane) {
-  for (int e0 = tid - lane; e0 < nWords; e0 += ORBFE_FAST_THREADS) {
-    const int e = e0 + lane;
-    const unsigned w = e < nWords ? wq[e] : 0u;
-    const unsigned nib = w & 15u;
-    int pos = orbfe_fast_reserve(__popc(nib), counter, lane);
-    const unsigned code = (((w >> 10) + 3u) << 8) | (((w >> 4) & 63u) << 2);
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if ((nib >> b) & 1u) {
-        if (pos < q1Cap) q1[pos] = (unsigned short)(code + b);
-        ++pos;
-      }
-  }
+  return pos;
 }
 
 // LOW: both thresholds are below 128 (the usual case; the other instance handles any thresholds)
@@ -173,7 +153,7 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, co
   unsigned short* q2 = reinterpret_cast<unsigned short*>(smem + lay.q2Off);
   unsigned short* lists = reinterpret_cast<unsigned short*>(smem + lay.listOff);  // [cell][listCap] survivors y << 8 | x
   __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ int s_qn[2][3];                         // [round][Q1 / Q2 / word queue] entries pushed
+  __shared__ int s_qn[2][2];                         // [round][Q1 / Q2] entries pushed
   __shared__ int s_cellN[ORBFE_FAST_MAXG];           // survivors per cell
   __shared__ uint8_t s_colCell[ORBFE_FAST_TP];       // tile column -> cell of this CTA (0xff outside the inner band)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -197,7 +177,7 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, co
   const int ix0 = 4 + off, ix1 = winW - 2 + off;   // inner columns (tile coordinates)
   if (tid == 0) {
     orbfe_tile_barrier_init(&s_bar);
-    s_qn[0][0] = s_qn[0][1] = s_qn[0][2] = s_qn[1][0] = s_qn[1][1] = s_qn[1][2] = 0;
+    s_qn[0][0] = s_qn[0][1] = s_qn[1][0] = s_qn[1][1] = 0;
   }
   if (tid < ORBFE_FAST_MAXG) s_cellN[tid] = 0;
   __syncthreads();
@@ -211,7 +191,8 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, co
     uint4* z = reinterpret_cast<uint4*>(scoreB);
     for (int k = tid; k < rows * (ORBFE_FAST_TP / 16); k += ORBFE_FAST_THREADS) z[k] = make_uint4(0u, 0u, 0u, 0u);
     // (x - ix0) / wCell by multiply-shift: exact for x - ix0 < 256 and wCell <= 234
-    s_colCell[tid] = (uint8_t)((tid >= ix0 && tid < ix1) ? ((unsigned)(tid - ix0) * (unsigned)L.wCellMagic) >> 16 : 0xffu);
+    for (int x = tid; x < ORBFE_FAST_TP; x += ORBFE_FAST_THREADS)
+      s_colCell[x] = (uint8_t)((x >= ix0 && x < ix1) ? ((unsigned)(x - ix0) * (unsigned)L.wCellMagic) >> 16 : 0xffu);
   }
   const int yEnd = rows - 3;                       // inner rows [3, yEnd)
   const int wLo = ix0 >> 2, nW = (ix1 - 1) >> 2;   // inner words wLo .. nW (wLo >= 1: the pre-test reads word wx - 1)
@@ -220,16 +201,17 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, co
   const bool twoRounds = thB < thA;
   const unsigned KA = (unsigned)(thA < 128 ? 127 - thA : 255 - thA) * 0x01010101u;
   const unsigned KB = (unsigned)(thB < 128 ? 127 - thB : 255 - thB) * 0x01010101u;
-  const unsigned baseWord = (unsigned)((wid << 10) | ((wLo + lane) << 4));
-  const int nItems = 2 * ((yEnd - 3 + 7) >> 3);    // word items per thread: rows 3 + wid + 8 it, it < nItems / 2
+  const unsigned baseCode = (unsigned)(((3 + wid) << 8) | (4 * (wLo + lane)));
   orbfe_tile_wait(&s_bar, 0);
   __syncthreads();
 
   // ---- 1. pre-test at both thresholds -> flag registers
-  unsigned a0 = 0u, a1 = 0u, b0 = 0u, b1 = 0u;     // a: iniThFAST, b: minThFAST
+  unsigned fa[ORBFE_FAST_NACC], fb[ORBFE_FAST_NACC];  // a: iniThFAST, b: minThFAST
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int y = 3 + wid + 8 * it;
+  for (int q = 0; q < ORBFE_FAST_NACC; ++q) fa[q] = fb[q] = 0u;
+#pragma unroll
+  for (int it = 0; it < ORBFE_FAST_ITS; ++it) {
+    const int y = 3 + wid + ORBFE_FAST_WARPS * it;
     if (y < yEnd) {                                // warp-uniform
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -265,8 +247,8 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, co
 #undef ORBFE_PAIRS
 #undef ORBFE_GT_LO
 #undef ORBFE_GT_HI
-          if (it < 4) { a0 |= mA >> (2 * it + j); b0 |= mB >> (2 * it + j); }
-          else { a1 |= mA >> (2 * (it - 4) + j); b1 |= mB >> (2 * (it - 4) + j); }
+          fa[it >> 2] |= mA >> (2 * (it & 3) + j);
+          fb[it >> 2] |= mB >> (2 * (it & 3) + j);
         }
       }
     }
@@ -277,7 +259,6 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, co
     const int th = round == 0 ? thA : thB;
     int* qn1 = &s_qn[round][0];
     int* qn2 = &s_qn[round][1];
-    int* qnw = &s_qn[round][2];
     // ---- 2. flag registers -> Q1
     if (round == 1) {
       if (!twoRounds) break;
@@ -293,11 +274,17 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, co
           const unsigned c = x < ORBFE_FAST_TP ? s_colCell[x] : 0xffu;
           if (c != 0xffu && ((fallMask >> c) & 1u)) keep |= (j ? 0x55u : 0xaau) << (8 * b);
         }
-      a0 = b0 & keep; a1 = b1 & keep;
+#pragma unroll
+      for (int q = 0; q < ORBFE_FAST_NACC; ++q) fa[q] = fb[q] & keep;
     }
-    orbfe_fast_push_words(a0, a1, nItems, q2, qnw, baseWord, lane);   // the word queue lives in Q2's storage
-    __syncthreads();
-    orbfe_fast_expand(q2, *qnw, q1, q1Cap, qn1, tid, lane);
+    {
+      int cntA = 0;
+#pragma unroll
+      for (int q = 0; q < ORBFE_FAST_NACC; ++q) cntA += __popc(fa[q]);
+      int pos = orbfe_fast_reserve(cntA, qn1, lane);
+#pragma unroll
+      for (int q = 0; q < ORBFE_FAST_NACC; ++q) pos = orbfe_fast_unpack(fa[q], 8 * q, pos, q1Cap, q1, baseCode);
+    }
     __syncthreads();
     // ---- 3. exact score; corner at th <=> score >= th.  Corners -> score plane + Q2 (warp ballot)
     const bool dense = *qn1 > q1Cap;

@@ -178,7 +178,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   g.imgStride = (unsigned)align_up_sz((size_t)w0 * h0, 4);
   size_t pyrOff = 0, blurOff = 0, cellListOff = 0, candOff = 0, nodeOff = 0;
   int cellBase = 0, outOff = 0, tileBase = 0, lutOff = 0, maxSort = 1;
-  int maxInnerH = 1, fastBase = 0, maxQueue = 1, maxCellCap = 1, maxWords = 1;
+  int maxInnerH = 1, fastBase = 0, maxQueue = 1, maxCellCap = 1;
   std::vector<unsigned> fastTasks;
   std::vector<ResizeLut> lut;
   std::vector<PyrWordLut> wlut;
@@ -276,16 +276,11 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
     L.cellCap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
     L.cellListOff = (unsigned)cellListOff;
     cellListOff += (size_t)L.nCols * L.nRows * L.cellCap;
-    // FAST CTAs: a band segment of fG cells; the tile (1 + fG*wCell + 6 px) is one 256-byte-wide TMA box
+    // FAST CTAs: a band segment of fG cells; the tile (<= 16 + fG*wCell + 6 px) is one 256-byte-wide TMA box.  As many cells
+    // as fit: the per-CTA set-up (tile fetch, plane clearing, barriers) is paid once per tile
     L.fG = 1;
-    {
-      double best = 1e30;
-      for (int fg = 1; fg <= ORBFE_FAST_MAXG && fg * L.wCell <= ORBFE_FAST_MAXW; ++fg) {
-        const int words = (fg * L.wCell + 3) / 4;  // minimise 32-lane word iterations per cell
-        const double cost = (double)((words + 31) / 32) / fg;
-        if (cost <= best) { best = cost; L.fG = fg; }
-      }
-    }
+    while (L.fG < ORBFE_FAST_MAXG && (L.fG + 1) * L.wCell <= ORBFE_FAST_MAXW) ++L.fG;
+    if (const char* e = getenv("ORBFE_TUNE_FAST_FG")) { const int v = atoi(e); if (v >= 1 && v <= L.fG) L.fG = v; }  // tuning only
     L.fSegs = L.nCols > 0 ? (L.nCols + L.fG - 1) / L.fG : 0;
     L.fastBase = fastBase;
     fastBase += L.fSegs * L.nRows;
@@ -294,7 +289,6 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
       maxInnerH = std::max(maxInnerH, L.hCell);
       maxQueue = std::max(maxQueue, L.fG * L.wCell * L.hCell);
       maxCellCap = std::max(maxCellCap, L.cellCap);
-      maxWords = std::max(maxWords, ((L.fG * L.wCell + 3) / 4 + 2) * L.hCell);  // inner words of a tile (word queue bound)
       for (int i = 0; i < L.nRows; ++i)
         for (int s = 0; s < L.fSegs; ++s) fastTasks.push_back(orbfe_fast_task(l, i, s * L.fG));
     }
@@ -359,13 +353,13 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
 #define ORBFE_FAST_CTAS_PER_SM 5
 #endif
     ex->fastListCap = maxCellCap;
-    const size_t planes = (size_t)orbfe_fast_layout(ex->fastRows, 0, maxWords, ex->fastListCap).total;
+    const size_t planes = (size_t)orbfe_fast_layout(ex->fastRows, 0, 0, ex->fastListCap).total;
     const size_t target = (227 * 1024) / ORBFE_FAST_CTAS_PER_SM - 4 * 1024;
     int cap = maxQueue;
-    if (planes + 2 * (size_t)maxQueue > target) cap = (int)std::max<size_t>((target > planes ? (target - planes) / 2 : 0), (size_t)maxQueue / 8);
+    if (planes + 3 * (size_t)maxQueue > target) cap = (int)std::max<size_t>((target > planes ? (target - planes) / 3 : 0), (size_t)maxQueue / 8);
     if (const char* e = getenv("ORBFE_TEST_FAST_QUEUE_PCT")) { const int pc = atoi(e); if (pc >= 1 && pc <= 100) cap = std::max(maxQueue * pc / 100, 32); }
     ex->fastQ1Cap = std::min(maxQueue, cap);
-    ex->fastQ2Cap = std::max(ex->fastQ1Cap / 2, maxWords);  // Q2's storage doubles as the word queue
+    ex->fastQ2Cap = std::max(ex->fastQ1Cap / 2, 16);
   }
   ex->fastSmem = (size_t)orbfe_fast_layout(ex->fastRows, ex->fastQ1Cap, ex->fastQ2Cap, ex->fastListCap).total;
   if (ex->fastSmem > 200 * 1024) return orbfe_fail(ORBFE_ERR_INVALID, "FAST cell too large");
