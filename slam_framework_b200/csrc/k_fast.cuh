@@ -185,6 +185,7 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, co
     OrbfeTmaPlane P;
     P.base = pyr + L.planeOff; P.sliceStride = g.pyrStride; P.pitch = L.pitch; P.rows = L.h + 2 * ORBFE_EDGE;
     P.slices = gridDim.y; P.boxW = ORBFE_FAST_TP; P.boxH = maxRows;
+    orbfe_tmap_acquire(tmaps + level);
     orbfe_tile_issue(smem, &s_bar, tmaps + level, P, gx0, iniY + ORBFE_EDGE, slot);
   }
   {  // while the tile is in flight: clear the score plane, build the column -> cell table

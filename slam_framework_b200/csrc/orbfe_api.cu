@@ -59,6 +59,8 @@ struct orbfe_extractor {
   size_t fastSmem = 0, octSmem = 0;
   CUtensorMap* d_tmaps = nullptr;   // per level: the padded pyramid planes of every slot (box = 256 B x fastRows)
   unsigned* d_fastTasks = nullptr;  // per FAST CTA: level | cell row | first cell
+  CUtensorMap* d_tmapsBlur = nullptr;  // the same planes with the blur's box (ORBFE_BLUR_BOXW x ORBFE_BLUR_RB)
+  unsigned* d_blurTasks = nullptr;  // per blur CTA: level | column strip
   int octStageCap = 0;
   // device arena
   uint8_t* d_img = nullptr;
@@ -142,6 +144,7 @@ static void build_resize_lut(int dn, int sn, ResizeLut* out) {
 static void free_arena(orbfe_extractor* ex) {
   cudaFree(ex->d_color); ex->d_color = nullptr; ex->colorStride = 0;
   cudaFree(ex->d_tmaps); ex->d_tmaps = nullptr; cudaFree(ex->d_fastTasks); ex->d_fastTasks = nullptr;
+  cudaFree(ex->d_tmapsBlur); ex->d_tmapsBlur = nullptr; cudaFree(ex->d_blurTasks); ex->d_blurTasks = nullptr;
   cudaFree(ex->d_img); cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_cellCnt); cudaFree(ex->d_cellList);
   cudaFree(ex->oct.cand); cudaFree(ex->oct.knode); cudaFree(ex->oct.cellStart); cudaFree(ex->oct.nodes);
   cudaFree(ex->oct.childCnt); cudaFree(ex->oct.childSlot); cudaFree(ex->oct.best); cudaFree(ex->oct.finSeq);
@@ -179,7 +182,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   size_t pyrOff = 0, blurOff = 0, cellListOff = 0, candOff = 0, nodeOff = 0;
   int cellBase = 0, outOff = 0, tileBase = 0, lutOff = 0, maxSort = 1;
   int maxInnerH = 1, fastBase = 0, maxQueue = 1, maxCellCap = 1;
-  std::vector<unsigned> fastTasks;
+  std::vector<unsigned> fastTasks, blurTasks;
   std::vector<ResizeLut> lut;
   std::vector<PyrWordLut> wlut;
   std::vector<PyrRowLut> rlut;
@@ -310,10 +313,12 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
     L.outOff = outOff;
     outOff += L.outCap;
     maxSort = std::max(maxSort, std::max(L.outCap, std::max(L.N, nIni)));
-    L.tilesX = (L.w + ORBFE_BLUR_TW - 1) / ORBFE_BLUR_TW;
-    L.tilesY = (L.h + ORBFE_BLUR_TH - 1) / ORBFE_BLUR_TH;
+    L.tilesX = (L.w + ORBFE_BLUR_TW - 1) / ORBFE_BLUR_TW;  // blur: column strips of 128 px x vertical segments
+    L.tilesY = std::max(1, (L.h + ORBFE_BLUR_SEG / 2) / ORBFE_BLUR_SEG);
     L.tileBase = tileBase;
     tileBase += L.tilesX * L.tilesY;
+    for (int sg = 0; sg < L.tilesY; ++sg)
+      for (int tx = 0; tx < L.tilesX; ++tx) blurTasks.push_back(orbfe_blur_task(l, sg, tx));
   }
   g.totalCells = cellBase;
   g.totalTiles = tileBase;
@@ -408,6 +413,18 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
     }
     CUDA_TRY(cudaMalloc(&ex->d_tmaps, nl * sizeof(CUtensorMap)));
     CUDA_TRY(cudaMemcpy(ex->d_tmaps, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    for (int l = 0; l < nl; ++l) {
+      OrbfeTmaPlane P;
+      P.base = ex->d_pyr + g.lv[l].planeOff; P.sliceStride = g.pyrStride; P.pitch = g.lv[l].pitch;
+      P.rows = g.lv[l].h + 2 * ORBFE_EDGE; P.slices = (int)S; P.boxW = ORBFE_BLUR_BOXW; P.boxH = ORBFE_BLUR_RB;
+      const int r = orbfe_tma_encode(&maps[l], P);
+      if (r != 0) return orbfe_fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled failed for the blur box of level %d (%d)", l, r);
+    }
+    CUDA_TRY(cudaMalloc(&ex->d_tmapsBlur, nl * sizeof(CUtensorMap)));
+    CUDA_TRY(cudaMemcpy(ex->d_tmapsBlur, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&ex->d_blurTasks, std::max<size_t>(blurTasks.size(), 1) * sizeof(unsigned)));
+    if (!blurTasks.empty())
+      CUDA_TRY(cudaMemcpy(ex->d_blurTasks, blurTasks.data(), blurTasks.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
   }
   {
     // IC_Angle weights (orb_extractor.cpp:18-45, umax :393-410): byte p of the 36-byte aligned window of patch
@@ -509,8 +526,8 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
   ORBFE_LAUNCH(ex, k_octree, dim3(n, g.nlevels), dim3(ORBFE_OCT_THREADS), ex->octSmem, g, ex->d_cellCnt, ex->d_cellList,
                ex->oct, ex->d_lvlKp, ex->d_lvlCnt, ex->d_err, ex->octStageCap);
   if ((rc = stage_event(ex, 3))) return rc;
-  ORBFE_LAUNCH(ex, k_blur, dim3((g.totalTiles + ORBFE_BLUR_THREADS / 32 - 1) / (ORBFE_BLUR_THREADS / 32), n),
-               dim3(ORBFE_BLUR_THREADS), 0, g, ex->d_pyr, ex->d_blur);  // one warp per strip
+  ORBFE_LAUNCH(ex, k_blur, dim3(g.totalTiles, n), dim3(ORBFE_BLUR_THREADS), 0, g, ex->d_pyr, ex->d_tmapsBlur, ex->d_blurTasks,
+               ex->d_blur, orbfe_blur_consts());  // one CTA (one warp) per 128-px column strip of a level
   if ((rc = stage_event(ex, 4))) return rc;
   {
     int kpw = n >= 4 ? 8 : 4;  // keypoints per warp (see k_orient_describe; measured: 8 beats 32 even at 128 frames)

@@ -108,13 +108,20 @@ __device__ __forceinline__ void orbfe_tile_barrier_init(unsigned long long* bar)
 #endif
 }
 
+// one thread, once per CTA before its first orbfe_tile_issue: the map lives in global memory (written by the host before the
+// launch); order its generic-proxy image before the tensormap-proxy reads.  (Not per copy: the fence drops the cached descriptor.)
+__device__ __forceinline__ void orbfe_tmap_acquire(const CUtensorMap* map) {
+#ifndef ORBFE_EMU
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(map) : "memory");
+#else
+  (void)map;
+#endif
+}
+
 // one thread: fetch the box whose first byte is (x, y) of slot z into dst (dense [boxH][boxW] bytes, 128-byte aligned)
 __device__ __forceinline__ void orbfe_tile_issue(void* dst, unsigned long long* bar, const CUtensorMap* map, const OrbfeTmaPlane& P,
                                                  int x, int y, int z) {
 #ifndef ORBFE_EMU
-  // the map lives in global memory (written by the host before the launch): order its generic-proxy image before
-  // the tensormap-proxy read
-  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(map) : "memory");
   orbfe_mbar_expect_tx(bar, (unsigned)(P.boxW * P.boxH));
   orbfe_tma_load_3d(dst, map, bar, x, y, z);
 #else
