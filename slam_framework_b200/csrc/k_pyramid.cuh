@@ -8,6 +8,7 @@
 // vertical blend ((b0*(T0>>4))>>16 + (b1*(T1>>4))>>16 + 2)>>2.
 #pragma once
 #include "orbfe_common.cuh"
+#include "orbfe_tma.cuh"
 
 #define ORBFE_PYR_THREADS 256
 
@@ -227,3 +228,141 @@ k_pyramid_resize(const __grid_constant__ Geom g, const int level, const int stri
   orbfe_resize_strip<true>(g, level, blockIdx.y, task, threadIdx.x & 31, stripRows, pyr, rlut, wlut);
 }
 
+
+// ---- streaming resize (levels >= 1, the k_pyramid_resize arithmetic fed from shared memory) ----------------------
+// One WARP = a column strip of 32 words (128 px) of the PADDED destination plane x one vertical segment of the level's
+// interior rows; the ORBFE_PYRS_WPC warps of a CTA work on consecutive strips and share nothing.  The rows of the source level arrive as a stream of TMA boxes (pyrBoxW bytes x ORBFE_PYRS_RB
+// rows) through a ring of ORBFE_PYRS_NB shared-memory buffers with one mbarrier each (orbfe_tma.cuh): the warp marches
+// down its destination rows, waits for the box that holds the lower source row of the current row, and re-arms a buffer
+// as soon as the march has left its rows.  No load sits on the dependent chain of a row any more (the previous form was
+// bound by it: ncu long-scoreboard 7.8 per issue), and every source byte is fetched from L2 once per strip.
+// Columns: the per-word LUT of k_pyramid_resize (source word, byte shift, PRMT selectors, 11-bit coefficient pairs); the
+// box starts at the 16-byte boundary at or below the strip's first source byte (host table pyrBoxX).  Rows: the
+// interior rows of the per-row LUT.  The 19-px top / bottom borders are BORDER_REFLECT_101 images of interior rows
+// 1..19 and h-20..h-2 of the SAME level (orb_extractor.cpp:1066,1071), so the warp that produces such a row stores it
+// twice; the left / right borders are ordinary words of the strip whose LUT entries point at the reflected columns.
+#ifndef ORBFE_PYRS_RB
+#define ORBFE_PYRS_RB 8      // source rows per box (power of two)
+#endif
+#ifndef ORBFE_PYRS_NB
+#define ORBFE_PYRS_NB 4      // boxes in the ring (power of two): the ring holds RB * NB source rows
+#endif
+#ifndef ORBFE_PYRS_SEG
+#define ORBFE_PYRS_SEG 56    // target destination rows per segment (A/B on B200: 112 -> 0.253 ms, 56 -> 0.246, 32 -> 0.263, 20 -> 0.285)
+#endif
+#ifndef ORBFE_PYRS_WPC
+#define ORBFE_PYRS_WPC 1     // independent warps (strips) per CTA.  A/B on B200 (128 frames): 1 -> 0.246 ms, 2 -> 0.266, 4 -> 0.271
+#endif
+#define ORBFE_PYRS_THREADS (32 * ORBFE_PYRS_WPC)
+#define ORBFE_PYRS_RING (ORBFE_PYRS_RB * ORBFE_PYRS_NB)
+
+// horizontal interpolation of the lane's 4 pixels from one source row held in shared memory
+__device__ __forceinline__ void orbfe_hrow_smem(const unsigned* srow, const int sh, const unsigned (&sel)[4], const unsigned (&cp)[4],
+                                                unsigned (&T)[4]) {
+  const unsigned w0 = srow[0], w1 = srow[1], w2 = srow[2];
+  const unsigned lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) T[j] = __dp2a_lo(cp[j], __byte_perm(lo, hi, sel[j]), 0u) >> 4;  // (S0*c0 + S1*c1) >> 4
+}
+
+__global__ void __launch_bounds__(ORBFE_PYRS_THREADS, 32 / ORBFE_PYRS_WPC)
+k_pyramid_strip(const __grid_constant__ Geom g, const int level, uint8_t* __restrict__ pyr, const CUtensorMap* __restrict__ tmaps,
+                const PyrRowLut* __restrict__ rlut, const PyrWordLut* __restrict__ wlut, const int* __restrict__ boxX,
+                const int nSegs) {
+  // dynamic shared memory: the ring (RING rows of pyrBoxW bytes: source row r of the segment lives at row r % RING; a box
+  // of RB rows starts on a 128-byte boundary because pyrBoxW is a multiple of 16 and RB of 8), then the segment's row LUT
+  // (a global load per row would sit on the march's critical path)
+  ORBFE_DYN_SMEM(smem);
+  __shared__ __align__(8) unsigned long long s_bars[ORBFE_PYRS_WPC][ORBFE_PYRS_NB];
+  static_assert((ORBFE_PYRS_RB & (ORBFE_PYRS_RB - 1)) == 0 && (ORBFE_PYRS_NB & (ORBFE_PYRS_NB - 1)) == 0 && ORBFE_PYRS_RB % 8 == 0,
+                "ring geometry");
+  const LevelGeom& L = g.lv[level];
+  const LevelGeom& S = g.lv[level - 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, slot = blockIdx.y;
+  const int nStrips = (L.pyrWords + 31) >> 5;
+  const int task = blockIdx.x * ORBFE_PYRS_WPC + wid;
+  const int sg = task / nStrips, tx = task - sg * nStrips;
+  const int segH = (L.h + nSegs - 1) / nSegs;
+  const int y0 = sg * segH, y1 = min(y0 + segH, L.h);
+  if (sg >= nSegs || y0 >= y1) return;
+  const int pitchW = L.pyrBoxW >> 2;              // box row pitch in words
+  const int warpBytes = (ORBFE_PYRS_RING * L.pyrBoxW + segH * (int)sizeof(PyrRowLut) + 127) & ~127;  // this warp's slice
+  unsigned* s_ring = reinterpret_cast<unsigned*>(smem + wid * warpBytes);
+  PyrRowLut* s_rl = reinterpret_cast<PyrRowLut*>(smem + wid * warpBytes + ORBFE_PYRS_RING * L.pyrBoxW);
+  unsigned long long* s_bar = s_bars[wid];
+  const int wx = min(tx * 32 + lane, L.pyrWords - 1);  // duplicate lanes rewrite the last word with the same value
+  const PyrWordLut W = wlut[L.wlutOff + wx];
+  unsigned sel[4], cp[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sel[j] = (W.sel >> (8 * j)) & 0xffu; cp[j] = W.cpack[j]; }
+  const int bx = boxX[L.pyrBoxOff + tx];          // first byte of the boxes (padded source column, multiple of 16)
+  const unsigned* ringLane = s_ring + (W.srcW - (bx >> 2));  // the lane's first source word inside a ring row
+  const int sh = W.sh;
+  const PyrRowLut* rl = rlut + L.rlutOff + ORBFE_EDGE;  // entry of interior row y at [y]
+  const int sBase = rl[y0].s0;                    // first source row of the segment (interior coordinates)
+  for (int r = lane; r < y1 - y0; r += 32) {      // source rows relative to the segment's first
+    PyrRowLut R = rl[y0 + r];
+    R.s0 -= sBase; R.s1 -= sBase;
+    s_rl[r] = R;
+  }
+  const int nBoxes = (rl[y1 - 1].s1 - sBase) / ORBFE_PYRS_RB + 1;
+  OrbfeTmaPlane P;
+  P.base = pyr + S.planeOff; P.sliceStride = g.pyrStride; P.pitch = S.pitch; P.rows = S.h + 2 * ORBFE_EDGE;
+  P.slices = gridDim.y; P.boxW = L.pyrBoxW; P.boxH = ORBFE_PYRS_RB;
+  const int by = ORBFE_EDGE + sBase;              // padded source row of box 0
+  const int boxWords = ORBFE_PYRS_RB * pitchW;
+  if (lane == 0)
+    for (int b = 0; b < ORBFE_PYRS_NB; ++b) orbfe_tile_barrier_init(&s_bar[b]);
+  __syncwarp();  // the barriers, the ring and the row LUT belong to this warp alone
+  int nextIssue = min(ORBFE_PYRS_NB, nBoxes), waited = 0;
+  if (lane == 0) {
+    orbfe_tmap_acquire(tmaps + level);
+    for (int b = 0; b < nextIssue; ++b)
+      orbfe_tile_issue(s_ring + b * boxWords, &s_bar[b], tmaps + level, P, bx, by + b * ORBFE_PYRS_RB, slot);
+  }
+  const int dpitchW = L.pitch >> 2;
+  unsigned* plane = reinterpret_cast<unsigned*>(pyr + (size_t)slot * g.pyrStride + L.planeOff) + wx;
+  unsigned* drow = plane + (size_t)(ORBFE_EDGE + y0) * dpitchW;
+  unsigned TA[4] = {0, 0, 0, 0}, TB[4] = {0, 0, 0, 0};
+  int ra = -1, rb = -1;
+  int landed = 0;  // source rows [0, landed) of the segment are in the ring
+  // one destination row: upper source row in Tt (cached as rt), lower in Tb (rbm)
+  auto row = [&](const int y, unsigned (&Tt)[4], int& rt, unsigned (&Tb)[4], int& rbm, const bool border) {
+    const PyrRowLut R = s_rl[y - y0];
+    if (R.s1 >= landed) {  // warp-uniform, once per box: the lower source row enters the next box
+      orbfe_tile_wait_warp(&s_bar[waited & (ORBFE_PYRS_NB - 1)], (unsigned)(waited / ORBFE_PYRS_NB) & 1u);
+      ++waited;
+      landed += ORBFE_PYRS_RB;
+      // re-arm the boxes the march has left (every lane has read them: __syncwarp): box nextIssue re-uses the buffer
+      // of box nextIssue - NB, whose last row is (nextIssue - NB + 1) * RB - 1
+      if (nextIssue < nBoxes && (nextIssue - ORBFE_PYRS_NB + 1) * ORBFE_PYRS_RB <= R.s0) {
+        __syncwarp();
+        if (lane == 0)
+          orbfe_tile_issue(s_ring + (nextIssue & (ORBFE_PYRS_NB - 1)) * boxWords, &s_bar[nextIssue & (ORBFE_PYRS_NB - 1)],
+                           tmaps + level, P, bx, by + nextIssue * ORBFE_PYRS_RB, slot);
+        ++nextIssue;
+      }
+    }
+    if (rt != R.s0) { orbfe_hrow_smem(ringLane + (R.s0 & (ORBFE_PYRS_RING - 1)) * pitchW, sh, sel, cp, Tt); rt = R.s0; }
+    if (rbm != R.s1) { orbfe_hrow_smem(ringLane + (R.s1 & (ORBFE_PYRS_RING - 1)) * pitchW, sh, sel, cp, Tb); rbm = R.s1; }
+    const unsigned out = orbfe_vblend(R, Tt, Tb);
+    *drow = out;
+    drow += dpitchW;
+    if (border) {
+      if (y <= ORBFE_EDGE && y >= 1) plane[(size_t)(ORBFE_EDGE - y) * dpitchW] = out;  // top border: row -y = row y
+      if (y >= L.h - 1 - ORBFE_EDGE && y <= L.h - 2) plane[(size_t)(2 * (L.h - 1) - y + ORBFE_EDGE) * dpitchW] = out;  // bottom
+    }
+  };
+  // the two register sets swap roles from row to row, so that the common "+1 source row" step re-uses the previous
+  // lower row as the new upper row without moves.  Rows that also feed a border row: y <= 19 or y >= h - 20.
+  const int yA = min(y1, max(y0, ORBFE_EDGE + 1)), yB = max(yA, min(y1, L.h - 1 - ORBFE_EDGE));  // [yA, yB): no border copies
+  int y = y0;
+  bool flip = false;
+  for (; y < yA; ++y, flip = !flip) { if (!flip) row(y, TA, ra, TB, rb, true); else row(y, TB, rb, TA, ra, true); }
+  if (flip && y < yB) { row(y, TB, rb, TA, ra, false); ++y; flip = false; }
+  for (; y + 1 < yB; y += 2) {
+    row(y, TA, ra, TB, rb, false);
+    row(y + 1, TB, rb, TA, ra, false);
+  }
+  for (; y < y1; ++y, flip = !flip) { if (!flip) row(y, TA, ra, TB, rb, y >= yB); else row(y, TB, rb, TA, ra, y >= yB); }
+}

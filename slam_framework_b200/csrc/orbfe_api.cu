@@ -61,6 +61,8 @@ struct orbfe_extractor {
   unsigned* d_fastTasks = nullptr;  // per FAST CTA: level | cell row | first cell
   CUtensorMap* d_tmapsBlur = nullptr;  // the same planes with the blur's box (ORBFE_BLUR_BOXW x ORBFE_BLUR_RB)
   unsigned* d_blurTasks = nullptr;  // per blur CTA: level | column strip
+  CUtensorMap* d_tmapsPyr = nullptr;   // per level l >= 1: the planes of level l-1 with the streaming resize's box
+  int* d_pyrBoxX = nullptr;         // per (level, strip): first source byte of the strip's boxes
   int octStageCap = 0;
   // device arena
   uint8_t* d_img = nullptr;
@@ -145,6 +147,7 @@ static void free_arena(orbfe_extractor* ex) {
   cudaFree(ex->d_color); ex->d_color = nullptr; ex->colorStride = 0;
   cudaFree(ex->d_tmaps); ex->d_tmaps = nullptr; cudaFree(ex->d_fastTasks); ex->d_fastTasks = nullptr;
   cudaFree(ex->d_tmapsBlur); ex->d_tmapsBlur = nullptr; cudaFree(ex->d_blurTasks); ex->d_blurTasks = nullptr;
+  cudaFree(ex->d_tmapsPyr); ex->d_tmapsPyr = nullptr; cudaFree(ex->d_pyrBoxX); ex->d_pyrBoxX = nullptr;
   cudaFree(ex->d_img); cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_cellCnt); cudaFree(ex->d_cellList);
   cudaFree(ex->oct.cand); cudaFree(ex->oct.knode); cudaFree(ex->oct.cellStart); cudaFree(ex->oct.nodes);
   cudaFree(ex->oct.childCnt); cudaFree(ex->oct.childSlot); cudaFree(ex->oct.best); cudaFree(ex->oct.finSeq);
@@ -183,6 +186,7 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   int cellBase = 0, outOff = 0, tileBase = 0, lutOff = 0, maxSort = 1;
   int maxInnerH = 1, fastBase = 0, maxQueue = 1, maxCellCap = 1;
   std::vector<unsigned> fastTasks, blurTasks;
+  std::vector<int> pyrBoxX;
   std::vector<ResizeLut> lut;
   std::vector<PyrWordLut> wlut;
   std::vector<PyrRowLut> rlut;
@@ -244,6 +248,22 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
       if (ok) {
         wlut.insert(wlut.end(), words.begin(), words.end());
         L.fastResize = 1;
+        // streaming form: per 32-word strip the 16-byte-aligned start of its source bytes; box width = the widest strip
+        L.pyrStrip = L.h >= ORBFE_EDGE + 1 ? 1 : 0;  // the row borders are copies of interior rows 1..19 / h-20..h-2
+        L.pyrSegs = 0;  // unused: the segment count is a launch argument
+        L.pyrBoxOff = (int)pyrBoxX.size();
+        L.pyrBoxW = 16;
+        for (int t = 0; t * 32 < L.pyrWords; ++t) {
+          int lo = 1 << 30, hi = 0;
+          for (int k = t * 32; k < std::min(t * 32 + 32, L.pyrWords); ++k) {
+            lo = std::min(lo, words[k].srcW * 4);
+            hi = std::max(hi, (words[k].srcW + 3) * 4);
+          }
+          const int x0 = lo & ~15;
+          pyrBoxX.push_back(x0);
+          L.pyrBoxW = std::max(L.pyrBoxW, align_up(hi - x0, 16));
+        }
+        if (L.pyrBoxW > 256) L.pyrStrip = 0;
         // per padded destination row: source rows + vertical coefficients of its REFLECT_101 image row
         L.rlutOff = (int)rlut.size();
         const ResizeLut* ly = lut.data() + L.lutYOff;
@@ -422,6 +442,19 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
     }
     CUDA_TRY(cudaMalloc(&ex->d_tmapsBlur, nl * sizeof(CUtensorMap)));
     CUDA_TRY(cudaMemcpy(ex->d_tmapsBlur, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    for (int l = 1; l < nl; ++l) {
+      if (!g.lv[l].pyrStrip) continue;
+      OrbfeTmaPlane P;
+      P.base = ex->d_pyr + g.lv[l - 1].planeOff; P.sliceStride = g.pyrStride; P.pitch = g.lv[l - 1].pitch;
+      P.rows = g.lv[l - 1].h + 2 * ORBFE_EDGE; P.slices = (int)S; P.boxW = g.lv[l].pyrBoxW; P.boxH = ORBFE_PYRS_RB;
+      const int r = orbfe_tma_encode(&maps[l], P);
+      if (r != 0) return orbfe_fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled failed for the resize box of level %d (%d)", l, r);
+    }
+    CUDA_TRY(cudaMalloc(&ex->d_tmapsPyr, nl * sizeof(CUtensorMap)));
+    CUDA_TRY(cudaMemcpy(ex->d_tmapsPyr, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&ex->d_pyrBoxX, std::max<size_t>(pyrBoxX.size(), 1) * sizeof(int)));
+    if (!pyrBoxX.empty())
+      CUDA_TRY(cudaMemcpy(ex->d_pyrBoxX, pyrBoxX.data(), pyrBoxX.size() * sizeof(int), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&ex->d_blurTasks, std::max<size_t>(blurTasks.size(), 1) * sizeof(unsigned)));
     if (!blurTasks.empty())
       CUDA_TRY(cudaMemcpy(ex->d_blurTasks, blurTasks.data(), blurTasks.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
@@ -501,7 +534,22 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
       ORBFE_LAUNCH(ex, k_pyramid_level0, dim3(L.h + 2 * ORBFE_EDGE, n), dim3(ORBFE_PYR0_THREADS), 0, g, ex->d_img, ex->d_pyr);
       continue;
     }
-    if (L.fastResize) {
+    if (L.pyrStrip && !getenv("ORBFE_TUNE_PYR_OLD")) {
+      // vertical segments: about ORBFE_PYRS_SEG rows each, shorter on the small levels so that a launch still brings a few
+      // thousand warps (a warp marches its rows one after the other: the launch cannot end before the longest march)
+      const int strips = (L.pyrWords + 31) / 32;
+      int segT = ORBFE_PYRS_SEG, minSeg = 16, wantWarps = 0;  // A/B on B200 (128 frames): forcing 3000 / 6000 / 12000 warps per launch -> 0.253 / 0.262 / 0.291 ms (0: 0.251)
+      if (const char* e = getenv("ORBFE_TUNE_PYR_SEG")) { const int v = atoi(e); if (v >= 8 && v <= 512) segT = v; }      // tuning only
+      if (const char* e = getenv("ORBFE_TUNE_PYR_WARPS")) { const int v = atoi(e); if (v >= 0) wantWarps = v; }           // tuning only
+      int segs = (L.h + segT - 1) / segT;
+      segs = std::max(segs, std::min((L.h + minSeg - 1) / minSeg, (wantWarps + strips * n - 1) / (strips * n)));
+      const int segH = (L.h + segs - 1) / segs;
+      const size_t warpBytes = ((size_t)ORBFE_PYRS_RING * L.pyrBoxW + (size_t)segH * sizeof(PyrRowLut) + 127) & ~(size_t)127;
+      const size_t smem = warpBytes * ORBFE_PYRS_WPC;
+      const int tasks = strips * segs;
+      ORBFE_LAUNCH(ex, k_pyramid_strip, dim3((tasks + ORBFE_PYRS_WPC - 1) / ORBFE_PYRS_WPC, n), dim3(ORBFE_PYRS_THREADS), smem, g, l, ex->d_pyr,
+                   ex->d_tmapsPyr, ex->d_rlut, ex->d_wlut, ex->d_pyrBoxX, segs);
+    } else if (L.fastResize) {
       // a strip is a chain of dependent loads: long strips (row re-use) only when the launch still fills
       // the GPU with warps several times over; otherwise short strips, more warps, less latency
       const int strips = (L.pyrWords + 31) / 32, ph = L.h + 2 * ORBFE_EDGE;

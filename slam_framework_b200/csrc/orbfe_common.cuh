@@ -53,6 +53,8 @@ struct LevelGeom {
   int tilesX, tilesY, tileBase;
   // pyramid tiling (rows of 4-px words)
   int pyrWords, pyrBlockBase, pyrBlocks;
+  // streaming resize (k_pyramid_strip): eligible, vertical segments, TMA box width (bytes), offset into the box-origin table
+  int pyrStrip, pyrSegs, pyrBoxW, pyrBoxOff;
   float scale;           // mvScaleFactor[level]
   float kpSize;          // (float)(int)(PATCH_SIZE*scale), orb_extractor.cpp:776
 };

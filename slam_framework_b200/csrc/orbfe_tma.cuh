@@ -136,6 +136,16 @@ __device__ __forceinline__ void orbfe_tile_issue(void* dst, unsigned long long* 
 #endif
 }
 
+// the same for a barrier that belongs to ONE warp of the CTA (each warp streams its own boxes): every lane of that warp
+__device__ __forceinline__ void orbfe_tile_wait_warp(unsigned long long* bar, unsigned parity) {
+#ifndef ORBFE_EMU
+  orbfe_mbar_wait(bar, parity);
+#else
+  (void)bar; (void)parity;
+  __syncwarp();
+#endif
+}
+
 // every thread that reads the tile; `parity` = number of completed phases of this barrier & 1
 __device__ __forceinline__ void orbfe_tile_wait(unsigned long long* bar, unsigned parity) {
 #ifndef ORBFE_EMU
