@@ -12,6 +12,9 @@
 #include <new>
 #include <sys/mman.h>
 
+// dropin/Makefile compiles this file too: the same entry points around the DROP-IN classes (dropin/orb_features/orb_extractor.h
+// is then the "orb_extractor.h" found first), on the same heap, so that both libraries run the reference's Frame / KeyFrame /
+// MapPoint / DBoW2 code in the same environment.
 // ---- a monotonic heap for everything this library allocates --------------------------------------------------------------
 // DistributeOctTree sorts pair<int, ExtractorNode*> (orb_extractor.cpp:625), so nodes of equal size are ordered by their HEAP
 // ADDRESS: with a general-purpose malloc that order depends on which freed chunks get reused.  This library is linked with
@@ -22,7 +25,11 @@
 namespace {
 char* g_base = nullptr;
 std::atomic<size_t> g_off(0);
-const size_t kArena = (size_t)1 << 36;  // virtual reservation, committed lazily
+#ifndef REF_ARENA_BITS
+#define REF_ARENA_BITS 36
+#endif
+const size_t kArena = (size_t)1 << REF_ARENA_BITS;  // virtual reservation, committed lazily (dropin/Makefile asks for less: both
+                                                    // libraries live in one test process)
 std::once_flag g_once;
 std::atomic<int> g_malloc_mode(0);  // > 0: plain malloc/free (throughput runs: the arena never reclaims memory)
 inline void* arena_alloc(size_t n) {  // thread-safe: Frame's stereo constructor extracts on two std::threads (frame.cpp:86-89)
@@ -49,13 +56,15 @@ static inline void* any_alloc(size_t n) {
   if (!p) throw std::bad_alloc();
   return p;
 }
-void* operator new(size_t n) { return any_alloc(n); }
-void* operator new[](size_t n) { return any_alloc(n); }
+// the replacements serve this library only: oracle/hide_new.map keeps them out of the dynamic symbol table
+#define REF_HIDDEN
+REF_HIDDEN void* operator new(size_t n) { return any_alloc(n); }
+REF_HIDDEN void* operator new[](size_t n) { return any_alloc(n); }
 extern "C" void ref_set_malloc_mode(int on) { g_malloc_mode.store(on); }
-void operator delete(void* p) noexcept { if (p && !in_arena(p)) free(p); }
-void operator delete[](void* p) noexcept { if (p && !in_arena(p)) free(p); }
-void operator delete(void* p, size_t) noexcept { if (p && !in_arena(p)) free(p); }
-void operator delete[](void* p, size_t) noexcept { if (p && !in_arena(p)) free(p); }
+REF_HIDDEN void operator delete(void* p) noexcept { if (p && !in_arena(p)) free(p); }
+REF_HIDDEN void operator delete[](void* p) noexcept { if (p && !in_arena(p)) free(p); }
+REF_HIDDEN void operator delete(void* p, size_t) noexcept { if (p && !in_arena(p)) free(p); }
+REF_HIDDEN void operator delete[](void* p, size_t) noexcept { if (p && !in_arena(p)) free(p); }
 
 typedef DBoW2::TemplatedVocabulary<DBoW2::FORB::TDescriptor, DBoW2::FORB> RefVocabulary;
 

@@ -47,8 +47,15 @@ cv::Mat make_K(float fx, float fy, float cx, float cy) {
   K.at<float>(0, 0) = fx; K.at<float>(1, 1) = fy; K.at<float>(0, 2) = cx; K.at<float>(1, 2) = cy;
   return K;
 }
-cv::Mat make_pose(const float* t) {  // identity rotation, translation t
+// rotation / Sim3 scale given to every pose that is built from a translation (ref_set_test_transform; identity and 1 by
+// default).  make_pose(nullptr) stays the identity: "seen from the origin".
+float g_rot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+float g_sim3_scale = 1.f;
+cv::Mat make_pose(const float* t) {  // rotation g_rot (identity unless set), translation t
   cv::Mat T = cv::Mat::eye(4, 4, CV_32F);
+  if (t)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) T.at<float>(r, c) = g_rot[3 * r + c];
   for (int i = 0; i < 3; ++i) T.at<float>(i, 3) = t ? t[i] : 0.f;
   return T;
 }
@@ -104,6 +111,11 @@ void* ref_frame_mono(const unsigned char* img, int w, int h, int nfeatures, floa
   return R;
 }
 void ref_frame_destroy(void* p) { delete static_cast<RefFrame*>(p); }
+// every pose / Sim3 the entry points below build from a translation gets this rotation (row-major 3x3) and Sim3 scale
+void ref_set_test_transform(const float* R9, float sim3_scale) {
+  for (int i = 0; i < 9; ++i) g_rot[i] = R9 ? R9[i] : (i % 4 == 0 ? 1.f : 0.f);
+  g_sim3_scale = sim3_scale > 0 ? sim3_scale : 1.f;
+}
 void ref_set_vocabulary(void* voc) { g_voc = static_cast<RefVoc*>(voc); }
 void ref_frame_set_translation(void* p, const float* t) { static_cast<RefFrame*>(p)->f()->SetPose(make_pose(t)); }
 int ref_frame_n(void* p) { return static_cast<RefFrame*>(p)->f()->NumKeypoints(); }
@@ -389,7 +401,12 @@ static void free_points(RefFrame* R, int n, const float* world_pos, const int* i
     max_out[i] = pts[i]->GetMaxDistanceInvariance();
   }
 }
-static cv::Mat make_sim3(const float* t) { return make_pose(t); }  // scale 1, identity rotation
+static cv::Mat make_sim3(const float* t) {  // [s R | t], s = 1 and R = I unless ref_set_test_transform changed them
+  cv::Mat S = make_pose(t);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) S.at<float>(r, c) = g_sim3_scale * g_rot[3 * r + c];
+  return S;
+}
 
 // OrbMatcher::SearchByProjection(KeyFrame*, cv::Mat Scw, vpPoints, vpMatched, th) (orb_matcher.cpp:384-497).  matched_in[k]
 // pre-fills vpMatched[k] with a foreign point; matched[k] (out) = index of the point this call wrote there, else -1.
@@ -485,8 +502,10 @@ int ref_search_by_sim3(void* pkf1, void* pkf2, const float* t12, float th, const
   std::vector<MapPoint*> m12((size_t)n1, nullptr);
   for (int i = 0; i < n1; ++i) if (pre_idx2 && pre_idx2[i] >= 0 && K2->pts[pre_idx2[i]]) m12[i] = K2->pts[pre_idx2[i]];
   cv::Mat R12 = cv::Mat::eye(3, 3, CV_32F);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) R12.at<float>(r, c) = g_rot[3 * r + c];
   OrbMatcher matcher(0.75f, true);
-  const int nf = matcher.SearchBySim3(K1->kf.get(), K2->kf.get(), m12, 1.0f, R12, make_vec3(t12), th);
+  const int nf = matcher.SearchBySim3(K1->kf.get(), K2->kf.get(), m12, g_sim3_scale, R12, make_vec3(t12), th);
   for (int i = 0; i < n1; ++i) {
     std::map<MapPoint*, int>::const_iterator it = index2.find(m12[i]);
     match12[i] = it == index2.end() ? -1 : it->second;

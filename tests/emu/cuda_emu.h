@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <vector>
 #include <sys/mman.h>
 
@@ -148,8 +149,12 @@ inline void warp_barrier() {
 
 constexpr size_t kStack = 128 * 1024;
 
+// launches from different host threads (Frame's stereo constructor extracts on two std::threads) run one after the other
+inline std::mutex& launch_mutex() { static std::mutex m; return m; }
+
 template <class F>
 void launch(dim3 grid, dim3 block, size_t smem, F&& f) {
+  std::lock_guard<std::mutex> serialise(launch_mutex());
   State& s = S();
   s.grid = grid; s.block = block;
   const int nthreads = (int)(block.x * block.y * block.z);

@@ -39,6 +39,8 @@ def lib():
         L.ref_frame_mono.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int] + [C.c_float] * 6
         L.ref_frame_mono.restype = vp
         L.ref_frame_destroy.argtypes = [vp]
+        L.ref_set_test_transform.argtypes = [vp, C.c_float]
+        L.ref_set_test_transform.restype = None
         L.ref_frame_set_translation.argtypes = [vp, vp]
         for fn in (L.ref_frame_n, L.ref_frame_n_right, L.ref_frame_levels):
             fn.argtypes = [vp]
@@ -70,6 +72,15 @@ def lib():
 
 def _p(a):
     return a.ctypes.data_as(vp) if a is not None else None
+
+
+def set_test_transform(R=None, sim3_scale=1.0):
+    """rotation (3x3) and Sim3 scale given to every pose the entry points build from a translation; None = identity"""
+    if R is None:
+        lib().ref_set_test_transform(None, float(sim3_scale))
+    else:
+        R = np.ascontiguousarray(R, np.float32).reshape(9)
+        lib().ref_set_test_transform(_p(R), float(sim3_scale))
 
 
 def extract(img, nfeatures=2000, scale=1.2, nlevels=8, ini_th=20, min_th=7):
