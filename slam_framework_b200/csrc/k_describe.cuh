@@ -283,6 +283,7 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
         val |= (unsigned)(tv[0] < tv[1]) << t;
       }
     } else {
+      __syncwarp();  // keeps the reads of the staged iteration k-1 ahead of the writes of iteration k+1 (same buffer parity)
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         int tv[2];

@@ -214,10 +214,8 @@ k_stereo_median(const StereoPair* __restrict__ pairs, const int maxKp, int* __re
   // count accepted matches
   int c = 0;
   for (int i = tid; i < nL; i += ORBFE_ST_THREADS) c += P.sad[i] >= 0;
-  const int total = __syncthreads_count(0) * 0 + 0;  // placeholder to keep barrier structure uniform
-  (void)total;
   // block sum of c via histogram slot 0
-  if (tid < 256) s_hist[tid] = 0;
+  for (int b = tid; b < 256; b += ORBFE_ST_THREADS) s_hist[b] = 0;
   __syncthreads();
   if (c) atomicAdd(&s_hist[0], c);
   __syncthreads();
@@ -229,7 +227,7 @@ k_stereo_median(const StereoPair* __restrict__ pairs, const int maxKp, int* __re
   }
   const int rank = size / 2;  // element size/2 of the ascending sort
   // pass 1: high byte of the 16-bit SAD (SAD <= 121*510 = 61710 < 65536)
-  if (tid < 256) s_hist[tid] = 0;
+  for (int b = tid; b < 256; b += ORBFE_ST_THREADS) s_hist[b] = 0;
   __syncthreads();
   for (int i = tid; i < nL; i += ORBFE_ST_THREADS) {
     const int s = P.sad[i];
@@ -244,7 +242,7 @@ k_stereo_median(const StereoPair* __restrict__ pairs, const int maxKp, int* __re
   __syncthreads();
   const int hiBin = s_sel[0], rank2 = s_sel[1];
   __syncthreads();
-  if (tid < 256) s_hist[tid] = 0;
+  for (int b = tid; b < 256; b += ORBFE_ST_THREADS) s_hist[b] = 0;
   __syncthreads();
   for (int i = tid; i < nL; i += ORBFE_ST_THREADS) {
     const int s = P.sad[i];
@@ -267,7 +265,7 @@ k_stereo_median(const StereoPair* __restrict__ pairs, const int maxKp, int* __re
     else ++kept;
   }
   __syncthreads();
-  if (tid < 256) s_hist[tid] = 0;
+  for (int b = tid; b < 256; b += ORBFE_ST_THREADS) s_hist[b] = 0;
   __syncthreads();
   if (kept) atomicAdd(&s_hist[0], kept);
   __syncthreads();

@@ -501,10 +501,10 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   CUDA_TRY(cudaMemsetAsync(ex->d_nMatched, 0, S * sizeof(int), ex->stream));
   CUDA_TRY(cudaStreamSynchronize(ex->stream));  // `lut` goes out of scope
 #ifndef ORBFE_EMU
-  CUDA_TRY(cudaFuncSetAttribute(k_fast_cells<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
-  CUDA_TRY(cudaFuncSetAttribute(k_fast_cells<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fastSmem));
-  CUDA_TRY(cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octSmem));
-  CUDA_TRY(cudaFuncSetAttribute(k_stereo_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->rowSmem));
+  CUDA_TRY(orbfe_raise_dynamic_smem(k_fast_cells<true>, ex->device, ex->fastSmem));
+  CUDA_TRY(orbfe_raise_dynamic_smem(k_fast_cells<false>, ex->device, ex->fastSmem));
+  CUDA_TRY(orbfe_raise_dynamic_smem(k_octree, ex->device, ex->octSmem));
+  CUDA_TRY(orbfe_raise_dynamic_smem(k_stereo_rows, ex->device, ex->rowSmem));
 #endif
   ex->configured = true;
   return ORBFE_OK;
@@ -1054,6 +1054,14 @@ int orbfe_stereo_match(orbfe_extractor* left, orbfe_extractor* right, int n_left
   const Geom& g = left->g;
   if (n_left > g.totalOut || n_right > right->g.totalOut)
     return orbfe_fail(ORBFE_ERR_INVALID, "more keypoints than one image can produce (%d/%d > %d)", n_left, n_right, g.totalOut);
+  // the kernels index the level geometry with keypoint.octave: a keypoint of another detector (octave -1, or more levels than
+  // this handle has) must not reach them
+  for (int i = 0; i < n_left; ++i)
+    if (kps_left[i].octave < 0 || kps_left[i].octave >= g.nlevels)
+      return orbfe_fail(ORBFE_ERR_INVALID, "left keypoint %d: octave %d outside [0, %d)", i, kps_left[i].octave, g.nlevels);
+  for (int i = 0; i < n_right; ++i)
+    if (kps_right[i].octave < 0 || kps_right[i].octave >= g.nlevels)
+      return orbfe_fail(ORBFE_ERR_INVALID, "right keypoint %d: octave %d outside [0, %d)", i, kps_right[i].octave, g.nlevels);
   CUDA_TRY(cudaSetDevice(left->device));
   CUDA_TRY(cudaStreamSynchronize(right->stream));  // right pyramid complete
   CUDA_TRY(cudaStreamSynchronize(left->stream));

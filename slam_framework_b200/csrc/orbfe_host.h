@@ -19,3 +19,24 @@ struct OrbfeSlotView {
   float scale[16];
 };
 int orbfe_internal_slot_view(orbfe_extractor* ex, int slot, OrbfeSlotView* out);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel, shared by every handle and thread of the
+// process: it is only ever RAISED (a handle with a smaller geometry must not lower the limit a live handle launches with), under
+// a lock, and the call is skipped when the recorded maximum already covers the request.
+#ifndef ORBFE_EMU
+#include <cuda_runtime.h>
+#include <map>
+#include <mutex>
+#include <utility>
+template <class K>
+static inline cudaError_t orbfe_raise_dynamic_smem(K kernel, int device, size_t bytes) {
+  static std::mutex m;
+  static std::map<std::pair<const void*, int>, size_t> have;
+  std::lock_guard<std::mutex> lock(m);
+  size_t& cur = have[std::make_pair((const void*)kernel, device)];
+  if (bytes <= cur) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
+#endif

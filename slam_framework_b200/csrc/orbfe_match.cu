@@ -165,7 +165,8 @@ static int run_search(orbfe_frame* f, const HostQueries& Q, const SearchSpec& sp
   if (Q.hasObs) CUDA_TRY(cudaMemcpyAsync(f->d_qHasObs, Q.hasObs, (size_t)nq, cudaMemcpyHostToDevice, st));
   if (occupied) CUDA_TRY(cudaMemcpyAsync(f->d_occ, occupied, (size_t)f->n, cudaMemcpyHostToDevice, st));
 #ifndef ORBFE_EMU
-  CUDA_TRY(cudaFuncSetAttribute(k_match_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // k_match_resolve (and its dynamic shared memory) is only launched for SearchForInitialization
+  if (mode == ORBFE_MODE_INIT) CUDA_TRY(orbfe_raise_dynamic_smem(k_match_resolve, f->device, smem));
 #endif
   const bool jacobi = mode != ORBFE_MODE_INIT;
   const bool initJacobi = mode == ORBFE_MODE_INIT && f->n < (1 << 22) && nq > 0;  // parallel SearchForInitialization (k_init_iterate)
