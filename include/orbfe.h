@@ -161,6 +161,11 @@ int orbfe_frame_create(int device, int n, const orbfe_keypoint* kps_un, const ui
                        const float* u_right, float min_x, float max_x, float min_y, float max_y,
                        int nlevels, const float* scale_factors, orbfe_frame** out);
 int orbfe_frame_destroy(orbfe_frame* f);
+/* Destroyed frame handles keep their stream, device arrays and pinned staging and are recycled by the next
+ * orbfe_frame_create / orbfe_frame_from_extractor on the same device (Tracking builds one view per frame: frame.cpp:61-111 runs
+ * per frame; a steady-state frame then allocates nothing).  At most 16 idle handles are kept; this call frees them and
+ * returns how many it freed.  Live handles are not touched. */
+int orbfe_frame_pool_trim(void);
 /* The same handle built from the DEVICE-resident results of extractor slot `slot` (after orbfe_run / orbfe_extract; with
  * use_stereo the slot's stereo coordinates from orbfe_run_stereo / orbfe_stereo_match are taken as StereoCoordRight()):
  * keypoints and descriptors go device to device.  Only for cameras whose undistortion is the identity (Frame::

@@ -2,7 +2,21 @@
 // OrbMatcher classes (src/data/*.cpp, src/orb_features/orb_matcher.cpp), compiled unmodified from /root/reference into
 // oracle/_ref/libslam_ref.so by oracle/Makefile.ref.  Nothing here restates reference logic: the wrappers build the reference's
 // objects from test inputs, call the reference's functions and copy the results out.
+#include <opencv2/core/core.hpp>
+#include <deque>
+#include <list>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+// Frame::mbInitialComputations (frame.h:218, private static) gates the once-per-process MakeInitialComputations (image bounds,
+// grid cell sizes, intrinsics); ref_set_test_distortion must re-arm it when it changes the calibration.  Access only: the
+// reference sources themselves are compiled unmodified and the data layout does not depend on access specifiers.
+#define private public
 #include "data/frame.h"
+#undef private
 #include "data/keyframe.h"
 #include "data/map.h"
 #include "data/map_point.h"
@@ -49,6 +63,7 @@ cv::Mat make_K(float fx, float fy, float cx, float cy) {
 }
 // rotation / Sim3 scale given to every pose that is built from a translation (ref_set_test_transform; identity and 1 by
 // default).  make_pose(nullptr) stays the identity: "seen from the origin".
+float g_dist[4] = {0, 0, 0, 0};   // k1 k2 p1 p2 given to every Frame constructed below (ref_set_test_distortion)
 float g_rot[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 float g_sim3_scale = 1.f;
 cv::Mat make_pose(const float* t) {  // rotation g_rot (identity unless set), translation t
@@ -85,6 +100,7 @@ void* ref_frame_stereo(const unsigned char* left, const unsigned char* right, in
   R->map = std::make_shared<Map>();
   cv::Mat imL(h, w, CV_8UC1, const_cast<unsigned char*>(left)), imR(h, w, CV_8UC1, const_cast<unsigned char*>(right));
   cv::Mat K = make_K(fx, fy, cx, cy), D = cv::Mat::zeros(4, 1, CV_32F);
+  for (int i = 0; i < 4; ++i) D.at<float>(i) = g_dist[i];
   for (int pass = 0; pass < 2; ++pass) {
     if (pass) R->f()->~Frame();
     new (R->storage) Frame(imL, imR, 0.0, R->exL, R->exR, voc_ptr(), K, D, bf, th_depth);
@@ -104,6 +120,7 @@ void* ref_frame_mono(const unsigned char* img, int w, int h, int nfeatures, floa
   R->map = std::make_shared<Map>();
   cv::Mat im(h, w, CV_8UC1, const_cast<unsigned char*>(img));
   cv::Mat K = make_K(fx, fy, cx, cy), D = cv::Mat::zeros(4, 1, CV_32F);
+  for (int i = 0; i < 4; ++i) D.at<float>(i) = g_dist[i];
   new (R->storage) Frame(im, 0.0, R->exL, voc_ptr(), K, D, bf, th_depth);
   R->live = true;
   R->f()->SetPose(make_pose(nullptr));
@@ -115,6 +132,12 @@ void ref_frame_destroy(void* p) { delete static_cast<RefFrame*>(p); }
 void ref_set_test_transform(const float* R9, float sim3_scale) {
   for (int i = 0; i < 9; ++i) g_rot[i] = R9 ? R9[i] : (i % 4 == 0 ? 1.f : 0.f);
   g_sim3_scale = sim3_scale > 0 ? sim3_scale : 1.f;
+}
+// distortion coefficients (k1 k2 p1 p2; null = none) of every Frame built from now on: the k1 != 0 paths of
+// Frame::UndistortKeyPoints (frame.cpp:614-641) and Frame::ComputeImageBounds (:644-673)
+void ref_set_test_distortion(const float* d4) {
+  for (int i = 0; i < 4; ++i) g_dist[i] = d4 ? d4[i] : 0.f;
+  Frame::mbInitialComputations = true;   // the next Frame recomputes bounds / grid / intrinsics (frame.cpp:100-103)
 }
 void ref_set_vocabulary(void* voc) { g_voc = static_cast<RefVoc*>(voc); }
 void ref_frame_set_translation(void* p, const float* t) { static_cast<RefFrame*>(p)->f()->SetPose(make_pose(t)); }

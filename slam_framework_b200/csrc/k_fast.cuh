@@ -97,18 +97,12 @@ __device__ __forceinline__ unsigned orbfe_fast_colmask(const int wx, const int c
   return (0x80808080u >> (8 * (4 - hi))) & (0x80808080u << (8 * lo));
 }
 
-// warp-aggregated reservation of `cnt` queue slots per lane: returns this lane's first slot
+// warp-aggregated reservation of the warp's queue slots: returns the warp's first slot (warp-uniform)
 __device__ __forceinline__ int orbfe_fast_reserve(const int cnt, int* counter, const int lane) {
-  int inc = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
+  const int total = __reduce_add_sync(0xffffffffu, cnt);
   int base = 0;
-  if (lane == 31 && inc > 0) base = atomicAdd(counter, inc);
-  base = __shfl_sync(0xffffffffu, base, 31);
-  return base + inc - cnt;
+  if (lane == 0 && total > 0) base = atomicAdd(counter, total);
+  return __shfl_sync(0xffffffffu, base, 0);
 }
 
 struct FastSmemLayout {
@@ -125,15 +119,24 @@ __host__ __device__ __forceinline__ FastSmemLayout orbfe_fast_layout(const int m
 }
 
 // step 2: a flag register of a thread (items kBase .. kBase + 7; bit 8b + 7 - (k & 7) = byte b of item k; item k = 2 * it + j
-// is the word (row 3 + wid + WARPS * it, column wLo + lane + 32 j)) -> queue codes y << 8 | x from `pos` on
+// is the word (row 3 + wid + WARPS * it, column wLo + lane + 32 j)) -> queue codes y << 8 | x from the warp's slot `pos` on.
+// ROUND-MAJOR order: in every pass each lane that still has a flag contributes ONE entry, so that 32 consecutive queue
+// entries come from (nearly) 32 different lanes = 32 different word columns = 32 different shared-memory banks.  The score
+// step gathers 16 ring bytes per entry; with the tile pitch a multiple of 128 bytes the bank of a pixel depends on its column
+// only, and the lane-major order this replaces (all flags of lane 0, then lane 1, ...) put up to 8 pixels of one column into
+// one warp of the score loop (47 M bank conflicts per 128 frames, shared-memory pipe at 67 %).  Returns the warp's next slot.
 __device__ __forceinline__ int orbfe_fast_unpack(unsigned acc, const int kBase, int pos, const int cap, unsigned short* q,
-                                                 const unsigned baseCode) {
-  while (acc) {
-    const int p = __ffs((int)acc) - 1;
-    acc &= acc - 1;
-    const int k = kBase + 7 - (p & 7);
-    if (pos < cap) q[pos] = (unsigned short)(baseCode + (k >> 1) * (ORBFE_FAST_WARPS << 8) + ((k & 1) << 7) + (p >> 3));
-    ++pos;
+                                                 const unsigned baseCode, const unsigned ltMask) {
+  unsigned any;
+  while ((any = __ballot_sync(0xffffffffu, acc != 0u)) != 0u) {
+    if (acc) {
+      const int p = __ffs((int)acc) - 1;
+      acc &= acc - 1;
+      const int k = kBase + 7 - (p & 7);
+      const int slot = pos + __popc(any & ltMask);
+      if (slot < cap) q[slot] = (unsigned short)(baseCode + (k >> 1) * (ORBFE_FAST_WARPS << 8) + ((k & 1) << 7) + (p >> 3));
+    }
+    pos += __popc(any);
   }
   return pos;
 }
@@ -284,7 +287,7 @@ k_fast_cells(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, co
       for (int q = 0; q < ORBFE_FAST_NACC; ++q) cntA += __popc(fa[q]);
       int pos = orbfe_fast_reserve(cntA, qn1, lane);
 #pragma unroll
-      for (int q = 0; q < ORBFE_FAST_NACC; ++q) pos = orbfe_fast_unpack(fa[q], 8 * q, pos, q1Cap, q1, baseCode);
+      for (int q = 0; q < ORBFE_FAST_NACC; ++q) pos = orbfe_fast_unpack(fa[q], 8 * q, pos, q1Cap, q1, baseCode, (1u << lane) - 1u);
     }
     __syncthreads();
     // ---- 3. exact score; corner at th <=> score >= th.  Corners -> score plane + Q2 (warp ballot)

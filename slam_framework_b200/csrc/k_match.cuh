@@ -17,6 +17,9 @@
 //                     consistency check (ComputeThreeMaxima :1584-1625).
 #pragma once
 #include "orbfe_common.cuh"
+#ifndef ORBFE_EMU
+#include <cooperative_groups.h>
+#endif
 
 #define ORBFE_GRID_COLS 64   // frame.h:104
 #define ORBFE_GRID_ROWS 48   // frame.h:105
@@ -132,11 +135,9 @@ __device__ __forceinline__ bool orbfe_window_cells(const FrameGrid& F, float x, 
 // ---- phase A: ordered candidates + distances, one warp per query ----------------------------------
 #define ORBFE_MATCH_THREADS 128
 
-__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
-k_match_candidates(const FrameGrid F, const MatchQueries Q, const MatchScratch S) {
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
-  if (q >= Q.n) return;
+// one query, one warp (q < Q.n, warp-uniform)
+__device__ __forceinline__ void orbfe_candidates_query(const FrameGrid& F, const MatchQueries& Q, const MatchScratch& S, const int q,
+                                                       const int lane) {
   int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
   const float x = Q.x[q], y = Q.y[q], r = Q.r[q];
   const bool live = Q.valid[q] && orbfe_window_cells(F, x, y, r, x0, x1, y0, y1);
@@ -205,6 +206,13 @@ k_match_candidates(const FrameGrid F, const MatchQueries Q, const MatchScratch S
     }
   }
   if (lane == 0) { S.qOff[q] = base; S.qCnt[q] = count; }
+}
+
+__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
+k_match_candidates(const FrameGrid F, const MatchQueries Q, const MatchScratch S) {
+  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
+  if (q >= Q.n) return;
+  orbfe_candidates_query(F, Q, S, q, threadIdx.x & 31);
 }
 
 // ---- phase B: serial-order resolve, one warp ------------------------------------------------------
@@ -387,13 +395,21 @@ struct BowFilter {
   float ex, ey;             // epipole in the second image (:643-649)
 };
 
-__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
-k_match_candidates_bow(const FrameGrid F, const uint8_t* __restrict__ qDescAll, const int* __restrict__ qDescIdx,
-                       const unsigned* __restrict__ featIdx, const int* __restrict__ qSrcOff, const int nQ,
-                       const MatchScratch S, const BowFilter B) {
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
-  if (q >= nQ) return;
+struct BowQueries {          // vocabulary-node searches: where a query's descriptor and candidate list come from
+  const uint8_t* qDescAll;   // all side-1 descriptors
+  const int* qDescIdx;       // per query: row of qDescAll
+  const unsigned* featIdx;   // the searched frame's flattened feature-vector indices
+  const int* qSrcOff;        // per query: first entry of its node's list in featIdx
+  int nQ;
+};
+
+// one query, one warp (q < BQ.nQ, warp-uniform)
+__device__ __forceinline__ void orbfe_candidates_bow_query(const FrameGrid& F, const BowQueries& BQ, const MatchScratch& S,
+                                                           const BowFilter& B, const int q, const int lane) {
+  const uint8_t* qDescAll = BQ.qDescAll;
+  const int* qDescIdx = BQ.qDescIdx;
+  const unsigned* featIdx = BQ.featIdx;
+  const int* qSrcOff = BQ.qSrcOff;
   const int cnt = S.qCnt[q], off = S.qOff[q], src = qSrcOff[q];
   const uint8_t* qd = qDescAll + (size_t)qDescIdx[q] * 32;
   const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(qd)), a1 = __ldg(reinterpret_cast<const uint4*>(qd) + 1);
@@ -435,6 +451,13 @@ k_match_candidates_bow(const FrameGrid F, const uint8_t* __restrict__ qDescAll, 
   }
 }
 
+__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
+k_match_candidates_bow(const FrameGrid F, const BowQueries BQ, const MatchScratch S, const BowFilter B) {
+  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
+  if (q >= BQ.nQ) return;
+  orbfe_candidates_bow_query(F, BQ, S, B, q, threadIdx.x & 31);
+}
+
 // SearchBySim3 agreement check (orb_matcher.cpp:1291-1307): match12[i1] = idx2 iff vnMatch1[i1] == idx2 and
 // vnMatch2[idx2] == i1
 __global__ void __launch_bounds__(256)
@@ -466,16 +489,9 @@ struct JacobiState {
   int* changed;   // per-iteration "some query changed its answer" flags
 };
 
-__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
-k_match_iterate(const ResolveArgs A, const MatchScratch S, const JacobiState J, const int t) {
-  if (S.cursor[1]) return;                       // candidate buffer overflowed: the host re-runs
-  if (t > 0 && J.changed[t - 1] == 0) return;    // converged
-  const int lane = threadIdx.x & 31;
-  const int gtid = blockIdx.x * ORBFE_MATCH_THREADS + threadIdx.x, gsz = gridDim.x * ORBFE_MATCH_THREADS;
-  int* ownClear = J.own + (size_t)((t + 2) % 3) * A.nKp;   // becomes the write target of iteration t+1
-  for (int i = gtid; i < A.nKp; i += gsz) ownClear[i] = 0x7f7f7f7f;
-  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
-  if (q >= A.nQ) return;
+// iteration t of query q, one warp (q < A.nQ, warp-uniform); raises *changed when the query's answer differs from iteration t-1
+__device__ __forceinline__ void orbfe_iterate_query(const ResolveArgs& A, const MatchScratch& S, const JacobiState& J, const int t,
+                                                    const int q, const int lane, int* changed) {
   const int* ownPrev = J.own + (size_t)(t % 3) * A.nKp;
   int* ownNext = J.own + (size_t)((t + 1) % 3) * A.nKp;
   const int cnt = S.qCnt[q], off = S.qOff[q];
@@ -483,7 +499,7 @@ k_match_iterate(const ResolveArgs A, const MatchScratch S, const JacobiState J, 
   for (int c = lane; c < cnt; c += 32) {
     const uint2 cd = S.cand[off + c];
     const int dist = (int)(cd.y & 0xffffu);
-    if (dist < 256 && !(A.occupiedIn && A.occupiedIn[cd.x]) && !(ownPrev[cd.x] < q)) {
+    if (dist < 256 && !(A.occupiedIn && A.occupiedIn[cd.x]) && !(__ldcg(ownPrev + cd.x) < q)) {  // L2: other SMs wrote it
       const unsigned key = ((unsigned)dist << 20) | (unsigned)(A.tieLast ? 0xfffff - c : c);
       if (key < best) { second = best; best = key; } else if (key < second) second = key;
     }
@@ -511,19 +527,30 @@ k_match_iterate(const ResolveArgs A, const MatchScratch S, const JacobiState J, 
     }
     if (accept) newBest = (int)bc.x;
   }
-  if (t == 0 || newBest != J.best[q]) { J.best[q] = newBest; J.changed[t] = 1; }
+  if (t == 0 || newBest != J.best[q]) { J.best[q] = newBest; *changed = 1; }
   if (newBest >= 0 && (A.feedback == ORBFE_FEEDBACK_ALL || (A.feedback == ORBFE_FEEDBACK_HASOBS && A.hasObs[q])))
     atomicMin(&ownNext[newBest], q);
 }
 
+__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
+k_match_iterate(const ResolveArgs A, const MatchScratch S, const JacobiState J, const int t) {
+  if (S.cursor[1]) return;                       // candidate buffer overflowed: the host re-runs
+  if (t > 0 && J.changed[t - 1] == 0) return;    // converged
+  const int gtid = blockIdx.x * ORBFE_MATCH_THREADS + threadIdx.x, gsz = gridDim.x * ORBFE_MATCH_THREADS;
+  int* ownClear = J.own + (size_t)((t + 2) % 3) * A.nKp;   // becomes the write target of iteration t+1
+  for (int i = gtid; i < A.nKp; i += gsz) ownClear[i] = 0x7f7f7f7f;
+  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
+  if (q >= A.nQ) return;
+  orbfe_iterate_query(A, S, J, t, q, threadIdx.x & 31, J.changed + t);
+}
+
 // after convergence: F.SetMapPoint results (the LAST accepted query on a keypoint wins), the match count and
 // the rotation-consistency check (one CTA)
-__global__ void __launch_bounds__(1024)
-k_match_finalize(const ResolveArgs A, const MatchScratch S, const JacobiState J) {
+// one CTA (any size)
+__device__ __forceinline__ void orbfe_match_finalize_block(const ResolveArgs& A, const JacobiState& J) {
   __shared__ int s_hist[ORBFE_HISTO_LENGTH];
   __shared__ int s_ind[3];
   __shared__ int s_n;
-  if (S.cursor[1]) return;
   const int tid = threadIdx.x, T = blockDim.x;
   if (!A.perQuery)
     for (int i = tid; i < A.nKp; i += T) A.out[i] = -1;
@@ -581,6 +608,12 @@ k_match_finalize(const ResolveArgs A, const MatchScratch S, const JacobiState J)
   if (tid == 0) A.result[0] = s_n;
 }
 
+__global__ void __launch_bounds__(1024)
+k_match_finalize(const ResolveArgs A, const MatchScratch S, const JacobiState J) {
+  if (S.cursor[1]) return;
+  orbfe_match_finalize_block(A, J);
+}
+
 // ---- SearchForInitialization, parallel form (orb_matcher.cpp:264-382) ----------------------------------------------------
 // The coupling between queries is vMatchedDistance: query q skips a candidate c when an EARLIER accepted query q' < q took c
 // at a distance <= dist(q, c) (:306-307; every accept on c lowers vMatchedDistance[c], so the value q sees is the minimum over
@@ -598,16 +631,8 @@ struct InitJacobi {
   int* overflow;
 };
 
-__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
-k_init_iterate(const ResolveArgs A, const MatchScratch S, const InitJacobi J, const int t) {
-  if (S.cursor[1]) return;
-  if (t > 0 && J.changed[t - 1] == 0) return;
-  const int lane = threadIdx.x & 31;
-  const int gtid = blockIdx.x * ORBFE_MATCH_THREADS + threadIdx.x, gsz = gridDim.x * ORBFE_MATCH_THREADS;
-  int* cntClear = J.cnt + (size_t)((t + 2) % 3) * A.nKp;
-  for (int i = gtid; i < A.nKp; i += gsz) cntClear[i] = 0;
-  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
-  if (q >= A.nQ) return;
+__device__ __forceinline__ void orbfe_init_iterate_query(const ResolveArgs& A, const MatchScratch& S, const InitJacobi& J, const int t,
+                                                         const int q, const int lane, int* changed) {
   const int* cntPrev = J.cnt + (size_t)(t % 3) * A.nKp;
   const uint2* slotPrev = J.slots + (size_t)(t % 3) * A.nKp * ORBFE_INIT_SLOTS;
   int* cntNext = J.cnt + (size_t)((t + 1) % 3) * A.nKp;
@@ -618,9 +643,9 @@ k_init_iterate(const ResolveArgs A, const MatchScratch S, const InitJacobi J, co
     const uint2 cd = S.cand[off + c];
     const int dist = (int)(cd.y & 0xffffu);
     int matched = 0x7fffffff;  // vMatchedDistance[i2] as query q sees it
-    const int na = min(cntPrev[cd.x], ORBFE_INIT_SLOTS);
+    const int na = min(__ldcg(cntPrev + cd.x), ORBFE_INIT_SLOTS);  // L2: other SMs wrote it
     for (int k = 0; k < na; ++k) {
-      const uint2 a = slotPrev[(size_t)cd.x * ORBFE_INIT_SLOTS + k];
+      const uint2 a = __ldcg(slotPrev + (size_t)cd.x * ORBFE_INIT_SLOTS + k);
       if ((int)a.x < q) matched = min(matched, (int)a.y);
     }
     if (!(matched <= dist)) {
@@ -647,17 +672,27 @@ k_init_iterate(const ResolveArgs A, const MatchScratch S, const InitJacobi J, co
       else *J.overflow = 1;
     }
   }
-  if (t == 0 || acc != J.acc[q]) { J.acc[q] = acc; J.changed[t] = 1; }
+  if (t == 0 || acc != J.acc[q]) { J.acc[q] = acc; *changed = 1; }
+}
+
+__global__ void __launch_bounds__(ORBFE_MATCH_THREADS)
+k_init_iterate(const ResolveArgs A, const MatchScratch S, const InitJacobi J, const int t) {
+  if (S.cursor[1]) return;
+  if (t > 0 && J.changed[t - 1] == 0) return;
+  const int gtid = blockIdx.x * ORBFE_MATCH_THREADS + threadIdx.x, gsz = gridDim.x * ORBFE_MATCH_THREADS;
+  int* cntClear = J.cnt + (size_t)((t + 2) % 3) * A.nKp;
+  for (int i = gtid; i < A.nKp; i += gsz) cntClear[i] = 0;
+  const int q = blockIdx.x * (ORBFE_MATCH_THREADS / 32) + (threadIdx.x >> 5);
+  if (q >= A.nQ) return;
+  orbfe_init_iterate_query(A, S, J, t, q, threadIdx.x & 31, J.changed + t);
 }
 
 // after convergence: vnMatches12 (the LAST accepted query on a keypoint owns it, :325-333), nmatches, rotation check (:339-374;
 // the histogram counts every accept, stolen ones included, exactly as rotHist does)
-__global__ void __launch_bounds__(1024)
-k_init_finalize(const ResolveArgs A, const MatchScratch S, const InitJacobi J, int* __restrict__ owner) {
+__device__ __forceinline__ void orbfe_init_finalize_block(const ResolveArgs& A, const InitJacobi& J, int* __restrict__ owner) {
   __shared__ int s_hist[ORBFE_HISTO_LENGTH];
   __shared__ int s_ind[3];
   __shared__ int s_n;
-  if (S.cursor[1] || *J.overflow) return;
   const int tid = threadIdx.x, T = blockDim.x;
   for (int i = tid; i < A.nKp; i += T) owner[i] = -1;
   for (int q = tid; q < A.nQ; q += T) A.out[q] = -1;
@@ -713,6 +748,76 @@ k_init_finalize(const ResolveArgs A, const MatchScratch S, const InitJacobi J, i
   }
   if (tid == 0) A.result[0] = s_n;
 }
+
+__global__ void __launch_bounds__(1024)
+k_init_finalize(const ResolveArgs A, const MatchScratch S, const InitJacobi J, int* __restrict__ owner) {
+  if (S.cursor[1] || *J.overflow) return;
+  orbfe_init_finalize_block(A, J, owner);
+}
+
+#ifndef ORBFE_EMU
+// ---- the whole search in ONE cooperative launch ------------------------------------------------------------------------
+// candidates -> grid barrier -> Jacobi iterations to the fixed point (one grid barrier each) -> finalize (CTA 0).  The grid
+// is persistent (at most what is co-resident); warps stride over the queries.  No host round trip between the phases: the
+// host enqueues one H2D copy of the packed queries, this kernel, and the D2H copy of the result.
+struct SolveCfg {
+  int bow;        // candidates from vocabulary nodes (BowQueries) instead of grid windows
+  int init;       // SearchForInitialization coupling (InitJacobi) instead of the occupancy feedback (JacobiState)
+  int* flags;     // 3 rotating "some query changed" flags
+  int* iowner;    // init: per-keypoint owner scratch
+};
+#define ORBFE_SOLVE_THREADS 512
+
+__global__ void __launch_bounds__(ORBFE_SOLVE_THREADS)
+k_match_solve(const FrameGrid F, const MatchQueries Q, const BowQueries BQ, const BowFilter B, const MatchScratch S, const ResolveArgs A,
+              const JacobiState J, const InitJacobi IJ, const SolveCfg C) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int lane = threadIdx.x & 31;
+  const int gtid = blockIdx.x * ORBFE_SOLVE_THREADS + threadIdx.x, gsz = gridDim.x * ORBFE_SOLVE_THREADS;
+  const int gwarp = gtid >> 5, nwarps = gsz >> 5;
+  const int nQ = A.nQ;
+  // state of iteration 0: "no owners / no acceptors" in the buffers iteration 0 reads (0) and writes (1)
+  if (C.init) {
+    for (int i = gtid; i < 2 * A.nKp; i += gsz) IJ.cnt[i] = 0;
+  } else {
+    for (int i = gtid; i < 2 * A.nKp; i += gsz) J.own[i] = 0x7f7f7f7f;
+  }
+  if (gtid < 3) C.flags[gtid] = 0;
+  if (gtid == 0 && C.init) *IJ.overflow = 0;
+  if (C.bow) {
+    for (int q = gwarp; q < nQ; q += nwarps) orbfe_candidates_bow_query(F, BQ, S, B, q, lane);
+  } else {
+    for (int q = gwarp; q < nQ; q += nwarps) orbfe_candidates_query(F, Q, S, q, lane);
+  }
+  grid.sync();
+  if (*reinterpret_cast<volatile int*>(S.cursor + 1)) return;   // candidate buffer too small (grid-uniform): the host grows it and re-runs
+  const bool coupled = C.init || A.feedback != ORBFE_FEEDBACK_NONE;
+  for (int t = 0; t <= nQ; ++t) {
+    int* changed = C.flags + t % 3;
+    if (gtid == 0) C.flags[(t + 1) % 3] = 0;
+    if (C.init) {
+      int* cntClear = IJ.cnt + (size_t)((t + 2) % 3) * A.nKp;
+      for (int i = gtid; i < A.nKp; i += gsz) cntClear[i] = 0;
+      for (int q = gwarp; q < nQ; q += nwarps) orbfe_init_iterate_query(A, S, IJ, t, q, lane, changed);
+    } else {
+      int* ownClear = J.own + (size_t)((t + 2) % 3) * A.nKp;
+      for (int i = gtid; i < A.nKp; i += gsz) ownClear[i] = 0x7f7f7f7f;
+      for (int q = gwarp; q < nQ; q += nwarps) orbfe_iterate_query(A, S, J, t, q, lane, changed);
+    }
+    if (!coupled) break;     // independent queries: one evaluation is the answer
+    grid.sync();
+    if (*reinterpret_cast<volatile int*>(changed) == 0) break;   // fixed point (grid-uniform)
+  }
+  if (!coupled) grid.sync();
+  if (blockIdx.x != 0) return;
+  if (C.init) {
+    if (*reinterpret_cast<volatile int*>(IJ.overflow)) return;   // the host falls back to the serial resolve
+    orbfe_init_finalize_block(A, IJ, C.iowner);
+  } else {
+    orbfe_match_finalize_block(A, J);
+  }
+}
+#endif
 
 // ---- OrbMatcher::DescriptorDistance, batched (orb_matcher.cpp:1630-1646) --------------------------
 __global__ void __launch_bounds__(256)

@@ -95,7 +95,7 @@ struct orbfe_extractor {
   int rowCap = 0;
   size_t rowSmem = 0;
   // pinned staging
-  int* h_n = nullptr;          // S counts + S matched + 1 err
+  int* h_n = nullptr;          // S counts + S matched + 1 err + 2 scratch (orbfe_stereo_match)
   orbfe_kp_dev* h_kps = nullptr;
   uint8_t* h_desc = nullptr;
   float* h_uR = nullptr;
@@ -106,7 +106,15 @@ struct orbfe_extractor {
   unsigned char stageHas[64] = {};  // 1 = extract recorded, 2 = stereo recorded too
   int stageRuns = 0;                // runs recorded since the last summary
   int pairsCached = 0;              // d_pairs holds the same-handle table for this many pairs
+  // single-frame / single-pair calls (orbfe_extract, orbfe_extract_batch with <= 2 images): the whole sequence
+  // H2D -> 15 kernels -> D2H is captured ONCE per geometry into a CUDA graph and replayed per frame (one launch call)
+  uint8_t* h_img = nullptr;         // pinned staging of <= 2 input frames (graph memcpy nodes need a fixed source)
+#ifndef ORBFE_EMU
+  cudaGraphExec_t xGraph[2][4] = {};  // [n_imgs - 1][kps | desc << 1]
+  int xGraphLaunches[2][4] = {};
+#endif
   bool stageTiming = false;
+  bool slotDirty = true;            // the device keypoint rows are NOT what h_n / h_kps / h_desc hold (no download yet, or overwritten)
   long long launches = 0;
 };
 
@@ -157,6 +165,12 @@ static void free_arena(orbfe_extractor* ex) {
   ex->d_rowStart = nullptr; ex->d_rowItems = nullptr;
   cudaFreeHost(ex->h_n); cudaFreeHost(ex->h_kps); cudaFreeHost(ex->h_desc); cudaFreeHost(ex->h_uR);
   cudaFreeHost(ex->h_depth); cudaFreeHost(ex->h_pairs);
+#ifndef ORBFE_EMU
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 4; ++b)
+      if (ex->xGraph[a][b]) { cudaGraphExecDestroy(ex->xGraph[a][b]); ex->xGraph[a][b] = nullptr; }
+#endif
+  cudaFreeHost(ex->h_img); ex->h_img = nullptr;
   ex->d_img = ex->d_pyr = ex->d_blur = nullptr; ex->d_cellCnt = nullptr; ex->d_cellList = nullptr;
   ex->oct = OctScratch{}; ex->d_lvlKp = nullptr; ex->d_lvlCnt = nullptr; ex->d_kps = nullptr; ex->d_desc = nullptr;
   ex->d_nKp = nullptr; ex->d_lut = nullptr; ex->d_err = nullptr; ex->d_pairs = nullptr; ex->d_uR = nullptr;
@@ -487,8 +501,9 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
   ex->rowSmem = (size_t)(h0 + 1) * sizeof(int);
   CUDA_TRY(cudaMalloc(&ex->d_rowStart, S * (size_t)(h0 + 1) * sizeof(int)));
   CUDA_TRY(cudaMalloc(&ex->d_rowItems, S * (size_t)ex->rowCap * sizeof(uint2)));
-  CUDA_TRY(cudaMallocHost(&ex->h_n, (2 * S + 1) * sizeof(int)));
-  memset(ex->h_n, 0, (2 * S + 1) * sizeof(int));
+  CUDA_TRY(cudaMallocHost(&ex->h_img, std::min<size_t>(S, 2) * (size_t)w0 * h0));
+  CUDA_TRY(cudaMallocHost(&ex->h_n, (2 * S + 3) * sizeof(int)));
+  memset(ex->h_n, 0, (2 * S + 3) * sizeof(int));
   CUDA_TRY(cudaMallocHost(&ex->h_kps, S * g.totalOut * sizeof(orbfe_kp_dev)));
   CUDA_TRY(cudaMallocHost(&ex->h_desc, S * g.totalOut * 32));
   CUDA_TRY(cudaMallocHost(&ex->h_uR, S * g.totalOut * sizeof(float)));
@@ -527,6 +542,7 @@ static int stage_event(orbfe_extractor* ex, int k) {
 static int enqueue_extract(orbfe_extractor* ex, int n) {
   const Geom& g = ex->g;
   int rc;
+  ex->slotDirty = true;
   if ((rc = stage_event(ex, 0))) return rc;
   for (int l = 0; l < g.nlevels; ++l) {
     const LevelGeom& L = g.lv[l];
@@ -826,26 +842,27 @@ int orbfe_run_stereo(orbfe_extractor* ex, int n_pairs, float bf, float baseline)
   return enqueue_stereo(ex, n_pairs, bf, baseline);
 }
 
-int orbfe_download(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t* desc, int capacity, int* n_out,
-                   float* u_right, float* depth) {
-  int rc = check_images(ex, 0, n_imgs);
-  if (rc) return rc;
-  if (!ex->configured) return orbfe_fail(ORBFE_ERR_INVALID, "orbfe_download before any orbfe_upload");
-  if (!n_out || capacity < 0) return orbfe_fail(ORBFE_ERR_INVALID, "bad output arguments");
-  if (n_imgs == 0) return ORBFE_OK;
-  CUDA_TRY(cudaSetDevice(ex->device));
-  const Geom& g = ex->g;
-  const size_t S = (size_t)ex->S, T = (size_t)g.totalOut, n = (size_t)n_imgs;
+// D2H of the results of n images into the handle's pinned staging (enqueue only)
+static int enqueue_download(orbfe_extractor* ex, size_t n, bool kps, bool desc, bool u_right, bool depth) {
+  const size_t S = (size_t)ex->S, T = (size_t)ex->g.totalOut;
   CUDA_TRY(cudaMemcpyAsync(ex->h_n, ex->d_nKp, n * sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
   CUDA_TRY(cudaMemcpyAsync(ex->h_n + 2 * S, ex->d_err, sizeof(int), cudaMemcpyDeviceToHost, ex->stream));
   if (kps) CUDA_TRY(cudaMemcpyAsync(ex->h_kps, ex->d_kps, n * T * sizeof(orbfe_kp_dev), cudaMemcpyDeviceToHost, ex->stream));
   if (desc) CUDA_TRY(cudaMemcpyAsync(ex->h_desc, ex->d_desc, n * T * 32, cudaMemcpyDeviceToHost, ex->stream));
   if (u_right) CUDA_TRY(cudaMemcpyAsync(ex->h_uR, ex->d_uR, n * T * sizeof(float), cudaMemcpyDeviceToHost, ex->stream));
   if (depth) CUDA_TRY(cudaMemcpyAsync(ex->h_depth, ex->d_depth, n * T * sizeof(float), cudaMemcpyDeviceToHost, ex->stream));
-  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  return ORBFE_OK;
+}
+
+// after the stream has been synchronised: pinned staging -> the caller's arrays
+static int deliver_download(orbfe_extractor* ex, size_t n, orbfe_keypoint* kps, uint8_t* desc, int capacity, int* n_out,
+                            float* u_right, float* depth) {
+  const size_t S = (size_t)ex->S, T = (size_t)ex->g.totalOut;
   if (ex->h_n[2 * S] != 0) {
+    const int flag = ex->h_n[2 * S];
+    ex->h_n[2 * S] = 0;
     cudaMemsetAsync(ex->d_err, 0, sizeof(int), ex->stream);
-    return orbfe_fail(ORBFE_ERR_CUDA, "quad-tree kernel reported an internal capacity error (flag %d)", ex->h_n[2 * S]);
+    return orbfe_fail(ORBFE_ERR_CUDA, "quad-tree kernel reported an internal capacity error (flag %d)", flag);
   }
   int status = ORBFE_OK;
   for (size_t i = 0; i < n; ++i) {
@@ -860,7 +877,21 @@ int orbfe_download(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t
     }
   }
   if (status != ORBFE_OK) return orbfe_fail(status, "capacity %d too small for the keypoint count", capacity);
+  if (kps && desc) ex->slotDirty = false;   // the pinned copies now mirror the device rows (orbfe_stereo_match)
   return ORBFE_OK;
+}
+
+int orbfe_download(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t* desc, int capacity, int* n_out,
+                   float* u_right, float* depth) {
+  int rc = check_images(ex, 0, n_imgs);
+  if (rc) return rc;
+  if (!ex->configured) return orbfe_fail(ORBFE_ERR_INVALID, "orbfe_download before any orbfe_upload");
+  if (!n_out || capacity < 0) return orbfe_fail(ORBFE_ERR_INVALID, "bad output arguments");
+  if (n_imgs == 0) return ORBFE_OK;
+  CUDA_TRY(cudaSetDevice(ex->device));
+  if ((rc = enqueue_download(ex, (size_t)n_imgs, kps != nullptr, desc != nullptr, u_right != nullptr, depth != nullptr))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  return deliver_download(ex, (size_t)n_imgs, kps, desc, capacity, n_out, u_right, depth);
 }
 
 int orbfe_download_async(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t* desc, int capacity, int* n_out,
@@ -896,10 +927,70 @@ int orbfe_sync(orbfe_extractor* ex) {
   return ORBFE_OK;
 }
 
+#ifndef ORBFE_EMU
+// The latency path: <= 2 frames per call.  The first call of a geometry captures  H2D (from pinned staging) -> pyramid ->
+// FAST -> quad-tree -> blur -> orientation + rBRIEF -> D2H (into pinned staging)  on the handle's stream into a CUDA graph;
+// every later call is one host copy of the frame(s) into the staging buffer, ONE cudaGraphLaunch and one synchronisation
+// instead of 1 + 15 + 4 stream operations.  Capture is thread-local: the other extraction thread of a stereo Frame
+// (frame.cpp:86-89) keeps issuing its own work meanwhile.
+static int extract_graph(orbfe_extractor* ex, const uint8_t* const* imgs, int n, int w, int h, size_t stride, orbfe_keypoint* kps,
+                         uint8_t* desc, int capacity, int* n_out, bool* used) {
+  *used = false;
+  if (n < 1 || n > 2 || n > ex->S || ex->stageTiming || getenv("ORBFE_NO_GRAPH")) return ORBFE_OK;
+  int rc = check_images(ex, 0, n);
+  if (rc) return rc;
+  if (!imgs || w <= 0 || h <= 0 || stride < (size_t)w || !n_out || capacity < 0) return ORBFE_OK;  // the plain path reports it
+  for (int i = 0; i < n; ++i) if (!imgs[i]) return ORBFE_OK;
+  CUDA_TRY(cudaSetDevice(ex->device));
+  if ((rc = configure(ex, w, h))) return rc;
+  const size_t bytes = (size_t)w * h;
+  const int key = (kps ? 1 : 0) | (desc ? 2 : 0);
+  cudaGraphExec_t& exec = ex->xGraph[n - 1][key];
+  if (!exec) {
+    CUDA_TRY(cudaStreamSynchronize(ex->stream));
+    const long long l0 = ex->launches;
+    CUDA_TRY(cudaStreamBeginCapture(ex->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < n && e == cudaSuccess; ++i)
+      e = cudaMemcpyAsync(ex->d_img + (size_t)i * ex->g.imgStride, ex->h_img + (size_t)i * bytes, bytes, cudaMemcpyHostToDevice, ex->stream);
+    rc = e == cudaSuccess ? enqueue_extract(ex, n) : ORBFE_ERR_CUDA;
+    if (rc == ORBFE_OK) rc = enqueue_download(ex, (size_t)n, kps != nullptr, desc != nullptr, false, false);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(ex->stream, &graph);
+    ex->xGraphLaunches[n - 1][key] = (int)(ex->launches - l0);
+    ex->launches = l0;
+    if (rc == ORBFE_OK && e == cudaSuccess && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != ORBFE_OK || e != cudaSuccess || !exec) {  // not capturable here: the plain path does the work
+      exec = nullptr;
+      cudaGetLastError();
+      return ORBFE_OK;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    uint8_t* d = ex->h_img + (size_t)i * bytes;
+    if (stride == (size_t)w) memcpy(d, imgs[i], bytes);
+    else for (int y = 0; y < h; ++y) memcpy(d + (size_t)y * w, imgs[i] + (size_t)y * stride, (size_t)w);
+  }
+  ex->slotDirty = true;
+  CUDA_TRY(cudaGraphLaunch(exec, ex->stream));
+  ex->launches += ex->xGraphLaunches[n - 1][key];
+  CUDA_TRY(cudaStreamSynchronize(ex->stream));
+  *used = true;
+  return deliver_download(ex, (size_t)n, kps, desc, capacity, n_out, nullptr, nullptr);
+}
+#endif
+
 int orbfe_extract_batch(orbfe_extractor* ex, const uint8_t* const* imgs, int n_imgs, int w, int h, size_t stride,
                         orbfe_keypoint* kps, uint8_t* desc, int capacity, int* n_out) {
-  int rc = orbfe_upload(ex, 0, imgs, n_imgs, w, h, stride);
-  if (rc) return rc;
+  int rc;
+#ifndef ORBFE_EMU
+  if (ex && n_imgs >= 1 && n_imgs <= 2) {
+    bool used = false;
+    if ((rc = extract_graph(ex, imgs, n_imgs, w, h, stride, kps, desc, capacity, n_out, &used)) || used) return rc;
+  }
+#endif
+  if ((rc = orbfe_upload(ex, 0, imgs, n_imgs, w, h, stride))) return rc;
   if ((rc = orbfe_run(ex, n_imgs))) return rc;
   return orbfe_download(ex, n_imgs, kps, desc, capacity, n_out, nullptr, nullptr);
 }
@@ -1071,14 +1162,27 @@ int orbfe_stereo_match(orbfe_extractor* left, orbfe_extractor* right, int n_left
   // upload them into slot 0 of each handle's keypoint block (slot 1 of `left` if both are one handle)
   const size_t rslot = same ? 1 : 0;
   if (same && left->S < 2) return orbfe_fail(ORBFE_ERR_INVALID, "one shared handle needs max_images >= 2");
-  int* cnts = ex->h_n;
+  // ... unless they ARE what the handles just produced (the usual case: keypoints_ / descriptors_ straight from the two
+  // Compute calls): the pinned copies of the last download say so, and the device rows are already in place
+  const size_t T = (size_t)g.totalOut;
+  auto resident = [&](orbfe_extractor* e, size_t slot, int n, const orbfe_keypoint* k, const uint8_t* d) {
+    return !e->slotDirty && e->h_n[slot] == n && !memcmp(e->h_kps + slot * T, k, (size_t)n * sizeof(orbfe_kp_dev)) &&
+           !memcmp(e->h_desc + slot * T * 32, d, (size_t)n * 32);
+  };
+  int* cnts = ex->h_n + 2 * (size_t)ex->S + 1;
   cnts[0] = n_left; cnts[1] = n_right;
-  CUDA_TRY(cudaMemcpyAsync(left->d_kps, kps_left, (size_t)n_left * sizeof(orbfe_kp_dev), cudaMemcpyHostToDevice, ex->stream));
-  CUDA_TRY(cudaMemcpyAsync(left->d_desc, desc_left, (size_t)n_left * 32, cudaMemcpyHostToDevice, ex->stream));
-  CUDA_TRY(cudaMemcpyAsync(right->d_kps + rslot * right->g.totalOut, kps_right, (size_t)n_right * sizeof(orbfe_kp_dev), cudaMemcpyHostToDevice, ex->stream));
-  CUDA_TRY(cudaMemcpyAsync(right->d_desc + rslot * right->g.totalOut * 32, desc_right, (size_t)n_right * 32, cudaMemcpyHostToDevice, ex->stream));
-  CUDA_TRY(cudaMemcpyAsync(left->d_nKp, &cnts[0], sizeof(int), cudaMemcpyHostToDevice, ex->stream));
-  CUDA_TRY(cudaMemcpyAsync(right->d_nKp + rslot, &cnts[1], sizeof(int), cudaMemcpyHostToDevice, ex->stream));
+  if (!resident(left, 0, n_left, kps_left, desc_left)) {
+    CUDA_TRY(cudaMemcpyAsync(left->d_kps, kps_left, (size_t)n_left * sizeof(orbfe_kp_dev), cudaMemcpyHostToDevice, ex->stream));
+    CUDA_TRY(cudaMemcpyAsync(left->d_desc, desc_left, (size_t)n_left * 32, cudaMemcpyHostToDevice, ex->stream));
+    CUDA_TRY(cudaMemcpyAsync(left->d_nKp, &cnts[0], sizeof(int), cudaMemcpyHostToDevice, ex->stream));
+    left->slotDirty = true;
+  }
+  if (!resident(right, rslot, n_right, kps_right, desc_right)) {
+    CUDA_TRY(cudaMemcpyAsync(right->d_kps + rslot * right->g.totalOut, kps_right, (size_t)n_right * sizeof(orbfe_kp_dev), cudaMemcpyHostToDevice, ex->stream));
+    CUDA_TRY(cudaMemcpyAsync(right->d_desc + rslot * right->g.totalOut * 32, desc_right, (size_t)n_right * 32, cudaMemcpyHostToDevice, ex->stream));
+    CUDA_TRY(cudaMemcpyAsync(right->d_nKp + rslot, &cnts[1], sizeof(int), cudaMemcpyHostToDevice, ex->stream));
+    right->slotDirty = true;
+  }
   StereoPair& P = ex->h_pairs[0];
   P.pyrL = left->d_pyr; P.pyrR = right->d_pyr + rslot * right->g.pyrStride;
   P.kpL = left->d_kps; P.kpR = right->d_kps + rslot * right->g.totalOut;

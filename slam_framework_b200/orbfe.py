@@ -44,7 +44,7 @@ EXPORTS = [
     "orbfe_event_record", "orbfe_event_elapsed_ms", "orbfe_set_stage_timing", "orbfe_stage_summary",
     "orbfe_launch_count",
     "orbfe_debug_candidates", "orbfe_debug_level_keypoints", "orbfe_debug_blurred", "orbfe_stereo_match",
-    "orbfe_descriptor_distance", "orbfe_frame_create", "orbfe_frame_destroy", "orbfe_features_in_area",
+    "orbfe_descriptor_distance", "orbfe_frame_create", "orbfe_frame_destroy", "orbfe_frame_pool_trim", "orbfe_features_in_area",
     "orbfe_search_for_initialization", "orbfe_search_by_projection_mappoints",
     "orbfe_search_by_projection_lastframe", "orbfe_search_by_bow",
     "orbfe_search_by_projection_sim3", "orbfe_search_by_projection_keyframe", "orbfe_fuse", "orbfe_fuse_sim3",
@@ -106,6 +106,7 @@ def load(path=None, _test_emulation=False):
     L.orbfe_descriptor_distance.argtypes = [i, vp, vp, i, vp]
     L.orbfe_frame_create.argtypes = [i, i, vp, vp, vp, f, f, f, f, i, vp, C.POINTER(vp)]
     L.orbfe_frame_destroy.argtypes = [vp]
+    L.orbfe_frame_pool_trim.argtypes = []
     L.orbfe_frame_from_extractor.argtypes = [vp, i, i, f, f, f, f, C.POINTER(vp)]
     L.orbfe_frame_refresh_from_extractor.argtypes = [vp, vp, i, i, f, f, f, f]
     L.orbfe_frame_num_keypoints.argtypes = [vp]

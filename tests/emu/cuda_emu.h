@@ -256,6 +256,17 @@ static inline unsigned __ballot_sync(unsigned, int p) {
   emu::warp_barrier();
   return r;
 }
+static inline int __reduce_add_sync(unsigned, int v) {
+  emu::State& s = emu::S();
+  emu::Warp& w = s.warps[s.cur->warp];
+  w.slot[s.cur->lane] = (unsigned long long)(long long)v;
+  emu::warp_barrier();
+  long long r = 0;
+  for (int i = 0; i < 32; ++i)
+    if (w.live_mask >> i & 1) r += (long long)w.slot[i];
+  emu::warp_barrier();
+  return (int)r;
+}
 static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
 static inline int __all_sync(unsigned m, int p) { return __ballot_sync(m, !p) == 0; }
 
@@ -297,6 +308,7 @@ static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4
 static inline int __float_as_int(float f) { int u; std::memcpy(&u, &f, 4); return u; }
 static inline float __int_as_float(int u) { float f; std::memcpy(&f, &u, 4); return f; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
   const unsigned long long v = ((unsigned long long)b << 32) | a;
   unsigned r = 0;

@@ -74,6 +74,19 @@ def _p(a):
     return a.ctypes.data_as(vp) if a is not None else None
 
 
+def set_test_distortion(d4=None):
+    """k1 k2 p1 p2 of every Frame built from now on (None: undistorted camera again)"""
+    L = lib()
+    L.ref_set_test_distortion.argtypes = [C.c_void_p]
+    L.ref_set_test_distortion.restype = None
+    if d4 is None:
+        L.ref_set_test_distortion(None)
+    else:
+        d = np.ascontiguousarray(d4, np.float32)
+        assert d.shape == (4,)
+        L.ref_set_test_distortion(d.ctypes.data)
+
+
 def set_test_transform(R=None, sim3_scale=1.0):
     """rotation (3x3) and Sim3 scale given to every pose the entry points build from a translation; None = identity"""
     if R is None:

@@ -447,3 +447,77 @@ def test_fuzz_slice_matchers_on_tie_heavy_keypoints():
     r = subprocess.run([sys.executable, os.path.join(here, "fuzz_matchers.py"), "gpu", "9"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "failures 0" in r.stdout
+
+
+def test_single_process_multi_gpu_runner_matches_per_rank_digests(lib):
+    """shard.SequenceRunner (ONE process, a host thread and two streams per device) against the per-rank run of the same
+    sequence: identical digests pair by pair; on a multi-GPU box every visible device takes a shard."""
+    from slam_framework_b200 import shard
+    n_pairs, bf, bl = 23, 386.1448, 386.1448 / 718.856
+    pairs = [synth.stereo_pair(188, 620, seed=900 + i) for i in range(n_pairs)]
+    ex = orbfe.ORBextractor(1000, lib=lib, max_images=2)
+
+    def one(i):
+        ex.upload(list(pairs[i])); ex.run(2); ex.run_stereo(1, bf, bl)
+        b = ex.download(2, ex.make_buffers(2, stereo=True))
+        n0, n1 = b["n"]
+        return [b["kps"][0, :n0], b["desc"][0, :n0], b["kps"][1, :n1], b["desc"][1, :n1], b["ur"][0, :n0], b["depth"][0, :n0]]
+    single = shard.process_sequence(one, n_pairs, 0, 1)
+    ex.close()
+    ndev = lib.orbfe_device_count()
+    for devices in ([0], list(range(ndev)) if ndev > 1 else [0, 0, 0]):
+        runner = shard.SequenceRunner(lib, devices=devices, params=dict(nfeatures=1000), batch_pairs=4, lanes=2)
+        assert runner.run(lambda i: pairs[i], n_pairs, bf, bl) == single
+
+
+def test_extract_graph_replay_equals_plain_path(lib, monkeypatch):
+    """orbfe_extract replays a captured CUDA graph from the second frame of a geometry on; the results must equal the
+    stream-ordered path (ORBFE_NO_GRAPH) bit for bit, for one frame and for a two-frame batch, across changing content."""
+    imgs = [synth.frame(seed=70 + i) for i in range(4)]
+    ex = orbfe.ORBextractor(2000, lib=lib, max_images=2)
+    got = [ex.Compute(im) for im in imgs] + [ex.Compute(imgs[0])]
+    got2 = ex.extract_batch([imgs[1], imgs[2]])
+    monkeypatch.setenv("ORBFE_NO_GRAPH", "1")
+    ref = orbfe.ORBextractor(2000, lib=lib, max_images=2)
+    want = [ref.Compute(im) for im in imgs] + [ref.Compute(imgs[0])]
+    want2 = ref.extract_batch([imgs[1], imgs[2]])
+    for (k, d), (rk, rd) in zip(got + got2, want + want2):
+        assert np.array_equal(k, rk) and np.array_equal(d, rd)
+    ex.close(); ref.close()
+
+
+def test_n2_distorted_camera_frame_equals_the_references_own_code(lib):
+    """the k1 != 0 path (frame.cpp:614-673) without the oracle in between: the reference's own stereo Frame constructor on a
+    distorted camera against orbfe_undistort_keypoints (keypoints and the four image corners = ComputeImageBounds), the stereo
+    matches on the original keypoints, and the grid searches of a frame handle built with those bounds."""
+    import reference_lib as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libslam_ref.so not present")
+    dist = np.array([-0.28, 0.07, 0.0002, -0.0002], np.float32)
+    fx, fy, cx, cy, bf = 718.856, 718.856, 607.1928, 185.2157, 386.1448   # reference_lib.Frame's defaults
+    l, r = synth.stereo_pair(seed=17)
+    try:
+        R.set_test_distortion(dist)
+        F = R.Frame(l, r)
+    finally:
+        R.set_test_distortion(None)
+    eL, eR = orbfe.ORBextractor(lib=lib), orbfe.ORBextractor(lib=lib)
+    kl, dl = eL.Compute(l)
+    kr, dr = eR.Compute(r)
+    un = orbfe.UndistortKeyPoints(kl, fx, fy, cx, cy, dist, lib=lib)
+    for f in P.KP_FIELDS:
+        assert np.array_equal(un[f], F.kps_un[f]), f
+    h, w = l.shape
+    corners = np.zeros(4, orbfe.KP_DTYPE)
+    corners["x"], corners["y"] = [0, w, 0, w], [0, 0, h, h]
+    c = orbfe.UndistortKeyPoints(corners, fx, fy, cx, cy, dist, lib=lib)
+    bounds = (min(c["x"][0], c["x"][2]), max(c["x"][1], c["x"][3]), min(c["y"][0], c["y"][1]), max(c["y"][2], c["y"][3]))
+    assert np.array_equal(np.array(bounds, np.float32), F.bounds)
+    n, ur, dp = orbfe.ComputeStereoMatches(eL, eR, kl, dl, kr, dr, bf, float(np.float32(bf) / np.float32(fx)))
+    assert np.array_equal(ur, F.u_right) and np.array_equal(dp, F.depth) and n > 100
+    G = orbfe.Frame(un, dl, eL.GetScaleFactors(), bounds, ur, lib=lib)
+    rng = np.random.default_rng(2)
+    for _ in range(40):
+        x, y, rad = float(rng.uniform(bounds[0], bounds[1])), float(rng.uniform(bounds[2], bounds[3])), float(rng.uniform(5, 120))
+        assert np.array_equal(G.GetFeaturesInArea(x, y, rad), F.features_in_area(x, y, rad))
+    G.close(); eL.close(); eR.close()

@@ -71,3 +71,18 @@ def test_two_rank_gloo_sharding_matches_single_process():
     assert owned == [[0, 1, 2], [3, 4]]
     assert merged == single
     assert t == 2.0  # max over ranks
+
+
+def test_single_process_runner_matches_per_rank_run():
+    """shard.SequenceRunner (one process, one host thread per device, two handles per device taking the batches in turn) against
+    the per-rank run: same digest for every pair.  Two logical devices on the one emulated device: the sharding, the lane
+    rotation, partial last batches and the async downloads are what is under test here."""
+    sys.path.insert(0, HERE)
+    from emu import build_emu
+    from slam_framework_b200 import orbfe, synth
+    single = shard.process_sequence(_pair_fn(), N_PAIRS, 0, 1)
+    L = orbfe.load(build_emu.build(), _test_emulation=True)
+    runner = shard.SequenceRunner(L, devices=[0, 0], params=dict(nfeatures=400), batch_pairs=2, lanes=2)
+    got = runner.run(lambda i: synth.stereo_pair(120, 400, seed=50 + i), N_PAIRS, 386.1448, 386.1448 / 718.856)
+    assert got == single
+    assert runner.seconds > 0

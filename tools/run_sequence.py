@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""The offline sequence (BASELINE.json configs[2], 4541 synthetic KITTI-size stereo pairs) through shard.SequenceRunner: ONE
+process driving every visible GPU (a host thread and `--lanes` streams per device), host arrays in, host arrays out.
+Prints one JSON line with the wall-clock pairs/s, for comparison with bench.py's per-rank (torchrun) end-to-end figure.
+
+    python tools/run_sequence.py [--gpus N] [--pairs 4541] [--batch 64] [--lanes 3]"""
+import argparse, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench as B  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=0)
+    ap.add_argument("--pairs", type=int, default=B.SEQ_PAIRS)
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--lanes", type=int, default=3)
+    ap.add_argument("--distinct", type=int, default=64)
+    a = ap.parse_args()
+    from slam_framework_b200 import orbfe, shard
+    L = orbfe.load()
+    n = a.gpus or L.orbfe_device_count()
+    pairs = B.make_pairs(a.distinct, 0)
+    runner = shard.SequenceRunner(L, devices=list(range(n)), params=dict(nfeatures=B.NFEATURES, scaleFactor=B.SCALE, nlevels=B.NLEVELS,
+                                                                          iniThFAST=B.INI_TH, minThFAST=B.MIN_TH),
+                                  batch_pairs=a.batch, lanes=a.lanes)
+    runner.run(lambda i: pairs[i % a.distinct], min(a.pairs, 8 * a.batch * n), B.BF, B.BF / B.FX)   # warm-up: arenas, clocks
+    d = runner.run(lambda i: pairs[i % a.distinct], a.pairs, B.BF, B.BF / B.FX)
+    print(json.dumps({"driver": "single process, one host thread per GPU", "gpus": n, "pairs": a.pairs, "batch_pairs": a.batch, "lanes": a.lanes,
+                      "seconds": runner.seconds, "pairs_per_s": a.pairs / runner.seconds, "digests": len(d),
+                      "note": "wall clock incl. python-side digesting of every pair's outputs and pageable host arrays"}))
+
+
+if __name__ == "__main__":
+    main()
