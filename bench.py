@@ -506,6 +506,38 @@ def run_ours(args):
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     barrier()
     clocks = sampler.stop()
+    # ---- copy-only ceiling of this box for the e2e leg: per batch ONE pinned H2D copy of the frames and ONE D2H copy of the
+    # results, the two directions on separate streams, no kernels, all ranks at once (tools/copy_ceiling.py is the
+    # stand-alone form).  e2e / ceiling says how much of the host <-> device path the pipeline uses.
+    ceil_pairs = None
+    try:
+        cap0 = ex.max_keypoints()
+        hb, db = n_img * H * W, n_img * cap0 * (28 + 32 + 4 + 4) + n_img * 4
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        h_in = [torch.empty(hb, dtype=torch.uint8, pin_memory=True) for _ in range(NL)]
+        d_in = [torch.empty(hb, dtype=torch.uint8, device="cuda") for _ in range(NL)]
+        h_out = [torch.empty(db, dtype=torch.uint8, pin_memory=True) for _ in range(NL)]
+        d_out = [torch.empty(db, dtype=torch.uint8, device="cuda") for _ in range(NL)]
+
+        def pump(k):
+            for j in range(k):
+                with torch.cuda.stream(s_in):
+                    d_in[j % NL].copy_(h_in[j % NL], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    h_out[j % NL].copy_(d_out[j % NL], non_blocking=True)
+        pump(10)
+        barrier()
+        iters = 150
+        t0 = time.perf_counter()
+        pump(iters)
+        torch.cuda.synchronize()
+        t_copy = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        ceil_pairs = world * B * iters / t_copy
+        ceil_gbs = world * (hb + db) * iters / t_copy / 1e9
+        del h_in, d_in, h_out, d_out
+    except Exception:
+        ceil_pairs = None
     buf = lanes[0][1]
     for e, _ in lanes[1:]:
         e.close()
@@ -565,7 +597,7 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "note": "the dominant kernel (grid FAST) is bound by the integer pipes, not by HBM: see DESIGN.md section 4 and profiles/",
+                "note": "the dominant kernel (grid FAST) is bound by instruction issue (integer pipes + shared-memory gathers), not by HBM: see DESIGN.md section 4 and profiles/",
                 "alg_bytes_per_launch": dom_bytes / stage_launches[dom], "launch_ms": dom_ms / stage_launches[dom],
                 "whole_step": {"alg_bytes": alg["extract_total"] * 2 * n_local, "gbs": whole, "frac": whole / peak},
                 "stages": per_stage}
@@ -613,6 +645,10 @@ def run_ours(args):
                                          "`value` is the single-stream figure its per-stage times belong to"},
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": 1e3 * t_e2e / args.steps, "lanes": NL,
+                   "copy_ceiling": None if not ceil_pairs else {
+                       "pairs_per_s": ceil_pairs, "combined_gbs": ceil_gbs, "fraction_of_ceiling": e2e_value / ceil_pairs,
+                       "what": "the same per-batch H2D + D2H copies alone (pinned, full duplex, all ranks at once, no kernels), "
+                               "measured in this run right after the e2e leg"},
                    "note": "bytes are rank 0's per step (= per pass over its shard); pinned host buffers both ways"},
            "clocks": clocks, "roofline": roofline,
            "keypoints_per_image": kp_img, "stereo_matches_per_pair": n_matched / max(nb_last if n_batches == 1 else B, 1)}

@@ -765,6 +765,7 @@ struct SolveCfg {
   int init;       // SearchForInitialization coupling (InitJacobi) instead of the occupancy feedback (JacobiState)
   int* flags;     // 3 rotating "some query changed" flags
   int* iowner;    // init: per-keypoint owner scratch
+  int* hist;      // ORBFE_HISTO_LENGTH rotation-histogram bins, zeroed by the host with the cursor block
 };
 #define ORBFE_SOLVE_THREADS 512
 
@@ -784,6 +785,13 @@ k_match_solve(const FrameGrid F, const MatchQueries Q, const BowQueries BQ, cons
   }
   if (gtid < 3) C.flags[gtid] = 0;
   if (gtid == 0 && C.init) *IJ.overflow = 0;
+  // the result arrays start "unmatched" (the finalize phase below only writes accepts)
+  if (C.init) {
+    for (int i = gtid; i < A.nKp; i += gsz) C.iowner[i] = -1;
+    for (int q = gtid; q < nQ; q += gsz) A.out[q] = -1;
+  } else if (!A.perQuery) {
+    for (int i = gtid; i < A.nKp; i += gsz) A.out[i] = -1;
+  }
   if (C.bow) {
     for (int q = gwarp; q < nQ; q += nwarps) orbfe_candidates_bow_query(F, BQ, S, B, q, lane);
   } else {
@@ -809,13 +817,92 @@ k_match_solve(const FrameGrid F, const MatchQueries Q, const BowQueries BQ, cons
     if (*reinterpret_cast<volatile int*>(changed) == 0) break;   // fixed point (grid-uniform)
   }
   if (!coupled) grid.sync();
-  if (blockIdx.x != 0) return;
+  // ---- finalize, spread over the grid (the one-CTA forms above are what the emulated build launches) -------------------
+  __shared__ int s_hist[ORBFE_HISTO_LENGTH];
+  __shared__ int s_ind[3];
+  const bool ori = A.checkOri != 0;
+  const float factor = 1.0f / ORBFE_HISTO_LENGTH;  // orb_matcher.cpp:275 / :1322 (the reference's bin-width bug, kept)
+  if (threadIdx.x < ORBFE_HISTO_LENGTH) s_hist[threadIdx.x] = 0;
+  __syncthreads();
+  int mine = 0;
   if (C.init) {
-    if (*reinterpret_cast<volatile int*>(IJ.overflow)) return;   // the host falls back to the serial resolve
-    orbfe_init_finalize_block(A, IJ, C.iowner);
+    if (*reinterpret_cast<volatile int*>(IJ.overflow)) return;   // grid-uniform: the host falls back to the serial resolve
+    // the LAST accepted query on a keypoint owns it (:325-333)
+    for (int q = gtid; q < nQ; q += gsz) {
+      const int acc = IJ.acc[q];
+      if (acc >= 0) atomicMax(&C.iowner[acc & 0x3fffff], q);
+    }
+    grid.sync();
+    for (int q = gtid; q < nQ; q += gsz) {
+      const int acc = IJ.acc[q];
+      int bin = -1;
+      if (acc >= 0) {
+        const int idx = acc & 0x3fffff;
+        if (__ldcg(C.iowner + idx) == q) { A.out[q] = idx; ++mine; }
+        if (ori) {  // the histogram counts every accept, stolen ones included, exactly as rotHist does (:339-374)
+          float rot = __fsub_rn(A.qAngle[q], A.kp[idx].angle);
+          if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+          bin = (int)roundf(__fmul_rn(rot, factor));
+          if (bin == ORBFE_HISTO_LENGTH) bin = 0;
+          atomicAdd(&s_hist[bin], 1);
+        }
+      }
+      A.evBin[q] = bin;
+    }
   } else {
-    orbfe_match_finalize_block(A, J);
+    for (int q = gtid; q < nQ; q += gsz) {
+      const int b = J.best[q];
+      int bin = -1;
+      if (A.perQuery) A.out[q] = b;
+      if (b >= 0) {
+        ++mine;
+        if (!A.perQuery) atomicMax(&A.out[b], q);   // F.SetMapPoint: the last accepted query on a keypoint wins
+        if (ori) {
+          float rot = __fsub_rn(A.qAngle[q], A.kp[b].angle);
+          if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+          bin = (int)roundf(__fmul_rn(rot, factor));
+          if (bin == ORBFE_HISTO_LENGTH) bin = 0;
+          atomicAdd(&s_hist[bin], 1);
+        }
+      }
+      A.evBin[q] = bin;
+    }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane == 0 && mine) atomicAdd(A.result, mine);
+  if (!ori) return;
+  __syncthreads();
+  if (threadIdx.x < ORBFE_HISTO_LENGTH && s_hist[threadIdx.x]) atomicAdd(C.hist + threadIdx.x, s_hist[threadIdx.x]);
+  grid.sync();   // every accept is in out[] / hist[] before anybody removes one
+  if (threadIdx.x == 0) {  // ComputeThreeMaxima (orb_matcher.cpp:1584-1625), once per CTA
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+    for (int i = 0; i < ORBFE_HISTO_LENGTH; i++) {
+      const int h = __ldcg(C.hist + i);
+      if (h > max1) { max3 = max2; max2 = max1; max1 = h; ind3 = ind2; ind2 = ind1; ind1 = i; }
+      else if (h > max2) { max3 = max2; max2 = h; ind3 = ind2; ind2 = i; }
+      else if (h > max3) { max3 = h; ind3 = i; }
+    }
+    if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) ind3 = -1;
+    s_ind[0] = ind1; s_ind[1] = ind2; s_ind[2] = ind3;
+  }
+  __syncthreads();
+  int removed = 0;
+  for (int q = gtid; q < nQ; q += gsz) {
+    const int bin = A.evBin[q];
+    if (bin >= 0 && bin != s_ind[0] && bin != s_ind[1] && bin != s_ind[2]) {
+      if (C.init) {
+        if (A.out[q] >= 0) { A.out[q] = -1; ++removed; }  // :364-370
+      } else {
+        A.out[A.perQuery ? q : J.best[q]] = -1;  // CurrentFrame.SetMapPoint(idx, NULL); nmatches-- (:1441-1446); vMatches12[idx1] = -1 (:784)
+        ++removed;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+  if (lane == 0 && removed) atomicSub(A.result, removed);
 }
 #endif
 

@@ -40,7 +40,7 @@ struct StereoPair {
 // S1 (frame.cpp:415-433): right keypoint iR is pushed into every row yi in [floor(y-r), ceil(y+r)],
 // r = 2*scale[octave].  One CTA per pair builds the table (count, scan, fill); the order inside a row
 // does not matter because the search reduces on (distance, iR).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_stereo_rows(const __grid_constant__ Geom g, const StereoPair* __restrict__ pairs, const int maxKp) {
   ORBFE_DYN_SMEM(smem);
   int* s_cnt = reinterpret_cast<int*>(smem);  // nRows + 1

@@ -559,6 +559,10 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
       if (const char* e = getenv("ORBFE_TUNE_PYR_WARPS")) { const int v = atoi(e); if (v >= 0) wantWarps = v; }           // tuning only
       int segs = (L.h + segT - 1) / segT;
       segs = std::max(segs, std::min((L.h + minSeg - 1) / minSeg, (wantWarps + strips * n - 1) / (strips * n)));
+      // latency path (a frame or a pair per launch): 56-row marches leave most SMs idle and the launch lasts as long as one
+      // march; shorter segments (>= 12 rows) until the launch brings about 4 warps per SM
+      if (!getenv("ORBFE_TUNE_PYR_SEG") && !getenv("ORBFE_TUNE_PYR_WARPS"))
+        while ((long long)strips * segs * n < 600 && (L.h + segs) / (segs + 1) >= 12) ++segs;
       const int segH = (L.h + segs - 1) / segs;
       const size_t warpBytes = ((size_t)ORBFE_PYRS_RING * L.pyrBoxW + (size_t)segH * sizeof(PyrRowLut) + 127) & ~(size_t)127;
       const size_t smem = warpBytes * ORBFE_PYRS_WPC;
@@ -814,7 +818,8 @@ static void fill_pairs_same_handle(orbfe_extractor* ex, int n_pairs) {
 
 static int enqueue_stereo(orbfe_extractor* ex, int n_pairs, float bf, float baseline) {
   const Geom& g = ex->g;
-  ORBFE_LAUNCH(ex, k_stereo_rows, dim3(n_pairs), dim3(256), ex->rowSmem, g, ex->d_pairs, g.totalOut);
+  // one CTA per pair; a lone pair (the latency path) gets 1024 threads: its two passes over the right keypoints are latency-bound
+  ORBFE_LAUNCH(ex, k_stereo_rows, dim3(n_pairs), dim3(n_pairs <= 8 ? 1024 : 256), ex->rowSmem, g, ex->d_pairs, g.totalOut);
   ORBFE_LAUNCH(ex, k_stereo_search, dim3((g.totalOut + ORBFE_ST_THREADS / 32 - 1) / (ORBFE_ST_THREADS / 32), n_pairs),
                dim3(ORBFE_ST_THREADS), 0, g, ex->d_pairs, bf, baseline, g.totalOut);
   int rc;

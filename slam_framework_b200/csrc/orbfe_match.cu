@@ -27,6 +27,8 @@
 #define MATCH_LAUNCH(f, kernel, grid, block, smem, ...) kernel<<<grid, block, smem, (f)->stream>>>(__VA_ARGS__)
 #endif
 
+#define ORBFE_CURSOR_INTS 40   // [0] cursor [1] overflow [2] nmatches [3] init overflow [4..6] solve flags [7] misc counter [8..38) histogram
+
 struct orbfe_frame {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -247,7 +249,7 @@ static int solve(orbfe_frame* f, SolveInput& in, const SearchSpec& sp, int32_t* 
   int* hres = reinterpret_cast<int*>(f->h_outStage);
   int* hout = hres + 4;
   for (int attempt = 0; attempt < 8; ++attempt) {
-    CUDA_TRY(cudaMemsetAsync(f->d_cursor, 0, 8 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(f->d_cursor, 0, ORBFE_CURSOR_INTS * sizeof(int), st));
     MatchScratch S;
     S.cand = f->d_cand; S.cursor = f->d_cursor; S.capacity = f->candCap;
     S.qOff = in.bow ? const_cast<int*>(in.qOff) : f->d_qOff;
@@ -271,7 +273,7 @@ static int solve(orbfe_frame* f, SolveInput& in, const SearchSpec& sp, int32_t* 
         f->coopBlocks = std::max(1, perSm * sms);
       }
       SolveCfg C;
-      C.bow = in.bow; C.init = init ? 1 : 0; C.flags = f->d_cursor + 4; C.iowner = f->d_iowner;
+      C.bow = in.bow; C.init = init ? 1 : 0; C.flags = f->d_cursor + 4; C.iowner = f->d_iowner; C.hist = f->d_cursor + 8;
       const int wpb = ORBFE_SOLVE_THREADS / 32;
       const int blocks = std::max(1, std::min(f->coopBlocks, (nq + wpb - 1) / wpb));
       void* args[] = {(void*)&G, (void*)&in.MQ, (void*)&in.BQ, (void*)&in.B, (void*)&S, (void*)&A, (void*)&J, (void*)&IJ, (void*)&C};
@@ -459,7 +461,7 @@ static int frame_acquire(int device, orbfe_frame** out) {
     f->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&f->d_cellStart, (ORBFE_GRID_CELLS + 1) * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_cursor, 8 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_cursor, ORBFE_CURSOR_INTS * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&f->d_lvl, 3 * ORBFE_MAX_LEVELS * sizeof(float));
     if (e == cudaSuccess) e = cudaMallocHost(&f->h_res, 4 * sizeof(int));
     if (e != cudaSuccess) {
