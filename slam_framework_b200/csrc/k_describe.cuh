@@ -14,6 +14,7 @@
 //       size = (float)(int)(31*scale), octave = level, class_id = -1.
 #pragma once
 #include "orbfe_common.cuh"
+#include "orbfe_tma.cuh"
 
 #ifndef ORBFE_DESC_THREADS
 #define ORBFE_DESC_THREADS 64
@@ -21,7 +22,18 @@
 #ifndef ORBFE_DESC_UNROLL
 #define ORBFE_DESC_UNROLL 2
 #endif
-#define ORBFE_DESC_PW 12  // words per staged patch row (48 B >= 37 + 3 alignment bytes)
+// Both patches of a keypoint arrive by TMA (one cp.async.bulk.tensor each, issued by lane 0, orbfe_tma.cuh): the 31 x 31 disc of
+// the UNBLURRED level for the moments (box 48 B x 31 rows) and the 37 x 37 rBRIEF window of the BLURRED level (box 64 B x 37 rows).
+// A box starts at the 16-byte boundary at or below the patch's first column, so 31 + 15 <= 48 and 37 + 15 <= 64 bytes per row.
+// The tensor maps are written by the host before any launch and never modified, so no tensormap-proxy fence is needed.
+// Each warp owns two 128-byte aligned buffers with one mbarrier each: while keypoint k is processed from one, the box of keypoint
+// k + 1 lands in the other.  (The previous form staged the window with 14 rounds of per-lane loads and index arithmetic and
+// read the disc with 22 global loads per lane: 250 of the ~700 warp instructions per keypoint.)
+#define ORBFE_DESC_PYR_BW 48
+#define ORBFE_DESC_PYR_BH 31
+#define ORBFE_DESC_BLUR_BW 64
+#define ORBFE_DESC_BLUR_BH 37
+#define ORBFE_DESC_BUF 2432  // bytes per buffer: 37 x 64 rounded up to a multiple of 128
 constexpr int kDescUnroll = ORBFE_DESC_UNROLL;  // keypoints processed per loop iteration (memory-level parallelism)
 
 // global (L1-cached) rather than __constant__: each lane reads ITS 32 bytes, and per-lane addresses in
@@ -115,7 +127,8 @@ __device__ __forceinline__ float orbfe_sincosf(float y, int is_cos) {
 __global__ void __launch_bounds__(ORBFE_DESC_THREADS, ORBFE_DESC_MINB)
 k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, const uint8_t* __restrict__ blur,
                   const unsigned* __restrict__ lvlKp, const int* __restrict__ lvlCnt, orbfe_kp_dev* __restrict__ kps,
-                  uint8_t* __restrict__ desc, int* __restrict__ nKp, const int kpw, const uint2* __restrict__ icw) {
+                  uint8_t* __restrict__ desc, int* __restrict__ nKp, const int kpw, const uint2* __restrict__ icw,
+                  const CUtensorMap* __restrict__ tmPyr, const CUtensorMap* __restrict__ tmBlur) {
   const int slot = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int wglobal = blockIdx.x * (ORBFE_DESC_THREADS / 32) + (threadIdx.x >> 5);
@@ -133,6 +146,13 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
   }
   __syncthreads();
 #endif
+  __shared__ __align__(128) unsigned char s_buf[ORBFE_DESC_THREADS / 32][2][ORBFE_DESC_BUF];
+  __shared__ __align__(8) unsigned long long s_bars[ORBFE_DESC_THREADS / 32][2];
+  unsigned char (*wbuf)[ORBFE_DESC_BUF] = s_buf[threadIdx.x >> 5];
+  unsigned long long* wbar = s_bars[threadIdx.x >> 5];
+  if (lane == 0) { orbfe_tile_barrier_init(&wbar[0]); orbfe_tile_barrier_init(&wbar[1]); }
+  __syncwarp();  // the buffers and barriers belong to this warp alone
+  unsigned par0 = 0, par1 = 0;      // completed phases of the two barriers (warp-uniform)
   const int* cnt = lvlCnt + (size_t)slot * g.nlevels;
   // kpw keypoints per warp: 32 for large batches (the lane-parallel phase is fully used), fewer when
   // only a frame or two is in flight so that the keypoints spread over more warps (latency)
@@ -155,7 +175,6 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
     kx = ORBFE_PX(pk) + ORBFE_MINB; ky = ORBFE_PY(pk) + ORBFE_MINB;  // level coordinates
     resp = ORBFE_PS(pk);
   }
-  const uint8_t* pyrSlot = pyr + (size_t)slot * g.pyrStride;
   // ---- E5: intensity centroid on the unblurred level.  A patch row's 31 bytes lie in 9 aligned words; lanes
   // = (row within a group of 3, word), so one load instruction touches 3 rows (few L1 wavefronts) and the
   // patch takes 11 of them.  Per-byte weights (u+15 inside the disc, 0 outside) and the 0/1 disc mask come
@@ -163,15 +182,25 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
   // m10 = sum(u*I) = sum((u+15)*I) - 15*sum(I),  m01 = sum_v v * sum_u I  (exact integer sums).
   int my10 = 0, my01 = 0;
   const int rg = lane / 9, wi = lane - 9 * rg;  // lanes 27..31 idle in this phase
-#pragma unroll kDescUnroll
+  // box of keypoint k (warp-uniform arguments) into buffer k & 1
+  auto issue_pyr = [&](const int k, const int lv, const int cx, const int cy) {
+    if (lane == 0) {
+      const LevelGeom& L = g.lv[lv];
+      OrbfeTmaPlane P;
+      P.base = pyr + L.planeOff; P.sliceStride = g.pyrStride; P.pitch = L.pitch; P.rows = L.h + 2 * ORBFE_EDGE;
+      P.slices = gridDim.y; P.boxW = ORBFE_DESC_PYR_BW; P.boxH = ORBFE_DESC_PYR_BH;
+      const int col = cx + ORBFE_EDGE - ORBFE_HALF_PATCH;
+      orbfe_tile_issue(wbuf[k & 1], &wbar[k & 1], tmPyr + lv, P, col & ~15, cy + ORBFE_EDGE - ORBFE_HALF_PATCH, slot);
+    }
+  };
+  issue_pyr(0, __shfl_sync(0xffffffffu, level, 0), __shfl_sync(0xffffffffu, kx, 0), __shfl_sync(0xffffffffu, ky, 0));
   for (int k = 0; k < nk; ++k) {
-    const int lv = __shfl_sync(0xffffffffu, level, k);
-    const int cx = __shfl_sync(0xffffffffu, kx, k), cy = __shfl_sync(0xffffffffu, ky, k);
-    const LevelGeom& L = g.lv[lv];
+    const int cx = __shfl_sync(0xffffffffu, kx, k);
+    if (k + 1 < nk)  // buffer (k + 1) & 1 was last read in iteration k - 1, which ended with a __syncwarp
+      issue_pyr(k + 1, __shfl_sync(0xffffffffu, level, k + 1), __shfl_sync(0xffffffffu, kx, k + 1), __shfl_sync(0xffffffffu, ky, k + 1));
     const int col = cx + ORBFE_EDGE - ORBFE_HALF_PATCH;  // padded column of a row's first pixel
-    const int pitchW = L.pitch >> 2;
-    const unsigned* p0 = reinterpret_cast<const unsigned*>(pyrSlot + L.planeOff) +
-                         (size_t)(cy + ORBFE_EDGE - ORBFE_HALF_PATCH) * pitchW + (col >> 2) + wi;
+    if (k & 1) { orbfe_tile_wait_warp(&wbar[1], par1 & 1u); ++par1; } else { orbfe_tile_wait_warp(&wbar[0], par0 & 1u); ++par0; }
+    const unsigned* p0 = reinterpret_cast<const unsigned*>(wbuf[k & 1]) + ((col & 15) >> 2) + wi;
     const uint2* wt = icw + (col & 3) * (16 * 9) + wi;
     unsigned su = 0, s1 = 0;
     int m01 = 0;
@@ -181,7 +210,7 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
         const int r = 3 * it + rg;  // patch row 0..30 (v = r - 15)
         if (r < 31) {
           const int v = r - ORBFE_HALF_PATCH;
-          const unsigned w = __ldg(p0 + (size_t)r * pitchW);
+          const unsigned w = p0[r * (ORBFE_DESC_PYR_BW / 4)];
           const uint2 t = __ldg(wt + (v < 0 ? -v : v) * 9);
           su = __dp4a(w, t.x, su);
           const unsigned rs = __dp4a(w, t.y, 0u);
@@ -197,6 +226,7 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
       m01 += __shfl_xor_sync(0xffffffffu, m01, o);
     }
     if (lane == k) { my10 = m10; my01 = m01; }
+    __syncwarp();
   }
   // ---- lane-parallel angle, sin/cos and keypoint record
   float angle = 0.f, a = 1.f, b = 0.f;
@@ -240,35 +270,42 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
 #define ORBFE_DESC_PX(t, h) px[2 * (t) + (h)]
 #define ORBFE_DESC_PY(t, h) py[2 * (t) + (h)]
 #endif
-  __shared__ unsigned s_patch[ORBFE_DESC_THREADS / 32][2][37 * ORBFE_DESC_PW];
   const uint8_t* blurSlot = blur + (size_t)slot * g.blurStride;
   uint8_t* dOut = desc + ((size_t)slot * g.totalOut + base) * 32;
-#pragma unroll kDescUnroll
+  // the pattern reaches 18 px (|offset| <= 18 after rotation): keypoints at least 19 px inside the level need no edge
+  // handling and take their window from the TMA box (warp-uniform test; ~97 % of the keypoints)
+  auto inside = [&](const int lv, const int cx, const int cy) {
+    const LevelGeom& L = g.lv[lv];
+    return cx >= 18 && cy >= 18 && cx + 18 < L.w && cy + 18 < L.h;
+  };
+  auto issue_blur = [&](const int k, const int lv, const int cx, const int cy) {
+    if (lane == 0) {
+      const LevelGeom& L = g.lv[lv];
+      OrbfeTmaPlane P;
+      P.base = blur + L.blurOff; P.sliceStride = g.blurStride; P.pitch = L.bpitch; P.rows = L.h;
+      P.slices = gridDim.y; P.boxW = ORBFE_DESC_BLUR_BW; P.boxH = ORBFE_DESC_BLUR_BH;
+      orbfe_tile_issue(wbuf[k & 1], &wbar[k & 1], tmBlur + lv, P, (cx - 18) & ~15, cy - 18, slot);
+    }
+  };
+  {
+    const int lv0 = __shfl_sync(0xffffffffu, level, 0), cx0 = __shfl_sync(0xffffffffu, kx, 0), cy0 = __shfl_sync(0xffffffffu, ky, 0);
+    if (inside(lv0, cx0, cy0)) issue_blur(0, lv0, cx0, cy0);
+  }
   for (int k = 0; k < nk; ++k) {
     const int lv = __shfl_sync(0xffffffffu, level, k);
     const int cx = __shfl_sync(0xffffffffu, kx, k), cy = __shfl_sync(0xffffffffu, ky, k);
     const float ca = __shfl_sync(0xffffffffu, a, k), sb = __shfl_sync(0xffffffffu, b, k);
+    if (k + 1 < nk) {  // buffer (k + 1) & 1 was last read in iteration k - 1, which ended with a __syncwarp
+      const int lvn = __shfl_sync(0xffffffffu, level, k + 1), cxn = __shfl_sync(0xffffffffu, kx, k + 1), cyn = __shfl_sync(0xffffffffu, ky, k + 1);
+      if (inside(lvn, cxn, cyn)) issue_blur(k + 1, lvn, cxn, cyn);
+    }
     const LevelGeom& L = g.lv[lv];
     const uint8_t* bplane = blurSlot + L.blurOff;
     const int W = L.w, Hh = L.h, bp = L.bpitch;
     unsigned val = 0;
-    // the pattern reaches 18 px (|offset| <= 18 after rotation): keypoints at least 19 px inside the level
-    // need no edge handling (warp-uniform branch; ~97 % of the keypoints)
-    const int pbase = (cx - 18) & ~3;  // first staged column (word aligned)
-    if (cx >= 18 && cy >= 18 && cx + 18 < W && cy + 18 < Hh && pbase + 4 * ORBFE_DESC_PW <= bp) {
-      // the 37 x 37 sampling window is staged in shared memory with coalesced word loads; the 512 scattered
-      // byte reads then cost ~3 bank-conflict wavefronts each instead of one L1 wavefront per touched line
-      unsigned* patch = s_patch[threadIdx.x >> 5][k & 1];
-      const unsigned* gsrc = reinterpret_cast<const unsigned*>(bplane + (size_t)(cy - 18) * bp + pbase);
-      const int bpW = bp >> 2;
-#pragma unroll
-      for (int i = 0; i < (37 * ORBFE_DESC_PW + 31) / 32; ++i) {
-        const int t = 32 * i + lane;
-        const int row = t / ORBFE_DESC_PW, wc = t - row * ORBFE_DESC_PW;
-        if (t < 37 * ORBFE_DESC_PW) patch[t] = __ldg(gsrc + (size_t)row * bpW + wc);
-      }
-      __syncwarp();
-      const uint8_t* centre = reinterpret_cast<const uint8_t*>(patch) + 18 * (4 * ORBFE_DESC_PW) + (cx - pbase);
+    if (inside(lv, cx, cy)) {
+      if (k & 1) { orbfe_tile_wait_warp(&wbar[1], par1 & 1u); ++par1; } else { orbfe_tile_wait_warp(&wbar[0], par0 & 1u); ++par0; }
+      const uint8_t* centre = wbuf[k & 1] + 18 * ORBFE_DESC_BLUR_BW + 18 + ((cx - 18) & 15);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         int tv[2];
@@ -278,12 +315,11 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
           const float x = ORBFE_DESC_PX(t, h), y = ORBFE_DESC_PY(t, h);
           const int iy = __float2int_rn(__fadd_rn(__fmul_rn(x, sb), __fmul_rn(y, ca)));
           const int ix = __float2int_rn(__fsub_rn(__fmul_rn(x, ca), __fmul_rn(y, sb)));
-          tv[h] = (int)centre[iy * (4 * ORBFE_DESC_PW) + ix];
+          tv[h] = (int)centre[iy * ORBFE_DESC_BLUR_BW + ix];
         }
         val |= (unsigned)(tv[0] < tv[1]) << t;
       }
     } else {
-      __syncwarp();  // keeps the reads of the staged iteration k-1 ahead of the writes of iteration k+1 (same buffer parity)
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         int tv[2];
@@ -303,5 +339,6 @@ k_orient_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ py
       }
     }
     dOut[k * 32 + lane] = (uint8_t)val;
+    __syncwarp();  // every lane has read buffer k & 1 before the box of keypoint k + 2 may land in it
   }
 }

@@ -62,6 +62,8 @@ struct orbfe_extractor {
   CUtensorMap* d_tmapsBlur = nullptr;  // the same planes with the blur's box (ORBFE_BLUR_BOXW x ORBFE_BLUR_RB)
   unsigned* d_blurTasks = nullptr;  // per blur CTA: level | column strip
   CUtensorMap* d_tmapsPyr = nullptr;   // per level l >= 1: the planes of level l-1 with the streaming resize's box
+  CUtensorMap* d_tmapsDescPyr = nullptr;   // k_orient_describe: padded planes, box 48 B x 31 rows (the IC_Angle disc)
+  CUtensorMap* d_tmapsDescBlur = nullptr;  // k_orient_describe: blurred planes, box 64 B x 37 rows (the rBRIEF window)
   int* d_pyrBoxX = nullptr;         // per (level, strip): first source byte of the strip's boxes
   int octStageCap = 0;
   // device arena
@@ -156,6 +158,7 @@ static void free_arena(orbfe_extractor* ex) {
   cudaFree(ex->d_tmaps); ex->d_tmaps = nullptr; cudaFree(ex->d_fastTasks); ex->d_fastTasks = nullptr;
   cudaFree(ex->d_tmapsBlur); ex->d_tmapsBlur = nullptr; cudaFree(ex->d_blurTasks); ex->d_blurTasks = nullptr;
   cudaFree(ex->d_tmapsPyr); ex->d_tmapsPyr = nullptr; cudaFree(ex->d_pyrBoxX); ex->d_pyrBoxX = nullptr;
+  cudaFree(ex->d_tmapsDescPyr); ex->d_tmapsDescPyr = nullptr; cudaFree(ex->d_tmapsDescBlur); ex->d_tmapsDescBlur = nullptr;
   cudaFree(ex->d_img); cudaFree(ex->d_pyr); cudaFree(ex->d_blur); cudaFree(ex->d_cellCnt); cudaFree(ex->d_cellList);
   cudaFree(ex->oct.cand); cudaFree(ex->oct.knode); cudaFree(ex->oct.cellStart); cudaFree(ex->oct.nodes);
   cudaFree(ex->oct.childCnt); cudaFree(ex->oct.childSlot); cudaFree(ex->oct.best); cudaFree(ex->oct.finSeq);
@@ -466,6 +469,24 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
     }
     CUDA_TRY(cudaMalloc(&ex->d_tmapsPyr, nl * sizeof(CUtensorMap)));
     CUDA_TRY(cudaMemcpy(ex->d_tmapsPyr, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    for (int l = 0; l < nl; ++l) {
+      OrbfeTmaPlane P;
+      P.base = ex->d_pyr + g.lv[l].planeOff; P.sliceStride = g.pyrStride; P.pitch = g.lv[l].pitch;
+      P.rows = g.lv[l].h + 2 * ORBFE_EDGE; P.slices = (int)S; P.boxW = ORBFE_DESC_PYR_BW; P.boxH = ORBFE_DESC_PYR_BH;
+      const int r = orbfe_tma_encode(&maps[l], P);
+      if (r != 0) return orbfe_fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled failed for the moment box of level %d (%d)", l, r);
+    }
+    CUDA_TRY(cudaMalloc(&ex->d_tmapsDescPyr, nl * sizeof(CUtensorMap)));
+    CUDA_TRY(cudaMemcpy(ex->d_tmapsDescPyr, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    for (int l = 0; l < nl; ++l) {
+      OrbfeTmaPlane P;
+      P.base = ex->d_blur + g.lv[l].blurOff; P.sliceStride = g.blurStride; P.pitch = g.lv[l].bpitch;
+      P.rows = g.lv[l].h; P.slices = (int)S; P.boxW = ORBFE_DESC_BLUR_BW; P.boxH = ORBFE_DESC_BLUR_BH;
+      const int r = orbfe_tma_encode(&maps[l], P);
+      if (r != 0) return orbfe_fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled failed for the descriptor box of level %d (%d)", l, r);
+    }
+    CUDA_TRY(cudaMalloc(&ex->d_tmapsDescBlur, nl * sizeof(CUtensorMap)));
+    CUDA_TRY(cudaMemcpy(ex->d_tmapsDescBlur, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&ex->d_pyrBoxX, std::max<size_t>(pyrBoxX.size(), 1) * sizeof(int)));
     if (!pyrBoxX.empty())
       CUDA_TRY(cudaMemcpy(ex->d_pyrBoxX, pyrBoxX.data(), pyrBoxX.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -602,7 +623,7 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
     if (const char* e = getenv("ORBFE_TUNE_KPW")) { const int v = atoi(e); if (v >= 1 && v <= 32) kpw = v; }  // tuning only
     const int warps = (g.totalOut + kpw - 1) / kpw, wpc = ORBFE_DESC_THREADS / 32;
     ORBFE_LAUNCH(ex, k_orient_describe, dim3((warps + wpc - 1) / wpc, n), dim3(ORBFE_DESC_THREADS), 0, g, ex->d_pyr, ex->d_blur,
-                 ex->d_lvlKp, ex->d_lvlCnt, ex->d_kps, ex->d_desc, ex->d_nKp, kpw, ex->d_icw);
+                 ex->d_lvlKp, ex->d_lvlCnt, ex->d_kps, ex->d_desc, ex->d_nKp, kpw, ex->d_icw, ex->d_tmapsDescPyr, ex->d_tmapsDescBlur);
   }
   if ((rc = stage_event(ex, 5))) return rc;
   CUDA_TRY(cudaGetLastError());

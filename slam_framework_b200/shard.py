@@ -63,7 +63,7 @@ class SequenceRunner:
         self.L, self.devices, self.params, self.B, self.lanes = lib, list(devices), dict(params or {}), int(batch_pairs), int(lanes)
         self.seconds = None
 
-    def _device_loop(self, slot, dev, lo, hi, get_pair, bf, baseline, out, errors):
+    def _device_loop(self, slot, dev, lo, hi, get_pair, bf, baseline, out, errors, digests=True):
         from . import orbfe
         try:
             first = get_pair(lo)[0]
@@ -80,6 +80,9 @@ class SequenceRunner:
                 ex.sync()
                 for k, i in enumerate(range(*pend)):
                     n0, n1 = int(buf["n"][2 * k]), int(buf["n"][2 * k + 1])
+                    if not digests:   # throughput runs: keypoint counts and stereo matches only
+                        out[i] = (n0, n1, int((buf["ur"][2 * k, :n0] >= 0).sum()))
+                        continue
                     out[i] = digest([buf["kps"][2 * k, :n0], buf["desc"][2 * k, :n0], buf["kps"][2 * k + 1, :n1], buf["desc"][2 * k + 1, :n1],
                                      buf["ur"][2 * k, :n0], buf["depth"][2 * k, :n0]])
                 lane[2] = None
@@ -101,7 +104,7 @@ class SequenceRunner:
         except Exception as exc:  # surfaced by run()
             errors.append((slot, dev, exc))
 
-    def run(self, get_pair, n_pairs, bf, baseline):
+    def run(self, get_pair, n_pairs, bf, baseline, digests=True):
         import threading
         import time
         out, errors, threads = {}, [], []
@@ -110,7 +113,7 @@ class SequenceRunner:
             lo, hi = shard_range(n_pairs, slot, len(self.devices))
             if hi <= lo:
                 continue
-            t = threading.Thread(target=self._device_loop, args=(slot, dev, lo, hi, get_pair, bf, baseline, out, errors))
+            t = threading.Thread(target=self._device_loop, args=(slot, dev, lo, hi, get_pair, bf, baseline, out, errors, digests))
             t.start()
             threads.append(t)
         for t in threads:
