@@ -478,15 +478,17 @@ static int configure(orbfe_extractor* ex, int w0, int h0) {
     }
     CUDA_TRY(cudaMalloc(&ex->d_tmapsDescPyr, nl * sizeof(CUtensorMap)));
     CUDA_TRY(cudaMemcpy(ex->d_tmapsDescPyr, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-    for (int l = 0; l < nl; ++l) {
+    std::vector<CUtensorMap> maps2(2 * nl);  // [l]: 64-byte rows, [nl + l]: 48-byte rows (k_describe.cuh)
+    for (int l = 0; l < 2 * nl; ++l) {
+      const int lv = l % nl;
       OrbfeTmaPlane P;
-      P.base = ex->d_blur + g.lv[l].blurOff; P.sliceStride = g.blurStride; P.pitch = g.lv[l].bpitch;
-      P.rows = g.lv[l].h; P.slices = (int)S; P.boxW = ORBFE_DESC_BLUR_BW; P.boxH = ORBFE_DESC_BLUR_BH;
-      const int r = orbfe_tma_encode(&maps[l], P);
-      if (r != 0) return orbfe_fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled failed for the descriptor box of level %d (%d)", l, r);
+      P.base = ex->d_blur + g.lv[lv].blurOff; P.sliceStride = g.blurStride; P.pitch = g.lv[lv].bpitch;
+      P.rows = g.lv[lv].h; P.slices = (int)S; P.boxW = l < nl ? ORBFE_DESC_BLUR_BW : ORBFE_DESC_PYR_BW; P.boxH = ORBFE_DESC_BLUR_BH;
+      const int r = orbfe_tma_encode(&maps2[l], P);
+      if (r != 0) return orbfe_fail(ORBFE_ERR_CUDA, "cuTensorMapEncodeTiled failed for the descriptor box of level %d (%d)", lv, r);
     }
-    CUDA_TRY(cudaMalloc(&ex->d_tmapsDescBlur, nl * sizeof(CUtensorMap)));
-    CUDA_TRY(cudaMemcpy(ex->d_tmapsDescBlur, maps.data(), nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&ex->d_tmapsDescBlur, 2 * nl * sizeof(CUtensorMap)));
+    CUDA_TRY(cudaMemcpy(ex->d_tmapsDescBlur, maps2.data(), 2 * nl * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&ex->d_pyrBoxX, std::max<size_t>(pyrBoxX.size(), 1) * sizeof(int)));
     if (!pyrBoxX.empty())
       CUDA_TRY(cudaMemcpy(ex->d_pyrBoxX, pyrBoxX.data(), pyrBoxX.size() * sizeof(int), cudaMemcpyHostToDevice));
