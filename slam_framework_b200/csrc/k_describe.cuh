@@ -19,9 +19,6 @@
 #ifndef ORBFE_DESC_THREADS
 #define ORBFE_DESC_THREADS 64
 #endif
-#ifndef ORBFE_DESC_UNROLL
-#define ORBFE_DESC_UNROLL 2
-#endif
 // Both patches of a keypoint arrive by TMA (one cp.async.bulk.tensor each, issued by lane 0, orbfe_tma.cuh): the 31 x 31 disc of
 // the UNBLURRED level for the moments (box 48 B x 31 rows) and the 37 x 37 rBRIEF window of the BLURRED level (box 64 B x 37 rows).
 // A box starts at the 16-byte boundary at or below the patch's first column, so 31 + 15 <= 48 and 37 + 15 <= 64 bytes per row.
@@ -34,7 +31,6 @@
 #define ORBFE_DESC_BLUR_BW 64
 #define ORBFE_DESC_BLUR_BH 37
 #define ORBFE_DESC_BUF 2432  // bytes per buffer: 37 x 64 rounded up to a multiple of 128
-constexpr int kDescUnroll = ORBFE_DESC_UNROLL;  // keypoints processed per loop iteration (memory-level parallelism)
 
 // global (L1-cached) rather than __constant__: each lane reads ITS 32 bytes, and per-lane addresses in
 // the constant bank are serialised by the address-divergence unit (58 % ADU busy in the ncu profile)
@@ -120,8 +116,9 @@ __device__ __forceinline__ float orbfe_sincosf(float y, int is_cos) {
 #define ORBFE_DESC_PATSMEM 1  // pattern points as floats in shared memory instead of 32 registers per lane
 #endif
 #ifndef ORBFE_DESC_MINB
-// A/B on B200, 64 pairs (pattern in registers -> in smem): MINB 12 0.269 -> 0.249 ms; smem + MINB 14 (72 registers, 28 warps/SM)
-// 0.247; MINB 16 (64 registers, spills) 0.265; MINB 20 0.324; 128-thread CTAs 0.259; deeper keypoint unrolling (3, 4) 0.29-0.31
+// A/B on B200, 64 pairs, staged-by-loads form (pattern in registers -> in smem): MINB 12 0.269 -> 0.249 ms; smem + MINB 14
+// (72 registers, 28 warps/SM) 0.247; MINB 16 (64 registers, spills) 0.265; MINB 20 0.324; 128-thread CTAs 0.259.
+// TMA form: MINB 12 0.197, MINB 14 0.191, MINB 16 0.191, 128-thread CTAs (MINB 7) 0.191
 #define ORBFE_DESC_MINB 14
 #endif
 __global__ void __launch_bounds__(ORBFE_DESC_THREADS, ORBFE_DESC_MINB)
