@@ -281,13 +281,10 @@ k_octree(const __grid_constant__ Geom g, const int* __restrict__ cellCnt, const 
     }
     __syncthreads();
     if (finish) break;
-    // next generation becomes current; clear the NEW flag of the keys
-    for (int k = tid; k < n; k += T) {
-      const int v = knode[k];
-      if (v >= 0) knode[k] = v & ~ORBFE_OCT_NEW;
-    }
+    // next generation becomes current.  The NEW flag of the moved keys needs no clearing pass: step B of the next generation
+    // masks it when it reads a key and rewrites the key without it, and nothing reads knode[] in between (the barrier after
+    // the counter reset below orders G's writes before B's reads).
     OctNode* t = cur; cur = nxt; nxt = t;
-    __syncthreads();
   }
 
   // ---- 4. finals: add the expandable nodes still alive, pick the best key of each (:682-701) --
