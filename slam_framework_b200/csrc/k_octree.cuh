@@ -62,6 +62,7 @@ k_octree(const __grid_constant__ Geom g, const int* __restrict__ cellCnt, const 
   // grid = (slots, levels): blocks are dispatched x-first, so the long level-0 trees of every image start first and the
   // short top-level ones fill the tail of the launch
   const int level = blockIdx.y, slot = blockIdx.x;
+  const bool latencyForm = gridDim.x <= 8;  // a few frames in flight: barrier-bound, see orbfe_block_sort_desc
   const LevelGeom& L = g.lv[level];
   const int N = L.N;
 
@@ -197,7 +198,7 @@ k_octree(const __grid_constant__ Geom g, const int* __restrict__ cellCnt, const 
       for (int p = tid; p < m2; p += T)
         s_sort[p] = p < m ? (((unsigned long long)(unsigned)cur[p].cnt << 32) | (unsigned)p) : 0ull;
       // (cnt, creation index) descending == back-to-front walk of the ascending std::sort (:625-627)
-      orbfe_block_sort_desc(s_sort, m2);
+      orbfe_block_sort_desc(s_sort, m2, latencyForm);
     }
     // E: prefix scans in processing order (chunks of T)
     int baseNe = 0, baseNx = 0, baseDelta = 0, nSplit = 0;
@@ -214,8 +215,16 @@ k_octree(const __grid_constant__ Geom g, const int* __restrict__ cellCnt, const 
       const int exDelta = orbfe_block_exscan(p < m ? ne - 1 : 0, s_scan, &totDelta);
       // a node is split iff the list was still below N before it (:672-673); phase-1 splits all
       const bool split = p < m && (mode == 0 || prevSize + baseDelta + exDelta < N);
-      const int exNe = orbfe_block_exscan(split ? ne : 0, s_scan, &totNe);
-      const int exNx = orbfe_block_exscan(split ? nx : 0, s_scan, &totNx);
+      int exNe, exNx;
+      if (L.nodeCap < 65536) {  // block-uniform: the two child counts share one scan while their sums fit 16 bits each
+        int totP;               // (a generation creates at most nodeCap children)
+        const int exP = orbfe_block_exscan(split ? (ne | (nx << 16)) : 0, s_scan, &totP);
+        exNe = exP & 0xffff; exNx = exP >> 16;
+        totNe = totP & 0xffff; totNx = totP >> 16;
+      } else {
+        exNe = orbfe_block_exscan(split ? ne : 0, s_scan, &totNe);
+        exNx = orbfe_block_exscan(split ? nx : 0, s_scan, &totNx);
+      }
       if (p < m) {
         if (split) {
           const OctNode nd = cur[j];
@@ -333,7 +342,7 @@ k_octree(const __grid_constant__ Geom g, const int* __restrict__ cellCnt, const 
   while (n2 < nfin) n2 <<= 1;
   for (int t = tid; t < n2; t += T)
     s_sort[t] = t < nfin ? ((((unsigned long long)(unsigned)finSeq[t] + 1ull) << 32) | (unsigned)t) : 0ull;
-  orbfe_block_sort_desc(s_sort, n2);
+  orbfe_block_sort_desc(s_sort, n2, latencyForm);
   for (int t = tid; t < nfin; t += T) out[t] = cand[finKey[(int)(s_sort[t] & 0xffffffffu)]];
   if (tid == 0) *outCnt = nfin;
 }

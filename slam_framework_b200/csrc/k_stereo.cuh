@@ -206,8 +206,10 @@ k_stereo_search(const __grid_constant__ Geom g, const StereoPair* __restrict__ p
 
 __global__ void __launch_bounds__(ORBFE_ST_THREADS)
 k_stereo_median(const StereoPair* __restrict__ pairs, const int maxKp, int* __restrict__ nMatched) {
+  static_assert(ORBFE_ST_THREADS >= 256 && ORBFE_ST_THREADS % 32 == 0, "one histogram bin per thread in the rank search");
   __shared__ int s_hist[256];
   __shared__ int s_sel[4];
+  __shared__ int s_scan[33];
   const StereoPair P = pairs[blockIdx.x];
   const int nL = min(*P.nL, maxKp);
   const int tid = threadIdx.x;
@@ -234,10 +236,11 @@ k_stereo_median(const StereoPair* __restrict__ pairs, const int maxKp, int* __re
     if (s >= 0) atomicAdd(&s_hist[(s >> 8) & 0xff], 1);
   }
   __syncthreads();
-  if (tid == 0) {
-    int acc = 0, b = 0;
-    for (; b < 256; ++b) { if (acc + s_hist[b] > rank) break; acc += s_hist[b]; }
-    s_sel[0] = b; s_sel[1] = rank - acc;
+  {  // the bin that holds element `rank`: exclusive prefix <= rank < inclusive prefix (one bin per thread, block scan)
+    const int hcnt = tid < 256 ? s_hist[tid] : 0;
+    int tot;
+    const int ex = orbfe_block_exscan(hcnt, s_scan, &tot);
+    if (tid < 256 && ex <= rank && rank < ex + hcnt) { s_sel[0] = tid; s_sel[1] = rank - ex; }
   }
   __syncthreads();
   const int hiBin = s_sel[0], rank2 = s_sel[1];
@@ -249,10 +252,11 @@ k_stereo_median(const StereoPair* __restrict__ pairs, const int maxKp, int* __re
     if (s >= 0 && ((s >> 8) & 0xff) == hiBin) atomicAdd(&s_hist[s & 0xff], 1);
   }
   __syncthreads();
-  if (tid == 0) {
-    int acc = 0, b = 0;
-    for (; b < 256; ++b) { if (acc + s_hist[b] > rank2) break; acc += s_hist[b]; }
-    s_sel[2] = (hiBin << 8) | b;
+  {
+    const int hcnt = tid < 256 ? s_hist[tid] : 0;
+    int tot;
+    const int ex = orbfe_block_exscan(hcnt, s_scan, &tot);
+    if (tid < 256 && ex <= rank2 && rank2 < ex + hcnt) s_sel[2] = (hiBin << 8) | tid;
   }
   __syncthreads();
   const float median = (float)s_sel[2];
