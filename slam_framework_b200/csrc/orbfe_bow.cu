@@ -43,8 +43,12 @@ struct orbfe_vocabulary {
   unsigned *d_word = nullptr, *d_node = nullptr, *d_bowWord = nullptr, *d_fvNode = nullptr, *d_fvIdx = nullptr;
   double *d_fw = nullptr, *d_bowValue = nullptr;
   unsigned long long *d_wkey = nullptr, *d_nkey = nullptr;
-  int *d_bowStart = nullptr, *d_fvStart = nullptr, *d_counts = nullptr;
-  int* h_counts = nullptr;  // pinned
+  int *d_bowStart = nullptr, *d_fvStart = nullptr, *d_counts = nullptr;   // d_fvStart, d_counts and the arrays above: views into d_out
+  // one transform = one H2D copy (descriptors from a pinned staging copy) and ONE D2H copy: every output array lives in one
+  // device block (laid out per call for n features) with a pinned mirror
+  char* d_out = nullptr;
+  char* h_out = nullptr;    // pinned
+  uint8_t* h_feat = nullptr;  // pinned
   VocabTree tree() const {
     VocabTree V;
     V.desc = d_desc; V.childStart = d_childStart; V.child = d_child; V.weight = d_weight; V.wordId = d_wordId;
@@ -67,10 +71,15 @@ static int ensure_scratch(orbfe_vocabulary* v, int n) {
   CUDA_TRY(cudaStreamSynchronize(v->stream));
   const size_t c = (size_t)n2;
   CUDA_TRY(regrow(&v->d_feat, c * 32));
-  CUDA_TRY(regrow(&v->d_word, c)); CUDA_TRY(regrow(&v->d_node, c)); CUDA_TRY(regrow(&v->d_bowWord, c));
-  CUDA_TRY(regrow(&v->d_fvNode, c)); CUDA_TRY(regrow(&v->d_fvIdx, c)); CUDA_TRY(regrow(&v->d_fw, c));
-  CUDA_TRY(regrow(&v->d_bowValue, c)); CUDA_TRY(regrow(&v->d_wkey, c)); CUDA_TRY(regrow(&v->d_nkey, c));
-  CUDA_TRY(regrow(&v->d_bowStart, c + 1)); CUDA_TRY(regrow(&v->d_fvStart, c + 1));
+  CUDA_TRY(regrow(&v->d_fw, c));
+  CUDA_TRY(regrow(&v->d_wkey, c)); CUDA_TRY(regrow(&v->d_nkey, c));
+  CUDA_TRY(regrow(&v->d_bowStart, c + 1));
+  CUDA_TRY(regrow(&v->d_out, 36 * c + 256));
+  if (v->h_out) cudaFreeHost(v->h_out);
+  if (v->h_feat) cudaFreeHost(v->h_feat);
+  v->h_out = nullptr; v->h_feat = nullptr;
+  CUDA_TRY(cudaMallocHost(&v->h_out, 36 * c + 256));
+  CUDA_TRY(cudaMallocHost(&v->h_feat, c * 32));
   v->cap = n2;
   return ORBFE_OK;
 }
@@ -82,10 +91,10 @@ int orbfe_vocabulary_destroy(orbfe_vocabulary* v) {
   cudaSetDevice(v->device);
   if (v->stream) cudaStreamSynchronize(v->stream);
   cudaFree(v->d_desc); cudaFree(v->d_childStart); cudaFree(v->d_child); cudaFree(v->d_weight); cudaFree(v->d_wordId);
-  cudaFree(v->d_feat); cudaFree(v->d_word); cudaFree(v->d_node); cudaFree(v->d_bowWord); cudaFree(v->d_fvNode);
-  cudaFree(v->d_fvIdx); cudaFree(v->d_fw); cudaFree(v->d_bowValue); cudaFree(v->d_wkey); cudaFree(v->d_nkey);
-  cudaFree(v->d_bowStart); cudaFree(v->d_fvStart); cudaFree(v->d_counts);
-  cudaFreeHost(v->h_counts);
+  cudaFree(v->d_feat); cudaFree(v->d_fw); cudaFree(v->d_wkey); cudaFree(v->d_nkey);
+  cudaFree(v->d_bowStart); cudaFree(v->d_out);
+  if (v->h_out) cudaFreeHost(v->h_out);
+  if (v->h_feat) cudaFreeHost(v->h_feat);
   if (v->stream) cudaStreamDestroy(v->stream);
   delete v;
   return ORBFE_OK;
@@ -130,8 +139,6 @@ int orbfe_vocabulary_create(int device, int k, int L, int scoring, int weighting
   if (e == cudaSuccess) e = cudaMalloc(&v->d_child, (child.size() + 1) * sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc(&v->d_weight, (size_t)n_nodes * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&v->d_wordId, (size_t)n_nodes * sizeof(unsigned));
-  if (e == cudaSuccess) e = cudaMalloc(&v->d_counts, 4 * sizeof(int));
-  if (e == cudaSuccess) e = cudaMallocHost(&v->h_counts, 4 * sizeof(int));
   // node 0 (root): no descriptor / weight in the file
   if (e == cudaSuccess) e = cudaMemcpy(v->d_desc, d0.data(), 32, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(v->d_weight, w0.data(), sizeof(double), cudaMemcpyHostToDevice);
@@ -210,7 +217,19 @@ int orbfe_bow_transform(orbfe_vocabulary* v, int n, const uint8_t* desc, int lev
   int n2 = 1024;
   while (n2 < n) n2 <<= 1;
   cudaStream_t st = v->stream;
-  CUDA_TRY(cudaMemcpyAsync(v->d_feat, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+  // output block for n features: counts | bowValue (f64) | word | node | bowWord | fvNode | fvIdx | fvStart (n + 1)
+  const size_t N = ((size_t)n + 3) & ~(size_t)3;
+  size_t off = 16;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+  const size_t oVal = take(N * 8), oWord = take(N * 4), oNode = take(N * 4), oBw = take(N * 4), oFn = take(N * 4), oFi = take(N * 4),
+               oFs = take((N + 4) * 4);
+  v->d_counts = reinterpret_cast<int*>(v->d_out);
+  v->d_bowValue = reinterpret_cast<double*>(v->d_out + oVal);
+  v->d_word = reinterpret_cast<unsigned*>(v->d_out + oWord); v->d_node = reinterpret_cast<unsigned*>(v->d_out + oNode);
+  v->d_bowWord = reinterpret_cast<unsigned*>(v->d_out + oBw); v->d_fvNode = reinterpret_cast<unsigned*>(v->d_out + oFn);
+  v->d_fvIdx = reinterpret_cast<unsigned*>(v->d_out + oFi); v->d_fvStart = reinterpret_cast<int*>(v->d_out + oFs);
+  memcpy(v->h_feat, desc, (size_t)n * 32);
+  CUDA_TRY(cudaMemcpyAsync(v->d_feat, v->h_feat, (size_t)n * 32, cudaMemcpyHostToDevice, st));
   BOW_LAUNCH(v, k_bow_descend, dim3((n + ORBFE_BOW_THREADS / 32 - 1) / (ORBFE_BOW_THREADS / 32)), dim3(ORBFE_BOW_THREADS), v->tree(),
              v->d_feat, n, levelsup, v->d_word, v->d_node, v->d_fw, v->d_wkey, v->d_nkey);
   // scoring -> normalisation (ScoringObject.h:73-90): L2_NORM -> L2, DOT_PRODUCT -> none, everything else L1
@@ -220,21 +239,22 @@ int orbfe_bow_transform(orbfe_vocabulary* v, int n, const uint8_t* desc, int lev
   O.fvStart = v->d_fvStart; O.fvIdx = v->d_fvIdx; O.counts = v->d_counts;
   BOW_LAUNCH(v, k_bow_assemble, dim3(1), dim3(1024), v->d_wkey, v->d_nkey, n, n2, v->d_fw, v->weighting, norm, O);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(v->h_counts, v->d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (word_id) CUDA_TRY(cudaMemcpyAsync(word_id, v->d_word, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-  if (node_id) CUDA_TRY(cudaMemcpyAsync(node_id, v->d_node, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(v->h_out, v->d_out, off, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  const int nb = v->h_counts[0], nf = v->h_counts[1], kept = v->h_counts[2];
+  const int* hc = reinterpret_cast<const int*>(v->h_out);
+  const int nb = hc[0], nf = hc[1], kept = hc[2];
+  if (nb < 0 || nb > n || nf < 0 || nf > n || kept < 0 || kept > n) return orbfe_fail(ORBFE_ERR_CUDA, "vocabulary transform returned inconsistent counts");
+  if (word_id) memcpy(word_id, v->h_out + oWord, (size_t)n * sizeof(unsigned));
+  if (node_id) memcpy(node_id, v->h_out + oNode, (size_t)n * sizeof(unsigned));
   if (nb) {
-    CUDA_TRY(cudaMemcpyAsync(bow_words, v->d_bowWord, (size_t)nb * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(bow_values, v->d_bowValue, (size_t)nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+    memcpy(bow_words, v->h_out + oBw, (size_t)nb * sizeof(unsigned));
+    memcpy(bow_values, v->h_out + oVal, (size_t)nb * sizeof(double));
   }
   if (nf) {
-    CUDA_TRY(cudaMemcpyAsync(fv_nodes, v->d_fvNode, (size_t)nf * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(fv_idx, v->d_fvIdx, (size_t)kept * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    memcpy(fv_nodes, v->h_out + oFn, (size_t)nf * sizeof(unsigned));
+    memcpy(fv_idx, v->h_out + oFi, (size_t)kept * sizeof(unsigned));
   }
-  CUDA_TRY(cudaMemcpyAsync(fv_start, v->d_fvStart, ((size_t)nf + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(fv_start, v->h_out + oFs, ((size_t)nf + 1) * sizeof(int));
   *n_bow = nb; *n_fv = nf;
   return ORBFE_OK;
 }

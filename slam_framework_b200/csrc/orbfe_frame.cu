@@ -34,6 +34,8 @@ struct ScratchCache {
   int device = -1;
   char* base = nullptr;
   size_t cap = 0;
+  char* pinned = nullptr;   // host staging: a call packs its inputs here (ONE H2D copy) and lands its outputs here (ONE D2H copy)
+  size_t pinnedCap = 0;
   ~ScratchCache() { /* the CUDA context may be gone at thread exit: the block is left to process teardown */ }
 };
 static thread_local ScratchCache t_scratch;
@@ -55,6 +57,20 @@ struct DeviceArena {
       c.cap = want;
     }
     base = c.base; cap = c.cap; used = 0;
+    return cudaSuccess;
+  }
+  // the calling thread's pinned staging block, at least `bytes` long
+  static cudaError_t pinned(size_t bytes, char** out) {
+    ScratchCache& c = t_scratch;
+    if (c.pinnedCap < bytes) {
+      if (c.pinned) cudaFreeHost(c.pinned);
+      c.pinned = nullptr; c.pinnedCap = 0;
+      const size_t want = bytes + bytes / 2 + 4096;
+      const cudaError_t e = cudaMallocHost(&c.pinned, want);
+      if (e != cudaSuccess) { c.pinned = nullptr; return e; }
+      c.pinnedCap = want;
+    }
+    *out = c.pinned;
     return cudaSuccess;
   }
 };
@@ -109,31 +125,35 @@ int orbfe_is_in_frustum(int device, int n, const float* world_pos, const float* 
   F.fx = fx; F.fy = fy; F.cx = cx; F.cy = cy; F.bf = bf; F.minX = min_x; F.maxX = max_x; F.minY = min_y; F.maxY = max_y;
   F.logScaleFactor = log_scale_factor; F.viewingCosLimit = viewing_cos_limit; F.nLevels = n_levels;
   const size_t N = (size_t)n;
+  // inputs: world (3N) | normal (3N) | min | max | raw floats; outputs: px | py | pxr | view_cos floats | level ints | count | in_view bytes.
+  // Both blocks are contiguous on the device and mirrored in pinned host memory: one copy each way instead of twelve.
+  const size_t inBytes = 9 * N * 4, outBytes = 5 * N * 4 + 16 + N;
   DeviceArena A;
-  CUDA_TRY(A.acquire(device, 2 * DeviceArena::pad(N * 12) + 8 * DeviceArena::pad(N * 4) + DeviceArena::pad(N) + 256));
-  float* d_w = A.take<float>(N * 3); float* d_n = A.take<float>(N * 3);
-  float* d_min = A.take<float>(N); float* d_max = A.take<float>(N); float* d_raw = A.take<float>(N);
-  float* d_px = A.take<float>(N); float* d_py = A.take<float>(N); float* d_pxr = A.take<float>(N); float* d_vc = A.take<float>(N);
-  int* d_lvl = A.take<int>(N);
-  uint8_t* d_in = A.take<uint8_t>(N);
-  int* d_cnt = A.take<int>(1);
-  CUDA_TRY(cudaMemcpy(d_w, world_pos, N * 12, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(d_n, normal, N * 12, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(d_min, min_dist, N * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(d_max, max_dist, N * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMemcpy(d_raw, max_dist_raw, N * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(A.acquire(device, DeviceArena::pad(inBytes) + DeviceArena::pad(outBytes) + 256));
+  char* h = nullptr;
+  CUDA_TRY(DeviceArena::pinned(DeviceArena::pad(inBytes) + outBytes, &h));
+  float* d_w = A.take<float>(9 * N);
+  float* d_n = d_w + 3 * N; float* d_min = d_n + 3 * N; float* d_max = d_min + N; float* d_raw = d_max + N;
+  char* d_outBlock = A.take<char>(outBytes);
+  float* d_px = reinterpret_cast<float*>(d_outBlock); float* d_py = d_px + N; float* d_pxr = d_py + N; float* d_vc = d_pxr + N;
+  int* d_lvl = reinterpret_cast<int*>(d_vc + N);
+  int* d_cnt = d_lvl + N;
+  uint8_t* d_in = reinterpret_cast<uint8_t*>(d_cnt + 4);
+  float* hIn = reinterpret_cast<float*>(h);
+  memcpy(hIn, world_pos, N * 12); memcpy(hIn + 3 * N, normal, N * 12);
+  memcpy(hIn + 6 * N, min_dist, N * 4); memcpy(hIn + 7 * N, max_dist, N * 4); memcpy(hIn + 8 * N, max_dist_raw, N * 4);
+  CUDA_TRY(cudaMemcpy(d_w, hIn, inBytes, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemset(d_cnt, 0, sizeof(int)));
   FRAME_LAUNCH(k_is_in_frustum, dim3((n + 255) / 256), dim3(256), F, n, d_w, d_n, d_min, d_max, d_raw, d_in, d_px, d_py, d_pxr, d_lvl,
                d_vc, d_cnt);
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpy(in_view, d_in, N, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(proj_x, d_px, N * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(proj_y, d_py, N * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(proj_xr, d_pxr, N * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(scale_level, d_lvl, N * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(cudaMemcpy(view_cos, d_vc, N * 4, cudaMemcpyDeviceToHost));
+  char* hOut = h + DeviceArena::pad(inBytes);
+  CUDA_TRY(cudaMemcpy(hOut, d_outBlock, outBytes, cudaMemcpyDeviceToHost));
+  memcpy(proj_x, hOut, N * 4); memcpy(proj_y, hOut + N * 4, N * 4); memcpy(proj_xr, hOut + 2 * N * 4, N * 4);
+  memcpy(view_cos, hOut + 3 * N * 4, N * 4); memcpy(scale_level, hOut + 4 * N * 4, N * 4);
   int cnt = 0;
-  CUDA_TRY(cudaMemcpy(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost));
+  memcpy(&cnt, hOut + 5 * N * 4, sizeof(int));
+  memcpy(in_view, hOut + 5 * N * 4 + 16, N);
   if (n_in_view) *n_in_view = cnt;
   return ORBFE_OK;
 }

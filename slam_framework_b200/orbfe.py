@@ -451,7 +451,10 @@ class OrbMatcher:
 
 
 def flatten_feature_vector(fv):
-    """DBoW2::FeatureVector (dict node id -> list of feature indices) -> (ids ascending, starts, indices)"""
+    """DBoW2::FeatureVector (dict node id -> list of feature indices) -> (ids ascending, starts, indices); a tuple that is
+    already in that form passes through (callers that keep their feature vectors flat, as the C++ shim does)"""
+    if isinstance(fv, tuple):
+        return fv
     ids = np.array(sorted(fv), np.uint32)
     starts = np.zeros(len(ids) + 1, np.int32)
     idx = []
