@@ -767,9 +767,16 @@ struct SolveCfg {
   int* iowner;    // init: per-keypoint owner scratch
   int* hist;      // ORBFE_HISTO_LENGTH rotation-histogram bins, zeroed by the host with the cursor block
 };
+// A/B on B200 (tools/probes/solve_probe.py; 20 000 queries against 8000 keypoints / 2000 against 2000): 512 threads, 64 registers
+// 0.344 / 0.090 ms; 512 x 3 CTAs (40 registers, spills) 0.482 / 0.091; 256 x 4 0.375 / 0.090; 256 x 6 0.510 / 0.090; 128 x 12 0.549 / 0.090
+#ifndef ORBFE_SOLVE_THREADS
 #define ORBFE_SOLVE_THREADS 512
+#endif
+#ifndef ORBFE_SOLVE_MINB
+#define ORBFE_SOLVE_MINB 1
+#endif
 
-__global__ void __launch_bounds__(ORBFE_SOLVE_THREADS)
+__global__ void __launch_bounds__(ORBFE_SOLVE_THREADS, ORBFE_SOLVE_MINB)
 k_match_solve(const FrameGrid F, const MatchQueries Q, const BowQueries BQ, const BowFilter B, const MatchScratch S, const ResolveArgs A,
               const JacobiState J, const InitJacobi IJ, const SolveCfg C) {
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
