@@ -117,6 +117,19 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(n_seq, pairs_per_batch, distinct, world):
+    """`config` of the JSON line: the workload, identical for the GPU arm and the reference (CPU) arm of the same invocation"""
+    n_img = 2 * pairs_per_batch
+    lo, hi = 0, -(-n_seq // world)
+    return {"workload": f"configs[2]: offline batch of {n_seq} synthetic KITTI-size stereo pairs (1241x376; configs[1] per pair: "
+                        "L+R ORB extraction, nFeatures 2000, 8 levels, 1.2, FAST 20/7, + ComputeStereoMatches), sharded "
+                        "frame-wise across the ranks, processed in batches",
+            "step": "one pass over the whole sequence (each rank: its contiguous shard)", "sequence_pairs": n_seq,
+            "pairs_per_batch": pairs_per_batch, "batches_per_step_rank0": -(-min(hi, n_seq) // pairs_per_batch), "distinct_pairs": distinct,
+            "parallelism": f"frames sharded x{world}, no collective",
+            "l2": "per-batch working set (images+pyramids+blur) ~%d MB > 126 MB L2" % ((n_img * (H * W + 2 * 1738559)) >> 20)}
+
+
 def make_pairs(n, seed0):
     from slam_framework_b200 import synth
     return [synth.stereo_pair(H, W, seed=seed0 + i) for i in range(n)]
@@ -198,10 +211,9 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": f"configs[2]: offline batch of {SEQ_PAIRS} synthetic KITTI-size stereo pairs (1241x376; configs[1] per "
-                                  "pair: L+R ORB extraction, nFeatures 2000, 8 levels, 1.2, FAST 20/7, + ComputeStereoMatches); each "
-                                  "step is a bounded sample of the sequence",
-                      "pairs_per_step": per_step, "sequence_pairs": SEQ_PAIRS, "nfeatures": NFEATURES, "levels": NLEVELS},
+           "config": workload_config(args.sequence, args.pairs, min(args.pairs, args.distinct), max(args.gpus, 1)),
+           "reference_sample": {"pairs_per_step": per_step, "note": "each step of this arm is a bounded sample of the sequence "
+                                "(the same synthetic pairs, seeds 0..) on the host cores"},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
                             "port_value": done / sec, "reference_build_value": ref_build,
                             "note": "port = oracle restatement; reference_build = the reference's own sources compiled against the "
@@ -632,13 +644,7 @@ def run_ours(args):
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "u8", "data": "synthetic",
-           "config": {"workload": f"configs[2]: offline batch of {n_seq} synthetic KITTI-size stereo pairs (1241x376; configs[1] per pair: "
-                                  "L+R ORB extraction, nFeatures 2000, 8 levels, 1.2, FAST 20/7, + ComputeStereoMatches), sharded "
-                                  "frame-wise across the ranks, processed in batches",
-                      "step": "one pass over the whole sequence (each rank: its contiguous shard)", "sequence_pairs": n_seq,
-                      "pairs_per_batch": B, "batches_per_step_rank0": n_batches, "distinct_pairs": distinct,
-                      "parallelism": f"frames sharded x{world}, no collective", "host_affinity_cores": numa,
-                      "l2": "per-batch working set (images+pyramids+blur) ~%d MB > 126 MB L2" % ((n_img * (H * W + 2 * 1738559)) >> 20)},
+           "config": workload_config(n_seq, B, distinct, world), "host_affinity_cores": numa,
            "gpu_launches": int(launches),
            "value_multistream": {"value": n_seq * args.steps / t_lanes, "unit": UNIT, "streams": NL,
                                  "note": "inputs resident, batches issued round-robin on the handles the e2e leg uses (wall clock); "
