@@ -52,29 +52,51 @@ class SequenceRunner:
     walks the sequence in a loop).  The pairs are sharded contiguously across `devices` (shard_range); each device gets one host
     thread (the C-ABI calls release the GIL) and `lanes` extractor handles = `lanes` streams, which take the device's batches in
     turn so that the H2D copy of batch k+1 and the D2H copy of batch k-1 overlap the kernels of batch k.  No device talks to
-    another: frames do not interact on this path.
+    another: frames do not interact on this path.  The handles (arenas, pinned result buffers) are created by the first run and
+    kept until close().
 
         runner = SequenceRunner(lib, devices=[0, 1, 2, 3], params=dict(nfeatures=2000), batch_pairs=64)
         digests = runner.run(get_pair, n_pairs, bf, baseline)          # {pair index: sha256 of its outputs}
 
-    get_pair(i) -> (left, right) u8 arrays.  The digests equal those of the per-rank run (process_sequence) frame by frame."""
+    get_pair(i) -> (left, right) u8 arrays; or get_batch(s, e) -> one contiguous (2 (e - s), H, W) u8 array holding the pairs
+    s .. e-1 as L, R, L, R, ... (ideally in pinned memory: it is handed to the DMA engine as it is).  The digests equal those of
+    the per-rank run (process_sequence) frame by frame; digests=False returns (n_left, n_right, n_stereo) per pair instead."""
 
     def __init__(self, lib, devices, params=None, batch_pairs=64, lanes=2):
         self.L, self.devices, self.params, self.B, self.lanes = lib, list(devices), dict(params or {}), int(batch_pairs), int(lanes)
         self.seconds = None
+        self._lanes = {}   # device slot -> [[extractor, host buffers, pending pair range], ...]
 
-    def _device_loop(self, slot, dev, lo, hi, get_pair, bf, baseline, out, errors, digests=True):
+    def _buffers(self, ex, n_img):
+        """make_buffers layout, in pinned host memory when torch is there (the D2H copies then need no staging)"""
         from . import orbfe
         try:
-            first = get_pair(lo)[0]
-            h, w = first.shape
-            lanes = []
-            for _ in range(self.lanes):
-                ex = orbfe.ORBextractor(device=dev, max_images=2 * self.B, max_size=(w, h), lib=self.L, **self.params)
-                lanes.append([ex, ex.make_buffers(2 * self.B, stereo=True), None])   # handle, host buffers, pending pair range
+            import torch
+            cap = ex.max_keypoints()
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+            return dict(kps=mk((n_img, cap, 28), torch.uint8).view(orbfe.KP_DTYPE).reshape(n_img, cap), desc=mk((n_img, cap, 32), torch.uint8),
+                        n=mk((n_img,), torch.int32), cap=cap, ur=mk((n_img, cap), torch.float32), depth=mk((n_img, cap), torch.float32))
+        except Exception:
+            return ex.make_buffers(n_img, stereo=True)
+
+    def _device_loop(self, slot, dev, lo, hi, get_pair, get_batch, bf, baseline, out, errors, digests):
+        import ctypes
+        from . import orbfe
+        try:
+            if get_batch is not None:
+                h, w = get_batch(lo, lo + 1).shape[1:]
+            else:
+                h, w = get_pair(lo)[0].shape
+            lanes = self._lanes.get(slot)
+            if lanes is None or lanes[0][0].max_images != 2 * self.B:
+                lanes = []
+                for _ in range(self.lanes):
+                    ex = orbfe.ORBextractor(device=dev, max_images=2 * self.B, max_size=(w, h), lib=self.L, **self.params)
+                    lanes.append([ex, self._buffers(ex, 2 * self.B), None])   # handle, host buffers, pending pair range
+                self._lanes[slot] = lanes
 
             def collect(lane):
-                ex, buf, pend = lane
+                ex, buf, pend = lane[0], lane[1], lane[2]
                 if pend is None:
                     return
                 ex.sync()
@@ -90,21 +112,29 @@ class SequenceRunner:
                 lane = lanes[j % self.lanes]
                 collect(lane)                      # the batch this handle took `lanes` batches ago has delivered
                 e = min(s + self.B, hi)
-                imgs = [im for i in range(s, e) for im in get_pair(i)]
-                ex, buf, _ = lane
-                ex.upload(imgs)
-                ex.run(len(imgs))
+                ex, buf = lane[0], lane[1]
+                if get_batch is not None:
+                    frames = get_batch(s, e)
+                    n_img = len(frames)
+                    ptrs = (ctypes.c_void_p * n_img)(*[frames[i].ctypes.data for i in range(n_img)])
+                    ex.upload_ptrs(ptrs, n_img, w, h, frames.strides[1])
+                    lane.append(frames)            # keeps the source alive until the copy has been consumed
+                    del lane[3:-1]
+                else:
+                    imgs = [im for i in range(s, e) for im in get_pair(i)]
+                    n_img = len(imgs)
+                    ex.upload(imgs)
+                ex.run(n_img)
                 ex.run_stereo(e - s, bf, baseline)
-                ex.download_async(len(imgs), buf)
+                ex.download_async(n_img, buf)
                 lane[2] = (s, e)
             for lane in lanes:
                 collect(lane)
-            for ex, _, _ in lanes:
-                ex.close()
+                del lane[3:]
         except Exception as exc:  # surfaced by run()
             errors.append((slot, dev, exc))
 
-    def run(self, get_pair, n_pairs, bf, baseline, digests=True):
+    def run(self, get_pair, n_pairs, bf, baseline, digests=True, get_batch=None):
         import threading
         import time
         out, errors, threads = {}, [], []
@@ -113,7 +143,7 @@ class SequenceRunner:
             lo, hi = shard_range(n_pairs, slot, len(self.devices))
             if hi <= lo:
                 continue
-            t = threading.Thread(target=self._device_loop, args=(slot, dev, lo, hi, get_pair, bf, baseline, out, errors, digests))
+            t = threading.Thread(target=self._device_loop, args=(slot, dev, lo, hi, get_pair, get_batch, bf, baseline, out, errors, digests))
             t.start()
             threads.append(t)
         for t in threads:
@@ -122,3 +152,9 @@ class SequenceRunner:
         if errors:
             raise RuntimeError(f"device loop failed: {errors[0]}")
         return out
+
+    def close(self):
+        for lanes in self._lanes.values():
+            for lane in lanes:
+                lane[0].close()
+        self._lanes = {}

@@ -468,6 +468,9 @@ def test_single_process_multi_gpu_runner_matches_per_rank_digests(lib):
     for devices in ([0], list(range(ndev)) if ndev > 1 else [0, 0, 0]):
         runner = shard.SequenceRunner(lib, devices=devices, params=dict(nfeatures=1000), batch_pairs=4, lanes=2)
         assert runner.run(lambda i: pairs[i], n_pairs, bf, bl) == single
+        frames = np.stack([im for p in pairs for im in p])
+        assert runner.run(None, n_pairs, bf, bl, get_batch=lambda s, e: frames[2 * s:2 * e]) == single   # the batch form, kept handles
+        runner.close()
 
 
 def test_extract_graph_replay_equals_plain_path(lib, monkeypatch):

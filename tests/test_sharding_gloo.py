@@ -86,3 +86,10 @@ def test_single_process_runner_matches_per_rank_run():
     got = runner.run(lambda i: synth.stereo_pair(120, 400, seed=50 + i), N_PAIRS, 386.1448, 386.1448 / 718.856)
     assert got == single
     assert runner.seconds > 0
+    # the batch form (one contiguous block of frames per batch, handed to the copy engine as it is) on the same, kept handles
+    import numpy as np
+    frames = np.stack([im for i in range(N_PAIRS) for im in synth.stereo_pair(120, 400, seed=50 + i)])
+    assert runner.run(None, N_PAIRS, 386.1448, 386.1448 / 718.856, get_batch=lambda s, e: frames[2 * s:2 * e]) == single
+    counts = runner.run(None, N_PAIRS, 386.1448, 386.1448 / 718.856, digests=False, get_batch=lambda s, e: frames[2 * s:2 * e])
+    assert sorted(counts) == list(range(N_PAIRS)) and all(len(c) == 3 and c[0] > 0 for c in counts.values())
+    runner.close()

@@ -56,13 +56,13 @@ if cfg and "error" not in cfg:
         extra = "".join(f"; {a.replace('gpu_', '').replace('_p50_ms', '')}: {v[a]:.3f}" for a in ("gpu_fused_p50_ms", "gpu_cpp_shim_p50_ms") if a in v)
         out.append(f"| {k} | {v['gpu_p50_ms']:.3f}{extra} | {v['cpu_p50_ms']:.1f} ({v['cpu_threads']}) | {v['path']} |")
     out.append("")
-sc = [(n, jline(f)) for n in (1, 2, 4, 8) for f in [newest(f"r02*_bench_n{n}.json")] if f]
+sc = [(n, jline(f)) for n in (1, 2, 4, 8) for f in [newest(f"r02g_bench_n{n}.json")] if f]
 ceil = newest("r02*_copy_ceiling_8gpu.json")
 if len(sc) > 1 and ceil:
     cj = {r_["gpus"]: r_ for r_ in json.load(open(ceil))["runs"]}
-    sc8 = [(n, jline(os.path.join(P, f"r02d_bench_n{n}.json"))) for n in (1, 2, 4, 8) if os.path.exists(os.path.join(P, f"r02d_bench_n{n}.json"))]
+    sc8 = [(n, jline(os.path.join(P, f"r02g_bench_n{n}.json"))) for n in (1, 2, 4, 8) if os.path.exists(os.path.join(P, f"r02g_bench_n{n}.json"))]
     v1, e1 = sc8[0][1]["value"], sc8[0][1]["e2e"]["value"]
-    out += ["## Strong scaling on one 8-GPU box (`r02d_bench_n*.json`: torchrun, one rank per GPU, the 4541-pair sequence sharded, no collective)\n",
+    out += ["## Strong scaling on one 8-GPU box (`r02g_bench_n*.json`: torchrun, one rank per GPU, the 4541-pair sequence sharded, no collective)\n",
             "| GPUs | `value` pairs/s | x N=1 | `e2e` pairs/s | x N=1 | copies alone (in-run) | copies alone (`tools/copy_ceiling.py`) |", "|---|---|---|---|---|---|---|"]
     for n, dd in sc8:
         c2 = dd["e2e"].get("copy_ceiling") or {}
