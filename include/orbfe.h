@@ -115,6 +115,12 @@ int orbfe_download(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t
 int orbfe_download_async(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, uint8_t* desc, int capacity,
                          int* n_out, float* u_right, float* depth);
 int orbfe_sync(orbfe_extractor* ex);
+/* Page-locked host memory for frames (orbfe_upload) and results (orbfe_download_async), allocated PORTABLE (cudaHostAlloc with
+ * cudaHostAllocPortable): pinned for every device of the process, so one process can feed several GPUs from it without
+ * staging copies.  The reference reads its frames with cv::imread into pageable cv::Mat (examples/main_stereo.cpp:102-143);
+ * decoding into a buffer from here removes the driver's staging copy.  orbfe_pinned_free(NULL) is a no-op. */
+int orbfe_pinned_alloc(size_t bytes, void** out);
+int orbfe_pinned_free(void* p);
 /* CUDA-event timing on the handle's own stream: record event `slot` (0..63) now; elapsed ms
  * between two recorded slots (after orbfe_sync). */
 int orbfe_event_record(orbfe_extractor* ex, int slot);

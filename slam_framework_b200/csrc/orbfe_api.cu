@@ -942,6 +942,18 @@ int orbfe_download_async(orbfe_extractor* ex, int n_imgs, orbfe_keypoint* kps, u
   return ORBFE_OK;
 }
 
+int orbfe_pinned_alloc(size_t bytes, void** out) {
+  if (!out) return orbfe_fail(ORBFE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+  return ORBFE_OK;
+}
+
+int orbfe_pinned_free(void* p) {
+  if (p) CUDA_TRY(cudaFreeHost(p));
+  return ORBFE_OK;
+}
+
 int orbfe_sync(orbfe_extractor* ex) {
   if (!ex) return orbfe_fail(ORBFE_ERR_INVALID, "null extractor handle");
   CUDA_TRY(cudaSetDevice(ex->device));

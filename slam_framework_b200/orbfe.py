@@ -40,7 +40,7 @@ EXPORTS = [
     "orbfe_last_error", "orbfe_version", "orbfe_device_count", "orbfe_extractor_create", "orbfe_extractor_destroy",
     "orbfe_extractor_tables", "orbfe_extractor_max_keypoints", "orbfe_extract", "orbfe_extract_batch",
     "orbfe_pyramid_level", "orbfe_upload", "orbfe_upload_color", "orbfe_run", "orbfe_run_stereo", "orbfe_download", "orbfe_download_async",
-    "orbfe_sync",
+    "orbfe_sync", "orbfe_pinned_alloc", "orbfe_pinned_free",
     "orbfe_event_record", "orbfe_event_elapsed_ms", "orbfe_set_stage_timing", "orbfe_stage_summary",
     "orbfe_launch_count",
     "orbfe_debug_candidates", "orbfe_debug_level_keypoints", "orbfe_debug_blurred", "orbfe_stereo_match",
@@ -107,6 +107,8 @@ def load(path=None, _test_emulation=False):
     L.orbfe_frame_create.argtypes = [i, i, vp, vp, vp, f, f, f, f, i, vp, C.POINTER(vp)]
     L.orbfe_frame_destroy.argtypes = [vp]
     L.orbfe_frame_pool_trim.argtypes = []
+    L.orbfe_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.orbfe_pinned_free.argtypes = [vp]
     L.orbfe_frame_from_extractor.argtypes = [vp, i, i, f, f, f, f, C.POINTER(vp)]
     L.orbfe_frame_refresh_from_extractor.argtypes = [vp, vp, i, i, f, f, f, f]
     L.orbfe_frame_num_keypoints.argtypes = [vp]
@@ -143,6 +145,40 @@ def _check(L, rc, allow=()):
     if rc != 0 and rc not in allow:
         raise OrbfeError(f"orbfe error {rc}: {L.orbfe_last_error().decode(errors='replace')}")
     return rc
+
+
+class _PinnedBlock:
+    """owner of one orbfe_pinned_alloc block: freed when the last numpy view of it is gone"""
+
+    def __init__(self, L, nbytes):
+        self.L, self.p = L, vp()
+        _check(L, L.orbfe_pinned_alloc(nbytes, C.byref(self.p)))
+        self.buf = (C.c_uint8 * max(nbytes, 1)).from_address(self.p.value)
+
+    def __del__(self):
+        if getattr(self, "p", None) and self.p.value:
+            self.L.orbfe_pinned_free(self.p)
+            self.p = vp()
+
+
+def pinned_empty(shape, dtype=np.uint8, lib=None):
+    """numpy array in PORTABLE page-locked host memory (orbfe_pinned_alloc): pinned for every device of the process, so frames
+    and result buffers can be handed to the copy engines of several GPUs from one process"""
+    L = lib or load()
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    blk = _PinnedBlock(L, n)
+    a = np.frombuffer(blk.buf, dtype=np.uint8, count=n).view(dt).reshape(shape)
+    _pinned_owners[id(blk.buf)] = blk   # np.frombuffer keeps blk.buf alive; the block object is parked until release_pinned()
+    return a
+
+
+_pinned_owners = {}
+
+
+def release_pinned():
+    """frees every pinned_empty block (call when no array from pinned_empty is in use any more)"""
+    _pinned_owners.clear()
 
 
 def device_count(lib=None):

@@ -68,14 +68,13 @@ class SequenceRunner:
         self._lanes = {}   # device slot -> [[extractor, host buffers, pending pair range], ...]
 
     def _buffers(self, ex, n_img):
-        """make_buffers layout, in pinned host memory when torch is there (the D2H copies then need no staging)"""
+        """make_buffers layout in PORTABLE pinned host memory (orbfe_pinned_alloc): the D2H copies need no staging, on any device"""
         from . import orbfe
         try:
-            import torch
             cap = ex.max_keypoints()
-            mk = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
-            return dict(kps=mk((n_img, cap, 28), torch.uint8).view(orbfe.KP_DTYPE).reshape(n_img, cap), desc=mk((n_img, cap, 32), torch.uint8),
-                        n=mk((n_img,), torch.int32), cap=cap, ur=mk((n_img, cap), torch.float32), depth=mk((n_img, cap), torch.float32))
+            mk = lambda shape, dt: orbfe.pinned_empty(shape, dt, lib=self.L)
+            return dict(kps=mk((n_img, cap), orbfe.KP_DTYPE), desc=mk((n_img, cap, 32), np.uint8), n=mk((n_img,), np.int32), cap=cap,
+                        ur=mk((n_img, cap), np.float32), depth=mk((n_img, cap), np.float32))
         except Exception:
             return ex.make_buffers(n_img, stereo=True)
 

@@ -24,19 +24,18 @@ def main():
     n = a.gpus or L.orbfe_device_count()
     pairs = B.make_pairs(a.distinct, 0)
     import numpy as np
-    try:  # the sequence's frames in pinned memory, as a capture / decode thread would deliver them (bench.py's e2e leg does the same)
-        import torch
-        tiled = torch.empty((2 * a.distinct, B.H, B.W), dtype=torch.uint8, pin_memory=True).numpy()
-    except Exception:
-        tiled = np.empty((2 * a.distinct, B.H, B.W), np.uint8)
-    for p_, (l, r) in enumerate(pairs):
-        tiled[2 * p_], tiled[2 * p_ + 1] = l, r
+    # the sequence's frames in portable pinned memory, as a capture / decode thread would deliver them.  Pair i of the sequence is
+    # synthetic pair i % distinct; the block holds them twice over so that every batch [s, e) is ONE contiguous window of it
+    # (a wrap-around batch assembled with np.concatenate would be a 60 MB pageable copy per batch: that, not the GPUs, is what
+    # an earlier version of this tool measured on shards that do not start at a multiple of `distinct`)
+    assert a.batch <= a.distinct
+    tiled = orbfe.pinned_empty((4 * a.distinct, B.H, B.W), np.uint8, lib=L)
+    for p_ in range(2 * a.distinct):
+        tiled[2 * p_], tiled[2 * p_ + 1] = pairs[p_ % a.distinct]
 
-    def get_batch(s, e):   # pairs s .. e-1 of the sequence = pairs (i % distinct) of the tiled block; batches are aligned to it
+    def get_batch(s, e):
         s0 = s % a.distinct
-        if s0 + (e - s) <= a.distinct:
-            return tiled[2 * s0:2 * (s0 + e - s)]
-        return np.concatenate([tiled[2 * s0:], tiled[:2 * ((s0 + e - s) - a.distinct)]])
+        return tiled[2 * s0:2 * (s0 + e - s)]
     runner = shard.SequenceRunner(L, devices=list(range(n)), params=dict(nfeatures=B.NFEATURES, scaleFactor=B.SCALE, nlevels=B.NLEVELS,
                                                                           iniThFAST=B.INI_TH, minThFAST=B.MIN_TH),
                                   batch_pairs=a.batch, lanes=a.lanes)
