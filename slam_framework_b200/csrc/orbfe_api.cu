@@ -621,7 +621,8 @@ static int enqueue_extract(orbfe_extractor* ex, int n) {
                ex->d_blur, orbfe_blur_consts());  // one CTA (one warp) per 128-px column strip of a level
   if ((rc = stage_event(ex, 4))) return rc;
   {
-    int kpw = n >= 4 ? 8 : 4;  // keypoints per warp (see k_orient_describe; measured: 8 beats 32 even at 128 frames)
+    int kpw = n >= 4 ? 8 : 4;  // keypoints per warp (see k_orient_describe).  A/B at 128 frames, TMA form: 4 -> 0.203 ms, 6 -> 0.194, 8 -> 0.191,
+                               // 12 -> 0.190, 16 -> 0.205, 32 -> 0.215
     if (const char* e = getenv("ORBFE_TUNE_KPW")) { const int v = atoi(e); if (v >= 1 && v <= 32) kpw = v; }  // tuning only
     const int warps = (g.totalOut + kpw - 1) / kpw, wpc = ORBFE_DESC_THREADS / 32;
     ORBFE_LAUNCH(ex, k_orient_describe, dim3((warps + wpc - 1) / wpc, n), dim3(ORBFE_DESC_THREADS), 0, g, ex->d_pyr, ex->d_blur,
