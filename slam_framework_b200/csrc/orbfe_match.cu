@@ -69,6 +69,7 @@ struct orbfe_frame {
   char* h_outStage = nullptr;   // pinned landing zone of the results ([0,16): d_cursor, then d_out, then routine-specific extras)
   size_t outStageCap = 0;
   int coopBlocks = 0;           // co-resident CTAs of k_match_solve on this device (0 = not queried yet)
+  bool complete = false;        // stream and fixed-size blocks exist (frame_acquire succeeded): the handle may be recycled
   template <class T> T* dev(const T* hostPtr) const {
     return reinterpret_cast<T*>(d_stage + (reinterpret_cast<const char*>(hostPtr) - h_stage));
   }
@@ -427,7 +428,7 @@ int orbfe_frame_destroy(orbfe_frame* f) {
   if (!f) return ORBFE_OK;
   cudaSetDevice(f->device);
   if (f->stream) cudaStreamSynchronize(f->stream);
-  if (f->stream && f->d_cursor && f->h_res && !getenv("ORBFE_NO_HANDLE_POOL")) {
+  if (f->complete && !getenv("ORBFE_NO_HANDLE_POOL")) {
     std::lock_guard<std::mutex> lock(g_poolMu);
     if (g_pool.size() < kPoolMax) {
       f->n = 0;
@@ -469,6 +470,7 @@ static int frame_acquire(int device, orbfe_frame** out) {
       return orbfe_fail(ORBFE_ERR_CUDA, "frame setup failed: %s", cudaGetErrorString(e));
     }
   }
+  f->complete = true;
   *out = f;
   return ORBFE_OK;
 }

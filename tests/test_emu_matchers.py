@@ -204,3 +204,42 @@ def test_fuzz_slice_matchers_on_tie_heavy_keypoints():
     r = subprocess.run([sys.executable, os.path.join(here, "fuzz_matchers.py"), "emu", "6"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "failures 0" in r.stdout
+
+
+def test_frame_handles_are_recycled_and_reset(emu):
+    """orbfe_frame_destroy parks a handle, the next orbfe_frame_create takes it over: a recycled handle must behave like a new one
+    (other keypoint count, bounds, level table), orbfe_frame_pool_trim frees the idle ones, and ORBFE_NO_HANDLE_POOL-free
+    operation is what every other test already runs on."""
+    emu.orbfe_frame_pool_trim()
+    big = synth.frame(240, 800, seed=11)
+    small = synth.frame(120, 400, seed=12)
+    kb, db = oracle_extract(big, 1500)
+    ks, ds = O.Extractor(400, 1.5, 5, 20, 7).extract(small)
+    sb, ss = O.Extractor(1500).tables()["scale"], O.Extractor(400, 1.5, 5, 20, 7).tables()["scale"]
+    for rounds in range(2):   # big -> small -> big on recycled handles
+        assert P.check_search_by_projection_mappoints(emu, kb, db, sb, 800, 240, 1200, seed=3) > 50
+        assert P.check_search_by_projection_mappoints(emu, ks, ds, ss, 400, 120, 300, seed=4) >= 0
+        assert P.check_search_by_projection_lastframe(emu, ks, ds, ss, 400, 120, seed=5) >= 0
+    import gc
+    gc.collect()                                   # the Frame wrappers above are gone: their handles sit in the pool
+    assert emu.orbfe_frame_pool_trim() >= 1
+    assert emu.orbfe_frame_pool_trim() == 0
+    assert P.check_search_by_projection_mappoints(emu, kb, db, sb, 800, 240, 1200, seed=3) > 50   # fresh handles again
+
+
+def test_pinned_host_buffers(emu):
+    """orbfe_pinned_alloc through the numpy wrapper: frames uploaded from it and results downloaded into it are the same bytes"""
+    l, r = synth.stereo_pair(120, 400, seed=21)
+    frames = orbfe.pinned_empty((2, 120, 400), np.uint8, lib=emu)
+    frames[0], frames[1] = l, r
+    ex = orbfe.ORBextractor(400, lib=emu, max_images=2)
+    ex.upload([frames[0], frames[1]]); ex.run(2)
+    cap = ex.max_keypoints()
+    buf = dict(kps=orbfe.pinned_empty((2, cap), orbfe.KP_DTYPE, lib=emu), desc=orbfe.pinned_empty((2, cap, 32), np.uint8, lib=emu),
+               n=orbfe.pinned_empty((2,), np.int32, lib=emu), cap=cap, ur=None, depth=None)
+    ex.download_async(2, buf); ex.sync()
+    k0, d0 = oracle_extract(l, 400)
+    n0 = int(buf["n"][0])
+    assert n0 == len(k0) and np.array_equal(buf["desc"][0, :n0], d0) and np.array_equal(buf["kps"]["x"][0, :n0], k0["x"])
+    ex.close()
+    orbfe.release_pinned()
